@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""Headline benchmark: flow-chain log-prob forward+backward samples/s (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2]
+
+Workload (BASELINE.json configs[1], the one the metric is quoted on): 10-flow chain
+(planar, radial, affine) x 3 + planar over 2-D y with a trainable base distribution,
+P = 48 parameters per sample, batch 2^20 rows PER GPU (weak scaling), fused forward +
+reverse sweep with the mean-NLL cotangent -1/B.  One "step" = one pass of the hot path
+over one batch of synthetic fp32 input.
+
+  value     device-resident: inputs already in HBM, CUDA-event timed, max over ranks
+  e2e       the same pass through the HOST-buffer C-ABI call
+            (nfn_chain_forward_backward_host): pinned host t/y -> H2D -> kernel -> D2H of
+            logp/dt + the loss scalar, copies inside the timed region
+  roofline  algorithmic bytes 4*(2P+d+1) per row / measured kernel time vs the measured
+            HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline / --impl reference
+            the op-for-op float32 torch-CPU restatement of the reference's TF graph
+            (oracle/flow_oracle.py; TensorFlow itself cannot run in this image) with
+            autograd backward on all host cores, on a bounded sample of the same workload.
+
+N > 1 (torchrun): every rank runs its own 2^20-row shard; the step additionally performs
+the one exchange a data-parallel training step needs from this path, a packed all-reduce
+of [dt column sums (bias gradient of the emitting layer) | sum logp] over NCCL.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (flow_types, n_dims, trainable_base, rows per GPU, fwd+bwd?)
+    "cfg2": (["planar", "radial", "affine"] * 3 + ["planar"], 2, True, 1 << 20, True),
+    "cfg3": (["radial", "planar"] * 8, 4, True, 1 << 23, False),
+    "cfg4": (["radial"] * 5, 1, True, 1 << 20, True),
+    "cfg1": (["radial"] * 3, 1, True, 2048, True),
+}
+WORKLOAD_NAMES = {
+    "cfg2": "NFN 10 flows (planar,radial,affine)x3+planar, 2-D y, P=48, batch 2^20 per GPU, log-prob fwd+bwd",
+    "cfg3": "NFN 16 flows (radial,planar)x8, 4-D y, P=128, 2^23 (x,y) pairs per GPU, density-grid log-prob fwd",
+    "cfg4": "Bayesian NFN 5 radial flows, 1-D y, P=17, S*B = 2^20 rows per GPU, log-prob fwd+bwd",
+    "cfg1": "NFN 3 radial flows, 1-D y, P=11, batch 2048, log-prob fwd+bwd",
+}
+METRIC = "flow log-prob fwd+bwd samples/sec"
+UNIT = "samples/s"
+
+
+def param_size(flow_types, d, tb):
+    sz = {"planar": 2 * d + 1, "radial": d + 2, "affine": 2 * d}
+    return sum(sz[f] for f in flow_types) + (2 * d if tb else 0)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        except Exception:
+            pass
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def load_traffic(cfg):
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture, or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(cfg)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+            self.f.close()
+            sm, mx, reasons = [], [], set()
+            for line in open(self.path):
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                       "samples": len(sm)}
+        except Exception:
+            pass
+        finally:
+            try:
+                os.remove(self.path)
+            except Exception:
+                pass
+        return out
+
+
+# --------------------------------------------------------------------------- CPU baseline
+def cpu_pass_fn(cfg, rows, seed=22):
+    """Returns a callable doing one fwd(+bwd) pass of the TF-equivalent fp32 CPU restatement."""
+    import torch
+
+    from oracle import flow_oracle as fo
+
+    ft, d, tb, _, bwd = CONFIGS[cfg]
+    P = param_size(ft, d, tb)
+    g = torch.Generator().manual_seed(seed)
+    t = (torch.randn((rows, P), generator=g) * 0.5)
+    y = torch.randn((rows, d), generator=g)
+
+    def one_pass():
+        if bwd:
+            tt = t.detach().requires_grad_(True)
+            nll = -fo.chain_log_prob(tt, y, ft, d, tb).mean()
+            nll.backward()
+            return float(nll)
+        with torch.no_grad():
+            return float(fo.chain_log_prob(t, y, ft, d, tb).mean())
+
+    return one_pass
+
+
+def cpu_baseline(cfg, budget_s=12.0, rows=1 << 16):
+    import torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fn = cpu_pass_fn(cfg, rows)
+    fn()  # warm-up (allocator, thread pool)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        fn()
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or n >= 200:
+            break
+    return {
+        "value": rows * n / el, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": "%d passes over %d rows of the same workload (fp32 torch-CPU op-for-op restatement of the "
+                  "reference's TF graph + autograd; TensorFlow not installable here)" % (n, rows),
+    }
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (port; see cpu_baseline)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+
+    cfg = args.config
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rows = 1 << 16
+    fn = cpu_pass_fn(cfg, rows)
+    for _ in range(max(1, args.warmup)):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    el = time.perf_counter() - t0
+    value = rows * args.steps / el
+    ft, d, tb, _, bwd = CONFIGS[cfg]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAMES[cfg], "rows_per_step": rows,
+                   "note": "bounded sample of the workload per step; host cores only"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d rows per step; fp32 torch-CPU op-for-op restatement of the reference's TF "
+                                   "graph + autograd (TensorFlow/TFP not installable in this image)" % rows},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+
+    from normalizingflownetwork_b200 import _lib, parallel
+    from normalizingflownetwork_b200 import functional as F
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: normalizingflownetwork_b200 has no CPU fallback")
+    rank, world, local_rank = parallel.init_process_group()
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    cfg = args.config
+    ft, d, tb, B, bwd = CONFIGS[cfg]
+    if args.rows:
+        B = args.rows
+    P = param_size(ft, d, tb)
+    desc = _lib.make_desc(ft, d, tb)
+    specialized = bool(lib.nfn_chain_is_specialized(ctypes.byref(desc)))
+    K, W = args.steps, args.warmup
+
+    gen = torch.Generator(device=device).manual_seed(22 + rank)
+    t = torch.randn((B, P), generator=gen, device=device) * 0.5
+    y = torch.randn((B, d), generator=gen, device=device)
+    logp = torch.empty(B, device=device)
+    dt = torch.empty((B, P), device=device) if bwd else None
+    lsum = torch.zeros(1, dtype=torch.float64, device=device)
+    col = torch.zeros(P, device=device) if (bwd and world > 1) else None
+    packed = parallel.PackedAllReduce([(P,), (1,)], device) if (bwd and world > 1) else None
+    g_scale = -1.0 / (B * world)
+    stream = _lib.current_stream(device)
+
+    def step():
+        if bwd:
+            _lib.check(lib.nfn_chain_forward_backward(
+                ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), B, None, ctypes.c_float(g_scale), _lib.ptr(logp),
+                _lib.ptr(dt), None, _lib.ptr(lsum), _lib.ptr(col), B, stream))
+            if packed is not None:
+                packed.pack([col, lsum])
+                packed.reduce()
+        else:
+            _lib.check(lib.nfn_chain_forward(ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), B, _lib.ptr(logp), B,
+                                             stream))
+
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.nfn_launch_count_reset()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(K):
+        ev[i][0].record()
+        if bwd:
+            _lib.check(lib.nfn_chain_forward_backward(
+                ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), B, None, ctypes.c_float(g_scale), _lib.ptr(logp),
+                _lib.ptr(dt), None, _lib.ptr(lsum), _lib.ptr(col), B, stream))
+        else:
+            _lib.check(lib.nfn_chain_forward(ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), B, _lib.ptr(logp), B,
+                                             stream))
+        ev[i][1].record()
+        if packed is not None:
+            packed.pack([col, lsum])
+            packed.reduce()
+        ev[i][2].record()
+    t_end.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    torch.cuda.synchronize()
+    launches = int(lib.nfn_launch_count_reset())
+    total_ms = parallel.max_over_ranks(t_start.elapsed_time(t_end), device)
+    kern_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev)
+    kern_ms = parallel.max_over_ranks(kern_ms, device)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / K
+    value = B * world * K / (total_ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host buffers)
+    h_t = torch.empty((B, P), dtype=torch.float32).pin_memory()
+    h_y = torch.empty((B, d), dtype=torch.float32).pin_memory()
+    h_t.copy_(t)
+    h_y.copy_(y)
+    h_logp = torch.empty(B, dtype=torch.float32).pin_memory()
+    h_dt = torch.empty((B, P), dtype=torch.float32).pin_memory() if bwd else None
+    h_sum = ctypes.c_double(0.0)
+
+    def e2e_step():
+        if bwd:
+            _lib.check(lib.nfn_chain_forward_backward_host(
+                ctypes.byref(desc), _lib.ptr(h_t), _lib.ptr(h_y), B, None, ctypes.c_float(g_scale),
+                _lib.ptr(h_logp), _lib.ptr(h_dt), ctypes.byref(h_sum), None, B))
+        else:
+            _lib.check(lib.nfn_chain_forward_host(ctypes.byref(desc), _lib.ptr(h_t), _lib.ptr(h_y), B,
+                                                  _lib.ptr(h_logp), B))
+
+    e2e_steps = max(3, min(K, 10))
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = parallel.max_over_ranks(time.perf_counter() - t0, device)
+    parallel.barrier()
+    e2e_value = B * world * e2e_steps / e2e_s
+    h2d = 4 * B * (P + d)
+    d2h = 4 * B * (1 + (P if bwd else 0)) + 8
+    lib.nfn_host_release()
+    # the host path must reproduce the device path bit for bit
+    same = bool(torch.equal(h_logp, logp.cpu()))
+
+    if rank != 0:
+        return 0
+    bytes_per_row = 4 * ((2 * P if bwd else P) + d + 1)
+    peak, peak_src = load_peaks()
+    achieved = bytes_per_row * B / (kern_ms * 1e-3) / 1e9
+    cpu = cpu_baseline(cfg) if (world == 1 and not args.no_cpu_baseline) else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": WORKLOAD_NAMES[cfg], "rows_per_gpu": B, "param_width": P, "n_dims": d,
+            "fwd_bwd": bwd, "specialized_kernel": specialized, "math": "accurate" if os.environ.get(
+                "NFN_B200_MATH") == "accurate" else "fast",
+            "l2": "inputs+outputs per step (%d MB) exceed the 126 MB L2; no flush needed" % (
+                bytes_per_row * B // (1 << 20)),
+            "parallelism": "dp%d (rows sharded, no data-path collective%s)" % (
+                world, "; one packed all-reduce of [dt colsum | sum logp] per step" if packed is not None else ""),
+            "t_sigma": 0.5, "seed": 22,
+        },
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "nfn_chain_forward_backward_host" if bwd else "nfn_chain_forward_host",
+                "host_equals_device_bitwise": same},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": load_traffic(cfg), "peak_source": peak_src,
+                     "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": bytes_per_row * B},
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

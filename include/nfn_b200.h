@@ -1,0 +1,182 @@
+/*
+ * nfn_b200.h -- C ABI of libnfn_b200.so: the B200 (sm_100a) flow-chain / mixture-head
+ * log-likelihood hot path of siboehm/NormalizingFlowNetwork.
+ *
+ * The reference has no native layer at all (pure Python on TensorFlow/TFP), so there is
+ * no existing FFI to mirror; each entry point below names the reference interface
+ * (path:line under the reference tree) whose arithmetic it replaces.  Python binds these
+ * with ctypes (normalizingflownetwork_b200/_lib.py); see INTEGRATION.md for the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns NFN_OK (0) or a negative nfn_status; it never throws and
+ *     never terminates the process.  nfn_last_error() returns a thread-local message.
+ *   - "device" pointers are CUDA device pointers owned by the caller; fp32, row-major,
+ *     dense (row stride == row width).  t/dt base pointers must be 16-byte aligned
+ *     (NFN_ERR_ALIGN otherwise).  The library allocates no persistent device memory in
+ *     the device entry points, never synchronises the host, and is CUDA-graph
+ *     capturable.  `stream` is a cudaStream_t passed as void* (NULL = legacy default).
+ *   - the *_host entry points take HOST pointers (pinned memory recommended), run a
+ *     chunked H2D -> kernel -> D2H pipeline on library-owned streams/staging buffers
+ *     (per calling thread, released by nfn_host_release()), and return after the
+ *     results are in the host buffers.
+ *   - one process (or thread) per GPU; the current CUDA device of the calling thread is
+ *     used.  No global mutable state apart from the thread-local error string, the
+ *     read-only kernel registry and the per-thread host-pipeline workspace.
+ */
+#ifndef NFN_B200_H
+#define NFN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFN_B200_VERSION 100 /* 0.1.0 */
+
+#define NFN_MAX_FLOWS 64
+#define NFN_MAX_DIMS 8
+
+typedef enum nfn_status {
+  NFN_OK = 0,
+  NFN_ERR_NULL = -1,        /* required pointer is NULL */
+  NFN_ERR_DESC = -2,        /* malformed descriptor (n_dims, n_flows, flow type code) */
+  NFN_ERR_SHAPE = -3,       /* bad B / y_rows / width */
+  NFN_ERR_ALIGN = -4,       /* t or dt not 16-byte aligned */
+  NFN_ERR_CUDA = -5,        /* CUDA runtime error, see nfn_last_error() */
+  NFN_ERR_UNSUPPORTED = -6  /* valid request this build cannot serve */
+} nfn_status;
+
+/* Flow type codes: the keys of FLOWS in estimators/normalizing_flows/__init__.py:5 */
+enum { NFN_FLOW_PLANAR = 0, NFN_FLOW_RADIAL = 1, NFN_FLOW_AFFINE = 2 };
+
+/*
+ * Chain descriptor == the constructor arguments of InverseNormalizingFlowLayer
+ * (estimators/DistributionLayers.py:220-243).  flow_type[] is in `flow_types` order:
+ * data y passes through flow_type[0] first.  The parameter-row layout is the
+ * reference's (DistributionLayers.py:252, :267-278, :283-288):
+ *   [ mu(d) | sigma_raw(d) ]  (only if trainable_base)   then
+ *   [ theta(flow K-1) | theta(flow K-2) | ... | theta(flow 0) ]   (REVERSED order)
+ * with theta = planar [u(d), w_raw(d), b], radial [alpha_raw, beta_raw, gamma(d)],
+ * affine [shift(d), scale_raw(d)].
+ */
+typedef struct nfn_chain_desc {
+  int32_t n_dims;         /* d, 1..NFN_MAX_DIMS */
+  int32_t n_flows;        /* K, 0..NFN_MAX_FLOWS */
+  int32_t trainable_base; /* 0 | 1 */
+  uint8_t flow_type[NFN_MAX_FLOWS];
+} nfn_chain_desc;
+
+/* InverseNormalizingFlowLayer.get_total_param_size (DistributionLayers.py:257-265).
+ * Returns P > 0 or a negative nfn_status. */
+int nfn_chain_param_size(const nfn_chain_desc* desc);
+
+/* 1 if a compile-time specialised kernel exists for this chain, 0 if the generic
+ * runtime-chain kernel will serve it, negative nfn_status on a bad descriptor. */
+int nfn_chain_is_specialized(const nfn_chain_desc* desc);
+
+/*
+ * log_prob of TransformedDistribution(base, Invert(Chain(flows))) for B rows:
+ * replaces dist.log_prob(y) built by InverseNormalizingFlowLayer._get_distribution_fn
+ * (DistributionLayers.py:245-255) as called from BaseEstimator.py:57,75,86.
+ *   t      [B, P] device      y [y_rows, d] device, y_rows == B or 1 (broadcast)
+ *   logp   [B]    device out
+ */
+int nfn_chain_forward(const nfn_chain_desc* desc, const float* t, const float* y,
+                      int64_t y_rows, float* logp, int64_t B, void* stream);
+
+/*
+ * Fused forward + reverse sweep: replaces log_prob + tape.gradient of the Keras train
+ * step (BaseEstimator.py:55-59 loss closure under Sequential.fit).
+ *   g_logp     [B] device, nullable: upstream cotangent of logp per row
+ *   g_scale    scalar multiplied into the cotangent (cot_b = g_scale * (g_logp ? g_logp[b] : 1));
+ *              mean-NLL training passes g_logp = NULL, g_scale = -1/B_global
+ *   logp       [B] device out
+ *   dt         [B, P] device out:  cot_b * d logp_b / d t[b, :]
+ *   dy         [B, d] device out, nullable: cot_b * d logp_b / d y[b, :] (requires y_rows == B)
+ *   logp_sum   device double*, nullable: += sum_b logp_b  (one atomic per CTA)
+ *   dt_colsum  [P] device, nullable: += sum_b dt[b, :]  (gradient of the bias of the
+ *              Dense(P) layer that emits t, MaximumLikelihoodNNEstimator.py:43)
+ */
+int nfn_chain_forward_backward(const nfn_chain_desc* desc, const float* t, const float* y,
+                               int64_t y_rows, const float* g_logp, float g_scale, float* logp,
+                               float* dt, float* dy, double* logp_sum, float* dt_colsum,
+                               int64_t B, void* stream);
+
+/*
+ * One bijector on its own: Flow(t, n_dims).forward(z) and ._forward_log_det_jacobian(z)
+ * (PlanarFlow.py:68-80, RadialFlow.py:51-70, AffineFlow.py:7-9), the calls made by
+ * tests/test_flows.py:19-41.  t [B, size(flow)], z [z_rows, d] (z_rows == B or 1),
+ * z_out [B, d] nullable, fldj [B] nullable.  Always uses the accurate math path.
+ */
+int nfn_flow_forward(int flow_type, int n_dims, const float* t, const float* z, int64_t z_rows,
+                     float* z_out, float* fldj, int64_t B, void* stream);
+
+/*
+ * MDN head: tfd.Mixture.log_prob built by GaussianMixtureLayer._get_distribution_fn
+ * (DistributionLayers.py:196-212).  t [B, 2*K*d + K] =
+ * [ (mu_k(d), sigma_raw_k(d))_{k<K} | logits(K) ];  same cotangent / output conventions
+ * as nfn_chain_forward_backward.
+ */
+int nfn_mdn_forward(int n_centers, int n_dims, const float* t, const float* y, int64_t y_rows,
+                    float* logp, int64_t B, void* stream);
+int nfn_mdn_forward_backward(int n_centers, int n_dims, const float* t, const float* y,
+                             int64_t y_rows, const float* g_logp, float g_scale, float* logp,
+                             float* dt, float* dy, double* logp_sum, float* dt_colsum, int64_t B,
+                             void* stream);
+
+/*
+ * KMN head: tfd.MixtureSameFamily.log_prob built by
+ * GaussianKernelsLayer._get_distribution_fn (DistributionLayers.py:118-133).
+ *   t      [B, M] logits        locs [M, d] device (shared centres)
+ *   scales [M] device (shared isotropic bandwidths; may be negative, |.| is used)
+ *   dscales [M] device, nullable: += sum_b cot_b * d logp_b / d scales[m]
+ */
+int nfn_kmn_forward(int n_components, int n_dims, const float* t, const float* y, int64_t y_rows,
+                    const float* locs, const float* scales, float* logp, int64_t B, void* stream);
+int nfn_kmn_forward_backward(int n_components, int n_dims, const float* t, const float* y,
+                             int64_t y_rows, const float* locs, const float* scales,
+                             const float* g_logp, float g_scale, float* logp, float* dt, float* dy,
+                             float* dscales, double* logp_sum, int64_t B, void* stream);
+
+/*
+ * Posterior-predictive epilogue of BayesianNNEstimator.score
+ * (BayesianNNEstimator.py:65-76, evaluation/scorers.py:13-27) for S draws folded into
+ * the batch: logp_sb [S, B] -> out[b] = logsumexp_s(logp_sb[s, b]) - log(S).
+ */
+int nfn_logmeanexp_draws(const float* logp_sb, int64_t S, int64_t B, float* out, void* stream);
+
+/*
+ * HOST-buffer entry points (the end-to-end call): same semantics as the device entry
+ * points with every pointer a HOST pointer.  logp_sum is a host double* (overwritten,
+ * nullable); dt_colsum a host float[P] (overwritten, nullable).  Copies are chunked and
+ * overlapped with compute on library-owned streams.  Blocking.
+ */
+int nfn_chain_forward_host(const nfn_chain_desc* desc, const float* t, const float* y,
+                           int64_t y_rows, float* logp, int64_t B);
+int nfn_chain_forward_backward_host(const nfn_chain_desc* desc, const float* t, const float* y,
+                                    int64_t y_rows, const float* g_logp, float g_scale,
+                                    float* logp, float* dt, double* logp_sum, float* dt_colsum,
+                                    int64_t B);
+int nfn_mdn_forward_backward_host(int n_centers, int n_dims, const float* t, const float* y,
+                                  int64_t y_rows, const float* g_logp, float g_scale, float* logp,
+                                  float* dt, double* logp_sum, int64_t B);
+/* Free this thread's host-pipeline workspace (streams, events, staging buffers). */
+int nfn_host_release(void);
+
+/* Number of kernel launches issued by this thread since the last call (then reset). */
+int64_t nfn_launch_count_reset(void);
+
+/* Math path of the chain / mixture kernels: 0 = fast (default; one MUFU per transcendental,
+ * cancellation-free forms), 1 = accurate (CUDA libm, IEEE division).  Process-wide; the
+ * environment variable NFN_B200_MATH=accurate selects 1 at first use. */
+int nfn_set_math_mode(int accurate);
+
+const char* nfn_last_error(void);
+int nfn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFN_B200_H */

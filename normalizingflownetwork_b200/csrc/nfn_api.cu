@@ -1,0 +1,519 @@
+// nfn_api.cu -- the C ABI of libnfn_b200.so (include/nfn_b200.h): descriptor validation,
+// kernel registry and dispatch, and the chunked host-buffer pipeline.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "nfn_common.h"
+
+namespace nfn {
+
+cudaError_t launch_chain_generic(const nfn_chain_desc* desc, const ChainArgs& a, bool bwd, int mode,
+                                 cudaStream_t st);
+cudaError_t launch_flow_single(int type, int d, const float* t, const float* z, int zb, float* zo,
+                               float* f, long long B, cudaStream_t st);
+
+// ------------------------------------------------------------------ errors, counters
+static thread_local char g_err[512] = "";
+static thread_local long long g_launches = 0;
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_error(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return NFN_OK;
+  return set_error(NFN_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+void count_launch() { ++g_launches; }
+
+const DeviceInfo& device_info() {
+  static thread_local DeviceInfo info;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+  if (dev != info.device) {
+    info.device = dev;
+    info.sm_count = 148;
+    info.smem_optin = 227 * 1024;
+    if (dev >= 0) {
+      cudaDeviceGetAttribute(&info.sm_count, cudaDevAttrMultiProcessorCount, dev);
+      cudaDeviceGetAttribute(&info.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+  }
+  return info;
+}
+
+static int g_math_mode = -1;
+int math_mode() {
+  if (g_math_mode < 0) {
+    const char* e = getenv("NFN_B200_MATH");
+    g_math_mode = (e && (!strcmp(e, "accurate") || !strcmp(e, "1"))) ? 1 : 0;
+  }
+  return g_math_mode;
+}
+
+// ------------------------------------------------------------------ registry
+static std::unordered_map<std::string, ChainKernels>& registry() {
+  static std::unordered_map<std::string, ChainKernels> r;
+  return r;
+}
+
+std::string chain_key(int d, bool base, int k, const uint8_t* types) {
+  std::string s = "d" + std::to_string(d) + (base ? "b1:" : "b0:");
+  for (int i = 0; i < k; ++i) s.push_back("pra"[types[i]]);
+  return s;
+}
+
+void register_chain(const std::string& key, const ChainKernels& k) { registry()[key] = k; }
+
+const ChainKernels* find_chain(const std::string& key) {
+  if (getenv("NFN_B200_FORCE_GENERIC")) return nullptr;
+  auto it = registry().find(key);
+  return it == registry().end() ? nullptr : &it->second;
+}
+
+// ------------------------------------------------------------------ validation
+static int check_desc(const nfn_chain_desc* d) {
+  if (!d) return set_error(NFN_ERR_NULL, "chain descriptor is NULL");
+  if (d->n_dims < 1 || d->n_dims > NFN_MAX_DIMS)
+    return set_error(NFN_ERR_DESC, "n_dims=%d outside 1..%d", d->n_dims, NFN_MAX_DIMS);
+  if (d->n_flows < 0 || d->n_flows > NFN_MAX_FLOWS)
+    return set_error(NFN_ERR_DESC, "n_flows=%d outside 0..%d", d->n_flows, NFN_MAX_FLOWS);
+  if (d->trainable_base != 0 && d->trainable_base != 1)
+    return set_error(NFN_ERR_DESC, "trainable_base=%d is not 0/1", d->trainable_base);
+  for (int k = 0; k < d->n_flows; ++k)
+    if (d->flow_type[k] > NFN_FLOW_AFFINE)
+      return set_error(NFN_ERR_DESC, "flow_type[%d]=%d is not planar(0)/radial(1)/affine(2)", k,
+                       (int)d->flow_type[k]);
+  return NFN_OK;
+}
+
+static int param_size(const nfn_chain_desc* d) {
+  int p = d->trainable_base ? 2 * d->n_dims : 0;
+  for (int k = 0; k < d->n_flows; ++k) p += flow_param_size(d->flow_type[k], d->n_dims);
+  return p;
+}
+
+static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+static size_t event_align(int d) { return d == 4 ? 16 : (d == 2 ? 8 : 4); }
+
+static int check_rows(int64_t B, int64_t y_rows) {
+  if (B < 0) return set_error(NFN_ERR_SHAPE, "B=%lld is negative", (long long)B);
+  if (y_rows != B && y_rows != 1)
+    return set_error(NFN_ERR_SHAPE, "y_rows=%lld must equal B=%lld or 1", (long long)y_rows,
+                     (long long)B);
+  return NFN_OK;
+}
+
+static int chain_dispatch(const nfn_chain_desc* desc, const ChainArgs& a, bool bwd, cudaStream_t st) {
+  const std::string key = chain_key(desc->n_dims, desc->trainable_base != 0, desc->n_flows, desc->flow_type);
+  const int mode = math_mode();
+  const ChainKernels* k = find_chain(key);
+  cudaError_t e;
+  if (k && k->fn[mode][bwd ? 1 : 0]) {
+    e = k->fn[mode][bwd ? 1 : 0](a, st);
+  } else {
+    ChainArgs g = a;
+    g.dt_colsum = nullptr;  // the generic kernel leaves the column sums to a second pass
+    e = launch_chain_generic(desc, g, bwd, mode, st);
+    if (e == cudaSuccess && bwd && a.dt_colsum) {
+      int rc = launch_colsum(a.dt, a.B, param_size(desc), a.dt_colsum, st);
+      if (rc != NFN_OK) return rc;
+    }
+  }
+  return cuda_error(e, key.c_str());
+}
+
+}  // namespace nfn
+
+using namespace nfn;
+
+// =================================================================== C ABI
+extern "C" {
+
+int nfn_version(void) { return NFN_B200_VERSION; }
+
+const char* nfn_last_error(void) { return g_err; }
+
+int64_t nfn_launch_count_reset(void) {
+  const long long n = g_launches;
+  g_launches = 0;
+  return n;
+}
+
+int nfn_set_math_mode(int accurate) {
+  g_math_mode = accurate ? 1 : 0;
+  return NFN_OK;
+}
+
+int nfn_chain_param_size(const nfn_chain_desc* desc) {
+  int rc = check_desc(desc);
+  if (rc != NFN_OK) return rc;
+  return param_size(desc);
+}
+
+int nfn_chain_is_specialized(const nfn_chain_desc* desc) {
+  int rc = check_desc(desc);
+  if (rc != NFN_OK) return rc;
+  return find_chain(chain_key(desc->n_dims, desc->trainable_base != 0, desc->n_flows, desc->flow_type)) ? 1 : 0;
+}
+
+int nfn_chain_forward(const nfn_chain_desc* desc, const float* t, const float* y, int64_t y_rows,
+                      float* logp, int64_t B, void* stream) {
+  int rc = check_desc(desc);
+  if (rc != NFN_OK) return rc;
+  if ((rc = check_rows(B, y_rows)) != NFN_OK) return rc;
+  if (B == 0) return NFN_OK;
+  const int P = param_size(desc);
+  if (!y || !logp || (P > 0 && !t)) return set_error(NFN_ERR_NULL, "t, y and logp must be non-NULL");
+  if (!aligned(t, 16)) return set_error(NFN_ERR_ALIGN, "t must be 16-byte aligned");
+  if (!aligned(y, event_align(desc->n_dims)))
+    return set_error(NFN_ERR_ALIGN, "y must be %zu-byte aligned", event_align(desc->n_dims));
+  ChainArgs a{};
+  a.t = t; a.y = y; a.logp = logp; a.B = B; a.g_scale = 1.0f; a.y_broadcast = (y_rows == 1 && B != 1);
+  return chain_dispatch(desc, a, false, (cudaStream_t)stream);
+}
+
+int nfn_chain_forward_backward(const nfn_chain_desc* desc, const float* t, const float* y,
+                               int64_t y_rows, const float* g_logp, float g_scale, float* logp,
+                               float* dt, float* dy, double* logp_sum, float* dt_colsum, int64_t B,
+                               void* stream) {
+  int rc = check_desc(desc);
+  if (rc != NFN_OK) return rc;
+  if ((rc = check_rows(B, y_rows)) != NFN_OK) return rc;
+  if (B == 0) return NFN_OK;
+  const int P = param_size(desc);
+  if (!y || !logp || (P > 0 && (!t || !dt)))
+    return set_error(NFN_ERR_NULL, "t, y, logp and dt must be non-NULL");
+  if (!aligned(t, 16) || !aligned(dt, 16))
+    return set_error(NFN_ERR_ALIGN, "t and dt must be 16-byte aligned");
+  if (!aligned(y, event_align(desc->n_dims)))
+    return set_error(NFN_ERR_ALIGN, "y must be %zu-byte aligned", event_align(desc->n_dims));
+  if (dy && y_rows != B) return set_error(NFN_ERR_SHAPE, "dy requires y_rows == B");
+  ChainArgs a{};
+  a.t = t; a.y = y; a.g_logp = g_logp; a.logp = logp; a.dt = dt; a.dy = dy;
+  a.logp_sum = logp_sum; a.dt_colsum = dt_colsum; a.B = B; a.g_scale = g_scale;
+  a.y_broadcast = (y_rows == 1 && B != 1);
+  return chain_dispatch(desc, a, true, (cudaStream_t)stream);
+}
+
+int nfn_flow_forward(int flow_type, int n_dims, const float* t, const float* z, int64_t z_rows,
+                     float* z_out, float* fldj, int64_t B, void* stream) {
+  if (flow_type < 0 || flow_type > NFN_FLOW_AFFINE)
+    return set_error(NFN_ERR_DESC, "flow_type=%d is not planar(0)/radial(1)/affine(2)", flow_type);
+  if (n_dims < 1 || n_dims > NFN_MAX_DIMS)
+    return set_error(NFN_ERR_DESC, "n_dims=%d outside 1..%d", n_dims, NFN_MAX_DIMS);
+  int rc = check_rows(B, z_rows);
+  if (rc != NFN_OK) return rc;
+  if (B == 0) return NFN_OK;
+  if (!t || !z) return set_error(NFN_ERR_NULL, "t and z must be non-NULL");
+  if (!aligned(z, event_align(n_dims)))
+    return set_error(NFN_ERR_ALIGN, "z must be %zu-byte aligned", event_align(n_dims));
+  return cuda_error(launch_flow_single(flow_type, n_dims, t, z, (z_rows == 1 && B != 1), z_out, fldj, B,
+                                       (cudaStream_t)stream),
+                    "flow_single_kernel");
+}
+
+// ------------------------------------------------------------------ mixture heads
+static int mix_common(int K, int d, const float* t, const float* y, int64_t y_rows, float* logp,
+                      int64_t B) {
+  if (K < 1 || K > 4096) return set_error(NFN_ERR_DESC, "n_centers=%d outside 1..4096", K);
+  if (d < 1 || d > NFN_MAX_DIMS) return set_error(NFN_ERR_DESC, "n_dims=%d outside 1..%d", d, NFN_MAX_DIMS);
+  int rc = check_rows(B, y_rows);
+  if (rc != NFN_OK) return rc;
+  if (B == 0) return 1;  // nothing to do
+  if (!t || !y || !logp) return set_error(NFN_ERR_NULL, "t, y and logp must be non-NULL");
+  if (!aligned(t, 16)) return set_error(NFN_ERR_ALIGN, "t must be 16-byte aligned");
+  if (!aligned(y, event_align(d))) return set_error(NFN_ERR_ALIGN, "y must be %zu-byte aligned", event_align(d));
+  return NFN_OK;
+}
+
+int nfn_mdn_forward(int n_centers, int n_dims, const float* t, const float* y, int64_t y_rows,
+                    float* logp, int64_t B, void* stream) {
+  int rc = mix_common(n_centers, n_dims, t, y, y_rows, logp, B);
+  if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
+  MixArgs a{};
+  a.t = t; a.y = y; a.logp = logp; a.B = B; a.g_scale = 1.0f; a.K = n_centers;
+  a.y_broadcast = (y_rows == 1 && B != 1);
+  return launch_mdn(n_dims, false, a, (cudaStream_t)stream);
+}
+
+int nfn_mdn_forward_backward(int n_centers, int n_dims, const float* t, const float* y,
+                             int64_t y_rows, const float* g_logp, float g_scale, float* logp,
+                             float* dt, float* dy, double* logp_sum, float* dt_colsum, int64_t B,
+                             void* stream) {
+  int rc = mix_common(n_centers, n_dims, t, y, y_rows, logp, B);
+  if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
+  if (!dt) return set_error(NFN_ERR_NULL, "dt must be non-NULL");
+  if (!aligned(dt, 16)) return set_error(NFN_ERR_ALIGN, "dt must be 16-byte aligned");
+  if (dy && y_rows != B) return set_error(NFN_ERR_SHAPE, "dy requires y_rows == B");
+  MixArgs a{};
+  a.t = t; a.y = y; a.g_logp = g_logp; a.logp = logp; a.dt = dt; a.dy = dy; a.logp_sum = logp_sum;
+  a.dt_colsum = dt_colsum; a.B = B; a.g_scale = g_scale; a.K = n_centers;
+  a.y_broadcast = (y_rows == 1 && B != 1);
+  return launch_mdn(n_dims, true, a, (cudaStream_t)stream);
+}
+
+int nfn_kmn_forward(int n_components, int n_dims, const float* t, const float* y, int64_t y_rows,
+                    const float* locs, const float* scales, float* logp, int64_t B, void* stream) {
+  int rc = mix_common(n_components, n_dims, t, y, y_rows, logp, B);
+  if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
+  if (!locs || !scales) return set_error(NFN_ERR_NULL, "locs and scales must be non-NULL");
+  MixArgs a{};
+  a.t = t; a.y = y; a.locs = locs; a.scales = scales; a.logp = logp; a.B = B; a.g_scale = 1.0f;
+  a.K = n_components; a.y_broadcast = (y_rows == 1 && B != 1);
+  return launch_kmn(n_dims, false, a, (cudaStream_t)stream);
+}
+
+int nfn_kmn_forward_backward(int n_components, int n_dims, const float* t, const float* y,
+                             int64_t y_rows, const float* locs, const float* scales,
+                             const float* g_logp, float g_scale, float* logp, float* dt, float* dy,
+                             float* dscales, double* logp_sum, int64_t B, void* stream) {
+  int rc = mix_common(n_components, n_dims, t, y, y_rows, logp, B);
+  if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
+  if (!locs || !scales || !dt) return set_error(NFN_ERR_NULL, "locs, scales and dt must be non-NULL");
+  if (!aligned(dt, 16)) return set_error(NFN_ERR_ALIGN, "dt must be 16-byte aligned");
+  if (dy && y_rows != B) return set_error(NFN_ERR_SHAPE, "dy requires y_rows == B");
+  MixArgs a{};
+  a.t = t; a.y = y; a.g_logp = g_logp; a.locs = locs; a.scales = scales; a.logp = logp; a.dt = dt;
+  a.dy = dy; a.dscales = dscales; a.logp_sum = logp_sum; a.B = B; a.g_scale = g_scale;
+  a.K = n_components; a.y_broadcast = (y_rows == 1 && B != 1);
+  return launch_kmn(n_dims, true, a, (cudaStream_t)stream);
+}
+
+int nfn_logmeanexp_draws(const float* logp_sb, int64_t S, int64_t B, float* out, void* stream) {
+  if (S < 1 || B < 0) return set_error(NFN_ERR_SHAPE, "S=%lld, B=%lld", (long long)S, (long long)B);
+  if (B == 0) return NFN_OK;
+  if (!logp_sb || !out) return set_error(NFN_ERR_NULL, "logp_sb and out must be non-NULL");
+  return launch_logmeanexp(logp_sb, S, B, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// =================================================================== host-buffer pipeline
+namespace nfn {
+
+// Per-thread workspace: NS slots, each with its own stream and device staging buffers.
+// Chunk i runs H2D -> kernel -> D2H on stream i % NS; chunks on different streams overlap
+// (both copy engines + SMs busy), a slot is reused only by later chunks on the same stream.
+struct HostPipe {
+  static constexpr int NS = 3;
+  int device = -1;
+  cudaStream_t stream[NS] = {};
+  void* buf[NS] = {};
+  size_t cap[NS] = {};
+  double* acc[NS] = {};    // device: logp_sum per slot
+  float* colacc[NS] = {};  // device: dt_colsum per slot
+  size_t colcap = 0;
+  bool live = false;
+
+  int ensure(size_t bytes, int P) {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_error(e, "cudaGetDevice");
+    if (live && dev != device) release();
+    if (!live) {
+      for (int i = 0; i < NS; ++i) {
+        if ((e = cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking)) != cudaSuccess)
+          return cuda_error(e, "cudaStreamCreate");
+        if ((e = cudaMalloc((void**)&acc[i], sizeof(double))) != cudaSuccess)
+          return cuda_error(e, "cudaMalloc(acc)");
+      }
+      device = dev;
+      live = true;
+    }
+    for (int i = 0; i < NS; ++i) {
+      if (cap[i] < bytes) {
+        if (buf[i]) cudaFree(buf[i]);
+        buf[i] = nullptr;
+        cap[i] = 0;
+        if ((e = cudaMalloc(&buf[i], bytes)) != cudaSuccess) return cuda_error(e, "cudaMalloc(staging)");
+        cap[i] = bytes;
+      }
+    }
+    if (colcap < (size_t)P) {
+      for (int i = 0; i < NS; ++i) {
+        if (colacc[i]) cudaFree(colacc[i]);
+        colacc[i] = nullptr;
+        if ((e = cudaMalloc((void**)&colacc[i], (size_t)P * sizeof(float))) != cudaSuccess)
+          return cuda_error(e, "cudaMalloc(colacc)");
+      }
+      colcap = (size_t)P;
+    }
+    return NFN_OK;
+  }
+
+  void release() {
+    if (!live) return;
+    for (int i = 0; i < NS; ++i) {
+      if (stream[i]) { cudaStreamSynchronize(stream[i]); cudaStreamDestroy(stream[i]); }
+      if (buf[i]) cudaFree(buf[i]);
+      if (acc[i]) cudaFree(acc[i]);
+      if (colacc[i]) cudaFree(colacc[i]);
+      stream[i] = nullptr; buf[i] = nullptr; acc[i] = nullptr; colacc[i] = nullptr; cap[i] = 0;
+    }
+    colcap = 0;
+    live = false;
+  }
+};
+
+static thread_local HostPipe g_pipe;
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Generic chunked driver.  `run` enqueues the device work for one chunk.
+struct ChunkPtrs {
+  float* t; float* y; float* g; float* logp; float* dt;
+};
+
+template <class Run>
+static int host_pipeline(int P, int d, bool bwd, const float* t, const float* y, int64_t y_rows,
+                         const float* g_logp, float* logp, float* dt, double* logp_sum,
+                         float* dt_colsum, int64_t B, Run run) {
+  if (B == 0) {
+    if (logp_sum) *logp_sum = 0.0;
+    if (dt_colsum) memset(dt_colsum, 0, (size_t)P * sizeof(float));
+    return NFN_OK;
+  }
+  // ~16 MiB of parameters per chunk, at least 3 chunks in flight when B allows it
+  int64_t rows = (int64_t)((16u << 20) / ((size_t)(P > 0 ? P : 1) * sizeof(float)));
+  rows = rows / 1024 * 1024;
+  if (rows < 1024) rows = 1024;
+  if (rows > B) rows = B;
+  const size_t t_b = align_up((size_t)rows * P * sizeof(float), 256);
+  const size_t y_b = align_up((size_t)rows * d * sizeof(float), 256);
+  const size_t r_b = align_up((size_t)rows * sizeof(float), 256);
+  const size_t total = t_b + y_b + r_b /*g*/ + r_b /*logp*/ + (bwd ? t_b : 0);
+  HostPipe& hp = g_pipe;
+  int rc = hp.ensure(total, P > 0 ? P : 1);
+  if (rc != NFN_OK) return rc;
+  cudaError_t e;
+  for (int s = 0; s < HostPipe::NS; ++s) {
+    if ((e = cudaMemsetAsync(hp.acc[s], 0, sizeof(double), hp.stream[s])) != cudaSuccess)
+      return cuda_error(e, "cudaMemsetAsync");
+    if (bwd && dt_colsum && P > 0 &&
+        (e = cudaMemsetAsync(hp.colacc[s], 0, (size_t)P * sizeof(float), hp.stream[s])) != cudaSuccess)
+      return cuda_error(e, "cudaMemsetAsync");
+  }
+  int64_t done = 0;
+  for (int64_t c = 0; done < B; ++c, done += rows) {
+    const int s = (int)(c % HostPipe::NS);
+    const int64_t n = (B - done < rows) ? (B - done) : rows;
+    cudaStream_t st = hp.stream[s];
+    char* base = (char*)hp.buf[s];
+    ChunkPtrs p;
+    p.t = (float*)base;
+    p.y = (float*)(base + t_b);
+    p.g = (float*)(base + t_b + y_b);
+    p.logp = (float*)(base + t_b + y_b + r_b);
+    p.dt = bwd ? (float*)(base + t_b + y_b + 2 * r_b) : nullptr;
+    if (P > 0 && (e = cudaMemcpyAsync(p.t, t + done * P, (size_t)n * P * sizeof(float),
+                                      cudaMemcpyHostToDevice, st)) != cudaSuccess)
+      return cuda_error(e, "H2D t");
+    const bool ybc = (y_rows == 1 && B != 1);
+    if ((e = cudaMemcpyAsync(p.y, ybc ? y : y + done * d, (size_t)(ybc ? 1 : n) * d * sizeof(float),
+                             cudaMemcpyHostToDevice, st)) != cudaSuccess)
+      return cuda_error(e, "H2D y");
+    if (bwd && g_logp &&
+        (e = cudaMemcpyAsync(p.g, g_logp + done, (size_t)n * sizeof(float), cudaMemcpyHostToDevice,
+                             st)) != cudaSuccess)
+      return cuda_error(e, "H2D g_logp");
+    rc = run(p, n, ybc ? 1 : n, (bwd && g_logp) ? p.g : nullptr, hp.acc[s],
+             (bwd && dt_colsum) ? hp.colacc[s] : nullptr, st);
+    if (rc != NFN_OK) return rc;
+    if ((e = cudaMemcpyAsync(logp + done, p.logp, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost,
+                             st)) != cudaSuccess)
+      return cuda_error(e, "D2H logp");
+    if (bwd && P > 0 &&
+        (e = cudaMemcpyAsync(dt + done * P, p.dt, (size_t)n * P * sizeof(float), cudaMemcpyDeviceToHost,
+                             st)) != cudaSuccess)
+      return cuda_error(e, "D2H dt");
+  }
+  double sum = 0.0;
+  std::vector<float> col((size_t)(P > 0 ? P : 1));
+  if (dt_colsum) memset(dt_colsum, 0, (size_t)P * sizeof(float));
+  for (int s = 0; s < HostPipe::NS; ++s) {
+    if ((e = cudaStreamSynchronize(hp.stream[s])) != cudaSuccess) return cuda_error(e, "stream sync");
+    double part = 0.0;
+    if ((e = cudaMemcpy(&part, hp.acc[s], sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess)
+      return cuda_error(e, "D2H logp_sum");
+    sum += part;
+    if (bwd && dt_colsum && P > 0) {
+      if ((e = cudaMemcpy(col.data(), hp.colacc[s], (size_t)P * sizeof(float), cudaMemcpyDeviceToHost)) !=
+          cudaSuccess)
+        return cuda_error(e, "D2H dt_colsum");
+      for (int j = 0; j < P; ++j) dt_colsum[j] += col[j];
+    }
+  }
+  if (logp_sum) *logp_sum = sum;
+  return NFN_OK;
+}
+
+}  // namespace nfn
+
+extern "C" {
+
+int nfn_chain_forward_host(const nfn_chain_desc* desc, const float* t, const float* y, int64_t y_rows,
+                           float* logp, int64_t B) {
+  int rc = check_desc(desc);
+  if (rc != NFN_OK) return rc;
+  if ((rc = check_rows(B, y_rows)) != NFN_OK) return rc;
+  const int P = param_size(desc);
+  if (B > 0 && (!y || !logp || (P > 0 && !t))) return set_error(NFN_ERR_NULL, "t, y and logp must be non-NULL");
+  return host_pipeline(P, desc->n_dims, false, t, y, y_rows, nullptr, logp, nullptr, nullptr, nullptr, B,
+                       [&](const ChunkPtrs& p, int64_t n, int64_t yr, const float*, double*, float*,
+                           cudaStream_t st) {
+                         return nfn_chain_forward(desc, p.t, p.y, yr, p.logp, n, st);
+                       });
+}
+
+int nfn_chain_forward_backward_host(const nfn_chain_desc* desc, const float* t, const float* y,
+                                    int64_t y_rows, const float* g_logp, float g_scale, float* logp,
+                                    float* dt, double* logp_sum, float* dt_colsum, int64_t B) {
+  int rc = check_desc(desc);
+  if (rc != NFN_OK) return rc;
+  if ((rc = check_rows(B, y_rows)) != NFN_OK) return rc;
+  const int P = param_size(desc);
+  if (B > 0 && (!y || !logp || (P > 0 && (!t || !dt))))
+    return set_error(NFN_ERR_NULL, "t, y, logp and dt must be non-NULL");
+  return host_pipeline(P, desc->n_dims, true, t, y, y_rows, g_logp, logp, dt, logp_sum, dt_colsum, B,
+                       [&](const ChunkPtrs& p, int64_t n, int64_t yr, const float* g, double* acc,
+                           float* col, cudaStream_t st) {
+                         return nfn_chain_forward_backward(desc, p.t, p.y, yr, g, g_scale, p.logp, p.dt,
+                                                           nullptr, acc, col, n, st);
+                       });
+}
+
+int nfn_mdn_forward_backward_host(int n_centers, int n_dims, const float* t, const float* y,
+                                  int64_t y_rows, const float* g_logp, float g_scale, float* logp,
+                                  float* dt, double* logp_sum, int64_t B) {
+  if (n_centers < 1 || n_centers > 4096) return set_error(NFN_ERR_DESC, "n_centers=%d outside 1..4096", n_centers);
+  if (n_dims < 1 || n_dims > NFN_MAX_DIMS) return set_error(NFN_ERR_DESC, "n_dims=%d outside 1..%d", n_dims, NFN_MAX_DIMS);
+  int rc = check_rows(B, y_rows);
+  if (rc != NFN_OK) return rc;
+  if (B > 0 && (!t || !y || !logp || !dt)) return set_error(NFN_ERR_NULL, "t, y, logp and dt must be non-NULL");
+  const int P = 2 * n_centers * n_dims + n_centers;
+  return host_pipeline(P, n_dims, true, t, y, y_rows, g_logp, logp, dt, logp_sum, nullptr, B,
+                       [&](const ChunkPtrs& p, int64_t n, int64_t yr, const float* g, double* acc, float*,
+                           cudaStream_t st) {
+                         return nfn_mdn_forward_backward(n_centers, n_dims, p.t, p.y, yr, g, g_scale, p.logp,
+                                                         p.dt, nullptr, acc, nullptr, n, st);
+                       });
+}
+
+int nfn_host_release(void) {
+  g_pipe.release();
+  return NFN_OK;
+}
+
+}  // extern "C"

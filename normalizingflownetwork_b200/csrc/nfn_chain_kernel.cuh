@@ -1,0 +1,358 @@
+// nfn_chain_kernel.cuh -- compile-time specialised fused flow-chain kernels (sm_100a).
+//
+// One thread = one (x, y) pair.  A CTA of T threads owns tiles of T consecutive rows of
+// the parameter tensor t[B, P] == one contiguous T*P*4-byte span of HBM:
+//
+//   global t  --cp.async.cg 16 B, fully coalesced-->  smem tile [T][S]   (double buffered)
+//   each thread reads its own row with 128/64/32-bit LDS at compile-time offsets,
+//   runs all K flows in registers (z history kept for the reverse sweep), writes
+//   d logp / d theta back IN PLACE over the parameters it just consumed,
+//   smem tile  --LDS.128 + STG.128 (streaming), fully coalesced-->  global dt
+//
+// Row stride S (floats) is chosen so the per-thread vector reads are bank-conflict free:
+// with V = min(4, largest power of two dividing P) the reads are V-wide and need S/V odd;
+// S = P except when V == 4 and P/4 is even, where each row is padded by one 16-byte chunk
+// (cp.async places chunks individually, so padding costs nothing).
+//
+// Replaces, per row: TransformedDistribution.log_prob over Invert(Chain(flows))
+// (reference estimators/DistributionLayers.py:245-294) and its tape gradient
+// (estimators/BaseEstimator.py:55-59 under Keras fit).
+#pragma once
+#include <cstdint>
+
+#include "nfn_flows.cuh"
+
+namespace nfn {
+
+// ---------------------------------------------------------------- compile-time chain
+template <int D_, bool BASE_, int... F>
+struct ChainSpec {
+  static constexpr int D = D_;
+  static constexpr bool BASE = BASE_;
+  static constexpr int K = sizeof...(F);
+  static constexpr int KA = K > 0 ? K : 1;
+  static constexpr int base_size = BASE ? 2 * D : 0;
+  __host__ __device__ static constexpr int type(int k) {
+    const int arr[KA + 1] = {F..., -1};
+    return arr[k];
+  }
+  __host__ __device__ static constexpr int size(int k) { return flow_param_size(type(k), D); }
+  // the LAST flow owns the first columns after the base block (DistributionLayers.py:267-278)
+  __host__ __device__ static constexpr int offset(int k) {
+    int off = base_size;
+    for (int j = K - 1; j > k; --j) off += flow_param_size(type(j), D);
+    return off;
+  }
+  __host__ __device__ static constexpr int P() {
+    int p = base_size;
+    for (int j = 0; j < K; ++j) p += flow_param_size(type(j), D);
+    return p;
+  }
+};
+
+__host__ __device__ constexpr int row_vec(int P) { return (P % 4 == 0) ? 4 : ((P % 2 == 0) ? 2 : 1); }
+__host__ __device__ constexpr int row_stride(int P) {
+  return (P % 4 == 0 && (P / 4) % 2 == 0) ? P + 4 : P;
+}
+
+struct ChainArgs {
+  const float* t;
+  const float* y;
+  const float* g_logp;
+  float* logp;
+  float* dt;
+  float* dy;
+  double* logp_sum;
+  float* dt_colsum;
+  long long B;
+  float g_scale;
+  int y_broadcast;
+};
+
+// ---------------------------------------------------------------- smem span load/store
+template <int OFF, int N, int V>
+struct Span {
+  NFN_DEVI static void load(const float* row, float* out) {
+    if constexpr (N <= 0) {
+      return;
+    } else if constexpr (V >= 4 && OFF % 4 == 0 && N >= 4) {
+      const float4 v = *reinterpret_cast<const float4*>(row + OFF);
+      out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+      Span<OFF + 4, N - 4, V>::load(row, out + 4);
+    } else if constexpr (V >= 2 && OFF % 2 == 0 && N >= 2) {
+      const float2 v = *reinterpret_cast<const float2*>(row + OFF);
+      out[0] = v.x; out[1] = v.y;
+      Span<OFF + 2, N - 2, V>::load(row, out + 2);
+    } else {
+      out[0] = row[OFF];
+      Span<OFF + 1, N - 1, V>::load(row, out + 1);
+    }
+  }
+  NFN_DEVI static void store(float* row, const float* in) {
+    if constexpr (N <= 0) {
+      return;
+    } else if constexpr (V >= 4 && OFF % 4 == 0 && N >= 4) {
+      *reinterpret_cast<float4*>(row + OFF) = make_float4(in[0], in[1], in[2], in[3]);
+      Span<OFF + 4, N - 4, V>::store(row, in + 4);
+    } else if constexpr (V >= 2 && OFF % 2 == 0 && N >= 2) {
+      *reinterpret_cast<float2*>(row + OFF) = make_float2(in[0], in[1]);
+      Span<OFF + 2, N - 2, V>::store(row, in + 2);
+    } else {
+      row[OFF] = in[0];
+      Span<OFF + 1, N - 1, V>::store(row, in + 1);
+    }
+  }
+};
+
+// ---------------------------------------------------------------- async copy helpers
+NFN_DEVI void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+NFN_DEVI void cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+}
+NFN_DEVI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+NFN_DEVI void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+NFN_DEVI void st_stream_f4(float* gdst, const float4& v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gdst), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// Tile geometry shared by the chain and mixture kernels: tile of T rows x P floats in
+// global (contiguous), T x S floats in smem.
+template <int P, int T>
+struct TileIO {
+  static constexpr int V = row_vec(P);
+  static constexpr int S = row_stride(P);
+  static constexpr int kTileFloats = T * P;
+  static constexpr int kChunks = (T * P) / 4;  // T % 4 == 0 -> exact
+  static_assert(T % 4 == 0, "tile must be a whole number of 16-byte chunks");
+
+  // smem float index of flat tile element e (e = row * P + col)
+  NFN_DEVI static int smem_index(int e) {
+    if constexpr (S == P) return e; else return e + (e / P) * (S - P);
+  }
+
+  // async global -> smem for the tile starting at row0 (valid rows: min(T, B - row0))
+  NFN_DEVI static void load_async(float* smem, const float* __restrict__ g, long long row0,
+                                  long long B) {
+    const long long base = row0 * P;                 // first float of the tile
+    const long long total = B * (long long)P;        // floats in the tensor
+    const long long remain = total - base;           // floats available from base
+    const float* src = g + base;
+    for (int q = threadIdx.x; q < kChunks; q += T) {
+      const int e = q * 4;
+      if ((long long)e + 4 <= remain) {
+        cp_async16(smem + smem_index(e), src + e);   // S == P or P % 4 == 0: chunk stays in-row
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if ((long long)e + j < remain) cp_async4(smem + smem_index(e + j), src + e + j);
+      }
+    }
+  }
+
+  // smem -> global, coalesced 16-byte streaming stores
+  NFN_DEVI static void store(const float* smem, float* __restrict__ g, long long row0,
+                             long long B) {
+    const long long base = row0 * P;
+    const long long remain = B * (long long)P - base;
+    float* dst = g + base;
+    for (int q = threadIdx.x; q < kChunks; q += T) {
+      const int e = q * 4;
+      if ((long long)e + 4 <= remain) {
+        const float4 v = *reinterpret_cast<const float4*>(smem + smem_index(e));
+        st_stream_f4(dst + e, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if ((long long)e + j < remain) dst[e + j] = smem[smem_index(e + j)];
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------- static chain sweeps
+template <class Spec, class M, int V, int K0>
+struct FwdSweep {
+  // flows K0 .. K-1
+  NFN_DEVI static void run(const float* row, float (&z)[Spec::D], float (&zs)[Spec::KA][Spec::D],
+                           LogDetAcc<M>& ld) {
+    if constexpr (K0 < Spec::K) {
+      constexpr int D = Spec::D;
+      constexpr int type = Spec::type(K0);
+      constexpr int N = flow_param_size(type, D);
+      float th[N];
+      Span<Spec::offset(K0), N, V>::load(row, th);
+#pragma unroll
+      for (int i = 0; i < D; ++i) zs[K0][i] = z[i];
+      if constexpr (type == kPlanar) PlanarFlow<D, M>::fwd(th, z, ld);
+      else if constexpr (type == kRadial) RadialFlow<D, M>::fwd(th, z, ld);
+      else AffineFlow<D, M>::fwd(th, z, ld);
+      FwdSweep<Spec, M, V, K0 + 1>::run(row, z, zs, ld);
+    }
+  }
+};
+
+template <class Spec, class M, int V, int K0>
+struct BwdSweep {
+  // flows K0 .. 0 (descending)
+  NFN_DEVI static void run(float* row, const float (&zs)[Spec::KA][Spec::D], float (&G)[Spec::D],
+                           float cot) {
+    if constexpr (K0 >= 0) {
+      constexpr int D = Spec::D;
+      constexpr int type = Spec::type(K0);
+      constexpr int N = flow_param_size(type, D);
+      float th[N], gth[N];
+      Span<Spec::offset(K0), N, V>::load(row, th);
+      if constexpr (type == kPlanar) PlanarFlow<D, M>::bwd(th, zs[K0], G, cot, gth);
+      else if constexpr (type == kRadial) RadialFlow<D, M>::bwd(th, zs[K0], G, cot, gth);
+      else AffineFlow<D, M>::bwd(th, zs[K0], G, cot, gth);
+      Span<Spec::offset(K0), N, V>::store(row, gth);
+      BwdSweep<Spec, M, V, K0 - 1>::run(row, zs, G, cot);
+    }
+  }
+};
+
+template <int D>
+NFN_DEVI void load_event(const float* __restrict__ y, long long r, float (&z)[D]) {
+  if constexpr (D == 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(y) + r);
+    z[0] = v.x; z[1] = v.y; z[2] = v.z; z[3] = v.w;
+  } else if constexpr (D == 2) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(y) + r);
+    z[0] = v.x; z[1] = v.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < D; ++i) z[i] = __ldg(y + r * D + i);
+  }
+}
+
+template <int D>
+NFN_DEVI void store_event(float* __restrict__ y, long long r, const float (&z)[D]) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) y[r * D + i] = z[i];
+}
+
+// block-wide sum of a double; result valid in thread 0
+template <int T>
+NFN_DEVI double block_sum(double v, double* scratch /* >= T/32 doubles */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < T / 32; ++i) s += scratch[i];
+  }
+  return s;
+}
+
+// ---------------------------------------------------------------- the kernel
+template <class Spec, bool BWD, class M, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
+  constexpr int D = Spec::D;
+  constexpr int P = Spec::P();
+  using IO = TileIO<(P > 0 ? P : 4), T>;
+  constexpr int V = IO::V;
+  constexpr int S = IO::S;
+  constexpr int NB = 2;
+
+  extern __shared__ __align__(16) float smem[];
+  __shared__ double red[T / 32];
+
+  const long long ntiles = (a.B + T - 1) / T;
+  constexpr int NCOL = P > 0 ? (P + T - 1) / T : 1;
+  float colsum[NCOL];  // thread tid accumulates columns tid, tid+T, ... of dt over this CTA's tiles
+#pragma unroll
+  for (int c = 0; c < NCOL; ++c) colsum[c] = 0.0f;
+  double lsum = 0.0;
+
+  long long tile = blockIdx.x;
+  if constexpr (P > 0) {
+    if (tile < ntiles) IO::load_async(smem, a.t, tile * T, a.B);
+    cp_async_commit();
+  }
+
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    float* buf = smem + (size_t)(it % NB) * (T * S);
+    if constexpr (P > 0) {
+      const long long nxt = tile + gridDim.x;
+      // the other buffer was last read by the previous iteration's store, which every
+      // thread finished before the barrier that ended that iteration
+      if (nxt < ntiles) IO::load_async(smem + (size_t)((it + 1) % NB) * (T * S), a.t, nxt * T, a.B);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncthreads();
+    }
+
+    const long long r = tile * T + threadIdx.x;
+    if (r < a.B) {
+      float* row = buf + threadIdx.x * S;
+      float z[D];
+      load_event<D>(a.y, a.y_broadcast ? 0 : r, z);
+      float zs[Spec::KA][D];
+      LogDetAcc<M> ld;
+      FwdSweep<Spec, M, V, 0>::run(row, z, zs, ld);
+      using Base = BaseDist<D, Spec::BASE, M>;
+      float bth[Base::NA];
+      if constexpr (Spec::BASE) Span<0, 2 * D, V>::load(row, bth);
+      const float lp = Base::log_prob(bth, z) + ld.nat();
+      a.logp[r] = lp;
+      lsum += (double)lp;
+      if constexpr (BWD) {
+        const float cot = a.g_scale * (a.g_logp ? __ldg(a.g_logp + r) : 1.0f);
+        float G[D];
+        float gb[Base::NA];
+        Base::bwd(bth, z, cot, G, gb);
+        if constexpr (Spec::BASE) Span<0, 2 * D, V>::store(row, gb);
+        BwdSweep<Spec, M, V, Spec::K - 1>::run(row, zs, G, cot);
+        if (a.dy) store_event<D>(a.dy, r, G);
+      }
+    }
+
+    if constexpr (BWD && P > 0) {
+      __syncthreads();
+      IO::store(buf, a.dt, tile * T, a.B);
+      if (a.dt_colsum) {
+        const long long rem = a.B - tile * T;
+        const int rows = rem < T ? (int)rem : T;
+#pragma unroll
+        for (int c = 0; c < NCOL; ++c) {
+          const int j = threadIdx.x + c * T;
+          if (j < P) {
+            float acc = 0.0f;
+            for (int rr = 0; rr < rows; ++rr) acc += buf[rr * S + j];
+            colsum[c] += acc;
+          }
+        }
+      }
+      __syncthreads();
+    } else if constexpr (P > 0) {
+      __syncthreads();
+    }
+  }
+  if constexpr (P > 0) cp_async_wait<0>();
+
+  if (a.logp_sum) {
+    const double s = block_sum<T>(lsum, red);
+    if (threadIdx.x == 0) atomicAdd(a.logp_sum, s);
+  }
+  if constexpr (BWD && P > 0) {
+    if (a.dt_colsum) {
+#pragma unroll
+      for (int c = 0; c < NCOL; ++c) {
+        const int j = threadIdx.x + c * T;
+        if (j < P) atomicAdd(a.dt_colsum + j, colsum[c]);
+      }
+    }
+  }
+}
+
+}  // namespace nfn

@@ -1,0 +1,114 @@
+// nfn_common.h -- host-side plumbing shared by the translation units of libnfn_b200.so:
+// thread-local error string, launch counter, device properties, and the registry that maps
+// a chain descriptor to its compile-time specialised launchers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "../../include/nfn_b200.h"
+#include "nfn_chain_kernel.cuh"
+
+namespace nfn {
+
+int set_error(int code, const char* fmt, ...);
+int cuda_error(cudaError_t e, const char* what);
+void count_launch();
+
+struct DeviceInfo {
+  int device = -1;
+  int sm_count = 0;
+  int smem_optin = 0;
+};
+const DeviceInfo& device_info();
+
+// Math mode: 0 = fast (MUFU-based, default), 1 = accurate (CUDA libm + IEEE division).
+int math_mode();
+
+typedef cudaError_t (*ChainLaunchFn)(const ChainArgs&, cudaStream_t);
+
+struct ChainKernels {
+  // [math mode][bwd]
+  ChainLaunchFn fn[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+};
+
+std::string chain_key(int d, bool base, int k, const uint8_t* types);
+void register_chain(const std::string& key, const ChainKernels& k);
+const ChainKernels* find_chain(const std::string& key);
+
+// ------------------------------------------------------------------ specialised launcher
+template <class Spec, bool BWD, class M>
+cudaError_t launch_chain(const ChainArgs& a, cudaStream_t st) {
+  constexpr int P = Spec::P();
+  constexpr int T = 128;
+  constexpr int S = row_stride(P > 0 ? P : 4);
+  constexpr size_t kSmem = P > 0 ? (size_t)2 * T * S * sizeof(float) : 0;
+  // CTAs per SM the shared-memory budget allows (227 KB usable, 1 KB reserved per CTA)
+  constexpr int kBySmem = kSmem ? (int)((227 * 1024) / (kSmem + 1024)) : 16;
+  constexpr int kCap = BWD ? 5 : 6;  // 640 / 768 threads per SM: leaves >= 80 registers per thread
+  constexpr int MINB = kBySmem < 1 ? 1 : (kBySmem > kCap ? kCap : kBySmem);
+  static_assert(kSmem <= 227 * 1024, "parameter row too wide for the double-buffered tile");
+  auto kern = chain_kernel<Spec, BWD, M, T, MINB>;
+
+  struct Cfg {
+    int device = -1;
+    int ctas_per_sm = 0;
+  };
+  static thread_local Cfg cfg;
+  const DeviceInfo& di = device_info();
+  if (cfg.device != di.device) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, kSmem);
+    if (e != cudaSuccess) return e;
+    cfg.ctas_per_sm = occ > 0 ? occ : 1;
+    cfg.device = di.device;
+  }
+  const long long ntiles = (a.B + T - 1) / T;
+  long long grid = (long long)di.sm_count * cfg.ctas_per_sm;
+  if (grid > ntiles) grid = ntiles;
+  kern<<<(unsigned)grid, T, kSmem, st>>>(a);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <class Spec>
+struct ChainRegistrar {
+  explicit ChainRegistrar() {
+    ChainKernels k;
+    k.fn[0][0] = &launch_chain<Spec, false, MathFast>;
+    k.fn[0][1] = &launch_chain<Spec, true, MathFast>;
+    k.fn[1][0] = &launch_chain<Spec, false, MathAccurate>;
+    k.fn[1][1] = &launch_chain<Spec, true, MathAccurate>;
+    uint8_t types[Spec::KA];
+    for (int i = 0; i < Spec::K; ++i) types[i] = (uint8_t)Spec::type(i);
+    register_chain(chain_key(Spec::D, Spec::BASE, Spec::K, types), k);
+  }
+};
+
+// mixture heads (nfn_mixture.cu)
+struct MixArgs {
+  const float* t;
+  const float* y;
+  const float* g_logp;
+  const float* locs;    // KMN only
+  const float* scales;  // KMN only
+  float* logp;
+  float* dt;
+  float* dy;
+  float* dscales;       // KMN only
+  double* logp_sum;
+  float* dt_colsum;
+  long long B;
+  float g_scale;
+  int y_broadcast;
+  int K;                // components
+};
+int launch_mdn(int d, bool bwd, const MixArgs& a, cudaStream_t st);
+int launch_kmn(int d, bool bwd, const MixArgs& a, cudaStream_t st);
+int launch_logmeanexp(const float* in, long long S, long long B, float* out, cudaStream_t st);
+int launch_colsum(const float* dt, long long B, int P, float* out, cudaStream_t st);
+
+}  // namespace nfn

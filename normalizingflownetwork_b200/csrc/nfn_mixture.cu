@@ -1,0 +1,440 @@
+// nfn_mixture.cu -- fused Gaussian-mixture logsumexp heads (sm_100a).
+//
+//   MDN : tfd.Mixture of K diagonal Gaussians parameterised per sample
+//         (reference estimators/DistributionLayers.py:196-212), row layout
+//         [ (mu_k(d), sigma_raw_k(d))_{k<K} | logits(K) ], sigma = softplus(0.05 raw + c0).
+//   KMN : tfd.MixtureSameFamily over M fixed centres with shared isotropic bandwidths
+//         (estimators/DistributionLayers.py:118-133), row = logits(M).
+//   logmeanexp over S posterior draws (estimators/BayesianNNEstimator.py:65-76).
+//
+// Same data movement as the flow chain: one thread per sample, T-row tiles staged with
+// coalesced 16-byte cp.async into a double-buffered, bank-conflict-free padded smem tile,
+// gradients written in place and streamed back with coalesced 16-byte stores.  The row
+// width is a runtime value here (K is not a template parameter); D and the row vector
+// width V are.  Forward is an online logsumexp (one EX2 per component); the reverse sweep
+// reuses sigma (written over sigma_raw by the forward pass) so softplus is not recomputed.
+#include "nfn_common.h"
+
+namespace nfn {
+
+constexpr int kMixT = 128;
+
+// ------------------------------------------------------------------ runtime-width tile io
+struct RtTile {
+  int P;      // floats per row in global
+  int S;      // floats per row in smem
+  int P4;     // P / 4 when P % 4 == 0 (padded layout), else 0
+};
+
+NFN_DEVI int rt_index(const RtTile& g, int e) {
+  return g.S == g.P ? e : e + (e / g.P) * (g.S - g.P);
+}
+
+NFN_DEVI void rt_load_async(const RtTile& g, float* smem, const float* __restrict__ src0, long long row0,
+                            long long B) {
+  const long long base = row0 * g.P;
+  const long long remain = B * (long long)g.P - base;
+  const float* src = src0 + base;
+  const int chunks = (kMixT * g.P) / 4;
+  for (int q = threadIdx.x; q < chunks; q += kMixT) {
+    const int e = q * 4;
+    if ((long long)e + 4 <= remain) {
+      cp_async16(smem + rt_index(g, e), src + e);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if ((long long)e + j < remain) cp_async4(smem + rt_index(g, e + j), src + e + j);
+    }
+  }
+}
+
+NFN_DEVI void rt_store(const RtTile& g, const float* smem, float* __restrict__ dst0, long long row0,
+                       long long B) {
+  const long long base = row0 * g.P;
+  const long long remain = B * (long long)g.P - base;
+  float* dst = dst0 + base;
+  const int chunks = (kMixT * g.P) / 4;
+  for (int q = threadIdx.x; q < chunks; q += kMixT) {
+    const int e = q * 4;
+    if ((long long)e + 4 <= remain) {
+      const float4 v = *reinterpret_cast<const float4*>(smem + rt_index(g, e));
+      st_stream_f4(dst + e, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if ((long long)e + j < remain) dst[e + j] = smem[rt_index(g, e + j)];
+    }
+  }
+}
+
+// per-thread load/store of N consecutive floats at a runtime offset whose alignment
+// (in floats) is at least A (compile time)
+template <int N, int A>
+NFN_DEVI void ld_vec(const float* p, float (&v)[N]) {
+  if constexpr (A >= 4 && N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(p + i);
+      v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
+    }
+  } else if constexpr (A >= 2 && N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+      const float2 x = *reinterpret_cast<const float2*>(p + i);
+      v[i] = x.x; v[i + 1] = x.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = p[i];
+  }
+}
+template <int N, int A>
+NFN_DEVI void st_vec(float* p, const float (&v)[N]) {
+  if constexpr (A >= 4 && N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  } else if constexpr (A >= 2 && N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 2) *reinterpret_cast<float2*>(p + i) = make_float2(v[i], v[i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = v[i];
+  }
+}
+
+// online logsumexp update with one exponential
+template <class M>
+NFN_DEVI void lse_push(float x, float& m, float& s) {
+  const float e = M::exp(-fabsf(x - m));
+  s = (x > m) ? fmaf(s, e, 1.0f) : s + e;
+  m = fmaxf(m, x);
+}
+
+// ------------------------------------------------------------------ MDN
+// V4: rows are 16-byte aligned in smem (P % 4 == 0) so the (mu, sigma_raw) block of a
+// component, 2*D floats at offset k*2*D, can be read with the widest aligned vectors.
+template <int D, bool V4, bool BWD, class M>
+__global__ void __launch_bounds__(kMixT, BWD ? 3 : 4) mdn_kernel(const MixArgs a, const RtTile g) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ double red[kMixT / 32];
+  constexpr int A = V4 ? ((2 * D) % 4 == 0 ? 4 : ((2 * D) % 2 == 0 ? 2 : 1)) : 1;
+  const int K = a.K;
+  const int LO = 2 * K * D;  // logits offset
+  const long long ntiles = (a.B + kMixT - 1) / kMixT;
+  double lsum = 0.0;
+  const int tile_floats = kMixT * g.S;
+
+  long long tile = blockIdx.x;
+  if (tile < ntiles) rt_load_async(g, smem, a.t, tile * kMixT, a.B);
+  cp_async_commit();
+
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    float* buf = smem + (size_t)(it & 1) * tile_floats;
+    const long long nxt = tile + gridDim.x;
+    if (nxt < ntiles) rt_load_async(g, smem + (size_t)((it + 1) & 1) * tile_floats, a.t, nxt * kMixT, a.B);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+
+    const long long r = tile * kMixT + threadIdx.x;
+    if (r < a.B) {
+      float* row = buf + threadIdx.x * g.S;
+      float y[D];
+      load_event<D>(a.y, a.y_broadcast ? 0 : r, y);
+      // log-softmax normaliser of the logits
+      float lm = -INFINITY, ls = 0.0f;
+      for (int k = 0; k < K; ++k) lse_push<M>(row[LO + k], lm, ls);
+      const float lse = lm + M::log(ls);
+      // components, online logsumexp
+      float m = -INFINITY, s = 0.0f;
+      for (int k = 0; k < K; ++k) {
+        float th[2 * D];
+        ld_vec<2 * D, A>(row + k * 2 * D, th);
+        float quad = 0.0f, prod = 1.0f;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          const float sig = M::softplus(fmaf(0.05f, th[D + i], kC0));
+          const float e = M::div(y[i] - th[i], sig);
+          quad = fmaf(e, e, quad);
+          prod *= sig;
+          if constexpr (BWD) th[D + i] = sig;
+        }
+        if constexpr (BWD) st_vec<2 * D, A>(row + k * 2 * D, th);  // keep sigma for the reverse sweep
+        const float lp = row[LO + k] - fmaf(0.5f, quad, M::log(prod));
+        lse_push<M>(lp, m, s);
+      }
+      const float top = m + M::log(s);                       // logsumexp_k(logit_k + log N_k) + d/2 log 2pi
+      const float logp = top - lse - (float)D * kHalfLog2Pi;
+      a.logp[r] = logp;
+      lsum += (double)logp;
+      if constexpr (BWD) {
+        const float cot = a.g_scale * (a.g_logp ? __ldg(a.g_logp + r) : 1.0f);
+        float dy[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) dy[i] = 0.0f;
+        for (int k = 0; k < K; ++k) {
+          float th[2 * D];
+          ld_vec<2 * D, A>(row + k * 2 * D, th);           // (mu, sigma)
+          float e[D], rs[D];
+          float quad = 0.0f, prod = 1.0f;
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            rs[i] = M::rcp(th[D + i]);
+            e[i] = (y[i] - th[i]) * rs[i];
+            quad = fmaf(e[i], e[i], quad);
+            prod *= th[D + i];
+          }
+          const float logit = row[LO + k];
+          const float lp = logit - fmaf(0.5f, quad, M::log(prod));
+          const float crho = cot * M::exp(lp - top);         // cot * responsibility
+          row[LO + k] = fmaf(-cot, M::exp(logit - lse), crho);
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            const float gm = crho * e[i] * rs[i];
+            // d sigma / d raw = 0.05 * sigmoid(x), and sigmoid(x) = 1 - exp(-softplus(x))
+            const float dsig = 0.05f * (1.0f - M::exp(-th[D + i]));
+            th[D + i] = crho * fmaf(e[i], e[i], -1.0f) * rs[i] * dsig;
+            th[i] = gm;
+            dy[i] -= gm;
+          }
+          st_vec<2 * D, A>(row + k * 2 * D, th);
+        }
+        if (a.dy) store_event<D>(a.dy, r, dy);
+      }
+    }
+    __syncthreads();
+    if constexpr (BWD) {
+      rt_store(g, buf, a.dt, tile * kMixT, a.B);
+      __syncthreads();
+    }
+  }
+  cp_async_wait<0>();
+  if (a.logp_sum) {
+    const double sblk = block_sum<kMixT>(lsum, red);
+    if (threadIdx.x == 0) atomicAdd(a.logp_sum, sblk);
+  }
+}
+
+// ------------------------------------------------------------------ KMN
+// smem: [2 buffers of T x S logits] [locs M x D] [coef M: -0.5 / s^2] [lognorm M: -D log|s|]
+template <int D, bool BWD, class M>
+__global__ void __launch_bounds__(kMixT, BWD ? 3 : 4) kmn_kernel(const MixArgs a, const RtTile g) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ double red[kMixT / 32];
+  const int K = a.K;
+  const int tile_floats = kMixT * g.S;
+  float* s_loc = smem + 2 * (size_t)tile_floats;
+  float* s_coef = s_loc + K * D;
+  float* s_lnorm = s_coef + K;
+  float* s_dsc = s_lnorm + K;  // block accumulators of d logp / d scale (BWD)
+  for (int i = threadIdx.x; i < K * D; i += kMixT) s_loc[i] = __ldg(a.locs + i);
+  for (int i = threadIdx.x; i < K; i += kMixT) {
+    const float sc = __ldg(a.scales + i);
+    s_coef[i] = -0.5f / (sc * sc);
+    s_lnorm[i] = -(float)D * logf(fabsf(sc));
+    if constexpr (BWD) s_dsc[i] = 0.0f;
+  }
+  const long long ntiles = (a.B + kMixT - 1) / kMixT;
+  double lsum = 0.0;
+
+  long long tile = blockIdx.x;
+  if (tile < ntiles) rt_load_async(g, smem, a.t, tile * kMixT, a.B);
+  cp_async_commit();
+
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    float* buf = smem + (size_t)(it & 1) * tile_floats;
+    const long long nxt = tile + gridDim.x;
+    if (nxt < ntiles) rt_load_async(g, smem + (size_t)((it + 1) & 1) * tile_floats, a.t, nxt * kMixT, a.B);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+
+    const long long r = tile * kMixT + threadIdx.x;
+    const bool valid = r < a.B;
+    float* row = buf + threadIdx.x * g.S;
+    float y[D];
+    float lse = 0.0f, top = 0.0f, cot = 0.0f;
+    if (valid) {
+      load_event<D>(a.y, a.y_broadcast ? 0 : r, y);
+      float lm = -INFINITY, ls = 0.0f;
+      for (int k = 0; k < K; ++k) lse_push<M>(row[k], lm, ls);
+      lse = lm + M::log(ls);
+      float m = -INFINITY, s = 0.0f;
+      for (int k = 0; k < K; ++k) {
+        float q = 0.0f;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          const float dlt = y[i] - s_loc[k * D + i];
+          q = fmaf(dlt, dlt, q);
+        }
+        lse_push<M>(row[k] + fmaf(s_coef[k], q, s_lnorm[k]), m, s);
+      }
+      top = m + M::log(s);
+      const float logp = top - lse - (float)D * kHalfLog2Pi;
+      a.logp[r] = logp;
+      lsum += (double)logp;
+    } else {
+#pragma unroll
+      for (int i = 0; i < D; ++i) y[i] = 0.0f;
+    }
+    if constexpr (BWD) {
+      if (valid) cot = a.g_scale * (a.g_logp ? __ldg(a.g_logp + r) : 1.0f);
+      float dy[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) dy[i] = 0.0f;
+      for (int k = 0; k < K; ++k) {  // all lanes stay in the loop: warp reduction of d/dscale
+        float wsc = 0.0f;
+        if (valid) {
+          float q = 0.0f, dl[D];
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            dl[i] = y[i] - s_loc[k * D + i];
+            q = fmaf(dl[i], dl[i], q);
+          }
+          const float logit = row[k];
+          const float crho = cot * M::exp(logit + fmaf(s_coef[k], q, s_lnorm[k]) - top);
+          row[k] = fmaf(-cot, M::exp(logit - lse), crho);
+          const float c2 = -2.0f * s_coef[k];               // 1 / s^2
+#pragma unroll
+          for (int i = 0; i < D; ++i) dy[i] -= crho * dl[i] * c2;
+          wsc = crho * fmaf(q, c2, -(float)D);               // * 1/s applied on the host side of the sum
+        }
+        if (a.dscales) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) wsc += __shfl_xor_sync(0xffffffffu, wsc, o);
+          if ((threadIdx.x & 31) == 0) atomicAdd(&s_dsc[k], wsc);
+        }
+      }
+      if (valid && a.dy) store_event<D>(a.dy, r, dy);
+    }
+    __syncthreads();
+    if constexpr (BWD) {
+      rt_store(g, buf, a.dt, tile * kMixT, a.B);
+      __syncthreads();
+    }
+  }
+  cp_async_wait<0>();
+  if constexpr (BWD) {
+    if (a.dscales) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < K; i += kMixT) atomicAdd(a.dscales + i, s_dsc[i] / __ldg(a.scales + i));
+    }
+  }
+  if (a.logp_sum) {
+    const double sblk = block_sum<kMixT>(lsum, red);
+    if (threadIdx.x == 0) atomicAdd(a.logp_sum, sblk);
+  }
+}
+
+// ------------------------------------------------------------------ launchers
+static RtTile make_tile(int P) {
+  RtTile g;
+  g.P = P;
+  g.S = row_stride(P);
+  g.P4 = (P % 4 == 0) ? P / 4 : 0;
+  return g;
+}
+
+template <class Kern>
+static int launch_tiled(Kern kern, const MixArgs& a, const RtTile& g, size_t smem, const char* name,
+                        cudaStream_t st) {
+  const DeviceInfo& di = device_info();
+  if (smem > (size_t)di.smem_optin)
+    return set_error(NFN_ERR_UNSUPPORTED, "%s: row of %d floats needs %zu bytes of shared memory (> %d)", name,
+                     g.P, smem, di.smem_optin);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_error(e, name);
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kMixT, smem);
+  if (e != cudaSuccess) return cuda_error(e, name);
+  if (occ < 1) occ = 1;
+  const long long ntiles = (a.B + kMixT - 1) / kMixT;
+  long long grid = (long long)di.sm_count * occ;
+  if (grid > ntiles) grid = ntiles;
+  kern<<<(unsigned)grid, kMixT, smem, st>>>(a, g);
+  count_launch();
+  return cuda_error(cudaGetLastError(), name);
+}
+
+template <int D, bool V4>
+static int launch_mdn_dv(bool bwd, const MixArgs& a, const RtTile& g, size_t smem, cudaStream_t st) {
+  if (math_mode() == 0) {
+    return bwd ? launch_tiled(mdn_kernel<D, V4, true, MathFast>, a, g, smem, "mdn_kernel", st)
+               : launch_tiled(mdn_kernel<D, V4, false, MathFast>, a, g, smem, "mdn_kernel", st);
+  }
+  return bwd ? launch_tiled(mdn_kernel<D, V4, true, MathAccurate>, a, g, smem, "mdn_kernel", st)
+             : launch_tiled(mdn_kernel<D, V4, false, MathAccurate>, a, g, smem, "mdn_kernel", st);
+}
+
+template <int D>
+static int launch_mdn_d(bool bwd, const MixArgs& a, cudaStream_t st) {
+  const int P = 2 * a.K * D + a.K;
+  const RtTile g = make_tile(P);
+  const size_t smem = (size_t)2 * kMixT * g.S * sizeof(float);
+  int rc = (P % 4 == 0) ? launch_mdn_dv<D, true>(bwd, a, g, smem, st) : launch_mdn_dv<D, false>(bwd, a, g, smem, st);
+  if (rc == NFN_OK && bwd && a.dt_colsum) rc = launch_colsum(a.dt, a.B, P, a.dt_colsum, st);
+  return rc;
+}
+
+int launch_mdn(int d, bool bwd, const MixArgs& a, cudaStream_t st) {
+  switch (d) {
+    case 1: return launch_mdn_d<1>(bwd, a, st);
+    case 2: return launch_mdn_d<2>(bwd, a, st);
+    case 3: return launch_mdn_d<3>(bwd, a, st);
+    case 4: return launch_mdn_d<4>(bwd, a, st);
+    case 5: return launch_mdn_d<5>(bwd, a, st);
+    case 6: return launch_mdn_d<6>(bwd, a, st);
+    case 7: return launch_mdn_d<7>(bwd, a, st);
+    case 8: return launch_mdn_d<8>(bwd, a, st);
+  }
+  return set_error(NFN_ERR_DESC, "n_dims=%d", d);
+}
+
+template <int D>
+static int launch_kmn_d(bool bwd, const MixArgs& a, cudaStream_t st) {
+  const RtTile g = make_tile(a.K);
+  const size_t smem = ((size_t)2 * kMixT * g.S + (size_t)a.K * (D + 3)) * sizeof(float);
+  if (math_mode() == 0) {
+    return bwd ? launch_tiled(kmn_kernel<D, true, MathFast>, a, g, smem, "kmn_kernel", st)
+               : launch_tiled(kmn_kernel<D, false, MathFast>, a, g, smem, "kmn_kernel", st);
+  }
+  return bwd ? launch_tiled(kmn_kernel<D, true, MathAccurate>, a, g, smem, "kmn_kernel", st)
+             : launch_tiled(kmn_kernel<D, false, MathAccurate>, a, g, smem, "kmn_kernel", st);
+}
+
+int launch_kmn(int d, bool bwd, const MixArgs& a, cudaStream_t st) {
+  switch (d) {
+    case 1: return launch_kmn_d<1>(bwd, a, st);
+    case 2: return launch_kmn_d<2>(bwd, a, st);
+    case 3: return launch_kmn_d<3>(bwd, a, st);
+    case 4: return launch_kmn_d<4>(bwd, a, st);
+    case 5: return launch_kmn_d<5>(bwd, a, st);
+    case 6: return launch_kmn_d<6>(bwd, a, st);
+    case 7: return launch_kmn_d<7>(bwd, a, st);
+    case 8: return launch_kmn_d<8>(bwd, a, st);
+  }
+  return set_error(NFN_ERR_DESC, "n_dims=%d", d);
+}
+
+// ------------------------------------------------------------------ posterior-draw epilogue
+// out[b] = logsumexp_s in[s, b] - log S ; thread per b, coalesced across b for every s.
+__global__ void __launch_bounds__(256) logmeanexp_kernel(const float* __restrict__ in, long long S, long long B,
+                                                         float* __restrict__ out) {
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B;
+       b += (long long)gridDim.x * blockDim.x) {
+    float m = -INFINITY, s = 0.0f;
+    for (long long k = 0; k < S; ++k) lse_push<MathAccurate>(__ldg(in + k * B + b), m, s);
+    out[b] = m + logf(s) - logf((float)S);
+  }
+}
+
+int launch_logmeanexp(const float* in, long long S, long long B, float* out, cudaStream_t st) {
+  long long blocks = (B + 255) / 256;
+  const long long cap = (long long)device_info().sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  logmeanexp_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, S, B, out);
+  count_launch();
+  return cuda_error(cudaGetLastError(), "logmeanexp_kernel");
+}
+
+}  // namespace nfn

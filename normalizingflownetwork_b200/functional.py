@@ -1,0 +1,312 @@
+"""Tensor-level entry points over the C ABI (torch.Tensor in, torch.Tensor out).
+
+Every function here enqueues hand-written sm_100a kernels from libnfn_b200.so on the
+current CUDA stream; torch only owns the memory.  CPU tensors are rejected (no fallback).
+
+Autograd: ``chain_log_prob`` / ``mdn_log_prob`` / ``kmn_log_prob`` are differentiable in
+the parameter tensor ``t`` (and ``y``): the forward launches the forward-only kernel and
+the backward launches the fused forward+reverse-sweep kernel with the incoming cotangent,
+so no per-flow activation is ever stored.  Training loops that own the loss should call
+``chain_forward_backward`` directly (one launch, cotangent -1/B folded in) and feed ``dt``
+to ``t.backward(dt)``.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _as_f32_cuda(x, name, device=None):
+    if not torch.is_tensor(x):
+        if device is None:
+            raise RuntimeError("%s: cannot infer the CUDA device from a non-tensor input" % name)
+        x = torch.as_tensor(x, dtype=torch.float32).to(device)
+    _lib.require_cuda(x, name)
+    if x.dtype != torch.float32:
+        x = x.to(torch.float32)
+    return x.contiguous()
+
+
+def _aligned(x, nbytes=16):
+    """Kernels need 16-byte aligned bases; torch allocations are, sliced views may not be."""
+    return x if x.data_ptr() % nbytes == 0 else x.clone(memory_format=torch.contiguous_format)
+
+
+def _prep_ty(t, y, n_dims, width, what):
+    t = _as_f32_cuda(t, "t")
+    if t.dim() != 2:
+        raise ValueError("%s: parameter tensor must be rank 2 [B, P], got shape %s" % (what, tuple(t.shape)))
+    y = _as_f32_cuda(y, "y", device=t.device)
+    if y.dim() != 2 or y.shape[1] != n_dims:
+        raise ValueError("%s: y must be [B, %d] or [1, %d], got %s" % (what, n_dims, n_dims, tuple(y.shape)))
+    B = t.shape[0]
+    if t.shape[1] != width:
+        raise AssertionError("%s: expected %d parameter columns, got %d" % (what, width, t.shape[1]))
+    if y.shape[0] not in (B, 1):
+        if B == 1:  # [1, P] parameters against many y rows: materialise the parameter rows
+            t = t.expand(y.shape[0], width).contiguous()
+            B = y.shape[0]
+        else:
+            raise ValueError("%s: y has %d rows, parameters have %d" % (what, y.shape[0], B))
+    return _aligned(t), _aligned(y), B
+
+
+# ----------------------------------------------------------------------------- flow chain
+def chain_param_size(flow_types, n_dims, trainable_base_dist):
+    lib = _lib.load()
+    return _lib.check(lib.nfn_chain_param_size(ctypes.byref(_lib.make_desc(flow_types, n_dims, trainable_base_dist))))
+
+
+def chain_is_specialized(flow_types, n_dims, trainable_base_dist):
+    lib = _lib.load()
+    return bool(_lib.check(lib.nfn_chain_is_specialized(ctypes.byref(_lib.make_desc(flow_types, n_dims, trainable_base_dist)))))
+
+
+def chain_forward(t, y, flow_types, n_dims, trainable_base_dist):
+    """log_prob[B] of the inverted flow chain (no autograd)."""
+    lib = _lib.load()
+    desc = _lib.make_desc(flow_types, n_dims, trainable_base_dist)
+    P = _lib.check(lib.nfn_chain_param_size(ctypes.byref(desc)))
+    t, y, B = _prep_ty(t, y, n_dims, P, "chain_forward")
+    logp = torch.empty(B, dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.check(lib.nfn_chain_forward(ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), y.shape[0],
+                                         _lib.ptr(logp), B, _lib.current_stream(t.device)))
+    return logp
+
+
+def chain_forward_backward(t, y, flow_types, n_dims, trainable_base_dist, g_logp=None, g_scale=1.0,
+                           want_dy=False, logp_sum=None, dt_colsum=None, out_logp=None, out_dt=None):
+    """Fused forward + reverse sweep.  Returns (logp[B], dt[B,P], dy[B,d] or None).
+
+    dt = cot[:, None] * dlogp/dt with cot = g_scale * (g_logp if given else 1).
+    ``logp_sum`` (float64 [1]) and ``dt_colsum`` (float32 [P]) are accumulated into when given.
+    """
+    lib = _lib.load()
+    desc = _lib.make_desc(flow_types, n_dims, trainable_base_dist)
+    P = _lib.check(lib.nfn_chain_param_size(ctypes.byref(desc)))
+    t, y, B = _prep_ty(t, y, n_dims, P, "chain_forward_backward")
+    dev = t.device
+    logp = out_logp if out_logp is not None else torch.empty(B, dtype=torch.float32, device=dev)
+    dt = out_dt if out_dt is not None else torch.empty((B, P), dtype=torch.float32, device=dev)
+    dy = torch.empty((B, n_dims), dtype=torch.float32, device=dev) if want_dy else None
+    if want_dy and y.shape[0] != B:
+        raise ValueError("dy needs one y row per parameter row")
+    if g_logp is not None:
+        g_logp = _as_f32_cuda(g_logp, "g_logp", device=dev).reshape(-1)
+        if g_logp.numel() != B:
+            raise ValueError("g_logp must have B=%d elements" % B)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_chain_forward_backward(
+            ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), y.shape[0], _lib.ptr(g_logp),
+            ctypes.c_float(g_scale), _lib.ptr(logp), _lib.ptr(dt), _lib.ptr(dy), _lib.ptr(logp_sum),
+            _lib.ptr(dt_colsum), B, _lib.current_stream(dev)))
+    return logp, dt, dy
+
+
+class _ChainLogProb(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, y, flow_types, n_dims, trainable_base_dist):
+        ctx.save_for_backward(t, y)
+        ctx.cfg = (tuple(flow_types), n_dims, trainable_base_dist)
+        return chain_forward(t, y, flow_types, n_dims, trainable_base_dist)
+
+    @staticmethod
+    def backward(ctx, g):
+        t, y = ctx.saved_tensors
+        flow_types, n_dims, tb = ctx.cfg
+        need_dy = ctx.needs_input_grad[1]
+        B = g.shape[0]
+        if t.shape[0] == 1 and B != 1:
+            t_rows = t.expand(B, t.shape[1]).contiguous()
+        else:
+            t_rows = t
+        y_rows = y.expand(B, y.shape[1]).contiguous() if (need_dy and y.shape[0] != B) else y
+        _, dt, dy = chain_forward_backward(t_rows, y_rows, flow_types, n_dims, tb, g_logp=g.contiguous(),
+                                           want_dy=need_dy)
+        if t.shape[0] == 1 and B != 1:
+            dt = dt.sum(0, keepdim=True)
+        if need_dy and y.shape[0] != B:
+            dy = dy.sum(0, keepdim=True)
+        return (dt if ctx.needs_input_grad[0] else None), (dy if need_dy else None), None, None, None
+
+
+def chain_log_prob(t, y, flow_types, n_dims, trainable_base_dist):
+    """Differentiable log_prob[B] (see module docstring)."""
+    t = _as_f32_cuda(t, "t")
+    y = _as_f32_cuda(y, "y", device=t.device)
+    return _ChainLogProb.apply(t, y, tuple(flow_types), int(n_dims), bool(trainable_base_dist))
+
+
+def flow_forward(flow_type, t, z, n_dims, want_z=True, want_fldj=True):
+    """One bijector: returns (forward(z) [B,d] or None, fldj [B] or None)."""
+    lib = _lib.load()
+    t = _as_f32_cuda(t, "t")
+    z = _as_f32_cuda(z, "z", device=t.device)
+    if t.dim() != 2 or z.dim() != 2 or z.shape[1] != n_dims:
+        raise ValueError("flow_forward: t must be [B, size], z must be [B, %d] or [1, %d]" % (n_dims, n_dims))
+    B = t.shape[0]
+    if z.shape[0] not in (B, 1):
+        if B != 1:
+            raise ValueError("flow_forward: z has %d rows, t has %d" % (z.shape[0], B))
+        t = t.expand(z.shape[0], t.shape[1]).contiguous()
+        B = z.shape[0]
+    t, z = _aligned(t), _aligned(z)
+    z_out = torch.empty((B, n_dims), dtype=torch.float32, device=t.device) if want_z else None
+    fldj = torch.empty(B, dtype=torch.float32, device=t.device) if want_fldj else None
+    with torch.cuda.device(t.device):
+        _lib.check(lib.nfn_flow_forward(_lib.FLOW_CODES[flow_type], n_dims, _lib.ptr(t), _lib.ptr(z),
+                                        z.shape[0], _lib.ptr(z_out), _lib.ptr(fldj), B,
+                                        _lib.current_stream(t.device)))
+    return z_out, fldj
+
+
+# ----------------------------------------------------------------------------- MDN head
+def mdn_param_size(n_centers, n_dims):
+    return 2 * n_centers * n_dims + n_centers
+
+
+def mdn_forward(t, y, n_centers, n_dims):
+    lib = _lib.load()
+    t, y, B = _prep_ty(t, y, n_dims, mdn_param_size(n_centers, n_dims), "mdn_forward")
+    logp = torch.empty(B, dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.check(lib.nfn_mdn_forward(n_centers, n_dims, _lib.ptr(t), _lib.ptr(y), y.shape[0],
+                                       _lib.ptr(logp), B, _lib.current_stream(t.device)))
+    return logp
+
+
+def mdn_forward_backward(t, y, n_centers, n_dims, g_logp=None, g_scale=1.0, want_dy=False,
+                         logp_sum=None, dt_colsum=None):
+    lib = _lib.load()
+    P = mdn_param_size(n_centers, n_dims)
+    t, y, B = _prep_ty(t, y, n_dims, P, "mdn_forward_backward")
+    dev = t.device
+    logp = torch.empty(B, dtype=torch.float32, device=dev)
+    dt = torch.empty((B, P), dtype=torch.float32, device=dev)
+    dy = torch.empty((B, n_dims), dtype=torch.float32, device=dev) if want_dy else None
+    if g_logp is not None:
+        g_logp = _as_f32_cuda(g_logp, "g_logp", device=dev).reshape(-1)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_mdn_forward_backward(
+            n_centers, n_dims, _lib.ptr(t), _lib.ptr(y), y.shape[0], _lib.ptr(g_logp),
+            ctypes.c_float(g_scale), _lib.ptr(logp), _lib.ptr(dt), _lib.ptr(dy), _lib.ptr(logp_sum),
+            _lib.ptr(dt_colsum), B, _lib.current_stream(dev)))
+    return logp, dt, dy
+
+
+class _MdnLogProb(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, y, n_centers, n_dims):
+        ctx.save_for_backward(t, y)
+        ctx.cfg = (n_centers, n_dims)
+        return mdn_forward(t, y, n_centers, n_dims)
+
+    @staticmethod
+    def backward(ctx, g):
+        t, y = ctx.saved_tensors
+        K, d = ctx.cfg
+        need_dy = ctx.needs_input_grad[1]
+        B = g.shape[0]
+        t_rows = t.expand(B, t.shape[1]).contiguous() if (t.shape[0] == 1 and B != 1) else t
+        y_rows = y.expand(B, d).contiguous() if (need_dy and y.shape[0] != B) else y
+        _, dt, dy = mdn_forward_backward(t_rows, y_rows, K, d, g_logp=g.contiguous(), want_dy=need_dy)
+        if t.shape[0] == 1 and B != 1:
+            dt = dt.sum(0, keepdim=True)
+        if need_dy and y.shape[0] != B:
+            dy = dy.sum(0, keepdim=True)
+        return (dt if ctx.needs_input_grad[0] else None), (dy if need_dy else None), None, None
+
+
+def mdn_log_prob(t, y, n_centers, n_dims):
+    t = _as_f32_cuda(t, "t")
+    y = _as_f32_cuda(y, "y", device=t.device)
+    return _MdnLogProb.apply(t, y, int(n_centers), int(n_dims))
+
+
+# ----------------------------------------------------------------------------- KMN head
+def kmn_forward(t, y, locs, scales):
+    lib = _lib.load()
+    locs = _as_f32_cuda(locs, "locs")
+    M, d = locs.shape
+    scales = _as_f32_cuda(scales, "scales", device=locs.device).reshape(-1)
+    t, y, B = _prep_ty(t, y, d, M, "kmn_forward")
+    logp = torch.empty(B, dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.check(lib.nfn_kmn_forward(M, d, _lib.ptr(t), _lib.ptr(y), y.shape[0], _lib.ptr(locs),
+                                       _lib.ptr(scales), _lib.ptr(logp), B, _lib.current_stream(t.device)))
+    return logp
+
+
+def kmn_forward_backward(t, y, locs, scales, g_logp=None, g_scale=1.0, want_dy=False, want_dscales=True,
+                         logp_sum=None):
+    lib = _lib.load()
+    locs = _as_f32_cuda(locs, "locs")
+    M, d = locs.shape
+    scales = _as_f32_cuda(scales, "scales", device=locs.device).reshape(-1)
+    t, y, B = _prep_ty(t, y, d, M, "kmn_forward_backward")
+    dev = t.device
+    logp = torch.empty(B, dtype=torch.float32, device=dev)
+    dt = torch.empty((B, M), dtype=torch.float32, device=dev)
+    dy = torch.empty((B, d), dtype=torch.float32, device=dev) if want_dy else None
+    dscales = torch.zeros(M, dtype=torch.float32, device=dev) if want_dscales else None
+    if g_logp is not None:
+        g_logp = _as_f32_cuda(g_logp, "g_logp", device=dev).reshape(-1)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_kmn_forward_backward(
+            M, d, _lib.ptr(t), _lib.ptr(y), y.shape[0], _lib.ptr(locs), _lib.ptr(scales), _lib.ptr(g_logp),
+            ctypes.c_float(g_scale), _lib.ptr(logp), _lib.ptr(dt), _lib.ptr(dy), _lib.ptr(dscales),
+            _lib.ptr(logp_sum), B, _lib.current_stream(dev)))
+    return logp, dt, dy, dscales
+
+
+class _KmnLogProb(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, y, locs, scales):
+        ctx.save_for_backward(t, y, locs, scales)
+        return kmn_forward(t, y, locs, scales)
+
+    @staticmethod
+    def backward(ctx, g):
+        t, y, locs, scales = ctx.saved_tensors
+        need_dy = ctx.needs_input_grad[1]
+        B = g.shape[0]
+        t_rows = t.expand(B, t.shape[1]).contiguous() if (t.shape[0] == 1 and B != 1) else t
+        y_rows = y.expand(B, y.shape[1]).contiguous() if (need_dy and y.shape[0] != B) else y
+        _, dt, dy, dsc = kmn_forward_backward(t_rows, y_rows, locs, scales, g_logp=g.contiguous(),
+                                              want_dy=need_dy, want_dscales=ctx.needs_input_grad[3])
+        if t.shape[0] == 1 and B != 1:
+            dt = dt.sum(0, keepdim=True)
+        if need_dy and y.shape[0] != B:
+            dy = dy.sum(0, keepdim=True)
+        if dsc is not None:
+            dsc = dsc.reshape(scales.shape)
+        return (dt if ctx.needs_input_grad[0] else None), (dy if need_dy else None), None, dsc
+
+
+def kmn_log_prob(t, y, locs, scales):
+    t = _as_f32_cuda(t, "t")
+    y = _as_f32_cuda(y, "y", device=t.device)
+    return _KmnLogProb.apply(t, y, _as_f32_cuda(locs, "locs", device=t.device),
+                             _as_f32_cuda(scales, "scales", device=t.device))
+
+
+# ----------------------------------------------------------------------------- epilogue
+def logmeanexp_draws(logp_sb):
+    """[S, B] -> [B]: logsumexp over posterior draws minus log S (BayesianNNEstimator.score)."""
+    lib = _lib.load()
+    x = _as_f32_cuda(logp_sb, "logp_sb")
+    S, B = x.shape
+    out = torch.empty(B, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.nfn_logmeanexp_draws(_lib.ptr(x), S, B, _lib.ptr(out), _lib.current_stream(x.device)))
+    return out
+
+
+def launch_count_reset():
+    return int(_lib.load().nfn_launch_count_reset())
+
+
+def set_math_mode(accurate):
+    _lib.check(_lib.load().nfn_set_math_mode(1 if accurate else 0))

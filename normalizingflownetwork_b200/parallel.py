@@ -1,0 +1,88 @@
+"""Data-parallel plumbing for the hot path: one process per GPU, rows sharded, no
+data-path collective.  The only exchange a training step needs is one small all-reduce of
+[bias-gradient column sums of dt | sum of log-probs | MLP gradients]; the
+density-grid scoring path needs none.  Works with the ``nccl`` backend on GPUs and with
+``gloo`` on CPU tensors (used by the world_size-2 tests of this host-side logic).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def env_rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(
+        os.environ.get("LOCAL_RANK", "0"))
+
+
+def init_process_group(backend=None):
+    """Initialise torch.distributed from the torchrun environment (no-op for world size 1)."""
+    rank, world, local_rank = env_rank_world()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kwargs = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            kwargs["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kwargs)
+    return rank, world, local_rank
+
+
+def shard_rows(n_rows, rank, world):
+    """Contiguous row block [lo, hi) of rank ``rank``; block sizes differ by at most one and
+    every block boundary is the same on every rank."""
+    base, rem = divmod(int(n_rows), int(world))
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+class PackedAllReduce:
+    """One flat float64 buffer = [segments...]; a single all-reduce(sum) per step.
+
+    ``pack`` copies the given tensors (any float dtype) into the buffer, ``reduce`` sums it
+    across ranks in place, ``unpack`` returns float64 views in the original shapes.  Messages
+    are a few KB, i.e. latency-bound: one collective, no bucketing.
+    """
+
+    def __init__(self, shapes, device):
+        self.shapes = [tuple(s) for s in shapes]
+        self.sizes = [int(torch.Size(s).numel()) for s in self.shapes]
+        self.buf = torch.zeros(sum(self.sizes), dtype=torch.float64, device=device)
+
+    def pack(self, tensors):
+        assert len(tensors) == len(self.sizes)
+        off = 0
+        for t, n in zip(tensors, self.sizes):
+            self.buf[off: off + n].copy_(t.reshape(-1))
+            off += n
+        return self.buf
+
+    def reduce(self):
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
+        return self.buf
+
+    def unpack(self):
+        out, off = [], 0
+        for s, n in zip(self.shapes, self.sizes):
+            out.append(self.buf[off: off + n].view(s))
+            off += n
+        return out
+
+
+def barrier():
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+
+
+def max_over_ranks(value, device):
+    """Max of a python float over ranks (timings are reported as the slowest rank)."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

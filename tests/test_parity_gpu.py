@@ -1,0 +1,390 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star; fp32 kernels vs float64 oracle on identical fp32 inputs):
+  log-prob   |delta| <= 1e-5 * max(1, |logp|)
+  gradients  |delta| <= 1e-4 * max(1, |g|)
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import analytic_np as an
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LOGP_RTOL = 1e-5
+GRAD_RTOL = 1e-4
+
+CONFIG_CHAINS = {
+    "cfg1": (["radial"] * 3, 1, True),
+    "cfg2": (["planar", "radial", "affine"] * 3 + ["planar"], 2, True),
+    "cfg3": (["radial", "planar"] * 8, 4, True),
+    "cfg4": (["radial"] * 5, 1, True),
+}
+
+
+def rel_err(got, ref):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    return np.abs(got - ref) / np.maximum(1.0, np.abs(ref))
+
+
+def assert_logp(got, ref, tol=LOGP_RTOL, what=""):
+    e = rel_err(got, ref)
+    assert np.all(np.isfinite(np.asarray(got))), what
+    assert e.max() <= tol, "%s logp rel err %.3e at %d" % (what, e.max(), int(e.argmax()))
+
+
+def assert_grad(got, ref, tol=GRAD_RTOL, what=""):
+    e = rel_err(got, ref)
+    assert np.all(np.isfinite(np.asarray(got))), what
+    assert e.max() <= tol, "%s grad rel err %.3e at %s" % (what, e.max(), np.unravel_index(e.argmax(), e.shape))
+
+
+@pytest.fixture(params=["fast", "accurate"])
+def math_mode(request, nfn_lib):
+    from normalizingflownetwork_b200 import functional as F
+
+    F.set_math_mode(request.param == "accurate")
+    yield request.param
+    F.set_math_mode(False)
+
+
+@pytest.fixture(params=["specialized", "generic"])
+def kernel_path(request):
+    if request.param == "generic":
+        os.environ["NFN_B200_FORCE_GENERIC"] = "1"
+    yield request.param
+    os.environ.pop("NFN_B200_FORCE_GENERIC", None)
+
+
+def dev(x, device):
+    return torch.tensor(np.asarray(x, dtype=np.float32), device=device)
+
+
+# ----------------------------------------------------------------------------- golden fixtures
+def test_known_answers_single_flow(cuda_device, nfn_lib):
+    from normalizingflownetwork_b200 import FLOWS
+
+    ka = json.load(open(os.path.join(GOLDEN, "known_answers.json")))
+    for c in ka["single_flow"]:
+        d = c["n_dims"]
+        cls = FLOWS[c["flow"]]
+        flow = cls(torch.ones((10, cls.get_param_size(d)), device=cuda_device), d)
+        z = torch.full((10, d), c["z"], device=cuda_device)
+        fwd = flow.forward(z).cpu().numpy()
+        fldj = flow._forward_log_det_jacobian(z).cpu().numpy()
+        assert fwd.shape == (10, d) and fldj.shape == (10,)
+        np.testing.assert_allclose(fwd, np.tile(c["forward"], (10, 1)), rtol=2e-6, atol=2e-7)
+        # the accurate path keeps tiny log-dets (4.26e-7 for planar d=4, t=1, z=1) relative-accurate
+        np.testing.assert_allclose(fldj, c["fldj"], rtol=2e-3, atol=3e-7)
+        # [1, d] z broadcasts against the batch (reference tests/test_flows.py:24-29)
+        assert flow.forward(z[:1]).shape == (10, d)
+        assert flow._forward_log_det_jacobian(z[:1]).shape == (10,)
+
+
+def test_known_answers_layer(cuda_device, nfn_lib, math_mode, kernel_path):
+    from normalizingflownetwork_b200 import InverseNormalizingFlowLayer
+
+    ka = json.load(open(os.path.join(GOLDEN, "known_answers.json")))
+    for c in ka["layer"]:
+        layer = InverseNormalizingFlowLayer(c["flow_types"], c["n_dims"], c["trainable_base_dist"])
+        P = layer.get_total_param_size()
+        dist = layer(torch.full((3, P), c["t"], device=cuda_device))
+        lp = dist.log_prob(torch.full((3, c["n_dims"]), c["y"], device=cuda_device)).cpu().numpy()
+        assert_logp(lp, np.full(3, c["log_prob"]), what=str(c))
+
+
+def test_golden_chain_vectors(cuda_device, nfn_lib, math_mode, kernel_path):
+    from normalizingflownetwork_b200 import functional as F
+
+    cases = json.load(open(os.path.join(GOLDEN, "chain_vectors.json")))
+    for c in cases:
+        ft, d, tb = c["flow_types"], c["n_dims"], c["trainable_base_dist"]
+        t, y, up = dev(c["t"], cuda_device), dev(c["y"], cuda_device), dev(c["upstream"], cuda_device)
+        if t.shape[1] == 0:
+            continue
+        tag = "%s sigma=%s %s/%s" % (c["name"], c["sigma"], math_mode, kernel_path)
+        # at sigma=1 the planar determinant can get small: the bar is stated for sigma=0.5
+        ltol = LOGP_RTOL if c["sigma"] <= 0.5 else 5e-5
+        gtol = GRAD_RTOL if c["sigma"] <= 0.5 else 1e-3
+        lp = F.chain_forward(t, y, ft, d, tb)
+        assert_logp(lp.cpu().numpy(), c["log_prob"], ltol, tag)
+        lp2, dt, dy = F.chain_forward_backward(t, y, ft, d, tb, g_logp=up, want_dy=True)
+        assert torch.equal(lp, lp2), tag
+        assert_grad(dt.cpu().numpy(), c["dt"], gtol, tag + " dt")
+        assert_grad(dy.cpu().numpy(), c["dy"], gtol, tag + " dy")
+        lb = F.chain_forward(t, y[3:4], ft, d, tb)
+        assert_logp(lb.cpu().numpy(), c["log_prob_y_row3_broadcast"], ltol, tag + " bcast")
+
+
+# ----------------------------------------------------------------------------- seeded parity
+@pytest.mark.parametrize("cfg", sorted(CONFIG_CHAINS))
+@pytest.mark.parametrize("B", [1, 127, 129, 4096 + 37])
+def test_chain_vs_oracle_ragged(cuda_device, nfn_lib, math_mode, kernel_path, cfg, B):
+    from normalizingflownetwork_b200 import functional as F
+
+    ft, d, tb = CONFIG_CHAINS[cfg]
+    rng = np.random.default_rng(22 + B)
+    P = an.layout(ft, d, tb)[1]
+    t = rng.normal(0, 0.5, (B, P)).astype(np.float32)
+    y = rng.normal(0, 1.0, (B, d)).astype(np.float32)
+    up = rng.normal(0, 1.0, (B,)).astype(np.float32)
+    ref_lp, ref_dt, ref_dy = an.chain_forward_backward(t, y, ft, d, tb, upstream=up * 0.5)
+    lp, dt, dy = F.chain_forward_backward(dev(t, cuda_device), dev(y, cuda_device), ft, d, tb,
+                                          g_logp=dev(up, cuda_device), g_scale=0.5, want_dy=True)
+    tag = "%s B=%d %s/%s" % (cfg, B, math_mode, kernel_path)
+    assert_logp(lp.cpu().numpy(), ref_lp, what=tag)
+    assert_grad(dt.cpu().numpy(), ref_dt, what=tag + " dt")
+    assert_grad(dy.cpu().numpy(), ref_dy, what=tag + " dy")
+    assert_logp(F.chain_forward(dev(t, cuda_device), dev(y, cuda_device), ft, d, tb).cpu().numpy(), ref_lp,
+                what=tag + " fwd")
+
+
+@pytest.mark.parametrize("cfg", sorted(CONFIG_CHAINS))
+def test_chain_vs_oracle_2p16(cuda_device, nfn_lib, cfg):
+    """2^16 rows, t ~ N(0, 0.5^2), y ~ N(0, 1), seed 22 -- the BASELINE.md parity protocol."""
+    from normalizingflownetwork_b200 import functional as F
+
+    ft, d, tb = CONFIG_CHAINS[cfg]
+    B = 1 << 16
+    rng = np.random.default_rng(22)
+    P = an.layout(ft, d, tb)[1]
+    t = rng.normal(0, 0.5, (B, P)).astype(np.float32)
+    y = rng.normal(0, 1.0, (B, d)).astype(np.float32)
+    ref_lp, ref_dt, _ = an.chain_forward_backward(t, y, ft, d, tb, upstream=-1.0)
+    lsum = torch.zeros(1, dtype=torch.float64, device=cuda_device)
+    col = torch.zeros(P, dtype=torch.float32, device=cuda_device)
+    lp, dt, _ = F.chain_forward_backward(dev(t, cuda_device), dev(y, cuda_device), ft, d, tb, g_scale=-1.0,
+                                         logp_sum=lsum, dt_colsum=col)
+    assert_logp(lp.cpu().numpy(), ref_lp, what=cfg)
+    assert_grad(dt.cpu().numpy(), ref_dt, what=cfg)
+    assert abs(lsum.item() - ref_lp.sum()) <= 1e-5 * np.abs(ref_lp).sum()
+    np.testing.assert_allclose(col.cpu().numpy(), ref_dt.sum(0), rtol=1e-3, atol=1e-2)
+
+
+def test_empty_and_zero_flow_chains(cuda_device, nfn_lib, kernel_path):
+    from normalizingflownetwork_b200 import functional as F
+
+    # B = 0
+    lp = F.chain_forward(torch.zeros((0, 11), device=cuda_device), torch.zeros((0, 1), device=cuda_device),
+                         ["radial"] * 3, 1, True)
+    assert lp.shape == (0,)
+    # n_flows = 0 with trainable base (reference tests/test_bayesian_estimator.py:45-61)
+    rng = np.random.default_rng(3)
+    t = rng.normal(0, 1, (300, 4)).astype(np.float32)
+    y = rng.normal(0, 1, (300, 2)).astype(np.float32)
+    ref_lp, ref_dt, ref_dy = an.chain_forward_backward(t, y, [], 2, True)
+    lp, dt, dy = F.chain_forward_backward(dev(t, cuda_device), dev(y, cuda_device), [], 2, True, want_dy=True)
+    assert_logp(lp.cpu().numpy(), ref_lp)
+    assert_grad(dt.cpu().numpy(), ref_dt)
+    assert_grad(dy.cpu().numpy(), ref_dy)
+    # n_flows = 0 without base parameters: P = 0, standard normal
+    y1 = rng.normal(0, 1, (257, 3)).astype(np.float32)
+    lp = F.chain_forward(torch.zeros((257, 0), device=cuda_device), dev(y1, cuda_device), [], 3, False)
+    ref = -0.5 * (y1.astype(np.float64) ** 2).sum(1) - 1.5 * np.log(2 * np.pi)
+    assert_logp(lp.cpu().numpy(), ref)
+
+
+def test_long_generic_chain_max_dims(cuda_device, nfn_lib):
+    """K = 64 flows, d = 8: the descriptor's maximum, served by the generic kernel."""
+    from normalizingflownetwork_b200 import functional as F
+
+    ft = (["planar", "radial", "affine", "radial"] * 16)[:64]
+    d, tb = 8, True
+    assert not F.chain_is_specialized(ft, d, tb)
+    rng = np.random.default_rng(5)
+    P = an.layout(ft, d, tb)[1]
+    t = rng.normal(0, 0.3, (513, P)).astype(np.float32)
+    y = rng.normal(0, 1.0, (513, d)).astype(np.float32)
+    ref_lp, ref_dt, ref_dy = an.chain_forward_backward(t, y, ft, d, tb)
+    lp, dt, dy = F.chain_forward_backward(dev(t, cuda_device), dev(y, cuda_device), ft, d, tb, want_dy=True)
+    assert_logp(lp.cpu().numpy(), ref_lp, tol=5e-5)
+    assert_grad(dt.cpu().numpy(), ref_dt, tol=1e-3)
+    assert_grad(dy.cpu().numpy(), ref_dy, tol=1e-3)
+
+
+def test_row_independence_bit_exact(cuda_device, nfn_lib):
+    """Permuting rows permutes outputs bit-for-bit (reference tests/test_flows.py:31-41)."""
+    from normalizingflownetwork_b200 import functional as F
+
+    ft, d, tb = CONFIG_CHAINS["cfg2"]
+    g = torch.Generator(device="cpu").manual_seed(22)
+    B = 5000
+    t = (torch.randn((B, 48), generator=g) * 0.5).to(cuda_device)
+    y = torch.randn((B, d), generator=g).to(cuda_device)
+    perm = torch.randperm(B, generator=g).to(cuda_device)
+    lp, dt, _ = F.chain_forward_backward(t, y, ft, d, tb)
+    lp2, dt2, _ = F.chain_forward_backward(t[perm].contiguous(), y[perm].contiguous(), ft, d, tb)
+    assert torch.equal(lp[perm], lp2)
+    assert torch.equal(dt[perm], dt2)
+
+
+def test_autograd_function_matches_fused(cuda_device, nfn_lib):
+    from normalizingflownetwork_b200 import InverseNormalizingFlowLayer
+
+    ft, d, tb = CONFIG_CHAINS["cfg2"]
+    rng = np.random.default_rng(9)
+    t = dev(rng.normal(0, 0.5, (1000, 48)), cuda_device).requires_grad_(True)
+    y = dev(rng.normal(0, 1.0, (1000, d)), cuda_device).requires_grad_(True)
+    dist = InverseNormalizingFlowLayer(ft, d, tb)(t)
+    loss = -dist.log_prob(y).mean()
+    loss.backward()
+    ref_lp, ref_dt, ref_dy = an.chain_forward_backward(t.detach().cpu().numpy(), y.detach().cpu().numpy(), ft, d,
+                                                       tb, upstream=-1.0 / 1000)
+    assert abs(loss.item() + ref_lp.mean()) < 1e-5 * max(1.0, abs(ref_lp.mean()))
+    assert_grad(t.grad.cpu().numpy() * 1000, ref_dt * 1000)
+    assert_grad(y.grad.cpu().numpy() * 1000, ref_dy * 1000)
+
+
+def test_host_pipeline_matches_device(cuda_device, nfn_lib):
+    import ctypes
+
+    from normalizingflownetwork_b200 import _lib
+    from normalizingflownetwork_b200 import functional as F
+
+    ft, d, tb = CONFIG_CHAINS["cfg2"]
+    B, P = 300_001, 48  # > 3 chunks of the pipeline, ragged tail
+    g = torch.Generator(device="cpu").manual_seed(22)
+    t = (torch.randn((B, P), generator=g) * 0.5).pin_memory()
+    y = torch.randn((B, d), generator=g).pin_memory()
+    logp = torch.empty(B).pin_memory()
+    dt = torch.empty((B, P)).pin_memory()
+    col = torch.empty(P)
+    lsum = ctypes.c_double(0.0)
+    desc = _lib.make_desc(ft, d, tb)
+    with torch.cuda.device(cuda_device):
+        _lib.check(nfn_lib.nfn_chain_forward_backward_host(
+            ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), B, None, ctypes.c_float(-1.0 / B), _lib.ptr(logp),
+            _lib.ptr(dt), ctypes.byref(lsum), _lib.ptr(col), B))
+    lp_d, dt_d, _ = F.chain_forward_backward(t.to(cuda_device), y.to(cuda_device), ft, d, tb, g_scale=-1.0 / B)
+    assert torch.equal(logp, lp_d.cpu())
+    assert torch.equal(dt, dt_d.cpu())
+    assert abs(lsum.value - lp_d.double().sum().item()) < 1e-6 * B
+    np.testing.assert_allclose(col.numpy(), dt_d.sum(0).cpu().numpy(), rtol=1e-3, atol=1e-5)
+    logp2 = torch.empty(B).pin_memory()
+    with torch.cuda.device(cuda_device):
+        _lib.check(nfn_lib.nfn_chain_forward_host(ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), B,
+                                                  _lib.ptr(logp2), B))
+        _lib.check(nfn_lib.nfn_host_release())
+    assert torch.equal(logp2, lp_d.cpu())
+
+
+def test_full_size_properties_cfg2(cuda_device, nfn_lib):
+    """BASELINE config 2 at full size (2^20 rows): size-independent properties."""
+    from normalizingflownetwork_b200 import functional as F
+
+    ft, d, tb = CONFIG_CHAINS["cfg2"]
+    B, P = 1 << 20, 48
+    g = torch.Generator(device=cuda_device).manual_seed(22)
+    t = torch.randn((B, P), generator=g, device=cuda_device) * 0.5
+    y = torch.randn((B, d), generator=g, device=cuda_device)
+    lsum = torch.zeros(1, dtype=torch.float64, device=cuda_device)
+    col = torch.zeros(P, device=cuda_device)
+    lp, dt, _ = F.chain_forward_backward(t, y, ft, d, tb, g_scale=-1.0 / B, logp_sum=lsum, dt_colsum=col)
+    assert torch.isfinite(lp).all() and torch.isfinite(dt).all()
+    assert abs(lsum.item() - lp.double().sum().item()) < 1e-7 * B
+    np.testing.assert_allclose(col.cpu().numpy(), dt.double().sum(0).cpu().numpy(), rtol=2e-3, atol=1e-6)
+    # linearity in the cotangent: scaling g_scale scales dt exactly by a power of two
+    _, dt2, _ = F.chain_forward_backward(t, y, ft, d, tb, g_scale=-2.0 / B)
+    assert torch.equal(dt2, dt * 2)
+    # forward-only kernel and fused kernel agree bit for bit on logp
+    assert torch.equal(F.chain_forward(t, y, ft, d, tb), lp)
+    # a random sample of rows against the float64 oracle
+    idx = torch.randint(0, B, (4096,), generator=g, device=cuda_device)
+    ref_lp, ref_dt, _ = an.chain_forward_backward(t[idx].cpu().numpy(), y[idx].cpu().numpy(), ft, d, tb,
+                                                  upstream=-1.0)
+    assert_logp(lp[idx].cpu().numpy(), ref_lp)
+    assert_grad((dt[idx] * B).cpu().numpy(), ref_dt)
+
+
+# ----------------------------------------------------------------------------- mixture heads
+def test_golden_mixture_vectors(cuda_device, nfn_lib, math_mode):
+    from normalizingflownetwork_b200 import functional as F
+
+    mv = json.load(open(os.path.join(GOLDEN, "mixture_vectors.json")))
+    for c in mv["mdn"]:
+        K, d = c["n_centers"], c["n_dims"]
+        t, y, up = dev(c["t"], cuda_device), dev(c["y"], cuda_device), dev(c["upstream"], cuda_device)
+        tag = "%s sigma=%s %s" % (c["name"], c["sigma"], math_mode)
+        assert_logp(F.mdn_forward(t, y, K, d).cpu().numpy(), c["log_prob"], what=tag)
+        lp, dt, dy = F.mdn_forward_backward(t, y, K, d, g_logp=up, want_dy=True)
+        assert_logp(lp.cpu().numpy(), c["log_prob"], what=tag)
+        assert_grad(dt.cpu().numpy(), c["dt"], what=tag + " dt")
+        assert_grad(dy.cpu().numpy(), c["dy"], what=tag + " dy")
+    for c in mv["kmn"]:
+        t, y, up = dev(c["t"], cuda_device), dev(c["y"], cuda_device), dev(c["upstream"], cuda_device)
+        locs, scales = dev(c["locs"], cuda_device), dev(c["scales"], cuda_device)
+        tag = "%s %s" % (c["name"], math_mode)
+        assert_logp(F.kmn_forward(t, y, locs, scales).cpu().numpy(), c["log_prob"], what=tag)
+        lp, dt, dy, dsc = F.kmn_forward_backward(t, y, locs, scales, g_logp=up, want_dy=True)
+        assert_logp(lp.cpu().numpy(), c["log_prob"], what=tag)
+        assert_grad(dt.cpu().numpy(), c["dt"], what=tag + " dt")
+        assert_grad(dy.cpu().numpy(), c["dy"], what=tag + " dy")
+        assert_grad(dsc.cpu().numpy(), c["dscales"], what=tag + " dscales")
+
+
+@pytest.mark.parametrize("K,d,B", [(20, 2, 1 << 15), (3, 1, 1000), (5, 5, 4097), (7, 3, 129), (1, 1, 5)])
+def test_mdn_vs_oracle(cuda_device, nfn_lib, math_mode, K, d, B):
+    from normalizingflownetwork_b200 import functional as F
+
+    rng = np.random.default_rng(22)
+    P = 2 * K * d + K
+    t = rng.normal(0, 0.5, (B, P)).astype(np.float32)
+    y = rng.normal(0, 1.0, (B, d)).astype(np.float32)
+    ref_lp, ref_dt, ref_dy = an.mdn_forward_backward(t, y, K, d, upstream=-1.0)
+    lsum = torch.zeros(1, dtype=torch.float64, device=cuda_device)
+    col = torch.zeros(P, device=cuda_device)
+    lp, dt, dy = F.mdn_forward_backward(dev(t, cuda_device), dev(y, cuda_device), K, d, g_scale=-1.0, want_dy=True,
+                                        logp_sum=lsum, dt_colsum=col)
+    assert_logp(lp.cpu().numpy(), ref_lp)
+    assert_grad(dt.cpu().numpy(), ref_dt)
+    assert_grad(dy.cpu().numpy(), ref_dy)
+    assert abs(lsum.item() - ref_lp.sum()) <= 1e-5 * np.abs(ref_lp).sum()
+    np.testing.assert_allclose(col.cpu().numpy(), ref_dt.sum(0), rtol=1e-3, atol=1e-2)
+    assert_logp(F.mdn_forward(dev(t, cuda_device), dev(y[:1], cuda_device), K, d).cpu().numpy(),
+                an.mdn_forward_backward(t, y[:1], K, d, need_grad=False))
+
+
+@pytest.mark.parametrize("M,d,B", [(20, 1, 5000), (60, 2, 1 << 14), (100, 3, 257)])
+def test_kmn_vs_oracle(cuda_device, nfn_lib, math_mode, M, d, B):
+    from normalizingflownetwork_b200 import functional as F
+
+    rng = np.random.default_rng(22)
+    t = rng.normal(0, 1.0, (B, M)).astype(np.float32)
+    y = rng.normal(0, 1.0, (B, d)).astype(np.float32)
+    locs = rng.normal(0, 1.0, (M, d)).astype(np.float32)
+    scales = np.where(np.arange(M) < M // 2, -0.357, 0.45).astype(np.float32)  # negative bandwidth, App. B.7
+    up = rng.normal(0, 1.0, (B,)).astype(np.float32)
+    ref_lp, ref_dt, ref_ds, ref_dy = an.kmn_forward_backward(t, y, locs, scales, upstream=up)
+    lp, dt, dy, dsc = F.kmn_forward_backward(dev(t, cuda_device), dev(y, cuda_device), dev(locs, cuda_device),
+                                             dev(scales, cuda_device), g_logp=dev(up, cuda_device), want_dy=True)
+    assert_logp(lp.cpu().numpy(), ref_lp)
+    assert_grad(dt.cpu().numpy(), ref_dt)
+    assert_grad(dy.cpu().numpy(), ref_dy)
+    np.testing.assert_allclose(dsc.cpu().numpy(), ref_ds, rtol=2e-3, atol=2e-3 * np.abs(ref_ds).max())
+
+
+def test_logmeanexp_draws(cuda_device, nfn_lib):
+    from normalizingflownetwork_b200 import functional as F
+
+    rng = np.random.default_rng(22)
+    x = rng.normal(-3, 2, (50, 10_001)).astype(np.float32)
+    ref = np.log(np.mean(np.exp(x.astype(np.float64)), axis=0))
+    out = F.logmeanexp_draws(dev(x, cuda_device)).cpu().numpy()
+    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_errors_are_loud(cuda_device, nfn_lib):
+    from normalizingflownetwork_b200 import InverseNormalizingFlowLayer
+    from normalizingflownetwork_b200 import functional as F
+
+    with pytest.raises(AssertionError):
+        F.chain_forward(torch.zeros((4, 12), device=cuda_device), torch.zeros((4, 1), device=cuda_device),
+                        ["radial"] * 3, 1, True)
+    with pytest.raises(RuntimeError):  # CPU tensors are rejected: no fallback
+        InverseNormalizingFlowLayer(["radial"], 1, False)(torch.zeros((4, 3))).log_prob(torch.zeros((4, 1)))
