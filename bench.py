@@ -43,8 +43,11 @@ CONFIGS = {
     "cfg3": (["radial", "planar"] * 8, 4, True, 1 << 23, False),
     "cfg4": (["radial"] * 5, 1, True, 1 << 20, True),
     "cfg1": (["radial"] * 3, 1, True, 2048, True),
+    # MDN head: flow_types slot holds ("mdn", n_centers)
+    "cfg5": (("mdn", 20), 2, None, 1 << 22, True),
 }
 WORKLOAD_NAMES = {
+    "cfg5": "MDN 20-component Gaussian mixture head, 2-D y, P=100, batch 2^22 per GPU, logsumexp log-lik fwd+bwd",
     "cfg2": "NFN 10 flows (planar,radial,affine)x3+planar, 2-D y, P=48, batch 2^20 per GPU, log-prob fwd+bwd",
     "cfg3": "NFN 16 flows (radial,planar)x8, 4-D y, P=128, 2^23 (x,y) pairs per GPU, density-grid log-prob fwd",
     "cfg4": "Bayesian NFN 5 radial flows, 1-D y, P=17, S*B = 2^20 rows per GPU, log-prob fwd+bwd",
@@ -54,7 +57,13 @@ METRIC = "flow log-prob fwd+bwd samples/sec"
 UNIT = "samples/s"
 
 
+def is_mdn(flow_types):
+    return isinstance(flow_types, tuple) and len(flow_types) == 2 and flow_types[0] == "mdn"
+
+
 def param_size(flow_types, d, tb):
+    if is_mdn(flow_types):
+        return 2 * flow_types[1] * d + flow_types[1]
     sz = {"planar": 2 * d + 1, "radial": d + 2, "affine": 2 * d}
     return sum(sz[f] for f in flow_types) + (2 * d if tb else 0)
 
@@ -81,60 +90,79 @@ def load_traffic(cfg):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons polled through NVML in a background thread DURING the
+    timed region (the region is a few milliseconds, too short for `nvidia-smi -lms`)."""
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
-        self.path = None
+        self.samples = []  # (perf_counter, sm_mhz, reasons bitmask)
+        self.stop_flag = False
+        self.thread = None
+        self.h = None
+        self.max_mhz = None
 
     def start(self):
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+            import threading
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        try:
-            self.proc.terminate()
-            self.proc.wait(timeout=5)
-            self.f.close()
-            sm, mx, reasons = [], [], set()
-            for line in open(self.path):
-                parts = [x.strip() for x in line.split(",")]
-                if len(parts) < 9:
-                    continue
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
                 try:
-                    sm.append(float(parts[1]))
-                    mx.append(float(parts[2]))
-                except ValueError:
-                    continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                     parts[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-            if sm:
-                out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                       "samples": len(sm)}
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        mhz = pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+                        rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                        self.samples.append((time.perf_counter(), float(mhz), int(rs)))
+                    except Exception:
+                        pass
+                    time.sleep(0.0005)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.thread = None
+
+    def stop(self, t0=None, t1=None):
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        if self.thread is None:
+            return out
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        nv = self.nv
+        inside = [s for s in self.samples if t0 is not None and t0 <= s[0] <= t1]
+        window = "timed region"
+        if len(inside) < 3:
+            inside = self.samples
+            window = "warm-up + timed region (timed region too short for >= 3 samples)"
+        if inside:
+            names = {
+                "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            }
+            mask = 0
+            for s in inside:
+                mask |= s[2]
+            out = {"sm_mhz": statistics.median(s[1] for s in inside), "sm_max_mhz": self.max_mhz,
+                   "reasons": sorted(k for k, v in names.items() if mask & v), "samples": len(inside),
+                   "window": window}
+        try:
+            nv.nvmlShutdown()
         except Exception:
             pass
-        finally:
-            try:
-                os.remove(self.path)
-            except Exception:
-                pass
         return out
 
 
@@ -151,14 +179,19 @@ def cpu_pass_fn(cfg, rows, seed=22):
     t = (torch.randn((rows, P), generator=g) * 0.5)
     y = torch.randn((rows, d), generator=g)
 
+    def logp_fn(tt):
+        if is_mdn(ft):
+            return fo.mdn_log_prob(tt, y, ft[1], d)
+        return fo.chain_log_prob(tt, y, ft, d, tb)
+
     def one_pass():
         if bwd:
             tt = t.detach().requires_grad_(True)
-            nll = -fo.chain_log_prob(tt, y, ft, d, tb).mean()
+            nll = -logp_fn(tt).mean()
             nll.backward()
-            return float(nll)
+            return float(nll.detach())
         with torch.no_grad():
-            return float(fo.chain_log_prob(t, y, ft, d, tb).mean())
+            return float(logp_fn(t).mean())
 
     return one_pass
 
@@ -238,8 +271,9 @@ def run_ours(args):
     if args.rows:
         B = args.rows
     P = param_size(ft, d, tb)
-    desc = _lib.make_desc(ft, d, tb)
-    specialized = bool(lib.nfn_chain_is_specialized(ctypes.byref(desc)))
+    mdn = is_mdn(ft)
+    desc = None if mdn else _lib.make_desc(ft, d, tb)
+    specialized = True if mdn else bool(lib.nfn_chain_is_specialized(ctypes.byref(desc)))
     K, W = args.steps, args.warmup
 
     gen = torch.Generator(device=device).manual_seed(22 + rank)
@@ -248,33 +282,41 @@ def run_ours(args):
     logp = torch.empty(B, device=device)
     dt = torch.empty((B, P), device=device) if bwd else None
     lsum = torch.zeros(1, dtype=torch.float64, device=device)
-    col = torch.zeros(P, device=device) if (bwd and world > 1) else None
-    packed = parallel.PackedAllReduce([(P,), (1,)], device) if (bwd and world > 1) else None
+    col = torch.zeros(P, device=device) if (bwd and world > 1 and not mdn) else None
+    packed = parallel.PackedAllReduce([(P,), (1,)], device) if col is not None else None
     g_scale = -1.0 / (B * world)
     stream = _lib.current_stream(device)
 
-    def step():
-        if bwd:
+    def kernel():
+        if mdn:
+            _lib.check(lib.nfn_mdn_forward_backward(
+                ft[1], d, _lib.ptr(t), _lib.ptr(y), B, None, ctypes.c_float(g_scale), _lib.ptr(logp),
+                _lib.ptr(dt), None, _lib.ptr(lsum), None, B, stream))
+        elif bwd:
             _lib.check(lib.nfn_chain_forward_backward(
                 ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), B, None, ctypes.c_float(g_scale), _lib.ptr(logp),
                 _lib.ptr(dt), None, _lib.ptr(lsum), _lib.ptr(col), B, stream))
-            if packed is not None:
-                packed.pack([col, lsum])
-                packed.reduce()
         else:
             _lib.check(lib.nfn_chain_forward(ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), B, _lib.ptr(logp), B,
                                              stream))
 
+    def step():
+        kernel()
+        if packed is not None:
+            packed.pack([col, lsum])
+            packed.reduce()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(W):
         step()
     torch.cuda.synchronize()
     parallel.barrier()
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     lib.nfn_launch_count_reset()
+    wall0 = time.perf_counter()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
            torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     t_start = torch.cuda.Event(enable_timing=True)
@@ -282,13 +324,7 @@ def run_ours(args):
     t_start.record()
     for i in range(K):
         ev[i][0].record()
-        if bwd:
-            _lib.check(lib.nfn_chain_forward_backward(
-                ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), B, None, ctypes.c_float(g_scale), _lib.ptr(logp),
-                _lib.ptr(dt), None, _lib.ptr(lsum), _lib.ptr(col), B, stream))
-        else:
-            _lib.check(lib.nfn_chain_forward(ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), B, _lib.ptr(logp), B,
-                                             stream))
+        kernel()
         ev[i][1].record()
         if packed is not None:
             packed.pack([col, lsum])
@@ -302,7 +338,7 @@ def run_ours(args):
     total_ms = parallel.max_over_ranks(t_start.elapsed_time(t_end), device)
     kern_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev)
     kern_ms = parallel.max_over_ranks(kern_ms, device)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, time.perf_counter()) if rank == 0 else None
     ms_per_step = total_ms / K
     value = B * world * K / (total_ms * 1e-3)
 
@@ -316,7 +352,11 @@ def run_ours(args):
     h_sum = ctypes.c_double(0.0)
 
     def e2e_step():
-        if bwd:
+        if mdn:
+            _lib.check(lib.nfn_mdn_forward_backward_host(
+                ft[1], d, _lib.ptr(h_t), _lib.ptr(h_y), B, None, ctypes.c_float(g_scale), _lib.ptr(h_logp),
+                _lib.ptr(h_dt), ctypes.byref(h_sum), B))
+        elif bwd:
             _lib.check(lib.nfn_chain_forward_backward_host(
                 ctypes.byref(desc), _lib.ptr(h_t), _lib.ptr(h_y), B, None, ctypes.c_float(g_scale),
                 _lib.ptr(h_logp), _lib.ptr(h_dt), ctypes.byref(h_sum), None, B))
@@ -363,7 +403,8 @@ def run_ours(args):
             "t_sigma": 0.5, "seed": 22,
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "nfn_chain_forward_backward_host" if bwd else "nfn_chain_forward_host",
+                "steps": e2e_steps, "api": ("nfn_mdn_forward_backward_host" if mdn else
+                        "nfn_chain_forward_backward_host" if bwd else "nfn_chain_forward_host"),
                 "host_equals_device_bitwise": same},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
