@@ -105,18 +105,22 @@ struct Span {
 };
 
 // ---------------------------------------------------------------- async copy helpers
-NFN_DEVI void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+NFN_DEVI unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+NFN_DEVI void cp_async16(unsigned smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
-NFN_DEVI void cp_async4(void* smem_dst, const void* gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+NFN_DEVI void cp_async4(unsigned smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 NFN_DEVI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 NFN_DEVI void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+NFN_DEVI float4 lds_f4(unsigned smem_src) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_src));
+  return v;
+}
 NFN_DEVI void st_stream_f4(float* gdst, const float4& v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gdst), "f"(v.x), "f"(v.y),
                "f"(v.z), "f"(v.w)
@@ -124,54 +128,101 @@ NFN_DEVI void st_stream_f4(float* gdst, const float4& v) {
 }
 
 // Tile geometry shared by the chain and mixture kernels: tile of T rows x P floats in
-// global (contiguous), T x S floats in smem.
+// global (contiguous), T x S floats in smem.  16-byte chunk q of the tile (q = e / 4 for
+// flat element e) sits at byte q*16 in global and, in smem, at
+//   dense  (S == P): byte q*16
+//   padded (S == P+4, P % 4 == 0): row = q / (P/4), c = q % (P/4) -> byte (row*S + 4c)*4.
+// Thread tid handles chunks tid, tid+T, ...: (row, c) advance incrementally, no division
+// in the loop.  Full tiles (every tile but the last) take a path without bounds checks.
 template <int P, int T>
 struct TileIO {
   static constexpr int V = row_vec(P);
   static constexpr int S = row_stride(P);
-  static constexpr int kTileFloats = T * P;
   static constexpr int kChunks = (T * P) / 4;  // T % 4 == 0 -> exact
+  static constexpr bool kPadded = (S != P);
+  static constexpr int P4 = P / 4;             // chunks per row (padded layout only)
+  static constexpr int kIters = (kChunks + T - 1) / T;
+  static constexpr bool kExact = (kChunks % T == 0);
   static_assert(T % 4 == 0, "tile must be a whole number of 16-byte chunks");
 
-  // smem float index of flat tile element e (e = row * P + col)
+  // smem float index of flat tile element e (slow path only)
   NFN_DEVI static int smem_index(int e) {
-    if constexpr (S == P) return e; else return e + (e / P) * (S - P);
+    if constexpr (!kPadded) return e; else return e + (e / P) * (S - P);
   }
 
+  struct Cursor {  // smem byte offset of this thread's current chunk
+    int row, c;
+    NFN_DEVI void init() {
+      if constexpr (kPadded) { row = (int)threadIdx.x / P4; c = (int)threadIdx.x % P4; }
+    }
+    NFN_DEVI unsigned offset(int i) const {
+      if constexpr (kPadded) return (unsigned)((row * S + 4 * c) * 4);
+      else return (unsigned)(((int)threadIdx.x + i * T) * 16);
+    }
+    NFN_DEVI void next() {
+      if constexpr (kPadded) {
+        row += T / P4;
+        c += T % P4;
+        if (c >= P4) { c -= P4; ++row; }
+      }
+    }
+  };
+
   // async global -> smem for the tile starting at row0 (valid rows: min(T, B - row0))
-  NFN_DEVI static void load_async(float* smem, const float* __restrict__ g, long long row0,
+  NFN_DEVI static void load_async(unsigned smem, const float* __restrict__ g, long long row0,
                                   long long B) {
-    const long long base = row0 * P;                 // first float of the tile
-    const long long total = B * (long long)P;        // floats in the tensor
-    const long long remain = total - base;           // floats available from base
-    const float* src = g + base;
-    for (int q = threadIdx.x; q < kChunks; q += T) {
-      const int e = q * 4;
-      if ((long long)e + 4 <= remain) {
-        cp_async16(smem + smem_index(e), src + e);   // S == P or P % 4 == 0: chunk stays in-row
-      } else {
+    const float* src = g + row0 * P;
+    if (B - row0 >= T) {
+      Cursor cur;
+      cur.init();
+      const float* s = src + 4 * (int)threadIdx.x;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if ((long long)e + j < remain) cp_async4(smem + smem_index(e + j), src + e + j);
+      for (int i = 0; i < kIters; ++i) {
+        if (kExact || (int)threadIdx.x + i * T < kChunks) cp_async16(smem + cur.offset(i), s + i * (4 * T));
+        cur.next();
+      }
+    } else {
+      const int remain = (int)(B - row0) * P;  // floats available from src (< T*P)
+      for (int q = threadIdx.x; q < kChunks; q += T) {
+        const int e = q * 4;
+        if (e + 4 <= remain) {
+          cp_async16(smem + 4u * smem_index(e), src + e);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (e + j < remain) cp_async4(smem + 4u * smem_index(e + j), src + e + j);
+        }
       }
     }
   }
 
   // smem -> global, coalesced 16-byte streaming stores
-  NFN_DEVI static void store(const float* smem, float* __restrict__ g, long long row0,
-                             long long B) {
-    const long long base = row0 * P;
-    const long long remain = B * (long long)P - base;
-    float* dst = g + base;
-    for (int q = threadIdx.x; q < kChunks; q += T) {
-      const int e = q * 4;
-      if ((long long)e + 4 <= remain) {
-        const float4 v = *reinterpret_cast<const float4*>(smem + smem_index(e));
-        st_stream_f4(dst + e, v);
-      } else {
+  NFN_DEVI static void store(unsigned smem, float* __restrict__ g, long long row0, long long B) {
+    float* dst = g + row0 * P;
+    if (B - row0 >= T) {
+      Cursor cur;
+      cur.init();
+      float* d = dst + 4 * (int)threadIdx.x;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if ((long long)e + j < remain) dst[e + j] = smem[smem_index(e + j)];
+      for (int i = 0; i < kIters; ++i) {
+        if (kExact || (int)threadIdx.x + i * T < kChunks) st_stream_f4(d + i * (4 * T), lds_f4(smem + cur.offset(i)));
+        cur.next();
+      }
+    } else {
+      const int remain = (int)(B - row0) * P;
+      for (int q = threadIdx.x; q < kChunks; q += T) {
+        const int e = q * 4;
+        if (e + 4 <= remain) {
+          st_stream_f4(dst + e, lds_f4(smem + 4u * smem_index(e)));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (e + j < remain) {
+              float v;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem + 4u * smem_index(e + j)));
+              dst[e + j] = v;
+            }
+        }
       }
     }
   }
@@ -274,9 +325,11 @@ __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
   for (int c = 0; c < NCOL; ++c) colsum[c] = 0.0f;
   double lsum = 0.0;
 
+  const unsigned smem_base = smem_u32(smem);
+  constexpr unsigned kBufBytes = (unsigned)(T * S * sizeof(float));
   long long tile = blockIdx.x;
   if constexpr (P > 0) {
-    if (tile < ntiles) IO::load_async(smem, a.t, tile * T, a.B);
+    if (tile < ntiles) IO::load_async(smem_base, a.t, tile * T, a.B);
     cp_async_commit();
   }
 
@@ -286,7 +339,7 @@ __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
       const long long nxt = tile + gridDim.x;
       // the other buffer was last read by the previous iteration's store, which every
       // thread finished before the barrier that ended that iteration
-      if (nxt < ntiles) IO::load_async(smem + (size_t)((it + 1) % NB) * (T * S), a.t, nxt * T, a.B);
+      if (nxt < ntiles) IO::load_async(smem_base + (unsigned)((it + 1) % NB) * kBufBytes, a.t, nxt * T, a.B);
       cp_async_commit();
       cp_async_wait<1>();
       __syncthreads();
@@ -319,7 +372,7 @@ __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
 
     if constexpr (BWD && P > 0) {
       __syncthreads();
-      IO::store(buf, a.dt, tile * T, a.B);
+      IO::store(smem_base + (unsigned)(it % NB) * kBufBytes, a.dt, tile * T, a.B);
       if (a.dt_colsum) {
         const long long rem = a.B - tile * T;
         const int rows = rem < T ? (int)rem : T;

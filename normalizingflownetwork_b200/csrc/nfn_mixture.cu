@@ -39,11 +39,11 @@ NFN_DEVI void rt_load_async(const RtTile& g, float* smem, const float* __restric
   for (int q = threadIdx.x; q < chunks; q += kMixT) {
     const int e = q * 4;
     if ((long long)e + 4 <= remain) {
-      cp_async16(smem + rt_index(g, e), src + e);
+      cp_async16(smem_u32(smem + rt_index(g, e)), src + e);
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if ((long long)e + j < remain) cp_async4(smem + rt_index(g, e + j), src + e + j);
+        if ((long long)e + j < remain) cp_async4(smem_u32(smem + rt_index(g, e + j)), src + e + j);
     }
   }
 }
