@@ -306,14 +306,14 @@ NFN_DEVI double block_sum(double v, double* scratch /* >= T/32 doubles */) {
 }
 
 // ---------------------------------------------------------------- the kernel
-template <class Spec, bool BWD, class M, int T, int MINB>
+template <class Spec, bool BWD, class M, int T, int NB, int MINB>
 __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
   constexpr int D = Spec::D;
   constexpr int P = Spec::P();
   using IO = TileIO<(P > 0 ? P : 4), T>;
   constexpr int V = IO::V;
   constexpr int S = IO::S;
-  constexpr int NB = 2;
+  static_assert(NB >= 1 && NB <= 4, "1..4 tile buffers");
 
   extern __shared__ __align__(16) float smem[];
   __shared__ double red[T / 32];
@@ -328,20 +328,35 @@ __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
   const unsigned smem_base = smem_u32(smem);
   constexpr unsigned kBufBytes = (unsigned)(T * S * sizeof(float));
   long long tile = blockIdx.x;
-  if constexpr (P > 0) {
-    if (tile < ntiles) IO::load_async(smem_base, a.t, tile * T, a.B);
-    cp_async_commit();
+  // NB-stage pipeline: tiles it+1 .. it+NB-1 are in flight while tile it is computed.
+  // NB == 1 keeps one buffer per CTA and relies on the other resident CTAs for overlap
+  // (wide rows: more CTAs per SM beat a second buffer).
+  if constexpr (P > 0 && NB > 1) {
+#pragma unroll
+    for (int s = 0; s < NB - 1; ++s) {
+      const long long tl = tile + (long long)s * gridDim.x;
+      if (tl < ntiles) IO::load_async(smem_base + (unsigned)s * kBufBytes, a.t, tl * T, a.B);
+      cp_async_commit();
+    }
   }
 
-  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
-    float* buf = smem + (size_t)(it % NB) * (T * S);
+  int slot = 0;  // buffer holding the current tile
+  for (; tile < ntiles; tile += gridDim.x) {
+    float* buf = smem + (size_t)slot * (T * S);
     if constexpr (P > 0) {
-      const long long nxt = tile + gridDim.x;
-      // the other buffer was last read by the previous iteration's store, which every
-      // thread finished before the barrier that ended that iteration
-      if (nxt < ntiles) IO::load_async(smem_base + (unsigned)((it + 1) % NB) * kBufBytes, a.t, nxt * T, a.B);
-      cp_async_commit();
-      cp_async_wait<1>();
+      if constexpr (NB > 1) {
+        // refill the buffer of the previous tile: every thread left it at the barrier
+        // that ended the previous iteration
+        const long long nxt = tile + (long long)(NB - 1) * gridDim.x;
+        const int ps = (slot == 0) ? NB - 1 : slot - 1;
+        if (nxt < ntiles) IO::load_async(smem_base + (unsigned)ps * kBufBytes, a.t, nxt * T, a.B);
+        cp_async_commit();
+        cp_async_wait<NB - 1>();
+      } else {
+        IO::load_async(smem_base, a.t, tile * T, a.B);
+        cp_async_commit();
+        cp_async_wait<0>();
+      }
       __syncthreads();
     }
 
@@ -372,7 +387,7 @@ __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
 
     if constexpr (BWD && P > 0) {
       __syncthreads();
-      IO::store(smem_base + (unsigned)(it % NB) * kBufBytes, a.dt, tile * T, a.B);
+      IO::store(smem_base + (unsigned)slot * kBufBytes, a.dt, tile * T, a.B);
       if (a.dt_colsum) {
         const long long rem = a.B - tile * T;
         const int rows = rem < T ? (int)rem : T;
@@ -390,6 +405,7 @@ __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
     } else if constexpr (P > 0) {
       __syncthreads();
     }
+    slot = (slot + 1 == NB) ? 0 : slot + 1;
   }
   if constexpr (P > 0) cp_async_wait<0>();
 

@@ -43,13 +43,19 @@ cudaError_t launch_chain(const ChainArgs& a, cudaStream_t st) {
   constexpr int P = Spec::P();
   constexpr int T = 128;
   constexpr int S = row_stride(P > 0 ? P : 4);
-  constexpr size_t kSmem = P > 0 ? (size_t)2 * T * S * sizeof(float) : 0;
-  // CTAs per SM the shared-memory budget allows (227 KB usable, 1 KB reserved per CTA)
-  constexpr int kBySmem = kSmem ? (int)((227 * 1024) / (kSmem + 1024)) : 16;
-  constexpr int kCap = BWD ? 5 : 6;  // 640 / 768 threads per SM: leaves >= 80 registers per thread
+  constexpr size_t kTile = P > 0 ? (size_t)T * S * sizeof(float) : 0;
+  // Tile buffers that fit one SM (227 KB usable, ~1 KB reserved per CTA), split between
+  // pipeline depth (NB buffers per CTA) and resident CTAs: aim for 4 CTAs (16 warps) first,
+  // then deepen the prefetch up to 4 stages so small rows keep enough bytes in flight.
+  constexpr int kBufs = kTile ? (int)((227 * 1024 - 6 * 1024) / kTile) : 64;
+  static_assert(kBufs >= 1, "parameter row too wide for one shared-memory tile");
+  constexpr int NB = kBufs / 4 < 1 ? 1 : (kBufs / 4 > 4 ? 4 : kBufs / 4);
+  // register budget: the reverse sweep keeps K*D floats of z history per thread
+  constexpr int kCap = BWD ? (Spec::K * Spec::D > 40 ? 2 : 5) : 6;
+  constexpr int kBySmem = kBufs / NB;
   constexpr int MINB = kBySmem < 1 ? 1 : (kBySmem > kCap ? kCap : kBySmem);
-  static_assert(kSmem <= 227 * 1024, "parameter row too wide for the double-buffered tile");
-  auto kern = chain_kernel<Spec, BWD, M, T, MINB>;
+  constexpr size_t kSmem = kTile * NB;
+  auto kern = chain_kernel<Spec, BWD, M, T, NB, MINB>;
 
   struct Cfg {
     int device = -1;

@@ -20,52 +20,114 @@ namespace nfn {
 constexpr int kMixT = 128;
 
 // ------------------------------------------------------------------ runtime-width tile io
+// Same chunk geometry as TileIO (nfn_chain_kernel.cuh) with the row width a runtime value.
 struct RtTile {
   int P;      // floats per row in global
-  int S;      // floats per row in smem
-  int P4;     // P / 4 when P % 4 == 0 (padded layout), else 0
+  int S;      // floats per row in smem (P, or P + 4 when P % 4 == 0 and P/4 is even)
+  int P4;     // chunks per row (padded layout only)
+  int dr, dc; // kMixT / P4, kMixT % P4: (row, chunk) step of a thread between its chunks
 };
 
 NFN_DEVI int rt_index(const RtTile& g, int e) {
   return g.S == g.P ? e : e + (e / g.P) * (g.S - g.P);
 }
 
-NFN_DEVI void rt_load_async(const RtTile& g, float* smem, const float* __restrict__ src0, long long row0,
+NFN_DEVI void rt_load_async(const RtTile& g, unsigned smem, const float* __restrict__ src0, long long row0,
                             long long B) {
-  const long long base = row0 * g.P;
-  const long long remain = B * (long long)g.P - base;
-  const float* src = src0 + base;
+  const float* src = src0 + row0 * g.P;
   const int chunks = (kMixT * g.P) / 4;
-  for (int q = threadIdx.x; q < chunks; q += kMixT) {
-    const int e = q * 4;
-    if ((long long)e + 4 <= remain) {
-      cp_async16(smem_u32(smem + rt_index(g, e)), src + e);
+  if (B - row0 >= kMixT) {
+    if (g.S == g.P) {
+      for (int q = threadIdx.x; q < chunks; q += kMixT) cp_async16(smem + 16u * q, src + 4 * q);
     } else {
+      int row = (int)threadIdx.x / g.P4, c = (int)threadIdx.x % g.P4;
+      for (int q = threadIdx.x; q < chunks; q += kMixT) {
+        cp_async16(smem + 4u * (row * g.S + 4 * c), src + 4 * q);
+        row += g.dr;
+        c += g.dc;
+        if (c >= g.P4) { c -= g.P4; ++row; }
+      }
+    }
+  } else {
+    const int remain = (int)(B - row0) * g.P;
+    for (int q = threadIdx.x; q < chunks; q += kMixT) {
+      const int e = q * 4;
+      if (e + 4 <= remain) {
+        cp_async16(smem + 4u * rt_index(g, e), src + e);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if ((long long)e + j < remain) cp_async4(smem_u32(smem + rt_index(g, e + j)), src + e + j);
+        for (int j = 0; j < 4; ++j)
+          if (e + j < remain) cp_async4(smem + 4u * rt_index(g, e + j), src + e + j);
+      }
     }
   }
 }
 
-NFN_DEVI void rt_store(const RtTile& g, const float* smem, float* __restrict__ dst0, long long row0,
-                       long long B) {
-  const long long base = row0 * g.P;
-  const long long remain = B * (long long)g.P - base;
-  float* dst = dst0 + base;
+NFN_DEVI void rt_store(const RtTile& g, unsigned smem, float* __restrict__ dst0, long long row0, long long B) {
+  float* dst = dst0 + row0 * g.P;
   const int chunks = (kMixT * g.P) / 4;
-  for (int q = threadIdx.x; q < chunks; q += kMixT) {
-    const int e = q * 4;
-    if ((long long)e + 4 <= remain) {
-      const float4 v = *reinterpret_cast<const float4*>(smem + rt_index(g, e));
-      st_stream_f4(dst + e, v);
+  if (B - row0 >= kMixT) {
+    if (g.S == g.P) {
+      for (int q = threadIdx.x; q < chunks; q += kMixT) st_stream_f4(dst + 4 * q, lds_f4(smem + 16u * q));
     } else {
+      int row = (int)threadIdx.x / g.P4, c = (int)threadIdx.x % g.P4;
+      for (int q = threadIdx.x; q < chunks; q += kMixT) {
+        st_stream_f4(dst + 4 * q, lds_f4(smem + 4u * (row * g.S + 4 * c)));
+        row += g.dr;
+        c += g.dc;
+        if (c >= g.P4) { c -= g.P4; ++row; }
+      }
+    }
+  } else {
+    const int remain = (int)(B - row0) * g.P;
+    for (int q = threadIdx.x; q < chunks; q += kMixT) {
+      const int e = q * 4;
+      if (e + 4 <= remain) {
+        st_stream_f4(dst + e, lds_f4(smem + 4u * rt_index(g, e)));
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if ((long long)e + j < remain) dst[e + j] = smem[rt_index(g, e + j)];
+        for (int j = 0; j < 4; ++j)
+          if (e + j < remain) {
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem + 4u * rt_index(g, e + j)));
+            dst[e + j] = v;
+          }
+      }
     }
   }
 }
+
+// Tile pipeline shared by the two heads: NB == 2 double-buffers inside the CTA, NB == 1 keeps
+// one buffer per CTA and relies on the other resident CTAs for overlap (wide rows).
+template <int NB>
+struct RtPipe {
+  unsigned base, buf_bytes;
+  int slot = 0;
+  NFN_DEVI void prologue(const RtTile& g, const float* t, long long tile, long long ntiles, long long B) {
+    if constexpr (NB == 2) {
+      if (tile < ntiles) rt_load_async(g, base, t, tile * kMixT, B);
+      cp_async_commit();
+    }
+  }
+  // makes the current tile resident; returns its smem byte address
+  NFN_DEVI unsigned acquire(const RtTile& g, const float* t, long long tile, long long ntiles, long long B) {
+    if constexpr (NB == 2) {
+      const long long nxt = tile + gridDim.x;
+      if (nxt < ntiles) rt_load_async(g, base + (unsigned)(slot ^ 1) * buf_bytes, t, nxt * kMixT, B);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      rt_load_async(g, base, t, tile * kMixT, B);
+      cp_async_commit();
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    return base + (unsigned)slot * buf_bytes;
+  }
+  NFN_DEVI void advance() {
+    if constexpr (NB == 2) slot ^= 1;
+  }
+};
 
 // per-thread load/store of N consecutive floats at a runtime offset whose alignment
 // (in floats) is at least A (compile time)
@@ -113,8 +175,8 @@ NFN_DEVI void lse_push(float x, float& m, float& s) {
 // ------------------------------------------------------------------ MDN
 // V4: rows are 16-byte aligned in smem (P % 4 == 0) so the (mu, sigma_raw) block of a
 // component, 2*D floats at offset k*2*D, can be read with the widest aligned vectors.
-template <int D, bool V4, bool BWD, class M>
-__global__ void __launch_bounds__(kMixT, BWD ? 3 : 4) mdn_kernel(const MixArgs a, const RtTile g) {
+template <int D, bool V4, bool BWD, class M, int NB>
+__global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) mdn_kernel(const MixArgs a, const RtTile g) {
   extern __shared__ __align__(16) float smem[];
   __shared__ double red[kMixT / 32];
   constexpr int A = V4 ? ((2 * D) % 4 == 0 ? 4 : ((2 * D) % 2 == 0 ? 2 : 1)) : 1;
@@ -123,18 +185,16 @@ __global__ void __launch_bounds__(kMixT, BWD ? 3 : 4) mdn_kernel(const MixArgs a
   const long long ntiles = (a.B + kMixT - 1) / kMixT;
   double lsum = 0.0;
   const int tile_floats = kMixT * g.S;
+  RtPipe<NB> pipe;
+  pipe.base = smem_u32(smem);
+  pipe.buf_bytes = (unsigned)tile_floats * 4u;
 
   long long tile = blockIdx.x;
-  if (tile < ntiles) rt_load_async(g, smem, a.t, tile * kMixT, a.B);
-  cp_async_commit();
+  pipe.prologue(g, a.t, tile, ntiles, a.B);
 
-  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
-    float* buf = smem + (size_t)(it & 1) * tile_floats;
-    const long long nxt = tile + gridDim.x;
-    if (nxt < ntiles) rt_load_async(g, smem + (size_t)((it + 1) & 1) * tile_floats, a.t, nxt * kMixT, a.B);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
+  for (; tile < ntiles; tile += gridDim.x) {
+    const unsigned buf_addr = pipe.acquire(g, a.t, tile, ntiles, a.B);
+    float* buf = smem + (size_t)pipe.slot * tile_floats;
 
     const long long r = tile * kMixT + threadIdx.x;
     if (r < a.B) {
@@ -204,9 +264,10 @@ __global__ void __launch_bounds__(kMixT, BWD ? 3 : 4) mdn_kernel(const MixArgs a
     }
     __syncthreads();
     if constexpr (BWD) {
-      rt_store(g, buf, a.dt, tile * kMixT, a.B);
+      rt_store(g, buf_addr, a.dt, tile * kMixT, a.B);
       __syncthreads();
     }
+    pipe.advance();
   }
   cp_async_wait<0>();
   if (a.logp_sum) {
@@ -217,13 +278,13 @@ __global__ void __launch_bounds__(kMixT, BWD ? 3 : 4) mdn_kernel(const MixArgs a
 
 // ------------------------------------------------------------------ KMN
 // smem: [2 buffers of T x S logits] [locs M x D] [coef M: -0.5 / s^2] [lognorm M: -D log|s|]
-template <int D, bool BWD, class M>
-__global__ void __launch_bounds__(kMixT, BWD ? 3 : 4) kmn_kernel(const MixArgs a, const RtTile g) {
+template <int D, bool BWD, class M, int NB>
+__global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) kmn_kernel(const MixArgs a, const RtTile g) {
   extern __shared__ __align__(16) float smem[];
   __shared__ double red[kMixT / 32];
   const int K = a.K;
   const int tile_floats = kMixT * g.S;
-  float* s_loc = smem + 2 * (size_t)tile_floats;
+  float* s_loc = smem + NB * (size_t)tile_floats;
   float* s_coef = s_loc + K * D;
   float* s_lnorm = s_coef + K;
   float* s_dsc = s_lnorm + K;  // block accumulators of d logp / d scale (BWD)
@@ -236,18 +297,16 @@ __global__ void __launch_bounds__(kMixT, BWD ? 3 : 4) kmn_kernel(const MixArgs a
   }
   const long long ntiles = (a.B + kMixT - 1) / kMixT;
   double lsum = 0.0;
+  RtPipe<NB> pipe;
+  pipe.base = smem_u32(smem);
+  pipe.buf_bytes = (unsigned)tile_floats * 4u;
 
   long long tile = blockIdx.x;
-  if (tile < ntiles) rt_load_async(g, smem, a.t, tile * kMixT, a.B);
-  cp_async_commit();
+  pipe.prologue(g, a.t, tile, ntiles, a.B);
 
-  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
-    float* buf = smem + (size_t)(it & 1) * tile_floats;
-    const long long nxt = tile + gridDim.x;
-    if (nxt < ntiles) rt_load_async(g, smem + (size_t)((it + 1) & 1) * tile_floats, a.t, nxt * kMixT, a.B);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
+  for (; tile < ntiles; tile += gridDim.x) {
+    const unsigned buf_addr = pipe.acquire(g, a.t, tile, ntiles, a.B);
+    float* buf = smem + (size_t)pipe.slot * tile_floats;
 
     const long long r = tile * kMixT + threadIdx.x;
     const bool valid = r < a.B;
@@ -309,9 +368,10 @@ __global__ void __launch_bounds__(kMixT, BWD ? 3 : 4) kmn_kernel(const MixArgs a
     }
     __syncthreads();
     if constexpr (BWD) {
-      rt_store(g, buf, a.dt, tile * kMixT, a.B);
+      rt_store(g, buf_addr, a.dt, tile * kMixT, a.B);
       __syncthreads();
     }
+    pipe.advance();
   }
   cp_async_wait<0>();
   if constexpr (BWD) {
@@ -331,8 +391,15 @@ static RtTile make_tile(int P) {
   RtTile g;
   g.P = P;
   g.S = row_stride(P);
-  g.P4 = (P % 4 == 0) ? P / 4 : 0;
+  g.P4 = (g.S != P) ? P / 4 : 1;
+  g.dr = kMixT / g.P4;
+  g.dc = kMixT % g.P4;
   return g;
+}
+
+// one buffer per CTA unless two buffers still leave >= 4 CTAs per SM
+static int pick_nb(size_t tile_bytes, size_t extra) {
+  return (4 * (2 * tile_bytes + extra + 1024) <= (size_t)227 * 1024) ? 2 : 1;
 }
 
 template <class Kern>
@@ -356,22 +423,29 @@ static int launch_tiled(Kern kern, const MixArgs& a, const RtTile& g, size_t sme
   return cuda_error(cudaGetLastError(), name);
 }
 
-template <int D, bool V4>
-static int launch_mdn_dv(bool bwd, const MixArgs& a, const RtTile& g, size_t smem, cudaStream_t st) {
+template <int D, bool V4, int NB>
+static int launch_mdn_dvn(bool bwd, const MixArgs& a, const RtTile& g, size_t smem, cudaStream_t st) {
   if (math_mode() == 0) {
-    return bwd ? launch_tiled(mdn_kernel<D, V4, true, MathFast>, a, g, smem, "mdn_kernel", st)
-               : launch_tiled(mdn_kernel<D, V4, false, MathFast>, a, g, smem, "mdn_kernel", st);
+    return bwd ? launch_tiled(mdn_kernel<D, V4, true, MathFast, NB>, a, g, smem, "mdn_kernel", st)
+               : launch_tiled(mdn_kernel<D, V4, false, MathFast, NB>, a, g, smem, "mdn_kernel", st);
   }
-  return bwd ? launch_tiled(mdn_kernel<D, V4, true, MathAccurate>, a, g, smem, "mdn_kernel", st)
-             : launch_tiled(mdn_kernel<D, V4, false, MathAccurate>, a, g, smem, "mdn_kernel", st);
+  return bwd ? launch_tiled(mdn_kernel<D, V4, true, MathAccurate, NB>, a, g, smem, "mdn_kernel", st)
+             : launch_tiled(mdn_kernel<D, V4, false, MathAccurate, NB>, a, g, smem, "mdn_kernel", st);
 }
 
 template <int D>
 static int launch_mdn_d(bool bwd, const MixArgs& a, cudaStream_t st) {
   const int P = 2 * a.K * D + a.K;
   const RtTile g = make_tile(P);
-  const size_t smem = (size_t)2 * kMixT * g.S * sizeof(float);
-  int rc = (P % 4 == 0) ? launch_mdn_dv<D, true>(bwd, a, g, smem, st) : launch_mdn_dv<D, false>(bwd, a, g, smem, st);
+  const size_t tile = (size_t)kMixT * g.S * sizeof(float);
+  const int nb = pick_nb(tile, 0);
+  const size_t smem = tile * nb;
+  int rc;
+  if (P % 4 == 0) {
+    rc = nb == 2 ? launch_mdn_dvn<D, true, 2>(bwd, a, g, smem, st) : launch_mdn_dvn<D, true, 1>(bwd, a, g, smem, st);
+  } else {
+    rc = nb == 2 ? launch_mdn_dvn<D, false, 2>(bwd, a, g, smem, st) : launch_mdn_dvn<D, false, 1>(bwd, a, g, smem, st);
+  }
   if (rc == NFN_OK && bwd && a.dt_colsum) rc = launch_colsum(a.dt, a.B, P, a.dt_colsum, st);
   return rc;
 }
@@ -390,16 +464,24 @@ int launch_mdn(int d, bool bwd, const MixArgs& a, cudaStream_t st) {
   return set_error(NFN_ERR_DESC, "n_dims=%d", d);
 }
 
+template <int D, int NB>
+static int launch_kmn_dn(bool bwd, const MixArgs& a, const RtTile& g, size_t smem, cudaStream_t st) {
+  if (math_mode() == 0) {
+    return bwd ? launch_tiled(kmn_kernel<D, true, MathFast, NB>, a, g, smem, "kmn_kernel", st)
+               : launch_tiled(kmn_kernel<D, false, MathFast, NB>, a, g, smem, "kmn_kernel", st);
+  }
+  return bwd ? launch_tiled(kmn_kernel<D, true, MathAccurate, NB>, a, g, smem, "kmn_kernel", st)
+             : launch_tiled(kmn_kernel<D, false, MathAccurate, NB>, a, g, smem, "kmn_kernel", st);
+}
+
 template <int D>
 static int launch_kmn_d(bool bwd, const MixArgs& a, cudaStream_t st) {
   const RtTile g = make_tile(a.K);
-  const size_t smem = ((size_t)2 * kMixT * g.S + (size_t)a.K * (D + 3)) * sizeof(float);
-  if (math_mode() == 0) {
-    return bwd ? launch_tiled(kmn_kernel<D, true, MathFast>, a, g, smem, "kmn_kernel", st)
-               : launch_tiled(kmn_kernel<D, false, MathFast>, a, g, smem, "kmn_kernel", st);
-  }
-  return bwd ? launch_tiled(kmn_kernel<D, true, MathAccurate>, a, g, smem, "kmn_kernel", st)
-             : launch_tiled(kmn_kernel<D, false, MathAccurate>, a, g, smem, "kmn_kernel", st);
+  const size_t tile = (size_t)kMixT * g.S * sizeof(float);
+  const size_t extra = (size_t)a.K * (D + 3) * sizeof(float);
+  const int nb = pick_nb(tile, extra);
+  const size_t smem = tile * nb + extra;
+  return nb == 2 ? launch_kmn_dn<D, 2>(bwd, a, g, smem, st) : launch_kmn_dn<D, 1>(bwd, a, g, smem, st);
 }
 
 int launch_kmn(int d, bool bwd, const MixArgs& a, cudaStream_t st) {
