@@ -340,9 +340,34 @@ __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
     }
   }
 
+  // y (and the upstream cotangent) of the NEXT tile are fetched into registers one iteration
+  // ahead, so their DRAM latency hides behind the current tile's arithmetic
+  float y_nxt[D];
+  float g_nxt = 1.0f;
+  {
+    const long long r0 = tile * T + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < D; ++i) y_nxt[i] = 0.0f;
+    if (tile < ntiles && r0 < a.B) {
+      load_event<D>(a.y, a.y_broadcast ? 0 : r0, y_nxt);
+      if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + r0); }
+    }
+  }
+
   int slot = 0;  // buffer holding the current tile
   for (; tile < ntiles; tile += gridDim.x) {
     float* buf = smem + (size_t)slot * (T * S);
+    float z[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) z[i] = y_nxt[i];
+    const float g_cur = g_nxt;
+    {
+      const long long rn = (tile + gridDim.x) * T + threadIdx.x;
+      if (rn < a.B) {
+        load_event<D>(a.y, a.y_broadcast ? 0 : rn, y_nxt);
+        if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + rn); }
+      }
+    }
     if constexpr (P > 0) {
       if constexpr (NB > 1) {
         // refill the buffer of the previous tile: every thread left it at the barrier
@@ -363,8 +388,6 @@ __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
     const long long r = tile * T + threadIdx.x;
     if (r < a.B) {
       float* row = buf + threadIdx.x * S;
-      float z[D];
-      load_event<D>(a.y, a.y_broadcast ? 0 : r, z);
       float zs[Spec::KA][D];
       LogDetAcc<M> ld;
       FwdSweep<Spec, M, V, 0>::run(row, z, zs, ld);
@@ -375,7 +398,7 @@ __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
       a.logp[r] = lp;
       lsum += (double)lp;
       if constexpr (BWD) {
-        const float cot = a.g_scale * (a.g_logp ? __ldg(a.g_logp + r) : 1.0f);
+        const float cot = a.g_scale * g_cur;
         float G[D];
         float gb[Base::NA];
         Base::bwd(bth, z, cot, G, gb);

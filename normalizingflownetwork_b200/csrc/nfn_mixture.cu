@@ -164,6 +164,31 @@ NFN_DEVI void st_vec(float* p, const float (&v)[N]) {
   }
 }
 
+// y (and the upstream cotangent) of the next tile are fetched one iteration ahead so their
+// DRAM latency hides behind the current tile's arithmetic
+template <int D, bool BWD>
+struct EventPrefetch {
+  float y_nxt[D];
+  float g_nxt = 1.0f;
+  NFN_DEVI void fetch(const MixArgs& a, long long r) {
+    if (r < a.B) {
+      load_event<D>(a.y, a.y_broadcast ? 0 : r, y_nxt);
+      if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + r); }
+    }
+  }
+  NFN_DEVI void first(const MixArgs& a, long long tile, long long ntiles) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) y_nxt[i] = 0.0f;
+    if (tile < ntiles) fetch(a, tile * kMixT + threadIdx.x);
+  }
+  NFN_DEVI void rotate(const MixArgs& a, long long tile, float (&y)[D], float& g) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) y[i] = y_nxt[i];
+    g = g_nxt;
+    fetch(a, (tile + gridDim.x) * kMixT + threadIdx.x);
+  }
+};
+
 // online logsumexp update with one exponential
 template <class M>
 NFN_DEVI void lse_push(float x, float& m, float& s) {
@@ -191,16 +216,19 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) mdn_kernel(const MixArgs a
 
   long long tile = blockIdx.x;
   pipe.prologue(g, a.t, tile, ntiles, a.B);
+  EventPrefetch<D, BWD> pf;
+  pf.first(a, tile, ntiles);
 
   for (; tile < ntiles; tile += gridDim.x) {
+    float y[D];
+    float g_cur;
+    pf.rotate(a, tile, y, g_cur);
     const unsigned buf_addr = pipe.acquire(g, a.t, tile, ntiles, a.B);
     float* buf = smem + (size_t)pipe.slot * tile_floats;
 
     const long long r = tile * kMixT + threadIdx.x;
     if (r < a.B) {
       float* row = buf + threadIdx.x * g.S;
-      float y[D];
-      load_event<D>(a.y, a.y_broadcast ? 0 : r, y);
       // log-softmax normaliser of the logits
       float lm = -INFINITY, ls = 0.0f;
       for (int k = 0; k < K; ++k) lse_push<M>(row[LO + k], lm, ls);
@@ -228,7 +256,7 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) mdn_kernel(const MixArgs a
       a.logp[r] = logp;
       lsum += (double)logp;
       if constexpr (BWD) {
-        const float cot = a.g_scale * (a.g_logp ? __ldg(a.g_logp + r) : 1.0f);
+        const float cot = a.g_scale * g_cur;
         float dy[D];
 #pragma unroll
         for (int i = 0; i < D; ++i) dy[i] = 0.0f;
@@ -303,18 +331,21 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) kmn_kernel(const MixArgs a
 
   long long tile = blockIdx.x;
   pipe.prologue(g, a.t, tile, ntiles, a.B);
+  EventPrefetch<D, BWD> pf;
+  pf.first(a, tile, ntiles);
 
   for (; tile < ntiles; tile += gridDim.x) {
+    float y[D];
+    float g_cur;
+    pf.rotate(a, tile, y, g_cur);
     const unsigned buf_addr = pipe.acquire(g, a.t, tile, ntiles, a.B);
     float* buf = smem + (size_t)pipe.slot * tile_floats;
 
     const long long r = tile * kMixT + threadIdx.x;
     const bool valid = r < a.B;
     float* row = buf + threadIdx.x * g.S;
-    float y[D];
     float lse = 0.0f, top = 0.0f, cot = 0.0f;
     if (valid) {
-      load_event<D>(a.y, a.y_broadcast ? 0 : r, y);
       float lm = -INFINITY, ls = 0.0f;
       for (int k = 0; k < K; ++k) lse_push<M>(row[k], lm, ls);
       lse = lm + M::log(ls);
@@ -332,12 +363,9 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) kmn_kernel(const MixArgs a
       const float logp = top - lse - (float)D * kHalfLog2Pi;
       a.logp[r] = logp;
       lsum += (double)logp;
-    } else {
-#pragma unroll
-      for (int i = 0; i < D; ++i) y[i] = 0.0f;
     }
     if constexpr (BWD) {
-      if (valid) cot = a.g_scale * (a.g_logp ? __ldg(a.g_logp + r) : 1.0f);
+      if (valid) cot = a.g_scale * g_cur;
       float dy[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) dy[i] = 0.0f;
