@@ -268,6 +268,8 @@ def run_ours(args):
     lib = _lib.load()
     cfg = args.config
     ft, d, tb, B, bwd = CONFIGS[cfg]
+    if args.fwd_only:
+        bwd = False
     if args.rows:
         B = args.rows
     P = param_size(ft, d, tb)
@@ -427,6 +429,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fwd-only", action="store_true", help="time the forward-only kernel of the config (tuning)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -9,7 +9,8 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libnfn_b200.so")
+# NFN_B200_LIB points at an A/B tuning variant built by build.py (tools only)
+LIB_PATH = os.environ.get("NFN_B200_LIB") or os.path.join(_PKG, "libnfn_b200.so")
 
 NFN_MAX_FLOWS = 64
 NFN_MAX_DIMS = 8

@@ -38,23 +38,45 @@ void register_chain(const std::string& key, const ChainKernels& k);
 const ChainKernels* find_chain(const std::string& key);
 
 // ------------------------------------------------------------------ specialised launcher
+// Launch geometry of a specialised chain kernel: T rows per tile, NB tile buffers per CTA,
+// MINB resident CTAs per SM promised to ptxas (sets the register budget).  Defaults come
+// from A/B sweeps on B200 (profiles/tuning_r01.md): the fused forward+backward kernel wants
+// registers more than warps (2 CTAs x 4 warps with a double-buffered tile, up to 255
+// registers), the forward kernel wants one buffer per CTA and up to 4 CTAs per SM.
+template <class Spec, bool BWD>
+struct ChainTune {
+  static constexpr int P = Spec::P();
+#ifdef NFN_TUNE_T
+  static constexpr int T = NFN_TUNE_T;
+#else
+  static constexpr int T = 128;
+#endif
+  static constexpr int S = row_stride(P > 0 ? P : 4);
+  static constexpr size_t kTile = P > 0 ? (size_t)T * S * sizeof(float) : 0;
+  // tile buffers that fit one SM (227 KB usable, ~1 KB reserved per CTA)
+  static constexpr int kBufs = kTile ? (int)((227 * 1024 - 6 * 1024) / kTile) : 64;
+  static_assert(kBufs >= 1, "parameter row too wide for one shared-memory tile");
+#ifdef NFN_TUNE_NB
+  static constexpr int NB = NFN_TUNE_NB;
+#else
+  static constexpr int NB = (BWD && kBufs >= 4) ? 2 : 1;
+#endif
+#ifdef NFN_TUNE_MINB
+  static constexpr int MINB = NFN_TUNE_MINB;
+#else
+  static constexpr int kBySmem = kBufs / NB;
+  static constexpr int kWant = BWD ? 2 : 4;
+  static constexpr int MINB = kBySmem < kWant ? kBySmem : kWant;
+#endif
+};
+
 template <class Spec, bool BWD, class M>
 cudaError_t launch_chain(const ChainArgs& a, cudaStream_t st) {
-  constexpr int P = Spec::P();
-  constexpr int T = 128;
-  constexpr int S = row_stride(P > 0 ? P : 4);
-  constexpr size_t kTile = P > 0 ? (size_t)T * S * sizeof(float) : 0;
-  // Tile buffers that fit one SM (227 KB usable, ~1 KB reserved per CTA), split between
-  // pipeline depth (NB buffers per CTA) and resident CTAs: aim for 4 CTAs (16 warps) first,
-  // then deepen the prefetch up to 4 stages so small rows keep enough bytes in flight.
-  constexpr int kBufs = kTile ? (int)((227 * 1024 - 6 * 1024) / kTile) : 64;
-  static_assert(kBufs >= 1, "parameter row too wide for one shared-memory tile");
-  constexpr int NB = kBufs / 4 < 1 ? 1 : (kBufs / 4 > 4 ? 4 : kBufs / 4);
-  // register budget: the reverse sweep keeps K*D floats of z history per thread
-  constexpr int kCap = BWD ? (Spec::K * Spec::D > 40 ? 2 : 5) : 6;
-  constexpr int kBySmem = kBufs / NB;
-  constexpr int MINB = kBySmem < 1 ? 1 : (kBySmem > kCap ? kCap : kBySmem);
-  constexpr size_t kSmem = kTile * NB;
+  using Tune = ChainTune<Spec, BWD>;
+  constexpr int T = Tune::T;
+  constexpr int NB = Tune::NB;
+  constexpr int MINB = Tune::MINB;
+  constexpr size_t kSmem = Tune::kTile * NB;
   auto kern = chain_kernel<Spec, BWD, M, T, NB, MINB>;
 
   struct Cfg {
