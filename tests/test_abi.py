@@ -1,0 +1,94 @@
+"""CPU: the C-ABI library loads here (no GPU) and exports every symbol include/nfn_b200.h
+declares; argument validation returns error codes without touching the device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "nfn_b200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(nfn_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(n for n in names if n not in ("nfn_status", "nfn_chain_desc")))
+
+
+def test_header_declares_expected_surface():
+    names = declared_functions()
+    for must in ("nfn_chain_forward", "nfn_chain_forward_backward", "nfn_mdn_forward_backward",
+                 "nfn_kmn_forward_backward", "nfn_flow_forward", "nfn_chain_forward_backward_host",
+                 "nfn_logmeanexp_draws", "nfn_last_error", "nfn_version"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(nfn_lib):
+    from normalizingflownetwork_b200 import _lib
+
+    for name in declared_functions():
+        assert hasattr(nfn_lib, name), "libnfn_b200.so does not export %s" % name
+        assert name in _lib.SIGNATURES, "ctypes binding is missing %s" % name
+    assert set(_lib.SIGNATURES) == set(declared_functions())
+    assert nfn_lib.nfn_version() == 100
+
+
+def test_struct_layout_matches_header():
+    from normalizingflownetwork_b200 import _lib
+
+    assert ctypes.sizeof(_lib.ChainDesc) == 12 + 64
+    assert _lib.ChainDesc.flow_type.offset == 12
+
+
+def test_descriptor_validation_without_gpu(nfn_lib):
+    from normalizingflownetwork_b200 import _lib
+
+    d = _lib.make_desc(["planar", "radial", "affine"], 3, True)
+    assert nfn_lib.nfn_chain_param_size(ctypes.byref(d)) == 7 + 5 + 6 + 6  # reference test_total_param_size_nf
+    d1 = _lib.make_desc(["planar", "radial", "affine"], 1, False)
+    assert nfn_lib.nfn_chain_param_size(ctypes.byref(d1)) == 3 + 3 + 2
+    assert nfn_lib.nfn_chain_is_specialized(ctypes.byref(d)) == 1
+    assert nfn_lib.nfn_chain_is_specialized(ctypes.byref(_lib.make_desc(["affine"] * 7, 5, False))) == 0
+    bad = _lib.ChainDesc()
+    bad.n_dims, bad.n_flows, bad.trainable_base = 0, 1, 0
+    assert nfn_lib.nfn_chain_param_size(ctypes.byref(bad)) == -2  # NFN_ERR_DESC
+    assert b"n_dims" in nfn_lib.nfn_last_error()
+    bad.n_dims, bad.n_flows = 2, 65
+    assert nfn_lib.nfn_chain_param_size(ctypes.byref(bad)) == -2
+    bad.n_flows = 1
+    bad.flow_type[0] = 7
+    assert nfn_lib.nfn_chain_param_size(ctypes.byref(bad)) == -2
+    assert nfn_lib.nfn_chain_param_size(None) == -1  # NFN_ERR_NULL
+    # shape / null / alignment checks happen before any CUDA call
+    assert nfn_lib.nfn_chain_forward(ctypes.byref(d), None, None, 5, None, 4, None) == -3  # y_rows != B, 1
+    assert nfn_lib.nfn_chain_forward(ctypes.byref(d), None, None, 4, None, 4, None) == -1
+    assert nfn_lib.nfn_chain_forward(ctypes.byref(d), None, None, 0, None, 0, None) == 0   # B = 0 is a no-op
+    buf = (ctypes.c_float * 64)()
+    addr = ctypes.addressof(buf)
+    odd = ctypes.c_void_p(addr + 4)
+    assert nfn_lib.nfn_chain_forward(ctypes.byref(d), odd, ctypes.c_void_p(addr), 1, ctypes.c_void_p(addr), 1,
+                                     None) == -4  # NFN_ERR_ALIGN
+    assert nfn_lib.nfn_mdn_forward(0, 2, ctypes.c_void_p(addr), ctypes.c_void_p(addr), 1, ctypes.c_void_p(addr), 1,
+                                   None) == -2
+    assert nfn_lib.nfn_flow_forward(3, 2, None, None, 1, None, None, 1, None) == -2
+    assert nfn_lib.nfn_logmeanexp_draws(None, 0, 4, None, None) == -3
+
+
+def test_missing_library_is_loud(monkeypatch, tmp_path):
+    from normalizingflownetwork_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "normalizingflownetwork_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert "import oracle" not in text and "from oracle" not in text, fn
