@@ -1,0 +1,264 @@
+"""BaseEstimator: the caller contract of the hot path (reference estimators/BaseEstimator.py).
+
+Keeps ``fit / score / pdf / log_pdf`` and the data-normalisation / noise-regularisation
+behaviour of the reference's Keras ``Sequential`` subclass, on a torch MLP (stock cuBLAS
+GEMMs: the conditioning network is a few kFLOP per sample and not the hot path) with the
+density head running in libnfn_b200.so.  One training step launches ONE fused
+forward+reverse-sweep kernel for the head (cotangent -1/B folded in) and feeds ``dt`` to the
+MLP backward; under torchrun the batch is sharded by rank and the flat gradient (+ loss) is
+summed with one all-reduce.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .. import functional as F
+from ..DistributionLayers import GaussianKernelsLayer, GaussianMixtureLayer, InverseNormalizingFlowLayer
+
+
+def default_device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("normalizingflownetwork_b200 estimators need a CUDA device (no CPU path)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class _Normalise(torch.nn.Module):
+    """Lambda x: (x - x_mean) / (x_std + 1e-8)  (MaximumLikelihoodNNEstimator.py:40)."""
+
+    def __init__(self, owner):
+        super().__init__()
+        self._owner = [owner]  # not a submodule
+
+    def forward(self, x):
+        o = self._owner[0]
+        return (x - o.x_mean) / (o.x_std + 1e-8)
+
+
+class _GaussianNoise(torch.nn.Module):
+    """tf.keras.layers.GaussianNoise: additive N(0, std) noise, active in training only."""
+
+    def __init__(self, owner, which):
+        super().__init__()
+        self._owner = [owner]
+        self._which = which
+
+    def forward(self, x):
+        std = getattr(self._owner[0], self._which)
+        if self.training and std > 0.0:
+            return x + std * torch.randn_like(x)
+        return x
+
+
+class BaseEstimator(torch.nn.Module):
+    # class-level like the reference's tf.Variables (BaseEstimator.py:9-10); the Bayesian
+    # subclass shadows them per instance
+    x_noise_std = 0.0
+    y_noise_std = 0.0
+
+    def __init__(self, layers, dist_layer, noise_fn_type="fixed_rate", noise_scale_factor=0.0, random_seed=22,
+                 device=None):
+        super().__init__()
+        self.device = torch.device(device) if device is not None else default_device()
+        self.noise_fn_type = noise_fn_type
+        self.noise_scale_factor = noise_scale_factor
+        self.random_seed = random_seed
+        self.net = torch.nn.Sequential(*layers)
+        self.dist_layer = dist_layer
+        for name in ("x_mean", "x_std", "y_mean", "y_std"):
+            self.register_buffer(name, torch.zeros(1))
+        self.x_std.fill_(1.0)
+        self.y_std.fill_(1.0)
+        self.optimizer = None
+        self.history = []
+        self.stop_training = False
+        self.to(self.device)
+
+    # ------------------------------------------------------------------ forward
+    def _to_dev(self, a):
+        if torch.is_tensor(a):
+            return a.to(device=self.device, dtype=torch.float32)
+        return torch.as_tensor(np.asarray(a, dtype=np.float32), device=self.device)
+
+    def params_from_x(self, x):
+        """Network output t[B, P] for conditioning inputs x."""
+        return self.net(self._to_dev(x))
+
+    def forward(self, x, training=False):
+        was = self.training
+        self.train(bool(training))
+        try:
+            with torch.set_grad_enabled(bool(training)):
+                return self.dist_layer(self.params_from_x(x))
+        finally:
+            self.train(was)
+
+    def call(self, x, training=False):
+        return self.forward(x, training=training)
+
+    # ------------------------------------------------------------------ data handling
+    def _assign_data_normalization(self, x, y):
+        x, y = np.asarray(x), np.asarray(y)
+        for name, v in (("x_mean", np.mean(x, axis=0, dtype=np.float32)), ("x_std", np.std(x, axis=0, dtype=np.float32)),
+                        ("y_mean", np.mean(y, axis=0, dtype=np.float32)), ("y_std", np.std(y, axis=0, dtype=np.float32))):
+            setattr(self, name, torch.as_tensor(v, device=self.device))
+
+    def _assign_noise_regularisation(self, n_dims, n_datapoints):
+        assert self.noise_fn_type in ["rule_of_thumb", "fixed_rate"]
+        if self.noise_fn_type == "rule_of_thumb":
+            noise_std = self.noise_scale_factor * (n_datapoints + 1) ** (-1 / (4 + n_dims))
+        else:
+            noise_std = self.noise_scale_factor
+        self._set_noise(float(noise_std))
+
+    def _set_noise(self, std):
+        type(self).x_noise_std = std
+        type(self).y_noise_std = std
+
+    def _y_input(self, y, training):
+        """y normalisation + training-only noise (BaseEstimator.py:61-69)."""
+        y = (self._to_dev(y) - self.y_mean) / self.y_std
+        if training and self.y_noise_std > 0.0:
+            y = y + self.y_noise_std * torch.randn_like(y)
+        return y
+
+    def _log_ystd_sum(self):
+        return torch.sum(torch.log(self.y_std))
+
+    # ------------------------------------------------------------------ head: fused fwd + reverse sweep
+    def _head_forward_backward(self, t, y, g_scale, logp_sum):
+        """Launches the fused kernel of the head; returns dt (and accumulates grads of the
+        head's own trainable parameters, i.e. the KMN bandwidths)."""
+        layer = self.dist_layer
+        td = t.detach()
+        if isinstance(layer, InverseNormalizingFlowLayer):
+            _, dt, _ = F.chain_forward_backward(td, y, layer._flow_types, layer._n_dims, layer._trainable_base_dist,
+                                                g_scale=g_scale, logp_sum=logp_sum)
+        elif isinstance(layer, GaussianMixtureLayer):
+            _, dt, _ = F.mdn_forward_backward(td, y, layer._n_centers, layer._n_dims, g_scale=g_scale,
+                                              logp_sum=logp_sum)
+        elif isinstance(layer, GaussianKernelsLayer):
+            scales = layer.scale_model()
+            _, dt, _, dsc = F.kmn_forward_backward(td, y, layer.locs, scales.detach(), g_scale=g_scale,
+                                                   logp_sum=logp_sum)
+            if scales.requires_grad:
+                scales.backward(dsc)
+        else:
+            raise TypeError("unsupported distribution layer %r" % type(layer).__name__)
+        return dt
+
+    def _extra_loss(self):
+        """Regulariser added to the mean NLL (KL term of the Bayesian estimators)."""
+        return None
+
+    def train_step(self, xb, yb, global_batch=None):
+        """One optimiser step on a (local) mini-batch; returns the device scalar loss
+        (mean NLL over the global batch + regulariser)."""
+        self.train(True)
+        B = xb.shape[0]
+        Bg = global_batch or B
+        self.optimizer.zero_grad(set_to_none=True)
+        t = self.params_from_x(xb)
+        y = self._y_input(yb, training=True)
+        logp_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
+        dt = self._head_forward_backward(t, y, -1.0 / Bg, logp_sum)
+        extra = self._extra_loss()
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        if extra is not None:
+            # the regulariser is replicated on every rank: weight 1/world so that the summed
+            # gradient counts it once
+            torch.autograd.backward([t, extra], [dt, torch.full_like(extra, 1.0 / world)])
+        else:
+            t.backward(dt)
+        if world > 1:
+            self._allreduce_grads(logp_sum)
+        self.optimizer.step()
+        loss = -logp_sum.to(torch.float32) / Bg + self._log_ystd_sum()
+        if extra is not None:
+            loss = loss + extra.detach()
+        return loss.reshape(())
+
+    def _allreduce_grads(self, logp_sum):
+        """One flat all-reduce(sum) of [all parameter grads | sum logp]."""
+        params = [p for p in self.parameters() if p.grad is not None]
+        flat = torch.cat([p.grad.reshape(-1).to(torch.float64) for p in params] + [logp_sum.reshape(-1)])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        off = 0
+        for p in params:
+            n = p.numel()
+            p.grad.copy_(flat[off: off + n].view_as(p.grad))
+            off += n
+        logp_sum.copy_(flat[off:])
+
+    # ------------------------------------------------------------------ Keras-like API
+    def fit(self, x, y, batch_size=None, epochs=None, verbose=1, shuffle=True, **kwargs):
+        x, y = np.asarray(x), np.asarray(y)
+        self._assign_data_normalization(x, y)
+        assert len(x.shape) == len(y.shape) == 2, "Please pass a matrix not a vector"
+        self._assign_noise_regularisation(n_dims=x.shape[1] + y.shape[1], n_datapoints=x.shape[0])
+        batch_size = batch_size or 32          # Keras default mini-batch
+        epochs = epochs or 1
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        xd, yd = self._to_dev(x), self._to_dev(y)
+        n = xd.shape[0]
+        gen = torch.Generator(device="cpu").manual_seed(self.random_seed)
+        self.stop_training = False
+        for epoch in range(epochs):
+            perm = torch.randperm(n, generator=gen).to(self.device) if shuffle else torch.arange(n, device=self.device)
+            losses = []
+            for lo in range(0, n, batch_size):
+                idx = perm[lo: lo + batch_size]
+                gb = idx.numel()
+                if world > 1:
+                    from ..parallel import shard_rows
+                    a, b = shard_rows(gb, rank, world)
+                    idx = idx[a:b]
+                if idx.numel() == 0:
+                    continue
+                losses.append(self.train_step(xd[idx], yd[idx], global_batch=gb))
+            ep_loss = torch.stack(losses).mean().item()   # one host sync per epoch
+            self.history.append(ep_loss)
+            if verbose:
+                print("Epoch %d/%d - loss: %.4f" % (epoch + 1, epochs, ep_loss))
+            if not math.isfinite(ep_loss):                # tf.keras.callbacks.TerminateOnNaN
+                self.stop_training = True
+                break
+        self.train(False)
+        return self
+
+    def _neg_log_likelihood(self, x, y, training=False):
+        """Per-sample NLL incl. the normalisation Jacobian (BaseEstimator.py:55-59)."""
+        dist_ = self.forward(x, training=training)
+        return -dist_.log_prob(self._y_input(y, training)) + self._log_ystd_sum()
+
+    def _get_neg_log_likelihood(self):
+        return lambda y, p_y: -p_y.log_prob(self._y_input(y, self.training)) + self._log_ystd_sum()
+
+    def evaluate(self, x, y, **kwargs):
+        with torch.no_grad():
+            v = self._neg_log_likelihood(x, y).mean()
+            extra = self._extra_loss()
+            return float(v + (extra if extra is not None else 0.0))
+
+    def score(self, x_data, y_data):
+        with torch.no_grad():
+            return float(-self._neg_log_likelihood(np.asarray(x_data, np.float32), np.asarray(y_data, np.float32)).mean())
+
+    def pdf(self, x, y):
+        assert tuple(np.shape(x)) == tuple(np.shape(y))
+        with torch.no_grad():
+            output = self.forward(x)
+            y_circ = (self._to_dev(y) - self.y_mean) / self.y_std
+            return output.prob(y_circ) / torch.prod(self.y_std)
+
+    def log_pdf(self, x, y):
+        x = np.asarray(x, dtype=np.float32) if not torch.is_tensor(x) else x
+        y = np.asarray(y, dtype=np.float32) if not torch.is_tensor(y) else y
+        assert tuple(x.shape) == tuple(y.shape)
+        with torch.no_grad():
+            output = self.forward(x)
+            assert output.event_shape == y.shape[-1]
+            y_circ = (self._to_dev(y) - self.y_mean) / self.y_std
+            return output.log_prob(y_circ) - self._log_ystd_sum()

@@ -1,0 +1,171 @@
+"""Bayesian estimator: mean-field variational dense layers + the density head
+(reference estimators/BayesianNNEstimator.py, tfp.layers.DenseVariational semantics).
+
+Weight-space work (sampling, exact Normal-Normal KL) is O(#weights) and stays in torch.  The
+effect on the hot path is the S-draw posterior predictive: the reference loops 50 sequential
+forward passes (BayesianNNEstimator.py:65-76); here the S weight draws are folded into the
+batch -- one batched GEMM per layer, ONE head launch over S*B rows, then the [S, B] -> [B]
+logsumexp epilogue kernel (nfn_logmeanexp_draws).
+"""
+import math
+
+import numpy as np
+import torch
+
+from .. import functional as F
+from ..DistributionLayers import MeanFieldLayer
+from .BaseEstimator import BaseEstimator, _GaussianNoise, _Normalise
+from .MaximumLikelihoodNNEstimator import ACTIVATIONS
+
+
+class DenseVariational(torch.nn.Module):
+    """y = act(x @ kernel + bias) with (kernel, bias) ~ q = mean-field normal; adds
+    kl_weight * KL(q || prior) to the loss (exact, or one-sample estimate)."""
+
+    def __init__(self, units, kl_weight, kl_use_exact, activation, map_mode, trainable_prior, prior_scale):
+        super().__init__()
+        self.units = units
+        self.kl_weight = kl_weight
+        self.kl_use_exact = kl_use_exact
+        self.map_mode = map_mode
+        self.trainable_prior = trainable_prior
+        self.prior_scale = float(prior_scale)
+        self.act = ACTIVATIONS[activation]()
+        self.in_features = None
+        self.register_parameter("posterior_params", None)
+        self.register_parameter("prior_loc", None)
+        self.last_kl = None
+
+    def _materialise(self, in_features, device):
+        self.in_features = in_features
+        size = in_features * self.units + self.units
+        # Keras initializer "normal" = RandomNormal(stddev=0.05); prior loc starts at zero
+        self.posterior_params = torch.nn.Parameter(
+            0.05 * torch.randn(size if self.map_mode else 2 * size, device=device))
+        self.prior_loc = torch.nn.Parameter(torch.zeros(size, device=device), requires_grad=self.trainable_prior)
+        self._post = MeanFieldLayer(size, scale=None, map_mode=self.map_mode)
+        self._prior = MeanFieldLayer(size, scale=self.prior_scale)
+
+    def _dists(self):
+        return self._post(self.posterior_params), self._prior(self.prior_loc)
+
+    def _kl(self, q, r, w):
+        if self.kl_use_exact:
+            return torch.distributions.kl_divergence(q, r)
+        return q.log_prob(w) - r.log_prob(w)
+
+    def forward(self, x, n_draws=None, generator=None):
+        """x: [B, in] (one shared draw, like the reference) or [S, B, in] with n_draws=S."""
+        if self.in_features is None:
+            self._materialise(x.shape[-1], x.device)
+        q, r = self._dists()
+        loc, scale = q.base_dist.loc, q.base_dist.scale
+        nk = self.in_features * self.units
+        if n_draws is None:
+            if self.map_mode:
+                w = loc
+            else:
+                w = loc + scale * torch.randn(loc.shape, device=loc.device, generator=generator)
+            self.last_kl = self.kl_weight * self._kl(q, r, w)
+            out = x @ w[:nk].view(self.in_features, self.units) + w[nk:]
+        else:
+            if self.map_mode:
+                w = loc.expand(n_draws, -1)
+            else:
+                w = loc + scale * torch.randn((n_draws,) + tuple(loc.shape), device=loc.device, generator=generator)
+            self.last_kl = None
+            out = torch.baddbmm(w[:, nk:].unsqueeze(1), x, w[:, :nk].view(n_draws, self.in_features, self.units))
+        return self.act(out)
+
+
+class BayesianNNEstimator(BaseEstimator):
+    def __init__(self, dist_layer, kl_weight_scale, kl_use_exact=True, hidden_sizes=(10,), activation="tanh",
+                 learning_rate=3e-2, noise_reg=("fixed_rate", 0.0), trainable_prior=False, map_mode=False,
+                 prior_scale=1.0, random_seed=22, device=None):
+        torch.manual_seed(random_seed)
+        torch.nn.Module.__init__(self)
+        self.map_mode = map_mode
+        self._bayes_cfg = dict(trainable_prior=trainable_prior, prior_scale=prior_scale, map_mode=map_mode)
+        layers = self._get_dense_layers(hidden_sizes=hidden_sizes, output_size=dist_layer.get_total_param_size(),
+                                        posterior=None, prior=None, kl_weight_scale=kl_weight_scale,
+                                        kl_use_exact=kl_use_exact, activation=activation)
+        super().__init__(layers, dist_layer, noise_fn_type=noise_reg[0], noise_scale_factor=noise_reg[1],
+                         random_seed=random_seed, device=device)
+        self.map_mode = map_mode
+        self.learning_rate = learning_rate
+        # instance-level noise levels (the reference shadows the class variables, :38-39)
+        self.x_noise_std = 0.0
+        self.y_noise_std = 0.0
+        # all ranks must draw the same weights in data-parallel training
+        self._wgen = None
+
+    def _set_noise(self, std):
+        self.x_noise_std = std
+        self.y_noise_std = std
+
+    def _get_dense_layers(self, hidden_sizes, output_size, posterior=None, prior=None, kl_weight_scale=1.0,
+                          kl_use_exact=True, activation="relu"):
+        assert type(hidden_sizes) == tuple or type(hidden_sizes) == list
+        assert kl_weight_scale <= 1.0
+        cfg = getattr(self, "_bayes_cfg", dict(trainable_prior=False, prior_scale=1.0, map_mode=False))
+        mk = lambda units, act: DenseVariational(units, kl_weight_scale, kl_use_exact, act, cfg["map_mode"],
+                                                 cfg["trainable_prior"], cfg["prior_scale"])
+        normalization = [_Normalise(self)]
+        noise_reg = [_GaussianNoise(self, "x_noise_std")]
+        hidden = [mk(size, activation) for size in hidden_sizes]
+        output = [mk(output_size, "linear")]
+        return normalization + noise_reg + hidden + output
+
+    # ------------------------------------------------------------------ forward with folded draws
+    def _weight_generator(self):
+        if self._wgen is None:
+            self._wgen = torch.Generator(device=self.device).manual_seed(self.random_seed + 1)
+        return self._wgen
+
+    def params_from_x(self, x):
+        h = self._to_dev(x)
+        for layer in self.net:
+            h = layer(h, generator=self._weight_generator()) if isinstance(layer, DenseVariational) else layer(h)
+        return h
+
+    def params_from_x_draws(self, x, n_draws):
+        """t[S*B, P] for S posterior weight draws folded into the batch (draw-major)."""
+        h = self._to_dev(x)
+        h = self.net[1](self.net[0](h))
+        h = h.unsqueeze(0).expand(n_draws, -1, -1)
+        for layer in self.net[2:]:
+            h = layer(h, n_draws=n_draws, generator=self._weight_generator())
+        return h.reshape(n_draws * h.shape[1], h.shape[2])
+
+    def _extra_loss(self):
+        kls = [l.last_kl for l in self.net if isinstance(l, DenseVariational) and l.last_kl is not None]
+        return torch.stack(kls).sum() if kls else None
+
+    def fit(self, x, y, batch_size=None, epochs=None, verbose=1, **kwargs):
+        self._assign_data_normalization(np.asarray(x), np.asarray(y))
+        with torch.no_grad():
+            self.params_from_x(np.asarray(x)[:2])
+        if self.optimizer is None:
+            self.optimizer = torch.optim.Adam(self.parameters(), lr=self.learning_rate, eps=1e-7)
+        return super().fit(x, y, batch_size=batch_size, epochs=epochs, verbose=verbose, **kwargs)
+
+    def log_posterior_predictive(self, x_data, y_data, posterior_draws=None, max_rows=1 << 22):
+        """log (1/S) sum_s p(y | x, w_s) per sample, S draws folded into the batch."""
+        S = posterior_draws or (1 if self.map_mode else 50)
+        x = self._to_dev(np.asarray(x_data, np.float32) if not torch.is_tensor(x_data) else x_data)
+        y = self._y_input(y_data, training=False)
+        B = x.shape[0]
+        chunk = max(1, max_rows // S)
+        out = torch.empty(B, dtype=torch.float32, device=self.device)
+        self.train(False)
+        with torch.no_grad():
+            for lo in range(0, B, chunk):
+                hi = min(B, lo + chunk)
+                t = self.params_from_x_draws(x[lo:hi], S)
+                yy = y[lo:hi].repeat(S, 1)
+                logp = self.dist_layer(t).log_prob(yy) - self._log_ystd_sum()
+                out[lo:hi] = F.logmeanexp_draws(logp.view(S, hi - lo))
+        return out
+
+    def score(self, x_data, y_data, posterior_draws=None):
+        return float(self.log_posterior_predictive(x_data, y_data, posterior_draws).mean())

@@ -1,0 +1,62 @@
+"""Maximum-likelihood estimator: MLP -> distribution layer, Adam on the mean NLL
+(reference estimators/MaximumLikelihoodNNEstimator.py)."""
+import torch
+
+from .BaseEstimator import BaseEstimator, _GaussianNoise, _Normalise
+
+ACTIVATIONS = {"relu": torch.nn.ReLU, "tanh": torch.nn.Tanh, "linear": torch.nn.Identity,
+               "sigmoid": torch.nn.Sigmoid, "elu": torch.nn.ELU}
+
+
+class _Dense(torch.nn.Module):
+    """Keras Dense: glorot-uniform kernel, zero bias, activation."""
+
+    def __init__(self, units, activation):
+        super().__init__()
+        self.linear = torch.nn.LazyLinear(units)
+        self.act = ACTIVATIONS[activation]()
+        self._init = False
+
+    def forward(self, x):
+        if not self._init:
+            out = self.linear(x)  # materialises the lazy weight
+            with torch.no_grad():
+                torch.nn.init.xavier_uniform_(self.linear.weight)
+                self.linear.bias.zero_()
+            self._init = True
+        return self.act(self.linear(x))
+
+
+class MaximumLikelihoodNNEstimator(BaseEstimator):
+    def __init__(self, dist_layer, hidden_sizes=(16, 16), noise_reg=("fixed_rate", 0.0), learning_rate=3e-3,
+                 activation="relu", random_seed=22, device=None):
+        assert len(noise_reg) == 2
+        torch.manual_seed(random_seed)
+        torch.nn.Module.__init__(self)  # so helper modules can hold a reference to self
+        layers = self._get_dense_layers(hidden_sizes=hidden_sizes, output_size=dist_layer.get_total_param_size(),
+                                        activation=activation)
+        super().__init__(layers, dist_layer, noise_fn_type=noise_reg[0], noise_scale_factor=noise_reg[1],
+                         random_seed=random_seed, device=device)
+        self.learning_rate = learning_rate
+
+    def _get_dense_layers(self, hidden_sizes, output_size, activation):
+        assert type(hidden_sizes) == tuple or type(hidden_sizes) == list
+        normalization = [_Normalise(self)]
+        noise_reg = [_GaussianNoise(self, "x_noise_std")]
+        hidden = [_Dense(size, activation) for size in hidden_sizes]
+        output = [_Dense(output_size, "linear")]
+        return normalization + noise_reg + hidden + output
+
+    def _ensure_optimizer(self):
+        if self.optimizer is None:
+            # Keras Adam defaults (epsilon 1e-7)
+            self.optimizer = torch.optim.Adam(self.parameters(), lr=self.learning_rate, eps=1e-7)
+
+    def fit(self, x, y, batch_size=None, epochs=None, verbose=1, **kwargs):
+        import numpy as np
+
+        self._assign_data_normalization(np.asarray(x), np.asarray(y))
+        with torch.no_grad():  # materialise lazy layers before the optimiser sees the parameters
+            self.params_from_x(np.asarray(x)[:2])
+        self._ensure_optimizer()
+        return super().fit(x, y, batch_size=batch_size, epochs=epochs, verbose=verbose, **kwargs)

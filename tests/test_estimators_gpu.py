@@ -1,0 +1,149 @@
+"""GPU: the estimator facade (reference API: fit / log_pdf / pdf / score, Bayesian variant
+with S draws folded into the batch) on top of the fused kernels."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import flow_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+
+def _cosine(n):
+    from normalizingflownetwork_b200.simulation import gen_cosine_noise_data
+
+    return gen_cosine_noise_data(n, noise_std=0.3, heterosced_noise=0.5)
+
+
+def _oracle_log_pdf(model, x, y):
+    """float64 oracle on the model's own network output: isolates the head + normalisation."""
+    with torch.no_grad():
+        t = model.params_from_x(x).double().cpu()
+    y64 = (torch.tensor(y, dtype=torch.float64) - model.y_mean.double().cpu()) / model.y_std.double().cpu()
+    layer = model.dist_layer
+    lp = fo.chain_log_prob(t, y64, list(layer._flow_types), layer._n_dims, layer._trainable_base_dist)
+    return (lp - torch.sum(torch.log(model.y_std.double().cpu()))).numpy()
+
+
+def test_dense_layer_generation(cuda_device):
+    from normalizingflownetwork_b200.estimators import BayesNormalizingFlowNetwork, NormalizingFlowNetwork
+
+    layers = NormalizingFlowNetwork(1)._get_dense_layers(hidden_sizes=(2, 2, 2), output_size=2, activation="linear")
+    assert len(layers) == 6
+    layers = BayesNormalizingFlowNetwork(1, 1.0)._get_dense_layers(hidden_sizes=(2, 2, 2), output_size=2,
+                                                                 posterior=None, prior=None)
+    assert len(layers) == 6
+
+
+@pytest.mark.parametrize("name,kwargs", [("NFN", dict(n_flows=3)), ("MDN", dict(n_centers=5)), ("KMN", dict(n_centers=5))])
+@pytest.mark.parametrize("d", [1, 3])
+def test_ml_model_output_dims(cuda_device, name, kwargs, d):
+    from normalizingflownetwork_b200.estimators import ESTIMATORS
+
+    x_train = np.linspace([[-1]] * d, [[1]] * d, 10).reshape((10, d))
+    y_train = np.linspace([[-1]] * d, [[1]] * d, 10).reshape((10, d)) + 0.01 * np.random.default_rng(0).normal(size=(10, d))
+    model = ESTIMATORS[name](d, **kwargs)
+    model.fit(x_train, y_train, epochs=1, verbose=0)
+    output = model(x_train)
+    assert output.event_shape == [d]
+    assert output.batch_shape == [10]
+    lp = output.log_prob([[0.0] * d])
+    assert tuple(lp.shape) == (10,) and torch.isfinite(lp).all()
+    assert tuple(model.pdf(x_train, y_train).shape) == (10,)
+
+
+def test_nfn_log_pdf_matches_oracle_and_training_improves(cuda_device):
+    from normalizingflownetwork_b200.estimators import NormalizingFlowNetwork
+
+    x, y = _cosine(2048)
+    model = NormalizingFlowNetwork.build_function(n_dims=1, n_flows=3, hidden_sizes=(16, 16), activation="tanh")
+    model.fit(x, y, batch_size=256, epochs=2, verbose=0)
+    first = model.history[0]
+    model.fit(x, y, batch_size=256, epochs=25, verbose=0)
+    assert model.history[-1] < first - 0.1, model.history
+    got = model.log_pdf(x, y).cpu().numpy()
+    ref = _oracle_log_pdf(model, x, y)
+    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) <= 1e-5
+    np.testing.assert_allclose(model.pdf(x, y).cpu().numpy(), np.exp(ref), rtol=2e-5, atol=1e-7)
+    # score == -evaluate (reference tests/test_evaluation.py:29)
+    assert model.score(x, y) == pytest.approx(-model.evaluate(x, y), rel=1e-5)
+    assert model.score(x, y) == pytest.approx(float(np.mean(ref)), rel=1e-5)
+    # noise is off at test time: pdf is deterministic (reference tests/test_noise_reg.py)
+    assert torch.equal(model.pdf(x, y), model.pdf(x, y))
+
+
+def test_train_step_gradients_match_float64_autograd(cuda_device):
+    """One fused train step vs float64 torch autograd through the oracle on a CPU copy of the MLP."""
+    from normalizingflownetwork_b200.estimators import NormalizingFlowNetwork
+
+    x, y = _cosine(512)
+    model = NormalizingFlowNetwork(1, n_flows=3, hidden_sizes=(16, 16), activation="tanh", learning_rate=0.0)
+    model.fit(x, y, batch_size=512, epochs=1, verbose=0, shuffle=False)  # lr = 0: weights unchanged
+    lin = [m.linear for m in model.net if hasattr(m, "linear")]
+    W = [(l.weight.detach().double().cpu().requires_grad_(True), l.bias.detach().double().cpu().requires_grad_(True))
+         for l in lin]
+    xm, xs = model.x_mean.double().cpu(), model.x_std.double().cpu()
+    h = (torch.tensor(x, dtype=torch.float64) - xm) / (xs + 1e-8)
+    for i, (w, b) in enumerate(W):
+        h = h @ w.T + b
+        if i < len(W) - 1:
+            h = torch.tanh(h)
+    y64 = (torch.tensor(y, dtype=torch.float64) - model.y_mean.double().cpu()) / model.y_std.double().cpu()
+    nll = -fo.chain_log_prob(h, y64, ["radial"] * 3, 1, True).mean()
+    nll.backward()
+    model.optimizer.zero_grad(set_to_none=True)
+    loss = model.train_step(model._to_dev(x), model._to_dev(y))
+    assert float(loss) == pytest.approx(float(nll) + float(torch.sum(torch.log(model.y_std.double().cpu()))), rel=1e-5)
+    for l, (w, b) in zip(lin, W):
+        gw, gb = l.weight.grad.double().cpu(), l.bias.grad.double().cpu()
+        scale = max(1e-3, float(w.grad.abs().max()))
+        assert float((gw - w.grad).abs().max()) <= 1e-4 * scale
+        assert float((gb - b.grad).abs().max()) <= 1e-4 * max(1e-3, float(b.grad.abs().max()))
+
+
+def test_mdn_and_kmn_train(cuda_device):
+    from normalizingflownetwork_b200.estimators import KernelMixtureNetwork, MixtureDensityNetwork
+
+    x, y = _cosine(1024)
+    for model in (MixtureDensityNetwork(1, n_centers=5, activation="tanh"),
+                  KernelMixtureNetwork(1, n_centers=10, activation="tanh")):
+        model.fit(x, y, batch_size=128, epochs=12, verbose=0)
+        assert np.isfinite(model.history).all()
+        assert model.history[-1] < model.history[0]
+        assert np.isfinite(model.score(x, y))
+    assert model.dist_layer.scale_vars.grad is not None  # KMN bandwidths are trained through dscales
+
+
+def test_bayesian_nfn(cuda_device):
+    from normalizingflownetwork_b200.estimators import BayesNormalizingFlowNetwork
+    from normalizingflownetwork_b200.evaluation.scorers import DummySklearWrapper, bayesian_log_likelihood_score
+
+    x, y = _cosine(512)
+    for n_flows, tb in [(3, False), (0, True), (10, True)]:
+        m = BayesNormalizingFlowNetwork(1, kl_weight_scale=1.0 / x.shape[0], n_flows=n_flows, hidden_sizes=(16, 16),
+                                        trainable_base_dist=tb)
+        m.fit(x, y, batch_size=64, epochs=2, verbose=0)
+        out = m(x[:10])
+        assert out.event_shape == [1] and out.batch_shape == [10]
+        assert tuple(out.log_prob([[0.0]]).shape) == (10,)
+        assert tuple(m.pdf(x[:10], y[:10]).shape) == (10,)
+        assert np.isfinite(m.history).all()
+    # S draws folded into the batch == logsumexp over the draws - log S
+    S, B = 8, 100
+    m.train(False)
+    with torch.no_grad():
+        m._wgen = torch.Generator(device=cuda_device).manual_seed(5)
+        t = m.params_from_x_draws(x[:B], S)
+        assert tuple(t.shape) == (S * B, m.dist_layer.get_total_param_size())
+        yy = m._y_input(y[:B], training=False)
+        logp = (m.dist_layer(t).log_prob(yy.repeat(S, 1)) - m._log_ystd_sum()).view(S, B)
+        ref = torch.logsumexp(logp.double(), 0) - np.log(S)
+        m._wgen = torch.Generator(device=cuda_device).manual_seed(5)
+        got = m.log_posterior_predictive(x[:B], y[:B], posterior_draws=S)
+    np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    # Bayes: stochastic between calls; MAP: deterministic (reference tests/test_bayesian_estimator.py:83-135)
+    assert m.score(x, y, posterior_draws=4) != m.score(x, y, posterior_draws=4)
+    mm = BayesNormalizingFlowNetwork(1, kl_weight_scale=1.0 / x.shape[0], n_flows=2, map_mode=True)
+    mm.fit(x, y, batch_size=64, epochs=1, verbose=0)
+    assert mm.score(x, y) == mm.score(x, y)
+    assert np.isfinite(bayesian_log_likelihood_score(DummySklearWrapper(m), x, y))
