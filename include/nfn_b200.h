@@ -96,12 +96,14 @@ int nfn_chain_forward(const nfn_chain_desc* desc, const float* t, const float* y
  *   dt         [B, P] device out:  cot_b * d logp_b / d t[b, :]
  *   dy         [B, d] device out, nullable: cot_b * d logp_b / d y[b, :] (requires y_rows == B)
  *   logp_sum   device double*, nullable: += sum_b logp_b  (one atomic per CTA)
- *   dt_colsum  [P] device, nullable: += sum_b dt[b, :]  (gradient of the bias of the
- *              Dense(P) layer that emits t, MaximumLikelihoodNNEstimator.py:43)
+ *   dt_colsum  device double[P], nullable: += sum_b dt[b, :]  (gradient of the bias of the
+ *              Dense(P) layer that emits t, MaximumLikelihoodNNEstimator.py:43).  logp_sum and
+ *              dt_colsum may be adjacent in ONE fp64 buffer so that a data-parallel step
+ *              reduces both with a single all-reduce.
  */
 int nfn_chain_forward_backward(const nfn_chain_desc* desc, const float* t, const float* y,
                                int64_t y_rows, const float* g_logp, float g_scale, float* logp,
-                               float* dt, float* dy, double* logp_sum, float* dt_colsum,
+                               float* dt, float* dy, double* logp_sum, double* dt_colsum,
                                int64_t B, void* stream);
 
 /*
@@ -123,7 +125,7 @@ int nfn_mdn_forward(int n_centers, int n_dims, const float* t, const float* y, i
                     float* logp, int64_t B, void* stream);
 int nfn_mdn_forward_backward(int n_centers, int n_dims, const float* t, const float* y,
                              int64_t y_rows, const float* g_logp, float g_scale, float* logp,
-                             float* dt, float* dy, double* logp_sum, float* dt_colsum, int64_t B,
+                             float* dt, float* dy, double* logp_sum, double* dt_colsum, int64_t B,
                              void* stream);
 
 /*
@@ -150,14 +152,14 @@ int nfn_logmeanexp_draws(const float* logp_sb, int64_t S, int64_t B, float* out,
 /*
  * HOST-buffer entry points (the end-to-end call): same semantics as the device entry
  * points with every pointer a HOST pointer.  logp_sum is a host double* (overwritten,
- * nullable); dt_colsum a host float[P] (overwritten, nullable).  Copies are chunked and
+ * nullable); dt_colsum a host double[P] (overwritten, nullable).  Copies are chunked and
  * overlapped with compute on library-owned streams.  Blocking.
  */
 int nfn_chain_forward_host(const nfn_chain_desc* desc, const float* t, const float* y,
                            int64_t y_rows, float* logp, int64_t B);
 int nfn_chain_forward_backward_host(const nfn_chain_desc* desc, const float* t, const float* y,
                                     int64_t y_rows, const float* g_logp, float g_scale,
-                                    float* logp, float* dt, double* logp_sum, float* dt_colsum,
+                                    float* logp, float* dt, double* logp_sum, double* dt_colsum,
                                     int64_t B);
 int nfn_mdn_forward_backward_host(int n_centers, int n_dims, const float* t, const float* y,
                                   int64_t y_rows, const float* g_logp, float g_scale, float* logp,

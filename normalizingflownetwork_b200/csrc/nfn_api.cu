@@ -186,7 +186,7 @@ int nfn_chain_forward(const nfn_chain_desc* desc, const float* t, const float* y
 
 int nfn_chain_forward_backward(const nfn_chain_desc* desc, const float* t, const float* y,
                                int64_t y_rows, const float* g_logp, float g_scale, float* logp,
-                               float* dt, float* dy, double* logp_sum, float* dt_colsum, int64_t B,
+                               float* dt, float* dy, double* logp_sum, double* dt_colsum, int64_t B,
                                void* stream) {
   int rc = check_desc(desc);
   if (rc != NFN_OK) return rc;
@@ -250,7 +250,7 @@ int nfn_mdn_forward(int n_centers, int n_dims, const float* t, const float* y, i
 
 int nfn_mdn_forward_backward(int n_centers, int n_dims, const float* t, const float* y,
                              int64_t y_rows, const float* g_logp, float g_scale, float* logp,
-                             float* dt, float* dy, double* logp_sum, float* dt_colsum, int64_t B,
+                             float* dt, float* dy, double* logp_sum, double* dt_colsum, int64_t B,
                              void* stream) {
   int rc = mix_common(n_centers, n_dims, t, y, y_rows, logp, B);
   if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
@@ -313,7 +313,7 @@ struct HostPipe {
   void* buf[NS] = {};
   size_t cap[NS] = {};
   double* acc[NS] = {};    // device: logp_sum per slot
-  float* colacc[NS] = {};  // device: dt_colsum per slot
+  double* colacc[NS] = {}; // device: dt_colsum per slot
   size_t colcap = 0;
   bool live = false;
 
@@ -345,7 +345,7 @@ struct HostPipe {
       for (int i = 0; i < NS; ++i) {
         if (colacc[i]) cudaFree(colacc[i]);
         colacc[i] = nullptr;
-        if ((e = cudaMalloc((void**)&colacc[i], (size_t)P * sizeof(float))) != cudaSuccess)
+        if ((e = cudaMalloc((void**)&colacc[i], (size_t)P * sizeof(double))) != cudaSuccess)
           return cuda_error(e, "cudaMalloc(colacc)");
       }
       colcap = (size_t)P;
@@ -379,10 +379,10 @@ struct ChunkPtrs {
 template <class Run>
 static int host_pipeline(int P, int d, bool bwd, const float* t, const float* y, int64_t y_rows,
                          const float* g_logp, float* logp, float* dt, double* logp_sum,
-                         float* dt_colsum, int64_t B, Run run) {
+                         double* dt_colsum, int64_t B, Run run) {
   if (B == 0) {
     if (logp_sum) *logp_sum = 0.0;
-    if (dt_colsum) memset(dt_colsum, 0, (size_t)P * sizeof(float));
+    if (dt_colsum) memset(dt_colsum, 0, (size_t)P * sizeof(double));
     return NFN_OK;
   }
   // ~16 MiB of parameters per chunk, at least 3 chunks in flight when B allows it
@@ -402,7 +402,7 @@ static int host_pipeline(int P, int d, bool bwd, const float* t, const float* y,
     if ((e = cudaMemsetAsync(hp.acc[s], 0, sizeof(double), hp.stream[s])) != cudaSuccess)
       return cuda_error(e, "cudaMemsetAsync");
     if (bwd && dt_colsum && P > 0 &&
-        (e = cudaMemsetAsync(hp.colacc[s], 0, (size_t)P * sizeof(float), hp.stream[s])) != cudaSuccess)
+        (e = cudaMemsetAsync(hp.colacc[s], 0, (size_t)P * sizeof(double), hp.stream[s])) != cudaSuccess)
       return cuda_error(e, "cudaMemsetAsync");
   }
   int64_t done = 0;
@@ -440,8 +440,8 @@ static int host_pipeline(int P, int d, bool bwd, const float* t, const float* y,
       return cuda_error(e, "D2H dt");
   }
   double sum = 0.0;
-  std::vector<float> col((size_t)(P > 0 ? P : 1));
-  if (dt_colsum) memset(dt_colsum, 0, (size_t)P * sizeof(float));
+  std::vector<double> col((size_t)(P > 0 ? P : 1));
+  if (dt_colsum) memset(dt_colsum, 0, (size_t)P * sizeof(double));
   for (int s = 0; s < HostPipe::NS; ++s) {
     if ((e = cudaStreamSynchronize(hp.stream[s])) != cudaSuccess) return cuda_error(e, "stream sync");
     double part = 0.0;
@@ -449,7 +449,7 @@ static int host_pipeline(int P, int d, bool bwd, const float* t, const float* y,
       return cuda_error(e, "D2H logp_sum");
     sum += part;
     if (bwd && dt_colsum && P > 0) {
-      if ((e = cudaMemcpy(col.data(), hp.colacc[s], (size_t)P * sizeof(float), cudaMemcpyDeviceToHost)) !=
+      if ((e = cudaMemcpy(col.data(), hp.colacc[s], (size_t)P * sizeof(double), cudaMemcpyDeviceToHost)) !=
           cudaSuccess)
         return cuda_error(e, "D2H dt_colsum");
       for (int j = 0; j < P; ++j) dt_colsum[j] += col[j];
@@ -471,7 +471,7 @@ int nfn_chain_forward_host(const nfn_chain_desc* desc, const float* t, const flo
   const int P = param_size(desc);
   if (B > 0 && (!y || !logp || (P > 0 && !t))) return set_error(NFN_ERR_NULL, "t, y and logp must be non-NULL");
   return host_pipeline(P, desc->n_dims, false, t, y, y_rows, nullptr, logp, nullptr, nullptr, nullptr, B,
-                       [&](const ChunkPtrs& p, int64_t n, int64_t yr, const float*, double*, float*,
+                       [&](const ChunkPtrs& p, int64_t n, int64_t yr, const float*, double*, double*,
                            cudaStream_t st) {
                          return nfn_chain_forward(desc, p.t, p.y, yr, p.logp, n, st);
                        });
@@ -479,7 +479,7 @@ int nfn_chain_forward_host(const nfn_chain_desc* desc, const float* t, const flo
 
 int nfn_chain_forward_backward_host(const nfn_chain_desc* desc, const float* t, const float* y,
                                     int64_t y_rows, const float* g_logp, float g_scale, float* logp,
-                                    float* dt, double* logp_sum, float* dt_colsum, int64_t B) {
+                                    float* dt, double* logp_sum, double* dt_colsum, int64_t B) {
   int rc = check_desc(desc);
   if (rc != NFN_OK) return rc;
   if ((rc = check_rows(B, y_rows)) != NFN_OK) return rc;
@@ -488,7 +488,7 @@ int nfn_chain_forward_backward_host(const nfn_chain_desc* desc, const float* t, 
     return set_error(NFN_ERR_NULL, "t, y, logp and dt must be non-NULL");
   return host_pipeline(P, desc->n_dims, true, t, y, y_rows, g_logp, logp, dt, logp_sum, dt_colsum, B,
                        [&](const ChunkPtrs& p, int64_t n, int64_t yr, const float* g, double* acc,
-                           float* col, cudaStream_t st) {
+                           double* col, cudaStream_t st) {
                          return nfn_chain_forward_backward(desc, p.t, p.y, yr, g, g_scale, p.logp, p.dt,
                                                            nullptr, acc, col, n, st);
                        });
@@ -504,7 +504,7 @@ int nfn_mdn_forward_backward_host(int n_centers, int n_dims, const float* t, con
   if (B > 0 && (!t || !y || !logp || !dt)) return set_error(NFN_ERR_NULL, "t, y, logp and dt must be non-NULL");
   const int P = 2 * n_centers * n_dims + n_centers;
   return host_pipeline(P, n_dims, true, t, y, y_rows, g_logp, logp, dt, logp_sum, nullptr, B,
-                       [&](const ChunkPtrs& p, int64_t n, int64_t yr, const float* g, double* acc, float*,
+                       [&](const ChunkPtrs& p, int64_t n, int64_t yr, const float* g, double* acc, double*,
                            cudaStream_t st) {
                          return nfn_mdn_forward_backward(n_centers, n_dims, p.t, p.y, yr, g, g_scale, p.logp,
                                                          p.dt, nullptr, acc, nullptr, n, st);

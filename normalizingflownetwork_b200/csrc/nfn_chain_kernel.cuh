@@ -63,7 +63,7 @@ struct ChainArgs {
   float* dt;
   float* dy;
   double* logp_sum;
-  float* dt_colsum;
+  double* dt_colsum;
   long long B;
   float g_scale;
   int y_broadcast;
@@ -305,6 +305,42 @@ NFN_DEVI double block_sum(double v, double* scratch /* >= T/32 doubles */) {
   return s;
 }
 
+// ---------------------------------------------------------------- column sums of a dt tile
+// s_col[j] += sum over the tile's valid rows of tile[row][j].  All T threads take part:
+// thread -> (row chunk, column group of V columns); V-wide LDS, one shared atomic per column.
+template <int P, int S, int T, int V>
+NFN_DEVI void colsum_tile(const float* tile, int rows, float* s_col) {
+  constexpr int G = (P + V - 1) / V;              // column groups (V | P by construction of V)
+  constexpr int NCH = (T / G) > 0 ? (T / G) : 1;  // row chunks handled in parallel
+  constexpr int R = (T + NCH - 1) / NCH;          // rows per chunk
+  for (int u = threadIdx.x; u < G * NCH; u += T) {
+    const int g = u % G, c = u / G;
+    const int r0 = c * R;
+    int r1 = r0 + R;
+    if (r1 > rows) r1 = rows;
+    float acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = 0.0f;
+    const float* p = tile + g * V;
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r) {
+      if constexpr (V == 4) {
+        const float4 x = *reinterpret_cast<const float4*>(p + r * S);
+        acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
+      } else if constexpr (V == 2) {
+        const float2 x = *reinterpret_cast<const float2*>(p + r * S);
+        acc[0] += x.x; acc[1] += x.y;
+      } else {
+        acc[0] += p[r * S];
+      }
+    }
+    if (r0 < rows) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) atomicAdd(&s_col[g * V + v], acc[v]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- the kernel
 template <class Spec, bool BWD, class M, int T, int NB, int MINB>
 __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
@@ -319,10 +355,13 @@ __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
   __shared__ double red[T / 32];
 
   const long long ntiles = (a.B + T - 1) / T;
-  constexpr int NCOL = P > 0 ? (P + T - 1) / T : 1;
-  float colsum[NCOL];  // thread tid accumulates columns tid, tid+T, ... of dt over this CTA's tiles
-#pragma unroll
-  for (int c = 0; c < NCOL; ++c) colsum[c] = 0.0f;
+  // per-CTA column sums of dt (bias gradient of the emitting layer), kept in smem across tiles
+  __shared__ float s_col[BWD && P > 0 ? P : 1];
+  if constexpr (BWD && P > 0) {
+    if (a.dt_colsum) {
+      for (int j = threadIdx.x; j < P; j += T) s_col[j] = 0.0f;
+    }
+  }
   double lsum = 0.0;
 
   const unsigned smem_base = smem_u32(smem);
@@ -413,16 +452,7 @@ __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
       IO::store(smem_base + (unsigned)slot * kBufBytes, a.dt, tile * T, a.B);
       if (a.dt_colsum) {
         const long long rem = a.B - tile * T;
-        const int rows = rem < T ? (int)rem : T;
-#pragma unroll
-        for (int c = 0; c < NCOL; ++c) {
-          const int j = threadIdx.x + c * T;
-          if (j < P) {
-            float acc = 0.0f;
-            for (int rr = 0; rr < rows; ++rr) acc += buf[rr * S + j];
-            colsum[c] += acc;
-          }
-        }
+        colsum_tile<P, S, T, V>(buf, rem < T ? (int)rem : T, s_col);
       }
       __syncthreads();
     } else if constexpr (P > 0) {
@@ -438,11 +468,8 @@ __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
   }
   if constexpr (BWD && P > 0) {
     if (a.dt_colsum) {
-#pragma unroll
-      for (int c = 0; c < NCOL; ++c) {
-        const int j = threadIdx.x + c * T;
-        if (j < P) atomicAdd(a.dt_colsum + j, colsum[c]);
-      }
+      __syncthreads();
+      for (int j = threadIdx.x; j < P; j += T) atomicAdd(a.dt_colsum + j, (double)s_col[j]);
     }
   }
 }

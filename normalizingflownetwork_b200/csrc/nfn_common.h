@@ -128,7 +128,7 @@ struct MixArgs {
   float* dy;
   float* dscales;       // KMN only
   double* logp_sum;
-  float* dt_colsum;
+  double* dt_colsum;
   long long B;
   float g_scale;
   int y_broadcast;
@@ -137,6 +137,6 @@ struct MixArgs {
 int launch_mdn(int d, bool bwd, const MixArgs& a, cudaStream_t st);
 int launch_kmn(int d, bool bwd, const MixArgs& a, cudaStream_t st);
 int launch_logmeanexp(const float* in, long long S, long long B, float* out, cudaStream_t st);
-int launch_colsum(const float* dt, long long B, int P, float* out, cudaStream_t st);
+int launch_colsum(const float* dt, long long B, int P, double* out, cudaStream_t st);
 
 }  // namespace nfn

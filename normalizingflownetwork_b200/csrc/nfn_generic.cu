@@ -233,7 +233,7 @@ cudaError_t launch_flow_single(int type, int d, const float* t, const float* z, 
 // ------------------------------------------------------------------ column sums of dt
 // out[j] += sum_b dt[b, j]; used by the generic chain path and the mixture heads.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dt, long long B, int P,
-                                                     float* __restrict__ out) {
+                                                     double* __restrict__ out) {
   extern __shared__ float acc[];
   for (int j = threadIdx.x; j < P; j += blockDim.x) acc[j] = 0.0f;
   __syncthreads();
@@ -244,10 +244,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
   if (hi > total) hi = total;
   for (long long e = lo + threadIdx.x; e < hi; e += blockDim.x) atomicAdd(&acc[e % P], __ldg(dt + e));
   __syncthreads();
-  for (int j = threadIdx.x; j < P; j += blockDim.x) atomicAdd(out + j, acc[j]);
+  for (int j = threadIdx.x; j < P; j += blockDim.x) atomicAdd(out + j, (double)acc[j]);
 }
 
-int launch_colsum(const float* dt, long long B, int P, float* out, cudaStream_t st) {
+int launch_colsum(const float* dt, long long B, int P, double* out, cudaStream_t st) {
   if (B <= 0 || P <= 0) return NFN_OK;
   long long blocks = (B * (long long)P + 65535) / 65536;
   const long long cap = (long long)device_info().sm_count * 4;

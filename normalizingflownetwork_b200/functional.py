@@ -81,7 +81,7 @@ def chain_forward_backward(t, y, flow_types, n_dims, trainable_base_dist, g_logp
     """Fused forward + reverse sweep.  Returns (logp[B], dt[B,P], dy[B,d] or None).
 
     dt = cot[:, None] * dlogp/dt with cot = g_scale * (g_logp if given else 1).
-    ``logp_sum`` (float64 [1]) and ``dt_colsum`` (float32 [P]) are accumulated into when given.
+    ``logp_sum`` (float64 [1]) and ``dt_colsum`` (float64 [P]) are accumulated into when given.
     """
     lib = _lib.load()
     desc = _lib.make_desc(flow_types, n_dims, trainable_base_dist)

@@ -158,7 +158,7 @@ def test_chain_vs_oracle_2p16(cuda_device, nfn_lib, cfg):
     y = rng.normal(0, 1.0, (B, d)).astype(np.float32)
     ref_lp, ref_dt, _ = an.chain_forward_backward(t, y, ft, d, tb, upstream=-1.0)
     lsum = torch.zeros(1, dtype=torch.float64, device=cuda_device)
-    col = torch.zeros(P, dtype=torch.float32, device=cuda_device)
+    col = torch.zeros(P, dtype=torch.float64, device=cuda_device)
     lp, dt, _ = F.chain_forward_backward(dev(t, cuda_device), dev(y, cuda_device), ft, d, tb, g_scale=-1.0,
                                          logp_sum=lsum, dt_colsum=col)
     assert_logp(lp.cpu().numpy(), ref_lp, what=cfg)
@@ -254,7 +254,7 @@ def test_host_pipeline_matches_device(cuda_device, nfn_lib):
     y = torch.randn((B, d), generator=g).pin_memory()
     logp = torch.empty(B).pin_memory()
     dt = torch.empty((B, P)).pin_memory()
-    col = torch.empty(P)
+    col = torch.empty(P, dtype=torch.float64)
     lsum = ctypes.c_double(0.0)
     desc = _lib.make_desc(ft, d, tb)
     with torch.cuda.device(cuda_device):
@@ -284,7 +284,7 @@ def test_full_size_properties_cfg2(cuda_device, nfn_lib):
     t = torch.randn((B, P), generator=g, device=cuda_device) * 0.5
     y = torch.randn((B, d), generator=g, device=cuda_device)
     lsum = torch.zeros(1, dtype=torch.float64, device=cuda_device)
-    col = torch.zeros(P, device=cuda_device)
+    col = torch.zeros(P, dtype=torch.float64, device=cuda_device)
     lp, dt, _ = F.chain_forward_backward(t, y, ft, d, tb, g_scale=-1.0 / B, logp_sum=lsum, dt_colsum=col)
     assert torch.isfinite(lp).all() and torch.isfinite(dt).all()
     assert abs(lsum.item() - lp.double().sum().item()) < 1e-7 * B
@@ -338,7 +338,7 @@ def test_mdn_vs_oracle(cuda_device, nfn_lib, math_mode, K, d, B):
     y = rng.normal(0, 1.0, (B, d)).astype(np.float32)
     ref_lp, ref_dt, ref_dy = an.mdn_forward_backward(t, y, K, d, upstream=-1.0)
     lsum = torch.zeros(1, dtype=torch.float64, device=cuda_device)
-    col = torch.zeros(P, device=cuda_device)
+    col = torch.zeros(P, dtype=torch.float64, device=cuda_device)
     lp, dt, dy = F.mdn_forward_backward(dev(t, cuda_device), dev(y, cuda_device), K, d, g_scale=-1.0, want_dy=True,
                                         logp_sum=lsum, dt_colsum=col)
     assert_logp(lp.cpu().numpy(), ref_lp)
