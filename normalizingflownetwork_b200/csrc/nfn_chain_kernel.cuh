@@ -306,40 +306,58 @@ NFN_DEVI double block_sum(double v, double* scratch /* >= T/32 doubles */) {
 }
 
 // ---------------------------------------------------------------- column sums of a dt tile
-// s_col[j] += sum over the tile's valid rows of tile[row][j].  All T threads take part:
-// thread -> (row chunk, column group of V columns); V-wide LDS, one shared atomic per column.
-template <int P, int S, int T, int V>
-NFN_DEVI void colsum_tile(const float* tile, int rows, float* s_col) {
-  constexpr int G = (P + V - 1) / V;              // column groups (V | P by construction of V)
-  constexpr int NCH = (T / G) > 0 ? (T / G) : 1;  // row chunks handled in parallel
-  constexpr int R = (T + NCH - 1) / NCH;          // rows per chunk
-  for (int u = threadIdx.x; u < G * NCH; u += T) {
-    const int g = u % G, c = u / G;
-    const int r0 = c * R;
-    int r1 = r0 + R;
-    if (r1 > rows) r1 = rows;
-    float acc[V];
+// s_col[j] += sum over the tile's valid rows of tile[row][j], without atomics (float
+// atomicAdd on shared memory is a CAS spin loop, ruinous under contention).  All T threads
+// take part: unit u -> (row chunk c, column group g of V columns) reduces its rows with V-wide
+// LDS into s_part[c][.]; after a barrier thread j owns column j and folds the NCH partials.
+// Must be called by every thread of the CTA (contains a barrier).
+template <int P, int T, int V>
+struct ColSum {
+  static constexpr int G = P / V;                        // column groups (V divides P)
+  static constexpr int NCH = (T / G) > 0 ? (T / G) : 1;  // row chunks reduced in parallel
+  static constexpr int R = (T + NCH - 1) / NCH;          // rows per chunk
+  static constexpr int kScratch = NCH > 1 ? NCH * P : 1; // <= T * V floats
+
+  template <int S>
+  NFN_DEVI static void add_tile(const float* tile, int rows, float* s_col, float* s_part) {
+    for (int u = threadIdx.x; u < G * NCH; u += T) {
+      const int g = u % G, c = u / G;
+      const int r0 = c * R;
+      int r1 = r0 + R;
+      if (r1 > rows) r1 = rows;
+      float acc[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = 0.0f;
-    const float* p = tile + g * V;
+      for (int v = 0; v < V; ++v) acc[v] = 0.0f;
+      const float* p = tile + g * V;
 #pragma unroll 4
-    for (int r = r0; r < r1; ++r) {
-      if constexpr (V == 4) {
-        const float4 x = *reinterpret_cast<const float4*>(p + r * S);
-        acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
-      } else if constexpr (V == 2) {
-        const float2 x = *reinterpret_cast<const float2*>(p + r * S);
-        acc[0] += x.x; acc[1] += x.y;
-      } else {
-        acc[0] += p[r * S];
+      for (int r = r0; r < r1; ++r) {
+        if constexpr (V == 4) {
+          const float4 x = *reinterpret_cast<const float4*>(p + r * S);
+          acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
+        } else if constexpr (V == 2) {
+          const float2 x = *reinterpret_cast<const float2*>(p + r * S);
+          acc[0] += x.x; acc[1] += x.y;
+        } else {
+          acc[0] += p[r * S];
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        if constexpr (NCH > 1) s_part[c * P + g * V + v] = acc[v];
+        else s_col[g * V + v] += acc[v];                 // one unit per column group: no sharing
       }
     }
-    if (r0 < rows) {
+    if constexpr (NCH > 1) {
+      __syncthreads();
+      for (int j = threadIdx.x; j < P; j += T) {
+        float s = 0.0f;
 #pragma unroll
-      for (int v = 0; v < V; ++v) atomicAdd(&s_col[g * V + v], acc[v]);
+        for (int c = 0; c < NCH; ++c) s += s_part[c * P + j];
+        s_col[j] += s;
+      }
     }
   }
-}
+};
 
 // ---------------------------------------------------------------- the kernel
 template <class Spec, bool BWD, class M, int T, int NB, int MINB>
@@ -356,7 +374,9 @@ __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
 
   const long long ntiles = (a.B + T - 1) / T;
   // per-CTA column sums of dt (bias gradient of the emitting layer), kept in smem across tiles
+  using CS = ColSum<(P > 0 ? P : 4), T, V>;
   __shared__ float s_col[BWD && P > 0 ? P : 1];
+  __shared__ float s_part[BWD && P > 0 ? CS::kScratch : 1];
   if constexpr (BWD && P > 0) {
     if (a.dt_colsum) {
       for (int j = threadIdx.x; j < P; j += T) s_col[j] = 0.0f;
@@ -452,7 +472,7 @@ __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
       IO::store(smem_base + (unsigned)slot * kBufBytes, a.dt, tile * T, a.B);
       if (a.dt_colsum) {
         const long long rem = a.B - tile * T;
-        colsum_tile<P, S, T, V>(buf, rem < T ? (int)rem : T, s_col);
+        CS::template add_tile<S>(buf, rem < T ? (int)rem : T, s_col, s_part);
       }
       __syncthreads();
     } else if constexpr (P > 0) {
