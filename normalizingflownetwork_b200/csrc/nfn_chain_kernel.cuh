@@ -229,10 +229,12 @@ struct TileIO {
 };
 
 // ---------------------------------------------------------------- static chain sweeps
-template <class Spec, class M, int V, int K0>
+// SAVE (fused fwd+bwd kernels): radial flows write their constrained (alpha, beta+1) back
+// over (alpha_raw, beta_raw) in the smem row so the reverse sweep skips the softplus.
+template <class Spec, class M, int V, bool SAVE, int K0>
 struct FwdSweep {
   // flows K0 .. K-1
-  NFN_DEVI static void run(const float* row, float (&z)[Spec::D], float (&zs)[Spec::KA][Spec::D],
+  NFN_DEVI static void run(float* row, float (&z)[Spec::D], float (&zs)[Spec::KA][Spec::D],
                            LogDetAcc<M>& ld) {
     if constexpr (K0 < Spec::K) {
       constexpr int D = Spec::D;
@@ -242,10 +244,19 @@ struct FwdSweep {
       Span<Spec::offset(K0), N, V>::load(row, th);
 #pragma unroll
       for (int i = 0; i < D; ++i) zs[K0][i] = z[i];
-      if constexpr (type == kPlanar) PlanarFlow<D, M>::fwd(th, z, ld);
-      else if constexpr (type == kRadial) RadialFlow<D, M>::fwd(th, z, ld);
-      else AffineFlow<D, M>::fwd(th, z, ld);
-      FwdSweep<Spec, M, V, K0 + 1>::run(row, z, zs, ld);
+      if constexpr (type == kPlanar) {
+        PlanarFlow<D, M>::fwd(th, z, ld);
+      } else if constexpr (type == kRadial) {
+        if constexpr (SAVE) {
+          RadialFlow<D, M>::fwd_save(th, z, ld);
+          Span<Spec::offset(K0), 2, V>::store(row, th);
+        } else {
+          RadialFlow<D, M>::fwd(th, z, ld);
+        }
+      } else {
+        AffineFlow<D, M>::fwd(th, z, ld);
+      }
+      FwdSweep<Spec, M, V, SAVE, K0 + 1>::run(row, z, zs, ld);
     }
   }
 };
@@ -262,7 +273,7 @@ struct BwdSweep {
       float th[N], gth[N];
       Span<Spec::offset(K0), N, V>::load(row, th);
       if constexpr (type == kPlanar) PlanarFlow<D, M>::bwd(th, zs[K0], G, cot, gth);
-      else if constexpr (type == kRadial) RadialFlow<D, M>::bwd(th, zs[K0], G, cot, gth);
+      else if constexpr (type == kRadial) RadialFlow<D, M>::bwd_saved(th, zs[K0], G, cot, gth);
       else AffineFlow<D, M>::bwd(th, zs[K0], G, cot, gth);
       Span<Spec::offset(K0), N, V>::store(row, gth);
       BwdSweep<Spec, M, V, K0 - 1>::run(row, zs, G, cot);
@@ -449,18 +460,19 @@ __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
       float* row = buf + threadIdx.x * S;
       float zs[Spec::KA][D];
       LogDetAcc<M> ld;
-      FwdSweep<Spec, M, V, 0>::run(row, z, zs, ld);
+      FwdSweep<Spec, M, V, BWD, 0>::run(row, z, zs, ld);
       using Base = BaseDist<D, Spec::BASE, M>;
       float bth[Base::NA];
       if constexpr (Spec::BASE) Span<0, 2 * D, V>::load(row, bth);
-      const float lp = Base::log_prob(bth, z) + ld.nat();
+      // fused kernel: sigma stays in registers (bth) for the reverse sweep
+      const float lp = (BWD ? Base::log_prob_save(bth, z) : Base::log_prob(bth, z)) + ld.nat();
       a.logp[r] = lp;
       lsum += (double)lp;
       if constexpr (BWD) {
         const float cot = a.g_scale * g_cur;
         float G[D];
         float gb[Base::NA];
-        Base::bwd(bth, z, cot, G, gb);
+        Base::bwd_saved(bth, z, cot, G, gb);
         if constexpr (Spec::BASE) Span<0, 2 * D, V>::store(row, gb);
         BwdSweep<Spec, M, V, Spec::K - 1>::run(row, zs, G, cot);
         if (a.dy) store_event<D>(a.dy, r, G);

@@ -139,9 +139,24 @@ template <int D, class M>
 struct RadialFlow {
   static constexpr int N = D + 2;
 
+  // fwd_save: as fwd, and replaces th[0], th[1] by the constrained alpha and beta + 1 so that
+  // the reverse sweep (bwd_saved) needs no softplus: sigmoid(x) = 1 - exp(-softplus(x)).
+  NFN_DEVI static void fwd_save(float (&th)[N], float (&z)[D], LogDetAcc<M>& ld) {
+    const float alpha = M::softplus(fmaf(0.3f, th[0], -2.0f));
+    const float spb = M::softplus(fmaf(0.1f, th[1], kC0));
+    fwd_core(alpha, spb - 1.0f, th, z, ld);
+    th[0] = alpha;
+    th[1] = spb;
+  }
+
   NFN_DEVI static void fwd(const float (&th)[N], float (&z)[D], LogDetAcc<M>& ld) {
     const float alpha = M::softplus(fmaf(0.3f, th[0], -2.0f));
     const float beta = M::softplus(fmaf(0.1f, th[1], kC0)) - 1.0f;
+    fwd_core(alpha, beta, th, z, ld);
+  }
+
+  NFN_DEVI static void fwd_core(float alpha, float beta, const float (&th)[N], float (&z)[D],
+                                LogDetAcc<M>& ld) {
     float delta[D];
     float r = 0.0f;
 #pragma unroll
@@ -172,6 +187,19 @@ struct RadialFlow {
     float alpha, sga, spb, sgb;
     M::softplus_sigmoid(fmaf(0.3f, th[0], -2.0f), alpha, sga);
     M::softplus_sigmoid(fmaf(0.1f, th[1], kC0), spb, sgb);
+    bwd_core(alpha, sga, spb, sgb, th, zin, G, cot, gth);
+  }
+
+  // th[0] = alpha, th[1] = beta + 1 as left by fwd_save
+  NFN_DEVI static void bwd_saved(const float (&th)[N], const float (&zin)[D], float (&G)[D], float cot,
+                                 float (&gth)[N]) {
+    const float sga = M::one_minus_exp_neg(th[0]);
+    const float sgb = M::one_minus_exp_neg(th[1]);
+    bwd_core(th[0], sga, th[1], sgb, th, zin, G, cot, gth);
+  }
+
+  NFN_DEVI static void bwd_core(float alpha, float sga, float spb, float sgb, const float (&th)[N],
+                                const float (&zin)[D], float (&G)[D], float cot, float (&gth)[N]) {
     const float beta = spb - 1.0f;
     float delta[D];
     float r = 0.0f, dG = 0.0f;
@@ -185,8 +213,11 @@ struct RadialFlow {
     const float ab = alpha * beta;
     const float abh = ab * h;
     const float ah = alpha * h;
-    const float rT1 = M::div(cot, 1.0f + abh);
-    const float rT2 = M::div(cot, fmaf(abh, ah, 1.0f));
+    // cot / T1 and cot / T2 from one reciprocal of T1 * T2 (both are > 0)
+    const float T1 = 1.0f + abh, T2 = fmaf(abh, ah, 1.0f);
+    const float r12 = cot * M::rcp(T1 * T2);
+    const float rT1 = T2 * r12;
+    const float rT2 = T1 * r12;
     const float k1 = (float)(D - 1) * rT1;
     // dL/dh, dL/dr, dL/d(alpha*beta) with T1 = 1+ab h, T2 = 1 + ab h (1 - h r)
     const float g_h = ab * (dG + k1 + (2.0f * ah - 1.0f) * rT2);
@@ -259,6 +290,46 @@ struct BaseDist {
 #pragma unroll
       for (int i = 0; i < D; ++i) quad = fmaf(z[i], z[i], quad);
       return -0.5f * quad - (float)D * kHalfLog2Pi;
+    }
+  }
+
+  // as log_prob, and replaces th[D+i] by sigma_i for bwd_saved
+  NFN_DEVI static float log_prob_save(float (&th)[NA], const float (&z)[D]) {
+    if constexpr (TRAINABLE) {
+      float quad = 0.0f;
+      LogDetAcc<M> ls;
+      float f = 1.0f;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const float sig = 1e-3f + M::softplus(fmaf(0.1f, th[D + i], kC0));
+        const float e = M::div(z[i] - th[i], sig);
+        quad = fmaf(e, e, quad);
+        if constexpr (M::kFast) f *= sig; else ls.add_factor(sig);
+        th[D + i] = sig;
+      }
+      if constexpr (M::kFast) ls.add_factor(f);
+      return fmaf(-0.5f, quad, -ls.nat()) - (float)D * kHalfLog2Pi;
+    } else {
+      return log_prob(th, z);
+    }
+  }
+
+  // th[D+i] = sigma_i as left by log_prob_save; d sigma / d raw = 0.1 * (1 - exp(-(sigma - 1e-3)))
+  NFN_DEVI static void bwd_saved(const float (&th)[NA], const float (&z)[D], float cot, float (&G)[D],
+                                 float (&gth)[NA]) {
+    if constexpr (TRAINABLE) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const float sg = M::one_minus_exp_neg(th[D + i] - 1e-3f);
+        const float rs = M::rcp(th[D + i]);
+        const float e = (z[i] - th[i]) * rs;
+        const float ce = cot * e * rs;
+        G[i] = -ce;
+        gth[i] = ce;
+        gth[D + i] = cot * fmaf(e, e, -1.0f) * rs * (0.1f * sg);
+      }
+    } else {
+      bwd(th, z, cot, G, gth);
     }
   }
 

@@ -35,6 +35,8 @@ struct MathAccurate {
   NFN_DEVI static float softplus(float x) {
     return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x)));
   }
+  // 1 - e^{-x}: sigmoid(v) when x = softplus(v)
+  NFN_DEVI static float one_minus_exp_neg(float x) { return -expm1f(-x); }
   // tanh(a) and sech^2(a) = 1 - tanh^2(a), the latter with full relative accuracy
   NFN_DEVI static void tanh_sech2(float a, float& th, float& s2) {
     th = tanhf(a);
@@ -75,6 +77,7 @@ struct MathFast {
     const float e = ex2(-fabsf(x) * kLog2e);
     return fmaf(lg2(1.0f + e), kLn2, fmaxf(x, 0.0f));
   }
+  NFN_DEVI static float one_minus_exp_neg(float x) { return 1.0f - ex2(-kLog2e * x); }
   NFN_DEVI static void tanh_sech2(float a, float& th, float& s2) {
     const float e = ex2(-2.0f * kLog2e * fabsf(a));
     const float r = rcp(1.0f + e);

@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) mdn_kernel(const MixArgs a
           for (int i = 0; i < D; ++i) {
             const float gm = crho * e[i] * rs[i];
             // d sigma / d raw = 0.05 * sigmoid(x), and sigmoid(x) = 1 - exp(-softplus(x))
-            const float dsig = 0.05f * (1.0f - M::exp(-th[D + i]));
+            const float dsig = 0.05f * M::one_minus_exp_neg(th[D + i]);
             th[D + i] = crho * fmaf(e[i], e[i], -1.0f) * rs[i] * dsig;
             th[i] = gm;
             dy[i] -= gm;
