@@ -25,6 +25,8 @@ struct MathAccurate {
   NFN_DEVI static float div(float a, float b) { return a / b; }
   NFN_DEVI static float log(float x) { return logf(x); }
   NFN_DEVI static float exp(float x) { return expf(x); }
+  NFN_DEVI static float ex2(float x) { return exp2f(x); }
+  NFN_DEVI static float lg2(float x) { return log2f(x); }
   // softplus(x) and sigmoid(x) from one exponential
   NFN_DEVI static void softplus_sigmoid(float x, float& sp, float& sg) {
     const float e = expf(-fabsf(x));

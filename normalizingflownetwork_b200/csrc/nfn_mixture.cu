@@ -97,21 +97,21 @@ NFN_DEVI void rt_store(const RtTile& g, unsigned smem, float* __restrict__ dst0,
   }
 }
 
-// Tile pipeline shared by the two heads: NB == 2 double-buffers inside the CTA, NB == 1 keeps
+// Tile pipeline shared by the two heads: nb == 2 double-buffers inside the CTA, nb == 1 keeps
 // one buffer per CTA and relies on the other resident CTAs for overlap (wide rows).
-template <int NB>
 struct RtPipe {
   unsigned base, buf_bytes;
+  int nb;
   int slot = 0;
   NFN_DEVI void prologue(const RtTile& g, const float* t, long long tile, long long ntiles, long long B) {
-    if constexpr (NB == 2) {
+    if (nb == 2) {
       if (tile < ntiles) rt_load_async(g, base, t, tile * kMixT, B);
       cp_async_commit();
     }
   }
   // makes the current tile resident; returns its smem byte address
   NFN_DEVI unsigned acquire(const RtTile& g, const float* t, long long tile, long long ntiles, long long B) {
-    if constexpr (NB == 2) {
+    if (nb == 2) {
       const long long nxt = tile + gridDim.x;
       if (nxt < ntiles) rt_load_async(g, base + (unsigned)(slot ^ 1) * buf_bytes, t, nxt * kMixT, B);
       cp_async_commit();
@@ -125,7 +125,7 @@ struct RtPipe {
     return base + (unsigned)slot * buf_bytes;
   }
   NFN_DEVI void advance() {
-    if constexpr (NB == 2) slot ^= 1;
+    if (nb == 2) slot ^= 1;
   }
 };
 
@@ -196,23 +196,35 @@ NFN_DEVI void lse_push(float x, float& m, float& s) {
   s = (x > m) ? fmaf(s, e, 1.0f) : s + e;
   m = fmaxf(m, x);
 }
+// the same in base 2 (x, m in log2 units): no multiply in front of the EX2
+template <class M>
+NFN_DEVI void lse2_push(float x, float& m, float& s) {
+  const float e = M::ex2(-fabsf(x - m));
+  s = (x > m) ? fmaf(s, e, 1.0f) : s + e;
+  m = fmaxf(m, x);
+}
 
 // ------------------------------------------------------------------ MDN
 // V4: rows are 16-byte aligned in smem (P % 4 == 0) so the (mu, sigma_raw) block of a
 // component, 2*D floats at offset k*2*D, can be read with the widest aligned vectors.
-template <int D, bool V4, bool BWD, class M, int NB>
-__global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) mdn_kernel(const MixArgs a, const RtTile g) {
+// LG: logits are read / their gradients written in groups of LG (4 when V4 and K % 4 == 0:
+// a scalar LDS at row stride S = 4*odd is 4-way bank conflicted, a 128-bit one is not).
+// All log-densities are carried in log2 units (one EX2 / LG2 per use, no rescaling multiply).
+template <int D, bool V4, int LG, bool BWD, class M>
+__global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) mdn_kernel(const MixArgs a, const RtTile g, const int nb) {
   extern __shared__ __align__(16) float smem[];
   __shared__ double red[kMixT / 32];
   constexpr int A = V4 ? ((2 * D) % 4 == 0 ? 4 : ((2 * D) % 2 == 0 ? 2 : 1)) : 1;
+  constexpr float kHalfLog2e = 0.5f * kLog2e;
   const int K = a.K;
   const int LO = 2 * K * D;  // logits offset
   const long long ntiles = (a.B + kMixT - 1) / kMixT;
   double lsum = 0.0;
   const int tile_floats = kMixT * g.S;
-  RtPipe<NB> pipe;
+  RtPipe pipe;
   pipe.base = smem_u32(smem);
   pipe.buf_bytes = (unsigned)tile_floats * 4u;
+  pipe.nb = nb;
 
   long long tile = blockIdx.x;
   pipe.prologue(g, a.t, tile, ntiles, a.B);
@@ -229,30 +241,41 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) mdn_kernel(const MixArgs a
     const long long r = tile * kMixT + threadIdx.x;
     if (r < a.B) {
       float* row = buf + threadIdx.x * g.S;
-      // log-softmax normaliser of the logits
+      // log-softmax normaliser of the logits (log2 units)
       float lm = -INFINITY, ls = 0.0f;
-      for (int k = 0; k < K; ++k) lse_push<M>(row[LO + k], lm, ls);
-      const float lse = lm + M::log(ls);
+      for (int k0 = 0; k0 < K; k0 += LG) {
+        float lg[LG];
+        ld_vec<LG, LG>(row + LO + k0, lg);
+#pragma unroll
+        for (int j = 0; j < LG; ++j) lse2_push<M>(lg[j] * kLog2e, lm, ls);
+      }
+      const float lse2 = lm + M::lg2(ls);
       // components, online logsumexp
       float m = -INFINITY, s = 0.0f;
-      for (int k = 0; k < K; ++k) {
-        float th[2 * D];
-        ld_vec<2 * D, A>(row + k * 2 * D, th);
-        float quad = 0.0f, prod = 1.0f;
+      for (int k0 = 0; k0 < K; k0 += LG) {
+        float lg[LG];
+        ld_vec<LG, LG>(row + LO + k0, lg);
 #pragma unroll
-        for (int i = 0; i < D; ++i) {
-          const float sig = M::softplus(fmaf(0.05f, th[D + i], kC0));
-          const float e = M::div(y[i] - th[i], sig);
-          quad = fmaf(e, e, quad);
-          prod *= sig;
-          if constexpr (BWD) th[D + i] = sig;
+        for (int j = 0; j < LG; ++j) {
+          float* blk = row + (k0 + j) * 2 * D;
+          float th[2 * D];
+          ld_vec<2 * D, A>(blk, th);
+          float quad = 0.0f, prod = 1.0f;
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            const float sig = M::softplus(fmaf(0.05f, th[D + i], kC0));
+            const float e = M::div(y[i] - th[i], sig);
+            quad = fmaf(e, e, quad);
+            prod *= sig;
+            if constexpr (BWD) th[D + i] = sig;
+          }
+          if constexpr (BWD) st_vec<2 * D, A>(blk, th);  // keep sigma for the reverse sweep
+          const float lp2 = fmaf(lg[j], kLog2e, -kHalfLog2e * quad) - M::lg2(prod);
+          lse2_push<M>(lp2, m, s);
         }
-        if constexpr (BWD) st_vec<2 * D, A>(row + k * 2 * D, th);  // keep sigma for the reverse sweep
-        const float lp = row[LO + k] - fmaf(0.5f, quad, M::log(prod));
-        lse_push<M>(lp, m, s);
       }
-      const float top = m + M::log(s);                       // logsumexp_k(logit_k + log N_k) + d/2 log 2pi
-      const float logp = top - lse - (float)D * kHalfLog2Pi;
+      const float top2 = m + M::lg2(s);  // log2 sum_k exp(logit_k + log N_k + d/2 log 2pi)
+      const float logp = (top2 - lse2) * kLn2 - (float)D * kHalfLog2Pi;
       a.logp[r] = logp;
       lsum += (double)logp;
       if constexpr (BWD) {
@@ -260,32 +283,39 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) mdn_kernel(const MixArgs a
         float dy[D];
 #pragma unroll
         for (int i = 0; i < D; ++i) dy[i] = 0.0f;
-        for (int k = 0; k < K; ++k) {
-          float th[2 * D];
-          ld_vec<2 * D, A>(row + k * 2 * D, th);           // (mu, sigma)
-          float e[D], rs[D];
-          float quad = 0.0f, prod = 1.0f;
+        for (int k0 = 0; k0 < K; k0 += LG) {
+          float lg[LG];
+          ld_vec<LG, LG>(row + LO + k0, lg);
 #pragma unroll
-          for (int i = 0; i < D; ++i) {
-            rs[i] = M::rcp(th[D + i]);
-            e[i] = (y[i] - th[i]) * rs[i];
-            quad = fmaf(e[i], e[i], quad);
-            prod *= th[D + i];
-          }
-          const float logit = row[LO + k];
-          const float lp = logit - fmaf(0.5f, quad, M::log(prod));
-          const float crho = cot * M::exp(lp - top);         // cot * responsibility
-          row[LO + k] = fmaf(-cot, M::exp(logit - lse), crho);
+          for (int j = 0; j < LG; ++j) {
+            float* blk = row + (k0 + j) * 2 * D;
+            float th[2 * D];
+            ld_vec<2 * D, A>(blk, th);                       // (mu, sigma)
+            float e[D], rs[D];
+            float quad = 0.0f, prod = 1.0f;
 #pragma unroll
-          for (int i = 0; i < D; ++i) {
-            const float gm = crho * e[i] * rs[i];
-            // d sigma / d raw = 0.05 * sigmoid(x), and sigmoid(x) = 1 - exp(-softplus(x))
-            const float dsig = 0.05f * M::one_minus_exp_neg(th[D + i]);
-            th[D + i] = crho * fmaf(e[i], e[i], -1.0f) * rs[i] * dsig;
-            th[i] = gm;
-            dy[i] -= gm;
+            for (int i = 0; i < D; ++i) {
+              rs[i] = M::rcp(th[D + i]);
+              e[i] = (y[i] - th[i]) * rs[i];
+              quad = fmaf(e[i], e[i], quad);
+              prod *= th[D + i];
+            }
+            const float l2 = lg[j] * kLog2e;
+            const float lp2 = fmaf(-kHalfLog2e, quad, l2) - M::lg2(prod);
+            const float crho = cot * M::ex2(lp2 - top2);     // cot * responsibility
+            lg[j] = fmaf(-cot, M::ex2(l2 - lse2), crho);     // cot * (rho_k - softmax_k)
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+              const float gm = crho * e[i] * rs[i];
+              // d sigma / d raw = 0.05 * sigmoid(x), and sigmoid(x) = 1 - exp(-softplus(x))
+              const float dsig = 0.05f * M::one_minus_exp_neg(th[D + i]);
+              th[D + i] = crho * fmaf(e[i], e[i], -1.0f) * rs[i] * dsig;
+              th[i] = gm;
+              dy[i] -= gm;
+            }
+            st_vec<2 * D, A>(blk, th);
           }
-          st_vec<2 * D, A>(row + k * 2 * D, th);
+          st_vec<LG, LG>(row + LO + k0, lg);
         }
         if (a.dy) store_event<D>(a.dy, r, dy);
       }
@@ -306,13 +336,13 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) mdn_kernel(const MixArgs a
 
 // ------------------------------------------------------------------ KMN
 // smem: [2 buffers of T x S logits] [locs M x D] [coef M: -0.5 / s^2] [lognorm M: -D log|s|]
-template <int D, bool BWD, class M, int NB>
-__global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) kmn_kernel(const MixArgs a, const RtTile g) {
+template <int D, bool BWD, class M>
+__global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) kmn_kernel(const MixArgs a, const RtTile g, const int nb) {
   extern __shared__ __align__(16) float smem[];
   __shared__ double red[kMixT / 32];
   const int K = a.K;
   const int tile_floats = kMixT * g.S;
-  float* s_loc = smem + NB * (size_t)tile_floats;
+  float* s_loc = smem + nb * (size_t)tile_floats;
   float* s_coef = s_loc + K * D;
   float* s_lnorm = s_coef + K;
   float* s_dsc = s_lnorm + K;  // block accumulators of d logp / d scale (BWD)
@@ -325,9 +355,10 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) kmn_kernel(const MixArgs a
   }
   const long long ntiles = (a.B + kMixT - 1) / kMixT;
   double lsum = 0.0;
-  RtPipe<NB> pipe;
+  RtPipe pipe;
   pipe.base = smem_u32(smem);
   pipe.buf_bytes = (unsigned)tile_floats * 4u;
+  pipe.nb = nb;
 
   long long tile = blockIdx.x;
   pipe.prologue(g, a.t, tile, ntiles, a.B);
@@ -431,7 +462,7 @@ static int pick_nb(size_t tile_bytes, size_t extra) {
 }
 
 template <class Kern>
-static int launch_tiled(Kern kern, const MixArgs& a, const RtTile& g, size_t smem, const char* name,
+static int launch_tiled(Kern kern, const MixArgs& a, const RtTile& g, size_t smem, int nb, const char* name,
                         cudaStream_t st) {
   const DeviceInfo& di = device_info();
   if (smem > (size_t)di.smem_optin)
@@ -446,19 +477,19 @@ static int launch_tiled(Kern kern, const MixArgs& a, const RtTile& g, size_t sme
   const long long ntiles = (a.B + kMixT - 1) / kMixT;
   long long grid = (long long)di.sm_count * occ;
   if (grid > ntiles) grid = ntiles;
-  kern<<<(unsigned)grid, kMixT, smem, st>>>(a, g);
+  kern<<<(unsigned)grid, kMixT, smem, st>>>(a, g, nb);
   count_launch();
   return cuda_error(cudaGetLastError(), name);
 }
 
-template <int D, bool V4, int NB>
-static int launch_mdn_dvn(bool bwd, const MixArgs& a, const RtTile& g, size_t smem, cudaStream_t st) {
+template <int D, bool V4, int LG>
+static int launch_mdn_dvl(bool bwd, const MixArgs& a, const RtTile& g, size_t smem, int nb, cudaStream_t st) {
   if (math_mode() == 0) {
-    return bwd ? launch_tiled(mdn_kernel<D, V4, true, MathFast, NB>, a, g, smem, "mdn_kernel", st)
-               : launch_tiled(mdn_kernel<D, V4, false, MathFast, NB>, a, g, smem, "mdn_kernel", st);
+    return bwd ? launch_tiled(mdn_kernel<D, V4, LG, true, MathFast>, a, g, smem, nb, "mdn_kernel", st)
+               : launch_tiled(mdn_kernel<D, V4, LG, false, MathFast>, a, g, smem, nb, "mdn_kernel", st);
   }
-  return bwd ? launch_tiled(mdn_kernel<D, V4, true, MathAccurate, NB>, a, g, smem, "mdn_kernel", st)
-             : launch_tiled(mdn_kernel<D, V4, false, MathAccurate, NB>, a, g, smem, "mdn_kernel", st);
+  return bwd ? launch_tiled(mdn_kernel<D, V4, LG, true, MathAccurate>, a, g, smem, nb, "mdn_kernel", st)
+             : launch_tiled(mdn_kernel<D, V4, LG, false, MathAccurate>, a, g, smem, nb, "mdn_kernel", st);
 }
 
 template <int D>
@@ -469,11 +500,9 @@ static int launch_mdn_d(bool bwd, const MixArgs& a, cudaStream_t st) {
   const int nb = pick_nb(tile, 0);
   const size_t smem = tile * nb;
   int rc;
-  if (P % 4 == 0) {
-    rc = nb == 2 ? launch_mdn_dvn<D, true, 2>(bwd, a, g, smem, st) : launch_mdn_dvn<D, true, 1>(bwd, a, g, smem, st);
-  } else {
-    rc = nb == 2 ? launch_mdn_dvn<D, false, 2>(bwd, a, g, smem, st) : launch_mdn_dvn<D, false, 1>(bwd, a, g, smem, st);
-  }
+  if (P % 4 == 0 && a.K % 4 == 0) rc = launch_mdn_dvl<D, true, 4>(bwd, a, g, smem, nb, st);
+  else if (P % 4 == 0) rc = launch_mdn_dvl<D, true, 1>(bwd, a, g, smem, nb, st);
+  else rc = launch_mdn_dvl<D, false, 1>(bwd, a, g, smem, nb, st);
   if (rc == NFN_OK && bwd && a.dt_colsum) rc = launch_colsum(a.dt, a.B, P, a.dt_colsum, st);
   return rc;
 }
@@ -492,16 +521,6 @@ int launch_mdn(int d, bool bwd, const MixArgs& a, cudaStream_t st) {
   return set_error(NFN_ERR_DESC, "n_dims=%d", d);
 }
 
-template <int D, int NB>
-static int launch_kmn_dn(bool bwd, const MixArgs& a, const RtTile& g, size_t smem, cudaStream_t st) {
-  if (math_mode() == 0) {
-    return bwd ? launch_tiled(kmn_kernel<D, true, MathFast, NB>, a, g, smem, "kmn_kernel", st)
-               : launch_tiled(kmn_kernel<D, false, MathFast, NB>, a, g, smem, "kmn_kernel", st);
-  }
-  return bwd ? launch_tiled(kmn_kernel<D, true, MathAccurate, NB>, a, g, smem, "kmn_kernel", st)
-             : launch_tiled(kmn_kernel<D, false, MathAccurate, NB>, a, g, smem, "kmn_kernel", st);
-}
-
 template <int D>
 static int launch_kmn_d(bool bwd, const MixArgs& a, cudaStream_t st) {
   const RtTile g = make_tile(a.K);
@@ -509,7 +528,12 @@ static int launch_kmn_d(bool bwd, const MixArgs& a, cudaStream_t st) {
   const size_t extra = (size_t)a.K * (D + 3) * sizeof(float);
   const int nb = pick_nb(tile, extra);
   const size_t smem = tile * nb + extra;
-  return nb == 2 ? launch_kmn_dn<D, 2>(bwd, a, g, smem, st) : launch_kmn_dn<D, 1>(bwd, a, g, smem, st);
+  if (math_mode() == 0) {
+    return bwd ? launch_tiled(kmn_kernel<D, true, MathFast>, a, g, smem, nb, "kmn_kernel", st)
+               : launch_tiled(kmn_kernel<D, false, MathFast>, a, g, smem, nb, "kmn_kernel", st);
+  }
+  return bwd ? launch_tiled(kmn_kernel<D, true, MathAccurate>, a, g, smem, nb, "kmn_kernel", st)
+             : launch_tiled(kmn_kernel<D, false, MathAccurate>, a, g, smem, nb, "kmn_kernel", st);
 }
 
 int launch_kmn(int d, bool bwd, const MixArgs& a, cudaStream_t st) {
