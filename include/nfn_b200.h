@@ -72,9 +72,20 @@ typedef struct nfn_chain_desc {
  * Returns P > 0 or a negative nfn_status. */
 int nfn_chain_param_size(const nfn_chain_desc* desc);
 
-/* 1 if a compile-time specialised kernel exists for this chain, 0 if the generic
- * runtime-chain kernel will serve it, negative nfn_status on a bad descriptor. */
+/* 1 if an ahead-of-time specialised kernel is built in for this chain, 0 otherwise (the chain
+ * is then specialised at first use by the runtime compiler -- NVRTC, cached in memory and under
+ * $NFN_B200_CACHE or ~/.cache/nfn_b200 -- or, if NVRTC is unavailable / NFN_B200_JIT=0 / the
+ * chain is too long for registers, served by the generic runtime-chain kernel).  Negative
+ * nfn_status on a bad descriptor. */
 int nfn_chain_is_specialized(const nfn_chain_desc* desc);
+
+/* Number of chains the runtime specialiser has compiled or loaded in this process. */
+int nfn_jit_cache_size(void);
+
+/* Compile (but do not load) the runtime-specialised kernels of a chain: needs NVRTC but no GPU.
+ * Returns the cubin size in bytes, or a negative nfn_status with the compiler log in
+ * nfn_last_error(). */
+int64_t nfn_jit_compile_check(const nfn_chain_desc* desc, int accurate);
 
 /*
  * log_prob of TransformedDistribution(base, Invert(Chain(flows))) for B rows:

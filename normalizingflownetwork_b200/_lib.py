@@ -46,6 +46,8 @@ SIGNATURES = {
     "nfn_host_release": (ctypes.c_int, []),
     "nfn_chain_param_size": (ctypes.c_int, [ctypes.POINTER(ChainDesc)]),
     "nfn_chain_is_specialized": (ctypes.c_int, [ctypes.POINTER(ChainDesc)]),
+    "nfn_jit_cache_size": (ctypes.c_int, []),
+    "nfn_jit_compile_check": (_i64, [ctypes.POINTER(ChainDesc), ctypes.c_int]),
     "nfn_chain_forward": (ctypes.c_int, [ctypes.POINTER(ChainDesc), _c_float_p, _c_float_p, _i64,
                                         _c_float_p, _i64, ctypes.c_void_p]),
     "nfn_chain_forward_backward": (ctypes.c_int, [ctypes.POINTER(ChainDesc), _c_float_p, _c_float_p, _i64,

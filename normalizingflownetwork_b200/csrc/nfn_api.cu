@@ -75,8 +75,13 @@ std::string chain_key(int d, bool base, int k, const uint8_t* types) {
 
 void register_chain(const std::string& key, const ChainKernels& k) { registry()[key] = k; }
 
+int jit_cache_size();
+long long jit_compile_check(const nfn_chain_desc* desc, int mode, std::string& log);
+
 const ChainKernels* find_chain(const std::string& key) {
-  if (getenv("NFN_B200_FORCE_GENERIC")) return nullptr;
+  // test / tuning switches: FORCE_GENERIC skips both specialised paths, FORCE_JIT skips the
+  // ahead-of-time instances so that the runtime specialiser serves every chain
+  if (getenv("NFN_B200_FORCE_GENERIC") || getenv("NFN_B200_FORCE_JIT")) return nullptr;
   auto it = registry().find(key);
   return it == registry().end() ? nullptr : &it->second;
 }
@@ -123,6 +128,11 @@ static int chain_dispatch(const nfn_chain_desc* desc, const ChainArgs& a, bool b
   if (k && k->fn[mode][bwd ? 1 : 0]) {
     e = k->fn[mode][bwd ? 1 : 0](a, st);
   } else {
+    if (!getenv("NFN_B200_FORCE_GENERIC")) {
+      bool served = false;
+      e = launch_chain_jit(desc, key, a, bwd, mode, st, &served);
+      if (e != cudaSuccess || served) return cuda_error(e, key.c_str());
+    }
     ChainArgs g = a;
     g.dt_colsum = nullptr;  // the generic kernel leaves the column sums to a second pass
     e = launch_chain_generic(desc, g, bwd, mode, st);
@@ -160,6 +170,17 @@ int nfn_chain_param_size(const nfn_chain_desc* desc) {
   int rc = check_desc(desc);
   if (rc != NFN_OK) return rc;
   return param_size(desc);
+}
+
+int nfn_jit_cache_size(void) { return jit_cache_size(); }
+
+int64_t nfn_jit_compile_check(const nfn_chain_desc* desc, int accurate) {
+  int rc = check_desc(desc);
+  if (rc != NFN_OK) return rc;
+  std::string log;
+  const long long n = jit_compile_check(desc, accurate ? 1 : 0, log);
+  if (n < 0) return set_error(NFN_ERR_UNSUPPORTED, "NVRTC: %s", log.substr(0, 400).c_str());
+  return n;
 }
 
 int nfn_chain_is_specialized(const nfn_chain_desc* desc) {

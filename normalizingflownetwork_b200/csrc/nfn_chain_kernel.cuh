@@ -18,8 +18,6 @@
 // (reference estimators/DistributionLayers.py:245-294) and its tape gradient
 // (estimators/BaseEstimator.py:55-59 under Keras fit).
 #pragma once
-#include <cstdint>
-
 #include "nfn_flows.cuh"
 
 namespace nfn {
@@ -53,6 +51,28 @@ struct ChainSpec {
 __host__ __device__ constexpr int row_vec(int P) { return (P % 4 == 0) ? 4 : ((P % 2 == 0) ? 2 : 1); }
 __host__ __device__ constexpr int row_stride(int P) {
   return (P % 4 == 0 && (P / 4) % 2 == 0) ? P + 4 : P;
+}
+
+// Launch geometry of a specialised chain kernel: T rows per tile, NB tile buffers per CTA,
+// MINB resident CTAs per SM promised to ptxas (sets the register budget).  Defaults come
+// from A/B sweeps on B200 (profiles/tuning_r01.md): the fused forward+backward kernel wants
+// registers more than warps (2 CTAs x 4 warps with a double-buffered tile, up to 255
+// registers), the forward kernel wants one buffer per CTA and up to 4 CTAs per SM.
+struct ChainGeometry {
+  int T, NB, MINB;
+  unsigned smem_bytes;
+};
+__host__ __device__ constexpr ChainGeometry chain_geometry(int P, bool bwd) {
+  const int T = 128;
+  const int S = row_stride(P > 0 ? P : 4);
+  const unsigned tile = P > 0 ? (unsigned)(T * S * 4) : 0u;
+  // tile buffers that fit one SM (227 KB usable, ~1 KB reserved per CTA)
+  const int bufs = tile ? (int)((227u * 1024u - 6u * 1024u) / tile) : 64;
+  const int nb = (bwd && bufs >= 4) ? 2 : 1;
+  const int by_smem = bufs / nb;
+  const int want = bwd ? 2 : 4;
+  const int minb = by_smem < 1 ? 1 : (by_smem < want ? by_smem : want);
+  return ChainGeometry{T, nb, minb, tile * (unsigned)nb};
 }
 
 struct ChainArgs {
@@ -371,8 +391,8 @@ struct ColSum {
 };
 
 // ---------------------------------------------------------------- the kernel
-template <class Spec, bool BWD, class M, int T, int NB, int MINB>
-__global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
+template <class Spec, bool BWD, class M, int T, int NB>
+NFN_DEVI void chain_body(const ChainArgs& a) {
   constexpr int D = Spec::D;
   constexpr int P = Spec::P();
   using IO = TileIO<(P > 0 ? P : 4), T>;
@@ -504,6 +524,11 @@ __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
       for (int j = threadIdx.x; j < P; j += T) atomicAdd(a.dt_colsum + j, (double)s_col[j]);
     }
   }
+}
+
+template <class Spec, bool BWD, class M, int T, int NB, int MINB>
+__global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
+  chain_body<Spec, BWD, M, T, NB>(a);
 }
 
 }  // namespace nfn

@@ -38,36 +38,27 @@ void register_chain(const std::string& key, const ChainKernels& k);
 const ChainKernels* find_chain(const std::string& key);
 
 // ------------------------------------------------------------------ specialised launcher
-// Launch geometry of a specialised chain kernel: T rows per tile, NB tile buffers per CTA,
-// MINB resident CTAs per SM promised to ptxas (sets the register budget).  Defaults come
-// from A/B sweeps on B200 (profiles/tuning_r01.md): the fused forward+backward kernel wants
-// registers more than warps (2 CTAs x 4 warps with a double-buffered tile, up to 255
-// registers), the forward kernel wants one buffer per CTA and up to 4 CTAs per SM.
+// Geometry of an AOT-specialised kernel; NFN_TUNE_* macros override it for A/B variant builds.
 template <class Spec, bool BWD>
 struct ChainTune {
-  static constexpr int P = Spec::P();
+  static constexpr ChainGeometry kGeo = chain_geometry(Spec::P(), BWD);
 #ifdef NFN_TUNE_T
   static constexpr int T = NFN_TUNE_T;
 #else
-  static constexpr int T = 128;
+  static constexpr int T = kGeo.T;
 #endif
-  static constexpr int S = row_stride(P > 0 ? P : 4);
-  static constexpr size_t kTile = P > 0 ? (size_t)T * S * sizeof(float) : 0;
-  // tile buffers that fit one SM (227 KB usable, ~1 KB reserved per CTA)
-  static constexpr int kBufs = kTile ? (int)((227 * 1024 - 6 * 1024) / kTile) : 64;
-  static_assert(kBufs >= 1, "parameter row too wide for one shared-memory tile");
 #ifdef NFN_TUNE_NB
   static constexpr int NB = NFN_TUNE_NB;
 #else
-  static constexpr int NB = (BWD && kBufs >= 4) ? 2 : 1;
+  static constexpr int NB = kGeo.NB;
 #endif
 #ifdef NFN_TUNE_MINB
   static constexpr int MINB = NFN_TUNE_MINB;
 #else
-  static constexpr int kBySmem = kBufs / NB;
-  static constexpr int kWant = BWD ? 2 : 4;
-  static constexpr int MINB = kBySmem < kWant ? kBySmem : kWant;
+  static constexpr int MINB = kGeo.MINB;
 #endif
+  static constexpr size_t kTile =
+      Spec::P() > 0 ? (size_t)T * row_stride(Spec::P()) * sizeof(float) : 0;
 };
 
 template <class Spec, bool BWD, class M>
@@ -115,6 +106,11 @@ struct ChainRegistrar {
     register_chain(chain_key(Spec::D, Spec::BASE, Spec::K, types), k);
   }
 };
+
+// runtime specialiser (nfn_jit.cu): NVRTC-compiled chain_kernel for chains without an AOT
+// instance.  Returns cudaErrorNotSupported when the chain should go to the generic kernel.
+cudaError_t launch_chain_jit(const nfn_chain_desc* desc, const std::string& key, const ChainArgs& a, bool bwd,
+                             int mode, cudaStream_t st, bool* served);
 
 // mixture heads (nfn_mixture.cu)
 struct MixArgs {

@@ -1,0 +1,290 @@
+// nfn_jit.cu -- runtime specialiser: any chain the descriptor can express gets the same
+// compile-time specialised kernel as the AOT-listed ones.
+//
+// On a registry miss the chain's ChainSpec is instantiated from the embedded device headers
+// (nfn_math.cuh / nfn_flows.cuh / nfn_chain_kernel.cuh, the exact sources the AOT kernels are
+// built from) with NVRTC for sm_100a, the cubin is loaded with cudaLibraryLoadData and the
+// kernels launched through their cudaKernel_t handles.  Compiled cubins are cached in memory
+// (per process) and on disk ($NFN_B200_CACHE or ~/.cache/nfn_b200).  libnvrtc is dlopen'ed
+// lazily, so the library loads (and everything AOT works) on machines without it; if NVRTC is
+// unavailable or NFN_B200_JIT=0 the generic runtime-chain kernel serves the chain instead.
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "nfn_common.h"
+
+// embedded by build.py (csrc/_gen/nfn_jit_sources.cu)
+extern const char* const nfn_jit_src_math;
+extern const char* const nfn_jit_src_flows;
+extern const char* const nfn_jit_src_chain;
+
+namespace nfn {
+
+namespace {
+
+// ------------------------------------------------------------------ NVRTC via dlopen
+typedef struct _nvrtcProgram* nvrtcProgram;
+struct Nvrtc {
+  void* h = nullptr;
+  int (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  int (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+  int (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+  int (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+  int (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+  int (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+  int (*DestroyProgram)(nvrtcProgram*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+
+Nvrtc& nvrtc() {
+  static Nvrtc n;
+  static bool tried = false;
+  if (tried) return n;
+  tried = true;
+  const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"};
+  for (const char* nm : names) {
+    n.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (n.h) break;
+  }
+  if (!n.h) return n;
+#define NFN_SYM(field, sym) *(void**)(&n.field) = dlsym(n.h, sym)
+  NFN_SYM(CreateProgram, "nvrtcCreateProgram");
+  NFN_SYM(CompileProgram, "nvrtcCompileProgram");
+  NFN_SYM(GetCUBINSize, "nvrtcGetCUBINSize");
+  NFN_SYM(GetCUBIN, "nvrtcGetCUBIN");
+  NFN_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+  NFN_SYM(GetProgramLog, "nvrtcGetProgramLog");
+  NFN_SYM(DestroyProgram, "nvrtcDestroyProgram");
+  NFN_SYM(GetErrorString, "nvrtcGetErrorString");
+#undef NFN_SYM
+  n.ok = n.CreateProgram && n.CompileProgram && n.GetCUBINSize && n.GetCUBIN && n.GetProgramLogSize &&
+         n.GetProgramLog && n.DestroyProgram;
+  return n;
+}
+
+// ------------------------------------------------------------------ cache
+struct JitEntry {
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t kern[2] = {nullptr, nullptr};  // [bwd]
+  ChainGeometry geo[2];
+  int ctas_per_sm[2] = {0, 0};
+  int device = -1;
+  bool failed = false;
+};
+
+std::mutex g_mu;
+std::map<std::string, JitEntry> g_cache;  // key: "<chain key>|m<mode>|dev<id>"
+
+unsigned long long fnv1a(const std::string& s, unsigned long long h = 1469598103934665603ull) {
+  for (unsigned char c : s) {
+    h ^= c;
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+std::string cache_dir() {
+  const char* e = getenv("NFN_B200_CACHE");
+  std::string d;
+  if (e && *e) {
+    d = e;
+  } else {
+    const char* home = getenv("HOME");
+    d = std::string(home && *home ? home : "/tmp") + "/.cache/nfn_b200";
+  }
+  std::string cur;
+  for (size_t i = 0; i <= d.size(); ++i) {  // mkdir -p
+    if (i == d.size() || d[i] == '/') {
+      if (!cur.empty()) mkdir(cur.c_str(), 0755);
+    }
+    if (i < d.size()) cur.push_back(d[i]);
+  }
+  return d;
+}
+
+bool read_file(const std::string& path, std::vector<char>& out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  out.resize(n > 0 ? (size_t)n : 0);
+  const bool ok = n > 0 && fread(out.data(), 1, (size_t)n, f) == (size_t)n;
+  fclose(f);
+  return ok;
+}
+
+void write_file_atomic(const std::string& path, const std::vector<char>& data) {
+  const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  const bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
+  fclose(f);
+  if (ok) rename(tmp.c_str(), path.c_str()); else remove(tmp.c_str());
+}
+
+// ------------------------------------------------------------------ program text
+std::string program_source(const nfn_chain_desc* d, int mode, const ChainGeometry (&geo)[2]) {
+  std::string spec = "nfn::ChainSpec<" + std::to_string(d->n_dims) + ", " + (d->trainable_base ? "true" : "false");
+  for (int k = 0; k < d->n_flows; ++k) spec += ", " + std::to_string((int)d->flow_type[k]);
+  spec += ">";
+  const char* math = mode == 0 ? "nfn::MathFast" : "nfn::MathAccurate";
+  std::string s = "#include \"nfn_chain_kernel.cuh\"\n";
+  s += "using Spec = " + spec + ";\n";
+  const char* names[2] = {"nfn_jit_chain_fwd", "nfn_jit_chain_fwd_bwd"};
+  for (int b = 0; b < 2; ++b) {
+    s += "extern \"C\" __global__ void __launch_bounds__(" + std::to_string(geo[b].T) + ", " +
+         std::to_string(geo[b].MINB) + ") " + names[b] + "(const nfn::ChainArgs a) {\n  nfn::chain_body<Spec, " +
+         (b ? "true" : "false") + ", " + math + ", " + std::to_string(geo[b].T) + ", " + std::to_string(geo[b].NB) +
+         ">(a);\n}\n";
+  }
+  return s;
+}
+
+bool compile_cubin(const std::string& src, std::vector<char>& cubin, std::string& log) {
+  Nvrtc& n = nvrtc();
+  if (!n.ok) {
+    log = "libnvrtc.so.12 not found";
+    return false;
+  }
+  const char* headers[3] = {nfn_jit_src_math, nfn_jit_src_flows, nfn_jit_src_chain};
+  const char* hnames[3] = {"nfn_math.cuh", "nfn_flows.cuh", "nfn_chain_kernel.cuh"};
+  nvrtcProgram prog = nullptr;
+  int rc = n.CreateProgram(&prog, src.c_str(), "nfn_jit_chain.cu", 3, headers, hnames);
+  if (rc != 0) {
+    log = "nvrtcCreateProgram failed";
+    return false;
+  }
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-lineinfo"};
+  rc = n.CompileProgram(prog, 4, opts);
+  size_t ls = 0;
+  n.GetProgramLogSize(prog, &ls);
+  if (ls > 1) {
+    log.resize(ls);
+    n.GetProgramLog(prog, &log[0]);
+  }
+  bool ok = false;
+  if (rc == 0) {
+    size_t cs = 0;
+    if (n.GetCUBINSize(prog, &cs) == 0 && cs > 0) {
+      cubin.resize(cs);
+      ok = n.GetCUBIN(prog, cubin.data()) == 0;
+    }
+  }
+  n.DestroyProgram(&prog);
+  return ok;
+}
+
+// chains whose z history would not fit the register file are left to the generic kernel
+bool jit_eligible(const nfn_chain_desc* d, int P) {
+  if (d->n_flows * d->n_dims > 96) return false;
+  if (P > 0 && chain_geometry(P, true).smem_bytes > 200u * 1024u) return false;
+  return true;
+}
+
+}  // namespace
+
+cudaError_t launch_chain_jit(const nfn_chain_desc* desc, const std::string& key, const ChainArgs& a, bool bwd,
+                             int mode, cudaStream_t st, bool* served) {
+  *served = false;
+  const char* env = getenv("NFN_B200_JIT");
+  if (env && !strcmp(env, "0")) return cudaSuccess;
+  int P = desc->trainable_base ? 2 * desc->n_dims : 0;
+  for (int k = 0; k < desc->n_flows; ++k) P += flow_param_size(desc->flow_type[k], desc->n_dims);
+  if (!jit_eligible(desc, P)) return cudaSuccess;
+  const DeviceInfo& di = device_info();
+  const std::string ckey = key + "|m" + std::to_string(mode) + "|dev" + std::to_string(di.device);
+
+  JitEntry* ent = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto it = g_cache.find(ckey);
+    if (it == g_cache.end()) {
+      JitEntry e;
+      e.device = di.device;
+      e.geo[0] = chain_geometry(P, false);
+      e.geo[1] = chain_geometry(P, true);
+      const std::string src = program_source(desc, mode, e.geo);
+      const std::string all = src + nfn_jit_src_math + nfn_jit_src_flows + nfn_jit_src_chain + "|sm_100a|v1";
+      char name[64];
+      snprintf(name, sizeof(name), "/chain_%016llx.cubin", fnv1a(all));
+      const std::string path = cache_dir() + name;
+      std::vector<char> cubin;
+      std::string log;
+      bool have = read_file(path, cubin);
+      if (!have) {
+        have = compile_cubin(src, cubin, log);
+        if (have) write_file_atomic(path, cubin);
+        else if (getenv("NFN_B200_JIT_VERBOSE")) fprintf(stderr, "[nfn_b200 jit] %s: %s\n", key.c_str(), log.c_str());
+      }
+      if (have) {
+        cudaError_t ce = cudaLibraryLoadData(&e.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+        if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&e.kern[0], e.lib, "nfn_jit_chain_fwd");
+        if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&e.kern[1], e.lib, "nfn_jit_chain_fwd_bwd");
+        for (int b = 0; b < 2 && ce == cudaSuccess; ++b) {
+          ce = cudaFuncSetAttribute((const void*)e.kern[b], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)e.geo[b].smem_bytes);
+          int occ = 0;
+          if (ce == cudaSuccess)
+            ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e.kern[b], e.geo[b].T,
+                                                               e.geo[b].smem_bytes);
+          e.ctas_per_sm[b] = occ > 0 ? occ : 1;
+        }
+        if (ce != cudaSuccess) {
+          cudaGetLastError();
+          e.failed = true;
+        }
+      } else {
+        e.failed = true;
+      }
+      it = g_cache.emplace(ckey, e).first;
+    }
+    ent = &it->second;
+  }
+  if (ent->failed) return cudaSuccess;  // generic kernel takes over
+
+  const int b = bwd ? 1 : 0;
+  const int T = ent->geo[b].T;
+  const long long ntiles = (a.B + T - 1) / T;
+  long long grid = (long long)di.sm_count * ent->ctas_per_sm[b];
+  if (grid > ntiles) grid = ntiles;
+  ChainArgs args = a;
+  void* params[] = {&args};
+  cudaError_t ce = cudaLaunchKernel((const void*)ent->kern[b], dim3((unsigned)grid), dim3((unsigned)T), params,
+                                    ent->geo[b].smem_bytes, st);
+  if (ce == cudaSuccess) {
+    count_launch();
+    *served = true;
+  }
+  return ce;
+}
+
+// compile only (no device needed): returns the cubin size, or -1 with the NVRTC log in `log`
+long long jit_compile_check(const nfn_chain_desc* desc, int mode, std::string& log) {
+  int P = desc->trainable_base ? 2 * desc->n_dims : 0;
+  for (int k = 0; k < desc->n_flows; ++k) P += flow_param_size(desc->flow_type[k], desc->n_dims);
+  ChainGeometry geo[2] = {chain_geometry(P, false), chain_geometry(P, true)};
+  std::vector<char> cubin;
+  if (!compile_cubin(program_source(desc, mode, geo), cubin, log)) return -1;
+  return (long long)cubin.size();
+}
+
+// number of chains compiled (or loaded from the disk cache) by this process
+int jit_cache_size() {
+  std::lock_guard<std::mutex> lock(g_mu);
+  int n = 0;
+  for (auto& kv : g_cache) n += kv.second.failed ? 0 : 1;
+  return n;
+}
+
+}  // namespace nfn

@@ -8,7 +8,9 @@
 //                  Never uses tanh.approx (2^-11).  Every form is cancellation-free
 //                  (SURVEY.md App. A.5), so fp32 stays inside the 1e-5 log-prob bar.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 
 namespace nfn {
 

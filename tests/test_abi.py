@@ -76,6 +76,17 @@ def test_descriptor_validation_without_gpu(nfn_lib):
     assert nfn_lib.nfn_logmeanexp_draws(None, 0, 4, None, None) == -3
 
 
+def test_runtime_specialiser_compiles_without_gpu(nfn_lib):
+    """The embedded device headers compile under NVRTC for sm_100a (no device needed)."""
+    from normalizingflownetwork_b200 import _lib
+
+    for ft, d, tb in [(["planar", "radial"], 3, True), (["affine", "radial", "planar"], 1, False), ([], 2, True)]:
+        desc = _lib.make_desc(ft, d, tb)
+        n = nfn_lib.nfn_jit_compile_check(ctypes.byref(desc), 0)
+        assert n > 10_000, nfn_lib.nfn_last_error()
+    assert nfn_lib.nfn_jit_compile_check(ctypes.byref(_lib.make_desc(["radial"], 2, True)), 1) > 10_000
+
+
 def test_missing_library_is_loud(monkeypatch, tmp_path):
     from normalizingflownetwork_b200 import _lib
 

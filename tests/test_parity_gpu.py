@@ -54,12 +54,17 @@ def math_mode(request, nfn_lib):
     F.set_math_mode(False)
 
 
-@pytest.fixture(params=["specialized", "generic"])
+@pytest.fixture(params=["specialized", "jit", "generic"])
 def kernel_path(request):
+    """specialized: ahead-of-time instance where one exists (else runtime-specialised);
+    jit: every chain through the NVRTC runtime specialiser; generic: runtime-chain kernel."""
     if request.param == "generic":
         os.environ["NFN_B200_FORCE_GENERIC"] = "1"
+    elif request.param == "jit":
+        os.environ["NFN_B200_FORCE_JIT"] = "1"
     yield request.param
     os.environ.pop("NFN_B200_FORCE_GENERIC", None)
+    os.environ.pop("NFN_B200_FORCE_JIT", None)
 
 
 def dev(x, device):
@@ -206,6 +211,38 @@ def test_long_generic_chain_max_dims(cuda_device, nfn_lib):
     assert_logp(lp.cpu().numpy(), ref_lp, tol=5e-5)
     assert_grad(dt.cpu().numpy(), ref_dt, tol=1e-3)
     assert_grad(dy.cpu().numpy(), ref_dy, tol=1e-3)
+
+
+def test_runtime_specialiser_serves_unlisted_chains(cuda_device, nfn_lib):
+    """A chain without an ahead-of-time instance is compiled at first use (NVRTC) and cached."""
+    from normalizingflownetwork_b200 import functional as F
+
+    ft, d, tb = ["affine", "planar", "radial", "planar", "affine", "radial"], 3, True
+    assert not F.chain_is_specialized(ft, d, tb)
+    rng = np.random.default_rng(11)
+    P = an.layout(ft, d, tb)[1]
+    B = 10_000 + 3
+    t = rng.normal(0, 0.5, (B, P)).astype(np.float32)
+    y = rng.normal(0, 1.0, (B, d)).astype(np.float32)
+    ref_lp, ref_dt, ref_dy = an.chain_forward_backward(t, y, ft, d, tb, upstream=-1.0)
+    before = nfn_lib.nfn_jit_cache_size()
+    lp, dt, dy = F.chain_forward_backward(dev(t, cuda_device), dev(y, cuda_device), ft, d, tb, g_scale=-1.0,
+                                          want_dy=True)
+    assert nfn_lib.nfn_jit_cache_size() == before + 1, "the chain should have been JIT-specialised, not run generically"
+    assert_logp(lp.cpu().numpy(), ref_lp)
+    assert_grad(dt.cpu().numpy(), ref_dt)
+    assert_grad(dy.cpu().numpy(), ref_dy)
+    F.chain_forward(dev(t, cuda_device), dev(y, cuda_device), ft, d, tb)
+    assert nfn_lib.nfn_jit_cache_size() == before + 1  # second call hits the cache
+    # NFN_B200_JIT=0 sends the same chain to the generic kernel; results agree within tolerance
+    os.environ["NFN_B200_JIT"] = "0"
+    try:
+        lp_g, dt_g, _ = F.chain_forward_backward(dev(t, cuda_device), dev(y, cuda_device), ft, d, tb, g_scale=-1.0)
+    finally:
+        os.environ.pop("NFN_B200_JIT")
+    assert_logp(lp_g.cpu().numpy(), ref_lp)
+    assert torch.allclose(lp, lp_g, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(dt, dt_g, rtol=1e-3, atol=1e-4)
 
 
 def test_row_independence_bit_exact(cuda_device, nfn_lib):
