@@ -299,7 +299,9 @@ def run_ours(args):
         row = acc_base + step_no[0] * row_bytes
         lsum = ctypes.c_void_p(row + 8 * P)
         col = ctypes.c_void_p(row) if want_col else None
-        if mdn:
+        if mdn and not bwd:
+            _lib.check(lib.nfn_mdn_forward(ft[1], d, _lib.ptr(t), _lib.ptr(y), B, _lib.ptr(logp), B, stream))
+        elif mdn:
             _lib.check(lib.nfn_mdn_forward_backward(
                 ft[1], d, _lib.ptr(t), _lib.ptr(y), B, None, ctypes.c_float(g_scale), _lib.ptr(logp),
                 _lib.ptr(dt), None, lsum, None, B, stream))
@@ -369,6 +371,8 @@ def run_ours(args):
     h_sum = ctypes.c_double(0.0)
 
     def e2e_step():
+        if mdn and not bwd:
+            raise SystemExit("--fwd-only has no host entry point for the MDN head")
         if mdn:
             _lib.check(lib.nfn_mdn_forward_backward_host(
                 ft[1], d, _lib.ptr(h_t), _lib.ptr(h_y), B, None, ctypes.c_float(g_scale), _lib.ptr(h_logp),
