@@ -118,6 +118,38 @@ int nfn_chain_forward_backward(const nfn_chain_desc* desc, const float* t, const
                                int64_t B, void* stream);
 
 /*
+ * Fused compute + all-reduce for data-parallel training on the GPUs of one box (one process
+ * per GPU): as nfn_chain_forward_backward, and the LAST CTA of the launch exchanges this
+ * rank's fp64 totals [dt column sums (P) | sum logp] with every peer through NVLink peer
+ * memory (push into each peer's IPC-mapped region, flag, wait, sum in rank order --
+ * deterministic), so the step needs no separate collective launch.  `reduced` (device
+ * double[P + 1]) holds the sums over all ranks when the kernel completes.  Every rank of the
+ * communicator must make the same sequence of calls; a rank that never arrives is abandoned
+ * after ~1 s (NaN in `reduced`) instead of hanging the GPU.  want_colsum = 0 skips the
+ * in-kernel column sums (their slots stay 0 unless the caller accumulated into them).
+ *
+ * Communicator set-up (see normalizingflownetwork_b200/parallel.py:PeerComm):
+ *   nfn_peer_alloc        cudaMalloc + zero one region, export its 64-byte cudaIpc handle
+ *   (exchange the handles between the processes, e.g. torch.distributed.all_gather)
+ *   nfn_peer_open         map a peer's region (cudaIpcOpenMemHandle, lazy peer access)
+ *   nfn_peer_comm_create  regions[world] in rank order (own region = the nfn_peer_alloc pointer)
+ *   nfn_peer_allreduce    stand-alone exchange of device double[n_values] (one tiny kernel)
+ */
+typedef struct nfn_peer_comm nfn_peer_comm;
+int64_t nfn_peer_region_bytes(int world, int n_values);
+int nfn_peer_alloc(int world, int n_values, void** region, unsigned char* handle64);
+int nfn_peer_open(const unsigned char* handle64, void** mapped);
+int nfn_peer_close(void* mapped);
+int nfn_peer_free(void* region);
+int nfn_peer_comm_create(int world, int rank, int n_values, void* const* regions, nfn_peer_comm** comm);
+int nfn_peer_comm_destroy(nfn_peer_comm* comm);
+int nfn_peer_allreduce(nfn_peer_comm* comm, const double* values, double* reduced, void* stream);
+int nfn_chain_forward_backward_peer(const nfn_chain_desc* desc, const float* t, const float* y,
+                                    int64_t y_rows, const float* g_logp, float g_scale, float* logp,
+                                    float* dt, float* dy, int want_colsum, nfn_peer_comm* comm,
+                                    double* reduced, int64_t B, void* stream);
+
+/*
  * One bijector on its own: Flow(t, n_dims).forward(z) and ._forward_log_det_jacobian(z)
  * (PlanarFlow.py:68-80, RadialFlow.py:51-70, AffineFlow.py:7-9), the calls made by
  * tests/test_flows.py:19-41.  t [B, size(flow)], z [z_rows, d] (z_rows == B or 1),

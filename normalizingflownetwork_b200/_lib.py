@@ -54,6 +54,19 @@ SIGNATURES = {
                                                  _c_float_p, ctypes.c_float, _c_float_p, _c_float_p,
                                                  _c_float_p, ctypes.c_void_p, _c_float_p, _i64,
                                                  ctypes.c_void_p]),
+    "nfn_peer_region_bytes": (_i64, [ctypes.c_int, ctypes.c_int]),
+    "nfn_peer_alloc": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
+    "nfn_peer_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "nfn_peer_close": (ctypes.c_int, [ctypes.c_void_p]),
+    "nfn_peer_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "nfn_peer_comm_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]),
+    "nfn_peer_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "nfn_peer_allreduce": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, _c_float_p, ctypes.c_void_p]),
+    "nfn_chain_forward_backward_peer": (ctypes.c_int, [ctypes.POINTER(ChainDesc), _c_float_p, _c_float_p, _i64,
+                                                      _c_float_p, ctypes.c_float, _c_float_p, _c_float_p,
+                                                      _c_float_p, ctypes.c_int, ctypes.c_void_p, _c_float_p,
+                                                      _i64, ctypes.c_void_p]),
     "nfn_flow_forward": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _i64,
                                        _c_float_p, _c_float_p, _i64, ctypes.c_void_p]),
     "nfn_mdn_forward": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _i64,

@@ -140,6 +140,10 @@ static int chain_dispatch(const nfn_chain_desc* desc, const ChainArgs& a, bool b
       int rc = launch_colsum(a.dt, a.B, param_size(desc), a.dt_colsum, st);
       if (rc != NFN_OK) return rc;
     }
+    if (e == cudaSuccess && a.peer.world > 0) {  // no fused epilogue in the generic kernel
+      int rc = launch_peer_allreduce(a.peer, st);
+      if (rc != NFN_OK) return rc;
+    }
   }
   return cuda_error(e, key.c_str());
 }
@@ -225,6 +229,36 @@ int nfn_chain_forward_backward(const nfn_chain_desc* desc, const float* t, const
   a.t = t; a.y = y; a.g_logp = g_logp; a.logp = logp; a.dt = dt; a.dy = dy;
   a.logp_sum = logp_sum; a.dt_colsum = dt_colsum; a.B = B; a.g_scale = g_scale;
   a.y_broadcast = (y_rows == 1 && B != 1);
+  return chain_dispatch(desc, a, true, (cudaStream_t)stream);
+}
+
+int nfn_chain_forward_backward_peer(const nfn_chain_desc* desc, const float* t, const float* y,
+                                    int64_t y_rows, const float* g_logp, float g_scale, float* logp,
+                                    float* dt, float* dy, int want_colsum, nfn_peer_comm* comm,
+                                    double* reduced, int64_t B, void* stream) {
+  int rc = check_desc(desc);
+  if (rc != NFN_OK) return rc;
+  if ((rc = check_rows(B, y_rows)) != NFN_OK) return rc;
+  if (!comm || !reduced) return set_error(NFN_ERR_NULL, "comm and reduced must be non-NULL");
+  const int P = param_size(desc);
+  if (B > 0 && (!y || !logp || (P > 0 && (!t || !dt))))
+    return set_error(NFN_ERR_NULL, "t, y, logp and dt must be non-NULL");
+  if (!aligned(t, 16) || !aligned(dt, 16))
+    return set_error(NFN_ERR_ALIGN, "t and dt must be 16-byte aligned");
+  if (!aligned(y, event_align(desc->n_dims)))
+    return set_error(NFN_ERR_ALIGN, "y must be %zu-byte aligned", event_align(desc->n_dims));
+  if (dy && y_rows != B) return set_error(NFN_ERR_SHAPE, "dy requires y_rows == B");
+  ChainArgs a{};
+  a.peer = make_peer_args(comm, reduced);
+  if (a.peer.n_values != P + 1)
+    return set_error(NFN_ERR_SHAPE, "communicator carries %d values, the chain needs P + 1 = %d", a.peer.n_values,
+                     P + 1);
+  if (B == 0)  // nothing local to add, but every rank must still take part in the exchange
+    return launch_peer_allreduce(a.peer, (cudaStream_t)stream);
+  a.t = t; a.y = y; a.g_logp = g_logp; a.logp = logp; a.dt = dt; a.dy = dy;
+  a.logp_sum = a.peer.acc + P;
+  a.dt_colsum = want_colsum ? a.peer.acc : nullptr;
+  a.B = B; a.g_scale = g_scale; a.y_broadcast = (y_rows == 1 && B != 1);
   return chain_dispatch(desc, a, true, (cudaStream_t)stream);
 }
 

@@ -75,6 +75,23 @@ __host__ __device__ constexpr ChainGeometry chain_geometry(int P, bool bwd) {
   return ChainGeometry{T, nb, minb, tile * (unsigned)nb};
 }
 
+// In-kernel all-reduce of the fp64 accumulators over NVLink peer memory (nfn_peer.cu).
+// Every rank owns one IPC-shared region laid out as
+//   slots[2][world][n_values] doubles | flags[2][world] u64
+// (2 = step parity).  The last CTA of a launch pushes this rank's totals into slot [par][rank]
+// of EVERY peer, publishes flag = step + 1, waits for all peers' flags in its own region and
+// sums the `world` slots in rank order (deterministic).  world == 0 disables the exchange.
+constexpr int kMaxPeers = 8;
+struct PeerArgs {
+  double* base[kMaxPeers];     // peer regions as mapped into this process (own region included)
+  double* acc;                 // local accumulators [n_values], self-resetting
+  double* out;                 // reduced result [n_values], local
+  unsigned* ticket;            // CTA arrival counter, self-resetting
+  unsigned long long step;     // launch sequence number of this communicator
+  int world, rank, n_values;
+  int pad_;
+};
+
 struct ChainArgs {
   const float* t;
   const float* y;
@@ -87,6 +104,7 @@ struct ChainArgs {
   long long B;
   float g_scale;
   int y_broadcast;
+  PeerArgs peer;
 };
 
 // ---------------------------------------------------------------- smem span load/store
@@ -390,6 +408,75 @@ struct ColSum {
   }
 };
 
+// ---------------------------------------------------------------- fused peer all-reduce
+NFN_DEVI unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+NFN_DEVI double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Called by every thread of every CTA after the CTA's accumulator atomics.  The last CTA to
+// arrive runs the exchange; a peer that never shows up is abandoned after ~1 s (NaN result)
+// so that a failed rank cannot hang this GPU.
+template <int T>
+NFN_DEVI void peer_allreduce(const PeerArgs& p) {
+  __shared__ int s_last, s_timeout;
+  __threadfence();  // this CTA's atomics into p.acc are visible device-wide
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(p.ticket, 1u);
+    s_last = (t == gridDim.x - 1) ? 1 : 0;
+    s_timeout = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int W = p.world, NV = p.n_values, par = (int)(p.step & 1ull);
+  const unsigned long long want = p.step + 1ull;
+  // 1. take (and reset) the local totals, push them into slot [par][rank] of every peer
+  for (int j = threadIdx.x; j < NV; j += T) {
+    const unsigned long long bits = atomicExch(reinterpret_cast<unsigned long long*>(p.acc + j), 0ull);
+    const double v = __longlong_as_double((long long)bits);
+    for (int q = 0; q < W; ++q) {
+      double* dst = p.base[q] + ((size_t)(par * W + p.rank) * NV + j);
+      asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(dst), "d"(v) : "memory");
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. publish this rank's flag on every peer, then wait for every peer's flag here
+  if ((int)threadIdx.x < W) {
+    unsigned long long* flags_q =
+        reinterpret_cast<unsigned long long*>(p.base[threadIdx.x] + (size_t)2 * W * NV) + (par * W + p.rank);
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(flags_q), "l"(want) : "memory");
+    const unsigned long long* mine =
+        reinterpret_cast<const unsigned long long*>(p.base[p.rank] + (size_t)2 * W * NV) + (par * W + threadIdx.x);
+    const long long t0 = clock64();
+    while (ld_volatile_u64(mine) < want) {
+      if (clock64() - t0 > 2000000000ll) {  // ~1 s at 2 GHz
+        s_timeout = 1;
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  // 3. sum the world slots of this parity in rank order
+  const double* slots = p.base[p.rank] + (size_t)par * W * NV;
+  for (int j = threadIdx.x; j < NV; j += T) {
+    double sum = 0.0;
+    for (int q = 0; q < W; ++q) sum += ld_volatile_f64(slots + (size_t)q * NV + j);
+    p.out[j] = s_timeout ? __longlong_as_double(0x7ff8000000000000ll) : sum;
+  }
+  if (threadIdx.x == 0) *p.ticket = 0u;
+}
+
 // ---------------------------------------------------------------- the kernel
 template <class Spec, bool BWD, class M, int T, int NB>
 NFN_DEVI void chain_body(const ChainArgs& a) {
@@ -524,6 +611,7 @@ NFN_DEVI void chain_body(const ChainArgs& a) {
       for (int j = threadIdx.x; j < P; j += T) atomicAdd(a.dt_colsum + j, (double)s_col[j]);
     }
   }
+  if (a.peer.world > 0) peer_allreduce<T>(a.peer);
 }
 
 template <class Spec, bool BWD, class M, int T, int NB, int MINB>

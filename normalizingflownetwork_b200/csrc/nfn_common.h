@@ -10,6 +10,8 @@
 #include "../../include/nfn_b200.h"
 #include "nfn_chain_kernel.cuh"
 
+struct nfn_peer_comm;  // opaque handle of the C ABI (nfn_peer.cu)
+
 namespace nfn {
 
 int set_error(int code, const char* fmt, ...);
@@ -111,6 +113,10 @@ struct ChainRegistrar {
 // instance.  Returns cudaErrorNotSupported when the chain should go to the generic kernel.
 cudaError_t launch_chain_jit(const nfn_chain_desc* desc, const std::string& key, const ChainArgs& a, bool bwd,
                              int mode, cudaStream_t st, bool* served);
+
+// peer-memory communicator (nfn_peer.cu)
+PeerArgs make_peer_args(::nfn_peer_comm* c, double* out);
+int launch_peer_allreduce(const PeerArgs& p, cudaStream_t st);
 
 // mixture heads (nfn_mixture.cu)
 struct MixArgs {

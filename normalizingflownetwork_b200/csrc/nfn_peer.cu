@@ -1,0 +1,136 @@
+// nfn_peer.cu -- peer-memory communicator for the fused in-kernel all-reduce of the hot
+// path's fp64 accumulators ([dt column sums | sum logp]) across the GPUs of one box.
+//
+// One process per GPU.  Each rank cudaMallocs one region (slots[2][world][n] | flags[2][world]),
+// exports it with cudaIpcGetMemHandle; the Python side exchanges the 64-byte handles over
+// torch.distributed and every rank maps its peers with cudaIpcOpenMemHandle (NVLink P2P).
+// The exchange itself runs inside the compute kernel's last CTA (peer_allreduce in
+// nfn_chain_kernel.cuh) or, for kernels without that epilogue, in a one-CTA kernel here.
+#include <cstring>
+#include <new>
+
+#include "nfn_common.h"
+
+struct nfn_peer_comm {
+  int world = 0, rank = 0, n_values = 0;
+  double* base[nfn::kMaxPeers] = {};
+  double* acc = nullptr;       // [n_values] local accumulators (self-resetting)
+  unsigned* ticket = nullptr;  // CTA arrival counter (self-resetting)
+  unsigned long long step = 0;
+};
+
+namespace nfn {
+
+__global__ void __launch_bounds__(128) peer_allreduce_kernel(const PeerArgs p) { peer_allreduce<128>(p); }
+
+PeerArgs make_peer_args(nfn_peer_comm* c, double* out) {
+  PeerArgs p{};
+  for (int i = 0; i < kMaxPeers; ++i) p.base[i] = c->base[i];
+  p.acc = c->acc;
+  p.out = out;
+  p.ticket = c->ticket;
+  p.step = c->step++;
+  p.world = c->world;
+  p.rank = c->rank;
+  p.n_values = c->n_values;
+  return p;
+}
+
+int launch_peer_allreduce(const PeerArgs& p, cudaStream_t st) {
+  peer_allreduce_kernel<<<1, 128, 0, st>>>(p);
+  count_launch();
+  return cuda_error(cudaGetLastError(), "peer_allreduce_kernel");
+}
+
+static size_t region_bytes(int world, int n) {
+  return (size_t)2 * world * n * sizeof(double) + (size_t)2 * world * sizeof(unsigned long long);
+}
+
+}  // namespace nfn
+
+using namespace nfn;
+
+extern "C" {
+
+int64_t nfn_peer_region_bytes(int world, int n_values) {
+  if (world < 1 || world > kMaxPeers || n_values < 1)
+    return set_error(NFN_ERR_SHAPE, "world=%d (1..%d), n_values=%d", world, kMaxPeers, n_values);
+  return (int64_t)region_bytes(world, n_values);
+}
+
+int nfn_peer_alloc(int world, int n_values, void** region, unsigned char* handle64) {
+  if (!region || !handle64) return set_error(NFN_ERR_NULL, "region and handle must be non-NULL");
+  if (world < 1 || world > kMaxPeers || n_values < 1)
+    return set_error(NFN_ERR_SHAPE, "world=%d (1..%d), n_values=%d", world, kMaxPeers, n_values);
+  const size_t bytes = region_bytes(world, n_values);
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return cuda_error(e, "cudaMalloc(peer region)");
+  if ((e = cudaMemset(p, 0, bytes)) != cudaSuccess) return cuda_error(e, "cudaMemset(peer region)");
+  cudaIpcMemHandle_t h;
+  if ((e = cudaIpcGetMemHandle(&h, p)) != cudaSuccess) {
+    cudaFree(p);
+    return cuda_error(e, "cudaIpcGetMemHandle");
+  }
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  *region = p;
+  return NFN_OK;
+}
+
+int nfn_peer_open(const unsigned char* handle64, void** mapped) {
+  if (!handle64 || !mapped) return set_error(NFN_ERR_NULL, "handle and mapped must be non-NULL");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  return cuda_error(cudaIpcOpenMemHandle(mapped, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+
+int nfn_peer_close(void* mapped) { return cuda_error(cudaIpcCloseMemHandle(mapped), "cudaIpcCloseMemHandle"); }
+
+int nfn_peer_free(void* region) { return cuda_error(cudaFree(region), "cudaFree(peer region)"); }
+
+int nfn_peer_comm_create(int world, int rank, int n_values, void* const* regions, nfn_peer_comm** comm) {
+  if (!regions || !comm) return set_error(NFN_ERR_NULL, "regions and comm must be non-NULL");
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || n_values < 1)
+    return set_error(NFN_ERR_SHAPE, "world=%d (1..%d), rank=%d, n_values=%d", world, kMaxPeers, rank, n_values);
+  nfn_peer_comm* c = new (std::nothrow) nfn_peer_comm();
+  if (!c) return set_error(NFN_ERR_CUDA, "out of host memory");
+  c->world = world;
+  c->rank = rank;
+  c->n_values = n_values;
+  for (int i = 0; i < world; ++i) {
+    if (!regions[i]) {
+      delete c;
+      return set_error(NFN_ERR_NULL, "regions[%d] is NULL", i);
+    }
+    c->base[i] = (double*)regions[i];
+  }
+  cudaError_t e = cudaMalloc((void**)&c->acc, (size_t)n_values * sizeof(double) + 16);
+  if (e == cudaSuccess) e = cudaMemset(c->acc, 0, (size_t)n_values * sizeof(double) + 16);
+  if (e != cudaSuccess) {
+    delete c;
+    return cuda_error(e, "cudaMalloc(peer accumulators)");
+  }
+  c->ticket = (unsigned*)(c->acc + n_values);
+  *comm = c;
+  return NFN_OK;
+}
+
+int nfn_peer_comm_destroy(nfn_peer_comm* comm) {
+  if (!comm) return NFN_OK;
+  cudaFree(comm->acc);
+  delete comm;
+  return NFN_OK;
+}
+
+int nfn_peer_allreduce(nfn_peer_comm* comm, const double* values, double* reduced, void* stream) {
+  if (!comm || !values || !reduced) return set_error(NFN_ERR_NULL, "comm, values and reduced must be non-NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  // accumulate the caller's values into the (zero) local accumulators, then exchange
+  cudaError_t e = cudaMemcpyAsync(comm->acc, values, (size_t)comm->n_values * sizeof(double),
+                                  cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return cuda_error(e, "cudaMemcpyAsync(values)");
+  return launch_peer_allreduce(make_peer_args(comm, reduced), st);
+}
+
+}  // extern "C"

@@ -105,6 +105,32 @@ def chain_forward_backward(t, y, flow_types, n_dims, trainable_base_dist, g_logp
     return logp, dt, dy
 
 
+def chain_forward_backward_peer(t, y, flow_types, n_dims, trainable_base_dist, comm, g_logp=None, g_scale=1.0,
+                                want_colsum=False, reduced=None, out_logp=None, out_dt=None):
+    """Fused forward + reverse sweep + in-kernel all-reduce over NVLink peer memory.
+
+    ``comm`` is a ``parallel.PeerComm`` with ``n_values == P + 1``.  Returns
+    (logp[B], dt[B,P], reduced[P+1] float64 = [sum over ALL ranks of dt column sums | of logp]).
+    """
+    lib = _lib.load()
+    desc = _lib.make_desc(flow_types, n_dims, trainable_base_dist)
+    P = _lib.check(lib.nfn_chain_param_size(ctypes.byref(desc)))
+    t, y, B = _prep_ty(t, y, n_dims, P, "chain_forward_backward_peer")
+    dev = t.device
+    logp = out_logp if out_logp is not None else torch.empty(B, dtype=torch.float32, device=dev)
+    dt = out_dt if out_dt is not None else torch.empty((B, P), dtype=torch.float32, device=dev)
+    if reduced is None:
+        reduced = torch.empty(P + 1, dtype=torch.float64, device=dev)
+    if g_logp is not None:
+        g_logp = _as_f32_cuda(g_logp, "g_logp", device=dev).reshape(-1)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_chain_forward_backward_peer(
+            ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), y.shape[0], _lib.ptr(g_logp), ctypes.c_float(g_scale),
+            _lib.ptr(logp), _lib.ptr(dt), None, 1 if want_colsum else 0, comm.comm, _lib.ptr(reduced), B,
+            _lib.current_stream(dev)))
+    return logp, dt, reduced
+
+
 class _ChainLogProb(torch.autograd.Function):
     @staticmethod
     def forward(ctx, t, y, flow_types, n_dims, trainable_base_dist):

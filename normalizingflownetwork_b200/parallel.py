@@ -74,6 +74,76 @@ class PackedAllReduce:
         return out
 
 
+class PeerComm:
+    """Peer-memory communicator for the fused in-kernel all-reduce (include/nfn_b200.h,
+    csrc/nfn_peer.cu).  One per process / GPU.  Each rank allocates one IPC-exportable region,
+    the 64-byte cudaIpc handles are exchanged with one all_gather over the default process
+    group (NCCL), and every rank maps its peers over NVLink.  Without an initialised process
+    group the communicator is a world of one (useful on a single GPU: same code path).
+    """
+
+    def __init__(self, n_values, device):
+        import ctypes
+
+        from . import _lib
+
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.n_values = int(n_values)
+        self.device = torch.device(device)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.mapped = []
+        with torch.cuda.device(self.device):
+            region = ctypes.c_void_p()
+            handle = ctypes.create_string_buffer(64)
+            _lib.check(self.lib.nfn_peer_alloc(self.world, self.n_values, ctypes.byref(region), handle))
+            self.region = region
+            handles = [bytes(handle.raw)]
+            if self.world > 1:
+                mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=self.device)
+                gathered = [torch.empty_like(mine) for _ in range(self.world)]
+                dist.all_gather(gathered, mine)
+                handles = [bytes(g.cpu().tolist()) for g in gathered]
+            regions = (ctypes.c_void_p * self.world)()
+            for r in range(self.world):
+                if r == self.rank:
+                    regions[r] = region.value
+                else:
+                    m = ctypes.c_void_p()
+                    _lib.check(self.lib.nfn_peer_open(handles[r], ctypes.byref(m)))
+                    self.mapped.append(m)
+                    regions[r] = m.value
+            comm = ctypes.c_void_p()
+            _lib.check(self.lib.nfn_peer_comm_create(self.world, self.rank, self.n_values, regions,
+                                                     ctypes.byref(comm)))
+            self.comm = comm
+        if self.world > 1:
+            dist.barrier()  # every rank has mapped every region before the first exchange
+
+    def allreduce(self, values, out=None):
+        """Sum device float64 ``values[n_values]`` over all ranks (one tiny kernel, no NCCL)."""
+        if out is None:
+            out = torch.empty(self.n_values, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._lib.check(self.lib.nfn_peer_allreduce(self.comm, self._lib.ptr(values), self._lib.ptr(out),
+                                                        self._lib.current_stream(self.device)))
+        return out
+
+    def close(self):
+        if getattr(self, "comm", None) is None:
+            return
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier()  # nobody unmaps while a peer may still push
+            self.lib.nfn_peer_comm_destroy(self.comm)
+            for m in self.mapped:
+                self.lib.nfn_peer_close(m)
+            self.lib.nfn_peer_free(self.region)
+        self.comm = None
+
+
 def barrier():
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
