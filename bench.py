@@ -289,6 +289,8 @@ def run_ours(args):
     acc_ring = torch.zeros((K + W + 1, P + 1), dtype=torch.float64, device=device)
     want_col = bool(bwd and args.colsum and not mdn)
     packed = (world > 1 and bwd)
+    use_peer = bool(packed and args.exchange == "peer" and not mdn)
+    comm = parallel.PeerComm(P + 1, device) if use_peer else None
     step_no = [0]
     acc_base = acc_ring.data_ptr()
     row_bytes = (P + 1) * 8
@@ -301,6 +303,10 @@ def run_ours(args):
         col = ctypes.c_void_p(row) if want_col else None
         if mdn and not bwd:
             _lib.check(lib.nfn_mdn_forward(ft[1], d, _lib.ptr(t), _lib.ptr(y), B, _lib.ptr(logp), B, stream))
+        elif use_peer:  # ONE launch: fused fwd+bwd + all-reduce of [payload | sum logp] in the last CTA
+            _lib.check(lib.nfn_chain_forward_backward_peer(
+                ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), B, None, ctypes.c_float(g_scale), _lib.ptr(logp),
+                _lib.ptr(dt), None, 1 if want_col else 0, comm.comm, ctypes.c_void_p(row), B, stream))
         elif mdn:
             _lib.check(lib.nfn_mdn_forward_backward(
                 ft[1], d, _lib.ptr(t), _lib.ptr(y), B, None, ctypes.c_float(g_scale), _lib.ptr(logp),
@@ -314,7 +320,7 @@ def run_ours(args):
                                              stream))
 
     def exchange():
-        if packed:
+        if packed and not use_peer:
             torch.distributed.all_reduce(acc_ring[step_no[0]])
         step_no[0] += 1
 
@@ -400,6 +406,8 @@ def run_ours(args):
     h2d = 4 * B * (P + d)
     d2h = 4 * B * (1 + (P if bwd else 0)) + 8
     lib.nfn_host_release()
+    if comm is not None:
+        comm.close()
     # the host path must reproduce the device path bit for bit
     same = bool(torch.equal(h_logp, logp.cpu()))
 
@@ -420,7 +428,9 @@ def run_ours(args):
             "l2": "inputs+outputs per step (%d MB) exceed the 126 MB L2; no flush needed" % (
                 bytes_per_row * B // (1 << 20)),
             "parallelism": "dp%d (rows sharded, no data-path collective%s)" % (
-                world, "; one fp64 all-reduce of [P-float gradient payload | sum logp] per step" if packed else ""),
+                world, ("; [P-value gradient payload | sum logp] summed over ranks every step, " + (
+                    "fused into the kernel's last CTA over NVLink peer memory" if use_peer else
+                    "one NCCL all-reduce")) if packed else ""),
             "t_sigma": 0.5, "seed": 22,
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -448,6 +458,9 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the step sums its fp64 accumulators over ranks -- 'peer' = fused into the "
+                         "kernel's last CTA over NVLink peer memory (default), 'nccl' = a separate all-reduce")
     ap.add_argument("--colsum", action="store_true", help="also accumulate dt column sums at N=1 (tuning)")
     ap.add_argument("--fwd-only", action="store_true", help="time the forward-only kernel of the config (tuning)")
     args = ap.parse_args()

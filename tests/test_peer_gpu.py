@@ -34,7 +34,8 @@ def _check_rank(rank, world, device, steps=6):
         if world > 1:
             torch.distributed.all_reduce(local)
         assert torch.isfinite(red).all()
-        assert torch.allclose(red, local, rtol=1e-6, atol=1e-9), (step, (red - local).abs().max())
+        # column sums are accumulated in fp32 inside a CTA (fp64 across CTAs and ranks)
+        assert torch.allclose(red, local, rtol=1e-4, atol=1e-5), (step, (red - local).abs().max())
         # want_colsum = 0: only the logp slot is filled
         _, _, red2 = F.chain_forward_backward_peer(t, y, ft, d, tb, comm, g_scale=-1.0 / B)
         assert float(red2[:P].abs().max()) == 0.0
@@ -55,7 +56,7 @@ def _check_rank(rank, world, device, steps=6):
     local = torch.cat([dt.double().sum(0), lp.double().sum().reshape(1)])
     if world > 1:
         torch.distributed.all_reduce(local)
-    assert torch.allclose(red, local, rtol=1e-6, atol=1e-9)
+    assert torch.allclose(red, local, rtol=1e-4, atol=1e-5)
     comm.close()
 
 
