@@ -76,11 +76,13 @@ __host__ __device__ constexpr ChainGeometry chain_geometry(int P, bool bwd) {
 }
 
 // In-kernel all-reduce of the fp64 accumulators over NVLink peer memory (nfn_peer.cu).
-// Every rank owns one IPC-shared region laid out as
-//   slots[2][world][n_values] doubles | flags[2][world] u64
-// (2 = step parity).  The last CTA of a launch pushes this rank's totals into slot [par][rank]
-// of EVERY peer, publishes flag = step + 1, waits for all peers' flags in its own region and
-// sums the `world` slots in rank order (deterministic).  world == 0 disables the exchange.
+// Every rank owns one IPC-shared region of 8-byte words laid out as
+//   words[2][world][n_values][2]        (2 = step parity; 2 words per fp64 value)
+// Low-latency protocol (flag travels WITH the data, so no fences and no separate flag write):
+// each word carries 32 bits of the value and the 32-bit step tag; one 8-byte store is atomic.
+// The last CTA of a launch pushes this rank's totals into [par][rank] of EVERY peer, then polls
+// its own region until every peer's words carry this step's tag and sums them in rank order
+// (deterministic).  world == 0 disables the exchange.
 constexpr int kMaxPeers = 8;
 struct PeerArgs {
   double* base[kMaxPeers];     // peer regions as mapped into this process (own region included)
@@ -414,10 +416,8 @@ NFN_DEVI unsigned long long ld_volatile_u64(const unsigned long long* p) {
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-NFN_DEVI double ld_volatile_f64(const double* p) {
-  double v;
-  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
+NFN_DEVI void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // Called by every thread of every CTA after the CTA's accumulator atomics.  The last CTA to
@@ -425,54 +425,49 @@ NFN_DEVI double ld_volatile_f64(const double* p) {
 // so that a failed rank cannot hang this GPU.
 template <int T>
 NFN_DEVI void peer_allreduce(const PeerArgs& p) {
-  __shared__ int s_last, s_timeout;
+  __shared__ int s_last;
   __threadfence();  // this CTA's atomics into p.acc are visible device-wide
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned t = atomicAdd(p.ticket, 1u);
     s_last = (t == gridDim.x - 1) ? 1 : 0;
-    s_timeout = 0;
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   const int W = p.world, NV = p.n_values, par = (int)(p.step & 1ull);
-  const unsigned long long want = p.step + 1ull;
-  // 1. take (and reset) the local totals, push them into slot [par][rank] of every peer
+  const unsigned long long tag = ((p.step + 1ull) & 0xffffffffull) << 32;  // never 0 in the first 2^32 steps
   for (int j = threadIdx.x; j < NV; j += T) {
+    // 1. take (and reset) the local total, push (value half | tag) words to every peer
     const unsigned long long bits = atomicExch(reinterpret_cast<unsigned long long*>(p.acc + j), 0ull);
-    const double v = __longlong_as_double((long long)bits);
+    const unsigned long long w0 = (bits & 0xffffffffull) | tag, w1 = (bits >> 32) | tag;
+    const size_t off = ((size_t)(par * W + p.rank) * NV + j) * 2;
     for (int q = 0; q < W; ++q) {
-      double* dst = p.base[q] + ((size_t)(par * W + p.rank) * NV + j);
-      asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(dst), "d"(v) : "memory");
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.base[q]) + off;
+      st_volatile_u64(dst, w0);
+      st_volatile_u64(dst + 1, w1);
     }
-  }
-  __threadfence_system();
-  __syncthreads();
-  // 2. publish this rank's flag on every peer, then wait for every peer's flag here
-  if ((int)threadIdx.x < W) {
-    unsigned long long* flags_q =
-        reinterpret_cast<unsigned long long*>(p.base[threadIdx.x] + (size_t)2 * W * NV) + (par * W + p.rank);
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(flags_q), "l"(want) : "memory");
+    // 2. poll this rank's region for every peer's words of this step; 3. sum in rank order
     const unsigned long long* mine =
-        reinterpret_cast<const unsigned long long*>(p.base[p.rank] + (size_t)2 * W * NV) + (par * W + threadIdx.x);
-    const long long t0 = clock64();
-    while (ld_volatile_u64(mine) < want) {
-      if (clock64() - t0 > 2000000000ll) {  // ~1 s at 2 GHz
-        s_timeout = 1;
-        break;
-      }
-      __nanosleep(64);
-    }
-  }
-  __syncthreads();
-  __threadfence_system();
-  // 3. sum the world slots of this parity in rank order
-  const double* slots = p.base[p.rank] + (size_t)par * W * NV;
-  for (int j = threadIdx.x; j < NV; j += T) {
+        reinterpret_cast<const unsigned long long*>(p.base[p.rank]) + ((size_t)par * W * NV + j) * 2;
     double sum = 0.0;
-    for (int q = 0; q < W; ++q) sum += ld_volatile_f64(slots + (size_t)q * NV + j);
-    p.out[j] = s_timeout ? __longlong_as_double(0x7ff8000000000000ll) : sum;
+    bool timeout = false;
+    const long long t0 = clock64();
+    for (int q = 0; q < W; ++q) {
+      const unsigned long long* src = mine + (size_t)q * NV * 2;
+      unsigned long long a0, a1;
+      while (true) {
+        a0 = ld_volatile_u64(src);
+        a1 = ld_volatile_u64(src + 1);
+        if ((a0 & 0xffffffff00000000ull) == tag && (a1 & 0xffffffff00000000ull) == tag) break;
+        if (clock64() - t0 > 2000000000ll) {  // ~1 s at 2 GHz
+          timeout = true;
+          break;
+        }
+      }
+      sum += __longlong_as_double((long long)((a0 & 0xffffffffull) | (a1 << 32)));
+    }
+    p.out[j] = timeout ? __longlong_as_double(0x7ff8000000000000ll) : sum;
   }
   if (threadIdx.x == 0) *p.ticket = 0u;
 }

@@ -1,7 +1,7 @@
 // nfn_peer.cu -- peer-memory communicator for the fused in-kernel all-reduce of the hot
 // path's fp64 accumulators ([dt column sums | sum logp]) across the GPUs of one box.
 //
-// One process per GPU.  Each rank cudaMallocs one region (slots[2][world][n] | flags[2][world]),
+// One process per GPU.  Each rank cudaMallocs one region (words[2][world][n][2], 8 bytes each),
 // exports it with cudaIpcGetMemHandle; the Python side exchanges the 64-byte handles over
 // torch.distributed and every rank maps its peers with cudaIpcOpenMemHandle (NVLink P2P).
 // The exchange itself runs inside the compute kernel's last CTA (peer_allreduce in
@@ -43,7 +43,7 @@ int launch_peer_allreduce(const PeerArgs& p, cudaStream_t st) {
 }
 
 static size_t region_bytes(int world, int n) {
-  return (size_t)2 * world * n * sizeof(double) + (size_t)2 * world * sizeof(unsigned long long);
+  return (size_t)2 * world * n * 2 * sizeof(unsigned long long);  // words[2][world][n][2]
 }
 
 }  // namespace nfn
