@@ -449,13 +449,105 @@ def run_ours(args):
     return 0
 
 
+def run_cfg1_pipeline(args):
+    """BASELINE config 1 as the real pipeline: NormalizingFlowNetwork (3 radial flows, 1-D y,
+    MLP (16,16) tanh) on gen_cosine_noise_data(2048): latency of log_pdf and of one Adam step
+    (eager launches vs one CUDA-graph replay), next to the same pipeline on the host cores
+    (torch-CPU MLP + the fp32 op-for-op restatement of the reference's TF graph)."""
+    import torch
+
+    from normalizingflownetwork_b200.estimators import NormalizingFlowNetwork
+    from normalizingflownetwork_b200.simulation import gen_cosine_noise_data
+    from oracle import flow_oracle as fo
+
+    B = 2048
+    x, y = gen_cosine_noise_data(B, noise_std=0.3, heterosced_noise=0.5)
+    model = NormalizingFlowNetwork.build_function(n_dims=1, n_flows=3, hidden_sizes=(16, 16), activation="tanh")
+    model.fit(x, y, batch_size=B, epochs=3, verbose=0)
+    xd, yd = model._to_dev(x), model._to_dev(y)
+    K, W = args.steps, args.warmup
+
+    def timed(fn, n):
+        for _ in range(W):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / n  # us
+
+    us_logpdf = timed(lambda: model.log_pdf(xd, yd), K)
+    us_step = timed(lambda: model.train_step(xd, yd), K)
+    model.capture_train_step(B, 1, 1)
+    us_step_graph = timed(lambda: model.train_step_graphed(xd, yd), K)
+    # host-side pipeline: numpy in, numpy out, copies included
+    t0 = time.perf_counter()
+    for _ in range(K):
+        model.log_pdf(x, y).cpu()
+    us_logpdf_e2e = (time.perf_counter() - t0) * 1e6 / K
+
+    # CPU port of the same pipeline
+    torch.set_num_threads(os.cpu_count() or 1)
+    lin = [m.linear for m in model.net if hasattr(m, "linear")]
+    Ws = [(l.weight.detach().cpu().clone().requires_grad_(True), l.bias.detach().cpu().clone().requires_grad_(True))
+          for l in lin]
+    params = [p for wb in Ws for p in wb]
+    opt = torch.optim.Adam(params, lr=3e-3, eps=1e-7)
+    xm, xs = model.x_mean.cpu(), model.x_std.cpu()
+    ym, ys = model.y_mean.cpu(), model.y_std.cpu()
+    xc, yc = torch.tensor(x), torch.tensor(y)
+
+    def cpu_logp():
+        h = (xc - xm) / (xs + 1e-8)
+        for i, (w, b) in enumerate(Ws):
+            h = h @ w.T + b
+            if i < len(Ws) - 1:
+                h = torch.tanh(h)
+        return fo.chain_log_prob(h, (yc - ym) / ys, ["radial"] * 3, 1, True) - torch.sum(torch.log(ys))
+
+    def cpu_step():
+        opt.zero_grad()
+        (-cpu_logp().mean()).backward()
+        opt.step()
+
+    def cpu_timed(fn, n):
+        fn()
+        t = time.perf_counter()
+        for _ in range(n):
+            fn()
+        return (time.perf_counter() - t) * 1e6 / n
+
+    with torch.no_grad():
+        us_cpu_logpdf = cpu_timed(cpu_logp, 50)
+    us_cpu_step = cpu_timed(cpu_step, 50)
+    line = {
+        "metric": "NFN config-1 pipeline latency (log_pdf, Adam fit step), batch 2048", "unit": "us",
+        "higher_is_better": False, "n_gpus": 1, "steps": K, "warmup": W, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "NormalizingFlowNetwork 3 radial flows, 1-D y, MLP (16,16) tanh, "
+                               "gen_cosine_noise_data(2048, 0.3, 0.5), batch 2048"},
+        "value": us_step_graph, "ms_per_step": us_step_graph * 1e-3, "vs_baseline": None,
+        "log_pdf_us": us_logpdf, "log_pdf_host_in_host_out_us": us_logpdf_e2e,
+        "fit_step_eager_us": us_step, "fit_step_cuda_graph_us": us_step_graph,
+        "samples_per_s_fit_graph": B / (us_step_graph * 1e-6), "samples_per_s_log_pdf": B / (us_logpdf * 1e-6),
+        "cpu_baseline": {"kind": "port", "cores": os.cpu_count(), "log_pdf_us": us_cpu_logpdf,
+                         "fit_step_us": us_cpu_step, "unit": "us",
+                         "sample": "same 2048-row batch; torch-CPU MLP + fp32 restatement of the reference's TF graph"},
+        "note": "launch-latency-bound (197 KB of head traffic): no roofline claim",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS) + ["cfg1-pipeline"])
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
@@ -466,6 +558,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.config == "cfg1-pipeline":
+        return run_cfg1_pipeline(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -147,3 +147,18 @@ def test_bayesian_nfn(cuda_device):
     mm.fit(x, y, batch_size=64, epochs=1, verbose=0)
     assert mm.score(x, y) == mm.score(x, y)
     assert np.isfinite(bayesian_log_likelihood_score(DummySklearWrapper(m), x, y))
+
+
+def test_cuda_graph_train_step_matches_eager(cuda_device):
+    """fit(cuda_graph=True) replays one captured graph per mini-batch and learns like the eager loop."""
+    from normalizingflownetwork_b200.estimators import NormalizingFlowNetwork
+
+    x, y = _cosine(2048)
+    eager = NormalizingFlowNetwork.build_function(n_dims=1, n_flows=3, hidden_sizes=(16, 16), activation="tanh")
+    graphed = NormalizingFlowNetwork.build_function(n_dims=1, n_flows=3, hidden_sizes=(16, 16), activation="tanh")
+    eager.fit(x, y, batch_size=512, epochs=12, verbose=0)
+    graphed.fit(x, y, batch_size=512, epochs=12, verbose=0, cuda_graph=True)
+    assert np.isfinite(graphed.history).all()
+    assert graphed.history[-1] < graphed.history[0] - 0.05
+    # same seed, same data order, noise off: the two loops follow the same trajectory
+    np.testing.assert_allclose(graphed.history, eager.history, rtol=2e-3, atol=2e-3)
