@@ -196,9 +196,10 @@ class BaseEstimator(torch.nn.Module):
         self._gx = torch.zeros((batch_size, x_dim), device=self.device)
         self._gy = torch.zeros((batch_size, y_dim), device=self.device)
         saved_model = {k: v.detach().clone() for k, v in self.state_dict().items()}
-        import copy
-
-        saved_opt = copy.deepcopy(self.optimizer.state_dict())
+        # optimiser state tensors are baked into the graph by address: remember their values and
+        # put them back IN PLACE after the warm-up / capture steps (which run on zeros)
+        saved_opt = {p: {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                     for p, st in self.optimizer.state.items()}
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -210,10 +211,15 @@ class BaseEstimator(torch.nn.Module):
             self._graph_loss = self.train_step(self._gx, self._gy)
         # the warm-up and capture steps ran on zeros: restore the real state
         self.load_state_dict(saved_model)
-        self.optimizer.load_state_dict(saved_opt)
-        for st in self.optimizer.state.values():
-            if "step" in st and torch.is_tensor(st["step"]) and not st["step"].is_cuda:
-                st["step"] = st["step"].to(self.device)
+        with torch.no_grad():
+            for p, st in self.optimizer.state.items():
+                old = saved_opt.get(p, {})
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        if k in old:
+                            v.copy_(old[k])
+                        else:
+                            v.zero_()
         self._graph_batch = batch_size
         return self
 

@@ -11,17 +11,23 @@ ACTIVATIONS = {"relu": torch.nn.ReLU, "tanh": torch.nn.Tanh, "linear": torch.nn.
 class _Dense(torch.nn.Module):
     """Keras Dense: glorot-uniform kernel, zero bias, activation."""
 
-    def __init__(self, units, activation):
+    def __init__(self, units, activation, seed=0):
         super().__init__()
         self.linear = torch.nn.LazyLinear(units)
         self.act = ACTIVATIONS[activation]()
         self._init = False
+        self._seed = seed
 
     def forward(self, x):
         if not self._init:
-            out = self.linear(x)  # materialises the lazy weight
+            self.linear(x)  # materialises the lazy weight
             with torch.no_grad():
-                torch.nn.init.xavier_uniform_(self.linear.weight)
+                # own generator: the initial weights depend on (random_seed, layer), not on
+                # whatever consumed the global RNG between construction and the first call
+                gen = torch.Generator(device="cpu").manual_seed(self._seed)
+                w = torch.empty(self.linear.weight.shape)
+                torch.nn.init.xavier_uniform_(w, generator=gen)
+                self.linear.weight.copy_(w)
                 self.linear.bias.zero_()
             self._init = True
         return self.act(self.linear(x))
@@ -33,6 +39,7 @@ class MaximumLikelihoodNNEstimator(BaseEstimator):
         assert len(noise_reg) == 2
         torch.manual_seed(random_seed)
         torch.nn.Module.__init__(self)  # so helper modules can hold a reference to self
+        self.random_seed = random_seed
         layers = self._get_dense_layers(hidden_sizes=hidden_sizes, output_size=dist_layer.get_total_param_size(),
                                         activation=activation)
         super().__init__(layers, dist_layer, noise_fn_type=noise_reg[0], noise_scale_factor=noise_reg[1],
@@ -43,8 +50,9 @@ class MaximumLikelihoodNNEstimator(BaseEstimator):
         assert type(hidden_sizes) == tuple or type(hidden_sizes) == list
         normalization = [_Normalise(self)]
         noise_reg = [_GaussianNoise(self, "x_noise_std")]
-        hidden = [_Dense(size, activation) for size in hidden_sizes]
-        output = [_Dense(output_size, "linear")]
+        seed = 1000 * getattr(self, "random_seed", 22)
+        hidden = [_Dense(size, activation, seed + i) for i, size in enumerate(hidden_sizes)]
+        output = [_Dense(output_size, "linear", seed + len(hidden_sizes))]
         return normalization + noise_reg + hidden + output
 
     def _ensure_optimizer(self):
