@@ -336,22 +336,26 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) mdn_kernel(const MixArgs a
 
 // ------------------------------------------------------------------ KMN
 // smem: [2 buffers of T x S logits] [locs M x D] [coef M: -0.5 / s^2] [lognorm M: -D log|s|]
-template <int D, bool BWD, class M>
+// LG: logits read / gradients written in groups of LG (4 when M % 4 == 0, see mdn_kernel).
+template <int D, int LG, bool BWD, class M>
 __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) kmn_kernel(const MixArgs a, const RtTile g, const int nb) {
   extern __shared__ __align__(16) float smem[];
   __shared__ double red[kMixT / 32];
+  constexpr int NW = kMixT / 32;
   const int K = a.K;
   const int tile_floats = kMixT * g.S;
   float* s_loc = smem + nb * (size_t)tile_floats;
-  float* s_coef = s_loc + K * D;
-  float* s_lnorm = s_coef + K;
-  float* s_dsc = s_lnorm + K;  // block accumulators of d logp / d scale (BWD)
+  float* s_coef = s_loc + K * D;   // -0.5 log2e / s^2  (log2 units)
+  float* s_lnorm = s_coef + K;     // -D log2|s|
+  float* s_dsc = s_lnorm + K;      // [NW][K] per-warp sums of d logp / d scale (BWD): no atomics
   for (int i = threadIdx.x; i < K * D; i += kMixT) s_loc[i] = __ldg(a.locs + i);
   for (int i = threadIdx.x; i < K; i += kMixT) {
     const float sc = __ldg(a.scales + i);
-    s_coef[i] = -0.5f / (sc * sc);
-    s_lnorm[i] = -(float)D * logf(fabsf(sc));
-    if constexpr (BWD) s_dsc[i] = 0.0f;
+    s_coef[i] = -0.5f * kLog2e / (sc * sc);
+    s_lnorm[i] = -(float)D * log2f(fabsf(sc));
+  }
+  if constexpr (BWD) {
+    for (int i = threadIdx.x; i < NW * K; i += kMixT) s_dsc[i] = 0.0f;
   }
   const long long ntiles = (a.B + kMixT - 1) / kMixT;
   double lsum = 0.0;
@@ -364,6 +368,7 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) kmn_kernel(const MixArgs a
   pipe.prologue(g, a.t, tile, ntiles, a.B);
   EventPrefetch<D, BWD> pf;
   pf.first(a, tile, ntiles);
+  float* my_dsc = s_dsc + (threadIdx.x >> 5) * K;
 
   for (; tile < ntiles; tile += gridDim.x) {
     float y[D];
@@ -375,23 +380,29 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) kmn_kernel(const MixArgs a
     const long long r = tile * kMixT + threadIdx.x;
     const bool valid = r < a.B;
     float* row = buf + threadIdx.x * g.S;
-    float lse = 0.0f, top = 0.0f, cot = 0.0f;
+    float lse2 = 0.0f, top2 = 0.0f, cot = 0.0f;
     if (valid) {
-      float lm = -INFINITY, ls = 0.0f;
-      for (int k = 0; k < K; ++k) lse_push<M>(row[k], lm, ls);
-      lse = lm + M::log(ls);
-      float m = -INFINITY, s = 0.0f;
-      for (int k = 0; k < K; ++k) {
-        float q = 0.0f;
+      float lm = -INFINITY, ls = 0.0f, m = -INFINITY, s = 0.0f;
+      for (int k0 = 0; k0 < K; k0 += LG) {
+        float lg[LG];
+        ld_vec<LG, LG>(row + k0, lg);
 #pragma unroll
-        for (int i = 0; i < D; ++i) {
-          const float dlt = y[i] - s_loc[k * D + i];
-          q = fmaf(dlt, dlt, q);
+        for (int j = 0; j < LG; ++j) {
+          const int k = k0 + j;
+          const float l2 = lg[j] * kLog2e;
+          lse2_push<M>(l2, lm, ls);
+          float q = 0.0f;
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            const float dlt = y[i] - s_loc[k * D + i];
+            q = fmaf(dlt, dlt, q);
+          }
+          lse2_push<M>(l2 + fmaf(s_coef[k], q, s_lnorm[k]), m, s);
         }
-        lse_push<M>(row[k] + fmaf(s_coef[k], q, s_lnorm[k]), m, s);
       }
-      top = m + M::log(s);
-      const float logp = top - lse - (float)D * kHalfLog2Pi;
+      lse2 = lm + M::lg2(ls);
+      top2 = m + M::lg2(s);
+      const float logp = (top2 - lse2) * kLn2 - (float)D * kHalfLog2Pi;
       a.logp[r] = logp;
       lsum += (double)logp;
     }
@@ -400,28 +411,40 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) kmn_kernel(const MixArgs a
       float dy[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) dy[i] = 0.0f;
-      for (int k = 0; k < K; ++k) {  // all lanes stay in the loop: warp reduction of d/dscale
-        float wsc = 0.0f;
+      for (int k0 = 0; k0 < K; k0 += LG) {  // all lanes stay in the loop: warp reduction of d/dscale
+        float lg[LG];
         if (valid) {
-          float q = 0.0f, dl[D];
+          ld_vec<LG, LG>(row + k0, lg);
+        } else {
 #pragma unroll
-          for (int i = 0; i < D; ++i) {
-            dl[i] = y[i] - s_loc[k * D + i];
-            q = fmaf(dl[i], dl[i], q);
+          for (int j = 0; j < LG; ++j) lg[j] = 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < LG; ++j) {
+          const int k = k0 + j;
+          float wsc = 0.0f;
+          if (valid) {
+            float q = 0.0f, dl[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+              dl[i] = y[i] - s_loc[k * D + i];
+              q = fmaf(dl[i], dl[i], q);
+            }
+            const float l2 = lg[j] * kLog2e;
+            const float crho = cot * M::ex2(l2 + fmaf(s_coef[k], q, s_lnorm[k]) - top2);
+            lg[j] = fmaf(-cot, M::ex2(l2 - lse2), crho);
+            const float c2 = -2.0f * kLn2 * s_coef[k];        // 1 / s^2
+#pragma unroll
+            for (int i = 0; i < D; ++i) dy[i] -= crho * dl[i] * c2;
+            wsc = crho * fmaf(q, c2, -(float)D);               // * 1/s applied when the sums are flushed
           }
-          const float logit = row[k];
-          const float crho = cot * M::exp(logit + fmaf(s_coef[k], q, s_lnorm[k]) - top);
-          row[k] = fmaf(-cot, M::exp(logit - lse), crho);
-          const float c2 = -2.0f * s_coef[k];               // 1 / s^2
+          if (a.dscales) {
 #pragma unroll
-          for (int i = 0; i < D; ++i) dy[i] -= crho * dl[i] * c2;
-          wsc = crho * fmaf(q, c2, -(float)D);               // * 1/s applied on the host side of the sum
+            for (int o = 16; o > 0; o >>= 1) wsc += __shfl_xor_sync(0xffffffffu, wsc, o);
+            if ((threadIdx.x & 31) == 0) my_dsc[k] += wsc;
+          }
         }
-        if (a.dscales) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) wsc += __shfl_xor_sync(0xffffffffu, wsc, o);
-          if ((threadIdx.x & 31) == 0) atomicAdd(&s_dsc[k], wsc);
-        }
+        if (valid) st_vec<LG, LG>(row + k0, lg);
       }
       if (valid && a.dy) store_event<D>(a.dy, r, dy);
     }
@@ -436,7 +459,12 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) kmn_kernel(const MixArgs a
   if constexpr (BWD) {
     if (a.dscales) {
       __syncthreads();
-      for (int i = threadIdx.x; i < K; i += kMixT) atomicAdd(a.dscales + i, s_dsc[i] / __ldg(a.scales + i));
+      for (int i = threadIdx.x; i < K; i += kMixT) {
+        float v = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) v += s_dsc[w * K + i];
+        atomicAdd(a.dscales + i, v / __ldg(a.scales + i));
+      }
     }
   }
   if (a.logp_sum) {
@@ -521,19 +549,24 @@ int launch_mdn(int d, bool bwd, const MixArgs& a, cudaStream_t st) {
   return set_error(NFN_ERR_DESC, "n_dims=%d", d);
 }
 
+template <int D, int LG>
+static int launch_kmn_dl(bool bwd, const MixArgs& a, const RtTile& g, size_t smem, int nb, cudaStream_t st) {
+  if (math_mode() == 0) {
+    return bwd ? launch_tiled(kmn_kernel<D, LG, true, MathFast>, a, g, smem, nb, "kmn_kernel", st)
+               : launch_tiled(kmn_kernel<D, LG, false, MathFast>, a, g, smem, nb, "kmn_kernel", st);
+  }
+  return bwd ? launch_tiled(kmn_kernel<D, LG, true, MathAccurate>, a, g, smem, nb, "kmn_kernel", st)
+             : launch_tiled(kmn_kernel<D, LG, false, MathAccurate>, a, g, smem, nb, "kmn_kernel", st);
+}
+
 template <int D>
 static int launch_kmn_d(bool bwd, const MixArgs& a, cudaStream_t st) {
   const RtTile g = make_tile(a.K);
   const size_t tile = (size_t)kMixT * g.S * sizeof(float);
-  const size_t extra = (size_t)a.K * (D + 3) * sizeof(float);
+  const size_t extra = (size_t)a.K * (D + 2 + kMixT / 32) * sizeof(float);
   const int nb = pick_nb(tile, extra);
   const size_t smem = tile * nb + extra;
-  if (math_mode() == 0) {
-    return bwd ? launch_tiled(kmn_kernel<D, true, MathFast>, a, g, smem, nb, "kmn_kernel", st)
-               : launch_tiled(kmn_kernel<D, false, MathFast>, a, g, smem, nb, "kmn_kernel", st);
-  }
-  return bwd ? launch_tiled(kmn_kernel<D, true, MathAccurate>, a, g, smem, nb, "kmn_kernel", st)
-             : launch_tiled(kmn_kernel<D, false, MathAccurate>, a, g, smem, nb, "kmn_kernel", st);
+  return (a.K % 4 == 0) ? launch_kmn_dl<D, 4>(bwd, a, g, smem, nb, st) : launch_kmn_dl<D, 1>(bwd, a, g, smem, nb, st);
 }
 
 int launch_kmn(int d, bool bwd, const MixArgs& a, cudaStream_t st) {
