@@ -150,6 +150,26 @@ int nfn_chain_forward_backward_peer(const nfn_chain_desc* desc, const float* t, 
                                     double* reduced, int64_t B, void* stream);
 
 /*
+ * The emitting Dense(P) layer fused into the flow-chain kernel: replaces
+ * `Dense(output_size, "linear")` (MaximumLikelihoodNNEstimator.py:43) + the NF layer's log_prob +
+ * their tape gradients.  t = h W + bias is formed tile by tile in shared memory on the tensor cores
+ * (3xTF32, fp32-level accuracy) and never written to HBM.
+ *   h [B, hidden] device    W [hidden, P] row-major (Keras kernel layout)    bias [P]
+ *   dh [B, hidden] out      dW [hidden, P] +=  h^T dt      dbias [P] += sum_b dt
+ * hidden must be 16, 32, 48 or 64.  Returns NFN_ERR_UNSUPPORTED when no fused kernel can serve the
+ * request (other widths; no ahead-of-time instance and NVRTC unavailable): compose
+ * t = h W + bias with nfn_chain_forward_backward then.
+ */
+int nfn_dense_chain_forward(const nfn_chain_desc* desc, int hidden, const float* h, const float* W,
+                            const float* bias, const float* y, int64_t y_rows, float* logp, int64_t B,
+                            void* stream);
+int nfn_dense_chain_forward_backward(const nfn_chain_desc* desc, int hidden, const float* h, const float* W,
+                                     const float* bias, const float* y, int64_t y_rows, const float* g_logp,
+                                     float g_scale, float* logp, float* dh, float* dW, float* dbias,
+                                     double* logp_sum, int64_t B, void* stream);
+int64_t nfn_jit_dense_compile_check(const nfn_chain_desc* desc, int hidden, int accurate);
+
+/*
  * One bijector on its own: Flow(t, n_dims).forward(z) and ._forward_log_det_jacobian(z)
  * (PlanarFlow.py:68-80, RadialFlow.py:51-70, AffineFlow.py:7-9), the calls made by
  * tests/test_flows.py:19-41.  t [B, size(flow)], z [z_rows, d] (z_rows == B or 1),

@@ -86,6 +86,18 @@ const ChainKernels* find_chain(const std::string& key) {
   return it == registry().end() ? nullptr : &it->second;
 }
 
+static std::unordered_map<std::string, DenseKernels>& dense_registry() {
+  static std::unordered_map<std::string, DenseKernels> r;
+  return r;
+}
+void register_dense(const std::string& key, const DenseKernels& k) { dense_registry()[key] = k; }
+const DenseKernels* find_dense(const std::string& key) {
+  if (getenv("NFN_B200_FORCE_JIT")) return nullptr;
+  auto it = dense_registry().find(key);
+  return it == dense_registry().end() ? nullptr : &it->second;
+}
+long long jit_dense_compile_check(const nfn_chain_desc* desc, int H, int mode, std::string& log);
+
 // ------------------------------------------------------------------ validation
 static int check_desc(const nfn_chain_desc* d) {
   if (!d) return set_error(NFN_ERR_NULL, "chain descriptor is NULL");
@@ -260,6 +272,73 @@ int nfn_chain_forward_backward_peer(const nfn_chain_desc* desc, const float* t, 
   a.dt_colsum = want_colsum ? a.peer.acc : nullptr;
   a.B = B; a.g_scale = g_scale; a.y_broadcast = (y_rows == 1 && B != 1);
   return chain_dispatch(desc, a, true, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ fused Dense(P) + chain
+static int dense_dispatch(const nfn_chain_desc* desc, int hidden, const DenseArgs& a, bool bwd, cudaStream_t st) {
+  const std::string key = chain_key(desc->n_dims, desc->trainable_base != 0, desc->n_flows, desc->flow_type);
+  const int mode = math_mode();
+  const DenseKernels* k = find_dense(key + "|h" + std::to_string(hidden));
+  if (k && k->fn[mode][bwd ? 1 : 0]) return cuda_error(k->fn[mode][bwd ? 1 : 0](a, st), key.c_str());
+  bool served = false;
+  cudaError_t e = launch_dense_jit(desc, hidden, key, a, bwd, mode, st, &served);
+  if (e != cudaSuccess) return cuda_error(e, key.c_str());
+  if (!served)
+    return set_error(NFN_ERR_UNSUPPORTED,
+                     "no fused dense kernel for chain %s with hidden width %d (needs a multiple of 16 <= 64 and an "
+                     "ahead-of-time instance or NVRTC): compose the layer and nfn_chain_forward_backward instead",
+                     key.c_str(), hidden);
+  return NFN_OK;
+}
+
+static int dense_common(const nfn_chain_desc* desc, int hidden, const float* h, const float* W, const float* bias,
+                        const float* y, int64_t y_rows, float* logp, int64_t B) {
+  int rc = check_desc(desc);
+  if (rc != NFN_OK) return rc;
+  if ((rc = check_rows(B, y_rows)) != NFN_OK) return rc;
+  if (hidden < 1) return set_error(NFN_ERR_SHAPE, "hidden=%d", hidden);
+  if (param_size(desc) < 1) return set_error(NFN_ERR_UNSUPPORTED, "the chain has no parameters to emit");
+  if (B == 0) return 1;
+  if (!h || !W || !bias || !y || !logp) return set_error(NFN_ERR_NULL, "h, W, bias, y and logp must be non-NULL");
+  if (!aligned(h, 16)) return set_error(NFN_ERR_ALIGN, "h must be 16-byte aligned");
+  if (!aligned(y, event_align(desc->n_dims)))
+    return set_error(NFN_ERR_ALIGN, "y must be %zu-byte aligned", event_align(desc->n_dims));
+  return NFN_OK;
+}
+
+int nfn_dense_chain_forward(const nfn_chain_desc* desc, int hidden, const float* h, const float* W,
+                            const float* bias, const float* y, int64_t y_rows, float* logp, int64_t B,
+                            void* stream) {
+  int rc = dense_common(desc, hidden, h, W, bias, y, y_rows, logp, B);
+  if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
+  DenseArgs a{};
+  a.h = h; a.W = W; a.bias = bias; a.y = y; a.logp = logp; a.B = B; a.g_scale = 1.0f;
+  a.y_broadcast = (y_rows == 1 && B != 1);
+  return dense_dispatch(desc, hidden, a, false, (cudaStream_t)stream);
+}
+
+int nfn_dense_chain_forward_backward(const nfn_chain_desc* desc, int hidden, const float* h, const float* W,
+                                     const float* bias, const float* y, int64_t y_rows, const float* g_logp,
+                                     float g_scale, float* logp, float* dh, float* dW, float* dbias,
+                                     double* logp_sum, int64_t B, void* stream) {
+  int rc = dense_common(desc, hidden, h, W, bias, y, y_rows, logp, B);
+  if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
+  if (!dh || !dW || !dbias) return set_error(NFN_ERR_NULL, "dh, dW and dbias must be non-NULL");
+  if (!aligned(dh, 16)) return set_error(NFN_ERR_ALIGN, "dh must be 16-byte aligned");
+  DenseArgs a{};
+  a.h = h; a.W = W; a.bias = bias; a.y = y; a.g_logp = g_logp; a.logp = logp; a.dh = dh; a.dW = dW;
+  a.dbias = dbias; a.logp_sum = logp_sum; a.B = B; a.g_scale = g_scale;
+  a.y_broadcast = (y_rows == 1 && B != 1);
+  return dense_dispatch(desc, hidden, a, true, (cudaStream_t)stream);
+}
+
+int64_t nfn_jit_dense_compile_check(const nfn_chain_desc* desc, int hidden, int accurate) {
+  int rc = check_desc(desc);
+  if (rc != NFN_OK) return rc;
+  std::string log;
+  const long long n = jit_dense_compile_check(desc, hidden, accurate ? 1 : 0, log);
+  if (n < 0) return set_error(NFN_ERR_UNSUPPORTED, "NVRTC: %s", log.substr(0, 400).c_str());
+  return n;
 }
 
 int nfn_flow_forward(int flow_type, int n_dims, const float* t, const float* z, int64_t z_rows,

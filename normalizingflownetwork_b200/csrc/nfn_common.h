@@ -9,6 +9,7 @@
 
 #include "../../include/nfn_b200.h"
 #include "nfn_chain_kernel.cuh"
+#include "nfn_dense_chain.cuh"
 
 struct nfn_peer_comm;  // opaque handle of the C ABI (nfn_peer.cu)
 
@@ -108,6 +109,62 @@ struct ChainRegistrar {
     register_chain(chain_key(Spec::D, Spec::BASE, Spec::K, types), k);
   }
 };
+
+// ------------------------------------------------------------------ fused Dense(P) + chain
+typedef cudaError_t (*DenseLaunchFn)(const DenseArgs&, cudaStream_t);
+struct DenseKernels {
+  DenseLaunchFn fn[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [math mode][bwd]
+};
+void register_dense(const std::string& key, const DenseKernels& k);
+const DenseKernels* find_dense(const std::string& key);
+
+template <class Spec, int H, bool BWD, class M>
+cudaError_t launch_dense(const DenseArgs& a, cudaStream_t st) {
+  constexpr int T = 128;
+  constexpr unsigned kSmem = dense_smem_bytes(Spec::P(), H, T, BWD);
+  constexpr int kBySmem = (int)((227u * 1024u) / (kSmem + 1024u));
+  constexpr int kWant = BWD ? 2 : 3;
+  constexpr int MINB = kBySmem < 1 ? 1 : (kBySmem < kWant ? kBySmem : kWant);
+  auto kern = dense_chain_kernel<Spec, H, BWD, M, T, MINB>;
+  struct Cfg {
+    int device = -1;
+    int ctas_per_sm = 0;
+  };
+  static thread_local Cfg cfg;
+  const DeviceInfo& di = device_info();
+  if (cfg.device != di.device) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, kSmem);
+    if (e != cudaSuccess) return e;
+    cfg.ctas_per_sm = occ > 0 ? occ : 1;
+    cfg.device = di.device;
+  }
+  const long long ntiles = (a.B + T - 1) / T;
+  long long grid = (long long)di.sm_count * cfg.ctas_per_sm;
+  if (grid > ntiles) grid = ntiles;
+  kern<<<(unsigned)grid, T, kSmem, st>>>(a);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <class Spec, int H>
+struct DenseRegistrar {
+  explicit DenseRegistrar() {
+    DenseKernels k;
+    k.fn[0][0] = &launch_dense<Spec, H, false, MathFast>;
+    k.fn[0][1] = &launch_dense<Spec, H, true, MathFast>;
+    k.fn[1][0] = &launch_dense<Spec, H, false, MathAccurate>;
+    k.fn[1][1] = &launch_dense<Spec, H, true, MathAccurate>;
+    uint8_t types[Spec::KA];
+    for (int i = 0; i < Spec::K; ++i) types[i] = (uint8_t)Spec::type(i);
+    register_dense(chain_key(Spec::D, Spec::BASE, Spec::K, types) + "|h" + std::to_string(H), k);
+  }
+};
+
+cudaError_t launch_dense_jit(const nfn_chain_desc* desc, int H, const std::string& key, const DenseArgs& a,
+                             bool bwd, int mode, cudaStream_t st, bool* served);
 
 // runtime specialiser (nfn_jit.cu): NVRTC-compiled chain_kernel for chains without an AOT
 // instance.  Returns cudaErrorNotSupported when the chain should go to the generic kernel.

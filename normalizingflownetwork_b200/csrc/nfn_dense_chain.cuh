@@ -1,0 +1,371 @@
+// nfn_dense_chain.cuh -- the emitting Dense(P) layer fused into the flow-chain kernel (sm_100a).
+//
+// the parameter tensor t[B, P] is produced by the last Dense layer of
+// the conditioning network (reference estimators/MaximumLikelihoodNNEstimator.py:43) from a
+// 16-64 wide hidden activation h[B, H], and is the dominant HBM traffic of the hot path.  This
+// kernel consumes h directly:
+//
+//   per tile of T rows:   t  = h W + b            (tensor cores, tile stays in shared memory)
+//                          flows forward + reverse sweep per row (nfn_flows.cuh), dt in place
+//                          dh = dt W^T,  dW += h^T dt,  db += 1^T dt     (tensor cores)
+//
+// so per row it reads 4(H + d) and writes 4(H + 1) bytes instead of 4(2P + d + 1), and the three
+// skinny cuBLAS GEMMs around the flow kernel (measured 124 + 146 + 215 us + 75 us for the bias sum
+// next to a 71 us flow kernel at B = 2^20, H = 16, P = 48) disappear.
+//
+// The GEMMs are tiny (K = 16..64): warp-level mma.sync.m16n8k8 TF32 with the 3xTF32 split
+// (x = hi + lo, D += A_lo B_hi + A_hi B_lo + A_hi B_hi) keeps fp32-level accuracy, which the
+// 1e-5 log-prob parity bar needs; plain TF32 (10-bit mantissa) would not pass it.
+#pragma once
+#include "nfn_chain_kernel.cuh"
+
+namespace nfn {
+
+struct DenseArgs {
+  const float* h;     // [B, H] last hidden activation
+  const float* W;     // [H, P] row-major (Keras kernel layout)
+  const float* bias;  // [P]
+  const float* y;
+  const float* g_logp;
+  float* logp;
+  float* dh;          // [B, H]
+  float* dW;          // [H, P]  += h^T dt
+  float* dbias;       // [P]     += sum_b dt
+  double* logp_sum;
+  long long B;
+  float g_scale;
+  int y_broadcast;
+};
+
+// ---------------------------------------------------------------- tensor-core helpers
+NFN_DEVI unsigned f2tf32(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+NFN_DEVI void split_tf32(float x, unsigned& hi, unsigned& lo) {
+  hi = f2tf32(x);
+  lo = f2tf32(x - __uint_as_float(hi));
+}
+NFN_DEVI void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// D += A B at fp32-level accuracy (small terms first)
+NFN_DEVI void mma_3xtf32(float (&d)[4], const unsigned (&ah)[4], const unsigned (&al)[4], const unsigned (&bh)[2],
+                         const unsigned (&bl)[2]) {
+  mma_tf32(d, al, bh);
+  mma_tf32(d, ah, bl);
+  mma_tf32(d, ah, bh);
+}
+
+// smallest stride >= n with stride % 32 in {8, 24}: B-fragment reads (k = lane%4, n = lane/4) are
+// then bank-conflict free
+__host__ __device__ constexpr int w_stride(int n) {
+  int s = n;
+  while (!(s % 32 == 8 || s % 32 == 24)) ++s;
+  return s;
+}
+
+// dynamic shared memory of the fused dense kernel (same arithmetic as DenseGeometry below)
+__host__ __device__ constexpr unsigned dense_smem_bytes(int P, int H, int T, bool bwd) {
+  const int S = row_stride(P), HS = H + 4, P8 = (P + 7) / 8 * 8, PW = w_stride(P8), NW = T / 32;
+  return (unsigned)(4 * (T * S + 2 * T * HS + H * PW + P8 + (bwd ? NW * H * P8 + NW * P8 : 0)));
+}
+
+template <int P, int H, int T>
+struct DenseGeometry {
+  static constexpr int S = row_stride(P);         // t / dt tile row stride
+  static constexpr int HS = H + 4;                // h tile row stride: A-fragment reads conflict-free
+  static constexpr int P8 = (P + 7) / 8 * 8;      // P padded to the mma N / K granule
+  static constexpr int PW = w_stride(P8);         // W row stride in smem
+  static constexpr int NW = T / 32;
+  static constexpr int kT = T * S;                // floats
+  static constexpr int kH = T * HS;               // per h buffer
+  static constexpr int kW = H * PW;
+  static constexpr int kAcc = NW * H * P8;        // per-warp dW partial sums
+  static constexpr int kAccB = NW * P8;           // per-warp dbias partial sums
+  __host__ __device__ static constexpr unsigned smem_bytes(bool bwd) {
+    return (unsigned)(sizeof(float) * (kT + 2 * kH + kW + P8 + (bwd ? kAcc + kAccB : 0)));
+  }
+};
+
+// ---------------------------------------------------------------- the fused body
+template <class Spec, int H, bool BWD, class M, int T>
+NFN_DEVI void dense_chain_body(const DenseArgs& a) {
+  constexpr int D = Spec::D;
+  constexpr int P = Spec::P();
+  static_assert(P > 0, "the fused dense kernel needs at least one parameter column");
+  static_assert(H % 16 == 0 && H >= 16 && H <= 64, "hidden width must be 16, 32, 48 or 64");
+  using G = DenseGeometry<P, H, T>;
+  constexpr int S = G::S, HS = G::HS, P8 = G::P8, PW = G::PW, NW = G::NW;
+  constexpr int V = row_vec(P);
+  constexpr int NT = P8 / 8;   // n-tiles over the parameter columns
+  constexpr int KH = H / 8;    // k-steps over the hidden units
+
+  extern __shared__ __align__(16) float smem[];
+  __shared__ double red[T / 32];
+  float* tT = smem;                    // [T][S]   t, then dt in place
+  float* hT = tT + G::kT;              // [2][T][HS]
+  float* sW = hT + 2 * G::kH;          // [H][PW]
+  float* sB = sW + G::kW;              // [P8]
+  float* sAcc = sB + P8;               // [NW][H][P8]   (BWD)
+  float* sAccB = sAcc + G::kAcc;       // [NW][P8]      (BWD)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tig = lane & 3;
+  const long long ntiles = (a.B + T - 1) / T;
+
+  // weights, bias (zero-padded to P8 columns), accumulators
+  for (int i = tid; i < H * PW; i += T) {
+    const int k = i / PW, n = i % PW;
+    sW[i] = (n < P) ? __ldg(a.W + k * P + n) : 0.0f;
+  }
+  for (int i = tid; i < P8; i += T) sB[i] = (i < P) ? __ldg(a.bias + i) : 0.0f;
+  if constexpr (BWD) {
+    for (int i = tid; i < G::kAcc + G::kAccB; i += T) sAcc[i] = 0.0f;
+  }
+
+  __syncthreads();
+
+  // Every warp owns rows [32 warp, 32 warp + 32) of each tile end to end (h load, the three GEMMs,
+  // the per-row flow chain, the dh store), so the tile loop needs only warp-level barriers.
+  // async h rows of this warp: 16-byte chunks into rows of stride HS; rows past B are zeroed
+  auto load_h = [&](int buf, long long tile) {
+    constexpr int CPR = H / 4;  // chunks per row
+    float* dst = hT + buf * G::kH + (warp * 32) * HS;
+    const long long row0 = tile * T + warp * 32;
+    for (int q = lane; q < 32 * CPR; q += 32) {
+      const int r = q / CPR, c = q % CPR;
+      float* d = dst + r * HS + 4 * c;
+      if (row0 + r < a.B) cp_async16(smem_u32(d), a.h + (row0 + r) * H + 4 * c);
+      else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+
+  long long tile = blockIdx.x;
+  if (tile < ntiles) load_h(0, tile);
+  cp_async_commit();
+
+  float y_nxt[D];
+  float g_nxt = 1.0f;
+  {
+    const long long r0 = tile * T + tid;
+#pragma unroll
+    for (int i = 0; i < D; ++i) y_nxt[i] = 0.0f;
+    if (tile < ntiles && r0 < a.B) {
+      load_event<D>(a.y, a.y_broadcast ? 0 : r0, y_nxt);
+      if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + r0); }
+    }
+  }
+  double lsum = 0.0;
+  int buf = 0;
+
+  for (; tile < ntiles; tile += gridDim.x) {
+    float z[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) z[i] = y_nxt[i];
+    const float g_cur = g_nxt;
+    {
+      const long long nxt = tile + gridDim.x;
+      if (nxt < ntiles) load_h(buf ^ 1, nxt);   // the other buffer was drained at the end of the last iteration
+      cp_async_commit();
+      const long long rn = nxt * T + tid;
+      if (rn < a.B) {
+        load_event<D>(a.y, a.y_broadcast ? 0 : rn, y_nxt);
+        if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + rn); }
+      }
+      cp_async_wait<1>();
+      __syncwarp();
+    }
+    float* hcur = hT + buf * G::kH;
+
+    // ---- GEMM 1: t[32 rows of this warp][P8] = h W + b
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r0 = warp * 32 + mt * 16;
+      unsigned ah[KH][4], al[KH][4];
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks) {
+        split_tf32(hcur[(r0 + g) * HS + 8 * ks + tig], ah[ks][0], al[ks][0]);
+        split_tf32(hcur[(r0 + g + 8) * HS + 8 * ks + tig], ah[ks][1], al[ks][1]);
+        split_tf32(hcur[(r0 + g) * HS + 8 * ks + tig + 4], ah[ks][2], al[ks][2]);
+        split_tf32(hcur[(r0 + g + 8) * HS + 8 * ks + tig + 4], ah[ks][3], al[ks][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int c0 = 8 * nt + 2 * tig;
+        float c[4] = {sB[c0], sB[c0 + 1], sB[c0], sB[c0 + 1]};
+#pragma unroll
+        for (int ks = 0; ks < KH; ++ks) {
+          unsigned bh[2], bl[2];
+          split_tf32(sW[(8 * ks + tig) * PW + 8 * nt + g], bh[0], bl[0]);
+          split_tf32(sW[(8 * ks + tig + 4) * PW + 8 * nt + g], bh[1], bl[1]);
+          mma_3xtf32(c, ah[ks], al[ks], bh, bl);
+        }
+        float* d0 = tT + (r0 + g) * S + c0;
+        float* d1 = tT + (r0 + g + 8) * S + c0;
+        if (c0 < P) { d0[0] = c[0]; d1[0] = c[2]; }
+        if (c0 + 1 < P) { d0[1] = c[1]; d1[1] = c[3]; }
+      }
+    }
+    __syncwarp();
+
+    // ---- per-row flow chain (registers), dt written in place over t
+    const long long r = tile * T + tid;
+    float* row = tT + tid * S;
+    if (r < a.B) {
+      float zs[Spec::KA][D];
+      LogDetAcc<M> ld;
+      FwdSweep<Spec, M, V, BWD, 0>::run(row, z, zs, ld);
+      using Base = BaseDist<D, Spec::BASE, M>;
+      float bth[Base::NA];
+      if constexpr (Spec::BASE) Span<0, 2 * D, V>::load(row, bth);
+      const float lp = (BWD ? Base::log_prob_save(bth, z) : Base::log_prob(bth, z)) + ld.nat();
+      a.logp[r] = lp;
+      lsum += (double)lp;
+      if constexpr (BWD) {
+        const float cot = a.g_scale * g_cur;
+        float Gz[D];
+        float gb[Base::NA];
+        Base::bwd_saved(bth, z, cot, Gz, gb);
+        if constexpr (Spec::BASE) Span<0, 2 * D, V>::store(row, gb);
+        BwdSweep<Spec, M, V, Spec::K - 1>::run(row, zs, Gz, cot);
+      }
+    } else if constexpr (BWD) {
+#pragma unroll
+      for (int j = 0; j < P; ++j) row[j] = 0.0f;   // rows past B contribute nothing to dW / db
+    }
+
+    if constexpr (BWD) {
+      __syncwarp();
+      // ---- GEMM 3: dW_warp[H][P8] += h_warp^T dt_warp  (K = this warp's 32 rows), db via a ones operand
+      {
+        const int R0 = warp * 32;
+        float* acc = sAcc + warp * (H * P8);
+        float* accb = sAccB + warp * P8;
+        const unsigned one[4] = {0x3f800000u, 0x3f800000u, 0x3f800000u, 0x3f800000u};
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          unsigned bh[4][2], bl[4][2];
+          const int col = 8 * nt + g;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const float v0 = (col < P) ? tT[(R0 + 8 * ks + tig) * S + col] : 0.0f;
+            const float v1 = (col < P) ? tT[(R0 + 8 * ks + tig + 4) * S + col] : 0.0f;
+            split_tf32(v0, bh[ks][0], bl[ks][0]);
+            split_tf32(v1, bh[ks][1], bl[ks][1]);
+          }
+          float cb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            mma_tf32(cb, one, bl[ks]);
+            mma_tf32(cb, one, bh[ks]);
+          }
+          if (g == 0) {
+            accb[8 * nt + 2 * tig] += cb[0];
+            accb[8 * nt + 2 * tig + 1] += cb[1];
+          }
+#pragma unroll
+          for (int mt = 0; mt < H / 16; ++mt) {
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              unsigned ah[4], al[4];
+              const float* hp = hcur + (R0 + 8 * ks + tig) * HS + 16 * mt + g;
+              split_tf32(hp[0], ah[0], al[0]);
+              split_tf32(hp[8], ah[1], al[1]);
+              split_tf32(hp[4 * HS], ah[2], al[2]);
+              split_tf32(hp[4 * HS + 8], ah[3], al[3]);
+              mma_3xtf32(c, ah, al, bh[ks], bl[ks]);
+            }
+            float* p0 = acc + (16 * mt + g) * P8 + 8 * nt + 2 * tig;
+            float* p1 = p0 + 8 * P8;
+            p0[0] += c[0]; p0[1] += c[1];
+            p1[0] += c[2]; p1[1] += c[3];
+          }
+        }
+      }
+      __syncwarp();
+      // ---- GEMM 2: dh[32 rows][H] = dt W^T  -> into the (now consumed) h tile of this warp's rows
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int r0 = warp * 32 + mt * 16;
+        float c[H / 8][4];
+#pragma unroll
+        for (int nt = 0; nt < H / 8; ++nt) { c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.0f; }
+#pragma unroll
+        for (int ks = 0; ks < NT; ++ks) {
+          unsigned ah[4], al[4];
+          const int k0 = 8 * ks + tig, k1 = k0 + 4;
+          split_tf32((k0 < P) ? tT[(r0 + g) * S + k0] : 0.0f, ah[0], al[0]);
+          split_tf32((k0 < P) ? tT[(r0 + g + 8) * S + k0] : 0.0f, ah[1], al[1]);
+          split_tf32((k1 < P) ? tT[(r0 + g) * S + k1] : 0.0f, ah[2], al[2]);
+          split_tf32((k1 < P) ? tT[(r0 + g + 8) * S + k1] : 0.0f, ah[3], al[3]);
+#pragma unroll
+          for (int nt = 0; nt < H / 8; ++nt) {
+            unsigned bh[2], bl[2];
+            split_tf32(sW[(8 * nt + g) * PW + k0], bh[0], bl[0]);
+            split_tf32(sW[(8 * nt + g) * PW + k1], bh[1], bl[1]);
+            mma_3xtf32(c[nt], ah, al, bh, bl);
+          }
+        }
+        __syncwarp();  // every lane of the warp is done reading this warp's h rows (GEMM 3)
+#pragma unroll
+        for (int nt = 0; nt < H / 8; ++nt) {
+          float* d0 = hcur + (r0 + g) * HS + 8 * nt + 2 * tig;
+          float* d1 = hcur + (r0 + g + 8) * HS + 8 * nt + 2 * tig;
+          *reinterpret_cast<float2*>(d0) = make_float2(c[nt][0], c[nt][1]);
+          *reinterpret_cast<float2*>(d1) = make_float2(c[nt][2], c[nt][3]);
+        }
+      }
+      __syncwarp();
+      // ---- dh rows of this warp -> global, coalesced 16-byte streaming stores
+      {
+        constexpr int CPR = H / 4;
+        const long long row0 = tile * T + warp * 32;
+        const float* src = hcur + (warp * 32) * HS;
+        for (int q = lane; q < 32 * CPR; q += 32) {
+          const int rr = q / CPR, cc = q % CPR;
+          if (row0 + rr < a.B)
+            st_stream_f4(a.dh + (row0 + rr) * H + 4 * cc, *reinterpret_cast<const float4*>(src + rr * HS + 4 * cc));
+        }
+      }
+    }
+    __syncwarp();
+    buf ^= 1;
+  }
+  cp_async_wait<0>();
+
+  if (a.logp_sum) {
+    const double sblk = block_sum<T>(lsum, red);
+    if (tid == 0) atomicAdd(a.logp_sum, sblk);
+  }
+  if constexpr (BWD) {
+    __syncthreads();
+    for (int i = tid; i < H * P8; i += T) {
+      const int k = i / P8, n = i % P8;
+      if (n < P) {
+        float v = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) v += sAcc[w * (H * P8) + i];
+        atomicAdd(a.dW + k * P + n, v);
+      }
+    }
+    for (int n = tid; n < P; n += T) {
+      float v = 0.0f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) v += sAccB[w * P8 + n];
+      atomicAdd(a.dbias + n, v);
+    }
+  }
+}
+
+template <class Spec, int H, bool BWD, class M, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) dense_chain_kernel(const DenseArgs a) {
+  dense_chain_body<Spec, H, BWD, M, T>(a);
+}
+
+}  // namespace nfn

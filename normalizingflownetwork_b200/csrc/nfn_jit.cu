@@ -21,11 +21,13 @@
 #include <vector>
 
 #include "nfn_common.h"
+#include "nfn_dense_chain.cuh"
 
 // embedded by build.py (csrc/_gen/nfn_jit_sources.cu)
 extern const char* const nfn_jit_src_math;
 extern const char* const nfn_jit_src_flows;
 extern const char* const nfn_jit_src_chain;
+extern const char* const nfn_jit_src_dense;
 
 namespace nfn {
 
@@ -76,7 +78,7 @@ Nvrtc& nvrtc() {
 struct JitEntry {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t kern[2] = {nullptr, nullptr};  // [bwd]
-  ChainGeometry geo[2];
+  ChainGeometry geo[2];                       // T, (NB), MINB, smem_bytes per kernel
   int ctas_per_sm[2] = {0, 0};
   int device = -1;
   bool failed = false;
@@ -157,10 +159,10 @@ bool compile_cubin(const std::string& src, std::vector<char>& cubin, std::string
     log = "libnvrtc.so.12 not found";
     return false;
   }
-  const char* headers[3] = {nfn_jit_src_math, nfn_jit_src_flows, nfn_jit_src_chain};
-  const char* hnames[3] = {"nfn_math.cuh", "nfn_flows.cuh", "nfn_chain_kernel.cuh"};
+  const char* headers[4] = {nfn_jit_src_math, nfn_jit_src_flows, nfn_jit_src_chain, nfn_jit_src_dense};
+  const char* hnames[4] = {"nfn_math.cuh", "nfn_flows.cuh", "nfn_chain_kernel.cuh", "nfn_dense_chain.cuh"};
   nvrtcProgram prog = nullptr;
-  int rc = n.CreateProgram(&prog, src.c_str(), "nfn_jit_chain.cu", 3, headers, hnames);
+  int rc = n.CreateProgram(&prog, src.c_str(), "nfn_jit_chain.cu", 4, headers, hnames);
   if (rc != 0) {
     log = "nvrtcCreateProgram failed";
     return false;
@@ -192,81 +194,155 @@ bool jit_eligible(const nfn_chain_desc* d, int P) {
   return true;
 }
 
+// Looks up / builds the two kernels (forward, forward+backward) of one program.  Returns nullptr
+// when the generic kernel should serve the request (NVRTC missing, compile or load failure).
+static JitEntry* get_or_build(const std::string& ckey, const std::string& src, const char* const (&names)[2],
+                              const ChainGeometry (&geo)[2]) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  auto it = g_cache.find(ckey);
+  if (it == g_cache.end()) {
+    JitEntry e;
+    e.device = device_info().device;
+    e.geo[0] = geo[0];
+    e.geo[1] = geo[1];
+    const std::string all = src + nfn_jit_src_math + nfn_jit_src_flows + nfn_jit_src_chain + nfn_jit_src_dense +
+                            "|sm_100a|v2";
+    char name[64];
+    snprintf(name, sizeof(name), "/chain_%016llx.cubin", fnv1a(all));
+    const std::string path = cache_dir() + name;
+    std::vector<char> cubin;
+    std::string log;
+    bool have = read_file(path, cubin);
+    if (!have) {
+      have = compile_cubin(src, cubin, log);
+      if (have) write_file_atomic(path, cubin);
+      else if (getenv("NFN_B200_JIT_VERBOSE")) fprintf(stderr, "[nfn_b200 jit] %s: %s\n", ckey.c_str(), log.c_str());
+    }
+    if (have) {
+      cudaError_t ce = cudaLibraryLoadData(&e.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+      for (int b = 0; b < 2 && ce == cudaSuccess; ++b) {
+        ce = cudaLibraryGetKernel(&e.kern[b], e.lib, names[b]);
+        if (ce == cudaSuccess)
+          ce = cudaFuncSetAttribute((const void*)e.kern[b], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)e.geo[b].smem_bytes);
+        int occ = 0;
+        if (ce == cudaSuccess)
+          ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e.kern[b], e.geo[b].T,
+                                                             e.geo[b].smem_bytes);
+        e.ctas_per_sm[b] = occ > 0 ? occ : 1;
+      }
+      if (ce != cudaSuccess) {
+        cudaGetLastError();
+        e.failed = true;
+      }
+    } else {
+      e.failed = true;
+    }
+    it = g_cache.emplace(ckey, e).first;
+  }
+  return it->second.failed ? nullptr : &it->second;
+}
+
+static bool jit_enabled() {
+  const char* env = getenv("NFN_B200_JIT");
+  return !(env && !strcmp(env, "0"));
+}
+
+static int desc_param_size(const nfn_chain_desc* desc) {
+  int P = desc->trainable_base ? 2 * desc->n_dims : 0;
+  for (int k = 0; k < desc->n_flows; ++k) P += flow_param_size(desc->flow_type[k], desc->n_dims);
+  return P;
+}
+
+static std::string spec_text(const nfn_chain_desc* d) {
+  std::string spec = "nfn::ChainSpec<" + std::to_string(d->n_dims) + ", " + (d->trainable_base ? "true" : "false");
+  for (int k = 0; k < d->n_flows; ++k) spec += ", " + std::to_string((int)d->flow_type[k]);
+  return spec + ">";
+}
+
+template <class Args>
+static cudaError_t launch_entry(JitEntry* ent, int b, const Args& a, long long B, cudaStream_t st) {
+  const int T = ent->geo[b].T;
+  const long long ntiles = (B + T - 1) / T;
+  long long grid = (long long)device_info().sm_count * ent->ctas_per_sm[b];
+  if (grid > ntiles) grid = ntiles;
+  Args args = a;
+  void* params[] = {&args};
+  cudaError_t ce = cudaLaunchKernel((const void*)ent->kern[b], dim3((unsigned)grid), dim3((unsigned)T), params,
+                                    ent->geo[b].smem_bytes, st);
+  if (ce == cudaSuccess) count_launch();
+  return ce;
+}
+
 }  // namespace
 
 cudaError_t launch_chain_jit(const nfn_chain_desc* desc, const std::string& key, const ChainArgs& a, bool bwd,
                              int mode, cudaStream_t st, bool* served) {
   *served = false;
-  const char* env = getenv("NFN_B200_JIT");
-  if (env && !strcmp(env, "0")) return cudaSuccess;
-  int P = desc->trainable_base ? 2 * desc->n_dims : 0;
-  for (int k = 0; k < desc->n_flows; ++k) P += flow_param_size(desc->flow_type[k], desc->n_dims);
+  if (!jit_enabled()) return cudaSuccess;
+  const int P = desc_param_size(desc);
   if (!jit_eligible(desc, P)) return cudaSuccess;
-  const DeviceInfo& di = device_info();
-  const std::string ckey = key + "|m" + std::to_string(mode) + "|dev" + std::to_string(di.device);
-
-  JitEntry* ent = nullptr;
-  {
-    std::lock_guard<std::mutex> lock(g_mu);
-    auto it = g_cache.find(ckey);
-    if (it == g_cache.end()) {
-      JitEntry e;
-      e.device = di.device;
-      e.geo[0] = chain_geometry(P, false);
-      e.geo[1] = chain_geometry(P, true);
-      const std::string src = program_source(desc, mode, e.geo);
-      const std::string all = src + nfn_jit_src_math + nfn_jit_src_flows + nfn_jit_src_chain + "|sm_100a|v1";
-      char name[64];
-      snprintf(name, sizeof(name), "/chain_%016llx.cubin", fnv1a(all));
-      const std::string path = cache_dir() + name;
-      std::vector<char> cubin;
-      std::string log;
-      bool have = read_file(path, cubin);
-      if (!have) {
-        have = compile_cubin(src, cubin, log);
-        if (have) write_file_atomic(path, cubin);
-        else if (getenv("NFN_B200_JIT_VERBOSE")) fprintf(stderr, "[nfn_b200 jit] %s: %s\n", key.c_str(), log.c_str());
-      }
-      if (have) {
-        cudaError_t ce = cudaLibraryLoadData(&e.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-        if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&e.kern[0], e.lib, "nfn_jit_chain_fwd");
-        if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&e.kern[1], e.lib, "nfn_jit_chain_fwd_bwd");
-        for (int b = 0; b < 2 && ce == cudaSuccess; ++b) {
-          ce = cudaFuncSetAttribute((const void*)e.kern[b], cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)e.geo[b].smem_bytes);
-          int occ = 0;
-          if (ce == cudaSuccess)
-            ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e.kern[b], e.geo[b].T,
-                                                               e.geo[b].smem_bytes);
-          e.ctas_per_sm[b] = occ > 0 ? occ : 1;
-        }
-        if (ce != cudaSuccess) {
-          cudaGetLastError();
-          e.failed = true;
-        }
-      } else {
-        e.failed = true;
-      }
-      it = g_cache.emplace(ckey, e).first;
-    }
-    ent = &it->second;
-  }
-  if (ent->failed) return cudaSuccess;  // generic kernel takes over
-
-  const int b = bwd ? 1 : 0;
-  const int T = ent->geo[b].T;
-  const long long ntiles = (a.B + T - 1) / T;
-  long long grid = (long long)di.sm_count * ent->ctas_per_sm[b];
-  if (grid > ntiles) grid = ntiles;
-  ChainArgs args = a;
-  void* params[] = {&args};
-  cudaError_t ce = cudaLaunchKernel((const void*)ent->kern[b], dim3((unsigned)grid), dim3((unsigned)T), params,
-                                    ent->geo[b].smem_bytes, st);
-  if (ce == cudaSuccess) {
-    count_launch();
-    *served = true;
-  }
+  const ChainGeometry geo[2] = {chain_geometry(P, false), chain_geometry(P, true)};
+  const char* const names[2] = {"nfn_jit_chain_fwd", "nfn_jit_chain_fwd_bwd"};
+  const std::string ckey = key + "|m" + std::to_string(mode) + "|dev" + std::to_string(device_info().device);
+  JitEntry* ent = get_or_build(ckey, program_source(desc, mode, geo), names, geo);
+  if (!ent) return cudaSuccess;  // generic kernel takes over
+  cudaError_t ce = launch_entry(ent, bwd ? 1 : 0, a, a.B, st);
+  if (ce == cudaSuccess) *served = true;
   return ce;
+}
+
+// ------------------------------------------------------------------ fused Dense(P) + chain
+static std::string dense_program_source(const nfn_chain_desc* d, int H, int mode, const ChainGeometry (&geo)[2]) {
+  const char* math = mode == 0 ? "nfn::MathFast" : "nfn::MathAccurate";
+  std::string s = "#include \"nfn_dense_chain.cuh\"\nusing Spec = " + spec_text(d) + ";\n";
+  const char* names[2] = {"nfn_jit_dense_fwd", "nfn_jit_dense_fwd_bwd"};
+  for (int b = 0; b < 2; ++b) {
+    s += "extern \"C\" __global__ void __launch_bounds__(" + std::to_string(geo[b].T) + ", " +
+         std::to_string(geo[b].MINB) + ") " + names[b] + "(const nfn::DenseArgs a) {\n  nfn::dense_chain_body<Spec, " +
+         std::to_string(H) + ", " + (b ? "true" : "false") + ", " + math + ", " + std::to_string(geo[b].T) +
+         ">(a);\n}\n";
+  }
+  return s;
+}
+
+static void dense_geometry(int P, int H, ChainGeometry (&geo)[2]) {
+  for (int b = 0; b < 2; ++b) {
+    geo[b].T = 128;
+    geo[b].NB = 2;
+    geo[b].smem_bytes = dense_smem_bytes(P, H, 128, b == 1);
+    const int by_smem = (int)((227u * 1024u) / (geo[b].smem_bytes + 1024u));
+    const int want = b ? 2 : 3;
+    geo[b].MINB = by_smem < 1 ? 1 : (by_smem < want ? by_smem : want);
+  }
+}
+
+// served == false (with cudaSuccess): the caller must use the unfused path
+cudaError_t launch_dense_jit(const nfn_chain_desc* desc, int H, const std::string& key, const DenseArgs& a,
+                             bool bwd, int mode, cudaStream_t st, bool* served) {
+  *served = false;
+  if (!jit_enabled()) return cudaSuccess;
+  const int P = desc_param_size(desc);
+  if (P < 1 || H % 16 != 0 || H < 16 || H > 64 || !jit_eligible(desc, P)) return cudaSuccess;
+  ChainGeometry geo[2];
+  dense_geometry(P, H, geo);
+  if (geo[1].smem_bytes > 220u * 1024u) return cudaSuccess;
+  const char* const names[2] = {"nfn_jit_dense_fwd", "nfn_jit_dense_fwd_bwd"};
+  const std::string ckey =
+      key + "|dense" + std::to_string(H) + "|m" + std::to_string(mode) + "|dev" + std::to_string(device_info().device);
+  JitEntry* ent = get_or_build(ckey, dense_program_source(desc, H, mode, geo), names, geo);
+  if (!ent) return cudaSuccess;
+  cudaError_t ce = launch_entry(ent, bwd ? 1 : 0, a, a.B, st);
+  if (ce == cudaSuccess) *served = true;
+  return ce;
+}
+
+long long jit_dense_compile_check(const nfn_chain_desc* desc, int H, int mode, std::string& log) {
+  ChainGeometry geo[2];
+  dense_geometry(desc_param_size(desc), H, geo);
+  std::vector<char> cubin;
+  if (!compile_cubin(dense_program_source(desc, H, mode, geo), cubin, log)) return -1;
+  return (long long)cubin.size();
 }
 
 // compile only (no device needed): returns the cubin size, or -1 with the NVRTC log in `log`

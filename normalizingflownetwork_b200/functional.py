@@ -131,6 +131,61 @@ def chain_forward_backward_peer(t, y, flow_types, n_dims, trainable_base_dist, c
     return logp, dt, reduced
 
 
+# ----------------------------------------------------------------------------- fused Dense(P) + chain
+def dense_chain_supported(hidden):
+    return hidden in (16, 32, 48, 64)
+
+
+def dense_chain_forward(h, W, bias, y, flow_types, n_dims, trainable_base_dist):
+    """log_prob[B] with the emitting layer fused: t = h @ W + bias never touches HBM.
+    h [B, H], W [H, P] (Keras kernel layout = torch ``linear.weight.t()``), bias [P]."""
+    lib = _lib.load()
+    desc = _lib.make_desc(flow_types, n_dims, trainable_base_dist)
+    P = _lib.check(lib.nfn_chain_param_size(ctypes.byref(desc)))
+    h = _aligned(_as_f32_cuda(h, "h"))
+    dev = h.device
+    W = _as_f32_cuda(W, "W", device=dev)
+    bias = _as_f32_cuda(bias, "bias", device=dev)
+    y = _aligned(_as_f32_cuda(y, "y", device=dev))
+    B, H = h.shape
+    assert tuple(W.shape) == (H, P) and tuple(bias.shape) == (P,), "W must be [H, P] and bias [P]"
+    logp = torch.empty(B, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_dense_chain_forward(ctypes.byref(desc), H, _lib.ptr(h), _lib.ptr(W), _lib.ptr(bias),
+                                               _lib.ptr(y), y.shape[0], _lib.ptr(logp), B, _lib.current_stream(dev)))
+    return logp
+
+
+def dense_chain_forward_backward(h, W, bias, y, flow_types, n_dims, trainable_base_dist, g_logp=None, g_scale=1.0,
+                                 logp_sum=None, dW=None, dbias=None):
+    """Fused layer + chain, forward and reverse sweep.  Returns (logp[B], dh[B,H], dW[H,P], dbias[P]);
+    dW / dbias are accumulated into when given (else fresh zero tensors)."""
+    lib = _lib.load()
+    desc = _lib.make_desc(flow_types, n_dims, trainable_base_dist)
+    P = _lib.check(lib.nfn_chain_param_size(ctypes.byref(desc)))
+    h = _aligned(_as_f32_cuda(h, "h"))
+    dev = h.device
+    W = _as_f32_cuda(W, "W", device=dev)
+    bias = _as_f32_cuda(bias, "bias", device=dev)
+    y = _aligned(_as_f32_cuda(y, "y", device=dev))
+    B, H = h.shape
+    assert tuple(W.shape) == (H, P) and tuple(bias.shape) == (P,), "W must be [H, P] and bias [P]"
+    logp = torch.empty(B, dtype=torch.float32, device=dev)
+    dh = torch.empty((B, H), dtype=torch.float32, device=dev)
+    if dW is None:
+        dW = torch.zeros((H, P), dtype=torch.float32, device=dev)
+    if dbias is None:
+        dbias = torch.zeros(P, dtype=torch.float32, device=dev)
+    if g_logp is not None:
+        g_logp = _as_f32_cuda(g_logp, "g_logp", device=dev).reshape(-1)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_dense_chain_forward_backward(
+            ctypes.byref(desc), H, _lib.ptr(h), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(y), y.shape[0],
+            _lib.ptr(g_logp), ctypes.c_float(g_scale), _lib.ptr(logp), _lib.ptr(dh), _lib.ptr(dW), _lib.ptr(dbias),
+            _lib.ptr(logp_sum), B, _lib.current_stream(dev)))
+    return logp, dh, dW, dbias
+
+
 class _ChainLogProb(torch.autograd.Function):
     @staticmethod
     def forward(ctx, t, y, flow_types, n_dims, trainable_base_dist):
