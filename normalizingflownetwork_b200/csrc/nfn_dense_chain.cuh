@@ -53,6 +53,24 @@ NFN_DEVI void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
+// three-level split x = x0 + x1 + x2 (11 + 11 + remaining bits): the forward GEMM t = h W + b feeds the
+// flows, whose log-prob can amplify a rounding of t by |dlogp/dt| ~ 10^2, so t gets full fp32 accuracy
+NFN_DEVI void split3_tf32(float x, unsigned& x0, unsigned& x1, unsigned& x2) {
+  x0 = f2tf32(x);
+  const float r1 = x - __uint_as_float(x0);
+  x1 = f2tf32(r1);
+  x2 = f2tf32(r1 - __uint_as_float(x1));
+}
+// D += A B with the six leading products of the three-level splits (smallest first)
+NFN_DEVI void mma_6xtf32(float (&d)[4], const unsigned (&a0)[4], const unsigned (&a1)[4], const unsigned (&a2)[4],
+                         const unsigned (&b0)[2], const unsigned (&b1)[2], const unsigned (&b2)[2]) {
+  mma_tf32(d, a2, b0);
+  mma_tf32(d, a0, b2);
+  mma_tf32(d, a1, b1);
+  mma_tf32(d, a1, b0);
+  mma_tf32(d, a0, b1);
+  mma_tf32(d, a0, b0);
+}
 // D += A B at fp32-level accuracy (small terms first)
 NFN_DEVI void mma_3xtf32(float (&d)[4], const unsigned (&ah)[4], const unsigned (&al)[4], const unsigned (&bh)[2],
                          const unsigned (&bl)[2]) {
@@ -186,25 +204,26 @@ NFN_DEVI void dense_chain_body(const DenseArgs& a) {
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
       const int r0 = warp * 32 + mt * 16;
-      unsigned ah[KH][4], al[KH][4];
+      unsigned a0[KH][4], a1[KH][4], a2[KH][4];
 #pragma unroll
       for (int ks = 0; ks < KH; ++ks) {
-        split_tf32(hcur[(r0 + g) * HS + 8 * ks + tig], ah[ks][0], al[ks][0]);
-        split_tf32(hcur[(r0 + g + 8) * HS + 8 * ks + tig], ah[ks][1], al[ks][1]);
-        split_tf32(hcur[(r0 + g) * HS + 8 * ks + tig + 4], ah[ks][2], al[ks][2]);
-        split_tf32(hcur[(r0 + g + 8) * HS + 8 * ks + tig + 4], ah[ks][3], al[ks][3]);
+        split3_tf32(hcur[(r0 + g) * HS + 8 * ks + tig], a0[ks][0], a1[ks][0], a2[ks][0]);
+        split3_tf32(hcur[(r0 + g + 8) * HS + 8 * ks + tig], a0[ks][1], a1[ks][1], a2[ks][1]);
+        split3_tf32(hcur[(r0 + g) * HS + 8 * ks + tig + 4], a0[ks][2], a1[ks][2], a2[ks][2]);
+        split3_tf32(hcur[(r0 + g + 8) * HS + 8 * ks + tig + 4], a0[ks][3], a1[ks][3], a2[ks][3]);
       }
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int c0 = 8 * nt + 2 * tig;
-        float c[4] = {sB[c0], sB[c0 + 1], sB[c0], sB[c0 + 1]};
+        float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
         for (int ks = 0; ks < KH; ++ks) {
-          unsigned bh[2], bl[2];
-          split_tf32(sW[(8 * ks + tig) * PW + 8 * nt + g], bh[0], bl[0]);
-          split_tf32(sW[(8 * ks + tig + 4) * PW + 8 * nt + g], bh[1], bl[1]);
-          mma_3xtf32(c, ah[ks], al[ks], bh, bl);
+          unsigned b0[2], b1[2], b2[2];
+          split3_tf32(sW[(8 * ks + tig) * PW + 8 * nt + g], b0[0], b1[0], b2[0]);
+          split3_tf32(sW[(8 * ks + tig + 4) * PW + 8 * nt + g], b0[1], b1[1], b2[1]);
+          mma_6xtf32(c, a0[ks], a1[ks], a2[ks], b0, b1, b2);
         }
+        c[0] += sB[c0]; c[1] += sB[c0 + 1]; c[2] += sB[c0]; c[3] += sB[c0 + 1];
         float* d0 = tT + (r0 + g) * S + c0;
         float* d1 = tT + (r0 + g + 8) * S + c0;
         if (c0 < P) { d0[0] = c[0]; d1[0] = c[2]; }

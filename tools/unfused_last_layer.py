@@ -34,6 +34,9 @@ def step(): fwd_gemm(); flow(); dgrad(); wgrad(); bgrad()
 dWf = torch.zeros((H, P), device=dev); dbf = torch.zeros(P, device=dev)
 def fused(): F.dense_chain_forward_backward(h, W, b, y, ft, d, True, g_scale=-1.0 / B, dW=dWf, dbias=dbf)
 def fused_fwd(): F.dense_chain_forward(h, W, b, y, ft, d, True)
+if len(sys.argv) > 1 and sys.argv[1] == "fused-only":
+    print("%-26s %8.1f us" % ("FUSED layer+flow fwd+bwd", timed(fused, 10)))
+    sys.exit(0)
 for name, fn in [("FUSED layer+flow fwd+bwd", fused), ("FUSED layer+flow fwd", fused_fwd), ("t = h W + b", fwd_gemm), ("flow fwd+bwd", flow), ("dh = dt W^T", dgrad), ("dW = h^T dt", wgrad),
                  ("db = sum dt", bgrad), ("whole unfused step", step)]:
     print("%-26s %8.1f us" % (name, timed(fn)))
