@@ -38,14 +38,14 @@ struct DenseArgs {
 };
 
 // ---------------------------------------------------------------- tensor-core helpers
-NFN_DEVI unsigned f2tf32(float x) {
-  unsigned r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// A TF32 operand is the upper 19 bits of an fp32 pattern: the tensor core ignores the low 13
+// mantissa bits, so the "high" part of a split needs no conversion at all (cvt.rna.tf32 is
+// emulated with ~6 instructions on sm_100 and dominated the first version of this kernel).
+// The residual x - trunc(x) is exact in fp32 and carries the next 11+ bits.
+NFN_DEVI float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 NFN_DEVI void split_tf32(float x, unsigned& hi, unsigned& lo) {
-  hi = f2tf32(x);
-  lo = f2tf32(x - __uint_as_float(hi));
+  hi = __float_as_uint(x);
+  lo = __float_as_uint(x - tf32_trunc(x));
 }
 NFN_DEVI void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
   asm volatile(
@@ -56,10 +56,10 @@ NFN_DEVI void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b
 // three-level split x = x0 + x1 + x2 (11 + 11 + remaining bits): the forward GEMM t = h W + b feeds the
 // flows, whose log-prob can amplify a rounding of t by |dlogp/dt| ~ 10^2, so t gets full fp32 accuracy
 NFN_DEVI void split3_tf32(float x, unsigned& x0, unsigned& x1, unsigned& x2) {
-  x0 = f2tf32(x);
-  const float r1 = x - __uint_as_float(x0);
-  x1 = f2tf32(r1);
-  x2 = f2tf32(r1 - __uint_as_float(x1));
+  x0 = __float_as_uint(x);
+  const float r1 = x - tf32_trunc(x);
+  x1 = __float_as_uint(r1);
+  x2 = __float_as_uint(r1 - tf32_trunc(r1));
 }
 // D += A B with the six leading products of the three-level splits (smallest first)
 NFN_DEVI void mma_6xtf32(float (&d)[4], const unsigned (&a0)[4], const unsigned (&a1)[4], const unsigned (&a2)[4],
@@ -267,38 +267,36 @@ NFN_DEVI void dense_chain_body(const DenseArgs& a) {
         float* accb = sAccB + warp * P8;
         const unsigned one[4] = {0x3f800000u, 0x3f800000u, 0x3f800000u, 0x3f800000u};
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          unsigned bh[4][2], bl[4][2];
-          const int col = 8 * nt + g;
+        for (int mt = 0; mt < H / 16; ++mt) {
+          // A = h^T fragments of this warp's 32 rows, split once and reused by every n-tile
+          unsigned ah[4][4], al[4][4];
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const float v0 = (col < P) ? tT[(R0 + 8 * ks + tig) * S + col] : 0.0f;
-            const float v1 = (col < P) ? tT[(R0 + 8 * ks + tig + 4) * S + col] : 0.0f;
-            split_tf32(v0, bh[ks][0], bl[ks][0]);
-            split_tf32(v1, bh[ks][1], bl[ks][1]);
-          }
-          float cb[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            mma_tf32(cb, one, bl[ks]);
-            mma_tf32(cb, one, bh[ks]);
-          }
-          if (g == 0) {
-            accb[8 * nt + 2 * tig] += cb[0];
-            accb[8 * nt + 2 * tig + 1] += cb[1];
+            const float* hp = hcur + (R0 + 8 * ks + tig) * HS + 16 * mt + g;
+            split_tf32(hp[0], ah[ks][0], al[ks][0]);
+            split_tf32(hp[8], ah[ks][1], al[ks][1]);
+            split_tf32(hp[4 * HS], ah[ks][2], al[ks][2]);
+            split_tf32(hp[4 * HS + 8], ah[ks][3], al[ks][3]);
           }
 #pragma unroll
-          for (int mt = 0; mt < H / 16; ++mt) {
+          for (int nt = 0; nt < NT; ++nt) {
+            const int col = 8 * nt + g;
             float c[4] = {0.f, 0.f, 0.f, 0.f};
+            float cb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              unsigned ah[4], al[4];
-              const float* hp = hcur + (R0 + 8 * ks + tig) * HS + 16 * mt + g;
-              split_tf32(hp[0], ah[0], al[0]);
-              split_tf32(hp[8], ah[1], al[1]);
-              split_tf32(hp[4 * HS], ah[2], al[2]);
-              split_tf32(hp[4 * HS + 8], ah[3], al[3]);
-              mma_3xtf32(c, ah, al, bh[ks], bl[ks]);
+              unsigned bh[2], bl[2];
+              split_tf32((col < P) ? tT[(R0 + 8 * ks + tig) * S + col] : 0.0f, bh[0], bl[0]);
+              split_tf32((col < P) ? tT[(R0 + 8 * ks + tig + 4) * S + col] : 0.0f, bh[1], bl[1]);
+              mma_3xtf32(c, ah[ks], al[ks], bh, bl);
+              if (mt == 0) {  // bias gradient: ones^T dt
+                mma_tf32(cb, one, bl);
+                mma_tf32(cb, one, bh);
+              }
+            }
+            if (mt == 0 && g == 0) {
+              accb[8 * nt + 2 * tig] += cb[0];
+              accb[8 * nt + 2 * tig + 1] += cb[1];
             }
             float* p0 = acc + (16 * mt + g) * P8 + 8 * nt + 2 * tig;
             float* p1 = p0 + 8 * P8;

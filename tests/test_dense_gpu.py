@@ -83,8 +83,9 @@ def test_dense_chain_equals_unfused_composition(cuda_device, nfn_lib):
     P, B = 48, 50_000
     g = torch.Generator(device=cuda_device).manual_seed(3)
     h = torch.tanh(torch.randn((B, H), generator=g, device=cuda_device))
-    W = torch.randn((H, P), generator=g, device=cuda_device) * 0.2
-    b = torch.randn(P, generator=g, device=cuda_device) * 0.1
+    # small parameter scale: no ill-conditioned rows, so the sums over the batch are comparable too
+    W = torch.randn((H, P), generator=g, device=cuda_device) * 0.06
+    b = torch.randn(P, generator=g, device=cuda_device) * 0.05
     y = torch.randn((B, d), generator=g, device=cuda_device)
     t = (h.double() @ W.double() + b.double()).float()
     lp_u, dt_u, _ = F.chain_forward_backward(t, y, ft, d, tb, g_scale=-1.0 / B)
