@@ -47,8 +47,10 @@ NFN_DEVI void split_tf32(float x, unsigned& hi, unsigned& lo) {
   hi = __float_as_uint(x);
   lo = __float_as_uint(x - tf32_trunc(x));
 }
+// (not volatile: independent accumulators must be free to interleave -- a chain of dependent HMMAs
+// costs its full latency per instruction)
 NFN_DEVI void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
@@ -200,34 +202,52 @@ NFN_DEVI void dense_chain_body(const DenseArgs& a) {
     }
     float* hcur = hT + buf * G::kH;
 
-    // ---- GEMM 1: t[32 rows of this warp][P8] = h W + b
+    // ---- GEMM 1: t[32 rows of this warp][P8] = h W + b.  Both m-tiles and all n-tiles are in flight and
+    // the products are issued term-major, so consecutive HMMAs never depend on each other, and every
+    // W fragment is loaded and split once for both m-tiles.
+    {
+      unsigned a0[2][KH][4], a1[2][KH][4], a2[2][KH][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      const int r0 = warp * 32 + mt * 16;
-      unsigned a0[KH][4], a1[KH][4], a2[KH][4];
+      for (int mt = 0; mt < 2; ++mt) {
+        const int r0 = warp * 32 + mt * 16;
 #pragma unroll
-      for (int ks = 0; ks < KH; ++ks) {
-        split3_tf32(hcur[(r0 + g) * HS + 8 * ks + tig], a0[ks][0], a1[ks][0], a2[ks][0]);
-        split3_tf32(hcur[(r0 + g + 8) * HS + 8 * ks + tig], a0[ks][1], a1[ks][1], a2[ks][1]);
-        split3_tf32(hcur[(r0 + g) * HS + 8 * ks + tig + 4], a0[ks][2], a1[ks][2], a2[ks][2]);
-        split3_tf32(hcur[(r0 + g + 8) * HS + 8 * ks + tig + 4], a0[ks][3], a1[ks][3], a2[ks][3]);
+        for (int ks = 0; ks < KH; ++ks) {
+          split3_tf32(hcur[(r0 + g) * HS + 8 * ks + tig], a0[mt][ks][0], a1[mt][ks][0], a2[mt][ks][0]);
+          split3_tf32(hcur[(r0 + g + 8) * HS + 8 * ks + tig], a0[mt][ks][1], a1[mt][ks][1], a2[mt][ks][1]);
+          split3_tf32(hcur[(r0 + g) * HS + 8 * ks + tig + 4], a0[mt][ks][2], a1[mt][ks][2], a2[mt][ks][2]);
+          split3_tf32(hcur[(r0 + g + 8) * HS + 8 * ks + tig + 4], a0[mt][ks][3], a1[mt][ks][3], a2[mt][ks][3]);
+        }
       }
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        const int c0 = 8 * nt + 2 * tig;
-        float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
         for (int ks = 0; ks < KH; ++ks) {
           unsigned b0[2], b1[2], b2[2];
           split3_tf32(sW[(8 * ks + tig) * PW + 8 * nt + g], b0[0], b1[0], b2[0]);
           split3_tf32(sW[(8 * ks + tig + 4) * PW + 8 * nt + g], b0[1], b1[1], b2[1]);
-          mma_6xtf32(c, a0[ks], a1[ks], a2[ks], b0, b1, b2);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt], a2[mt][ks], b0);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt], a0[mt][ks], b2);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt], a1[mt][ks], b1);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt], a1[mt][ks], b0);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt], a0[mt][ks], b1);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt], a0[mt][ks], b0);
         }
-        c[0] += sB[c0]; c[1] += sB[c0 + 1]; c[2] += sB[c0]; c[3] += sB[c0 + 1];
-        float* d0 = tT + (r0 + g) * S + c0;
-        float* d1 = tT + (r0 + g + 8) * S + c0;
-        if (c0 < P) { d0[0] = c[0]; d1[0] = c[2]; }
-        if (c0 + 1 < P) { d0[1] = c[1]; d1[1] = c[3]; }
+        const int c0 = 8 * nt + 2 * tig;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const int r0 = warp * 32 + mt * 16;
+          float* d0 = tT + (r0 + g) * S + c0;
+          float* d1 = tT + (r0 + g + 8) * S + c0;
+          if (c0 < P) { d0[0] = c[mt][0] + sB[c0]; d1[0] = c[mt][2] + sB[c0]; }
+          if (c0 + 1 < P) { d0[1] = c[mt][1] + sB[c0 + 1]; d1[1] = c[mt][3] + sB[c0 + 1]; }
+        }
       }
     }
     __syncwarp();
@@ -278,64 +298,97 @@ NFN_DEVI void dense_chain_body(const DenseArgs& a) {
             split_tf32(hp[4 * HS], ah[ks][2], al[ks][2]);
             split_tf32(hp[4 * HS + 8], ah[ks][3], al[ks][3]);
           }
+          float c[NT][4], cb[NT][4];
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
-            const int col = 8 * nt + g;
-            float c[4] = {0.f, 0.f, 0.f, 0.f};
-            float cb[4] = {0.f, 0.f, 0.f, 0.f};
+            c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.0f;
+            cb[nt][0] = cb[nt][1] = cb[nt][2] = cb[nt][3] = 0.0f;
+          }
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              unsigned bh[2], bl[2];
-              split_tf32((col < P) ? tT[(R0 + 8 * ks + tig) * S + col] : 0.0f, bh[0], bl[0]);
-              split_tf32((col < P) ? tT[(R0 + 8 * ks + tig + 4) * S + col] : 0.0f, bh[1], bl[1]);
-              mma_3xtf32(c, ah[ks], al[ks], bh, bl);
-              if (mt == 0) {  // bias gradient: ones^T dt
-                mma_tf32(cb, one, bl);
-                mma_tf32(cb, one, bh);
-              }
+          for (int ks = 0; ks < 4; ++ks) {
+            unsigned bh[NT][2], bl[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+              const int col = 8 * nt + g;
+              split_tf32((col < P) ? tT[(R0 + 8 * ks + tig) * S + col] : 0.0f, bh[nt][0], bl[nt][0]);
+              split_tf32((col < P) ? tT[(R0 + 8 * ks + tig + 4) * S + col] : 0.0f, bh[nt][1], bl[nt][1]);
             }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_tf32(c[nt], al[ks], bh[nt]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_tf32(c[nt], ah[ks], bl[nt]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_tf32(c[nt], ah[ks], bh[nt]);
+            if (mt == 0) {  // bias gradient: ones^T dt
+#pragma unroll
+              for (int nt = 0; nt < NT; ++nt) mma_tf32(cb[nt], one, bl[nt]);
+#pragma unroll
+              for (int nt = 0; nt < NT; ++nt) mma_tf32(cb[nt], one, bh[nt]);
+            }
+          }
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
             if (mt == 0 && g == 0) {
-              accb[8 * nt + 2 * tig] += cb[0];
-              accb[8 * nt + 2 * tig + 1] += cb[1];
+              accb[8 * nt + 2 * tig] += cb[nt][0];
+              accb[8 * nt + 2 * tig + 1] += cb[nt][1];
             }
             float* p0 = acc + (16 * mt + g) * P8 + 8 * nt + 2 * tig;
             float* p1 = p0 + 8 * P8;
-            p0[0] += c[0]; p0[1] += c[1];
-            p1[0] += c[2]; p1[1] += c[3];
+            p0[0] += c[nt][0]; p0[1] += c[nt][1];
+            p1[0] += c[nt][2]; p1[1] += c[nt][3];
           }
         }
       }
       __syncwarp();
-      // ---- GEMM 2: dh[32 rows][H] = dt W^T  -> into the (now consumed) h tile of this warp's rows
+      // ---- GEMM 2: dh[32 rows][H] = dt W^T  -> into the (now consumed) h rows of this warp
+      {
+        constexpr int NH = H / 8;
+        float c[2][NH][4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const int r0 = warp * 32 + mt * 16;
-        float c[H / 8][4];
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < H / 8; ++nt) { c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.0f; }
+          for (int nt = 0; nt < NH; ++nt) { c[mt][nt][0] = c[mt][nt][1] = c[mt][nt][2] = c[mt][nt][3] = 0.0f; }
 #pragma unroll
         for (int ks = 0; ks < NT; ++ks) {
-          unsigned ah[4], al[4];
           const int k0 = 8 * ks + tig, k1 = k0 + 4;
-          split_tf32((k0 < P) ? tT[(r0 + g) * S + k0] : 0.0f, ah[0], al[0]);
-          split_tf32((k0 < P) ? tT[(r0 + g + 8) * S + k0] : 0.0f, ah[1], al[1]);
-          split_tf32((k1 < P) ? tT[(r0 + g) * S + k1] : 0.0f, ah[2], al[2]);
-          split_tf32((k1 < P) ? tT[(r0 + g + 8) * S + k1] : 0.0f, ah[3], al[3]);
+          unsigned ah[2][4], al[2][4], bh[NH][2], bl[NH][2];
 #pragma unroll
-          for (int nt = 0; nt < H / 8; ++nt) {
-            unsigned bh[2], bl[2];
-            split_tf32(sW[(8 * nt + g) * PW + k0], bh[0], bl[0]);
-            split_tf32(sW[(8 * nt + g) * PW + k1], bh[1], bl[1]);
-            mma_3xtf32(c[nt], ah, al, bh, bl);
+          for (int mt = 0; mt < 2; ++mt) {
+            const int r0 = warp * 32 + mt * 16;
+            split_tf32((k0 < P) ? tT[(r0 + g) * S + k0] : 0.0f, ah[mt][0], al[mt][0]);
+            split_tf32((k0 < P) ? tT[(r0 + g + 8) * S + k0] : 0.0f, ah[mt][1], al[mt][1]);
+            split_tf32((k1 < P) ? tT[(r0 + g) * S + k1] : 0.0f, ah[mt][2], al[mt][2]);
+            split_tf32((k1 < P) ? tT[(r0 + g + 8) * S + k1] : 0.0f, ah[mt][3], al[mt][3]);
           }
+#pragma unroll
+          for (int nt = 0; nt < NH; ++nt) {
+            split_tf32(sW[(8 * nt + g) * PW + k0], bh[nt][0], bl[nt][0]);
+            split_tf32(sW[(8 * nt + g) * PW + k1], bh[nt][1], bl[nt][1]);
+          }
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NH; ++nt) mma_tf32(c[mt][nt], al[mt], bh[nt]);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NH; ++nt) mma_tf32(c[mt][nt], ah[mt], bl[nt]);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NH; ++nt) mma_tf32(c[mt][nt], ah[mt], bh[nt]);
         }
         __syncwarp();  // every lane of the warp is done reading this warp's h rows (GEMM 3)
 #pragma unroll
-        for (int nt = 0; nt < H / 8; ++nt) {
-          float* d0 = hcur + (r0 + g) * HS + 8 * nt + 2 * tig;
-          float* d1 = hcur + (r0 + g + 8) * HS + 8 * nt + 2 * tig;
-          *reinterpret_cast<float2*>(d0) = make_float2(c[nt][0], c[nt][1]);
-          *reinterpret_cast<float2*>(d1) = make_float2(c[nt][2], c[nt][3]);
+        for (int mt = 0; mt < 2; ++mt) {
+          const int r0 = warp * 32 + mt * 16;
+#pragma unroll
+          for (int nt = 0; nt < NH; ++nt) {
+            float* d0 = hcur + (r0 + g) * HS + 8 * nt + 2 * tig;
+            float* d1 = hcur + (r0 + g + 8) * HS + 8 * nt + 2 * tig;
+            *reinterpret_cast<float2*>(d0) = make_float2(c[mt][nt][0], c[mt][nt][1]);
+            *reinterpret_cast<float2*>(d1) = make_float2(c[mt][nt][2], c[mt][nt][3]);
+          }
         }
       }
       __syncwarp();
