@@ -97,6 +97,39 @@ class FlowChainDistribution:
         return torch.exp(self.log_prob(y))
 
 
+class FusedDenseFlowChainDistribution(FlowChainDistribution):
+    """The same density with the emitting Dense(P) layer folded into the kernel: holds the last hidden
+    activation h[B, H] and the layer's (W[H, P], bias[P]) instead of t[B, P]; ``log_prob`` runs the fused
+    dense+chain kernel (t is formed in shared memory and never written to HBM).  ``.t`` materialises the
+    parameter rows on demand for callers that want them."""
+
+    def __init__(self, h, W, bias, flow_types, n_dims, trainable_base_dist):
+        self.h, self.W, self.bias = h, W, bias
+        self.flow_types = tuple(flow_types)
+        self.n_dims = n_dims
+        self.trainable_base_dist = trainable_base_dist
+        self._t = None
+
+    @property
+    def t(self):
+        if self._t is None:
+            self._t = torch.addmm(self.bias, self.h, self.W)
+        return self._t
+
+    @property
+    def batch_shape(self):
+        return _Shape(self.h.shape[:-1])
+
+    def log_prob(self, y):
+        y = _to_tensor_like(y, self.h)
+        if torch.is_grad_enabled() and (self.h.requires_grad or self.W.requires_grad):
+            return super().log_prob(y)  # autograd path goes through t
+        if y.shape[0] not in (self.h.shape[0], 1):
+            return super().log_prob(y)
+        return F.dense_chain_forward(self.h, self.W, self.bias, y, self.flow_types, self.n_dims,
+                                     self.trainable_base_dist)
+
+
 class InverseNormalizingFlowLayer(torch.nn.Module):
     """Turns the network output into an inverted-flow density (reference :215-294).
 

@@ -15,7 +15,12 @@ import torch
 import torch.distributed as dist
 
 from .. import functional as F
-from ..DistributionLayers import GaussianKernelsLayer, GaussianMixtureLayer, InverseNormalizingFlowLayer
+from ..DistributionLayers import (
+    FusedDenseFlowChainDistribution,
+    GaussianKernelsLayer,
+    GaussianMixtureLayer,
+    InverseNormalizingFlowLayer,
+)
 
 
 def default_device():
@@ -85,11 +90,42 @@ class BaseEstimator(torch.nn.Module):
         """Network output t[B, P] for conditioning inputs x."""
         return self.net(self._to_dev(x))
 
+    # ------------------------------------------------------------------ fused last layer
+    fuse_last_layer = True
+
+    def _fusable_last_layer(self):
+        """The emitting Dense(P) layer if it can be folded into the flow kernel:
+        NF head with at least one parameter, plain (non-variational) linear output layer whose
+        input width is 16, 32, 48 or 64."""
+        if not self.fuse_last_layer or not isinstance(self.dist_layer, InverseNormalizingFlowLayer):
+            return None
+        last = self.net[-1]
+        lin = getattr(last, "linear", None)
+        if lin is None or not isinstance(lin, torch.nn.Linear) or isinstance(lin, torch.nn.LazyLinear):
+            return None
+        if not F.dense_chain_supported(lin.in_features) or self.dist_layer.get_total_param_size() < 1:
+            return None
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            return None  # the data-parallel step all-reduces autograd's .grad tensors; keep it simple
+        return lin
+
+    def hidden_from_x(self, x):
+        h = self._to_dev(x)
+        for layer in list(self.net)[:-1]:
+            h = layer(h)
+        return h
+
     def forward(self, x, training=False):
         was = self.training
         self.train(bool(training))
         try:
             with torch.set_grad_enabled(bool(training)):
+                lin = self._fusable_last_layer()
+                if lin is not None and not training:
+                    layer = self.dist_layer
+                    return FusedDenseFlowChainDistribution(self.hidden_from_x(x), lin.weight.t().contiguous(),
+                                                           lin.bias, layer._flow_types, layer._n_dims,
+                                                           layer._trainable_base_dist)
                 return self.dist_layer(self.params_from_x(x))
         finally:
             self.train(was)
@@ -159,18 +195,33 @@ class BaseEstimator(torch.nn.Module):
         B = xb.shape[0]
         Bg = global_batch or B
         self.optimizer.zero_grad(set_to_none=True)
-        t = self.params_from_x(xb)
         y = self._y_input(yb, training=True)
         logp_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
-        dt = self._head_forward_backward(t, y, -1.0 / Bg, logp_sum)
-        extra = self._extra_loss()
         world = dist.get_world_size() if dist.is_initialized() else 1
-        if extra is not None:
-            # the regulariser is replicated on every rank: weight 1/world so that the summed
-            # gradient counts it once
-            torch.autograd.backward([t, extra], [dt, torch.full_like(extra, 1.0 / world)])
+        lin = self._fusable_last_layer()
+        if lin is not None and self._extra_loss() is None:
+            # ONE kernel for [Dense(P) forward, flow chain forward + reverse sweep, Dense(P) backward]:
+            # t / dt never touch HBM; the kernel returns dh, dW, dbias
+            layer = self.dist_layer
+            h = self.hidden_from_x(xb)
+            _, dh, dW, db = F.dense_chain_forward_backward(
+                h.detach(), lin.weight.detach().t().contiguous(), lin.bias.detach(), y, layer._flow_types,
+                layer._n_dims, layer._trainable_base_dist, g_scale=-1.0 / Bg, logp_sum=logp_sum)
+            lin.weight.grad = dW.t().contiguous()
+            lin.bias.grad = db
+            if h.requires_grad:
+                h.backward(dh)
         else:
-            t.backward(dt)
+            t = self.params_from_x(xb)
+            dt = self._head_forward_backward(t, y, -1.0 / Bg, logp_sum)
+            extra = self._extra_loss()
+            if extra is not None:
+                # the regulariser is replicated on every rank: weight 1/world so that the summed
+                # gradient counts it once
+                torch.autograd.backward([t, extra], [dt, torch.full_like(extra, 1.0 / world)])
+            else:
+                t.backward(dt)
+        extra = self._extra_loss()
         if world > 1:
             self._allreduce_grads(logp_sum)
         self.optimizer.step()
