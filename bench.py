@@ -290,7 +290,23 @@ def run_ours(args):
     want_col = bool(bwd and args.colsum and not mdn)
     packed = (world > 1 and bwd)
     use_peer = bool(packed and args.exchange == "peer" and not mdn)
-    comm = parallel.PeerComm(P + 1, device) if use_peer else None
+    comm = None
+    if use_peer:
+        # cudaIpc peer mapping can be unavailable (e.g. ranks in different containers): every rank must
+        # agree, so the outcome is all-reduced and the NCCL exchange is the fallback
+        try:
+            comm = parallel.PeerComm(P + 1, device)
+            ok = 1
+        except Exception as exc:  # noqa: BLE001
+            ok = 0
+            if rank == 0:
+                print("peer exchange unavailable (%s): falling back to NCCL" % exc, file=sys.stderr)
+        flag = torch.tensor([ok], device=device)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if comm is not None:
+                comm.close()
+            comm, use_peer = None, False
     step_no = [0]
     acc_base = acc_ring.data_ptr()
     row_bytes = (P + 1) * 8

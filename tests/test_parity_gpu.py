@@ -425,3 +425,78 @@ def test_errors_are_loud(cuda_device, nfn_lib):
                         ["radial"] * 3, 1, True)
     with pytest.raises(RuntimeError):  # CPU tensors are rejected: no fallback
         InverseNormalizingFlowLayer(["radial"], 1, False)(torch.zeros((4, 3))).log_prob(torch.zeros((4, 1)))
+
+
+def test_outputs_stay_inside_their_buffers(cuda_device, nfn_lib, kernel_path):
+    """compute-sanitizer is closed on this pool, so out-of-bounds writes are hunted with canaries:
+    every output lives inside a larger sentinel-filled allocation that must come back untouched
+    (ragged row counts exercise the partial last tile of every kernel path)."""
+    import ctypes
+
+    from normalizingflownetwork_b200 import _lib
+
+    SENT = 12345.0
+    PAD = 1024  # floats on each side
+
+    def guarded(n):
+        buf = torch.full((n + 2 * PAD,), SENT, device=cuda_device)
+        return buf, buf[PAD: PAD + n]
+
+    def intact(buf, n):
+        return bool((buf[:PAD] == SENT).all()) and bool((buf[PAD + n:] == SENT).all())
+
+    g = torch.Generator(device=cuda_device).manual_seed(4)
+    for ft, d, tb in [CONFIG_CHAINS["cfg2"], CONFIG_CHAINS["cfg4"], (["affine", "planar"], 3, False)]:
+        desc = _lib.make_desc(ft, d, tb)
+        P = nfn_lib.nfn_chain_param_size(ctypes.byref(desc))
+        for B in (1, 127, 128, 129, 1000):
+            t = torch.randn((B, P), generator=g, device=cuda_device) * 0.5
+            y = torch.randn((B, d), generator=g, device=cuda_device)
+            b_lp, lp = guarded(B)
+            b_dt, dt = guarded(B * P)
+            b_dy, dy = guarded(B * d)
+            _lib.check(nfn_lib.nfn_chain_forward_backward(
+                ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), B, None, ctypes.c_float(1.0), _lib.ptr(lp),
+                _lib.ptr(dt), _lib.ptr(dy), None, None, B, _lib.current_stream(cuda_device)))
+            torch.cuda.synchronize()
+            assert intact(b_lp, B) and intact(b_dt, B * P) and intact(b_dy, B * d), (ft, B)
+            assert torch.isfinite(lp).all() and torch.isfinite(dt).all()
+            b_lp2, lp2 = guarded(B)
+            _lib.check(nfn_lib.nfn_chain_forward(ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), B, _lib.ptr(lp2), B,
+                                                 _lib.current_stream(cuda_device)))
+            torch.cuda.synchronize()
+            assert intact(b_lp2, B) and torch.equal(lp, lp2)
+    # fused dense kernel and MDN head (not path-dependent, run once)
+    if kernel_path == "specialized":
+        ft, d, tb = CONFIG_CHAINS["cfg2"]
+        desc = _lib.make_desc(ft, d, tb)
+        H, P = 16, 48
+        for B in (1, 33, 129, 1000):
+            h = torch.tanh(torch.randn((B, H), generator=g, device=cuda_device))
+            W = torch.randn((H, P), generator=g, device=cuda_device) * 0.1
+            bias = torch.zeros(P, device=cuda_device)
+            y = torch.randn((B, d), generator=g, device=cuda_device)
+            b_lp, lp = guarded(B)
+            b_dh, dh = guarded(B * H)
+            b_dw, dW = guarded(H * P)
+            b_db, db = guarded(P)
+            dW.zero_()
+            db.zero_()
+            _lib.check(nfn_lib.nfn_dense_chain_forward_backward(
+                ctypes.byref(desc), H, _lib.ptr(h), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(y), B, None,
+                ctypes.c_float(1.0), _lib.ptr(lp), _lib.ptr(dh), _lib.ptr(dW), _lib.ptr(db), None, B,
+                _lib.current_stream(cuda_device)))
+            torch.cuda.synchronize()
+            assert intact(b_lp, B) and intact(b_dh, B * H) and intact(b_dw, H * P) and intact(b_db, P), B
+        K, dm = 20, 2
+        Pm = 2 * K * dm + K
+        for B in (1, 129, 1000):
+            t = torch.randn((B, Pm), generator=g, device=cuda_device) * 0.5
+            y = torch.randn((B, dm), generator=g, device=cuda_device)
+            b_lp, lp = guarded(B)
+            b_dt, dt = guarded(B * Pm)
+            _lib.check(nfn_lib.nfn_mdn_forward_backward(K, dm, _lib.ptr(t), _lib.ptr(y), B, None, ctypes.c_float(1.0),
+                                                        _lib.ptr(lp), _lib.ptr(dt), None, None, None, B,
+                                                        _lib.current_stream(cuda_device)))
+            torch.cuda.synchronize()
+            assert intact(b_lp, B) and intact(b_dt, B * Pm), B
