@@ -94,32 +94,49 @@ class PeerComm:
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.mapped = []
+        self.comm = None
+        self.region = None
+        err = None
         with torch.cuda.device(self.device):
             region = ctypes.c_void_p()
             handle = ctypes.create_string_buffer(64)
-            _lib.check(self.lib.nfn_peer_alloc(self.world, self.n_values, ctypes.byref(region), handle))
-            self.region = region
+            try:
+                _lib.check(self.lib.nfn_peer_alloc(self.world, self.n_values, ctypes.byref(region), handle))
+                self.region = region
+            except Exception as exc:  # noqa: BLE001 -- every rank must still reach the collectives below
+                err = exc
             handles = [bytes(handle.raw)]
             if self.world > 1:
                 mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=self.device)
                 gathered = [torch.empty_like(mine) for _ in range(self.world)]
                 dist.all_gather(gathered, mine)
                 handles = [bytes(g.cpu().tolist()) for g in gathered]
-            regions = (ctypes.c_void_p * self.world)()
-            for r in range(self.world):
-                if r == self.rank:
-                    regions[r] = region.value
-                else:
-                    m = ctypes.c_void_p()
-                    _lib.check(self.lib.nfn_peer_open(handles[r], ctypes.byref(m)))
-                    self.mapped.append(m)
-                    regions[r] = m.value
-            comm = ctypes.c_void_p()
-            _lib.check(self.lib.nfn_peer_comm_create(self.world, self.rank, self.n_values, regions,
-                                                     ctypes.byref(comm)))
-            self.comm = comm
-        if self.world > 1:
-            dist.barrier()  # every rank has mapped every region before the first exchange
+            if err is None:
+                try:
+                    regions = (ctypes.c_void_p * self.world)()
+                    for r in range(self.world):
+                        if r == self.rank:
+                            regions[r] = region.value
+                        else:
+                            m = ctypes.c_void_p()
+                            _lib.check(self.lib.nfn_peer_open(handles[r], ctypes.byref(m)))
+                            self.mapped.append(m)
+                            regions[r] = m.value
+                    comm = ctypes.c_void_p()
+                    _lib.check(self.lib.nfn_peer_comm_create(self.world, self.rank, self.n_values, regions,
+                                                             ctypes.byref(comm)))
+                    self.comm = comm
+                except Exception as exc:  # noqa: BLE001
+                    err = exc
+            if self.world > 1:
+                # agreement + barrier in one: every rank has mapped every region, or nobody uses the comm
+                ok = torch.tensor([0 if err is not None else 1], device=self.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok.item()) == 0 and err is None:
+                    err = RuntimeError("peer-memory set-up failed on another rank")
+        if err is not None:
+            self._release()
+            raise RuntimeError("PeerComm set-up failed: %s" % err)
 
     def allreduce(self, values, out=None):
         """Sum device float64 ``values[n_values]`` over all ranks (one tiny kernel, no NCCL)."""
@@ -130,6 +147,16 @@ class PeerComm:
                                                         self._lib.current_stream(self.device)))
         return out
 
+    def _release(self):
+        with torch.cuda.device(self.device):
+            if self.comm is not None:
+                self.lib.nfn_peer_comm_destroy(self.comm)
+            for m in self.mapped:
+                self.lib.nfn_peer_close(m)
+            if self.region is not None:
+                self.lib.nfn_peer_free(self.region)
+        self.comm, self.region, self.mapped = None, None, []
+
     def close(self):
         if getattr(self, "comm", None) is None:
             return
@@ -137,11 +164,7 @@ class PeerComm:
             torch.cuda.synchronize()
             if self.world > 1:
                 dist.barrier()  # nobody unmaps while a peer may still push
-            self.lib.nfn_peer_comm_destroy(self.comm)
-            for m in self.mapped:
-                self.lib.nfn_peer_close(m)
-            self.lib.nfn_peer_free(self.region)
-        self.comm = None
+        self._release()
 
 
 def barrier():
