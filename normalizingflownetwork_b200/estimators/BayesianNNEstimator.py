@@ -73,7 +73,9 @@ class DenseVariational(torch.nn.Module):
                 w = loc.expand(n_draws, -1)
             else:
                 w = loc + scale * torch.randn((n_draws,) + tuple(loc.shape), device=loc.device, generator=generator)
-            self.last_kl = None
+            # exact KL does not depend on the draws; the one-sample estimate is averaged over them
+            self.last_kl = self.kl_weight * (self._kl(q, r, None) if self.kl_use_exact
+                                             else (q.log_prob(w) - r.log_prob(w)).mean())
             out = torch.baddbmm(w[:, nk:].unsqueeze(1), x, w[:, :nk].view(n_draws, self.in_features, self.units))
         return self.act(out)
 
@@ -81,7 +83,7 @@ class DenseVariational(torch.nn.Module):
 class BayesianNNEstimator(BaseEstimator):
     def __init__(self, dist_layer, kl_weight_scale, kl_use_exact=True, hidden_sizes=(10,), activation="tanh",
                  learning_rate=3e-2, noise_reg=("fixed_rate", 0.0), trainable_prior=False, map_mode=False,
-                 prior_scale=1.0, random_seed=22, device=None):
+                 prior_scale=1.0, random_seed=22, device=None, n_train_draws=1):
         torch.manual_seed(random_seed)
         torch.nn.Module.__init__(self)
         self.map_mode = map_mode
@@ -93,6 +95,9 @@ class BayesianNNEstimator(BaseEstimator):
                          random_seed=random_seed, device=device)
         self.map_mode = map_mode
         self.learning_rate = learning_rate
+        # S Monte-Carlo weight draws per training step, folded into the batch (BASELINE config 4);
+        # 1 = the reference's behaviour (one draw shared by the mini-batch)
+        self.n_train_draws = int(n_train_draws)
         # instance-level noise levels (the reference shadows the class variables, :38-39)
         self.x_noise_std = 0.0
         self.y_noise_std = 0.0
@@ -136,6 +141,30 @@ class BayesianNNEstimator(BaseEstimator):
         for layer in self.net[2:]:
             h = layer(h, n_draws=n_draws, generator=self._weight_generator())
         return h.reshape(n_draws * h.shape[1], h.shape[2])
+
+    def train_step(self, xb, yb, global_batch=None):
+        if self.n_train_draws <= 1 or self.map_mode:
+            return super().train_step(xb, yb, global_batch=global_batch)
+        # S draws folded into the batch: one batched GEMM per layer, ONE head launch over S*B rows
+        import torch.distributed as dist
+
+        self.train(True)
+        S = self.n_train_draws
+        B = xb.shape[0]
+        Bg = global_batch or B
+        self.optimizer.zero_grad(set_to_none=True)
+        t = self.params_from_x_draws(xb, S)
+        y = self._y_input(yb, training=True).repeat(S, 1)
+        logp_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
+        dt = self._head_forward_backward(t, y, -1.0 / (S * Bg), logp_sum)
+        extra = self._extra_loss()
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        torch.autograd.backward([t, extra], [dt, torch.full_like(extra, 1.0 / world)])
+        if world > 1:
+            self._allreduce_grads(logp_sum)
+        self.optimizer.step()
+        loss = -logp_sum.to(torch.float32) / (S * Bg) + self._log_ystd_sum() + extra.detach()
+        return loss.reshape(())
 
     def _extra_loss(self):
         kls = [l.last_kl for l in self.net if isinstance(l, DenseVariational) and l.last_kl is not None]

@@ -162,3 +162,19 @@ def test_cuda_graph_train_step_matches_eager(cuda_device):
     assert graphed.history[-1] < graphed.history[0] - 0.05
     # same seed, same data order, noise off: the two loops follow the same trajectory
     np.testing.assert_allclose(graphed.history, eager.history, rtol=2e-3, atol=2e-3)
+
+
+def test_bayesian_training_with_folded_draws(cuda_device):
+    """BASELINE config 4: S Monte-Carlo weight draws folded into the batch of one training step."""
+    from normalizingflownetwork_b200.estimators import BayesNormalizingFlowNetwork
+
+    x, y = _cosine(1024)
+    m = BayesNormalizingFlowNetwork(1, kl_weight_scale=1.0 / x.shape[0], n_flows=5, hidden_sizes=(16, 16),
+                                    n_train_draws=8)
+    m.fit(x, y, batch_size=256, epochs=15, verbose=0)
+    assert np.isfinite(m.history).all()
+    assert m.history[-1] < m.history[0]
+    # the S-draw step averages the NLL over draws: its loss is close to the 1-draw loss in expectation
+    m1 = BayesNormalizingFlowNetwork(1, kl_weight_scale=1.0 / x.shape[0], n_flows=5, hidden_sizes=(16, 16))
+    m1.fit(x, y, batch_size=256, epochs=15, verbose=0)
+    assert abs(m.history[-1] - m1.history[-1]) < 0.5
