@@ -177,4 +177,4 @@ def test_bayesian_training_with_folded_draws(cuda_device):
     # the S-draw step averages the NLL over draws: its loss is close to the 1-draw loss in expectation
     m1 = BayesNormalizingFlowNetwork(1, kl_weight_scale=1.0 / x.shape[0], n_flows=5, hidden_sizes=(16, 16))
     m1.fit(x, y, batch_size=256, epochs=15, verbose=0)
-    assert abs(m.history[-1] - m1.history[-1]) < 0.5
+    assert abs(m.history[-1] - m1.history[-1]) < 0.2 * abs(m1.history[-1])
