@@ -98,6 +98,15 @@ int nfn_chain_forward(const nfn_chain_desc* desc, const float* t, const float* y
                       int64_t y_rows, float* logp, int64_t B, void* stream);
 
 /*
+ * Outer-product density grid: every parameter row against every event of y_grid[n_y, d] -- the loop
+ * `for i in range(y_num): dist.prob(y[i])` of plot_model (evaluation/visualization/flow_plotting.py:33-53).
+ * logp is [n_y, B] (event-major).  Each parameter tile is staged once and reused for all n_y events,
+ * so the parameter tensor is read from HBM once instead of n_y times.
+ */
+int nfn_chain_forward_grid(const nfn_chain_desc* desc, const float* t, const float* y_grid, int64_t n_y,
+                           float* logp, int64_t B, void* stream);
+
+/*
  * Fused forward + reverse sweep: replaces log_prob + tape.gradient of the Keras train
  * step (BaseEstimator.py:55-59 loss closure under Sequential.fit).
  *   g_logp     [B] device, nullable: upstream cotangent of logp per row

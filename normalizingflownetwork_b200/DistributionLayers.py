@@ -96,6 +96,15 @@ class FlowChainDistribution:
     def prob(self, y):
         return torch.exp(self.log_prob(y))
 
+    def log_prob_grid(self, y_grid):
+        """[n_y, B]: every event of ``y_grid[n_y, d]`` against every batch row, parameters read once
+        (what the reference's plot_model does with one ``dist.prob(y[i])`` call per grid line)."""
+        return F.chain_forward_grid(self.t, _to_tensor_like(y_grid, self.t), self.flow_types, self.n_dims,
+                                    self.trainable_base_dist)
+
+    def prob_grid(self, y_grid):
+        return torch.exp(self.log_prob_grid(y_grid))
+
 
 class FusedDenseFlowChainDistribution(FlowChainDistribution):
     """The same density with the emitting Dense(P) layer folded into the kernel: holds the last hidden

@@ -50,6 +50,8 @@ SIGNATURES = {
     "nfn_jit_compile_check": (_i64, [ctypes.POINTER(ChainDesc), ctypes.c_int]),
     "nfn_chain_forward": (ctypes.c_int, [ctypes.POINTER(ChainDesc), _c_float_p, _c_float_p, _i64,
                                         _c_float_p, _i64, ctypes.c_void_p]),
+    "nfn_chain_forward_grid": (ctypes.c_int, [ctypes.POINTER(ChainDesc), _c_float_p, _c_float_p, _i64,
+                                             _c_float_p, _i64, ctypes.c_void_p]),
     "nfn_chain_forward_backward": (ctypes.c_int, [ctypes.POINTER(ChainDesc), _c_float_p, _c_float_p, _i64,
                                                  _c_float_p, ctypes.c_float, _c_float_p, _c_float_p,
                                                  _c_float_p, ctypes.c_void_p, _c_float_p, _i64,

@@ -221,6 +221,22 @@ int nfn_chain_forward(const nfn_chain_desc* desc, const float* t, const float* y
   return chain_dispatch(desc, a, false, (cudaStream_t)stream);
 }
 
+int nfn_chain_forward_grid(const nfn_chain_desc* desc, const float* t, const float* y_grid, int64_t n_y,
+                           float* logp, int64_t B, void* stream) {
+  int rc = check_desc(desc);
+  if (rc != NFN_OK) return rc;
+  if (B < 0 || n_y < 0 || n_y > (1 << 30)) return set_error(NFN_ERR_SHAPE, "B=%lld, n_y=%lld", (long long)B, (long long)n_y);
+  if (B == 0 || n_y == 0) return NFN_OK;
+  const int P = param_size(desc);
+  if (!y_grid || !logp || (P > 0 && !t)) return set_error(NFN_ERR_NULL, "t, y_grid and logp must be non-NULL");
+  if (!aligned(t, 16)) return set_error(NFN_ERR_ALIGN, "t must be 16-byte aligned");
+  if (!aligned(y_grid, event_align(desc->n_dims)))
+    return set_error(NFN_ERR_ALIGN, "y_grid must be %zu-byte aligned", event_align(desc->n_dims));
+  ChainArgs a{};
+  a.t = t; a.y = y_grid; a.logp = logp; a.B = B; a.g_scale = 1.0f; a.y_broadcast = 1; a.grid_ny = (int)n_y;
+  return chain_dispatch(desc, a, false, (cudaStream_t)stream);
+}
+
 int nfn_chain_forward_backward(const nfn_chain_desc* desc, const float* t, const float* y,
                                int64_t y_rows, const float* g_logp, float g_scale, float* logp,
                                float* dt, float* dy, double* logp_sum, double* dt_colsum, int64_t B,

@@ -106,6 +106,11 @@ struct ChainArgs {
   long long B;
   float g_scale;
   int y_broadcast;
+  // forward only: grid_ny > 0 scores the outer product of the B parameter rows with grid_ny events
+  // y[grid_ny, d]; logp is [grid_ny, B] (event-major).  The parameter tile is staged once and
+  // reused for every event (reference evaluation/visualization/flow_plotting.py:33-53).
+  int grid_ny;
+  int pad_;
   PeerArgs peer;
 };
 
@@ -558,6 +563,27 @@ NFN_DEVI void chain_body(const ChainArgs& a) {
     }
 
     const long long r = tile * T + threadIdx.x;
+    if constexpr (!BWD) {
+      if (a.grid_ny > 0) {
+        if (r < a.B) {
+          float* row = buf + threadIdx.x * S;
+          using Base = BaseDist<D, Spec::BASE, M>;
+          float bth[Base::NA];
+          if constexpr (Spec::BASE) Span<0, 2 * D, V>::load(row, bth);
+          for (int j = 0; j < a.grid_ny; ++j) {
+            float zg[D];
+            load_event<D>(a.y, j, zg);  // same address for the whole warp: one broadcast load
+            float zs[Spec::KA][D];
+            LogDetAcc<M> ld;
+            FwdSweep<Spec, M, V, false, 0>::run(row, zg, zs, ld);
+            a.logp[(long long)j * a.B + r] = Base::log_prob(bth, zg) + ld.nat();
+          }
+        }
+        if constexpr (P > 0) __syncthreads();
+        slot = (slot + 1 == NB) ? 0 : slot + 1;
+        continue;
+      }
+    }
     if (r < a.B) {
       float* row = buf + threadIdx.x * S;
       float zs[Spec::KA][D];

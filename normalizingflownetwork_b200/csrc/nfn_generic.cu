@@ -35,6 +35,34 @@ __global__ void __launch_bounds__(128) chain_generic_kernel(const ChainArgs a, c
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < a.B;
        r += (long long)gridDim.x * blockDim.x) {
     const float* row = a.t + r * c.P;
+    if constexpr (!BWD) {
+      if (a.grid_ny > 0) {  // outer-product scoring: B parameter rows x grid_ny events
+        for (int j = 0; j < a.grid_ny; ++j) {
+          float zg[D];
+          load_event<D>(a.y, j, zg);
+          LogDetAcc<M> ldg;
+          for (int k = 0; k < c.K; ++k) {
+            const float* p = row + c.off[k];
+            switch (c.type[k]) {
+              case kPlanar: { float th[2 * D + 1]; ld_row(p, th); PlanarFlow<D, M>::fwd(th, zg, ldg); } break;
+              case kRadial: { float th[D + 2]; ld_row(p, th); RadialFlow<D, M>::fwd(th, zg, ldg); } break;
+              default: { float th[2 * D]; ld_row(p, th); AffineFlow<D, M>::fwd(th, zg, ldg); } break;
+            }
+          }
+          float lpg;
+          if (c.base) {
+            float bt[2 * D];
+            ld_row(row, bt);
+            lpg = BaseDist<D, true, M>::log_prob(bt, zg) + ldg.nat();
+          } else {
+            float dummy[1] = {0.0f};
+            lpg = BaseDist<D, false, M>::log_prob(dummy, zg) + ldg.nat();
+          }
+          a.logp[(long long)j * a.B + r] = lpg;
+        }
+        continue;
+      }
+    }
     float z[D];
     load_event<D>(a.y, a.y_broadcast ? 0 : r, z);
     float zs[BWD ? NFN_MAX_FLOWS * D : 1];

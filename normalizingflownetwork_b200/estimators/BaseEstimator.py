@@ -363,6 +363,18 @@ class BaseEstimator(torch.nn.Module):
             y_circ = (self._to_dev(y) - self.y_mean) / self.y_std
             return output.prob(y_circ) / torch.prod(self.y_std)
 
+    def pdf_grid(self, x, y_values):
+        """Density heat-map [len(y_values), len(x)] of p(y | x) in data units: the reference's plot_model
+        loop (evaluation/visualization/flow_plotting.py:33-53) as ONE kernel launch for NF heads."""
+        with torch.no_grad():
+            output = self.forward(x)
+            y_circ = (self._to_dev(np.asarray(y_values, np.float32).reshape(-1, self.y_mean.numel())) - self.y_mean) / self.y_std
+            if hasattr(output, "log_prob_grid"):
+                lp = output.log_prob_grid(y_circ)
+            else:
+                lp = torch.stack([output.log_prob(y_circ[i:i + 1]) for i in range(y_circ.shape[0])])
+            return torch.exp(lp - self._log_ystd_sum())
+
     def log_pdf(self, x, y):
         x = np.asarray(x, dtype=np.float32) if not torch.is_tensor(x) else x
         y = np.asarray(y, dtype=np.float32) if not torch.is_tensor(y) else y

@@ -76,6 +76,26 @@ def chain_forward(t, y, flow_types, n_dims, trainable_base_dist):
     return logp
 
 
+def chain_forward_grid(t, y_grid, flow_types, n_dims, trainable_base_dist):
+    """log_prob of every parameter row against every event: returns [n_y, B] (event-major).
+    The parameter tensor is read once, not once per event."""
+    lib = _lib.load()
+    desc = _lib.make_desc(flow_types, n_dims, trainable_base_dist)
+    P = _lib.check(lib.nfn_chain_param_size(ctypes.byref(desc)))
+    t = _aligned(_as_f32_cuda(t, "t"))
+    if t.dim() != 2 or t.shape[1] != P:
+        raise AssertionError("chain_forward_grid: expected [B, %d] parameters, got %s" % (P, tuple(t.shape)))
+    y_grid = _aligned(_as_f32_cuda(y_grid, "y_grid", device=t.device))
+    if y_grid.dim() != 2 or y_grid.shape[1] != n_dims:
+        raise ValueError("chain_forward_grid: y_grid must be [n_y, %d]" % n_dims)
+    B, ny = t.shape[0], y_grid.shape[0]
+    logp = torch.empty((ny, B), dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.check(lib.nfn_chain_forward_grid(ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y_grid), ny, _lib.ptr(logp),
+                                              B, _lib.current_stream(t.device)))
+    return logp
+
+
 def chain_forward_backward(t, y, flow_types, n_dims, trainable_base_dist, g_logp=None, g_scale=1.0,
                            want_dy=False, logp_sum=None, dt_colsum=None, out_logp=None, out_dt=None):
     """Fused forward + reverse sweep.  Returns (logp[B], dt[B,P], dy[B,d] or None).

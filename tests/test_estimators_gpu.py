@@ -178,3 +178,20 @@ def test_bayesian_training_with_folded_draws(cuda_device):
     m1 = BayesNormalizingFlowNetwork(1, kl_weight_scale=1.0 / x.shape[0], n_flows=5, hidden_sizes=(16, 16))
     m1.fit(x, y, batch_size=256, epochs=15, verbose=0)
     assert abs(m.history[-1] - m1.history[-1]) < 0.2 * abs(m1.history[-1])
+
+
+def test_pdf_grid_matches_per_line_pdf(cuda_device):
+    """plot_model (evaluation/visualization/flow_plotting.py:33-53) scores one grid line per call;
+    pdf_grid does the whole heat-map in one launch and must agree line by line."""
+    from normalizingflownetwork_b200.estimators import NormalizingFlowNetwork
+
+    x, y = _cosine(512)
+    model = NormalizingFlowNetwork.build_function(n_dims=1, n_flows=3, hidden_sizes=(16, 16), activation="tanh")
+    model.fit(x, y, batch_size=128, epochs=2, verbose=0)
+    xs = np.linspace(-3, 3, 37, dtype=np.float32).reshape(-1, 1)
+    ys = np.linspace(-4, 4, 21, dtype=np.float32).reshape(-1, 1)
+    grid = model.pdf_grid(xs, ys).cpu().numpy()
+    assert grid.shape == (21, 37)
+    for j in range(21):
+        line = model.pdf(xs, np.full_like(xs, ys[j, 0])).cpu().numpy()
+        np.testing.assert_allclose(grid[j], line, rtol=2e-5, atol=1e-7)

@@ -151,6 +151,29 @@ def test_chain_vs_oracle_ragged(cuda_device, nfn_lib, math_mode, kernel_path, cf
 
 
 @pytest.mark.parametrize("cfg", sorted(CONFIG_CHAINS))
+@pytest.mark.parametrize("B,n_y", [(1, 1), (129, 7), (1000, 33)])
+def test_chain_grid_vs_oracle(cuda_device, nfn_lib, math_mode, kernel_path, cfg, B, n_y):
+    """Outer-product density grid (plot_model, evaluation/visualization/flow_plotting.py:33-53):
+    logp[j, b] must equal the broadcast-y log_prob of event j, which the oracle computes row by row."""
+    from normalizingflownetwork_b200 import functional as F
+
+    ft, d, tb = CONFIG_CHAINS[cfg]
+    rng = np.random.default_rng(1000 + B + n_y)
+    P = an.layout(ft, d, tb)[1]
+    t = rng.normal(0, 0.5, (B, P)).astype(np.float32)
+    yg = rng.normal(0, 1.5, (n_y, d)).astype(np.float32)
+    got = F.chain_forward_grid(dev(t, cuda_device), dev(yg, cuda_device), ft, d, tb).cpu().numpy()
+    assert got.shape == (n_y, B)
+    tag = "%s grid B=%d n_y=%d %s/%s" % (cfg, B, n_y, math_mode, kernel_path)
+    for j in range(n_y):
+        ref = an.chain_forward_backward(t, yg[j:j + 1], ft, d, tb, need_grad=False)[0]
+        assert_logp(got[j], ref, what=tag + " event %d" % j)
+    # the grid entry and the broadcast-y entry run the same arithmetic
+    one = F.chain_forward(dev(t, cuda_device), dev(yg[:1], cuda_device), ft, d, tb).cpu().numpy()
+    np.testing.assert_array_equal(one, got[0])
+
+
+@pytest.mark.parametrize("cfg", sorted(CONFIG_CHAINS))
 def test_chain_vs_oracle_2p16(cuda_device, nfn_lib, cfg):
     """2^16 rows, t ~ N(0, 0.5^2), y ~ N(0, 1), seed 22 -- the BASELINE.md parity protocol."""
     from normalizingflownetwork_b200 import functional as F
