@@ -535,8 +535,14 @@ static int host_pipeline(int P, int d, bool bwd, const float* t, const float* y,
     if (dt_colsum) memset(dt_colsum, 0, (size_t)P * sizeof(double));
     return NFN_OK;
   }
-  // ~16 MiB of parameters per chunk, at least 3 chunks in flight when B allows it
-  int64_t rows = (int64_t)((16u << 20) / ((size_t)(P > 0 ? P : 1) * sizeof(float)));
+  // ~16 MiB of parameters per chunk (NFN_B200_HOST_CHUNK_MB overrides, tuning only), at least 3
+  // chunks in flight when B allows it
+  size_t chunk_mb = 16;
+  if (const char* ev = getenv("NFN_B200_HOST_CHUNK_MB")) {
+    const long v = atol(ev);
+    if (v >= 1 && v <= 1024) chunk_mb = (size_t)v;
+  }
+  int64_t rows = (int64_t)((chunk_mb << 20) / ((size_t)(P > 0 ? P : 1) * sizeof(float)));
   rows = rows / 1024 * 1024;
   if (rows < 1024) rows = 1024;
   if (rows > B) rows = B;
