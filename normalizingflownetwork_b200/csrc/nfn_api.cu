@@ -295,6 +295,12 @@ static int dense_dispatch(const nfn_chain_desc* desc, int hidden, const DenseArg
   const std::string key = chain_key(desc->n_dims, desc->trainable_base != 0, desc->n_flows, desc->flow_type);
   const int mode = math_mode();
   const DenseKernels* k = find_dense(key + "|h" + std::to_string(hidden));
+  // Two implementations of the same contract: warp-level mma.sync (default) and tcgen05 / TMEM
+  // (NFN_B200_DENSE_MMA=tc5; see nfn_dense_tc5.cuh for where each one wins)
+  if (k && k->fn5[mode][bwd ? 1 : 0]) {
+    const char* ev = getenv("NFN_B200_DENSE_MMA");
+    if (ev && strcmp(ev, "tc5") == 0) return cuda_error(k->fn5[mode][bwd ? 1 : 0](a, st), key.c_str());
+  }
   if (k && k->fn[mode][bwd ? 1 : 0]) return cuda_error(k->fn[mode][bwd ? 1 : 0](a, st), key.c_str());
   bool served = false;
   cudaError_t e = launch_dense_jit(desc, hidden, key, a, bwd, mode, st, &served);

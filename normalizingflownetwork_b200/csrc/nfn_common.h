@@ -10,6 +10,7 @@
 #include "../../include/nfn_b200.h"
 #include "nfn_chain_kernel.cuh"
 #include "nfn_dense_chain.cuh"
+#include "nfn_dense_tc5.cuh"
 
 struct nfn_peer_comm;  // opaque handle of the C ABI (nfn_peer.cu)
 
@@ -113,7 +114,8 @@ struct ChainRegistrar {
 // ------------------------------------------------------------------ fused Dense(P) + chain
 typedef cudaError_t (*DenseLaunchFn)(const DenseArgs&, cudaStream_t);
 struct DenseKernels {
-  DenseLaunchFn fn[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [math mode][bwd]
+  DenseLaunchFn fn[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [math mode][bwd]  mma.sync version
+  DenseLaunchFn fn5[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [math mode][bwd]  tcgen05 / TMEM version
 };
 void register_dense(const std::string& key, const DenseKernels& k);
 const DenseKernels* find_dense(const std::string& key);
@@ -149,6 +151,43 @@ cudaError_t launch_dense(const DenseArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// tcgen05 / TMEM version (nfn_dense_tc5.cuh): 128 threads per CTA, one TMEM allocation per CTA
+template <class Spec, int H, bool BWD, class M>
+cudaError_t launch_dense_tc5(const DenseArgs& a, cudaStream_t st) {
+  using G = tc5::Geo<Spec::P(), H, BWD>;
+  constexpr int T = tc5::kRows;
+  constexpr unsigned kSmem = G::kBytes;
+  constexpr int kBySmem = (int)((227u * 1024u) / (kSmem + 1024u));
+  constexpr int kByTmem = (int)(512u / G::kCols);
+  constexpr int kWant = 4;
+  constexpr int kCap = kBySmem < kByTmem ? kBySmem : kByTmem;
+  constexpr int MINB = kCap < 1 ? 1 : (kCap < kWant ? kCap : kWant);
+  auto kern = tc5::dense_tc5_kernel<Spec, H, BWD, M, MINB>;
+  struct Cfg {
+    int device = -1;
+    int ctas_per_sm = 0;
+  };
+  static thread_local Cfg cfg;
+  const DeviceInfo& di = device_info();
+  if (cfg.device != di.device) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, kSmem);
+    if (e != cudaSuccess) return e;
+    // never more resident CTAs than TMEM allocations that fit (a CTA would spin in tcgen05.alloc)
+    if (occ > kByTmem) occ = kByTmem;
+    cfg.ctas_per_sm = occ > 0 ? occ : 1;
+    cfg.device = di.device;
+  }
+  const long long ntiles = (a.B + T - 1) / T;
+  long long grid = (long long)di.sm_count * cfg.ctas_per_sm;
+  if (grid > ntiles) grid = ntiles;
+  kern<<<(unsigned)grid, T, kSmem, st>>>(a);
+  count_launch();
+  return cudaGetLastError();
+}
+
 template <class Spec, int H>
 struct DenseRegistrar {
   explicit DenseRegistrar() {
@@ -157,6 +196,10 @@ struct DenseRegistrar {
     k.fn[0][1] = &launch_dense<Spec, H, true, MathFast>;
     k.fn[1][0] = &launch_dense<Spec, H, false, MathAccurate>;
     k.fn[1][1] = &launch_dense<Spec, H, true, MathAccurate>;
+    k.fn5[0][0] = &launch_dense_tc5<Spec, H, false, MathFast>;
+    k.fn5[0][1] = &launch_dense_tc5<Spec, H, true, MathFast>;
+    k.fn5[1][0] = &launch_dense_tc5<Spec, H, false, MathAccurate>;
+    k.fn5[1][1] = &launch_dense_tc5<Spec, H, true, MathAccurate>;
     uint8_t types[Spec::KA];
     for (int i = 0; i < Spec::K; ++i) types[i] = (uint8_t)Spec::type(i);
     register_dense(chain_key(Spec::D, Spec::BASE, Spec::K, types) + "|h" + std::to_string(H), k);

@@ -1,0 +1,474 @@
+// nfn_dense_tc5.cuh -- Dense(P) + flow chain with the GEMMs on tcgen05 / TMEM (sm_100a).
+//
+// Same contract as dense_chain_kernel (nfn_dense_chain.cuh): per tile of 128 rows
+//     t  = h W + b ;  flows forward + reverse sweep per row ;  dh = dt W^T ;  dW += h^T dt ;  db += 1^T dt
+// but the GEMMs are single-thread-issued tcgen05.mma (kind::f16 on exact three-level bf16 splits,
+// M = 128) with the accumulators in tensor memory, so the per-thread mma.sync fragment work (loads,
+// splits, shuffles: >60 % of the instructions of the warp-level version) disappears:
+//
+//   thread r splits its own h row (registers) into 3 bf16 levels -> K-major operand tiles in smem
+//   GEMM 1   D1[128 x PN]  = sum of the 9 level products  A_i[128 x H] * W_j[H x PN]      (fp32-grade t)
+//   tcgen05.ld 32x32b hands thread r exactly row r of D1  -> + bias -> per-row flows (nfn_flows.cuh)
+//   thread r splits its dt row into 3 bf16 levels -> operand tiles D_i [128 x PN]
+//   GEMM 2   D2[128 x H]   = dt W^T            (A = D_i K-major,          B = W[H][P] as N x K)
+//   GEMM 3   D3[PN  x H]   = dt^T h            (A = D_i read MN-major,    B = the h tiles read MN-major)
+//   GEMM 4   D4[PN  x 16]  = dt^T [1 0 ...]    (bias gradient: B is one constant 512-byte tile)
+//   tcgen05.ld D2 row r -> dh[r, :] ; D3 / D4 lanes p < P are summed over tiles in registers and leave
+//   as one atomic per entry per CTA.
+//
+// Why bf16 levels and not TF32: the backward GEMMs contract over the ROWS of the tile, i.e. they need the
+// dt and h tiles transposed.  With the no-swizzle canonical layout (8 x 16-byte core matrices) an
+// X[128][C] tile written K-major is, byte for byte, X^T in the MN-major layout -- but tcgen05 reads
+// MN-major TF32 operands only in the 128B/32B-swizzled layout (measured: tools/umma_probe.cu returns
+// zeros otherwise), which no K-major layout matches.  16-bit operands have no such restriction.  An fp32
+// value is EXACTLY x0 + x1 + x2 with three truncated bf16 levels (8 + 8 + 8 significand bits); products
+// of levels i + j <= 2 carry everything above 2^-24 relative, and K = 16 per instruction halves the
+// instruction count.
+#pragma once
+#include <cstdint>
+
+#include "nfn_dense_chain.cuh"
+
+namespace nfn {
+namespace tc5 {
+
+constexpr int kRows = 128;  // rows per tile == threads per CTA == TMEM lanes
+__host__ __device__ constexpr int round16(int x) { return (x + 15) / 16 * 16; }
+__host__ __device__ constexpr unsigned pow2_cols(int c) { return c <= 32 ? 32u : c <= 64 ? 64u : c <= 128 ? 128u : c <= 256 ? 256u : 512u; }
+
+// byte offset of element (row, col) in a K-major no-swizzle bf16 operand tile with C columns:
+// 8-row x 16-byte core matrices, the C/8 matrices of one 8-row group contiguous
+__host__ __device__ constexpr unsigned tile_off(int row, int col, int C) {
+  return (unsigned)((row >> 3) * (C / 8 * 128) + (col >> 3) * 128 + (row & 7) * 16 + (col & 7) * 2);
+}
+
+// shared-memory carve-up (bytes); every tile is 128-byte aligned
+template <int P, int H, bool BWD>
+struct Geo {
+  static constexpr int PN = round16(P);            // parameter columns padded to the MMA N / K granule
+  static constexpr int S = row_stride(P);          // t / dt row stride (floats) of the per-row flow tile
+  static constexpr unsigned kTT = kRows * S * 4;
+  // h tile: per 8-row group [level 0 | level 1 | level 2 | ones] x (H/8 chunks each, 2 for the ones block), so
+  // that read MN-major it is ONE operand [h0 | h1 | h2 | 1 0 ..] with N = 3H + 16 columns (GEMM 3 + bias
+  // gradient in one pass), and read K-major level i is the tile at byte offset i * kLvlA (GEMM 1)
+  static constexpr unsigned kLvlA = H / 8 * 128;                   // bytes of one level inside a group
+  static constexpr unsigned kGrpA = 3 * kLvlA + 256;               // bytes of one 8-row group
+  static constexpr unsigned kA = kRows / 8 * kGrpA;
+  static constexpr int NB3 = 3 * H + 16;                           // N of GEMM 3
+  static constexpr unsigned kD = kRows * PN * 2;   // one bf16 level of the dt tile
+  static constexpr unsigned kW = PN * H * 2;       // one level of W, either orientation
+  static constexpr unsigned oTT = 0;
+  static constexpr unsigned oA = (oTT + kTT + 127) / 128 * 128;
+  static constexpr unsigned oD = oA + kA;                          // 3 levels (BWD)
+  static constexpr unsigned oW1 = oD + (BWD ? 3 * kD : 0);         // W as [N = PN][K = H], 3 levels
+  // W as [N = H][K = PN], 3 levels back to back == ONE operand [W0; W1; W2] with N = 3H rows (GEMM 2)
+  static constexpr unsigned oW2 = oW1 + 3 * kW;
+  static constexpr unsigned oBias = oW2 + (BWD ? 3 * kW : 0);
+  static constexpr unsigned oBar = (oBias + PN * 4 + 15) / 16 * 16;  // 2 mbarriers + tmem base
+  static constexpr unsigned kBytes = oBar + 32;
+  // MN-major reads of the dt tiles with M = 128 run (16 - PN/8) chunks past the tile: what follows must be ours
+  static_assert(!BWD || 6 * kW >= (16 - PN / 8) * 128, "operand over-read must stay in the CTA's smem");
+  // TMEM columns: D1 [PN] | D2 [3H: dt W0^T | dt W1^T | dt W2^T] | D3 [3H + 16: dt^T h0 | dt^T h1 | dt^T h2 | db ..]
+  static constexpr int cD1 = 0, cD2 = PN, cD3 = PN + 3 * H;
+  static constexpr unsigned kCols = pow2_cols(BWD ? PN + 3 * H + NB3 : PN);
+  static_assert(3 * H <= 256 && NB3 <= 256, "MMA N limit");
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+NFN_DEVI void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+NFN_DEVI void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+NFN_DEVI void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+NFN_DEVI void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+NFN_DEVI void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+NFN_DEVI bool mbar_try_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded (2 s): a tensor-core op that never completes must not hang the GPU (the launch fails instead)
+NFN_DEVI void mbar_wait(unsigned bar, unsigned parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+      if (mbar_try_wait(bar, parity)) return;
+    }
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 2000000000ull) __trap();
+  }
+}
+NFN_DEVI void tmem_alloc(unsigned smem_dst, unsigned cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+NFN_DEVI void tmem_dealloc(unsigned taddr, unsigned cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// shared-memory matrix descriptor, no swizzle, sm_100 version field set.
+//   K-major : lbo = bytes between the two 16-byte K chunks of one instruction, sbo = between 8-row groups
+//   MN-major: lbo = bytes between 8-deep K groups,                           sbo = between 8-wide MN chunks
+// (measured with tools/umma_probe.cu)
+NFN_DEVI uint64_t smem_desc(unsigned saddr, unsigned lbo_bytes, unsigned sbo_bytes) {
+  return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor, kind::f16 with bf16 operands, fp32 accumulate
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+NFN_DEVI void mma_bf16(unsigned d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+NFN_DEVI void mma_commit(unsigned bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 16 consecutive columns of this thread's TMEM lane
+NFN_DEVI void tmem_ld16(unsigned taddr, unsigned (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+NFN_DEVI void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// N columns (multiple of 16) of this thread's lane -> floats; the values are pinned behind the wait
+template <int N>
+NFN_DEVI void tmem_load_row(unsigned taddr, float (&out)[N]) {
+  static_assert(N % 16 == 0, "16-column granules");
+  unsigned r[N / 16][16];
+#pragma unroll
+  for (int i = 0; i < N / 16; ++i) tmem_ld16(taddr + 16u * i, r[i]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < N / 16; ++i)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      asm volatile("" : "+r"(r[i][j]));  // a use the compiler cannot hoist above the wait
+      out[16 * i + j] = __uint_as_float(r[i][j]);
+    }
+}
+NFN_DEVI void sts_u4(unsigned saddr, unsigned a, unsigned b, unsigned c, unsigned d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+NFN_DEVI void sts_u16(unsigned saddr, unsigned v) {
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(saddr), "h"((unsigned short)v) : "memory");
+}
+
+// ---- exact three-level bf16 split of an fp32 value: x = x0 + x1 + x2, every level a truncated bf16
+// (8 significand bits each; the third remainder has at most 8 bits left, so nothing is lost)
+struct Bf3 {
+  unsigned b0, b1, b2;  // fp32 bit patterns whose low 16 bits are zero
+};
+NFN_DEVI Bf3 split_bf3(float x) {
+  Bf3 s;
+  s.b0 = __float_as_uint(x) & 0xffff0000u;
+  const float r1 = x - __uint_as_float(s.b0);
+  s.b1 = __float_as_uint(r1) & 0xffff0000u;
+  s.b2 = __float_as_uint(r1 - __uint_as_float(s.b1)) & 0xffff0000u;
+  return s;
+}
+// two bf16 (high halves of two fp32 patterns) -> one 32-bit word, element `even` at the lower address
+NFN_DEVI unsigned pack_bf(unsigned even, unsigned odd) { return __byte_perm(even, odd, 0x7632); }
+
+// 8 consecutive fp32 values -> one 16-byte chunk in each of the three level tiles
+NFN_DEVI void store_levels8(unsigned saddr, unsigned level_stride, const float* v) {
+  unsigned w0[4], w1[4], w2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const Bf3 e = split_bf3(v[2 * j]), o = split_bf3(v[2 * j + 1]);
+    w0[j] = pack_bf(e.b0, o.b0);
+    w1[j] = pack_bf(e.b1, o.b1);
+    w2[j] = pack_bf(e.b2, o.b2);
+  }
+  sts_u4(saddr, w0[0], w0[1], w0[2], w0[3]);
+  sts_u4(saddr + level_stride, w1[0], w1[1], w1[2], w1[3]);
+  sts_u4(saddr + 2 * level_stride, w2[0], w2[1], w2[2], w2[3]);
+}
+
+// level pairs (i, j) of a split product, smallest contribution first.  All nine reproduce the fp32
+// product exactly; the six with i + j <= 2 carry everything above 2^-24 relative.
+__device__ constexpr int kPairs9[9][2] = {{2, 2}, {1, 2}, {2, 1}, {0, 2}, {2, 0}, {1, 1}, {0, 1}, {1, 0}, {0, 0}};
+
+// ------------------------------------------------------------------ the fused body
+template <class Spec, int H, bool BWD, class M>
+NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
+  constexpr int D = Spec::D;
+  constexpr int P = Spec::P();
+  static_assert(P > 0 && P <= 128, "1..128 parameter columns");
+  static_assert(H % 16 == 0 && H >= 16 && H <= 64, "hidden width must be 16, 32, 48 or 64");
+  using G = Geo<P, H, BWD>;
+  constexpr int PN = G::PN, S = G::S, T = kRows;
+  constexpr int V = row_vec(P);
+  constexpr unsigned kGrpA = G::kGrpA;       // bytes between 8-row groups of the h tile
+  constexpr unsigned kGrpW1 = H / 8 * 128;   // ... of a W1 level tile (H columns)
+  constexpr unsigned kGrpD = PN / 8 * 128;   // ... of a tile with PN columns
+  constexpr uint32_t kI1 = instr_desc(128, PN, 0, 0);
+  constexpr uint32_t kI2 = instr_desc(128, 3 * H, 0, 0);
+  constexpr uint32_t kI3 = instr_desc(128, G::NB3, 1, 1);
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double red[T / 32];
+  const unsigned sbase = smem_u32(smem_raw);
+  float* tT = reinterpret_cast<float*>(smem_raw + G::oTT);
+  const float* sBias = reinterpret_cast<const float*>(smem_raw + G::oBias);
+  const unsigned bar1 = sbase + G::oBar, bar2 = bar1 + 8, tmem_slot = bar1 + 16;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const long long ntiles = (a.B + T - 1) / T;
+
+  // ---- one-time set-up: barriers, TMEM, split weight tiles, bias, ones tile
+  if (tid == 0) {
+    mbar_init(bar1, 1);
+    mbar_init(bar2, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, G::kCols);
+  for (int i = tid; i < PN * H; i += T) {   // W1[n][k] = W[k][n]
+    const int n = i / H, k = i % H;
+    const Bf3 w = split_bf3((n < P) ? __ldg(a.W + k * P + n) : 0.0f);
+    const unsigned o = sbase + G::oW1 + tile_off(n, k, H);
+    sts_u16(o, w.b0 >> 16);
+    sts_u16(o + G::kW, w.b1 >> 16);
+    sts_u16(o + 2 * G::kW, w.b2 >> 16);
+  }
+  for (int i = tid; i < PN; i += T) reinterpret_cast<float*>(smem_raw + G::oBias)[i] = (i < P) ? __ldg(a.bias + i) : 0.0f;
+  if constexpr (BWD) {
+    for (int i = tid; i < H * PN; i += T) {  // W2[n][k] = W[n][k]
+      const int n = i / PN, k = i % PN;
+      const Bf3 w = split_bf3((k < P) ? __ldg(a.W + n * P + k) : 0.0f);
+      const unsigned o = sbase + G::oW2 + tile_off(n, k, PN);
+      sts_u16(o, w.b0 >> 16);
+      sts_u16(o + G::kW, w.b1 >> 16);
+      sts_u16(o + 2 * G::kW, w.b2 >> 16);
+    }
+    // ones block of the h tile (written once): per row 16 bf16, the first one is 1.0
+    for (int i = tid; i < T * 16; i += T) {
+      const int r = i / 16, k = i % 16;
+      sts_u16(sbase + G::oA + (r >> 3) * kGrpA + 3 * G::kLvlA + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2, k == 0 ? 0x3f80u : 0u);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  unsigned tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  const unsigned lane_base = tmem_base + ((unsigned)(warp * 32) << 16);
+
+  // this thread's row of the next tile: h (registers), y, upstream cotangent
+  float h_nxt[H];
+  float y_nxt[D];
+  float g_nxt = 1.0f;
+  auto fetch = [&](long long tile) {
+    const long long r = tile * T + tid;
+#pragma unroll
+    for (int i = 0; i < H; ++i) h_nxt[i] = 0.0f;
+    if (tile < ntiles && r < a.B) {
+      const float4* src = reinterpret_cast<const float4*>(a.h + r * H);
+#pragma unroll
+      for (int c = 0; c < H / 4; ++c) {
+        const float4 v = __ldg(src + c);
+        h_nxt[4 * c] = v.x; h_nxt[4 * c + 1] = v.y; h_nxt[4 * c + 2] = v.z; h_nxt[4 * c + 3] = v.w;
+      }
+      load_event<D>(a.y, a.y_broadcast ? 0 : r, y_nxt);
+      if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + r); }
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < D; ++i) y_nxt[i] = 0.0f;
+  long long tile = blockIdx.x;
+  fetch(tile);
+
+  const unsigned a_row = sbase + G::oA + (tid >> 3) * kGrpA + (tid & 7) * 16;  // this thread's row in the h tile
+  const unsigned d_row = sbase + G::oD + tile_off(tid, 0, PN);   // ... in the dt level tiles
+  // operand descriptors of level 0 / k-step 0; the others differ by a constant in the address field
+  const uint64_t dA_k = smem_desc(sbase + G::oA, 128, kGrpA);     // h tile, one level K-major (GEMM 1)
+  const uint64_t dA_mn = smem_desc(sbase + G::oA, kGrpA, 128);    // h tile, all levels + ones MN-major (GEMM 3)
+  const uint64_t dW1 = smem_desc(sbase + G::oW1, 128, kGrpW1);
+  const uint64_t dD_k = smem_desc(sbase + G::oD, 128, kGrpD);     // dt level tiles, K-major (GEMM 2)
+  const uint64_t dD_mn = smem_desc(sbase + G::oD, kGrpD, 128);    // dt level tiles, MN-major (GEMM 3)
+  const uint64_t dW2 = smem_desc(sbase + G::oW2, 128, kGrpD);     // [W0; W1; W2], N = 3H
+  double lsum = 0.0;
+  float dw_acc[H], db_acc = 0.0f;  // lanes p < P: dW[:, p] and db[p] summed over this CTA's tiles
+#pragma unroll
+  for (int k = 0; k < H; ++k) dw_acc[k] = 0.0f;
+  unsigned it = 0;  // tiles done by this CTA: mbarrier phase parity
+
+  for (; tile < ntiles; tile += gridDim.x, ++it) {
+    float z[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) z[i] = y_nxt[i];
+    const float g_cur = g_nxt;
+
+    // ---- split h row -> three level tiles (the previous tile's GEMM 3 has completed: bar2 was waited on)
+#pragma unroll
+    for (int c = 0; c < H / 8; ++c) store_levels8(a_row + c * 128, G::kLvlA, h_nxt + 8 * c);
+    fetch(tile + gridDim.x);   // next tile's row: its latency hides behind this tile
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- GEMM 1 (one thread issues): the six level products with i + j <= 2, smallest first
+    if (tid == 0) {
+      tc_fence_after();
+      unsigned acc = 0;
+#pragma unroll
+      for (int q = 3; q < 9; ++q) {
+#pragma unroll
+        for (int ks = 0; ks < H / 16; ++ks) {
+          const uint64_t ad = dA_k + (uint64_t)((kPairs9[q][0] * G::kLvlA + ks * 256) >> 4);
+          const uint64_t bd = dW1 + (uint64_t)((kPairs9[q][1] * G::kW + ks * 256) >> 4);
+          mma_bf16(tmem_base + G::cD1, ad, bd, kI1, acc);
+          acc = 1;
+        }
+      }
+      mma_commit(bar1);
+    }
+    mbar_wait(bar1, it & 1);
+    tc_fence_after();
+
+    // ---- t row out of TMEM (+ bias) into this thread's row of the flow tile
+    float* row = tT + tid * S;
+    {
+      float tv[PN];
+      tmem_load_row<PN>(lane_base + G::cD1, tv);
+#pragma unroll
+      for (int j = 0; j < P; ++j) tv[j] += sBias[j];
+      Span<0, P, V>::store(row, tv);
+    }
+
+    // ---- per-row flow chain (registers), dt written in place over t
+    const long long r = tile * T + tid;
+    if (r < a.B) {
+      float zs[Spec::KA][D];
+      LogDetAcc<M> ld;
+      FwdSweep<Spec, M, V, BWD, 0>::run(row, z, zs, ld);
+      using Base = BaseDist<D, Spec::BASE, M>;
+      float bth[Base::NA];
+      if constexpr (Spec::BASE) Span<0, 2 * D, V>::load(row, bth);
+      const float lp = (BWD ? Base::log_prob_save(bth, z) : Base::log_prob(bth, z)) + ld.nat();
+      a.logp[r] = lp;
+      lsum += (double)lp;
+      if constexpr (BWD) {
+        const float cot = a.g_scale * g_cur;
+        float Gz[D];
+        float gb[Base::NA];
+        Base::bwd_saved(bth, z, cot, Gz, gb);
+        if constexpr (Spec::BASE) Span<0, 2 * D, V>::store(row, gb);
+        BwdSweep<Spec, M, V, Spec::K - 1>::run(row, zs, Gz, cot);
+      }
+    }
+
+    if constexpr (BWD) {
+      // ---- split dt row -> three level tiles (rows past B and the pad columns are zero)
+      {
+        float dv[PN];
+#pragma unroll
+        for (int j = 0; j < PN; ++j) dv[j] = 0.0f;
+        if (r < a.B) Span<0, P, V>::load(row, dv);
+#pragma unroll
+        for (int c = 0; c < PN / 8; ++c) store_levels8(d_row + c * 128, G::kD, dv + 8 * c);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+
+      if (tid == 0) {
+        tc_fence_after();
+        // GEMM 2: [dt W0^T | dt W1^T | dt W2^T] = dt_i [W0; W1; W2]^T, dt levels smallest first (all 9 products)
+        {
+          unsigned acc = 0;
+#pragma unroll
+          for (int lv = 2; lv >= 0; --lv) {
+#pragma unroll
+            for (int ks = 0; ks < PN / 16; ++ks) {
+              mma_bf16(tmem_base + G::cD2, dD_k + (uint64_t)((lv * G::kD + ks * 256) >> 4), dW2 + (uint64_t)((ks * 256) >> 4),
+                       kI2, acc);
+              acc = 1;
+            }
+          }
+        }
+        // GEMM 3: [dt^T h0 | dt^T h1 | dt^T h2 | dt^T 1 ..] over the tile's 128 rows, 16 rows (two 8-row
+        // groups) per instruction: dW^T and the bias gradient in one pass
+        {
+          unsigned acc = 0;
+#pragma unroll
+          for (int lv = 2; lv >= 0; --lv) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              mma_bf16(tmem_base + G::cD3, dD_mn + (uint64_t)((lv * G::kD + ks * 2 * kGrpD) >> 4),
+                       dA_mn + (uint64_t)((ks * 2 * kGrpA) >> 4), kI3, acc);
+              acc = 1;
+            }
+          }
+        }
+        mma_commit(bar2);
+      }
+      mbar_wait(bar2, it & 1);
+      tc_fence_after();
+
+      // ---- dh row out of TMEM (sum of the three W-level blocks, smallest first) -> global
+      {
+        float hv[3 * H];
+        tmem_load_row<3 * H>(lane_base + G::cD2, hv);
+        if (r < a.B) {
+#pragma unroll
+          for (int c = 0; c < H / 4; ++c) {
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = (hv[2 * H + 4 * c + j] + hv[H + 4 * c + j]) + hv[4 * c + j];
+            st_stream_f4(a.dh + r * H + 4 * c, make_float4(o[0], o[1], o[2], o[3]));
+          }
+        }
+      }
+      // ---- this tile's dW / db lanes (TMEM lane p < P) -> register accumulators; warps past P skip
+      if (warp * 32 < P) {
+        float wv[G::NB3];
+        tmem_load_row<G::NB3>(lane_base + G::cD3, wv);
+#pragma unroll
+        for (int k = 0; k < H; ++k) dw_acc[k] += (wv[2 * H + k] + wv[H + k]) + wv[k];
+        db_acc += wv[3 * H];
+      }
+    }
+  }
+
+  if (a.logp_sum) {
+    const double sblk = block_sum<T>(lsum, red);
+    if (tid == 0) atomicAdd(a.logp_sum, sblk);
+  }
+  if constexpr (BWD) {
+    if (tid < P) {   // TMEM lane p holds dW[:, p] and db[p]
+#pragma unroll
+      for (int k = 0; k < H; ++k) atomicAdd(a.dW + k * P + tid, dw_acc[k]);
+      atomicAdd(a.dbias + tid, db_acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, G::kCols);
+}
+
+template <class Spec, int H, bool BWD, class M, int MINB>
+__global__ void __launch_bounds__(kRows, MINB) dense_tc5_kernel(const DenseArgs a) {
+  dense_tc5_body<Spec, H, BWD, M>(a);
+}
+
+}  // namespace tc5
+}  // namespace nfn
