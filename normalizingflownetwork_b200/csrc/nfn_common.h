@@ -155,11 +155,16 @@ cudaError_t launch_dense(const DenseArgs& a, cudaStream_t st) {
 template <class Spec, int H, bool BWD, class M>
 cudaError_t launch_dense_tc5(const DenseArgs& a, cudaStream_t st) {
   using G = tc5::Geo<Spec::P(), H, BWD>;
-  constexpr int T = tc5::kRows;
+  constexpr int T = tc5::kRows;          // rows per tile
+  constexpr int NT = tc5::kThreads;      // threads per CTA
   constexpr unsigned kSmem = G::kBytes;
   constexpr int kBySmem = (int)((227u * 1024u) / (kSmem + 1024u));
   constexpr int kByTmem = (int)(512u / G::kCols);
-  constexpr int kWant = 4;
+#ifdef NFN_TUNE_TC5_MINB
+  constexpr int kWant = NFN_TUNE_TC5_MINB;
+#else
+  constexpr int kWant = BWD ? 2 : 3;   // compute warpgroup registers: 216 (BWD), 136 (forward)
+#endif
   constexpr int kCap = kBySmem < kByTmem ? kBySmem : kByTmem;
   constexpr int MINB = kCap < 1 ? 1 : (kCap < kWant ? kCap : kWant);
   auto kern = tc5::dense_tc5_kernel<Spec, H, BWD, M, MINB>;
@@ -173,7 +178,7 @@ cudaError_t launch_dense_tc5(const DenseArgs& a, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, kSmem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, kSmem);
     if (e != cudaSuccess) return e;
     // never more resident CTAs than TMEM allocations that fit (a CTA would spin in tcgen05.alloc)
     if (occ > kByTmem) occ = kByTmem;
@@ -183,7 +188,7 @@ cudaError_t launch_dense_tc5(const DenseArgs& a, cudaStream_t st) {
   const long long ntiles = (a.B + T - 1) / T;
   long long grid = (long long)di.sm_count * cfg.ctas_per_sm;
   if (grid > ntiles) grid = ntiles;
-  kern<<<(unsigned)grid, T, kSmem, st>>>(a);
+  kern<<<(unsigned)grid, NT, kSmem, st>>>(a);
   count_launch();
   return cudaGetLastError();
 }

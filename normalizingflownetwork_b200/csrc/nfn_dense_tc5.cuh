@@ -32,7 +32,16 @@
 namespace nfn {
 namespace tc5 {
 
-constexpr int kRows = 128;  // rows per tile == threads per CTA == TMEM lanes
+constexpr int kRows = 128;     // rows per tile == compute threads per CTA == TMEM lanes
+// + a second warpgroup whose first lane issues every tcgen05.mma.  A whole warpgroup because registers
+// are handed out per warpgroup: it gives its registers back (setmaxnreg) and the compute warpgroup takes them.
+constexpr int kThreads = 256;
+// Register budget for MINB resident CTAs: the launch-time allocation is 65536 / (MINB * 256) per thread
+// (rounded down to 8); the issuing warpgroup keeps kIssuer of it and the compute warpgroup gets the rest.
+// The sum must never exceed the CTA's pool, or setmaxnreg.inc would wait forever.
+__host__ __device__ constexpr int regs_launch(int minb) { return 65536 / (minb * kThreads) / 8 * 8; }
+__host__ __device__ constexpr int regs_issuer(int minb) { return minb <= 2 ? 56 : 32; }
+__host__ __device__ constexpr int regs_compute(int minb) { return 2 * regs_launch(minb) - regs_issuer(minb); }
 __host__ __device__ constexpr int round16(int x) { return (x + 15) / 16 * 16; }
 __host__ __device__ constexpr unsigned pow2_cols(int c) { return c <= 32 ? 32u : c <= 64 ? 64u : c <= 128 ? 128u : c <= 256 ? 256u : 512u; }
 
@@ -46,8 +55,6 @@ __host__ __device__ constexpr unsigned tile_off(int row, int col, int C) {
 template <int P, int H, bool BWD>
 struct Geo {
   static constexpr int PN = round16(P);            // parameter columns padded to the MMA N / K granule
-  static constexpr int S = row_stride(P);          // t / dt row stride (floats) of the per-row flow tile
-  static constexpr unsigned kTT = kRows * S * 4;
   // h tile: per 8-row group [level 0 | level 1 | level 2 | ones] x (H/8 chunks each, 2 for the ones block), so
   // that read MN-major it is ONE operand [h0 | h1 | h2 | 1 0 ..] with N = 3H + 16 columns (GEMM 3 + bias
   // gradient in one pass), and read K-major level i is the tile at byte offset i * kLvlA (GEMM 1)
@@ -57,20 +64,21 @@ struct Geo {
   static constexpr int NB3 = 3 * H + 16;                           // N of GEMM 3
   static constexpr unsigned kD = kRows * PN * 2;   // one bf16 level of the dt tile
   static constexpr unsigned kW = PN * H * 2;       // one level of W, either orientation
-  static constexpr unsigned oTT = 0;
-  static constexpr unsigned oA = (oTT + kTT + 127) / 128 * 128;
-  static constexpr unsigned oD = oA + kA;                          // 3 levels (BWD)
+  // BWD keeps TWO h tiles: GEMM 3 of tile i still reads h(i) while h(i+1) is split for GEMM 1 of tile i+1
+  static constexpr int NA = BWD ? 2 : 1;
+  static constexpr unsigned oA = 0;
+  static constexpr unsigned oD = oA + NA * kA;                     // 3 levels (BWD)
   static constexpr unsigned oW1 = oD + (BWD ? 3 * kD : 0);         // W as [N = PN][K = H], 3 levels
   // W as [N = H][K = PN], 3 levels back to back == ONE operand [W0; W1; W2] with N = 3H rows (GEMM 2)
   static constexpr unsigned oW2 = oW1 + 3 * kW;
   static constexpr unsigned oBias = oW2 + (BWD ? 3 * kW : 0);
-  static constexpr unsigned oBar = (oBias + PN * 4 + 15) / 16 * 16;  // 2 mbarriers + tmem base
-  static constexpr unsigned kBytes = oBar + 32;
+  static constexpr unsigned oBar = (oBias + PN * 4 + 15) / 16 * 16;  // 4 mbarriers + tmem base
+  static constexpr unsigned kBytes = oBar + 48;
   // MN-major reads of the dt tiles with M = 128 run (16 - PN/8) chunks past the tile: what follows must be ours
   static_assert(!BWD || 6 * kW >= (16 - PN / 8) * 128, "operand over-read must stay in the CTA's smem");
   // TMEM columns: D1 [PN] | D2 [3H: dt W0^T | dt W1^T | dt W2^T] | D3 [3H + 16: dt^T h0 | dt^T h1 | dt^T h2 | db ..]
   static constexpr int cD1 = 0, cD2 = PN, cD3 = PN + 3 * H;
-  static constexpr unsigned kCols = pow2_cols(BWD ? PN + 3 * H + NB3 : PN);
+  static constexpr unsigned kCols = pow2_cols(BWD ? cD3 + NB3 : PN);
   static_assert(3 * H <= 256 && NB3 <= 256, "MMA N limit");
 };
 
@@ -107,6 +115,9 @@ NFN_DEVI void mbar_wait(unsigned bar, unsigned parity) {
     if (t1 - t0 > 2000000000ull) __trap();
   }
 }
+NFN_DEVI void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 NFN_DEVI void tmem_alloc(unsigned smem_dst, unsigned cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -134,6 +145,12 @@ NFN_DEVI void mma_bf16(unsigned d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// one lane of a converged warp
+NFN_DEVI bool elect_one() {
+  unsigned p;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(p));
+  return p != 0;
 }
 NFN_DEVI void mma_commit(unsigned bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -207,15 +224,20 @@ NFN_DEVI void store_levels8(unsigned saddr, unsigned level_stride, const float* 
 __device__ constexpr int kPairs9[9][2] = {{2, 2}, {1, 2}, {2, 1}, {0, 2}, {2, 0}, {1, 1}, {0, 1}, {1, 0}, {0, 0}};
 
 // ------------------------------------------------------------------ the fused body
-template <class Spec, int H, bool BWD, class M>
+template <class Spec, int H, bool BWD, class M, int MINB>
 NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
+  constexpr int kRegsIssuer = regs_issuer(MINB), kRegsCompute = regs_compute(MINB);
+  static_assert(kRows * (kRegsIssuer + kRegsCompute) <= kThreads * regs_launch(MINB), "register pool");
+  static_assert(kRegsCompute <= 232 && kRegsCompute % 8 == 0 && kRegsIssuer % 8 == 0, "setmaxnreg range");
   constexpr int D = Spec::D;
   constexpr int P = Spec::P();
   static_assert(P > 0 && P <= 128, "1..128 parameter columns");
   static_assert(H % 16 == 0 && H >= 16 && H <= 64, "hidden width must be 16, 32, 48 or 64");
   using G = Geo<P, H, BWD>;
-  constexpr int PN = G::PN, S = G::S, T = kRows;
-  constexpr int V = row_vec(P);
+  constexpr int PN = G::PN, T = kRows, NT = kThreads;
+  // the parameter row lives in REGISTERS (straight out of TMEM): every access of the flow code is a
+  // compile-time index, scalar "vector width" 1 keeps it that way
+  constexpr int V = 1;
   constexpr unsigned kGrpA = G::kGrpA;       // bytes between 8-row groups of the h tile
   constexpr unsigned kGrpW1 = H / 8 * 128;   // ... of a W1 level tile (H columns)
   constexpr unsigned kGrpD = PN / 8 * 128;   // ... of a tile with PN columns
@@ -224,11 +246,12 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
   constexpr uint32_t kI3 = instr_desc(128, G::NB3, 1, 1);
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ double red[T / 32];
+  __shared__ double red[NT / 32];
   const unsigned sbase = smem_u32(smem_raw);
-  float* tT = reinterpret_cast<float*>(smem_raw + G::oTT);
   const float* sBias = reinterpret_cast<const float*>(smem_raw + G::oBias);
-  const unsigned bar1 = sbase + G::oBar, bar2 = bar1 + 8, tmem_slot = bar1 + 16;
+  // bar1 / bar2: tensor pipe -> compute threads (GEMM 1 done / GEMM 2+3 done);
+  // bar_h / bar_d: compute threads -> issuing thread (h tile written and D1 consumed / dt tiles written and D2, D3 drained)
+  const unsigned bar1 = sbase + G::oBar, bar2 = bar1 + 8, bar_h = bar1 + 16, bar_d = bar1 + 24, tmem_slot = bar1 + 32;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const long long ntiles = (a.B + T - 1) / T;
@@ -237,10 +260,12 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
   if (tid == 0) {
     mbar_init(bar1, 1);
     mbar_init(bar2, 1);
+    mbar_init(bar_h, T);
+    mbar_init(bar_d, T);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, G::kCols);
-  for (int i = tid; i < PN * H; i += T) {   // W1[n][k] = W[k][n]
+  for (int i = tid; i < PN * H; i += NT) {   // W1[n][k] = W[k][n]
     const int n = i / H, k = i % H;
     const Bf3 w = split_bf3((n < P) ? __ldg(a.W + k * P + n) : 0.0f);
     const unsigned o = sbase + G::oW1 + tile_off(n, k, H);
@@ -248,9 +273,9 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
     sts_u16(o + G::kW, w.b1 >> 16);
     sts_u16(o + 2 * G::kW, w.b2 >> 16);
   }
-  for (int i = tid; i < PN; i += T) reinterpret_cast<float*>(smem_raw + G::oBias)[i] = (i < P) ? __ldg(a.bias + i) : 0.0f;
+  for (int i = tid; i < PN; i += NT) reinterpret_cast<float*>(smem_raw + G::oBias)[i] = (i < P) ? __ldg(a.bias + i) : 0.0f;
   if constexpr (BWD) {
-    for (int i = tid; i < H * PN; i += T) {  // W2[n][k] = W[n][k]
+    for (int i = tid; i < H * PN; i += NT) {  // W2[n][k] = W[n][k]
       const int n = i / PN, k = i % PN;
       const Bf3 w = split_bf3((k < P) ? __ldg(a.W + n * P + k) : 0.0f);
       const unsigned o = sbase + G::oW2 + tile_off(n, k, PN);
@@ -259,9 +284,10 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
       sts_u16(o + 2 * G::kW, w.b2 >> 16);
     }
     // ones block of the h tile (written once): per row 16 bf16, the first one is 1.0
-    for (int i = tid; i < T * 16; i += T) {
-      const int r = i / 16, k = i % 16;
-      sts_u16(sbase + G::oA + (r >> 3) * kGrpA + 3 * G::kLvlA + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2, k == 0 ? 0x3f80u : 0u);
+    for (int i = tid; i < G::NA * T * 16; i += NT) {
+      const int b = i / (T * 16), r = (i / 16) % T, k = i % 16;
+      sts_u16(sbase + G::oA + b * G::kA + (r >> 3) * kGrpA + 3 * G::kLvlA + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2,
+              k == 0 ? 0x3f80u : 0u);
     }
   }
   fence_proxy_async();
@@ -270,6 +296,7 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
   tc_fence_after();
   unsigned tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);   // the same value in every lane: say so
   const unsigned lane_base = tmem_base + ((unsigned)(warp * 32) << 16);
 
   // this thread's row of the next tile: h (registers), y, upstream cotangent
@@ -305,102 +332,91 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
   const uint64_t dD_k = smem_desc(sbase + G::oD, 128, kGrpD);     // dt level tiles, K-major (GEMM 2)
   const uint64_t dD_mn = smem_desc(sbase + G::oD, kGrpD, 128);    // dt level tiles, MN-major (GEMM 3)
   const uint64_t dW2 = smem_desc(sbase + G::oW2, 128, kGrpD);     // [W0; W1; W2], N = 3H
-  double lsum = 0.0;
+  float ls_hi = 0.0f, ls_lo = 0.0f;   // this thread's sum of logp (compensated)
   float dw_acc[H], db_acc = 0.0f;  // lanes p < P: dW[:, p] and db[p] summed over this CTA's tiles
 #pragma unroll
   for (int k = 0; k < H; ++k) dw_acc[k] = 0.0f;
-  unsigned it = 0;  // tiles done by this CTA: mbarrier phase parity
 
-  for (; tile < ntiles; tile += gridDim.x, ++it) {
-    float z[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) z[i] = y_nxt[i];
-    const float g_cur = g_nxt;
-
-    // ---- split h row -> three level tiles (the previous tile's GEMM 3 has completed: bar2 was waited on)
-#pragma unroll
-    for (int c = 0; c < H / 8; ++c) store_levels8(a_row + c * 128, G::kLvlA, h_nxt + 8 * c);
-    fetch(tile + gridDim.x);   // next tile's row: its latency hides behind this tile
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-
-    // ---- GEMM 1 (one thread issues): the six level products with i + j <= 2, smallest first
-    if (tid == 0) {
-      tc_fence_after();
-      unsigned acc = 0;
-#pragma unroll
-      for (int q = 3; q < 9; ++q) {
-#pragma unroll
-        for (int ks = 0; ks < H / 16; ++ks) {
-          const uint64_t ad = dA_k + (uint64_t)((kPairs9[q][0] * G::kLvlA + ks * 256) >> 4);
-          const uint64_t bd = dW1 + (uint64_t)((kPairs9[q][1] * G::kW + ks * 256) >> 4);
-          mma_bf16(tmem_base + G::cD1, ad, bd, kI1, acc);
-          acc = 1;
-        }
-      }
-      mma_commit(bar1);
-    }
-    mbar_wait(bar1, it & 1);
+  // one thread issues; GEMM 1 of a tile reads h tile `buf`
+  // The issuing code runs warp-converged on warp-uniform values (so the operand descriptors live in
+  // uniform registers) and only the tcgen05 instructions themselves are predicated on one elected lane.
+  auto issue_gemm1 = [&](int buf, bool leader) {
     tc_fence_after();
-
-    // ---- t row out of TMEM (+ bias) into this thread's row of the flow tile
-    float* row = tT + tid * S;
-    {
-      float tv[PN];
-      tmem_load_row<PN>(lane_base + G::cD1, tv);
+    unsigned acc = 0;
 #pragma unroll
-      for (int j = 0; j < P; ++j) tv[j] += sBias[j];
-      Span<0, P, V>::store(row, tv);
+    for (int q = 3; q < 9; ++q) {   // the six level products with i + j <= 2, smallest first
+#pragma unroll
+      for (int ks = 0; ks < H / 16; ++ks) {
+        const uint64_t ad = dA_k + (uint64_t)((buf * G::kA + kPairs9[q][0] * G::kLvlA + ks * 256) >> 4);
+        const uint64_t bd = dW1 + (uint64_t)((kPairs9[q][1] * G::kW + ks * 256) >> 4);
+        if (leader) mma_bf16(tmem_base + G::cD1, ad, bd, kI1, acc);
+        acc = 1;
+      }
     }
+    if (leader) mma_commit(bar1);
+    __syncwarp();
+  };
+  auto split_h = [&](int buf) {
+#pragma unroll
+    for (int c = 0; c < H / 8; ++c) store_levels8(a_row + buf * G::kA + c * 128, G::kLvlA, h_nxt + 8 * c);
+  };
+  // dh row of a finished tile out of TMEM (sum of the three W-level blocks, smallest first) -> global,
+  // and that tile's dW / db lanes (TMEM lane p < P) -> register accumulators; warps past P skip the latter
+  auto drain_backward = [&](long long r_done) {
+    float hv[3 * H];
+    tmem_load_row<3 * H>(lane_base + G::cD2, hv);
+    if (r_done < a.B) {
+#pragma unroll
+      for (int c = 0; c < H / 4; ++c) {
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = (hv[2 * H + 4 * c + j] + hv[H + 4 * c + j]) + hv[4 * c + j];
+        st_stream_f4(a.dh + r_done * H + 4 * c, make_float4(o[0], o[1], o[2], o[3]));
+      }
+    }
+    if (warp * 32 < P) {
+      float wv[G::NB3];
+      tmem_load_row<G::NB3>(lane_base + G::cD3, wv);
+#pragma unroll
+      for (int k = 0; k < H; ++k) dw_acc[k] += (wv[2 * H + k] + wv[H + k]) + wv[k];
+      db_acc += wv[3 * H];
+    }
+  };
 
-    // ---- per-row flow chain (registers), dt written in place over t
-    const long long r = tile * T + tid;
-    if (r < a.B) {
-      float zs[Spec::KA][D];
-      LogDetAcc<M> ld;
-      FwdSweep<Spec, M, V, BWD, 0>::run(row, z, zs, ld);
-      using Base = BaseDist<D, Spec::BASE, M>;
-      float bth[Base::NA];
-      if constexpr (Spec::BASE) Span<0, 2 * D, V>::load(row, bth);
-      const float lp = (BWD ? Base::log_prob_save(bth, z) : Base::log_prob(bth, z)) + ld.nat();
-      a.logp[r] = lp;
-      lsum += (double)lp;
+  // Software pipeline over this CTA's tiles.  The tensor pipe runs in issue order and every tcgen05.mma
+  // costs its issuer ~46 cycles whatever the shape (tools/umma_probe.cu), so (a) ONE extra thread does
+  // all the issuing and the 128 compute threads never wait for it at a CTA barrier, and (b) GEMM 1 of
+  // the NEXT tile is issued ahead of GEMM 2 / 3 of the current one: the compute threads go straight to
+  // the next tile's flows while GEMM 2 / 3 complete behind them, and collect dh / dW one tile late.
+  //   compute, tile i: wait GEMM 1(i) -> t row -> flows -> [wait GEMM 2/3(i-1), drain] -> split h(i+1),
+  //                    arrive bar_h -> split dt(i), arrive bar_d
+  //   issuer,  tile i: wait bar_h -> GEMM 1(i+1) -> wait bar_d -> GEMM 2/3(i)
+  if (tid >= T) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssuer));
+    if (warp == T / 32) {
+    const bool leader = elect_one();
+    unsigned k = 0;
+    mbar_wait(bar_h, 0);
+    issue_gemm1(0, leader);
+    for (long long tl = blockIdx.x; tl < ntiles; tl += gridDim.x, ++k) {
+      const int buf = BWD ? (int)(k & 1) : 0;
+      mbar_wait(bar_h, (k + 1) & 1);
+      if (tl + gridDim.x < ntiles) issue_gemm1(BWD ? buf ^ 1 : 0, leader);
       if constexpr (BWD) {
-        const float cot = a.g_scale * g_cur;
-        float Gz[D];
-        float gb[Base::NA];
-        Base::bwd_saved(bth, z, cot, Gz, gb);
-        if constexpr (Spec::BASE) Span<0, 2 * D, V>::store(row, gb);
-        BwdSweep<Spec, M, V, Spec::K - 1>::run(row, zs, Gz, cot);
-      }
-    }
-
-    if constexpr (BWD) {
-      // ---- split dt row -> three level tiles (rows past B and the pad columns are zero)
-      {
-        float dv[PN];
-#pragma unroll
-        for (int j = 0; j < PN; ++j) dv[j] = 0.0f;
-        if (r < a.B) Span<0, P, V>::load(row, dv);
-#pragma unroll
-        for (int c = 0; c < PN / 8; ++c) store_levels8(d_row + c * 128, G::kD, dv + 8 * c);
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-
-      if (tid == 0) {
+        mbar_wait(bar_d, k & 1);
         tc_fence_after();
         // GEMM 2: [dt W0^T | dt W1^T | dt W2^T] = dt_i [W0; W1; W2]^T, dt levels smallest first (all 9 products)
+        // (the level loops stay rolled: this thread has few registers; the k-steps are unrolled so the
+        // descriptor moves into uniform registers pipeline)
         {
           unsigned acc = 0;
-#pragma unroll
+#pragma unroll 1
           for (int lv = 2; lv >= 0; --lv) {
 #pragma unroll
             for (int ks = 0; ks < PN / 16; ++ks) {
-              mma_bf16(tmem_base + G::cD2, dD_k + (uint64_t)((lv * G::kD + ks * 256) >> 4), dW2 + (uint64_t)((ks * 256) >> 4),
-                       kI2, acc);
+              if (leader)
+                mma_bf16(tmem_base + G::cD2, dD_k + (uint64_t)((lv * G::kD + ks * 256) >> 4),
+                         dW2 + (uint64_t)((ks * 256) >> 4), kI2, acc);
               acc = 1;
             }
           }
@@ -409,56 +425,121 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
         // groups) per instruction: dW^T and the bias gradient in one pass
         {
           unsigned acc = 0;
-#pragma unroll
+#pragma unroll 1
           for (int lv = 2; lv >= 0; --lv) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
-              mma_bf16(tmem_base + G::cD3, dD_mn + (uint64_t)((lv * G::kD + ks * 2 * kGrpD) >> 4),
-                       dA_mn + (uint64_t)((ks * 2 * kGrpA) >> 4), kI3, acc);
+              if (leader)
+                mma_bf16(tmem_base + G::cD3, dD_mn + (uint64_t)((lv * G::kD + ks * 2 * kGrpD) >> 4),
+                         dA_mn + (uint64_t)((buf * G::kA + ks * 2 * kGrpA) >> 4), kI3, acc);
               acc = 1;
             }
           }
         }
-        mma_commit(bar2);
+        if (leader) mma_commit(bar2);
+        __syncwarp();
       }
-      mbar_wait(bar2, it & 1);
-      tc_fence_after();
+    }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute));
+    split_h(0);
+    fence_proxy_async();
+    mbar_arrive(bar_h);
 
-      // ---- dh row out of TMEM (sum of the three W-level blocks, smallest first) -> global
-      {
-        float hv[3 * H];
-        tmem_load_row<3 * H>(lane_base + G::cD2, hv);
-        if (r < a.B) {
+    unsigned it = 0;          // tiles done by this CTA: mbarrier phase parity, h tile in use
+    long long r_prev = a.B;   // this thread's row of the previous tile (B: none)
+    for (; tile < ntiles; tile += gridDim.x, ++it) {
+      const int buf = BWD ? (int)(it & 1) : 0;
+      float z[D];
 #pragma unroll
-          for (int c = 0; c < H / 4; ++c) {
-            float o[4];
+      for (int i = 0; i < D; ++i) z[i] = y_nxt[i];
+      const float g_cur = g_nxt;
+      fetch(tile + gridDim.x);   // next tile's row: consumed after this tile's flows
+
+      // ---- t row out of TMEM (+ bias): thread r owns row r of the accumulator
+      mbar_wait(bar1, it & 1);
+      tc_fence_after();
+      float row[PN];
+      tmem_load_row<PN>(lane_base + G::cD1, row);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = (hv[2 * H + 4 * c + j] + hv[H + 4 * c + j]) + hv[4 * c + j];
-            st_stream_f4(a.dh + r * H + 4 * c, make_float4(o[0], o[1], o[2], o[3]));
-          }
+      for (int j = 0; j < P; ++j) row[j] += sBias[j];
+
+      // ---- per-row flow chain (registers), dt written in place over t
+      const long long r = tile * T + tid;
+      if (r < a.B) {
+        float zs[Spec::KA][D];
+        LogDetAcc<M> ld;
+        FwdSweep<Spec, M, V, BWD, 0>::run(row, z, zs, ld);
+        using Base = BaseDist<D, Spec::BASE, M>;
+        float bth[Base::NA];
+        if constexpr (Spec::BASE) Span<0, 2 * D, V>::load(row, bth);
+        const float lp = (BWD ? Base::log_prob_save(bth, z) : Base::log_prob(bth, z)) + ld.nat();
+        a.logp[r] = lp;
+        {  // compensated fp32 sum (fp64 adds are 1/64 rate here): ls_hi - ls_lo carries ~48 bits
+          const float yv = lp - ls_lo, tv = ls_hi + yv;
+          ls_lo = (tv - ls_hi) - yv;
+          ls_hi = tv;
+        }
+        if constexpr (BWD) {
+          const float cot = a.g_scale * g_cur;
+          float Gz[D];
+          float gb[Base::NA];
+          Base::bwd_saved(bth, z, cot, Gz, gb);
+          if constexpr (Spec::BASE) Span<0, 2 * D, V>::store(row, gb);
+          BwdSweep<Spec, M, V, Spec::K - 1>::run(row, zs, Gz, cot);
         }
       }
-      // ---- this tile's dW / db lanes (TMEM lane p < P) -> register accumulators; warps past P skip
-      if (warp * 32 < P) {
-        float wv[G::NB3];
-        tmem_load_row<G::NB3>(lane_base + G::cD3, wv);
+
+      if constexpr (BWD) {
+        // ---- the previous tile's GEMM 2 / 3 were issued before this tile's flows began: normally complete
+        if (it > 0) {
+          mbar_wait(bar2, (it - 1) & 1);
+          tc_fence_after();
+          drain_backward(r_prev);
+        }
+        r_prev = r;
+      }
+      // ---- next tile: split h (BWD: into the other h tile); D1 has been read, GEMM 1 may overwrite it
+      split_h(BWD ? buf ^ 1 : 0);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar_h);
+
+      if constexpr (BWD) {
+        // ---- split dt row -> three level tiles (rows past B and the pad columns are zero)
+        if (r >= a.B) {
 #pragma unroll
-        for (int k = 0; k < H; ++k) dw_acc[k] += (wv[2 * H + k] + wv[H + k]) + wv[k];
-        db_acc += wv[3 * H];
+          for (int j = 0; j < P; ++j) row[j] = 0.0f;
+        }
+#pragma unroll
+        for (int j = P; j < PN; ++j) row[j] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < PN / 8; ++c) store_levels8(d_row + c * 128, G::kD, row + 8 * c);
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_d);
+      }
+    }
+    if constexpr (BWD) {
+      if (it > 0) {
+        mbar_wait(bar2, (it - 1) & 1);
+        tc_fence_after();
+        drain_backward(r_prev);
+      }
+      if (tid < P) {   // TMEM lane p holds dW[:, p] and db[p]
+#pragma unroll
+        for (int k = 0; k < H; ++k) atomicAdd(a.dW + k * P + tid, dw_acc[k]);
+        atomicAdd(a.dbias + tid, db_acc);
       }
     }
   }
+  __syncwarp();
+  const double lsum = (double)ls_hi - (double)ls_lo;
 
   if (a.logp_sum) {
-    const double sblk = block_sum<T>(lsum, red);
+    const double sblk = block_sum<NT>(lsum, red);
     if (tid == 0) atomicAdd(a.logp_sum, sblk);
-  }
-  if constexpr (BWD) {
-    if (tid < P) {   // TMEM lane p holds dW[:, p] and db[p]
-#pragma unroll
-      for (int k = 0; k < H; ++k) atomicAdd(a.dW + k * P + tid, dw_acc[k]);
-      atomicAdd(a.dbias + tid, db_acc);
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -466,8 +547,8 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
 }
 
 template <class Spec, int H, bool BWD, class M, int MINB>
-__global__ void __launch_bounds__(kRows, MINB) dense_tc5_kernel(const DenseArgs a) {
-  dense_tc5_body<Spec, H, BWD, M>(a);
+__global__ void __launch_bounds__(kThreads, MINB) dense_tc5_kernel(const DenseArgs a) {
+  dense_tc5_body<Spec, H, BWD, M, MINB>(a);
 }
 
 }  // namespace tc5
