@@ -32,6 +32,16 @@ def _oracle(h, W, b, y, ft, d, tb, up):
     return lp, dt @ W.astype(np.float64).T, h.astype(np.float64).T @ dt, dt.sum(0), well
 
 
+@pytest.fixture(params=["auto", "sync", "tc5"])
+def dense_impl(request):
+    """auto: the library's own choice (tcgen05 / TMEM kernel for P >= 32, warp-level mma.sync below);
+    sync / tc5: one implementation forced for every chain that has both (ahead-of-time instances)."""
+    if request.param != "auto":
+        os.environ["NFN_B200_DENSE_MMA"] = request.param
+    yield request.param
+    os.environ.pop("NFN_B200_DENSE_MMA", None)
+
+
 def rel(got, ref):
     got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
     return np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref)))
@@ -39,7 +49,7 @@ def rel(got, ref):
 
 @pytest.mark.parametrize("case", range(len(CASES)))
 @pytest.mark.parametrize("B", [1, 100, 128 * 5 + 77, 20_000])
-def test_dense_chain_vs_oracle(cuda_device, nfn_lib, case, B):
+def test_dense_chain_vs_oracle(cuda_device, nfn_lib, dense_impl, case, B):
     from normalizingflownetwork_b200 import functional as F
 
     ft, d, tb, H = CASES[case]
@@ -75,7 +85,7 @@ def test_dense_chain_vs_oracle(cuda_device, nfn_lib, case, B):
     assert rel(got_b[well_b], ref_b[well_b]) <= 1e-5
 
 
-def test_dense_chain_equals_unfused_composition(cuda_device, nfn_lib):
+def test_dense_chain_equals_unfused_composition(cuda_device, nfn_lib, dense_impl):
     """Same answer as torch matmul + the plain chain kernel, and gradients accumulate (+=)."""
     from normalizingflownetwork_b200 import functional as F
 
@@ -102,6 +112,29 @@ def test_dense_chain_equals_unfused_composition(cuda_device, nfn_lib):
     dW2, db2 = dW.clone(), db.clone()
     F.dense_chain_forward_backward(h, W, b, y, ft, d, tb, g_scale=-1.0 / B, dW=dW2, dbias=db2)
     assert torch.allclose(dW2, 2 * dW, rtol=1e-4, atol=1e-6) and torch.allclose(db2, 2 * db, rtol=1e-4, atol=1e-6)
+
+
+def test_dense_chain_many_tiles_per_cta(cuda_device, nfn_lib, dense_impl):
+    """Every CTA runs several tiles (the tcgen05 kernel pipelines GEMM 1 of tile i+1 ahead of GEMM 2/3 of
+    tile i and drains dh / dW one tile late): ragged 150,001 rows against the float64 oracle."""
+    from normalizingflownetwork_b200 import functional as F
+
+    ft, d, tb, H = CASES[0]
+    P, B = 48, 150_001
+    rng = np.random.default_rng(77)
+    h = np.tanh(rng.normal(0, 1.0, (B, H))).astype(np.float32)
+    W = (rng.normal(0, 0.3, (H, P)) / np.sqrt(H)).astype(np.float32)
+    b = rng.normal(0, 0.1, (P,)).astype(np.float32)
+    y = rng.normal(0, 1.0, (B, d)).astype(np.float32)
+    ref_lp, ref_dh, ref_dW, ref_db, well = _oracle(h, W, b, y, ft, d, tb, -1.0 / B)
+    dev = lambda x: torch.tensor(x, device=cuda_device)
+    lp, dh, dW, db = F.dense_chain_forward_backward(dev(h), dev(W), dev(b), dev(y), ft, d, tb, g_scale=-1.0 / B)
+    assert rel(lp.cpu().numpy()[well], ref_lp[well]) <= 1e-5
+    assert rel(dh.cpu().numpy()[well] * B, ref_dh[well] * B) <= 1e-4
+    assert np.abs(dW.cpu().numpy() - ref_dW).max() <= 2e-3 * max(1.0, np.abs(ref_dW).max())
+    assert np.abs(db.cpu().numpy() - ref_db).max() <= 2e-3 * max(1.0, np.abs(ref_db).max())
+    lp_f = F.dense_chain_forward(dev(h), dev(W), dev(b), dev(y), ft, d, tb)
+    assert torch.equal(lp_f, lp)
 
 
 def test_dense_chain_unsupported_width_is_reported(cuda_device, nfn_lib):
