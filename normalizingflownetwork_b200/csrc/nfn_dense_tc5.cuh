@@ -64,8 +64,9 @@ struct Geo {
   static constexpr int NB3 = 3 * H + 16;                           // N of GEMM 3
   static constexpr unsigned kD = kRows * PN * 2;   // one bf16 level of the dt tile
   static constexpr unsigned kW = PN * H * 2;       // one level of W, either orientation
-  // BWD keeps TWO h tiles: GEMM 3 of tile i still reads h(i) while h(i+1) is split for GEMM 1 of tile i+1
-  static constexpr int NA = BWD ? 2 : 1;
+  // A ring of h tiles: GEMM 1 of tile i+1 is issued while tile i is still in its flows, and (BWD) GEMM 3 of
+  // tile i-1, which reads h(i-1), may still be running then
+  static constexpr int NA = BWD ? 3 : 2;
   static constexpr unsigned oA = 0;
   static constexpr unsigned oD = oA + NA * kA;                     // 3 levels (BWD)
   static constexpr unsigned oW1 = oD + (BWD ? 3 * kD : 0);         // W as [N = PN][K = H], 3 levels
@@ -303,7 +304,7 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
   float h_nxt[H];
   float y_nxt[D];
   float g_nxt = 1.0f;
-  auto fetch = [&](long long tile) {
+  auto fetch_h = [&](long long tile) {
     const long long r = tile * T + tid;
 #pragma unroll
     for (int i = 0; i < H; ++i) h_nxt[i] = 0.0f;
@@ -314,6 +315,11 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
         const float4 v = __ldg(src + c);
         h_nxt[4 * c] = v.x; h_nxt[4 * c + 1] = v.y; h_nxt[4 * c + 2] = v.z; h_nxt[4 * c + 3] = v.w;
       }
+    }
+  };
+  auto fetch_y = [&](long long tile) {
+    const long long r = tile * T + tid;
+    if (tile < ntiles && r < a.B) {
       load_event<D>(a.y, a.y_broadcast ? 0 : r, y_nxt);
       if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + r); }
     }
@@ -321,7 +327,6 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
 #pragma unroll
   for (int i = 0; i < D; ++i) y_nxt[i] = 0.0f;
   long long tile = blockIdx.x;
-  fetch(tile);
 
   const unsigned a_row = sbase + G::oA + (tid >> 3) * kGrpA + (tid & 7) * 16;  // this thread's row in the h tile
   const unsigned d_row = sbase + G::oD + tile_off(tid, 0, PN);   // ... in the dt level tiles
@@ -383,13 +388,14 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
     }
   };
 
-  // Software pipeline over this CTA's tiles.  The tensor pipe runs in issue order and every tcgen05.mma
-  // costs its issuer ~46 cycles whatever the shape (tools/umma_probe.cu), so (a) ONE extra thread does
-  // all the issuing and the 128 compute threads never wait for it at a CTA barrier, and (b) GEMM 1 of
-  // the NEXT tile is issued ahead of GEMM 2 / 3 of the current one: the compute threads go straight to
-  // the next tile's flows while GEMM 2 / 3 complete behind them, and collect dh / dW one tile late.
-  //   compute, tile i: wait GEMM 1(i) -> t row -> flows -> [wait GEMM 2/3(i-1), drain] -> split h(i+1),
-  //                    arrive bar_h -> split dt(i), arrive bar_d
+  // Software pipeline over this CTA's tiles.  The tensor pipe runs in issue order (across the CTAs of
+  // the SM too) and every tcgen05.mma costs ~46 cycles whatever the shape (tools/umma_probe.cu), so
+  // (a) a separate warp does all the issuing and the 128 compute threads never wait for it at a CTA barrier;
+  // (b) GEMM 1 of the NEXT tile is issued as soon as this tile's t row has left TMEM, a whole flow sweep
+  //     before its result is needed, and GEMM 2 / 3 of this tile complete behind the next tile's flows:
+  //     dh / dW are collected one tile late.
+  //   compute, tile i: wait GEMM 1(i) -> t row -> split h(i+1) -> arrive bar_h -> flows -> [wait GEMM 2/3(i-1),
+  //                    drain] -> split dt(i) -> arrive bar_d
   //   issuer,  tile i: wait bar_h -> GEMM 1(i+1) -> wait bar_d -> GEMM 2/3(i)
   if (tid >= T) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssuer));
@@ -399,9 +405,9 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
     mbar_wait(bar_h, 0);
     issue_gemm1(0, leader);
     for (long long tl = blockIdx.x; tl < ntiles; tl += gridDim.x, ++k) {
-      const int buf = BWD ? (int)(k & 1) : 0;
+      const int buf = (int)(k % G::NA);
       mbar_wait(bar_h, (k + 1) & 1);
-      if (tl + gridDim.x < ntiles) issue_gemm1(BWD ? buf ^ 1 : 0, leader);
+      if (tl + gridDim.x < ntiles) issue_gemm1((int)((k + 1) % G::NA), leader);
       if constexpr (BWD) {
         mbar_wait(bar_d, k & 1);
         tc_fence_after();
@@ -443,19 +449,20 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute));
+    fetch_h(tile);
     split_h(0);
     fence_proxy_async();
     mbar_arrive(bar_h);
+    fetch_h(tile + gridDim.x);
+    fetch_y(tile);
 
     unsigned it = 0;          // tiles done by this CTA: mbarrier phase parity, h tile in use
     long long r_prev = a.B;   // this thread's row of the previous tile (B: none)
     for (; tile < ntiles; tile += gridDim.x, ++it) {
-      const int buf = BWD ? (int)(it & 1) : 0;
       float z[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) z[i] = y_nxt[i];
       const float g_cur = g_nxt;
-      fetch(tile + gridDim.x);   // next tile's row: consumed after this tile's flows
 
       // ---- t row out of TMEM (+ bias): thread r owns row r of the accumulator
       mbar_wait(bar1, it & 1);
@@ -464,6 +471,14 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
       tmem_load_row<PN>(lane_base + G::cD1, row);
 #pragma unroll
       for (int j = 0; j < P; ++j) row[j] += sBias[j];
+
+      // ---- next tile's h row (fetched one tile ago) -> its h tile; D1 has been read: GEMM 1(i+1) may go
+      split_h((int)((it + 1) % G::NA));
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar_h);
+      fetch_h(tile + 2 * (long long)gridDim.x);   // consumed at the top of the next iteration
+      fetch_y(tile + gridDim.x);
 
       // ---- per-row flow chain (registers), dt written in place over t
       const long long r = tile * T + tid;
@@ -500,12 +515,6 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
         }
         r_prev = r;
       }
-      // ---- next tile: split h (BWD: into the other h tile); D1 has been read, GEMM 1 may overwrite it
-      split_h(BWD ? buf ^ 1 : 0);
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(bar_h);
-
       if constexpr (BWD) {
         // ---- split dt row -> three level tiles (rows past B and the pad columns are zero)
         if (r >= a.B) {
