@@ -177,6 +177,8 @@ int nfn_dense_chain_forward_backward(const nfn_chain_desc* desc, int hidden, con
                                      float g_scale, float* logp, float* dh, float* dW, float* dbias,
                                      double* logp_sum, int64_t B, void* stream);
 int64_t nfn_jit_dense_compile_check(const nfn_chain_desc* desc, int hidden, int accurate);
+/* the same check for the tcgen05 / TMEM implementation (csrc/nfn_dense_tc5.cuh) */
+int64_t nfn_jit_dense_tc5_compile_check(const nfn_chain_desc* desc, int hidden, int accurate);
 
 /*
  * One bijector on its own: Flow(t, n_dims).forward(z) and ._forward_log_det_jacobian(z)

@@ -97,6 +97,7 @@ const DenseKernels* find_dense(const std::string& key) {
   return it == dense_registry().end() ? nullptr : &it->second;
 }
 long long jit_dense_compile_check(const nfn_chain_desc* desc, int H, int mode, std::string& log);
+long long jit_dense_tc5_compile_check(const nfn_chain_desc* desc, int H, int mode, std::string& log);
 
 // ------------------------------------------------------------------ validation
 static int check_desc(const nfn_chain_desc* d) {
@@ -301,14 +302,18 @@ static int dense_dispatch(const nfn_chain_desc* desc, int hidden, const DenseArg
   //   fwd+bwd  P = 48: 127-134 vs 172 us   P = 17: 96 vs 86 us   P = 11: 94 vs 65 us
   //   forward  P = 48:      48 vs  72 us   P = 17: 37 vs 41 us   P = 11: 33 vs 31 us
   // NFN_B200_DENSE_MMA=tc5|sync forces one of them (A/B comparisons, tests).
-  if (k && k->fn5[mode][bwd ? 1 : 0]) {
-    const char* ev = getenv("NFN_B200_DENSE_MMA");
-    const bool force5 = ev && strcmp(ev, "tc5") == 0, force_sync = ev && strcmp(ev, "sync") == 0;
-    if (force5 || (!force_sync && param_size(desc) >= (bwd ? 32 : 16)))
-      return cuda_error(k->fn5[mode][bwd ? 1 : 0](a, st), key.c_str());
+  const char* ev = getenv("NFN_B200_DENSE_MMA");
+  const bool force5 = ev && strcmp(ev, "tc5") == 0, force_sync = ev && strcmp(ev, "sync") == 0;
+  const bool want5 = force5 || (!force_sync && param_size(desc) >= (bwd ? 32 : 16));
+  if (want5 && k && k->fn5[mode][bwd ? 1 : 0]) return cuda_error(k->fn5[mode][bwd ? 1 : 0](a, st), key.c_str());
+  bool served = false;
+  if (want5 && !(k && k->fn[mode][bwd ? 1 : 0] && !force5)) {
+    // no ahead-of-time instance of either kind (or tc5 forced): runtime-specialise the tcgen05 kernel
+    cudaError_t e5 = launch_dense_tc5_jit(desc, hidden, key, a, bwd, mode, st, &served);
+    if (e5 != cudaSuccess) return cuda_error(e5, key.c_str());
+    if (served) return NFN_OK;
   }
   if (k && k->fn[mode][bwd ? 1 : 0]) return cuda_error(k->fn[mode][bwd ? 1 : 0](a, st), key.c_str());
-  bool served = false;
   cudaError_t e = launch_dense_jit(desc, hidden, key, a, bwd, mode, st, &served);
   if (e != cudaSuccess) return cuda_error(e, key.c_str());
   if (!served)
@@ -358,6 +363,15 @@ int nfn_dense_chain_forward_backward(const nfn_chain_desc* desc, int hidden, con
   a.dbias = dbias; a.logp_sum = logp_sum; a.B = B; a.g_scale = g_scale;
   a.y_broadcast = (y_rows == 1 && B != 1);
   return dense_dispatch(desc, hidden, a, true, (cudaStream_t)stream);
+}
+
+int64_t nfn_jit_dense_tc5_compile_check(const nfn_chain_desc* desc, int hidden, int accurate) {
+  int rc = check_desc(desc);
+  if (rc != NFN_OK) return rc;
+  std::string log;
+  const long long n = jit_dense_tc5_compile_check(desc, hidden, accurate ? 1 : 0, log);
+  if (n < 0) return set_error(NFN_ERR_UNSUPPORTED, "NVRTC: %s", log.substr(0, 400).c_str());
+  return n;
 }
 
 int64_t nfn_jit_dense_compile_check(const nfn_chain_desc* desc, int hidden, int accurate) {

@@ -158,15 +158,12 @@ cudaError_t launch_dense_tc5(const DenseArgs& a, cudaStream_t st) {
   constexpr int T = tc5::kRows;          // rows per tile
   constexpr int NT = tc5::kThreads;      // threads per CTA
   constexpr unsigned kSmem = G::kBytes;
-  constexpr int kBySmem = (int)((227u * 1024u) / (kSmem + 1024u));
   constexpr int kByTmem = (int)(512u / G::kCols);
 #ifdef NFN_TUNE_TC5_MINB
-  constexpr int kWant = NFN_TUNE_TC5_MINB;
+  constexpr int MINB = NFN_TUNE_TC5_MINB;
 #else
-  constexpr int kWant = BWD ? 2 : 3;   // compute warpgroup registers: 216 (BWD), 136 (forward)
+  constexpr int MINB = tc5::min_blocks(Spec::P(), H, BWD);
 #endif
-  constexpr int kCap = kBySmem < kByTmem ? kBySmem : kByTmem;
-  constexpr int MINB = kCap < 1 ? 1 : (kCap < kWant ? kCap : kWant);
   auto kern = tc5::dense_tc5_kernel<Spec, H, BWD, M, MINB>;
   struct Cfg {
     int device = -1;
@@ -213,6 +210,8 @@ struct DenseRegistrar {
 
 cudaError_t launch_dense_jit(const nfn_chain_desc* desc, int H, const std::string& key, const DenseArgs& a,
                              bool bwd, int mode, cudaStream_t st, bool* served);
+cudaError_t launch_dense_tc5_jit(const nfn_chain_desc* desc, int H, const std::string& key, const DenseArgs& a,
+                                 bool bwd, int mode, cudaStream_t st, bool* served);
 
 // runtime specialiser (nfn_jit.cu): NVRTC-compiled chain_kernel for chains without an AOT
 // instance.  Returns cudaErrorNotSupported when the chain should go to the generic kernel.

@@ -25,7 +25,12 @@
 // of levels i + j <= 2 carry everything above 2^-24 relative, and K = 16 per instruction halves the
 // instruction count.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
+#else
+typedef unsigned long long uint64_t;   // the runtime specialiser (NVRTC) has no host headers
+typedef unsigned int uint32_t;
+#endif
 
 #include "nfn_dense_chain.cuh"
 
@@ -51,6 +56,35 @@ __host__ __device__ constexpr unsigned tile_off(int row, int col, int C) {
   return (unsigned)((row >> 3) * (C / 8 * 128) + (col >> 3) * 128 + (row & 7) * 16 + (col & 7) * 2);
 }
 
+// ---- geometry as plain constexpr functions of (P, H, backward?): shared by the kernel (Geo below), the
+// ahead-of-time launcher and the runtime specialiser, which only knows P and H at run time
+__host__ __device__ constexpr unsigned g_kLvlA(int H) { return (unsigned)(H / 8 * 128); }          // one h level inside an 8-row group
+__host__ __device__ constexpr unsigned g_kGrpA(int H) { return 3 * g_kLvlA(H) + 256; }            // [h0 | h1 | h2 | ones] per group
+__host__ __device__ constexpr unsigned g_kA(int H) { return (unsigned)(kRows / 8) * g_kGrpA(H); }  // one h tile
+__host__ __device__ constexpr unsigned g_kD(int P) { return (unsigned)(kRows * round16(P) * 2); }  // one bf16 level of the dt tile
+__host__ __device__ constexpr unsigned g_kW(int P, int H) { return (unsigned)(round16(P) * H * 2); }
+__host__ __device__ constexpr int g_NA(bool bwd) { return bwd ? 3 : 2; }
+__host__ __device__ constexpr unsigned g_oD(int H, bool bwd) { return (unsigned)g_NA(bwd) * g_kA(H); }
+__host__ __device__ constexpr unsigned g_oW1(int P, int H, bool bwd) { return g_oD(H, bwd) + (bwd ? 3 * g_kD(P) : 0); }
+__host__ __device__ constexpr unsigned g_oW2(int P, int H, bool bwd) { return g_oW1(P, H, bwd) + 3 * g_kW(P, H); }
+__host__ __device__ constexpr unsigned g_oBias(int P, int H, bool bwd) { return g_oW2(P, H, bwd) + (bwd ? 3 * g_kW(P, H) : 0); }
+__host__ __device__ constexpr unsigned g_oBar(int P, int H, bool bwd) { return (g_oBias(P, H, bwd) + round16(P) * 4 + 15) / 16 * 16; }
+__host__ __device__ constexpr unsigned smem_bytes(int P, int H, bool bwd) { return g_oBar(P, H, bwd) + 48; }
+__host__ __device__ constexpr int g_cD3(int P, int H) { return round16(P) + 3 * H; }
+__host__ __device__ constexpr unsigned tmem_cols(int P, int H, bool bwd) {
+  return pow2_cols(bwd ? g_cD3(P, H) + 3 * H + 16 : round16(P));
+}
+// resident CTAs per SM the kernel's register plan is built for (shared memory and TMEM columns permitting)
+__host__ __device__ constexpr int min_blocks(int P, int H, bool bwd) {
+  const int by_smem = (int)((227u * 1024u) / (smem_bytes(P, H, bwd) + 1024u));
+  const int by_tmem = (int)(512u / tmem_cols(P, H, bwd));
+  const int want = bwd ? 2 : 3;   // compute warpgroup registers: 200 (fwd+bwd), 128 (forward)
+  const int cap = by_smem < by_tmem ? by_smem : by_tmem;
+  // never below 2: this value fixes the register plan (256 threads x 128 registers at launch, re-split by
+  // setmaxnreg); when shared memory allows a single CTA the plan is simply the 2-CTA one
+  return cap < 2 ? 2 : (cap < want ? cap : want);
+}
+
 // shared-memory carve-up (bytes); every tile is 128-byte aligned
 template <int P, int H, bool BWD>
 struct Geo {
@@ -58,28 +92,28 @@ struct Geo {
   // h tile: per 8-row group [level 0 | level 1 | level 2 | ones] x (H/8 chunks each, 2 for the ones block), so
   // that read MN-major it is ONE operand [h0 | h1 | h2 | 1 0 ..] with N = 3H + 16 columns (GEMM 3 + bias
   // gradient in one pass), and read K-major level i is the tile at byte offset i * kLvlA (GEMM 1)
-  static constexpr unsigned kLvlA = H / 8 * 128;                   // bytes of one level inside a group
-  static constexpr unsigned kGrpA = 3 * kLvlA + 256;               // bytes of one 8-row group
-  static constexpr unsigned kA = kRows / 8 * kGrpA;
+  static constexpr unsigned kLvlA = g_kLvlA(H);
+  static constexpr unsigned kGrpA = g_kGrpA(H);
+  static constexpr unsigned kA = g_kA(H);
   static constexpr int NB3 = 3 * H + 16;                           // N of GEMM 3
-  static constexpr unsigned kD = kRows * PN * 2;   // one bf16 level of the dt tile
-  static constexpr unsigned kW = PN * H * 2;       // one level of W, either orientation
+  static constexpr unsigned kD = g_kD(P);          // one bf16 level of the dt tile
+  static constexpr unsigned kW = g_kW(P, H);       // one level of W, either orientation
   // A ring of h tiles: GEMM 1 of tile i+1 is issued while tile i is still in its flows, and (BWD) GEMM 3 of
   // tile i-1, which reads h(i-1), may still be running then
-  static constexpr int NA = BWD ? 3 : 2;
+  static constexpr int NA = g_NA(BWD);
   static constexpr unsigned oA = 0;
-  static constexpr unsigned oD = oA + NA * kA;                     // 3 levels (BWD)
-  static constexpr unsigned oW1 = oD + (BWD ? 3 * kD : 0);         // W as [N = PN][K = H], 3 levels
+  static constexpr unsigned oD = g_oD(H, BWD);                     // 3 levels (BWD)
+  static constexpr unsigned oW1 = g_oW1(P, H, BWD);                // W as [N = PN][K = H], 3 levels
   // W as [N = H][K = PN], 3 levels back to back == ONE operand [W0; W1; W2] with N = 3H rows (GEMM 2)
-  static constexpr unsigned oW2 = oW1 + 3 * kW;
-  static constexpr unsigned oBias = oW2 + (BWD ? 3 * kW : 0);
-  static constexpr unsigned oBar = (oBias + PN * 4 + 15) / 16 * 16;  // 4 mbarriers + tmem base
-  static constexpr unsigned kBytes = oBar + 48;
+  static constexpr unsigned oW2 = g_oW2(P, H, BWD);
+  static constexpr unsigned oBias = g_oBias(P, H, BWD);
+  static constexpr unsigned oBar = g_oBar(P, H, BWD);              // 4 mbarriers + tmem base
+  static constexpr unsigned kBytes = smem_bytes(P, H, BWD);
   // MN-major reads of the dt tiles with M = 128 run (16 - PN/8) chunks past the tile: what follows must be ours
   static_assert(!BWD || 6 * kW >= (16 - PN / 8) * 128, "operand over-read must stay in the CTA's smem");
   // TMEM columns: D1 [PN] | D2 [3H: dt W0^T | dt W1^T | dt W2^T] | D3 [3H + 16: dt^T h0 | dt^T h1 | dt^T h2 | db ..]
-  static constexpr int cD1 = 0, cD2 = PN, cD3 = PN + 3 * H;
-  static constexpr unsigned kCols = pow2_cols(BWD ? cD3 + NB3 : PN);
+  static constexpr int cD1 = 0, cD2 = PN, cD3 = g_cD3(P, H);
+  static constexpr unsigned kCols = tmem_cols(P, H, BWD);
   static_assert(3 * H <= 256 && NB3 <= 256, "MMA N limit");
 };
 
@@ -368,23 +402,34 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
   // dh row of a finished tile out of TMEM (sum of the three W-level blocks, smallest first) -> global,
   // and that tile's dW / db lanes (TMEM lane p < P) -> register accumulators; warps past P skip the latter
   auto drain_backward = [&](long long r_done) {
-    float hv[3 * H];
-    tmem_load_row<3 * H>(lane_base + G::cD2, hv);
-    if (r_done < a.B) {
+    // 16 hidden columns at a time: three level blocks in, one sum out (bounded register footprint for wide H)
 #pragma unroll
-      for (int c = 0; c < H / 4; ++c) {
-        float o[4];
+    for (int c = 0; c < H / 16; ++c) {
+      float b0[16], b1[16], b2[16];
+      tmem_load_row<16>(lane_base + G::cD2 + 16 * c, b0);
+      tmem_load_row<16>(lane_base + G::cD2 + H + 16 * c, b1);
+      tmem_load_row<16>(lane_base + G::cD2 + 2 * H + 16 * c, b2);
+      if (r_done < a.B) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = (hv[2 * H + 4 * c + j] + hv[H + 4 * c + j]) + hv[4 * c + j];
-        st_stream_f4(a.dh + r_done * H + 4 * c, make_float4(o[0], o[1], o[2], o[3]));
+        for (int q = 0; q < 4; ++q)
+          st_stream_f4(a.dh + r_done * H + 16 * c + 4 * q,
+                       make_float4((b2[4 * q] + b1[4 * q]) + b0[4 * q], (b2[4 * q + 1] + b1[4 * q + 1]) + b0[4 * q + 1],
+                                   (b2[4 * q + 2] + b1[4 * q + 2]) + b0[4 * q + 2], (b2[4 * q + 3] + b1[4 * q + 3]) + b0[4 * q + 3]));
       }
     }
     if (warp * 32 < P) {
-      float wv[G::NB3];
-      tmem_load_row<G::NB3>(lane_base + G::cD3, wv);
 #pragma unroll
-      for (int k = 0; k < H; ++k) dw_acc[k] += (wv[2 * H + k] + wv[H + k]) + wv[k];
-      db_acc += wv[3 * H];
+      for (int c = 0; c < H / 16; ++c) {
+        float b0[16], b1[16], b2[16];
+        tmem_load_row<16>(lane_base + G::cD3 + 16 * c, b0);
+        tmem_load_row<16>(lane_base + G::cD3 + H + 16 * c, b1);
+        tmem_load_row<16>(lane_base + G::cD3 + 2 * H + 16 * c, b2);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) dw_acc[16 * c + k] += (b2[k] + b1[k]) + b0[k];
+      }
+      float bv[16];
+      tmem_load_row<16>(lane_base + G::cD3 + 3 * H, bv);
+      db_acc += bv[0];
     }
   };
 

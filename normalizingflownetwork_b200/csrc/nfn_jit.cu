@@ -22,12 +22,14 @@
 
 #include "nfn_common.h"
 #include "nfn_dense_chain.cuh"
+#include "nfn_dense_tc5.cuh"
 
 // embedded by build.py (csrc/_gen/nfn_jit_sources.cu)
 extern const char* const nfn_jit_src_math;
 extern const char* const nfn_jit_src_flows;
 extern const char* const nfn_jit_src_chain;
 extern const char* const nfn_jit_src_dense;
+extern const char* const nfn_jit_src_dense_tc5;
 
 namespace nfn {
 
@@ -159,10 +161,12 @@ bool compile_cubin(const std::string& src, std::vector<char>& cubin, std::string
     log = "libnvrtc.so.12 not found";
     return false;
   }
-  const char* headers[4] = {nfn_jit_src_math, nfn_jit_src_flows, nfn_jit_src_chain, nfn_jit_src_dense};
-  const char* hnames[4] = {"nfn_math.cuh", "nfn_flows.cuh", "nfn_chain_kernel.cuh", "nfn_dense_chain.cuh"};
+  const char* headers[5] = {nfn_jit_src_math, nfn_jit_src_flows, nfn_jit_src_chain, nfn_jit_src_dense,
+                            nfn_jit_src_dense_tc5};
+  const char* hnames[5] = {"nfn_math.cuh", "nfn_flows.cuh", "nfn_chain_kernel.cuh", "nfn_dense_chain.cuh",
+                           "nfn_dense_tc5.cuh"};
   nvrtcProgram prog = nullptr;
-  int rc = n.CreateProgram(&prog, src.c_str(), "nfn_jit_chain.cu", 4, headers, hnames);
+  int rc = n.CreateProgram(&prog, src.c_str(), "nfn_jit_chain.cu", 5, headers, hnames);
   if (rc != 0) {
     log = "nvrtcCreateProgram failed";
     return false;
@@ -206,7 +210,7 @@ static JitEntry* get_or_build(const std::string& ckey, const std::string& src, c
     e.geo[0] = geo[0];
     e.geo[1] = geo[1];
     const std::string all = src + nfn_jit_src_math + nfn_jit_src_flows + nfn_jit_src_chain + nfn_jit_src_dense +
-                            "|sm_100a|v2";
+                            nfn_jit_src_dense_tc5 + "|sm_100a|v3";
     char name[64];
     snprintf(name, sizeof(name), "/chain_%016llx.cubin", fnv1a(all));
     const std::string path = cache_dir() + name;
@@ -229,6 +233,7 @@ static JitEntry* get_or_build(const std::string& ckey, const std::string& src, c
         if (ce == cudaSuccess)
           ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e.kern[b], e.geo[b].T,
                                                              e.geo[b].smem_bytes);
+        if (e.geo[b].max_ctas > 0 && occ > e.geo[b].max_ctas) occ = e.geo[b].max_ctas;
         e.ctas_per_sm[b] = occ > 0 ? occ : 1;
       }
       if (ce != cudaSuccess) {
@@ -263,7 +268,8 @@ static std::string spec_text(const nfn_chain_desc* d) {
 template <class Args>
 static cudaError_t launch_entry(JitEntry* ent, int b, const Args& a, long long B, cudaStream_t st) {
   const int T = ent->geo[b].T;
-  const long long ntiles = (B + T - 1) / T;
+  const int rows = ent->geo[b].rows > 0 ? ent->geo[b].rows : T;
+  const long long ntiles = (B + rows - 1) / rows;
   long long grid = (long long)device_info().sm_count * ent->ctas_per_sm[b];
   if (grid > ntiles) grid = ntiles;
   Args args = a;
@@ -315,6 +321,69 @@ static void dense_geometry(int P, int H, ChainGeometry (&geo)[2]) {
     const int want = b ? 2 : 3;
     geo[b].MINB = by_smem < 1 ? 1 : (by_smem < want ? by_smem : want);
   }
+}
+
+// ---- the tcgen05 / TMEM version (nfn_dense_tc5.cuh): 256 threads, 128 rows per tile
+static std::string dense_tc5_program_source(const nfn_chain_desc* d, int H, int mode, const ChainGeometry (&geo)[2]) {
+  const char* math = mode == 0 ? "nfn::MathFast" : "nfn::MathAccurate";
+  std::string s = "#include \"nfn_dense_tc5.cuh\"\nusing Spec = " + spec_text(d) + ";\n";
+  const char* names[2] = {"nfn_jit_dense_tc5_fwd", "nfn_jit_dense_tc5_fwd_bwd"};
+  for (int b = 0; b < 2; ++b) {
+    s += "extern \"C\" __global__ void __launch_bounds__(" + std::to_string(geo[b].T) + ", " +
+         std::to_string(geo[b].MINB) + ") " + names[b] + "(const nfn::DenseArgs a) {\n  nfn::tc5::dense_tc5_body<Spec, " +
+         std::to_string(H) + ", " + (b ? "true" : "false") + ", " + math + ", " + std::to_string(geo[b].MINB) +
+         ">(a);\n}\n";
+  }
+  return s;
+}
+
+static void dense_tc5_geometry(int P, int H, ChainGeometry (&geo)[2]) {
+  for (int b = 0; b < 2; ++b) {
+    geo[b].T = tc5::kThreads;
+    geo[b].rows = tc5::kRows;
+    geo[b].NB = 1;
+    geo[b].smem_bytes = tc5::smem_bytes(P, H, b == 1);
+    geo[b].MINB = tc5::min_blocks(P, H, b == 1);
+    geo[b].max_ctas = (int)(512u / tc5::tmem_cols(P, H, b == 1));
+  }
+}
+
+static bool dense_tc5_eligible(const nfn_chain_desc* desc, int P, int H) {
+  // P <= 128: one accumulator row per thread; the operand over-read of GEMM 3 must stay inside the CTA's smem
+  return P >= 1 && P <= 128 && H % 16 == 0 && H >= 16 && H <= 64 && jit_eligible(desc, P) &&
+         6 * tc5::g_kW(P, H) >= (unsigned)(16 - tc5::round16(P) / 8) * 128u && tc5::smem_bytes(P, H, true) <= 220u * 1024u;
+}
+
+// served == false (with cudaSuccess): the caller falls back to the mma.sync version
+cudaError_t launch_dense_tc5_jit(const nfn_chain_desc* desc, int H, const std::string& key, const DenseArgs& a,
+                                 bool bwd, int mode, cudaStream_t st, bool* served) {
+  *served = false;
+  if (!jit_enabled()) return cudaSuccess;
+  const int P = desc_param_size(desc);
+  if (!dense_tc5_eligible(desc, P, H)) return cudaSuccess;
+  ChainGeometry geo[2];
+  dense_tc5_geometry(P, H, geo);
+  const char* const names[2] = {"nfn_jit_dense_tc5_fwd", "nfn_jit_dense_tc5_fwd_bwd"};
+  const std::string ckey =
+      key + "|tc5dense" + std::to_string(H) + "|m" + std::to_string(mode) + "|dev" + std::to_string(device_info().device);
+  JitEntry* ent = get_or_build(ckey, dense_tc5_program_source(desc, H, mode, geo), names, geo);
+  if (!ent) return cudaSuccess;
+  cudaError_t ce = launch_entry(ent, bwd ? 1 : 0, a, a.B, st);
+  if (ce == cudaSuccess) *served = true;
+  return ce;
+}
+
+long long jit_dense_tc5_compile_check(const nfn_chain_desc* desc, int H, int mode, std::string& log) {
+  const int P = desc_param_size(desc);
+  if (!dense_tc5_eligible(desc, P, H)) {
+    log = "chain / hidden width not eligible for the tcgen05 kernel";
+    return -1;
+  }
+  ChainGeometry geo[2];
+  dense_tc5_geometry(P, H, geo);
+  std::vector<char> cubin;
+  if (!compile_cubin(dense_tc5_program_source(desc, H, mode, geo), cubin, log)) return -1;
+  return (long long)cubin.size();
 }
 
 // served == false (with cudaSuccess): the caller must use the unfused path

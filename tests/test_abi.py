@@ -85,6 +85,14 @@ def test_runtime_specialiser_compiles_without_gpu(nfn_lib):
         n = nfn_lib.nfn_jit_compile_check(ctypes.byref(desc), 0)
         assert n > 10_000, nfn_lib.nfn_last_error()
     assert nfn_lib.nfn_jit_compile_check(ctypes.byref(_lib.make_desc(["radial"], 2, True)), 1) > 10_000
+    # the fused Dense(P)+chain kernels, both implementations (warp-level mma.sync; tcgen05 / TMEM)
+    desc = _lib.make_desc(["radial", "planar"], 3, True)
+    assert nfn_lib.nfn_jit_dense_compile_check(ctypes.byref(desc), 32, 0) > 10_000, nfn_lib.nfn_last_error()
+    assert nfn_lib.nfn_jit_dense_tc5_compile_check(ctypes.byref(desc), 32, 0) > 10_000, nfn_lib.nfn_last_error()
+    desc = _lib.make_desc(["radial"] * 10, 2, True)
+    assert nfn_lib.nfn_jit_dense_tc5_compile_check(ctypes.byref(desc), 16, 1) > 10_000, nfn_lib.nfn_last_error()
+    # not eligible: hidden width the tensor-core tiles cannot take
+    assert nfn_lib.nfn_jit_dense_tc5_compile_check(ctypes.byref(desc), 10, 0) < 0
 
 
 def test_missing_library_is_loud(monkeypatch, tmp_path):
