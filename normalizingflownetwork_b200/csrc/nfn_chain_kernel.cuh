@@ -63,6 +63,7 @@ struct ChainGeometry {
   unsigned smem_bytes;
   int rows = 0;       // rows per tile when it differs from the thread count (0: == T)
   int max_ctas = 0;   // extra cap on resident CTAs per SM (TMEM columns); 0: none
+  int force_ctas = 0; // resident CTAs per SM to use instead of the occupancy API's answer; 0: ask the API
 };
 __host__ __device__ constexpr ChainGeometry chain_geometry(int P, bool bwd) {
   const int T = 128;
@@ -74,7 +75,7 @@ __host__ __device__ constexpr ChainGeometry chain_geometry(int P, bool bwd) {
   const int by_smem = bufs / nb;
   const int want = bwd ? 2 : 4;
   const int minb = by_smem < 1 ? 1 : (by_smem < want ? by_smem : want);
-  return ChainGeometry{T, nb, minb, tile * (unsigned)nb, 0, 0};
+  return ChainGeometry{T, nb, minb, tile * (unsigned)nb, 0, 0, 0};
 }
 
 // In-kernel all-reduce of the fp64 accumulators over NVLink peer memory (nfn_peer.cu).

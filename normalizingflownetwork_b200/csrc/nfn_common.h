@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/nfn_b200.h"
@@ -174,11 +176,15 @@ cudaError_t launch_dense_tc5(const DenseArgs& a, cudaStream_t st) {
   if (cfg.device != di.device) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
     if (e != cudaSuccess) return e;
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, kSmem);
-    if (e != cudaSuccess) return e;
-    // never more resident CTAs than TMEM allocations that fit (a CTA would spin in tcgen05.alloc)
-    if (occ > kByTmem) occ = kByTmem;
+    // the occupancy API reports 1 for kernels that allocate tensor memory: size the grid from our own geometry
+#ifdef NFN_TUNE_TC5_MINB
+    int occ = MINB < kByTmem ? MINB : kByTmem;
+#else
+    int occ = tc5::resident_ctas(Spec::P(), H, BWD);
+#endif
+    if (getenv("NFN_B200_DEBUG"))
+      fprintf(stderr, "[nfn_b200] dense_tc5 P=%d H=%d bwd=%d: %d CTAs/SM, TMEM cap %d, smem %u B, %d SMs\n", Spec::P(), H,
+              (int)BWD, occ, kByTmem, kSmem, di.sm_count);
     cfg.ctas_per_sm = occ > 0 ? occ : 1;
     cfg.device = di.device;
   }

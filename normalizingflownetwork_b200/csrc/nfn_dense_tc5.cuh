@@ -85,6 +85,17 @@ __host__ __device__ constexpr int min_blocks(int P, int H, bool bwd) {
   return cap < 2 ? 2 : (cap < want ? cap : want);
 }
 
+// Resident CTAs per SM to size the grid with.  Computed here, not asked of the occupancy API:
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for every kernel that allocates tensor memory
+// (measured), although shared memory, registers and TMEM columns all allow more.
+__host__ __device__ constexpr int resident_ctas(int P, int H, bool bwd) {
+  const int by_smem = (int)((227u * 1024u) / (smem_bytes(P, H, bwd) + 1024u));
+  const int by_tmem = (int)(512u / tmem_cols(P, H, bwd));
+  const int by_regs = min_blocks(P, H, bwd);   // the register plan: 65536 / (256 threads x launch registers)
+  const int c = by_smem < by_tmem ? (by_smem < by_regs ? by_smem : by_regs) : (by_tmem < by_regs ? by_tmem : by_regs);
+  return c < 1 ? 1 : c;
+}
+
 // shared-memory carve-up (bytes); every tile is 128-byte aligned
 template <int P, int H, bool BWD>
 struct Geo {

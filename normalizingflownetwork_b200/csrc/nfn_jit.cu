@@ -233,6 +233,7 @@ static JitEntry* get_or_build(const std::string& ckey, const std::string& src, c
         if (ce == cudaSuccess)
           ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e.kern[b], e.geo[b].T,
                                                              e.geo[b].smem_bytes);
+        if (e.geo[b].force_ctas > 0) occ = e.geo[b].force_ctas;
         if (e.geo[b].max_ctas > 0 && occ > e.geo[b].max_ctas) occ = e.geo[b].max_ctas;
         e.ctas_per_sm[b] = occ > 0 ? occ : 1;
       }
@@ -345,6 +346,7 @@ static void dense_tc5_geometry(int P, int H, ChainGeometry (&geo)[2]) {
     geo[b].smem_bytes = tc5::smem_bytes(P, H, b == 1);
     geo[b].MINB = tc5::min_blocks(P, H, b == 1);
     geo[b].max_ctas = (int)(512u / tc5::tmem_cols(P, H, b == 1));
+    geo[b].force_ctas = tc5::resident_ctas(P, H, b == 1);   // the occupancy API says 1 for TMEM kernels
   }
 }
 
