@@ -433,6 +433,7 @@ def run_ours(args):
     peak, peak_src = load_peaks()
     achieved = bytes_per_row * B / (kern_ms * 1e-3) / 1e9
     cpu = cpu_baseline(cfg) if (world == 1 and not args.no_cpu_baseline) else None
+    fused = fused_dense_step(cfg, device) if (world == 1 and not args.rows and not args.fwd_only) else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -461,8 +462,48 @@ def run_ours(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if fused is not None:
+        line["fused_dense_step"] = fused
     print(json.dumps(line), flush=True)
     return 0
+
+
+def fused_dense_step(cfg, device, steps=20):
+    """SURVEY §8(f) rank 1, reported next to the headline (not part of it): the emitting Dense(16 -> P)
+    layer + the flow chain, forward + backward, in ONE kernel (h[B,16] in, logp / dh / dW / db out; the
+    parameter tensor t never exists in HBM).  Same rows and chain as the headline workload."""
+    import torch
+
+    from normalizingflownetwork_b200 import functional as F
+
+    ft, d, tb, B, bwd = CONFIGS[cfg]
+    if is_mdn(ft) or not bwd:
+        return None
+    P, H = param_size(ft, d, tb), 16
+    g = torch.Generator(device=device).manual_seed(22)
+    h = torch.tanh(torch.randn((B, H), generator=g, device=device))
+    W = torch.randn((H, P), generator=g, device=device) * 0.3
+    b = torch.zeros(P, device=device)
+    y = torch.randn((B, d), generator=g, device=device)
+    dW, db = torch.zeros((H, P), device=device), torch.zeros(P, device=device)
+    try:
+        def step():
+            F.dense_chain_forward_backward(h, W, b, y, ft, d, tb, g_scale=-1.0 / B, dW=dW, dbias=db)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / steps
+    except Exception as exc:  # noqa: BLE001 -- an optional extra must not take the headline down
+        return {"error": str(exc)[:200]}
+    return {"what": "Dense(16->P) layer + flow chain fused, fwd+bwd, one kernel (tcgen05 / TMEM GEMMs); t never in HBM",
+            "rows": B, "hidden": H, "us_per_step": us, "samples_per_s": B / (us * 1e-6),
+            "bytes_per_row": 4 * (2 * H + d + 1), "hbm_frac": 4 * (2 * H + d + 1) * B / (us * 1e-6) / 1e9 / load_peaks()[0]}
 
 
 def run_cfg1_pipeline(args):
@@ -578,7 +619,16 @@ def main():
         return run_cfg1_pipeline(args)
     if args.impl == "reference":
         return run_reference(args)
-    return run_ours(args)
+    rc = run_ours(args)
+    try:  # leave the process group cleanly (NCCL warns on stderr otherwise)
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        pass
+    return rc
 
 
 if __name__ == "__main__":
