@@ -65,6 +65,11 @@ def test_descriptor_validation_without_gpu(nfn_lib):
     assert nfn_lib.nfn_chain_forward(ctypes.byref(d), None, None, 5, None, 4, None) == -3  # y_rows != B, 1
     assert nfn_lib.nfn_chain_forward(ctypes.byref(d), None, None, 4, None, 4, None) == -1
     assert nfn_lib.nfn_chain_forward(ctypes.byref(d), None, None, 0, None, 0, None) == 0   # B = 0 is a no-op
+    # density grid: empty grids are no-ops, negative sizes and NULL buffers are refused
+    assert nfn_lib.nfn_chain_forward_grid(ctypes.byref(d), None, None, 0, None, 4, None) == 0
+    assert nfn_lib.nfn_chain_forward_grid(ctypes.byref(d), None, None, 3, None, 0, None) == 0
+    assert nfn_lib.nfn_chain_forward_grid(ctypes.byref(d), None, None, -1, None, 4, None) == -3
+    assert nfn_lib.nfn_chain_forward_grid(ctypes.byref(d), None, None, 3, None, 4, None) == -1
     buf = (ctypes.c_float * 64)()
     addr = ctypes.addressof(buf)
     odd = ctypes.c_void_p(addr + 4)
