@@ -296,15 +296,15 @@ static int dense_dispatch(const nfn_chain_desc* desc, int hidden, const DenseArg
   const std::string key = chain_key(desc->n_dims, desc->trainable_base != 0, desc->n_flows, desc->flow_type);
   const int mode = math_mode();
   const DenseKernels* k = find_dense(key + "|h" + std::to_string(hidden));
-  // Two implementations of the same contract.  tcgen05 / TMEM (nfn_dense_tc5.cuh) pays a fixed ~46 cycles per
-  // tcgen05.mma -- 6 per 128-row tile forward, 39 forward+backward, whatever the chain -- so it wins where
-  // the per-row flow work is not tiny.  Measured (B = 2^20, H = 16, tcgen05 vs warp-level mma.sync):
-  //   fwd+bwd  P = 48: 95 vs 173 us   P = 32: 84 vs 131 us   P = 17: 84 vs 87 us   P = 11: 72 vs 66 us
-  //   forward  P = 48: 34 vs  72 us   P = 32: 33 vs  53 us   P = 17: 27 vs 41 us   P = 11: 23 vs 31 us
+  // Two implementations of the same contract: tcgen05 / TMEM (nfn_dense_tc5.cuh, the default wherever it
+  // exists) and warp-level mma.sync (nfn_dense_chain.cuh: the baseline it is measured against, and the
+  // fallback if the tcgen05 kernel cannot be built for a chain).  Measured, B = 2^20, H = 16, tcgen05 vs mma.sync:
+  //   fwd+bwd  P = 48: 88-92 vs 172 us   P = 32: 73 vs 131 us   P = 17: 68 vs 87 us   P = 11: 57 vs 66 us
+  //   forward  P = 48: 33 vs  72 us   P = 32: 33 vs  53 us   P = 17: 27 vs 40 us   P = 11: 24 vs 31 us
   // NFN_B200_DENSE_MMA=tc5|sync forces one of them (A/B comparisons, tests).
   const char* ev = getenv("NFN_B200_DENSE_MMA");
   const bool force5 = ev && strcmp(ev, "tc5") == 0, force_sync = ev && strcmp(ev, "sync") == 0;
-  const bool want5 = force5 || (!force_sync && (!bwd || param_size(desc) >= 16));
+  const bool want5 = force5 || !force_sync;
   if (want5 && k && k->fn5[mode][bwd ? 1 : 0]) return cuda_error(k->fn5[mode][bwd ? 1 : 0](a, st), key.c_str());
   bool served = false;
   if (want5 && !(k && k->fn[mode][bwd ? 1 : 0] && !force5)) {

@@ -11,10 +11,11 @@
 //   tcgen05.ld 32x32b hands thread r exactly row r of D1  -> + bias -> per-row flows (nfn_flows.cuh)
 //   thread r splits its dt row into 3 bf16 levels -> operand tiles D_i [128 x PN]
 //   GEMM 2   D2[128 x H]   = dt W^T            (A = D_i K-major,          B = W[H][P] as N x K)
-//   GEMM 3   D3[PN  x H]   = dt^T h            (A = D_i read MN-major,    B = the h tiles read MN-major)
-//   GEMM 4   D4[PN  x 16]  = dt^T [1 0 ...]    (bias gradient: B is one constant 512-byte tile)
-//   tcgen05.ld D2 row r -> dh[r, :] ; D3 / D4 lanes p < P are summed over tiles in registers and leave
-//   as one atomic per entry per CTA.
+//   GEMM 3   D3[.. x 3H+16] = [dt^T h0 | dt^T h1 | dt^T h2 | dt^T 1]   (A = the dt tile read MN-major: one M = 128
+//                              instruction spans 16 chunks of the [level 0 | level 1 | level 2] row groups, so
+//                              the dt levels ride in different TMEM lanes; B = the h tile read MN-major with
+//                              its three levels and a ones block side by side: dW^T and db in one pass)
+//   tcgen05.ld D2 row r -> dh[r, :] ; the D3 lanes (level, p) leave as atomics into dW[:, p], db[p].
 //
 // Why bf16 levels and not TF32: the backward GEMMs contract over the ROWS of the tile, i.e. they need the
 // dt and h tiles transposed.  With the no-swizzle canonical layout (8 x 16-byte core matrices) an
@@ -71,8 +72,11 @@ __host__ __device__ constexpr unsigned g_oBias(int P, int H, bool bwd) { return 
 __host__ __device__ constexpr unsigned g_oBar(int P, int H, bool bwd) { return (g_oBias(P, H, bwd) + round16(P) * 4 + 15) / 16 * 16; }
 __host__ __device__ constexpr unsigned smem_bytes(int P, int H, bool bwd) { return g_oBar(P, H, bwd) + 48; }
 __host__ __device__ constexpr int g_cD3(int P, int H) { return round16(P) + 3 * H; }
+// GEMM 3 reads the dt tile MN-major with M = 128 = 16 eight-column chunks per pass; the three levels of a row
+// group are 3 * PN/8 consecutive chunks, so ceil(3 PN / 128) passes cover them (1 for P <= 32, 2 for P <= 80)
+__host__ __device__ constexpr int g_NP3(int P) { return (3 * (round16(P) / 8) + 15) / 16; }
 __host__ __device__ constexpr unsigned tmem_cols(int P, int H, bool bwd) {
-  return pow2_cols(bwd ? g_cD3(P, H) + 3 * H + 16 : round16(P));
+  return pow2_cols(bwd ? g_cD3(P, H) + g_NP3(P) * (3 * H + 16) : round16(P));
 }
 // resident CTAs per SM the kernel's register plan is built for (shared memory and TMEM columns permitting)
 __host__ __device__ constexpr int min_blocks(int P, int H, bool bwd) {
@@ -107,7 +111,14 @@ struct Geo {
   static constexpr unsigned kGrpA = g_kGrpA(H);
   static constexpr unsigned kA = g_kA(H);
   static constexpr int NB3 = 3 * H + 16;                           // N of GEMM 3
-  static constexpr unsigned kD = g_kD(P);          // one bf16 level of the dt tile
+  // dt tile: per 8-row group [level 0 | level 1 | level 2] x (PN/8 chunks each).  Read K-major, level i is the
+  // tile at byte offset i * kLvlD (GEMM 2); read MN-major with M = 128, one instruction sees 16 consecutive
+  // chunks = SEVERAL LEVELS AT ONCE, each landing in its own TMEM lanes (GEMM 3 needs NP3 passes, not 3)
+  static constexpr int CL = PN / 8;                                // chunks per level
+  static constexpr unsigned kLvlD = CL * 128;
+  static constexpr unsigned kGrpD = 3 * kLvlD;
+  static constexpr int NP3 = g_NP3(P);
+  static constexpr unsigned kD = g_kD(P);          // bytes of one level over the whole tile (tile = 3 kD)
   static constexpr unsigned kW = g_kW(P, H);       // one level of W, either orientation
   // A ring of h tiles: GEMM 1 of tile i+1 is issued while tile i is still in its flows, and (BWD) GEMM 3 of
   // tile i-1, which reads h(i-1), may still be running then
@@ -121,8 +132,8 @@ struct Geo {
   static constexpr unsigned oBar = g_oBar(P, H, BWD);              // 4 mbarriers + tmem base
   static constexpr unsigned kBytes = smem_bytes(P, H, BWD);
   // MN-major reads of the dt tiles with M = 128 run (16 - PN/8) chunks past the tile: what follows must be ours
-  static_assert(!BWD || 6 * kW >= (16 - PN / 8) * 128, "operand over-read must stay in the CTA's smem");
-  // TMEM columns: D1 [PN] | D2 [3H: dt W0^T | dt W1^T | dt W2^T] | D3 [3H + 16: dt^T h0 | dt^T h1 | dt^T h2 | db ..]
+  static_assert(!BWD || 6 * kW >= (unsigned)(16 * NP3 - 3 * CL) * 128, "operand over-read must stay in the CTA's smem");
+  // TMEM columns: D1 [PN] | D2 [3H: dt W0^T | dt W1^T | dt W2^T] | D3 [NP3 x (3H + 16): dt^T h0 | dt^T h1 | dt^T h2 | db ..]
   static constexpr int cD1 = 0, cD2 = PN, cD3 = g_cD3(P, H);
   static constexpr unsigned kCols = tmem_cols(P, H, BWD);
   static_assert(3 * H <= 256 && NB3 <= 256, "MMA N limit");
@@ -286,7 +297,8 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
   constexpr int V = 1;
   constexpr unsigned kGrpA = G::kGrpA;       // bytes between 8-row groups of the h tile
   constexpr unsigned kGrpW1 = H / 8 * 128;   // ... of a W1 level tile (H columns)
-  constexpr unsigned kGrpD = PN / 8 * 128;   // ... of a tile with PN columns
+  constexpr unsigned kGrpD = G::kGrpD;       // ... of the dt tile (three levels side by side)
+  constexpr unsigned kGrpW2 = PN / 8 * 128;  // ... of a W2 level tile (PN columns)
   constexpr uint32_t kI1 = instr_desc(128, PN, 0, 0);
   constexpr uint32_t kI2 = instr_desc(128, 3 * H, 0, 0);
   constexpr uint32_t kI3 = instr_desc(128, G::NB3, 1, 1);
@@ -374,20 +386,27 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
   long long tile = blockIdx.x;
 
   const unsigned a_row = sbase + G::oA + (tid >> 3) * kGrpA + (tid & 7) * 16;  // this thread's row in the h tile
-  const unsigned d_row = sbase + G::oD + tile_off(tid, 0, PN);   // ... in the dt level tiles
+  const unsigned d_row = sbase + G::oD + (tid >> 3) * kGrpD + (tid & 7) * 16;   // ... in the dt tile
   // operand descriptors of level 0 / k-step 0; the others differ by a constant in the address field
   const uint64_t dA_k = smem_desc(sbase + G::oA, 128, kGrpA);     // h tile, one level K-major (GEMM 1)
   const uint64_t dA_mn = smem_desc(sbase + G::oA, kGrpA, 128);    // h tile, all levels + ones MN-major (GEMM 3)
   const uint64_t dW1 = smem_desc(sbase + G::oW1, 128, kGrpW1);
-  const uint64_t dD_k = smem_desc(sbase + G::oD, 128, kGrpD);     // dt level tiles, K-major (GEMM 2)
-  const uint64_t dD_mn = smem_desc(sbase + G::oD, kGrpD, 128);    // dt level tiles, MN-major (GEMM 3)
-  const uint64_t dW2 = smem_desc(sbase + G::oW2, 128, kGrpD);     // [W0; W1; W2], N = 3H
+  const uint64_t dD_k = smem_desc(sbase + G::oD, 128, kGrpD);     // dt tile, one level K-major (GEMM 2)
+  const uint64_t dD_mn = smem_desc(sbase + G::oD, kGrpD, 128);    // dt tile, 16 chunks across levels MN-major (GEMM 3)
+  const uint64_t dW2 = smem_desc(sbase + G::oW2, 128, kGrpW2);    // [W0; W1; W2], N = 3H
   float ls_hi = 0.0f, ls_lo = 0.0f;   // this thread's sum of logp (compensated)
-  float dw_acc[H], db_acc = 0.0f;  // lanes p < P: dW[:, p] and db[p] summed over this CTA's tiles
+  // GEMM 3, pass j: TMEM lane m holds chunk 16 j + m / 8 of the [level 0 | level 1 | level 2] row groups, i.e.
+  // the contribution of ONE bf16 level of dt[:, p] to dW[:, p] and db[p].  It accumulates in tensor memory over
+  // windows of kFlush tiles (bounding the number of in-place fp32 accumulations), then goes out as atomics,
+  // which also sum the levels and the CTAs.
+  // Narrow chains (one pass) have registers to spare: they drain D3 every tile into register accumulators and
+  // issue their atomics once, at the end (measured 69 vs 74 us at P = 17); wide ones use the TMEM windows
+  // (88 vs 94 us at P = 48, where the second accumulator set spilled).
+  constexpr bool kRegAcc = (G::NP3 == 1);
+  constexpr unsigned kFlush = kRegAcc ? 1u : 16u;
+  float dw_acc[kRegAcc ? H : 1], db_acc = 0.0f;
 #pragma unroll
-  for (int k = 0; k < H; ++k) dw_acc[k] = 0.0f;
-
-  // one thread issues; GEMM 1 of a tile reads h tile `buf`
+  for (int k = 0; k < (kRegAcc ? H : 1); ++k) dw_acc[k] = 0.0f;
   // The issuing code runs warp-converged on warp-uniform values (so the operand descriptors live in
   // uniform registers) and only the tcgen05 instructions themselves are predicated on one elected lane.
   auto issue_gemm1 = [&](int buf, bool leader) {
@@ -428,19 +447,32 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
                                    (b2[4 * q + 2] + b1[4 * q + 2]) + b0[4 * q + 2], (b2[4 * q + 3] + b1[4 * q + 3]) + b0[4 * q + 3]));
       }
     }
-    if (warp * 32 < P) {
+  };
+  auto flush_dw = [&]() {
 #pragma unroll
-      for (int c = 0; c < H / 16; ++c) {
-        float b0[16], b1[16], b2[16];
-        tmem_load_row<16>(lane_base + G::cD3 + 16 * c, b0);
-        tmem_load_row<16>(lane_base + G::cD3 + H + 16 * c, b1);
-        tmem_load_row<16>(lane_base + G::cD3 + 2 * H + 16 * c, b2);
+    for (int j = 0; j < G::NP3; ++j) {
+      if (16 * j + 4 * warp < 3 * G::CL) {   // this warp's 4 chunks of pass j exist (warp-uniform)
+        const int q = 16 * j + (tid >> 3), p = (q % G::CL) * 8 + (tid & 7);   // lane -> (level, column p)
+        const bool live = q < 3 * G::CL && p < P;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) dw_acc[16 * c + k] += (b2[k] + b1[k]) + b0[k];
+        for (int c = 0; c < H / 16; ++c) {
+          float b0[16], b1[16], b2[16];
+          tmem_load_row<16>(lane_base + G::cD3 + j * G::NB3 + 16 * c, b0);
+          tmem_load_row<16>(lane_base + G::cD3 + j * G::NB3 + H + 16 * c, b1);
+          tmem_load_row<16>(lane_base + G::cD3 + j * G::NB3 + 2 * H + 16 * c, b2);
+          if constexpr (kRegAcc) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) dw_acc[16 * c + k] += (b2[k] + b1[k]) + b0[k];
+          } else if (live) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) atomicAdd(a.dW + (16 * c + k) * P + p, (b2[k] + b1[k]) + b0[k]);
+          }
+        }
+        float bv[16];
+        tmem_load_row<16>(lane_base + G::cD3 + j * G::NB3 + 3 * H, bv);
+        if constexpr (kRegAcc) db_acc += bv[0];
+        else if (live) atomicAdd(a.dbias + p, bv[0]);
       }
-      float bv[16];
-      tmem_load_row<16>(lane_base + G::cD3 + 3 * H, bv);
-      db_acc += bv[0];
     }
   };
 
@@ -477,25 +509,23 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
 #pragma unroll
             for (int ks = 0; ks < PN / 16; ++ks) {
               if (leader)
-                mma_bf16(tmem_base + G::cD2, dD_k + (uint64_t)((lv * G::kD + ks * 256) >> 4),
+                mma_bf16(tmem_base + G::cD2, dD_k + (uint64_t)((lv * G::kLvlD + ks * 256) >> 4),
                          dW2 + (uint64_t)((ks * 256) >> 4), kI2, acc);
               acc = 1;
             }
           }
         }
         // GEMM 3: [dt^T h0 | dt^T h1 | dt^T h2 | dt^T 1 ..] over the tile's 128 rows, 16 rows (two 8-row
-        // groups) per instruction: dW^T and the bias gradient in one pass
-        {
-          unsigned acc = 0;
+        // groups) per instruction: dW^T and the bias gradient in one pass.  M = 128 spans 16 chunks of the
+        // [level 0 | level 1 | level 2] groups, so the levels ride in different lanes of the same instruction.
 #pragma unroll 1
-          for (int lv = 2; lv >= 0; --lv) {
+        for (int j = 0; j < G::NP3; ++j) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              if (leader)
-                mma_bf16(tmem_base + G::cD3, dD_mn + (uint64_t)((lv * G::kD + ks * 2 * kGrpD) >> 4),
-                         dA_mn + (uint64_t)((buf * G::kA + ks * 2 * kGrpA) >> 4), kI3, acc);
-              acc = 1;
-            }
+          for (int ks = 0; ks < 8; ++ks) {
+            if (leader)
+              mma_bf16(tmem_base + G::cD3 + j * G::NB3, dD_mn + (uint64_t)((j * 2048 + ks * 2 * kGrpD) >> 4),
+                       dA_mn + (uint64_t)((buf * G::kA + ks * 2 * kGrpA) >> 4), kI3,
+                       (ks > 0 || (k % kFlush) != 0) ? 1u : 0u);
           }
         }
         if (leader) mma_commit(bar2);
@@ -568,6 +598,7 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
           mbar_wait(bar2, (it - 1) & 1);
           tc_fence_after();
           drain_backward(r_prev);
+          if (it % kFlush == 0) flush_dw();   // tile it starts a new accumulation window in D3
         }
         r_prev = r;
       }
@@ -580,7 +611,7 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
 #pragma unroll
         for (int j = P; j < PN; ++j) row[j] = 0.0f;
 #pragma unroll
-        for (int c = 0; c < PN / 8; ++c) store_levels8(d_row + c * 128, G::kD, row + 8 * c);
+        for (int c = 0; c < PN / 8; ++c) store_levels8(d_row + c * 128, G::kLvlD, row + 8 * c);
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar_d);
@@ -591,11 +622,15 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
         mbar_wait(bar2, (it - 1) & 1);
         tc_fence_after();
         drain_backward(r_prev);
+        flush_dw();
       }
-      if (tid < P) {   // TMEM lane p holds dW[:, p] and db[p]
+      if constexpr (kRegAcc) {   // one pass: lane -> chunk tid / 8 of the [level 0 | level 1 | level 2] groups
+        const int q = tid >> 3, p = (q % G::CL) * 8 + (tid & 7);
+        if (q < 3 * G::CL && p < P) {
 #pragma unroll
-        for (int k = 0; k < H; ++k) atomicAdd(a.dW + k * P + tid, dw_acc[k]);
-        atomicAdd(a.dbias + tid, db_acc);
+          for (int k = 0; k < H; ++k) atomicAdd(a.dW + k * P + p, dw_acc[k]);
+          atomicAdd(a.dbias + p, db_acc);
+        }
       }
     }
   }

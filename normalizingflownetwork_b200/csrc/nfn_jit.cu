@@ -353,7 +353,8 @@ static void dense_tc5_geometry(int P, int H, ChainGeometry (&geo)[2]) {
 static bool dense_tc5_eligible(const nfn_chain_desc* desc, int P, int H) {
   // P <= 128: one accumulator row per thread; the operand over-read of GEMM 3 must stay inside the CTA's smem
   return P >= 1 && P <= 128 && H % 16 == 0 && H >= 16 && H <= 64 && jit_eligible(desc, P) &&
-         6 * tc5::g_kW(P, H) >= (unsigned)(16 - tc5::round16(P) / 8) * 128u && tc5::smem_bytes(P, H, true) <= 220u * 1024u;
+         6 * tc5::g_kW(P, H) >= (unsigned)(16 * tc5::g_NP3(P) - 3 * (tc5::round16(P) / 8)) * 128u &&
+         tc5::smem_bytes(P, H, true) <= 220u * 1024u;
 }
 
 // served == false (with cudaSuccess): the caller falls back to the mma.sync version
