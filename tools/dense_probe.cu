@@ -4,7 +4,7 @@
 //
 //   nvcc -O2 -std=c++17 -o build/dense_probe tools/dense_probe.cu -Lnormalizingflownetwork_b200 -lnfn_b200 \
 //        -Xlinker -rpath -Xlinker '$ORIGIN/../normalizingflownetwork_b200'
-//   build/dense_probe [rows=1048576] [cfg=2] [reps=20]
+//   build/dense_probe [rows=1048576] [cfg=2] [reps=20] [hidden=16]
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -39,7 +39,7 @@ int main(int argc, char** argv) {
   const long long B = argc > 1 ? atoll(argv[1]) : (1 << 20);
   const int cfg = argc > 2 ? atoi(argv[2]) : 2;
   const int reps = argc > 3 ? atoi(argv[3]) : 20;
-  const int H = 16;
+  const int H = argc > 4 ? atoi(argv[4]) : 16;
   nfn_chain_desc desc;
   memset(&desc, 0, sizeof(desc));
   desc.trainable_base = 1;
