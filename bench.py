@@ -543,6 +543,8 @@ def run_cfg1_pipeline(args):
     us_step = timed(lambda: model.train_step(xd, yd), K)
     model.capture_train_step(B, 1, 1)
     us_step_graph = timed(lambda: model.train_step_graphed(xd, yd), K)
+    model.capture_log_pdf(B, 1, 1)
+    us_logpdf_graph = timed(lambda: model.log_pdf_graphed(xd, yd), K)
     # host-side pipeline: numpy in, numpy out, copies included
     t0 = time.perf_counter()
     for _ in range(K):
@@ -589,7 +591,7 @@ def run_cfg1_pipeline(args):
         "config": {"workload": "NormalizingFlowNetwork 3 radial flows, 1-D y, MLP (16,16) tanh, "
                                "gen_cosine_noise_data(2048, 0.3, 0.5), batch 2048"},
         "value": us_step_graph, "ms_per_step": us_step_graph * 1e-3, "vs_baseline": None,
-        "log_pdf_us": us_logpdf, "log_pdf_host_in_host_out_us": us_logpdf_e2e,
+        "log_pdf_us": us_logpdf, "log_pdf_cuda_graph_us": us_logpdf_graph, "log_pdf_host_in_host_out_us": us_logpdf_e2e,
         "fit_step_eager_us": us_step, "fit_step_cuda_graph_us": us_step_graph,
         "samples_per_s_fit_graph": B / (us_step_graph * 1e-6), "samples_per_s_log_pdf": B / (us_logpdf * 1e-6),
         "cpu_baseline": {"kind": "port", "cores": os.cpu_count(), "log_pdf_us": us_cpu_logpdf,

@@ -195,3 +195,20 @@ def test_pdf_grid_matches_per_line_pdf(cuda_device):
     for j in range(21):
         line = model.pdf(xs, np.full_like(xs, ys[j, 0])).cpu().numpy()
         np.testing.assert_allclose(grid[j], line, rtol=2e-5, atol=1e-7)
+
+
+def test_cuda_graph_log_pdf_matches_eager(cuda_device):
+    """Graph-captured scoring (config 1 is launch-latency-bound) returns exactly the eager result and
+    follows in-place weight updates."""
+    from normalizingflownetwork_b200.estimators import NormalizingFlowNetwork
+
+    x, y = _cosine(2048)
+    model = NormalizingFlowNetwork.build_function(n_dims=1, n_flows=3, hidden_sizes=(16, 16), activation="tanh")
+    model.fit(x, y, batch_size=512, epochs=2, verbose=0)
+    xd, yd = model._to_dev(x), model._to_dev(y)
+    model.capture_log_pdf(2048, 1, 1)
+    assert torch.equal(model.log_pdf_graphed(xd, yd), model.log_pdf(xd, yd))
+    model.fit(x, y, batch_size=512, epochs=1, verbose=0)   # in-place updates: the graph sees the new weights
+    assert torch.equal(model.log_pdf_graphed(xd, yd), model.log_pdf(xd, yd))
+    perm = torch.randperm(2048, device=xd.device)
+    assert torch.equal(model.log_pdf_graphed(xd[perm], yd[perm]), model.log_pdf(xd[perm], yd[perm]))
