@@ -301,10 +301,13 @@ static int dense_dispatch(const nfn_chain_desc* desc, int hidden, const DenseArg
   // fallback if the tcgen05 kernel cannot be built for a chain).  Measured, B = 2^20, H = 16, tcgen05 vs mma.sync:
   //   fwd+bwd  P = 48: 88-92 vs 172 us   P = 32: 73 vs 131 us   P = 17: 68 vs 87 us   P = 11: 57 vs 66 us
   //   forward  P = 48: 33 vs  72 us   P = 32: 33 vs  53 us   P = 17: 27 vs 40 us   P = 11: 24 vs 31 us
-  // NFN_B200_DENSE_MMA=tc5|sync forces one of them (A/B comparisons, tests).
+  // Small launches are latency-bound and the tcgen05 kernel has the longer prologue (TMEM allocation, split
+  // weight tiles, a one-tile pipeline delay): B = 2048..16384 rows 8.4 vs 6.2 us (P = 11), 10.8 vs 10.3 us
+  // (P = 48); the crossover tracks rows x parameters, so tcgen05 takes launches with B * P >= 4 M (fwd+bwd) /
+  // 1 M (forward).  NFN_B200_DENSE_MMA=tc5|sync forces one of them (A/B comparisons, tests).
   const char* ev = getenv("NFN_B200_DENSE_MMA");
   const bool force5 = ev && strcmp(ev, "tc5") == 0, force_sync = ev && strcmp(ev, "sync") == 0;
-  const bool want5 = force5 || !force_sync;
+  const bool want5 = force5 || (!force_sync && a.B * (long long)param_size(desc) >= (bwd ? (4ll << 20) : (1ll << 20)));
   if (want5 && k && k->fn5[mode][bwd ? 1 : 0]) return cuda_error(k->fn5[mode][bwd ? 1 : 0](a, st), key.c_str());
   bool served = false;
   if (want5 && !(k && k->fn[mode][bwd ? 1 : 0] && !force5)) {
