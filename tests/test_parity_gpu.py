@@ -494,7 +494,8 @@ def test_outputs_stay_inside_their_buffers(cuda_device, nfn_lib, kernel_path):
         ft, d, tb = CONFIG_CHAINS["cfg2"]
         desc = _lib.make_desc(ft, d, tb)
         H, P = 16, 48
-        for B in (1, 33, 129, 1000):
+        for impl, B in [(i, b) for i in ("sync", "tc5") for b in (1, 33, 129, 1000, 128 * 300 + 5)]:
+            os.environ["NFN_B200_DENSE_MMA"] = impl   # both GEMM implementations (warp-level mma.sync; tcgen05 / TMEM)
             h = torch.tanh(torch.randn((B, H), generator=g, device=cuda_device))
             W = torch.randn((H, P), generator=g, device=cuda_device) * 0.1
             bias = torch.zeros(P, device=cuda_device)
@@ -510,7 +511,9 @@ def test_outputs_stay_inside_their_buffers(cuda_device, nfn_lib, kernel_path):
                 ctypes.c_float(1.0), _lib.ptr(lp), _lib.ptr(dh), _lib.ptr(dW), _lib.ptr(db), None, B,
                 _lib.current_stream(cuda_device)))
             torch.cuda.synchronize()
-            assert intact(b_lp, B) and intact(b_dh, B * H) and intact(b_dw, H * P) and intact(b_db, P), B
+            assert intact(b_lp, B) and intact(b_dh, B * H) and intact(b_dw, H * P) and intact(b_db, P), (impl, B)
+            assert torch.isfinite(lp).all() and torch.isfinite(dh).all() and torch.isfinite(dW).all(), (impl, B)
+        os.environ.pop("NFN_B200_DENSE_MMA", None)
         K, dm = 20, 2
         Pm = 2 * K * dm + K
         for B in (1, 129, 1000):
