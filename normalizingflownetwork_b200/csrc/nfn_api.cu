@@ -61,6 +61,14 @@ int math_mode() {
   return g_math_mode;
 }
 
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* ev = getenv("NFN_B200_PDL");
+    return !(ev && strcmp(ev, "0") == 0);
+  }();
+  return on;
+}
+
 // ------------------------------------------------------------------ registry
 static std::unordered_map<std::string, ChainKernels>& registry() {
   static std::unordered_map<std::string, ChainKernels> r;

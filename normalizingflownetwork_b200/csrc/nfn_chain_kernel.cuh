@@ -505,6 +505,12 @@ NFN_DEVI void chain_body(const ChainArgs& a) {
   }
   double lsum = 0.0;
 
+  // Programmatic dependent launch (no-ops unless the launch asked for it, see launch_chain): the next
+  // launch in the stream may be scheduled onto SMs as this grid's CTAs retire, and this grid touches global
+  // memory only after everything before it in the stream has completed and flushed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
   const unsigned smem_base = smem_u32(smem);
   constexpr unsigned kBufBytes = (unsigned)(T * S * sizeof(float));
   long long tile = blockIdx.x;

@@ -31,6 +31,8 @@ const DeviceInfo& device_info();
 
 // Math mode: 0 = fast (MUFU-based, default), 1 = accurate (CUDA libm + IEEE division).
 int math_mode();
+// Programmatic dependent launch for the specialised chain kernels (NFN_B200_PDL=0 turns it off).
+bool pdl_enabled();
 
 typedef cudaError_t (*ChainLaunchFn)(const ChainArgs&, cudaStream_t);
 
@@ -94,6 +96,24 @@ cudaError_t launch_chain(const ChainArgs& a, cudaStream_t st) {
   const long long ntiles = (a.B + T - 1) / T;
   long long grid = (long long)di.sm_count * cfg.ctas_per_sm;
   if (grid > ntiles) grid = ntiles;
+  if (pdl_enabled()) {
+    // programmatic dependent launch: this grid's CTAs may be scheduled while the previous launch in the
+    // stream is still retiring; the kernel waits (griddepcontrol.wait) before its first global access
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)grid);
+    lc.blockDim = dim3((unsigned)T);
+    lc.dynamicSmemBytes = kSmem;
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&lc, kern, a);
+    if (e != cudaSuccess) return e;
+    count_launch();
+    return cudaGetLastError();
+  }
   kern<<<(unsigned)grid, T, kSmem, st>>>(a);
   count_launch();
   return cudaGetLastError();
