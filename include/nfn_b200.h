@@ -181,6 +181,23 @@ int64_t nfn_jit_dense_compile_check(const nfn_chain_desc* desc, int hidden, int 
 int64_t nfn_jit_dense_tc5_compile_check(const nfn_chain_desc* desc, int hidden, int accurate);
 
 /*
+ * One hidden layer of the conditioning network, `Dense(units, activation)` (reference
+ * estimators/MaximumLikelihoodNNEstimator.py:37-44), as one kernel each way:
+ *   forward   out[B, N] = act(x[B, K] weight^T + bias)
+ *   backward  dpre = dout * act'(out);  dx[B, K] = dpre weight (NULL: not wanted);  dweight += dpre^T x;
+ *             dbias += sum_b dpre
+ * weight is [N, K] row-major (out_features x in_features); act: 0 linear, 1 tanh, 2 relu, 3 sigmoid, 4 elu.
+ * 1 <= K <= 64 and N in {8, 16, 32, 64}: nfn_dense_act_supported tells; other shapes stay with the caller's
+ * GEMM library.  All row pointers 16-byte aligned when K (resp. N) is a multiple of 4.
+ */
+int nfn_dense_act_supported(int in_features, int units, int act);
+int nfn_dense_act_forward(const float* x, const float* weight, const float* bias, int64_t B, int in_features,
+                          int units, int act, float* out, void* stream);
+int nfn_dense_act_backward(const float* x, const float* out, const float* dout, const float* weight, int64_t B,
+                           int in_features, int units, int act, float* dx, float* dweight, float* dbias,
+                           void* stream);
+
+/*
  * One bijector on its own: Flow(t, n_dims).forward(z) and ._forward_log_det_jacobian(z)
  * (PlanarFlow.py:68-80, RadialFlow.py:51-70, AffineFlow.py:7-9), the calls made by
  * tests/test_flows.py:19-41.  t [B, size(flow)], z [z_rows, d] (z_rows == B or 1),

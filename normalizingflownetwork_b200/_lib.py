@@ -77,6 +77,12 @@ SIGNATURES = {
                                                        _c_float_p, ctypes.c_void_p, _i64, ctypes.c_void_p]),
     "nfn_jit_dense_compile_check": (_i64, [ctypes.POINTER(ChainDesc), ctypes.c_int, ctypes.c_int]),
     "nfn_jit_dense_tc5_compile_check": (_i64, [ctypes.POINTER(ChainDesc), ctypes.c_int, ctypes.c_int]),
+    "nfn_dense_act_supported": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "nfn_dense_act_forward": (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, _i64, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_int, _c_float_p, ctypes.c_void_p]),
+    "nfn_dense_act_backward": (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, _c_float_p, _i64, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p,
+                                             ctypes.c_void_p]),
     "nfn_flow_forward": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _i64,
                                        _c_float_p, _c_float_p, _i64, ctypes.c_void_p]),
     "nfn_mdn_forward": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _i64,

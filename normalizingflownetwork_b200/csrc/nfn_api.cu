@@ -394,6 +394,39 @@ int64_t nfn_jit_dense_compile_check(const nfn_chain_desc* desc, int hidden, int 
   return n;
 }
 
+int nfn_dense_act_supported(int in_features, int units, int act) {
+  return mlp_layer_supported(in_features, units, act);
+}
+
+int nfn_dense_act_forward(const float* x, const float* weight, const float* bias, int64_t B, int in_features,
+                          int units, int act, float* out, void* stream) {
+  if (!mlp_layer_supported(in_features, units, act))
+    return set_error(NFN_ERR_UNSUPPORTED, "dense layer %d -> %d (act %d) is outside the fused kernels' range", in_features,
+                     units, act);
+  if (B < 0) return set_error(NFN_ERR_SHAPE, "B=%lld", (long long)B);
+  if (B == 0) return NFN_OK;
+  if (!x || !weight || !bias || !out) return set_error(NFN_ERR_NULL, "x, weight, bias and out must be non-NULL");
+  if (!aligned(out, 16) || (in_features % 4 == 0 && !aligned(x, 16)))
+    return set_error(NFN_ERR_ALIGN, "x and out must be 16-byte aligned");
+  return launch_dense_act_forward(x, weight, bias, out, B, in_features, units, act, (cudaStream_t)stream);
+}
+
+int nfn_dense_act_backward(const float* x, const float* out, const float* dout, const float* weight, int64_t B,
+                           int in_features, int units, int act, float* dx, float* dweight, float* dbias,
+                           void* stream) {
+  if (!mlp_layer_supported(in_features, units, act))
+    return set_error(NFN_ERR_UNSUPPORTED, "dense layer %d -> %d (act %d) is outside the fused kernels' range", in_features,
+                     units, act);
+  if (B < 0) return set_error(NFN_ERR_SHAPE, "B=%lld", (long long)B);
+  if (B == 0) return NFN_OK;
+  if (!x || !out || !dout || !weight || !dweight || !dbias)
+    return set_error(NFN_ERR_NULL, "x, out, dout, weight, dweight and dbias must be non-NULL");
+  if (!aligned(out, 16) || !aligned(dout, 16) || (in_features % 4 == 0 && !aligned(x, 16)))
+    return set_error(NFN_ERR_ALIGN, "x, out and dout must be 16-byte aligned");
+  return launch_dense_act_backward(x, out, dout, weight, dx, dweight, dbias, B, in_features, units, act,
+                                   (cudaStream_t)stream);
+}
+
 int nfn_flow_forward(int flow_type, int n_dims, const float* t, const float* z, int64_t z_rows,
                      float* z_out, float* fldj, int64_t B, void* stream) {
   if (flow_type < 0 || flow_type > NFN_FLOW_AFFINE)

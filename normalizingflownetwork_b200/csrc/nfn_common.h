@@ -271,4 +271,11 @@ int launch_kmn(int d, bool bwd, const MixArgs& a, cudaStream_t st);
 int launch_logmeanexp(const float* in, long long S, long long B, float* out, cudaStream_t st);
 int launch_colsum(const float* dt, long long B, int P, double* out, cudaStream_t st);
 
+// hidden layers of the conditioning network (nfn_mlp.cu)
+int mlp_layer_supported(int K, int N, int act);
+int launch_dense_act_forward(const float* x, const float* w, const float* b, float* out, long long B, int K, int N,
+                             int act, cudaStream_t st);
+int launch_dense_act_backward(const float* x, const float* out, const float* dout, const float* w, float* dx,
+                              float* dW, float* db, long long B, int K, int N, int act, cudaStream_t st);
+
 }  // namespace nfn

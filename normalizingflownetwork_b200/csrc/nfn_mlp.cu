@@ -1,0 +1,375 @@
+// nfn_mlp.cu -- the hidden layers of the conditioning network (sm_100a).
+//
+// SURVEY.md §8(f) rank 1 continued: once the emitting Dense(P) layer and the flow chain are one kernel
+// (nfn_dense_tc5.cuh), an estimator-level step at a large batch is dominated by the 16..64-wide hidden
+// layers around it -- `Dense(units, activation)` of MaximumLikelihoodNNEstimator.py:37-44 -- which cuBLAS
+// serves with skinny SIMT GEMMs plus separate bias / activation / reduction kernels (measured at
+// B = 2^20: ~900 us of a 960 us train step, next to a 73 us fused head kernel).  Here one layer is one
+// kernel each way, row per thread, weights in shared memory (every weight read is a warp broadcast):
+//
+//   forward   out = act(x W^T + b)                                 reads 4K, writes 4N bytes per row
+//   backward  dpre = dout * act'(out);  dx = dpre W;  dW += dpre^T x;  db += 1^T dpre
+//
+// fp32 throughout (the layers are tiny; exactness matters more than tensor-core throughput here).
+// `weight` is torch's / Keras-transposed layout [N][K] (out_features x in_features).
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "nfn_common.h"
+
+namespace nfn {
+namespace {
+
+enum Act { kLinear = 0, kTanh = 1, kRelu = 2, kSigmoid = 3, kElu = 4 };
+
+template <int ACT>
+__device__ __forceinline__ float act_fwd(float a) {
+  if constexpr (ACT == kTanh) return tanhf(a);
+  else if constexpr (ACT == kRelu) return a > 0.0f ? a : 0.0f;
+  else if constexpr (ACT == kSigmoid) return 1.0f / (1.0f + expf(-a));
+  else if constexpr (ACT == kElu) return a > 0.0f ? a : expm1f(a);
+  else return a;
+}
+// derivative written in terms of the OUTPUT o = act(a), so the backward pass needs no pre-activations
+template <int ACT>
+__device__ __forceinline__ float act_bwd(float o) {
+  if constexpr (ACT == kTanh) return 1.0f - o * o;
+  else if constexpr (ACT == kRelu) return o > 0.0f ? 1.0f : 0.0f;
+  else if constexpr (ACT == kSigmoid) return o * (1.0f - o);
+  else if constexpr (ACT == kElu) return o > 0.0f ? 1.0f : o + 1.0f;
+  else return 1.0f;
+}
+
+constexpr int kT = 128;  // rows per tile == threads per CTA
+
+// Cooperative, fully coalesced copy of a tile of kT rows x C floats between global [B][C] and shared [kT][S]:
+// consecutive threads move consecutive 16-byte chunks (row-per-thread global access at a 64-byte row stride
+// touches 32 sectors per warp instruction and was the bottleneck of the first version of these kernels).
+// Rows past B are zero-filled on the way in and skipped on the way out.
+template <bool TO_SMEM>
+__device__ __forceinline__ void tile_copy(float* s, int S, float* g, long long row0, long long B, int C) {
+  if (C % 4 == 0) {
+    const int C4 = C / 4;
+    for (int q = threadIdx.x; q < kT * C4; q += kT) {
+      const int r = q / C4, c = q - r * C4;
+      float4* sp = reinterpret_cast<float4*>(s + r * S + 4 * c);
+      if (row0 + r < B) {
+        float4* gp = reinterpret_cast<float4*>(g + (row0 + r) * C + 4 * c);
+        if (TO_SMEM) *sp = __ldg(reinterpret_cast<const float4*>(gp)); else *gp = *sp;
+      } else if (TO_SMEM) {
+        *sp = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  } else {
+    for (int e = threadIdx.x; e < kT * C; e += kT) {
+      const int r = e / C, c = e - r * C;
+      if (row0 + r < B) {
+        if (TO_SMEM) s[r * S + c] = __ldg(g + (row0 + r) * C + c); else g[(row0 + r) * C + c] = s[r * S + c];
+      } else if (TO_SMEM) {
+        s[r * S + c] = 0.0f;
+      }
+    }
+  }
+}
+
+__host__ __device__ constexpr int pad4(int n) { return (n + 3) / 4 * 4; }
+
+// ---------------------------------------------------------------- forward
+template <int N, int ACT>
+__global__ void __launch_bounds__(kT) dense_act_fwd(const float* __restrict__ x, const float* __restrict__ weight,
+                                                   const float* __restrict__ bias, float* __restrict__ out,
+                                                   long long B, int K) {
+  extern __shared__ __align__(16) float smem[];
+  const int SX = pad4(K) + 4;
+  constexpr int SO = N + 4;
+  float* sW = smem;                    // [K][N]  (transposed while loading)
+  float* sb = sW + pad4(K * N);        // [N]
+  float* sX = sb + N;                  // [kT][SX]
+  float* sO = sX + kT * SX;            // [kT][SO]
+  for (int i = threadIdx.x; i < K * N; i += kT) {
+    const int n = i / K, k = i % K;    // coalesced read of weight[n][k]
+    sW[k * N + n] = __ldg(weight + i);
+  }
+  for (int i = threadIdx.x; i < N; i += kT) sb[i] = __ldg(bias + i);
+  const long long ntiles = (B + kT - 1) / kT;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * kT;
+    tile_copy<true>(sX, SX, const_cast<float*>(x), row0, B, K);
+    __syncthreads();   // (also covers the weights on the first tile)
+    float acc[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) acc[n] = sb[n];
+    const float* xr = sX + threadIdx.x * SX;
+    for (int k = 0; k < K; ++k) {
+      const float a = xr[k];
+      const float4* w = reinterpret_cast<const float4*>(sW + k * N);
+#pragma unroll
+      for (int c = 0; c < N / 4; ++c) {
+        const float4 wv = w[c];
+        acc[4 * c] = fmaf(a, wv.x, acc[4 * c]);
+        acc[4 * c + 1] = fmaf(a, wv.y, acc[4 * c + 1]);
+        acc[4 * c + 2] = fmaf(a, wv.z, acc[4 * c + 2]);
+        acc[4 * c + 3] = fmaf(a, wv.w, acc[4 * c + 3]);
+      }
+    }
+    float4* o = reinterpret_cast<float4*>(sO + threadIdx.x * SO);
+#pragma unroll
+    for (int c = 0; c < N / 4; ++c)
+      o[c] = make_float4(act_fwd<ACT>(acc[4 * c]), act_fwd<ACT>(acc[4 * c + 1]), act_fwd<ACT>(acc[4 * c + 2]),
+                         act_fwd<ACT>(acc[4 * c + 3]));
+    __syncthreads();
+    tile_copy<false>(sO, SO, out, row0, B, N);
+    // the next iteration's sX fill cannot overtake this tile's reads of sX (they ended at the barrier above);
+    // its sO writes come after its own first barrier, i.e. after every thread has left this copy
+  }
+}
+
+// ---------------------------------------------------------------- backward
+// Per tile of kT rows: x, dout and out arrive in shared memory with coalesced copies; every thread forms dpre
+// for its row (written back over dout) and its dx row (written over out, stored with a coalesced copy).  The
+// weight gradient dW[n][k] = sum_r dpre[r][n] x[r][k] is register-tiled: the K x N entries are cut into
+// 4 x 4 blocks; a thread owns PER blocks (1 or 2) and one slice of the tile's rows, and per row reads one
+// float4 of x and one float4 of dpre for 16 FMAs.  Accumulators live in registers for the whole kernel; the
+// slices meet in shared memory at the end: one global atomic per entry per CTA.
+template <int N, int ACT, int PER>
+__global__ void __launch_bounds__(kT, 4) dense_act_bwd(const float* __restrict__ x, const float* __restrict__ out,
+                                                      const float* __restrict__ dout, const float* __restrict__ weight,
+                                                      float* __restrict__ dx, float* __restrict__ dW,
+                                                      float* __restrict__ db, long long B, int K) {
+  extern __shared__ __align__(16) float smem[];
+  const int K4 = (K + 3) / 4;
+  constexpr int N4 = N / 4;
+  const int SX = 4 * K4 + 4;                       // float4-aligned rows; the +4 skews the banks between rows
+  constexpr int SD = N + 4;
+  const int SO = (N > 4 * K4 ? N : 4 * K4) + 4;    // holds the out row, then the dx row
+  float* sW = smem;                                // [K][N]
+  float* sX = sW + pad4(K * N);                    // [kT][SX]   (columns K .. 4 K4 - 1 are zero)
+  float* sD = sX + kT * SX;                        // [kT][SD]   dout, then dpre
+  float* sO = sD + kT * SD;                        // [kT][SO]   out, then dx
+  for (int i = threadIdx.x; i < K * N; i += kT) {
+    const int n = i / K, k = i % K;
+    sW[k * N + n] = __ldg(weight + i);
+  }
+  if (K % 4 != 0) {                                // the pad columns of x stay zero for the whole kernel
+    for (int e = threadIdx.x; e < kT * SX; e += kT) sX[e] = 0.0f;
+  }
+  // ownership of the 4 x 4 blocks
+  const int G = K4 * N4;                           // blocks
+  const int Gt = (G + PER - 1) / PER;              // threads per row slice
+  const int S = kT / Gt > 0 ? kT / Gt : 1;         // row slices
+  const int R = (kT + S - 1) / S;                  // rows per slice
+  const int slice = threadIdx.x / Gt, member = threadIdx.x % Gt;
+  const bool active = slice < S;
+  const int r_lo = slice * R, r_hi = (r_lo + R < kT) ? r_lo + R : kT;
+  float gw[PER][16], gb[N];
+#pragma unroll
+  for (int j = 0; j < PER; ++j)
+#pragma unroll
+    for (int e = 0; e < 16; ++e) gw[j][e] = 0.0f;
+#pragma unroll
+  for (int n = 0; n < N; ++n) gb[n] = 0.0f;
+  __syncthreads();
+  const long long ntiles = (B + kT - 1) / kT;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * kT;
+    tile_copy<true>(sX, SX, const_cast<float*>(x), row0, B, K);
+    tile_copy<true>(sD, SD, const_cast<float*>(dout), row0, B, N);
+    tile_copy<true>(sO, SO, const_cast<float*>(out), row0, B, N);
+    __syncthreads();
+    {
+      float dpre[N];
+      float4* myd = reinterpret_cast<float4*>(sD + threadIdx.x * SD);
+      float4* myo = reinterpret_cast<float4*>(sO + threadIdx.x * SO);
+#pragma unroll
+      for (int c = 0; c < N4; ++c) {
+        const float4 g = myd[c], o = myo[c];       // rows past B are zero: dpre = 0
+        dpre[4 * c] = g.x * act_bwd<ACT>(o.x);
+        dpre[4 * c + 1] = g.y * act_bwd<ACT>(o.y);
+        dpre[4 * c + 2] = g.z * act_bwd<ACT>(o.z);
+        dpre[4 * c + 3] = g.w * act_bwd<ACT>(o.w);
+        myd[c] = make_float4(dpre[4 * c], dpre[4 * c + 1], dpre[4 * c + 2], dpre[4 * c + 3]);
+      }
+#pragma unroll
+      for (int n = 0; n < N; ++n) gb[n] += dpre[n];
+      if (dx != nullptr) {
+        float* mydx = sO + threadIdx.x * SO;
+        for (int k = 0; k < K; ++k) {
+          const float4* w = reinterpret_cast<const float4*>(sW + k * N);
+          float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+          for (int c = 0; c < N4; ++c) {
+            const float4 wv = w[c];
+            s0 = fmaf(dpre[4 * c], wv.x, s0);
+            s1 = fmaf(dpre[4 * c + 1], wv.y, s1);
+            s0 = fmaf(dpre[4 * c + 2], wv.z, s0);
+            s1 = fmaf(dpre[4 * c + 3], wv.w, s1);
+          }
+          mydx[k] = s0 + s1;
+        }
+      }
+    }
+    __syncthreads();
+    if (dx != nullptr) tile_copy<false>(sO, SO, dx, row0, B, K);
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        const int blk = member * PER + j;
+        if (blk < G) {
+          const int k4 = blk / N4, n4 = blk % N4;
+          const float* px = sX + 4 * k4;
+          const float* pd = sD + 4 * n4;
+#pragma unroll 4
+          for (int rr = r_lo; rr < r_hi; ++rr) {
+            const float4 xv = *reinterpret_cast<const float4*>(px + rr * SX);
+            const float4 dv = *reinterpret_cast<const float4*>(pd + rr * SD);
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 4; ++b) gw[j][4 * a + b] = fmaf(xs[a], ds[b], gw[j][4 * a + b]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // the row slices' partial sums meet in shared memory (the staging tiles are free now), so that every
+  // weight-gradient entry costs ONE global atomic per CTA
+  float* sAcc = sX;                                // [S][G * 16] <= kT * PER * 16 floats, inside sX | sD | sO
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int blk = member * PER + j;
+      if (blk < G) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) sAcc[(slice * G + blk) * 16 + e] = gw[j][e];
+      }
+    }
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < G * 16; o += kT) {
+    float v = 0.0f;
+    for (int sl = 0; sl < S; ++sl) v += sAcc[sl * G * 16 + o];
+    const int blk = o / 16, e = o % 16;
+    const int k = 4 * (blk / N4) + e / 4, n = 4 * (blk % N4) + e % 4;
+    if (k < K) atomicAdd(dW + n * K + k, v);
+  }
+  // bias gradient: warp shuffle reduction, one atomic per warp per column
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    float v = gb[n];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if ((threadIdx.x & 31) == 0) atomicAdd(db + n, v);
+  }
+}
+
+template <int N, int ACT>
+cudaError_t launch_fwd(const float* x, const float* w, const float* b, float* out, long long B, int K, cudaStream_t st) {
+  const DeviceInfo& di = device_info();
+  const size_t smem = (size_t)(pad4(K * N) + N + kT * (pad4(K) + 4) + kT * (N + 4)) * sizeof(float);
+  auto kern = dense_act_fwd<N, ACT>;
+  static thread_local int configured_for = -1;
+  if (configured_for != di.device) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    if (e != cudaSuccess) return e;
+    configured_for = di.device;
+  }
+  const long long ntiles = (B + kT - 1) / kT;
+  long long grid = (long long)di.sm_count * 6;
+  if (grid > ntiles) grid = ntiles;
+  kern<<<(unsigned)grid, kT, smem, st>>>(x, w, b, out, B, K);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <int N, int ACT, int PER>
+cudaError_t launch_bwd(const float* x, const float* out, const float* dout, const float* w, float* dx, float* dW, float* db,
+                       long long B, int K, cudaStream_t st) {
+  const DeviceInfo& di = device_info();
+  const int K4 = (K + 3) / 4;
+  const int so = (N > 4 * K4 ? N : 4 * K4) + 4;
+  const size_t smem = (size_t)(pad4(K * N) + kT * (4 * K4 + 4) + kT * (N + 4) + kT * so) * sizeof(float);
+  auto kern = dense_act_bwd<N, ACT, PER>;
+  static thread_local int configured_for = -1;
+  if (configured_for != di.device) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    if (e != cudaSuccess) return e;
+    configured_for = di.device;
+  }
+  const long long ntiles = (B + kT - 1) / kT;
+  long long grid = (long long)di.sm_count * 4;
+  if (grid > ntiles) grid = ntiles;
+  kern<<<(unsigned)grid, kT, smem, st>>>(x, out, dout, w, dx, dW, db, B, K);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <int N>
+cudaError_t dispatch_fwd(int act, const float* x, const float* w, const float* b, float* out, long long B, int K,
+                         cudaStream_t st) {
+  switch (act) {
+    case kLinear: return launch_fwd<N, kLinear>(x, w, b, out, B, K, st);
+    case kTanh: return launch_fwd<N, kTanh>(x, w, b, out, B, K, st);
+    case kRelu: return launch_fwd<N, kRelu>(x, w, b, out, B, K, st);
+    case kSigmoid: return launch_fwd<N, kSigmoid>(x, w, b, out, B, K, st);
+    default: return launch_fwd<N, kElu>(x, w, b, out, B, K, st);
+  }
+}
+
+template <int N, int PER>
+cudaError_t dispatch_bwd(int act, const float* x, const float* out, const float* dout, const float* w, float* dx,
+                         float* dW, float* db, long long B, int K, cudaStream_t st) {
+  switch (act) {
+    case kLinear: return launch_bwd<N, kLinear, PER>(x, out, dout, w, dx, dW, db, B, K, st);
+    case kTanh: return launch_bwd<N, kTanh, PER>(x, out, dout, w, dx, dW, db, B, K, st);
+    case kRelu: return launch_bwd<N, kRelu, PER>(x, out, dout, w, dx, dW, db, B, K, st);
+    case kSigmoid: return launch_bwd<N, kSigmoid, PER>(x, out, dout, w, dx, dW, db, B, K, st);
+    default: return launch_bwd<N, kElu, PER>(x, out, dout, w, dx, dW, db, B, K, st);
+  }
+}
+
+}  // namespace
+
+int mlp_layer_supported(int K, int N, int act) {
+  return K >= 1 && K <= 64 && (N == 8 || N == 16 || N == 32 || N == 64) && act >= 0 && act <= 4;
+}
+
+int launch_dense_act_forward(const float* x, const float* w, const float* b, float* out, long long B, int K, int N,
+                             int act, cudaStream_t st) {
+  cudaError_t e;
+  switch (N) {
+    case 8: e = dispatch_fwd<8>(act, x, w, b, out, B, K, st); break;
+    case 16: e = dispatch_fwd<16>(act, x, w, b, out, B, K, st); break;
+    case 32: e = dispatch_fwd<32>(act, x, w, b, out, B, K, st); break;
+    default: e = dispatch_fwd<64>(act, x, w, b, out, B, K, st); break;
+  }
+  return cuda_error(e, "dense_act_fwd");
+}
+
+int launch_dense_act_backward(const float* x, const float* out, const float* dout, const float* w, float* dx,
+                              float* dW, float* db, long long B, int K, int N, int act, cudaStream_t st) {
+  cudaError_t e;
+  // 4 x 4 blocks of the weight gradient per thread: one while ceil(K/4) * N/4 <= 128, else two (K * N <= 4096)
+  const int G = ((K + 3) / 4) * (N / 4);
+  if (G <= kT) {
+    switch (N) {
+      case 8: e = dispatch_bwd<8, 1>(act, x, out, dout, w, dx, dW, db, B, K, st); break;
+      case 16: e = dispatch_bwd<16, 1>(act, x, out, dout, w, dx, dW, db, B, K, st); break;
+      case 32: e = dispatch_bwd<32, 1>(act, x, out, dout, w, dx, dW, db, B, K, st); break;
+      default: e = dispatch_bwd<64, 1>(act, x, out, dout, w, dx, dW, db, B, K, st); break;
+    }
+  } else {
+    switch (N) {
+      case 8: e = dispatch_bwd<8, 2>(act, x, out, dout, w, dx, dW, db, B, K, st); break;
+      case 16: e = dispatch_bwd<16, 2>(act, x, out, dout, w, dx, dW, db, B, K, st); break;
+      case 32: e = dispatch_bwd<32, 2>(act, x, out, dout, w, dx, dW, db, B, K, st); break;
+      default: e = dispatch_bwd<64, 2>(act, x, out, dout, w, dx, dW, db, B, K, st); break;
+    }
+  }
+  return cuda_error(e, "dense_act_bwd");
+}
+
+}  // namespace nfn

@@ -2,6 +2,7 @@
 (reference estimators/MaximumLikelihoodNNEstimator.py)."""
 import torch
 
+from .. import functional as F
 from .BaseEstimator import BaseEstimator, _GaussianNoise, _Normalise
 
 ACTIVATIONS = {"relu": torch.nn.ReLU, "tanh": torch.nn.Tanh, "linear": torch.nn.Identity,
@@ -15,8 +16,10 @@ class _Dense(torch.nn.Module):
         super().__init__()
         self.linear = torch.nn.LazyLinear(units)
         self.act = ACTIVATIONS[activation]()
+        self._activation = activation
         self._init = False
         self._seed = seed
+        self.fused = False  # one kernel each way for the layer (csrc/nfn_mlp.cu) when its shape allows
 
     def forward(self, x):
         if not self._init:
@@ -30,7 +33,11 @@ class _Dense(torch.nn.Module):
                 self.linear.weight.copy_(w)
                 self.linear.bias.zero_()
             self._init = True
-        return self.act(self.linear(x))
+        lin = self.linear
+        if (self.fused and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
+                and F.dense_act_supported(lin.in_features, lin.out_features, self._activation)):
+            return F.dense_act(x.contiguous(), lin.weight, lin.bias, self._activation)
+        return self.act(lin(x))
 
 
 class MaximumLikelihoodNNEstimator(BaseEstimator):

@@ -151,6 +151,76 @@ def chain_forward_backward_peer(t, y, flow_types, n_dims, trainable_base_dist, c
     return logp, dt, reduced
 
 
+# ----------------------------------------------------------------------------- hidden layers of the MLP
+ACT_CODES = {"linear": 0, "tanh": 1, "relu": 2, "sigmoid": 3, "elu": 4}
+
+
+def dense_act_supported(in_features, units, activation):
+    """True when one fused kernel each way can serve ``Dense(units, activation)`` on ``in_features`` inputs."""
+    if activation not in ACT_CODES:
+        return False
+    return bool(_lib.load().nfn_dense_act_supported(int(in_features), int(units), ACT_CODES[activation]))
+
+
+def dense_act_forward(x, weight, bias, activation):
+    """act(x @ weight.T + bias) in one kernel; weight is torch's [units, in_features]."""
+    lib = _lib.load()
+    x = _aligned(_as_f32_cuda(x, "x"))
+    weight = _as_f32_cuda(weight, "weight", device=x.device)
+    bias = _as_f32_cuda(bias, "bias", device=x.device)
+    B, K = x.shape
+    N = weight.shape[0]
+    assert tuple(weight.shape) == (N, K) and tuple(bias.shape) == (N,)
+    out = torch.empty((B, N), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.nfn_dense_act_forward(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias), B, K, N,
+                                             ACT_CODES[activation], _lib.ptr(out), _lib.current_stream(x.device)))
+    return out
+
+
+def dense_act_backward(x, out, dout, weight, activation, need_dx=True):
+    """Gradients of dense_act_forward given the layer's OUTPUT: returns (dx or None, dweight, dbias)."""
+    lib = _lib.load()
+    x = _aligned(_as_f32_cuda(x, "x"))
+    dev = x.device
+    out = _aligned(_as_f32_cuda(out, "out", device=dev))
+    dout = _aligned(_as_f32_cuda(dout, "dout", device=dev))
+    weight = _as_f32_cuda(weight, "weight", device=dev)
+    B, K = x.shape
+    N = weight.shape[0]
+    dx = torch.empty((B, K), dtype=torch.float32, device=dev) if need_dx else None
+    dW = torch.zeros((N, K), dtype=torch.float32, device=dev)
+    db = torch.zeros(N, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_dense_act_backward(_lib.ptr(x), _lib.ptr(out), _lib.ptr(dout), _lib.ptr(weight), B, K, N,
+                                              ACT_CODES[activation], _lib.ptr(dx), _lib.ptr(dW), _lib.ptr(db),
+                                              _lib.current_stream(dev)))
+    return dx, dW, db
+
+
+class _DenseAct(torch.autograd.Function):
+    """Dense(units, activation) as one kernel each way (csrc/nfn_mlp.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, activation):
+        out = dense_act_forward(x, weight, bias, activation)
+        ctx.save_for_backward(x, out, weight)
+        ctx.activation = activation
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, out, weight = ctx.saved_tensors
+        dx, dW, db = dense_act_backward(x, out, dout.contiguous(), weight, ctx.activation,
+                                        need_dx=ctx.needs_input_grad[0])
+        return dx, dW, db, None
+
+
+def dense_act(x, weight, bias, activation):
+    """Differentiable fused hidden layer (forward kernel under no_grad, Function otherwise)."""
+    return _DenseAct.apply(x, weight, bias, activation)
+
+
 # ----------------------------------------------------------------------------- fused Dense(P) + chain
 def dense_chain_supported(hidden):
     return hidden in (16, 32, 48, 64)
