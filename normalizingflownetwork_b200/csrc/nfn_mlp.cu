@@ -51,8 +51,10 @@ template <bool TO_SMEM>
 __device__ __forceinline__ void tile_copy(float* s, int S, float* g, long long row0, long long B, int C) {
   if (C % 4 == 0) {
     const int C4 = C / 4;
+    // (row, chunk) advance incrementally: no division in the loop
+    int r = threadIdx.x / C4, c = threadIdx.x - r * C4;
+    const int dr = kT / C4, dc = kT - dr * C4;
     for (int q = threadIdx.x; q < kT * C4; q += kT) {
-      const int r = q / C4, c = q - r * C4;
       float4* sp = reinterpret_cast<float4*>(s + r * S + 4 * c);
       if (row0 + r < B) {
         float4* gp = reinterpret_cast<float4*>(g + (row0 + r) * C + 4 * c);
@@ -60,6 +62,9 @@ __device__ __forceinline__ void tile_copy(float* s, int S, float* g, long long r
       } else if (TO_SMEM) {
         *sp = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      r += dr;
+      c += dc;
+      if (c >= C4) { c -= C4; ++r; }
     }
   } else {
     for (int e = threadIdx.x; e < kT * C; e += kT) {

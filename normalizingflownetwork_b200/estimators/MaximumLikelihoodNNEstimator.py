@@ -19,7 +19,7 @@ class _Dense(torch.nn.Module):
         self._activation = activation
         self._init = False
         self._seed = seed
-        self.fused = False  # one kernel each way for the layer (csrc/nfn_mlp.cu) when its shape allows
+        self.fused = True   # one kernel each way for the layer (csrc/nfn_mlp.cu) when its shape allows
 
     def forward(self, x):
         if not self._init:
