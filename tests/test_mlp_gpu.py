@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("act", ["tanh", "relu", "linear", "sigmoid", "elu"])
-@pytest.mark.parametrize("K,N,B", [(1, 16, 1000), (16, 16, 4097), (3, 8, 129), (16, 32, 777), (64, 64, 300), (10, 16, 1)])
+@pytest.mark.parametrize("K,N,B", [(1, 16, 1000), (16, 16, 4097), (3, 8, 129), (16, 32, 777), (64, 64, 300), (64, 32, 300), (10, 16, 1)])
 def test_dense_act_matches_float64(cuda_device, nfn_lib, act, K, N, B):
     from normalizingflownetwork_b200 import functional as F
 
