@@ -382,7 +382,21 @@ def run_ours(args):
     total_ms = parallel.max_over_ranks(t_start.elapsed_time(t_end), device)
     kern_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev.values())
     kern_ms = parallel.max_over_ranks(kern_ms, device)
-    clocks = sampler.stop(wall0, time.perf_counter()) if rank == 0 else None
+    wall1 = time.perf_counter()
+    replay_note = None
+    if rank == 0 and sum(1 for smp in sampler.samples if wall0 <= smp[0] <= wall1) < 3 and world == 1:
+        # the timed region was shorter than three NVML polls: replay the identical launches (untimed) for
+        # ~40 ms so that the clocks are read under the same load
+        t_rep = time.perf_counter()
+        while time.perf_counter() - t_rep < 0.04:
+            for _ in range(20):
+                kernel()
+            torch.cuda.synchronize()
+        wall1 = time.perf_counter()
+        replay_note = "timed region + 40 ms untimed replay of the same launches (timed region shorter than 3 NVML polls)"
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    if clocks is not None and replay_note and clocks.get("window") == "timed region":
+        clocks["window"] = replay_note
     ms_per_step = total_ms / K
     value = B * world * K / (total_ms * 1e-3)
 
