@@ -269,14 +269,99 @@ __global__ void __launch_bounds__(kT, 4) dense_act_bwd(const float* __restrict__
     const int k = 4 * (blk / N4) + e / 4, n = 4 * (blk % N4) + e % 4;
     if (k < K) atomicAdd(dW + n * K + k, v);
   }
-  // bias gradient: warp shuffle reduction, one atomic per warp per column
+  // bias gradient: warp shuffles, then the CTA's warps meet in shared memory: one atomic per column per CTA
+  __syncthreads();   // sAcc has been read
+  float* sRed = sX;  // [kT / 32][N]
 #pragma unroll
   for (int n = 0; n < N; ++n) {
     float v = gb[n];
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    if ((threadIdx.x & 31) == 0) atomicAdd(db + n, v);
+    if ((threadIdx.x & 31) == 0) sRed[(threadIdx.x >> 5) * N + n] = v;
   }
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += kT) {
+    float v = 0.0f;
+#pragma unroll
+    for (int wi = 0; wi < kT / 32; ++wi) v += sRed[wi * N + n];
+    atomicAdd(db + n, v);
+  }
+}
+
+// ---------------------------------------------------------------- backward, first layer
+// The first layer of the network has few inputs (the conditioning variable: K = 1 .. 4) and nobody wants its
+// input gradient: what is left is a streaming reduction -- dW[n][k] = sum_r dpre[r][n] x[r][k], db[n] =
+// sum_r dpre[r][n] -- which each thread accumulates in registers over its rows; warps meet with shuffles,
+// one atomic per entry per warp at the end.  No shared memory, no barriers.
+template <int N, int ACT, int KS>
+__global__ void __launch_bounds__(kT) dense_act_bwd_first(const float* __restrict__ x, const float* __restrict__ out,
+                                                         const float* __restrict__ dout, float* __restrict__ dW,
+                                                         float* __restrict__ db, long long B, int K) {
+  float gw[KS][N], gb[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    gb[n] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) gw[k][n] = 0.0f;
+  }
+  for (long long r = (long long)blockIdx.x * kT + threadIdx.x; r < B; r += (long long)gridDim.x * kT) {
+    float xs[KS];
+#pragma unroll
+    for (int k = 0; k < KS; ++k) xs[k] = (k < K) ? __ldg(x + r * K + k) : 0.0f;
+    const float4* po = reinterpret_cast<const float4*>(out + r * N);
+    const float4* pg = reinterpret_cast<const float4*>(dout + r * N);
+#pragma unroll
+    for (int c = 0; c < N / 4; ++c) {
+      const float4 o = __ldg(po + c), g = __ldg(pg + c);
+      const float d[4] = {g.x * act_bwd<ACT>(o.x), g.y * act_bwd<ACT>(o.y), g.z * act_bwd<ACT>(o.z),
+                          g.w * act_bwd<ACT>(o.w)};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        gb[4 * c + j] += d[j];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) gw[k][4 * c + j] = fmaf(xs[k], d[j], gw[k][4 * c + j]);
+      }
+    }
+  }
+  // warps meet with shuffles, the CTA's warps in shared memory: ONE atomic per entry per CTA (atomics on the
+  // same few addresses serialise in L2: per-warp atomics cost more than the whole streaming pass)
+  __shared__ float sRed[kT / 32][(KS + 1) * N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    float v = gb[n];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if ((threadIdx.x & 31) == 0) sRed[threadIdx.x >> 5][n] = v;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      float w = gw[k][n];
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) w += __shfl_xor_sync(0xffffffffu, w, s);
+      if ((threadIdx.x & 31) == 0) sRed[threadIdx.x >> 5][(k + 1) * N + n] = w;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < (KS + 1) * N; e += kT) {
+    float v = 0.0f;
+#pragma unroll
+    for (int wi = 0; wi < kT / 32; ++wi) v += sRed[wi][e];
+    const int k = e / N - 1, n = e % N;
+    if (k < 0) atomicAdd(db + n, v);
+    else if (k < K) atomicAdd(dW + n * K + k, v);
+  }
+}
+
+template <int N, int ACT>
+cudaError_t launch_bwd_first(const float* x, const float* out, const float* dout, float* dW, float* db, long long B, int K,
+                             cudaStream_t st) {
+  const DeviceInfo& di = device_info();
+  const long long ntiles = (B + kT - 1) / kT;
+  long long grid = (long long)di.sm_count * 4;
+  if (grid > ntiles) grid = ntiles;
+  if (K == 1) dense_act_bwd_first<N, ACT, 1><<<(unsigned)grid, kT, 0, st>>>(x, out, dout, dW, db, B, K);
+  else dense_act_bwd_first<N, ACT, 4><<<(unsigned)grid, kT, 0, st>>>(x, out, dout, dW, db, B, K);
+  count_launch();
+  return cudaGetLastError();
 }
 
 template <int N, int ACT>
@@ -335,6 +420,17 @@ cudaError_t dispatch_fwd(int act, const float* x, const float* w, const float* b
 template <int N, int PER>
 cudaError_t dispatch_bwd(int act, const float* x, const float* out, const float* dout, const float* w, float* dx,
                          float* dW, float* db, long long B, int K, cudaStream_t st) {
+  if constexpr (N <= 32) {
+    if (dx == nullptr && K <= 4) {   // first layer of the network: streaming reduction, no staging
+      switch (act) {
+        case kLinear: return launch_bwd_first<N, kLinear>(x, out, dout, dW, db, B, K, st);
+        case kTanh: return launch_bwd_first<N, kTanh>(x, out, dout, dW, db, B, K, st);
+        case kRelu: return launch_bwd_first<N, kRelu>(x, out, dout, dW, db, B, K, st);
+        case kSigmoid: return launch_bwd_first<N, kSigmoid>(x, out, dout, dW, db, B, K, st);
+        default: return launch_bwd_first<N, kElu>(x, out, dout, dW, db, B, K, st);
+      }
+    }
+  }
   switch (act) {
     case kLinear: return launch_bwd<N, kLinear, PER>(x, out, dout, w, dx, dW, db, B, K, st);
     case kTanh: return launch_bwd<N, kTanh, PER>(x, out, dout, w, dx, dW, db, B, K, st);

@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("act", ["tanh", "relu", "linear", "sigmoid", "elu"])
-@pytest.mark.parametrize("K,N,B", [(1, 16, 1000), (16, 16, 4097), (3, 8, 129), (16, 32, 777), (64, 64, 300), (64, 32, 300), (10, 16, 1)])
+@pytest.mark.parametrize("K,N,B", [(1, 16, 1000), (2, 32, 5000), (4, 8, 333), (16, 16, 4097), (3, 8, 129), (16, 32, 777), (64, 64, 300), (64, 32, 300), (10, 16, 1)])
 def test_dense_act_matches_float64(cuda_device, nfn_lib, act, K, N, B):
     from normalizingflownetwork_b200 import functional as F
 
@@ -41,7 +41,9 @@ def test_dense_act_matches_float64(cuda_device, nfn_lib, act, K, N, B):
     with torch.no_grad():
         assert torch.equal(F.dense_act(x, w, b, act), out.detach())
     wg2 = w.clone().requires_grad_(True)
-    F.dense_act(x, wg2, b, act).backward(up)
+    bg2 = b.clone().requires_grad_(True)
+    F.dense_act(x, wg2, bg2, act).backward(up)
+    assert torch.allclose(bg2.grad, bg.grad, rtol=1e-4, atol=1e-4 * max(1.0, float(b64.grad.abs().max())))
     assert torch.allclose(wg2.grad, wg.grad, rtol=1e-4, atol=1e-4 * scale)   # atomics: summation order varies
 
 
