@@ -83,10 +83,13 @@ __device__ __forceinline__ void tile_copy(float* s, int S, float* g, long long r
 __host__ __device__ constexpr int pad4(int n) { return (n + 3) / 4 * 4; }
 
 // ---------------------------------------------------------------- forward
-template <int N, int ACT>
+// KC > 0 fixes the input width at compile time (the common 16 -> 16 layer: a quarter of the instructions of the
+// runtime-K version were address arithmetic)
+template <int N, int ACT, int KC>
 __global__ void __launch_bounds__(kT) dense_act_fwd(const float* __restrict__ x, const float* __restrict__ weight,
                                                    const float* __restrict__ bias, float* __restrict__ out,
-                                                   long long B, int K) {
+                                                   long long B, int K_rt) {
+  const int K = KC > 0 ? KC : K_rt;
   extern __shared__ __align__(16) float smem[];
   const int SX = pad4(K) + 4;
   constexpr int SO = N + 4;
@@ -141,11 +144,12 @@ __global__ void __launch_bounds__(kT) dense_act_fwd(const float* __restrict__ x,
 // 4 x 4 blocks; a thread owns PER blocks (1 or 2) and one slice of the tile's rows, and per row reads one
 // float4 of x and one float4 of dpre for 16 FMAs.  Accumulators live in registers for the whole kernel; the
 // slices meet in shared memory at the end: one global atomic per entry per CTA.
-template <int N, int ACT, int PER>
+template <int N, int ACT, int PER, int KC>
 __global__ void __launch_bounds__(kT, 4) dense_act_bwd(const float* __restrict__ x, const float* __restrict__ out,
                                                       const float* __restrict__ dout, const float* __restrict__ weight,
                                                       float* __restrict__ dx, float* __restrict__ dW,
-                                                      float* __restrict__ db, long long B, int K) {
+                                                      float* __restrict__ db, long long B, int K_rt) {
+  const int K = KC > 0 ? KC : K_rt;
   extern __shared__ __align__(16) float smem[];
   const int K4 = (K + 3) / 4;
   constexpr int N4 = N / 4;
@@ -368,10 +372,12 @@ template <int N, int ACT>
 cudaError_t launch_fwd(const float* x, const float* w, const float* b, float* out, long long B, int K, cudaStream_t st) {
   const DeviceInfo& di = device_info();
   const size_t smem = (size_t)(pad4(K * N) + N + kT * (pad4(K) + 4) + kT * (N + 4)) * sizeof(float);
-  auto kern = dense_act_fwd<N, ACT>;
+  auto kern = (K == 16) ? dense_act_fwd<N, ACT, 16> : dense_act_fwd<N, ACT, 0>;
   static thread_local int configured_for = -1;
   if (configured_for != di.device) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(dense_act_fwd<N, ACT, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dense_act_fwd<N, ACT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     if (e != cudaSuccess) return e;
     configured_for = di.device;
   }
@@ -390,10 +396,12 @@ cudaError_t launch_bwd(const float* x, const float* out, const float* dout, cons
   const int K4 = (K + 3) / 4;
   const int so = (N > 4 * K4 ? N : 4 * K4) + 4;
   const size_t smem = (size_t)(pad4(K * N) + kT * (4 * K4 + 4) + kT * (N + 4) + kT * so) * sizeof(float);
-  auto kern = dense_act_bwd<N, ACT, PER>;
+  auto kern = (K == 16) ? dense_act_bwd<N, ACT, PER, 16> : dense_act_bwd<N, ACT, PER, 0>;
   static thread_local int configured_for = -1;
   if (configured_for != di.device) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(dense_act_bwd<N, ACT, PER, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dense_act_bwd<N, ACT, PER, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     if (e != cudaSuccess) return e;
     configured_for = di.device;
   }
