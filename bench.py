@@ -564,6 +564,10 @@ def run_cfg1_pipeline(args):
     for _ in range(K):
         model.log_pdf(x, y).cpu()
     us_logpdf_e2e = (time.perf_counter() - t0) * 1e6 / K
+    t0 = time.perf_counter()
+    for _ in range(K):
+        model.log_pdf_graphed(x, y).cpu()
+    us_logpdf_e2e_graph = (time.perf_counter() - t0) * 1e6 / K
 
     # CPU port of the same pipeline
     torch.set_num_threads(os.cpu_count() or 1)
@@ -606,6 +610,7 @@ def run_cfg1_pipeline(args):
                                "gen_cosine_noise_data(2048, 0.3, 0.5), batch 2048"},
         "value": us_step_graph, "ms_per_step": us_step_graph * 1e-3, "vs_baseline": None,
         "log_pdf_us": us_logpdf, "log_pdf_cuda_graph_us": us_logpdf_graph, "log_pdf_host_in_host_out_us": us_logpdf_e2e,
+        "log_pdf_host_in_host_out_cuda_graph_us": us_logpdf_e2e_graph,
         "fit_step_eager_us": us_step, "fit_step_cuda_graph_us": us_step_graph,
         "samples_per_s_fit_graph": B / (us_step_graph * 1e-6), "samples_per_s_log_pdf": B / (us_logpdf * 1e-6),
         "cpu_baseline": {"kind": "port", "cores": os.cpu_count(), "log_pdf_us": us_cpu_logpdf,

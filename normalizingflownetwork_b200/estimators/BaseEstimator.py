@@ -306,10 +306,11 @@ class BaseEstimator(torch.nn.Module):
         return self
 
     def log_pdf_graphed(self, x, y):
-        """Replay the captured scoring graph on a new batch (device tensors of the captured shape); the
-        returned tensor is the graph's static output buffer (clone it to keep it across replays)."""
-        self._sx.copy_(x)
-        self._sy.copy_(y)
+        """Replay the captured scoring graph on a new batch of the captured shape (device tensors, or host
+        arrays which are copied in); the returned tensor is the graph's static output buffer (clone it to
+        keep it across replays)."""
+        self._sx.copy_(x if torch.is_tensor(x) else torch.as_tensor(np.asarray(x, dtype=np.float32)))
+        self._sy.copy_(y if torch.is_tensor(y) else torch.as_tensor(np.asarray(y, dtype=np.float32)))
         self._score_graph.replay()
         return self._score_out
 
