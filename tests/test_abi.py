@@ -81,6 +81,18 @@ def test_descriptor_validation_without_gpu(nfn_lib):
     assert nfn_lib.nfn_logmeanexp_draws(None, 0, 4, None, None) == -3
 
 
+def test_hidden_layer_kernel_range(nfn_lib):
+    """nfn_dense_act_supported is pure host logic: 1..64 inputs, 8/16/32/64 units, five activations."""
+    ok = nfn_lib.nfn_dense_act_supported
+    assert ok(1, 16, 1) and ok(16, 16, 1) and ok(64, 64, 4) and ok(3, 8, 0)
+    assert not ok(0, 16, 1) and not ok(65, 16, 1) and not ok(16, 10, 1) and not ok(16, 16, 5) and not ok(16, 16, -1)
+    # argument checks happen before any CUDA call
+    assert nfn_lib.nfn_dense_act_forward(None, None, None, 4, 16, 10, 1, None, None) == -6   # NFN_ERR_UNSUPPORTED
+    assert nfn_lib.nfn_dense_act_forward(None, None, None, 0, 16, 16, 1, None, None) == 0    # B = 0 is a no-op
+    assert nfn_lib.nfn_dense_act_forward(None, None, None, 4, 16, 16, 1, None, None) == -1   # NFN_ERR_NULL
+    assert nfn_lib.nfn_dense_act_backward(None, None, None, None, 4, 16, 16, 1, None, None, None, None) == -1
+
+
 def test_runtime_specialiser_compiles_without_gpu(nfn_lib):
     """The embedded device headers compile under NVRTC for sm_100a (no device needed)."""
     from normalizingflownetwork_b200 import _lib
