@@ -48,6 +48,10 @@ int main(int argc, char** argv) {
     desc.n_flows = 10;
     const uint8_t ft[10] = {0, 1, 2, 0, 1, 2, 0, 1, 2, 0};
     memcpy(desc.flow_type, ft, 10);
+  } else if (cfg == 3) {    // BASELINE config 3: 16 flows (radial, planar) x 8, 4-D y (P = 128)
+    desc.n_dims = 4;
+    desc.n_flows = 16;
+    for (int i = 0; i < 16; ++i) desc.flow_type[i] = (i % 2 == 0) ? 1 : 0;
   } else if (cfg == 10) {   // NormalizingFlowNetwork's default chain: 10 radial flows, 1-D y (P = 32)
     desc.n_dims = 1;
     desc.n_flows = 10;
