@@ -18,6 +18,7 @@ CASES = [
     (["radial", "planar"], 3, True, 32),       # P = 18: not a multiple of 8 (padded mma tiles)
     (["affine", "radial"], 2, False, 64),      # P = 8, no base parameters
     (["planar"], 1, True, 48),                 # P = 5 (odd row stride)
+    (["radial", "planar"] * 8, 4, True, 16),   # BASELINE config 3 chain: P = 128 (three GEMM-3 passes, 512 TMEM columns)
 ]
 
 
