@@ -18,4 +18,15 @@ documented TFP glue semantics, pinned three ways instead:
                                 the reference's own test inputs (``tf.ones`` cases),
 frozen into ``tests/golden/*.json`` by ``oracle/make_golden.py`` and cross-checked
 against the values derived independently in SURVEY.md App. A.7.
+
+What IS pinned by execution: ``oracle/tf_shim.py`` provides torch-CPU float64 stand-ins for
+the ~20 TF ops and 7 TFP glue classes the path touches, so that the reference's own
+``estimators/normalizing_flows/*.py`` and ``estimators/DistributionLayers.py`` are imported
+UNMODIFIED from /root/reference and run on the golden inputs
+(``oracle/make_reference_run.py`` -> ``tests/golden/reference_run.json``).  Their log-probs
+and the autograd gradients through them equal the oracle's to 1e-12 / 1e-9 on all 24 chain,
+6 MDN and 2 KMN cases and on the reference's ``tf.ones`` test inputs.  That pins every
+formula, constant, slice and ordering decision made in the reference's repository; TFP's own
+glue arithmetic (restated in the shim from its documented semantics) and float32 rounding
+remain unpinned.
 """

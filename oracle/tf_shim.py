@@ -1,0 +1,451 @@
+"""Stand-in ``tensorflow`` / ``tensorflow_probability`` modules so that the reference's OWN
+source files can be executed in this image.
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  TensorFlow and TFP are absent and not
+installable here, but the reference's hot path is ~250 lines of Python living under
+``/root/reference/estimators`` that touch TF through ~20 elementwise ops and TFP through seven
+glue classes.  This module provides exactly that surface on top of torch-CPU tensors
+(float64 by default) and registers it in ``sys.modules``; ``load_reference()`` then imports
+``estimators/normalizing_flows/*.py`` and ``estimators/DistributionLayers.py`` UNMODIFIED from
+``/root/reference`` and returns them.  What this pins: every formula, constant, slice offset
+and ordering decision the reference itself makes (parameter constraints, the L1 radius, the
+tail-first parameter layout, the nested GradientTape derivative, the base distribution, the
+mixture layouts).  What it does not pin: TFP's own glue, which is restated below from its
+documented semantics -- each class cites the reference call site it serves.
+
+Because the tensors are torch tensors, gradients of the reference's log_prob with respect to
+its inputs come from torch autograd THROUGH the reference's code (``tf.GradientTape`` is mapped
+onto ``torch.autograd.grad(create_graph=True)``).
+
+``oracle/make_reference_run.py`` uses this to freeze ``tests/golden/reference_run.json``; it can
+only run where ``/root/reference`` exists (this container), the fixture travels.
+"""
+import importlib
+import math
+import sys
+import types
+
+import numpy as np
+import torch
+
+REFERENCE_ROOT = "/root/reference"
+_DTYPE = torch.float64
+
+
+def _t(x):
+    """tf.convert_to_tensor for the shim's single working dtype."""
+    if isinstance(x, _Variable):
+        return x.value()
+    if isinstance(x, torch.Tensor):
+        return x if x.dtype == _DTYPE else x.to(_DTYPE)
+    return torch.as_tensor(np.asarray(x, dtype=np.float64), dtype=_DTYPE)
+
+
+def _softplus(x):
+    # log(1 + exp(x)) without torch's x > 20 shortcut (exact to the last bit in float64)
+    x = _t(x)
+    return torch.logaddexp(x, torch.zeros_like(x))
+
+
+def _reduce_sum(x, axis=None, keepdims=False):
+    x = _t(x)
+    if axis is None:
+        return torch.sum(x)
+    return torch.sum(x, dim=axis, keepdim=keepdims)
+
+
+class _GradientTape:
+    """RadialFlow.py:64-67: ``g.watch(r); h = ...; g.gradient(h, r)``.  tape.gradient of a
+    non-scalar target is the gradient of its sum (cotangent of ones)."""
+
+    def __init__(self, persistent=False):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def watch(self, x):
+        if not x.requires_grad:
+            x.requires_grad_(True)
+
+    def gradient(self, target, source):
+        return torch.autograd.grad(target, source, grad_outputs=torch.ones_like(target),
+                                   create_graph=True)[0]
+
+
+class _Variable:
+    """tf.Variable as GaussianKernelsLayer uses it (DistributionLayers.py:101-105, :169-170)."""
+
+    def __init__(self, initial_value=None, dtype=None, trainable=True, **kw):
+        self._v = _t(initial_value).clone()
+        self.trainable = trainable
+
+    def assign(self, value):
+        value = _t(value)
+        assert tuple(value.shape) == tuple(self._v.shape), (value.shape, self._v.shape)
+        self._v = value.clone()
+        return self
+
+    def value(self):
+        return self._v
+
+    @property
+    def shape(self):
+        return self._v.shape
+
+    def __mul__(self, other):
+        return self._v * _t(other)
+
+    __rmul__ = __mul__
+
+    def __getitem__(self, i):
+        return self._v[i]
+
+
+# ------------------------------------------------------------------ tfp.bijectors
+class _Bijector:
+    """tfp.bijectors.Bijector base as PlanarFlow.py:21 / RadialFlow.py:21 construct it.  With
+    event_ndims equal to the declared minimum (1) the public methods are the private ones."""
+
+    def __init__(self, validate_args=False, name=None, forward_min_event_ndims=None,
+                 inverse_min_event_ndims=None, **kw):
+        if forward_min_event_ndims is None:
+            forward_min_event_ndims = inverse_min_event_ndims
+        if inverse_min_event_ndims is None:
+            inverse_min_event_ndims = forward_min_event_ndims
+        self.forward_min_event_ndims = forward_min_event_ndims
+        self.inverse_min_event_ndims = inverse_min_event_ndims
+        self.name = name
+
+    def forward(self, x):
+        return self._forward(_t(x))
+
+    def forward_log_det_jacobian(self, x, event_ndims=None):
+        assert event_ndims in (None, self.forward_min_event_ndims)
+        return self._forward_log_det_jacobian(_t(x))
+
+
+class _Affine(_Bijector):
+    """tfp.bijectors.Affine(shift, scale_diag) (AffineFlow.py:7-9): y = scale_diag * x + shift,
+    fldj = sum_i log|scale_diag_i| (LinearOperatorDiag.log_abs_determinant), event_ndims 1."""
+
+    def __init__(self, shift=None, scale_diag=None, name="affine", **kw):
+        super().__init__(name=name, forward_min_event_ndims=1)
+        self.shift = _t(shift)
+        self._scale_diag = _t(scale_diag)
+
+    def _forward(self, x):
+        return self._scale_diag * x + self.shift
+
+    def _forward_log_det_jacobian(self, x):
+        return torch.sum(torch.log(torch.abs(self._scale_diag)), -1)
+
+
+class _Chain(_Bijector):
+    """tfp.bijectors.Chain (DistributionLayers.py:278): Chain([b0, b1, ...]).forward applies
+    the LAST bijector first; each log-det is evaluated at that bijector's own input."""
+
+    def __init__(self, bijectors=None, name="chain", **kw):
+        super().__init__(name=name, forward_min_event_ndims=1)
+        self.bijectors = list(bijectors or [])
+
+    def _forward(self, x):
+        for b in reversed(self.bijectors):
+            x = b.forward(x)
+        return x
+
+    def _forward_log_det_jacobian(self, x):
+        ld = torch.zeros((), dtype=_DTYPE)
+        for b in reversed(self.bijectors):
+            ld = ld + b.forward_log_det_jacobian(x, event_ndims=1)
+            x = b.forward(x)
+        return ld
+
+
+class _Invert(_Bijector):
+    """tfp.bijectors.Invert (DistributionLayers.py:250): swaps forward and inverse."""
+
+    def __init__(self, bijector, name=None, **kw):
+        super().__init__(name=name, forward_min_event_ndims=bijector.inverse_min_event_ndims,
+                         inverse_min_event_ndims=bijector.forward_min_event_ndims)
+        self.bijector = bijector
+
+    def inverse(self, y):
+        return self.bijector.forward(y)
+
+    def inverse_log_det_jacobian(self, y, event_ndims=None):
+        return self.bijector.forward_log_det_jacobian(y, event_ndims=event_ndims)
+
+
+# ------------------------------------------------------------------ tfp.distributions
+class _Distribution:
+    @staticmethod
+    def mean(d):
+        raise NotImplementedError
+
+    @staticmethod
+    def sample(d):
+        raise NotImplementedError
+
+
+class _MultivariateNormalDiag(_Distribution):
+    """tfd.MultivariateNormalDiag(loc, scale_diag | scale_identity_multiplier)
+    (DistributionLayers.py:125, :200, :283, :292).  log_prob(x) =
+    -1/2 sum(((x-loc)/s)^2) - sum(log|s|) - d/2 log(2 pi); an identity multiplier of shape [M]
+    is one isotropic scale per batch member (batch_shape [M], event_shape [d])."""
+
+    def __init__(self, loc=None, scale_diag=None, scale_identity_multiplier=None, name=None, **kw):
+        self.loc = _t(loc)
+        if scale_diag is not None:
+            self.scale = _t(scale_diag)
+        elif scale_identity_multiplier is not None:
+            self.scale = _t(scale_identity_multiplier)[..., None]
+        else:
+            self.scale = torch.ones((), dtype=_DTYPE)
+
+    @property
+    def event_shape(self):
+        return tuple(self.loc.shape[-1:])
+
+    @property
+    def batch_shape(self):
+        return tuple(torch.broadcast_shapes(self.loc.shape, self.scale.shape)[:-1])
+
+    def log_prob(self, x):
+        e = (_t(x) - self.loc) / self.scale
+        d = e.shape[-1]
+        log_s = torch.log(torch.abs(self.scale)) + torch.zeros_like(e)
+        return -0.5 * torch.sum(e * e, -1) - torch.sum(log_s, -1) - 0.5 * d * math.log(2.0 * math.pi)
+
+
+class _Categorical(_Distribution):
+    def __init__(self, logits=None, **kw):
+        self.logits = _t(logits)
+
+
+class _Mixture(_Distribution):
+    """tfd.Mixture(cat, components).log_prob (DistributionLayers.py:198-211):
+    logsumexp_k(log_softmax(logits)_k + components[k].log_prob(x))."""
+
+    def __init__(self, cat=None, components=None, **kw):
+        self.cat, self.components = cat, list(components)
+        assert self.cat.logits.shape[-1] == len(self.components)
+
+    def log_prob(self, x):
+        lp = torch.stack([c.log_prob(x) for c in self.components], -1)
+        return torch.logsumexp(lp + torch.log_softmax(self.cat.logits, -1), -1)
+
+
+class _MixtureSameFamily(_Distribution):
+    """tfd.MixtureSameFamily.log_prob (DistributionLayers.py:124-131): the event gets a
+    component axis, ``x[..., None, :]``, and is scored by the batched component distribution."""
+
+    def __init__(self, mixture_distribution=None, components_distribution=None, **kw):
+        self.mixture_distribution = mixture_distribution
+        self.components_distribution = components_distribution
+
+    def log_prob(self, x):
+        lp = self.components_distribution.log_prob(_t(x)[..., None, :])
+        return torch.logsumexp(lp + torch.log_softmax(self.mixture_distribution.logits, -1), -1)
+
+
+class _TransformedDistribution(_Distribution):
+    """tfd.TransformedDistribution.log_prob (DistributionLayers.py:246):
+    base.log_prob(bijector.inverse(y)) + bijector.inverse_log_det_jacobian(y, event_ndims=1)."""
+
+    def __init__(self, distribution=None, bijector=None, **kw):
+        self.distribution, self.bijector = distribution, bijector
+
+    def log_prob(self, y):
+        y = _t(y)
+        x = self.bijector.inverse(y)
+        ildj = self.bijector.inverse_log_det_jacobian(y, event_ndims=1)
+        return self.distribution.log_prob(x) + ildj
+
+
+class _Normal(_Distribution):
+    def __init__(self, loc=None, scale=None, **kw):
+        self.loc, self.scale = _t(loc), _t(scale)
+
+    def log_prob(self, x):
+        e = (_t(x) - self.loc) / self.scale
+        return -0.5 * e * e - torch.log(self.scale) - 0.5 * math.log(2.0 * math.pi)
+
+
+class _Independent(_Distribution):
+    def __init__(self, distribution=None, reinterpreted_batch_ndims=1, **kw):
+        self.distribution, self.n = distribution, reinterpreted_batch_ndims
+
+    def log_prob(self, x):
+        lp = self.distribution.log_prob(x)
+        return torch.sum(lp, dim=tuple(range(-self.n, 0)))
+
+
+# ------------------------------------------------------------------ tfp.layers / tf.keras
+class _DistributionLambda:
+    """tfp.layers.DistributionLambda: calling the layer builds the distribution from ``t``."""
+
+    def __init__(self, make_distribution_fn=None, convert_to_tensor_fn=None, dtype=None, **kw):
+        self._make_distribution_fn = make_distribution_fn
+        self._convert_to_tensor_fn = convert_to_tensor_fn
+
+    def __call__(self, t):
+        return self._make_distribution_fn(_t(t))
+
+
+class _VariableLayer:
+    """tfp.layers.VariableLayer (DistributionLayers.py:80-85): ignores its input."""
+
+    def __init__(self, shape=None, dtype=None, initializer="zeros", trainable=True, **kw):
+        assert initializer == "zeros"
+        n = shape if isinstance(shape, int) else int(np.prod(shape))
+        self.variable = torch.zeros(n, dtype=_DTYPE)
+        self.trainable = trainable
+
+    def __call__(self, _x):
+        return self.variable
+
+
+class _Lambda:
+    def __init__(self, function, **kw):
+        self.function = function
+
+    def __call__(self, x):
+        return self.function(x)
+
+
+class _Sequential:
+    def __init__(self, layers=None, **kw):
+        self.layers = list(layers or [])
+
+    def __call__(self, x):
+        for layer in self.layers:
+            x = layer(x)
+        return x
+
+
+def _module(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    m.__shim__ = True
+    return m
+
+
+def install(dtype=torch.float64):
+    """Register the stand-in modules.  Refuses to shadow a real TensorFlow."""
+    global _DTYPE
+    for name in ("tensorflow", "tensorflow_probability"):
+        mod = sys.modules.get(name)
+        if mod is not None and not getattr(mod, "__shim__", False):
+            raise RuntimeError(f"a real {name} is loaded; run the real reference instead")
+    _DTYPE = dtype
+
+    tf_math = _module(
+        "tensorflow.math",
+        reduce_sum=_reduce_sum,
+        softplus=_softplus,
+        tanh=lambda x: torch.tanh(_t(x)),
+        log=lambda x: torch.log(_t(x)),
+        abs=lambda x: torch.abs(_t(x)),
+        expm1=lambda x: torch.expm1(_t(x)),
+    )
+    tf_nn = _module("tensorflow.nn", softplus=_softplus)
+    keras = _module(
+        "tensorflow.keras",
+        models=_module("tensorflow.keras.models", Sequential=_Sequential),
+        layers=_module("tensorflow.keras.layers", Lambda=_Lambda),
+    )
+    tf2 = _module("tensorflow.python.tf2", enabled=lambda: True)
+    tf_python = _module("tensorflow.python", tf2=tf2)
+    tf = _module(
+        "tensorflow",
+        math=tf_math,
+        nn=tf_nn,
+        keras=keras,
+        python=tf_python,
+        float32="float32",
+        float64="float64",
+        abs=tf_math.abs,
+        squeeze=lambda x, axis=None: torch.squeeze(_t(x)) if axis is None else torch.squeeze(_t(x), dim=axis),
+        expand_dims=lambda x, axis: torch.unsqueeze(_t(x), axis),
+        zeros_like=lambda x: torch.zeros_like(_t(x)),
+        ones_like=lambda x: torch.ones_like(_t(x)),
+        zeros=lambda shape, dtype=None: torch.zeros(shape, dtype=_DTYPE),
+        constant=lambda v, dtype=None: _t(v),
+        concat=lambda values, axis=0: torch.cat([_t(v) for v in values], dim=axis),
+        convert_to_tensor=lambda v, dtype=None: _t(v),
+        GradientTape=_GradientTape,
+        Variable=_Variable,
+    )
+    tf.__path__ = []  # a package, so that ``from tensorflow.python import tf2`` resolves
+    tf_python.__path__ = []
+
+    bijectors = _module("tensorflow_probability.bijectors", Bijector=_Bijector, Affine=_Affine,
+                        Chain=_Chain, Invert=_Invert)
+    distributions = _module(
+        "tensorflow_probability.distributions",
+        Distribution=_Distribution,
+        MultivariateNormalDiag=_MultivariateNormalDiag,
+        Categorical=_Categorical,
+        Mixture=_Mixture,
+        MixtureSameFamily=_MixtureSameFamily,
+        TransformedDistribution=_TransformedDistribution,
+        Normal=_Normal,
+        Independent=_Independent,
+    )
+    layers = _module("tensorflow_probability.layers", DistributionLambda=_DistributionLambda,
+                     VariableLayer=_VariableLayer)
+    tfp = _module("tensorflow_probability", bijectors=bijectors, distributions=distributions,
+                  layers=layers)
+    tfp.__path__ = []
+
+    for m in (tf, tf_math, tf_nn, keras, keras.models, keras.layers, tf_python, tf2, tfp, bijectors,
+              distributions, layers):
+        sys.modules[m.__name__] = m
+    return tf, tfp
+
+
+def uninstall():
+    """Drop the stand-in modules and the reference modules loaded through them."""
+    for name in list(sys.modules):
+        top = name.split(".")[0]
+        if top in ("tensorflow", "tensorflow_probability", "estimators") and \
+                getattr(sys.modules.get(top), "__shim__", False):
+            if name != top:
+                del sys.modules[name]
+    for top in ("tensorflow", "tensorflow_probability", "estimators"):
+        if getattr(sys.modules.get(top), "__shim__", False):
+            del sys.modules[top]
+
+
+def load_reference(root=REFERENCE_ROOT, dtype=torch.float64):
+    """Import the reference's flow and distribution-layer modules, unmodified, from ``root``.
+
+    ``estimators/__init__.py`` is NOT executed (it pulls in the Keras estimator classes, which
+    are outside the path): an empty package object with the reference's ``__path__`` stands in
+    for it, so ``estimators.normalizing_flows`` and ``estimators.DistributionLayers`` are the
+    reference's own files.  Returns ``(FLOWS, DistributionLayers module)``.
+    """
+    import os
+
+    if not os.path.isdir(os.path.join(root, "estimators")):
+        raise FileNotFoundError(f"{root}/estimators not found (the reference does not travel)")
+    install(dtype)
+    pkg = types.ModuleType("estimators")
+    pkg.__path__ = [os.path.join(root, "estimators")]
+    pkg.__shim__ = True
+    for name in [n for n in sys.modules if n == "estimators" or n.startswith("estimators.")]:
+        del sys.modules[name]
+    sys.modules["estimators"] = pkg
+    keep, sys.dont_write_bytecode = sys.dont_write_bytecode, True  # never write into the reference tree
+    try:
+        flows = importlib.import_module("estimators.normalizing_flows")
+        layers = importlib.import_module("estimators.DistributionLayers")
+    finally:
+        sys.dont_write_bytecode = keep
+    for mod in (flows, layers):
+        assert mod.__file__.startswith(root), mod.__file__
+    return flows.FLOWS, layers

@@ -127,6 +127,51 @@ def test_golden_chain_vectors(cuda_device, nfn_lib, math_mode, kernel_path):
         assert_logp(lb.cpu().numpy(), c["log_prob_y_row3_broadcast"], ltol, tag + " bcast")
 
 
+def test_cuda_vs_reference_code_run(cuda_device, nfn_lib, math_mode):
+    """The CUDA path against what the reference's OWN flow / layer code returned for the same inputs
+    (tests/golden/reference_run.json, produced by oracle/make_reference_run.py; see tests/test_reference_run.py)."""
+    from normalizingflownetwork_b200 import functional as F
+
+    ref = json.load(open(os.path.join(GOLDEN, "reference_run.json")))
+    cases = json.load(open(os.path.join(GOLDEN, "chain_vectors.json")))
+    mv = json.load(open(os.path.join(GOLDEN, "mixture_vectors.json")))
+    n = 0
+    for r, c in zip(ref["chains"], cases):
+        assert (r["name"], r["sigma"]) == (c["name"], c["sigma"])
+        ft, d, tb = c["flow_types"], c["n_dims"], c["trainable_base_dist"]
+        t, y, up = dev(c["t"], cuda_device), dev(c["y"], cuda_device), dev(c["upstream"], cuda_device)
+        if t.shape[1] == 0:
+            continue
+        tag = "reference run %s sigma=%s %s" % (c["name"], c["sigma"], math_mode)
+        ltol = LOGP_RTOL if c["sigma"] <= 0.5 else 5e-5
+        gtol = GRAD_RTOL if c["sigma"] <= 0.5 else 1e-3
+        lp, dt, dy = F.chain_forward_backward(t, y, ft, d, tb, g_logp=up, want_dy=True)
+        assert_logp(lp.cpu().numpy(), r["log_prob"], ltol, tag)
+        assert_grad(dt.cpu().numpy(), np.asarray(r["dt"]).reshape(tuple(dt.shape)), gtol, tag + " dt")
+        assert_grad(dy.cpu().numpy(), r["dy"], gtol, tag + " dy")
+        lb = F.chain_forward(t, y[3:4], ft, d, tb)
+        assert_logp(lb.cpu().numpy(), r["log_prob_y_row3_broadcast"], ltol, tag + " bcast")
+        n += 1
+    assert n >= 22
+    for r, c in zip(ref["mixtures"]["mdn"], mv["mdn"]):
+        assert (r["name"], r["sigma"]) == (c["name"], c["sigma"])
+        t, y, up = dev(c["t"], cuda_device), dev(c["y"], cuda_device), dev(c["upstream"], cuda_device)
+        lp, dt, dy = F.mdn_forward_backward(t, y, c["n_centers"], c["n_dims"], g_logp=up, want_dy=True)
+        assert_logp(lp.cpu().numpy(), r["log_prob"], what=r["name"])
+        assert_grad(dt.cpu().numpy(), r["dt"], what=r["name"] + " dt")
+        assert_grad(dy.cpu().numpy(), r["dy"], what=r["name"] + " dy")
+    for r, c in zip(ref["mixtures"]["kmn"], mv["kmn"]):
+        assert r["name"] == c["name"]
+        t, y, up = dev(c["t"], cuda_device), dev(c["y"], cuda_device), dev(c["upstream"], cuda_device)
+        # the bandwidths the reference's scale_model returned (negative for init 0.3)
+        locs, scales = dev(c["locs"], cuda_device), dev(r["scales"], cuda_device)
+        lp, dt, dy, _ = F.kmn_forward_backward(t, y, locs, scales, g_logp=up, want_dy=True)
+        assert_logp(lp.cpu().numpy(), r["log_prob"], what=r["name"])
+        assert_grad(dt.cpu().numpy(), r["dt"], what=r["name"] + " dt")
+        assert_grad(dy.cpu().numpy(), r["dy"], what=r["name"] + " dy")
+
+
+
 # ----------------------------------------------------------------------------- seeded parity
 @pytest.mark.parametrize("cfg", sorted(CONFIG_CHAINS))
 @pytest.mark.parametrize("B", [1, 127, 129, 4096 + 37])
