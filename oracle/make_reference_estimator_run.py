@@ -1,0 +1,193 @@
+"""Run the reference's OWN estimator classes (normalisation, NLL closure, pdf / log_pdf / score)
+with fixed weights and freeze what they return as ``tests/golden/reference_estimator_run.json``.
+
+TEST INFRASTRUCTURE ONLY.  Runs only where ``/root/reference`` exists (this container):
+
+    python -m oracle.make_reference_estimator_run            # rewrite the fixture
+    python -m oracle.make_reference_estimator_run --check    # recompute and diff
+
+``estimators/{BaseEstimator,MaximumLikelihoodNNEstimator,NormalizingFlowNetwork,MixtureDensityNetwork,
+KernelMixtureNetwork}.py`` are imported unmodified through ``oracle/tf_shim.py`` (torch-CPU float64
+stand-ins for TF / Keras / TFP; the Keras training loop is not emulated).  Per case the script builds the
+reference estimator via its ``build_function``, calls the reference's ``_assign_data_normalization`` /
+``_assign_noise_regularisation``, sets seeded Dense weights, and records
+  log_pdf(x, y), pdf(x, y), score(x, y)                       (BaseEstimator.py:43-47, :71-86)
+  mean of _get_neg_log_likelihood()(y, model.call(x))          (BaseEstimator.py:55-59, the Keras loss)
+  its autograd gradients w.r.t. every Dense kernel / bias      (what one train step back-propagates)
+and for the kernel mixture the centres chosen by the reference's ``set_center_points``
+(DistributionLayers.py:135-171; ``KMeans(n_jobs=-2)`` no longer exists in scikit-learn, so the KMeans
+the reference module sees is wrapped to drop ``n_jobs`` and to fix ``n_init=10, random_state=22``).
+Each case is also evaluated with the oracle (``oracle/flow_oracle.py``) and must agree to 1e-11.
+"""
+import argparse
+import importlib.util
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+from oracle import flow_oracle as fo
+from oracle import tf_shim
+from oracle.make_reference_run import GOLDEN, diff, lst
+
+OUT = os.path.join(GOLDEN, "reference_estimator_run.json")
+F64 = torch.float64
+
+CASES = [
+    dict(name="nfn_d1_radial3_tanh", cls="NormalizingFlowNetwork", data="cosine", n=256,
+         build=dict(n_dims=1, n_flows=3, hidden_sizes=(16, 16), activation="tanh")),
+    dict(name="nfn_d2_radial4_relu_nobase", cls="NormalizingFlowNetwork", data="gauss2", n=192,
+         build=dict(n_dims=2, n_flows=4, hidden_sizes=(8,), trainable_base_dist=False, activation="relu")),
+    dict(name="mdn_d2_k5_relu", cls="MixtureDensityNetwork", data="gauss2", n=192,
+         build=dict(n_dims=2, n_centers=5, hidden_sizes=(16, 16), activation="relu")),
+    dict(name="kmn_d1_c10_tanh_rule_of_thumb", cls="KernelMixtureNetwork", data="cosine", n=256,
+         build=dict(n_dims=1, n_centers=10, hidden_sizes=(16,), activation="tanh",
+                    noise_reg=("rule_of_thumb", 0.2))),
+]
+
+
+def reference_cosine(n):
+    spec = importlib.util.spec_from_file_location(
+        "_ref_dummy_data_gen", os.path.join(tf_shim.REFERENCE_ROOT, "simulation", "dummy_data_gen.py"))
+    mod = importlib.util.module_from_spec(spec)
+    keep, sys.dont_write_bytecode = sys.dont_write_bytecode, True
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.dont_write_bytecode = keep
+    return mod.gen_cosine_noise_data(n, noise_std=0.3, heterosced_noise=0.5)  # demo.py:14
+
+
+def make_data(kind, n, rng):
+    if kind == "cosine":
+        return reference_cosine(n)
+    # pdf / log_pdf assert x.shape == y.shape (BaseEstimator.py:72, :79): x is 2-D as well
+    x = rng.normal(0.0, 1.5, size=(n, 2)).astype(np.float32)
+    y = (np.stack([np.sin(x[:, 0]) + 0.3 * x[:, 1], 0.5 * x[:, 0] * x[:, 1]], 1)
+         + rng.normal(0.0, 0.4, size=(n, 2))).astype(np.float32) * np.float32(2.5) + np.float32(1.0)
+    return x, y
+
+
+def oracle_log_prob(case, model, t, y_circ, DL):
+    b = case["build"]
+    if case["cls"] == "NormalizingFlowNetwork":
+        return fo.chain_log_prob(t, y_circ, ["radial"] * b["n_flows"], b["n_dims"], b.get("trainable_base_dist", True))
+    if case["cls"] == "MixtureDensityNetwork":
+        return fo.mdn_log_prob(t, y_circ, b["n_centers"], b["n_dims"])
+    layer = model.dist_layer
+    scales = fo.kmn_scales(torch.zeros(layer.n_scales, dtype=F64), layer.n_centers, (0.3, 0.7))
+    return fo.kmn_log_prob(t, y_circ, layer.locs[0].detach(), scales)
+
+
+def run_case(case, mods, DL, rng):
+    from sklearn.cluster import KMeans
+
+    x, y = make_data(case["data"], case["n"], rng)
+    model = getattr(mods[case["cls"]], case["cls"]).build_function(**case["build"])
+    rec = {"name": case["name"], "cls": case["cls"], "build": {k: (list(v) if isinstance(v, tuple) else v)
+                                                             for k, v in case["build"].items()},
+           "x": x.tolist(), "y": y.tolist()}
+    if case["cls"] == "KernelMixtureNetwork":
+        # the first lines of KernelMixtureNetwork.fit (KernelMixtureNetwork.py:37-40), then BaseEstimator.fit's
+        DL.KMeans = lambda n_clusters, n_jobs=None: KMeans(n_clusters=n_clusters, n_init=10, random_state=22)
+        y_mean = np.mean(y, axis=0, dtype=np.float32)
+        y_std = np.std(y, axis=0, dtype=np.float32)
+        model.dist_layer.set_center_points((y - y_mean) / y_std)
+        rec["locs"] = lst(model.dist_layer.locs[0])
+        rec["scales"] = lst(model.dist_layer.scale_model(0.0))
+    # what BaseEstimator.fit does before handing over to Keras (BaseEstimator.py:19-21)
+    model._assign_data_normalization(x, y)
+    model._assign_noise_regularisation(n_dims=x.shape[1] + y.shape[1], n_datapoints=x.shape[0])
+    rec["noise_std"] = [float(model.x_noise_std.value()), float(model.y_noise_std.value())]
+    rec["stats"] = {k: np.asarray(getattr(model, k), dtype=np.float64).tolist()
+                    for k in ("x_mean", "x_std", "y_mean", "y_std")}
+    tf_layers = sys.modules["tensorflow"].keras.layers
+    dense = [l for l in model.layers if isinstance(l, tf_layers.Dense)]
+    widths = [x.shape[1]] + [l.units for l in dense]
+    weights = []
+    for l, fan_in in zip(dense, widths):
+        k = torch.tensor(rng.normal(0.0, 0.7 / np.sqrt(fan_in), size=(fan_in, l.units)).astype(np.float32),
+                         dtype=F64, requires_grad=True)
+        b = torch.tensor(rng.normal(0.0, 0.2, size=(l.units,)).astype(np.float32), dtype=F64, requires_grad=True)
+        l.set_weights([k, b])
+        weights += [k, b]
+    assert dense[-1].units == model.layers[-1].get_total_param_size()
+    rec["weights"] = [lst(w) for w in weights]  # kernel [in, units], bias, per Dense layer in order
+
+    with torch.no_grad():
+        log_pdf, pdf, score = model.log_pdf(x, y), model.pdf(x, y), model.score(x, y)
+    nll = model._get_neg_log_likelihood()  # the loss handed to compile() (MaximumLikelihoodNNEstimator.py:33-35)
+    per_sample = nll(y, model.call(x, training=False))
+    loss = per_sample.mean()  # Keras reduces the per-sample loss with a mean
+    grads = torch.autograd.grad(loss, weights)
+    assert abs(float(score) + float(per_sample.detach().mean())) <= 1e-13 * max(1.0, abs(float(score)))
+
+    # the oracle on the same weights
+    # x_std + 1e-8 happens in NumPy float32 in the reference (MaximumLikelihoodNNEstimator.py:40): a no-op
+    # for x_std ~ 1, which is also what the product's float32 torch expression evaluates to
+    h = (torch.tensor(x, dtype=F64) - torch.tensor(np.asarray(model.x_mean), dtype=F64)) / \
+        torch.tensor(np.asarray(model.x_std) + 1e-8, dtype=F64)
+    ws = [w.detach() for w in weights]
+    act = {"tanh": torch.tanh, "relu": torch.relu}[case["build"]["activation"]]
+    for i in range(0, len(ws), 2):
+        h = h @ ws[i] + ws[i + 1]
+        if i + 2 < len(ws):
+            h = act(h)
+    y_std = torch.tensor(np.asarray(model.y_std), dtype=F64)
+    y_circ = fo.normalise_y(torch.tensor(y, dtype=F64), torch.tensor(np.asarray(model.y_mean), dtype=F64), y_std)
+    o_lp = oracle_log_prob(case, model, h, y_circ, DL)
+    o_log_pdf = o_lp - torch.sum(torch.log(y_std))
+    assert torch.allclose(o_log_pdf, log_pdf, rtol=1e-11, atol=1e-11), case["name"]
+    assert torch.allclose(fo.nll(o_lp, y_std), per_sample.detach(), rtol=1e-11, atol=1e-11), case["name"]
+    assert torch.allclose(torch.exp(o_log_pdf), pdf, rtol=1e-10, atol=1e-300), case["name"]
+
+    rec.update(log_pdf=lst(log_pdf), pdf=lst(pdf), score=float(score), loss=float(loss.detach()),
+               grads=[lst(g) for g in grads], t=lst(h))
+    return rec
+
+
+def compute():
+    FLOWS, DL = tf_shim.load_reference()
+    try:
+        mods = {c: tf_shim.load_reference_module("estimators." + c)
+                for c in ("NormalizingFlowNetwork", "MixtureDensityNetwork", "KernelMixtureNetwork")}
+        rng = np.random.default_rng(22)
+        return {
+            "provenance": {
+                "what": "outputs of the reference's own estimators/{BaseEstimator,MaximumLikelihoodNNEstimator,"
+                        "NormalizingFlowNetwork,MixtureDensityNetwork,KernelMixtureNetwork}.py, imported unmodified "
+                        "from /root/reference and executed on torch-CPU float64 stand-ins for TF / Keras / TFP "
+                        "(oracle/tf_shim.py), with seeded Dense weights",
+                "generator": "python -m oracle.make_reference_estimator_run",
+                "weights_layout": "per Dense layer: kernel [in, units] then bias [units] (Keras layout)",
+                "does_not_pin": "TFP / Keras own arithmetic (restated in the shim), float32 rounding, the Keras "
+                                "training loop and optimizer; KMeans seeding differs from the reference's unseeded call",
+            },
+            "cases": [run_case(c, mods, DL, rng) for c in CASES],
+        }
+    finally:
+        tf_shim.uninstall()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    got = compute()
+    if args.check:
+        with open(OUT) as f:
+            want = json.load(f)
+        m = diff(want, got)
+        print(f"max |fixture - rerun| = {m:.3e}")
+        sys.exit(0 if m <= 1e-12 else 1)
+    with open(OUT, "w") as f:
+        json.dump(got, f)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes;", [c["name"] for c in got["cases"]])
+    for c in got["cases"]:
+        print("  %-34s score %.6f loss %.6f" % (c["name"], c["score"], c["loss"]))
+
+
+if __name__ == "__main__":
+    main()

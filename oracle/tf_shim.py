@@ -32,13 +32,36 @@ REFERENCE_ROOT = "/root/reference"
 _DTYPE = torch.float64
 
 
+class _EagerTensor(torch.Tensor):
+    """torch tensor that, like a TF EagerTensor, combines with NumPy arrays on either side
+    (BaseEstimator.py:85 computes ``ndarray - tensor * ndarray``)."""
+
+
+def _binary(name):
+    base = getattr(torch.Tensor, name)
+
+    def op(self, other):
+        if isinstance(other, (np.ndarray, np.generic, _Variable)):
+            other = _t(other)
+        return base(self, other)
+
+    op.__name__ = name
+    return op
+
+
+for _name in ("__add__", "__radd__", "__sub__", "__rsub__", "__mul__", "__rmul__", "__truediv__", "__rtruediv__"):
+    setattr(_EagerTensor, _name, _binary(_name))
+
+
 def _t(x):
     """tf.convert_to_tensor for the shim's single working dtype."""
     if isinstance(x, _Variable):
         return x.value()
     if isinstance(x, torch.Tensor):
-        return x if x.dtype == _DTYPE else x.to(_DTYPE)
-    return torch.as_tensor(np.asarray(x, dtype=np.float64), dtype=_DTYPE)
+        x = x if x.dtype == _DTYPE else x.to(_DTYPE)
+    else:
+        x = torch.as_tensor(np.asarray(x, dtype=np.float64), dtype=_DTYPE)
+    return x if isinstance(x, _EagerTensor) else x.as_subclass(_EagerTensor)
 
 
 def _softplus(x):
@@ -59,12 +82,16 @@ class _GradientTape:
     non-scalar target is the gradient of its sum (cotangent of ones)."""
 
     def __init__(self, persistent=False):
-        pass
+        self._mode = None
 
     def __enter__(self):
+        # a tape records whatever the caller's torch grad mode is (the harness scores under no_grad)
+        self._mode = torch.enable_grad()
+        self._mode.__enter__()
         return self
 
     def __exit__(self, *exc):
+        self._mode.__exit__(*exc)
         return False
 
     def watch(self, x):
@@ -72,8 +99,11 @@ class _GradientTape:
             x.requires_grad_(True)
 
     def gradient(self, target, source):
-        return torch.autograd.grad(target, source, grad_outputs=torch.ones_like(target),
-                                   create_graph=True)[0]
+        keep = torch.is_grad_enabled()
+        with torch.enable_grad():
+            g = torch.autograd.grad(target, source, grad_outputs=torch.ones_like(target),
+                                    create_graph=True)[0]
+        return g if keep else g.detach()
 
 
 class _Variable:
@@ -181,6 +211,21 @@ class _Invert(_Bijector):
 
 
 # ------------------------------------------------------------------ tfp.distributions
+class _Shape(tuple):
+    """tf.TensorShape: ``TensorShape([d]) == d`` is True (``as_shape(d)``), which
+    BaseEstimator.py:81 relies on (``output.event_shape == y.shape[-1]``)."""
+
+    def __eq__(self, other):
+        if isinstance(other, int):
+            other = (other,)
+        return tuple(self) == tuple(other)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = tuple.__hash__
+
+
 class _Distribution:
     @staticmethod
     def mean(d):
@@ -189,6 +234,9 @@ class _Distribution:
     @staticmethod
     def sample(d):
         raise NotImplementedError
+
+    def prob(self, x):
+        return torch.exp(self.log_prob(x))
 
 
 class _MultivariateNormalDiag(_Distribution):
@@ -208,7 +256,7 @@ class _MultivariateNormalDiag(_Distribution):
 
     @property
     def event_shape(self):
-        return tuple(self.loc.shape[-1:])
+        return _Shape(self.loc.shape[-1:])
 
     @property
     def batch_shape(self):
@@ -234,6 +282,10 @@ class _Mixture(_Distribution):
         self.cat, self.components = cat, list(components)
         assert self.cat.logits.shape[-1] == len(self.components)
 
+    @property
+    def event_shape(self):
+        return self.components[0].event_shape
+
     def log_prob(self, x):
         lp = torch.stack([c.log_prob(x) for c in self.components], -1)
         return torch.logsumexp(lp + torch.log_softmax(self.cat.logits, -1), -1)
@@ -247,6 +299,10 @@ class _MixtureSameFamily(_Distribution):
         self.mixture_distribution = mixture_distribution
         self.components_distribution = components_distribution
 
+    @property
+    def event_shape(self):
+        return self.components_distribution.event_shape
+
     def log_prob(self, x):
         lp = self.components_distribution.log_prob(_t(x)[..., None, :])
         return torch.logsumexp(lp + torch.log_softmax(self.mixture_distribution.logits, -1), -1)
@@ -258,6 +314,10 @@ class _TransformedDistribution(_Distribution):
 
     def __init__(self, distribution=None, bijector=None, **kw):
         self.distribution, self.bijector = distribution, bijector
+
+    @property
+    def event_shape(self):
+        return self.distribution.event_shape
 
     def log_prob(self, y):
         y = _t(y)
@@ -317,14 +377,75 @@ class _Lambda:
         return self.function(x)
 
 
+class _GaussianNoise:
+    """tf.keras.layers.GaussianNoise (BaseEstimator.py:68, MaximumLikelihoodNNEstimator.py:41):
+    identity unless training.  Training-time noise would need TF's RNG stream: not emulated."""
+
+    def __init__(self, stddev, **kw):
+        self.stddev = stddev
+
+    def __call__(self, x, training=False):
+        if training and float(_t(self.stddev)) != 0.0:
+            raise NotImplementedError("training-time GaussianNoise draws are TF-RNG specific")
+        return x
+
+
+class _Dense:
+    """tf.keras.layers.Dense(units, activation) (MaximumLikelihoodNNEstimator.py:42-43):
+    ``activation(x @ kernel + bias)``, kernel [in, units].  Weights are set by the harness
+    (``set_weights``), never initialised here."""
+
+    _ACT = {"linear": lambda v: v, None: lambda v: v, "tanh": torch.tanh, "relu": torch.relu,
+            "sigmoid": torch.sigmoid}
+
+    def __init__(self, units, activation=None, **kw):
+        self.units, self.activation = units, activation
+        self.kernel = self.bias = None
+
+    def set_weights(self, weights):
+        kernel, bias = weights
+        self.kernel, self.bias = _t(kernel), _t(bias)
+        assert self.kernel.shape[1] == self.units and tuple(self.bias.shape) == (self.units,)
+
+    def get_weights(self):
+        return [self.kernel, self.bias]
+
+    def __call__(self, x):
+        assert self.kernel is not None, "Dense weights not set"
+        return self._ACT[self.activation](_t(x) @ self.kernel + self.bias)
+
+
 class _Sequential:
+    """tf.keras.Sequential as BaseEstimator subclasses it (BaseEstimator.py:8, :18, :61-69):
+    layer list, ``add``, ``call(x, training)``, ``__call__`` = inference call; ``compile`` only
+    records its arguments and ``fit`` (the Keras training loop) is not emulated."""
+
     def __init__(self, layers=None, **kw):
         self.layers = list(layers or [])
 
-    def __call__(self, x):
+    def add(self, layer):
+        self.layers.append(layer)
+
+    def call(self, x, training=False):
+        if isinstance(x, np.ndarray) or not isinstance(x, torch.Tensor):
+            x = _t(x)
         for layer in self.layers:
-            x = layer(x)
+            x = layer(x, training=training) if isinstance(layer, _GaussianNoise) else layer(x)
         return x
+
+    def __call__(self, x, training=False):
+        return self.call(x, training=training)
+
+    def compile(self, optimizer=None, loss=None, **kw):
+        self.optimizer, self.loss = optimizer, loss
+
+    def fit(self, *a, **kw):
+        raise NotImplementedError("the Keras training loop is not emulated")
+
+
+class _Adam:
+    def __init__(self, learning_rate=0.001, **kw):
+        self.learning_rate = learning_rate
 
 
 def _module(name, **attrs):
@@ -355,8 +476,12 @@ def install(dtype=torch.float64):
     tf_nn = _module("tensorflow.nn", softplus=_softplus)
     keras = _module(
         "tensorflow.keras",
+        Sequential=_Sequential,
         models=_module("tensorflow.keras.models", Sequential=_Sequential),
-        layers=_module("tensorflow.keras.layers", Lambda=_Lambda),
+        layers=_module("tensorflow.keras.layers", Lambda=_Lambda, GaussianNoise=_GaussianNoise, Dense=_Dense),
+        optimizers=_module("tensorflow.keras.optimizers", Adam=_Adam),
+        callbacks=_module("tensorflow.keras.callbacks", TerminateOnNaN=type("TerminateOnNaN", (), {})),
+        backend=_module("tensorflow.keras.backend", clear_session=lambda: None),
     )
     tf2 = _module("tensorflow.python.tf2", enabled=lambda: True)
     tf_python = _module("tensorflow.python", tf2=tf2)
@@ -369,6 +494,9 @@ def install(dtype=torch.float64):
         float32="float32",
         float64="float64",
         abs=tf_math.abs,
+        reduce_sum=_reduce_sum,
+        reduce_prod=lambda x, axis=None: torch.prod(_t(x)) if axis is None else torch.prod(_t(x), dim=axis),
+        random=_module("tensorflow.random", set_seed=lambda seed: None),
         squeeze=lambda x, axis=None: torch.squeeze(_t(x)) if axis is None else torch.squeeze(_t(x), dim=axis),
         expand_dims=lambda x, axis: torch.unsqueeze(_t(x), axis),
         zeros_like=lambda x: torch.zeros_like(_t(x)),
@@ -402,8 +530,8 @@ def install(dtype=torch.float64):
                   layers=layers)
     tfp.__path__ = []
 
-    for m in (tf, tf_math, tf_nn, keras, keras.models, keras.layers, tf_python, tf2, tfp, bijectors,
-              distributions, layers):
+    for m in (tf, tf_math, tf_nn, keras, keras.models, keras.layers, keras.optimizers, keras.callbacks,
+              keras.backend, tf.random, tf_python, tf2, tfp, bijectors, distributions, layers):
         sys.modules[m.__name__] = m
     return tf, tfp
 
@@ -449,3 +577,16 @@ def load_reference(root=REFERENCE_ROOT, dtype=torch.float64):
     for mod in (flows, layers):
         assert mod.__file__.startswith(root), mod.__file__
     return flows.FLOWS, layers
+
+
+def load_reference_module(name, root=REFERENCE_ROOT):
+    """Import one more of the reference's modules (e.g. ``estimators.NormalizingFlowNetwork``)
+    after ``load_reference()``; same guarantees (unmodified file under ``root``, no bytecode)."""
+    assert getattr(sys.modules.get("estimators"), "__shim__", False), "call load_reference() first"
+    keep, sys.dont_write_bytecode = sys.dont_write_bytecode, True
+    try:
+        mod = importlib.import_module(name)
+    finally:
+        sys.dont_write_bytecode = keep
+    assert mod.__file__.startswith(root), mod.__file__
+    return mod

@@ -212,3 +212,70 @@ def test_cuda_graph_log_pdf_matches_eager(cuda_device):
     assert torch.equal(model.log_pdf_graphed(xd, yd), model.log_pdf(xd, yd))
     perm = torch.randperm(2048, device=xd.device)
     assert torch.equal(model.log_pdf_graphed(xd[perm], yd[perm]), model.log_pdf(xd[perm], yd[perm]))
+
+
+# ----------------------------------------------------------------------------- the reference's own estimator code
+def _reference_estimator_cases():
+    import json
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_estimator_run.json")
+    with open(path) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_estimators_match_reference_code_run(cuda_device, idx):
+    """log_pdf / pdf / score and the train-step gradients against what the reference's OWN
+    BaseEstimator / MaximumLikelihoodNNEstimator / {NFN, MDN, KMN} classes returned for the same data and
+    weights (tests/golden/reference_estimator_run.json, oracle/make_reference_estimator_run.py)."""
+    from normalizingflownetwork_b200 import estimators as E
+
+    c = _reference_estimator_cases()[idx]
+    x, y = np.asarray(c["x"], np.float32), np.asarray(c["y"], np.float32)
+    build = dict(c["build"])
+    for k in ("hidden_sizes", "noise_reg"):
+        if k in build:
+            build[k] = tuple(build[k])
+    model = getattr(E, c["cls"]).build_function(learning_rate=0.0, **build)
+    try:
+        # lr = 0: fit only assigns the normalisation / noise / centres and materialises the lazy weights
+        model.fit(x, y, batch_size=len(x), epochs=1, verbose=0, shuffle=False)
+        for k, v in c["stats"].items():
+            np.testing.assert_allclose(getattr(model, k).cpu().numpy(), np.asarray(v, np.float32), rtol=1e-6, atol=1e-7)
+        assert float(model.x_noise_std) == pytest.approx(c["noise_std"][0], rel=1e-6, abs=1e-12)
+        assert float(model.y_noise_std) == pytest.approx(c["noise_std"][1], rel=1e-6, abs=1e-12)
+        lin = [m.linear for m in model.net if hasattr(m, "linear")]
+        assert 2 * len(lin) == len(c["weights"])
+        with torch.no_grad():
+            for i, l in enumerate(lin):
+                kernel = torch.tensor(c["weights"][2 * i], dtype=torch.float32)  # Keras layout [in, units]
+                l.weight.copy_(kernel.t().to(l.weight.device))
+                l.bias.copy_(torch.tensor(c["weights"][2 * i + 1], dtype=torch.float32).to(l.bias.device))
+            if "locs" in c:
+                locs = torch.tensor(c["locs"], dtype=torch.float32, device=model.dist_layer.locs.device)
+                # the product's own centre selection picked the same centres as the reference's code
+                np.testing.assert_allclose(model.dist_layer.locs.cpu().numpy(), locs.cpu().numpy(), rtol=1e-4, atol=1e-5)
+                model.dist_layer.locs.copy_(locs)
+                np.testing.assert_allclose(model.dist_layer.scale_model().detach().cpu().numpy(), c["scales"],
+                                           rtol=1e-6, atol=1e-7)
+
+        ref_lp = np.asarray(c["log_pdf"])
+        got = model.log_pdf(x, y).cpu().numpy()
+        assert np.max(np.abs(got - ref_lp) / np.maximum(1.0, np.abs(ref_lp))) <= 2e-5, c["name"]
+        np.testing.assert_allclose(model.pdf(x, y).cpu().numpy(), c["pdf"], rtol=1e-4, atol=1e-30)
+        assert model.score(x, y) == pytest.approx(c["score"], rel=2e-5)
+        assert model.evaluate(x, y) == pytest.approx(c["loss"], rel=2e-5)
+
+        model._set_noise(0.0)  # training-time noise draws are RNG specific; the reference run had none either
+        loss = model.train_step(model._to_dev(x), model._to_dev(y))
+        assert float(loss) == pytest.approx(c["loss"], rel=2e-5)
+        for i, l in enumerate(lin):
+            gk = np.asarray(c["grads"][2 * i]).T  # -> torch layout [units, in]
+            gb = np.asarray(c["grads"][2 * i + 1])
+            for got_g, ref_g, what in ((l.weight.grad, gk, "kernel"), (l.bias.grad, gb, "bias")):
+                scale = max(1e-3, float(np.abs(ref_g).max()))
+                err = float(np.abs(got_g.double().cpu().numpy() - ref_g).max())
+                assert err <= 2e-4 * scale, "%s layer %d %s grad err %.3e (scale %.3e)" % (c["name"], i, what, err, scale)
+    finally:
+        model._set_noise(0.0)

@@ -138,3 +138,53 @@ def test_reference_error_behaviour_under_the_shim():
                 torch.zeros((3, 2), dtype=torch.float64))
     finally:
         tf_shim.uninstall()
+
+
+# ----------------------------------------------------------------------------- estimator level
+def test_estimator_fixture_is_self_consistent():
+    """reference_estimator_run.json (the reference's own BaseEstimator / MaximumLikelihoodNNEstimator /
+    NFN / MDN / KMN classes, oracle/make_reference_estimator_run.py): score == -loss == mean log_pdf
+    (reference tests/test_evaluation.py:29), pdf == exp(log_pdf), and the oracle reproduces log_pdf from
+    the recorded network output."""
+    fx = load("reference_estimator_run.json")
+    assert "unmodified" in fx["provenance"]["what"]
+    assert [c["cls"] for c in fx["cases"]] == ["NormalizingFlowNetwork", "NormalizingFlowNetwork",
+                                               "MixtureDensityNetwork", "KernelMixtureNetwork"]
+    for c in fx["cases"]:
+        lp = np.asarray(c["log_pdf"])
+        assert c["score"] == pytest.approx(-c["loss"], rel=1e-13)
+        assert c["score"] == pytest.approx(lp.mean(), rel=1e-12)
+        np.testing.assert_allclose(np.exp(lp), c["pdf"], rtol=1e-10)
+        b, t = c["build"], t64(c["t"])
+        y_mean, y_std = t64(c["stats"]["y_mean"]), t64(c["stats"]["y_std"])
+        y_circ = fo.normalise_y(t64(c["y"]), y_mean, y_std)
+        if c["cls"] == "NormalizingFlowNetwork":
+            o = fo.chain_log_prob(t, y_circ, ["radial"] * b["n_flows"], b["n_dims"], b.get("trainable_base_dist", True))
+        elif c["cls"] == "MixtureDensityNetwork":
+            o = fo.mdn_log_prob(t, y_circ, b["n_centers"], b["n_dims"])
+        else:
+            o = fo.kmn_log_prob(t, y_circ, t64(c["locs"]), t64(c["scales"]))
+        np.testing.assert_allclose(-fo.nll(o, y_std).numpy(), lp, rtol=1e-11, atol=1e-11)
+    # rule-of-thumb noise level (BaseEstimator.py:36-39): 0.2 * (256 + 1) ** (-1 / (4 + 2))
+    assert fx["cases"][3]["noise_std"][0] == pytest.approx(0.2 * 257 ** (-1 / 6), rel=1e-6)
+
+
+def test_kmn_centre_selection_matches_reference_code():
+    """GaussianKernelsLayer.set_center_points (host-side, once per fit) against the centres the reference's
+    own set_center_points chose (DistributionLayers.py:135-171) with the same KMeans seeding."""
+    from normalizingflownetwork_b200.DistributionLayers import GaussianKernelsLayer
+
+    c = load("reference_estimator_run.json")["cases"][3]
+    y = np.asarray(c["y"], np.float32)
+    layer = GaussianKernelsLayer(c["build"]["n_centers"], c["build"]["n_dims"], trainable_scale=True)
+    layer.set_center_points((y - np.mean(y, axis=0, dtype=np.float32)) / np.std(y, axis=0, dtype=np.float32))
+    np.testing.assert_allclose(layer.locs.numpy(), np.asarray(c["locs"], np.float32), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(layer.scale_model().detach().numpy(), c["scales"], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="/root/reference does not travel to the GPU box")
+def test_rerunning_the_reference_estimators_reproduces_the_fixture():
+    from oracle import make_reference_estimator_run as mer
+    from oracle.make_reference_run import diff
+
+    assert diff(load("reference_estimator_run.json"), mer.compute()) <= 1e-12
