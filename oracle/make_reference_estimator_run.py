@@ -148,11 +148,83 @@ def run_case(case, mods, DL, rng):
     return rec
 
 
+BAYES_CASES = [
+    # MAP mode: the posterior mean is used, one "draw" (BayesianNNEstimator.py:71), fully deterministic
+    dict(name="bayes_nfn_map", n=128,
+         build=dict(n_dims=1, kl_weight_scale=1.0 / 128, n_flows=2, hidden_sizes=(10,), activation="tanh",
+                    map_mode=True, prior_scale=1.0)),
+    # 50 posterior draws, logsumexp over them (BayesianNNEstimator.py:65-76); the draws are the harness's
+    dict(name="bayes_nfn_50_draws", n=128,
+         build=dict(n_dims=1, kl_weight_scale=1.0 / 128, n_flows=2, hidden_sizes=(10,), activation="tanh",
+                    map_mode=False, prior_scale=0.7)),
+]
+
+
+def run_bayes_case(case, mod, rng):
+    x, y = reference_cosine(case["n"])
+    b = case["build"]
+    model = mod.BayesNormalizingFlowNetwork.build_function(**b)
+    model._assign_data_normalization(x, y)
+    model._assign_noise_regularisation(n_dims=x.shape[1] + y.shape[1], n_datapoints=x.shape[0])
+    tfp_layers = sys.modules["tensorflow_probability"].layers
+    dv = [l for l in model.layers if isinstance(l, tfp_layers.DenseVariational)]
+    widths = [x.shape[1]] + [l.units for l in dv]
+    post = []
+    for l, fan_in in zip(dv, widths):
+        l.build(fan_in)
+        size = fan_in * l.units + l.units
+        n_var = size if b["map_mode"] else 2 * size
+        assert tuple(l._posterior.layers[0].variable.shape) == (n_var,)
+        v = torch.tensor(rng.normal(0.0, 0.5, size=(n_var,)).astype(np.float32), dtype=F64, requires_grad=True)
+        l._posterior.layers[0].variable = v  # the VariableLayer weight (BayesianNNEstimator.py:100-105)
+        post.append(v)
+    draws = 1 if b["map_mode"] else 50
+    rec = {"name": case["name"], "build": {k: (list(v) if isinstance(v, tuple) else v) for k, v in b.items()},
+           "x": x.tolist(), "y": y.tolist(), "posterior_params": [lst(v) for v in post], "posterior_draws": draws,
+           "stats": {k: np.asarray(getattr(model, k), dtype=np.float64).tolist()
+                     for k in ("x_mean", "x_std", "y_mean", "y_std")}}
+    if not b["map_mode"]:
+        # draw s consumes one standard-normal vector per DenseVariational layer, in layer order
+        eps = [rng.normal(size=(draws, v.shape[0] // 2)).astype(np.float32) for v in post]
+        tf_shim.push_draws([eps[l][s] for s in range(draws) for l in range(len(dv))])
+        rec["eps"] = [e.tolist() for e in eps]
+    with torch.no_grad():
+        rec["score"] = float(model.score(x, y))  # the reference's own draw loop + logsumexp - log S
+    if b["map_mode"]:
+        with torch.no_grad():
+            rec["log_pdf"], rec["pdf"] = lst(model.log_pdf(x, y)), lst(model.pdf(x, y))
+    else:
+        tf_shim.push_draws([np.zeros(v.shape[0] // 2) for v in post])  # eps = 0: the KL below does not depend on it
+    nll = model._get_neg_log_likelihood()
+    per_sample = nll(y, model.call(x, training=False))
+    kls = model.losses  # what DenseVariational added through add_loss; Keras adds them to the compiled loss
+    assert len(kls) == len(dv)
+    rec["kl"] = [float(k.detach()) for k in kls]
+    if b["map_mode"]:
+        loss = per_sample.mean() + sum(kls)
+        rec["loss"] = float(loss.detach())
+        rec["grads"] = [lst(g) for g in torch.autograd.grad(loss, post)]
+        assert abs(rec["score"] + float(per_sample.detach().mean())) <= 1e-12
+    # independent restatement of the exact Normal-Normal KL (DistributionLayers.py:42-68 parameterisation)
+    for v, k, l in zip(post, rec["kl"], dv):
+        v = v.detach()
+        size = v.shape[0] if b["map_mode"] else v.shape[0] // 2
+        loc = v[:size]
+        sq = torch.ones(size, dtype=F64) if b["map_mode"] else \
+            1e-3 + torch.nn.functional.softplus(fo.LOG_EXPM1_1 + 0.05 * v[size:])
+        sr = b["prior_scale"]
+        want = b["kl_weight_scale"] * float(torch.sum(torch.log(sr / sq) + (sq ** 2 + loc ** 2) / (2 * sr ** 2) - 0.5))
+        assert abs(want - k) <= 1e-12 * max(1.0, abs(want)), (case["name"], want, k)
+    assert not tf_shim._EPS_QUEUE, "queued draws left over"
+    return rec
+
+
 def compute():
     FLOWS, DL = tf_shim.load_reference()
     try:
         mods = {c: tf_shim.load_reference_module("estimators." + c)
-                for c in ("NormalizingFlowNetwork", "MixtureDensityNetwork", "KernelMixtureNetwork")}
+                for c in ("NormalizingFlowNetwork", "MixtureDensityNetwork", "KernelMixtureNetwork",
+                          "BayesNormalizingFlowNetwork")}
         rng = np.random.default_rng(22)
         return {
             "provenance": {
@@ -166,6 +238,7 @@ def compute():
                                 "training loop and optimizer; KMeans seeding differs from the reference's unseeded call",
             },
             "cases": [run_case(c, mods, DL, rng) for c in CASES],
+            "bayes_cases": [run_bayes_case(c, mods["BayesNormalizingFlowNetwork"], rng) for c in BAYES_CASES],
         }
     finally:
         tf_shim.uninstall()
@@ -187,6 +260,8 @@ def main():
     print("wrote", OUT, os.path.getsize(OUT), "bytes;", [c["name"] for c in got["cases"]])
     for c in got["cases"]:
         print("  %-34s score %.6f loss %.6f" % (c["name"], c["score"], c["loss"]))
+    for c in got["bayes_cases"]:
+        print("  %-34s score %.6f kl %s" % (c["name"], c["score"], c["kl"]))
 
 
 if __name__ == "__main__":

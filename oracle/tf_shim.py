@@ -226,14 +226,23 @@ class _Shape(tuple):
     __hash__ = tuple.__hash__
 
 
-class _Distribution:
-    @staticmethod
-    def mean(d):
-        raise NotImplementedError
+_EPS_QUEUE = []  # standard-normal draws handed to ``sample()`` in order (filled by the harness)
 
-    @staticmethod
-    def sample(d):
-        raise NotImplementedError
+
+def push_draws(eps_list):
+    """Queue the standard-normal draws the next ``sample()`` calls consume (one array per call):
+    TF's RNG stream cannot be reproduced, so the harness owns the randomness and records it."""
+    _EPS_QUEUE.extend(_t(e) for e in eps_list)
+
+
+class _Distribution:
+    # DistributionLayers.py:36: ``tfd.Distribution.mean if map_mode else tfd.Distribution.sample`` is the
+    # layer's convert_to_tensor_fn, i.e. these are called unbound with the distribution as ``self``
+    def mean(self):
+        return self._mean()
+
+    def sample(self):
+        return self._sample()
 
     def prob(self, x):
         return torch.exp(self.log_prob(x))
@@ -330,6 +339,15 @@ class _Normal(_Distribution):
     def __init__(self, loc=None, scale=None, **kw):
         self.loc, self.scale = _t(loc), _t(scale)
 
+    def _mean(self):
+        return self.loc + torch.zeros_like(self.scale)
+
+    def _sample(self):
+        assert _EPS_QUEUE, "sample() without queued draws (oracle.tf_shim.push_draws)"
+        eps = _EPS_QUEUE.pop(0)
+        assert tuple(eps.shape) == tuple(torch.broadcast_shapes(self.loc.shape, self.scale.shape))
+        return self.loc + self.scale * eps
+
     def log_prob(self, x):
         e = (_t(x) - self.loc) / self.scale
         return -0.5 * e * e - torch.log(self.scale) - 0.5 * math.log(2.0 * math.pi)
@@ -343,6 +361,21 @@ class _Independent(_Distribution):
         lp = self.distribution.log_prob(x)
         return torch.sum(lp, dim=tuple(range(-self.n, 0)))
 
+    def _mean(self):
+        return self.distribution._mean()
+
+    def _sample(self):
+        return self.distribution._sample()
+
+
+def _kl_divergence(q, r):
+    """tfd.kl_divergence for Independent(Normal) pairs (the only pair on this path): the sum over
+    the reinterpreted dims of  log(s_r / s_q) + (s_q^2 + (m_q - m_r)^2) / (2 s_r^2) - 1/2."""
+    assert isinstance(q, _Independent) and isinstance(r, _Independent) and q.n == r.n
+    a, b = q.distribution, r.distribution
+    kl = torch.log(b.scale / a.scale) + (a.scale ** 2 + (a.loc - b.loc) ** 2) / (2.0 * b.scale ** 2) - 0.5
+    return torch.sum(kl, dim=tuple(range(-q.n, 0)))
+
 
 # ------------------------------------------------------------------ tfp.layers / tf.keras
 class _DistributionLambda:
@@ -353,14 +386,56 @@ class _DistributionLambda:
         self._convert_to_tensor_fn = convert_to_tensor_fn
 
     def __call__(self, t):
-        return self._make_distribution_fn(_t(t))
+        d = self._make_distribution_fn(_t(t))
+        d._convert_to_tensor_fn = self._convert_to_tensor_fn  # what tf.convert_to_tensor(d) would apply
+        return d
+
+
+class _DenseVariational:
+    """tfp.layers.DenseVariational (BayesianNNEstimator.py:128-148), restated from TFP's documented
+    behaviour: q = posterior(x), r = prior(x); the layer adds ``kl_weight * KL`` as a scalar loss (exact
+    KL, or the one-sample estimate log q(w) - log r(w)); w = convert_to_tensor(q) is split into
+    kernel = reshape(w[:in * units], [in, units]) and bias = w[in * units:]; out = act(x @ kernel + bias)."""
+
+    def __init__(self, units, make_posterior_fn=None, make_prior_fn=None, kl_weight=None, kl_use_exact=False,
+                 activation=None, use_bias=True, **kw):
+        assert use_bias
+        self.units, self.activation = units, activation
+        self._make_posterior_fn, self._make_prior_fn = make_posterior_fn, make_prior_fn
+        self.kl_weight, self.kl_use_exact = kl_weight, kl_use_exact
+        self._posterior = self._prior = None
+        self.losses = []
+
+    def build(self, in_features):
+        self.in_features = in_features
+        self._posterior = self._make_posterior_fn(in_features * self.units, self.units, None)
+        self._prior = self._make_prior_fn(in_features * self.units, self.units, None)
+
+    def __call__(self, x):
+        x = _t(x)
+        if self._posterior is None:
+            self.build(x.shape[-1])
+        q, r = self._posterior(x), self._prior(x)
+        w = q._convert_to_tensor_fn(q)
+        if self.kl_use_exact:
+            kl = _kl_divergence(q, r)
+        else:
+            kl = q.log_prob(w) - r.log_prob(w)
+        if self.kl_weight is not None:
+            kl = self.kl_weight * kl
+        self.losses = [torch.sum(kl)]
+        nk = self.in_features * self.units
+        kernel, bias = w[..., :nk].reshape(self.in_features, self.units), w[..., nk:]
+        return _Dense._ACT[self.activation](x @ kernel + bias)
 
 
 class _VariableLayer:
     """tfp.layers.VariableLayer (DistributionLayers.py:80-85): ignores its input."""
 
     def __init__(self, shape=None, dtype=None, initializer="zeros", trainable=True, **kw):
-        assert initializer == "zeros"
+        # "normal" (BayesianNNEstimator.py:102) is Keras RandomNormal(stddev=0.05); the harness overwrites
+        # ``variable`` with seeded values, so both initialisers start from zeros here
+        assert initializer in ("zeros", "normal")
         n = shape if isinstance(shape, int) else int(np.prod(shape))
         self.variable = torch.zeros(n, dtype=_DTYPE)
         self.trainable = trainable
@@ -436,6 +511,11 @@ class _Sequential:
     def __call__(self, x, training=False):
         return self.call(x, training=training)
 
+    @property
+    def losses(self):
+        """Keras ``model.losses``: the scalars layers added during the last call (added to the compiled loss)."""
+        return [l for layer in self.layers for l in getattr(layer, "losses", [])]
+
     def compile(self, optimizer=None, loss=None, **kw):
         self.optimizer, self.loss = optimizer, loss
 
@@ -472,6 +552,7 @@ def install(dtype=torch.float64):
         log=lambda x: torch.log(_t(x)),
         abs=lambda x: torch.abs(_t(x)),
         expm1=lambda x: torch.expm1(_t(x)),
+        reduce_logsumexp=lambda x, axis=None: torch.logsumexp(_t(x), dim=axis),
     )
     tf_nn = _module("tensorflow.nn", softplus=_softplus)
     keras = _module(
@@ -525,7 +606,7 @@ def install(dtype=torch.float64):
         Independent=_Independent,
     )
     layers = _module("tensorflow_probability.layers", DistributionLambda=_DistributionLambda,
-                     VariableLayer=_VariableLayer)
+                     VariableLayer=_VariableLayer, DenseVariational=_DenseVariational)
     tfp = _module("tensorflow_probability", bijectors=bijectors, distributions=distributions,
                   layers=layers)
     tfp.__path__ = []

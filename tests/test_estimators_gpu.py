@@ -279,3 +279,65 @@ def test_estimators_match_reference_code_run(cuda_device, idx):
                 assert err <= 2e-4 * scale, "%s layer %d %s grad err %.3e (scale %.3e)" % (c["name"], i, what, err, scale)
     finally:
         model._set_noise(0.0)
+
+
+@pytest.mark.parametrize("idx", range(2))
+def test_bayesian_estimator_matches_reference_code_run(cuda_device, idx, monkeypatch):
+    """BayesNormalizingFlowNetwork against the reference's OWN BayesianNNEstimator code
+    (tests/golden/reference_estimator_run.json "bayes_cases"): MAP mode (deterministic: log_pdf, pdf, score,
+    loss incl. the exact KL terms, posterior-parameter gradients) and the 50-draw posterior-predictive score
+    with the SAME weight draws (the fixture records them; torch.randn is patched to hand them out)."""
+    import json
+    import os
+
+    from normalizingflownetwork_b200 import estimators as E
+    from normalizingflownetwork_b200.estimators.BayesianNNEstimator import DenseVariational
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_estimator_run.json")
+    with open(path) as f:
+        c = json.load(f)["bayes_cases"][idx]
+    x, y = np.asarray(c["x"], np.float32), np.asarray(c["y"], np.float32)
+    build = dict(c["build"])
+    build["hidden_sizes"] = tuple(build["hidden_sizes"])
+    model = E.BayesNormalizingFlowNetwork.build_function(learning_rate=0.0, **build)
+    model.fit(x, y, batch_size=len(x), epochs=1, verbose=0, shuffle=False)  # lr = 0: set-up only
+    layers = [l for l in model.net if isinstance(l, DenseVariational)]
+    assert len(layers) == len(c["posterior_params"])
+    with torch.no_grad():
+        for l, v in zip(layers, c["posterior_params"]):
+            assert l.posterior_params.numel() == len(v)
+            l.posterior_params.copy_(torch.tensor(v, dtype=torch.float32).to(l.posterior_params.device))
+
+    if build["map_mode"]:
+        ref_lp = np.asarray(c["log_pdf"])
+        got = model.log_pdf(x, y).cpu().numpy()
+        assert np.max(np.abs(got - ref_lp) / np.maximum(1.0, np.abs(ref_lp))) <= 2e-5
+        np.testing.assert_allclose(model.pdf(x, y).cpu().numpy(), c["pdf"], rtol=1e-4, atol=1e-30)
+        assert model.score(x, y) == pytest.approx(c["score"], rel=2e-5)
+        assert model.evaluate(x, y) == pytest.approx(c["loss"], rel=2e-5)
+        for l, kl in zip(layers, c["kl"]):
+            assert float(l.last_kl) == pytest.approx(kl, rel=1e-5)
+        loss = model.train_step(model._to_dev(x), model._to_dev(y))
+        assert float(loss) == pytest.approx(c["loss"], rel=2e-5)
+        for l, g in zip(layers, c["grads"]):
+            g = np.asarray(g)
+            err = float(np.abs(l.posterior_params.grad.double().cpu().numpy() - g).max())
+            assert err <= 2e-4 * max(1e-3, float(np.abs(g).max())), err
+    else:
+        queue = [torch.tensor(e, dtype=torch.float32) for e in c["eps"]]  # per layer: [draws, size]
+
+        def handed_out(*shape, device=None, generator=None, **kw):
+            shape = tuple(shape[0]) if len(shape) == 1 and not isinstance(shape[0], int) else tuple(shape)
+            e = queue.pop(0)
+            assert tuple(e.shape) == shape, (e.shape, shape)
+            return e.to(device)
+
+        monkeypatch.setattr(torch, "randn", handed_out)
+        try:
+            score = model.score(x, y)
+        finally:
+            monkeypatch.undo()
+        assert not queue
+        assert score == pytest.approx(c["score"], rel=2e-5)
+        for l, kl in zip(layers, c["kl"]):
+            assert float(l.last_kl) == pytest.approx(kl, rel=1e-5)

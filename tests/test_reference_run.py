@@ -188,3 +188,44 @@ def test_rerunning_the_reference_estimators_reproduces_the_fixture():
     from oracle.make_reference_run import diff
 
     assert diff(load("reference_estimator_run.json"), mer.compute()) <= 1e-12
+
+
+def test_bayesian_fixture_matches_oracle_draw_loop():
+    """The reference's BayesianNNEstimator.score (50 weight draws -> logsumexp - log 50 -> mean,
+    BayesianNNEstimator.py:65-76) and MAP-mode log_pdf, re-derived with the oracle from the recorded
+    posterior parameters and draws."""
+    fx = load("reference_estimator_run.json")
+    assert [c["name"] for c in fx["bayes_cases"]] == ["bayes_nfn_map", "bayes_nfn_50_draws"]
+    for c in fx["bayes_cases"]:
+        b = c["build"]
+        x, y = t64(c["x"]), t64(c["y"])
+        st = {k: t64(v) for k, v in c["stats"].items()}
+        h0 = (x - st["x_mean"]) / t64(np.asarray(c["stats"]["x_std"], np.float32) + 1e-8)
+        y_circ = fo.normalise_y(y, st["y_mean"], st["y_std"])
+        S = c["posterior_draws"]
+        assert S == (1 if b["map_mode"] else 50)
+        scores = []
+        for s in range(S):
+            h = h0
+            for li, v in enumerate(c["posterior_params"]):
+                v = t64(v)
+                units = b["hidden_sizes"][li] if li < len(b["hidden_sizes"]) else None
+                size = v.shape[0] if b["map_mode"] else v.shape[0] // 2
+                fan_in = h.shape[1]
+                units = size // (fan_in + 1)
+                if b["map_mode"]:
+                    w = v
+                else:  # MeanFieldLayer (DistributionLayers.py:42-56)
+                    scale = 1e-3 + torch.nn.functional.softplus(fo.LOG_EXPM1_1 + 0.05 * v[size:])
+                    w = v[:size] + scale * t64(c["eps"][li][s])
+                h = h @ w[: fan_in * units].reshape(fan_in, units) + w[fan_in * units:]
+                if li < len(c["posterior_params"]) - 1:
+                    h = torch.tanh(h)
+            lp = fo.chain_log_prob(h, y_circ, ["radial"] * b["n_flows"], b["n_dims"], True)
+            scores.append(-fo.nll(lp, st["y_std"]))
+        scores = torch.stack(scores)
+        got = (torch.logsumexp(scores, 0) - np.log(S)).mean()
+        assert float(got) == pytest.approx(c["score"], rel=1e-11)
+        if b["map_mode"]:
+            np.testing.assert_allclose(scores[0].numpy(), c["log_pdf"], rtol=1e-11, atol=1e-11)
+            assert c["loss"] == pytest.approx(-c["score"] + sum(c["kl"]), rel=1e-12)
