@@ -60,6 +60,29 @@ def reference_cosine(n):
     return mod.gen_cosine_noise_data(n, noise_std=0.3, heterosced_noise=0.5)  # demo.py:14
 
 
+def reference_scorers():
+    """evaluation/scorers.py (NumPy / SciPy only), loaded by path so evaluation/__init__.py stays out."""
+    import contextlib
+    import io
+
+    spec = importlib.util.spec_from_file_location(
+        "_ref_scorers", os.path.join(tf_shim.REFERENCE_ROOT, "evaluation", "scorers.py"))
+    mod = importlib.util.module_from_spec(spec)
+    keep, sys.dont_write_bytecode = sys.dont_write_bytecode, True
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.dont_write_bytecode = keep
+
+    def quiet(fn):  # bayesian_log_likelihood_score prints two shapes per draw (scorers.py:24-26)
+        def call(model, x, y):
+            with contextlib.redirect_stdout(io.StringIO()), torch.no_grad():
+                return float(fn(mod.DummySklearWrapper(model), x, y))
+        return call
+
+    return quiet(mod.mle_log_likelihood_score), quiet(mod.bayesian_log_likelihood_score)
+
+
 def make_data(kind, n, rng):
     if kind == "cosine":
         return reference_cosine(n)
@@ -143,8 +166,10 @@ def run_case(case, mods, DL, rng):
     assert torch.allclose(fo.nll(o_lp, y_std), per_sample.detach(), rtol=1e-11, atol=1e-11), case["name"]
     assert torch.allclose(torch.exp(o_log_pdf), pdf, rtol=1e-10, atol=1e-300), case["name"]
 
+    scorer = reference_scorers()[0](model, x, y)  # evaluation/scorers.py:30-34
+    assert abs(scorer - float(score)) <= 1e-12 * max(1.0, abs(scorer))
     rec.update(log_pdf=lst(log_pdf), pdf=lst(pdf), score=float(score), loss=float(loss.detach()),
-               grads=[lst(g) for g in grads], t=lst(h))
+               grads=[lst(g) for g in grads], t=lst(h), scorer_mle=scorer)
     return rec
 
 
@@ -190,6 +215,10 @@ def run_bayes_case(case, mod, rng):
         rec["eps"] = [e.tolist() for e in eps]
     with torch.no_grad():
         rec["score"] = float(model.score(x, y))  # the reference's own draw loop + logsumexp - log S
+    if not b["map_mode"]:
+        tf_shim.push_draws([eps[l][s] for s in range(draws) for l in range(len(dv))])  # same draws again
+    rec["scorer_bayes"] = reference_scorers()[1](model, x, y)  # evaluation/scorers.py:13-27 (scipy logsumexp)
+    assert abs(rec["scorer_bayes"] - rec["score"]) <= 1e-12 * max(1.0, abs(rec["score"]))
     if b["map_mode"]:
         with torch.no_grad():
             rec["log_pdf"], rec["pdf"] = lst(model.log_pdf(x, y)), lst(model.pdf(x, y))

@@ -266,6 +266,10 @@ def test_estimators_match_reference_code_run(cuda_device, idx):
         np.testing.assert_allclose(model.pdf(x, y).cpu().numpy(), c["pdf"], rtol=1e-4, atol=1e-30)
         assert model.score(x, y) == pytest.approx(c["score"], rel=2e-5)
         assert model.evaluate(x, y) == pytest.approx(c["loss"], rel=2e-5)
+        from normalizingflownetwork_b200.evaluation import scorers  # reference evaluation/scorers.py:30-34
+
+        assert scorers.mle_log_likelihood_score(scorers.DummySklearWrapper(model), x, y) == \
+            pytest.approx(c["scorer_mle"], rel=2e-5)
 
         model._set_noise(0.0)  # training-time noise draws are RNG specific; the reference run had none either
         loss = model.train_step(model._to_dev(x), model._to_dev(y))
@@ -315,6 +319,10 @@ def test_bayesian_estimator_matches_reference_code_run(cuda_device, idx, monkeyp
         np.testing.assert_allclose(model.pdf(x, y).cpu().numpy(), c["pdf"], rtol=1e-4, atol=1e-30)
         assert model.score(x, y) == pytest.approx(c["score"], rel=2e-5)
         assert model.evaluate(x, y) == pytest.approx(c["loss"], rel=2e-5)
+        from normalizingflownetwork_b200.evaluation import scorers  # reference evaluation/scorers.py:13-27
+
+        assert scorers.bayesian_log_likelihood_score(scorers.DummySklearWrapper(model), x, y) == \
+            pytest.approx(c["scorer_bayes"], rel=2e-5)
         for l, kl in zip(layers, c["kl"]):
             assert float(l.last_kl) == pytest.approx(kl, rel=1e-5)
         loss = model.train_step(model._to_dev(x), model._to_dev(y))
