@@ -189,6 +189,39 @@ def _run_all(FLOWS, DL, ka, cv, mv):
     }
 
 
+def compute_f32():
+    """The same reference code executed in float32 (the reference's working precision) on the chain and
+    MDN inputs: how far the reference's OWN float32 evaluation sits from the float64 truth.  Context for the
+    parity tolerances (tools/accuracy_report.py); float32 results may differ in the last bits across CPUs, so
+    this file is not part of the rerun-equality check."""
+    FLOWS, DL = tf_shim.load_reference(dtype=torch.float32)
+    try:
+        out = {"provenance": "reference flow / layer code on torch-CPU float32 stand-ins (oracle/tf_shim.py); "
+                             "python -m oracle.make_reference_run --f32", "chains": [], "mdn": []}
+        f32 = lambda a, grad=False: torch.tensor(np.asarray(a, dtype=np.float32), requires_grad=grad)
+        for c in load("chain_vectors.json"):
+            layer = DL.InverseNormalizingFlowLayer(c["flow_types"], c["n_dims"],
+                                                   trainable_base_dist=c["trainable_base_dist"])
+            t, y = f32(c["t"], True), f32(c["y"], True)
+            logp = layer(t).log_prob(y)
+            assert logp.dtype == torch.float32
+            dt, dy = torch.autograd.grad(logp, [t, y], grad_outputs=f32(c["upstream"]))
+            out["chains"].append({"name": c["name"], "sigma": c["sigma"], "log_prob": lst(logp),
+                                  "dt": lst(dt), "dy": lst(dy)})
+        for c in load("mixture_vectors.json")["mdn"]:
+            layer = DL.GaussianMixtureLayer(c["n_centers"], c["n_dims"])
+            t, y = f32(c["t"], True), f32(c["y"], True)
+            logp = layer(t).log_prob(y)
+            dt, dy = torch.autograd.grad(logp, [t, y], grad_outputs=f32(c["upstream"]))
+            out["mdn"].append({"name": c["name"], "sigma": c["sigma"], "log_prob": lst(logp),
+                               "dt": lst(dt), "dy": lst(dy)})
+        return out
+    finally:
+        tf_shim.uninstall()
+        tf_shim.install(torch.float64)  # leave the module-level dtype as it was
+        tf_shim.uninstall()
+
+
 def diff(a, b, path=""):
     """Largest absolute difference between two nested fixtures (structure must match)."""
     if isinstance(a, dict):
@@ -206,7 +239,14 @@ def diff(a, b, path=""):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true", help="recompute and compare with the committed fixture")
+    ap.add_argument("--f32", action="store_true", help="write reference_run_f32.json (reference code in float32)")
     args = ap.parse_args()
+    if args.f32:
+        out = os.path.join(GOLDEN, "reference_run_f32.json")
+        with open(out, "w") as f:
+            json.dump(compute_f32(), f)
+        print("wrote", out, os.path.getsize(out), "bytes")
+        return
     got = compute()
     if args.check:
         with open(OUT) as f:

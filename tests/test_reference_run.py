@@ -229,3 +229,23 @@ def test_bayesian_fixture_matches_oracle_draw_loop():
         if b["map_mode"]:
             np.testing.assert_allclose(scores[0].numpy(), c["log_pdf"], rtol=1e-11, atol=1e-11)
             assert c["loss"] == pytest.approx(-c["score"] + sum(c["kl"]), rel=1e-12)
+
+
+def test_reference_code_in_float32_sits_within_the_parity_bars():
+    """reference_run_f32.json: the reference's own code in its working precision (float32) against its
+    float64 run.  The GPU parity bars (1e-5 log-prob, 1e-4 gradients) are an order of magnitude above what
+    the reference itself loses to rounding, so they do not hide formula differences
+    (profiles/r01_accuracy_vs_reference_fp32.md has the CUDA columns)."""
+    ref, f32 = load("reference_run.json"), load("reference_run_f32.json")
+    worst_lp = worst_dt = 0.0
+    for (r, h) in list(zip(ref["chains"], f32["chains"])) + list(zip(ref["mixtures"]["mdn"], f32["mdn"])):
+        assert (r["name"], r["sigma"]) == (h["name"], h["sigma"])
+        for key in ("log_prob", "dt"):
+            a = np.asarray(h[key], dtype=np.float64)
+            b = np.asarray(r[key], dtype=np.float64).reshape(a.shape)
+            e = float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))))
+            if key == "log_prob":
+                worst_lp = max(worst_lp, e)
+            else:
+                worst_dt = max(worst_dt, e)
+    assert 1e-8 < worst_lp < 2e-6 and 1e-8 < worst_dt < 2e-5, (worst_lp, worst_dt)
