@@ -182,13 +182,27 @@ BAYES_CASES = [
     dict(name="bayes_nfn_50_draws", n=128,
          build=dict(n_dims=1, kl_weight_scale=1.0 / 128, n_flows=2, hidden_sizes=(10,), activation="tanh",
                     map_mode=False, prior_scale=0.7)),
+    dict(name="bayes_mdn_50_draws", cls="BayesMixtureDensityNetwork", data="gauss2", n=96,
+         build=dict(n_dims=2, kl_weight_scale=1.0 / 96, n_centers=3, hidden_sizes=(10,), activation="tanh",
+                    map_mode=False, prior_scale=1.0)),
+    dict(name="bayes_kmn_map", cls="BayesKernelMixtureNetwork", data="cosine", n=128,
+         build=dict(n_dims=1, kl_weight_scale=1.0 / 128, n_centers=6, hidden_sizes=(10,), activation="tanh",
+                    map_mode=True, prior_scale=1.0)),
 ]
 
 
-def run_bayes_case(case, mod, rng):
-    x, y = reference_cosine(case["n"])
+def run_bayes_case(case, mods, DL, rng):
+    from sklearn.cluster import KMeans
+
+    x, y = make_data(case.get("data", "cosine"), case["n"], rng)
     b = case["build"]
-    model = mod.BayesNormalizingFlowNetwork.build_function(**b)
+    cls = case.get("cls", "BayesNormalizingFlowNetwork")
+    model = getattr(mods[cls], cls).build_function(**b)
+    kmn = {}
+    if cls == "BayesKernelMixtureNetwork":  # BayesKernelMixtureNetwork.py:47-50
+        DL.KMeans = lambda n_clusters, n_jobs=None: KMeans(n_clusters=n_clusters, n_init=10, random_state=22)
+        model.dist_layer.set_center_points((y - np.mean(y, axis=0, dtype=np.float32)) / np.std(y, axis=0, dtype=np.float32))
+        kmn = {"locs": lst(model.dist_layer.locs[0]), "scales": lst(model.dist_layer.scale_model(0.0))}
     model._assign_data_normalization(x, y)
     model._assign_noise_regularisation(n_dims=x.shape[1] + y.shape[1], n_datapoints=x.shape[0])
     tfp_layers = sys.modules["tensorflow_probability"].layers
@@ -204,7 +218,8 @@ def run_bayes_case(case, mod, rng):
         l._posterior.layers[0].variable = v  # the VariableLayer weight (BayesianNNEstimator.py:100-105)
         post.append(v)
     draws = 1 if b["map_mode"] else 50
-    rec = {"name": case["name"], "build": {k: (list(v) if isinstance(v, tuple) else v) for k, v in b.items()},
+    rec = {"name": case["name"], "cls": cls, **kmn,
+           "build": {k: (list(v) if isinstance(v, tuple) else v) for k, v in b.items()},
            "x": x.tolist(), "y": y.tolist(), "posterior_params": [lst(v) for v in post], "posterior_draws": draws,
            "stats": {k: np.asarray(getattr(model, k), dtype=np.float64).tolist()
                      for k in ("x_mean", "x_std", "y_mean", "y_std")}}
@@ -253,7 +268,7 @@ def compute():
     try:
         mods = {c: tf_shim.load_reference_module("estimators." + c)
                 for c in ("NormalizingFlowNetwork", "MixtureDensityNetwork", "KernelMixtureNetwork",
-                          "BayesNormalizingFlowNetwork")}
+                          "BayesNormalizingFlowNetwork", "BayesMixtureDensityNetwork", "BayesKernelMixtureNetwork")}
         rng = np.random.default_rng(22)
         return {
             "provenance": {
@@ -267,7 +282,7 @@ def compute():
                                 "training loop and optimizer; KMeans seeding differs from the reference's unseeded call",
             },
             "cases": [run_case(c, mods, DL, rng) for c in CASES],
-            "bayes_cases": [run_bayes_case(c, mods["BayesNormalizingFlowNetwork"], rng) for c in BAYES_CASES],
+            "bayes_cases": [run_bayes_case(c, mods, DL, rng) for c in BAYES_CASES],
         }
     finally:
         tf_shim.uninstall()

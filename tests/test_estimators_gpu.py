@@ -285,7 +285,7 @@ def test_estimators_match_reference_code_run(cuda_device, idx):
         model._set_noise(0.0)
 
 
-@pytest.mark.parametrize("idx", range(2))
+@pytest.mark.parametrize("idx", range(4))
 def test_bayesian_estimator_matches_reference_code_run(cuda_device, idx, monkeypatch):
     """BayesNormalizingFlowNetwork against the reference's OWN BayesianNNEstimator code
     (tests/golden/reference_estimator_run.json "bayes_cases"): MAP mode (deterministic: log_pdf, pdf, score,
@@ -303,8 +303,13 @@ def test_bayesian_estimator_matches_reference_code_run(cuda_device, idx, monkeyp
     x, y = np.asarray(c["x"], np.float32), np.asarray(c["y"], np.float32)
     build = dict(c["build"])
     build["hidden_sizes"] = tuple(build["hidden_sizes"])
-    model = E.BayesNormalizingFlowNetwork.build_function(learning_rate=0.0, **build)
+    model = getattr(E, c["cls"]).build_function(learning_rate=0.0, **build)
     model.fit(x, y, batch_size=len(x), epochs=1, verbose=0, shuffle=False)  # lr = 0: set-up only
+    if "locs" in c:
+        locs = torch.tensor(c["locs"], dtype=torch.float32, device=model.dist_layer.locs.device)
+        np.testing.assert_allclose(model.dist_layer.locs.cpu().numpy(), locs.cpu().numpy(), rtol=1e-4, atol=1e-5)
+        with torch.no_grad():
+            model.dist_layer.locs.copy_(locs)
     layers = [l for l in model.net if isinstance(l, DenseVariational)]
     assert len(layers) == len(c["posterior_params"])
     with torch.no_grad():

@@ -195,7 +195,12 @@ def test_bayesian_fixture_matches_oracle_draw_loop():
     BayesianNNEstimator.py:65-76) and MAP-mode log_pdf, re-derived with the oracle from the recorded
     posterior parameters and draws."""
     fx = load("reference_estimator_run.json")
-    assert [c["name"] for c in fx["bayes_cases"]] == ["bayes_nfn_map", "bayes_nfn_50_draws"]
+    assert [c["name"] for c in fx["bayes_cases"]] == ["bayes_nfn_map", "bayes_nfn_50_draws", "bayes_mdn_50_draws",
+                                                      "bayes_kmn_map"]
+    # with the six classes of "cases" + "bayes_cases" every entry of the reference's ESTIMATORS dict has been run
+    assert {c["cls"] for c in fx["cases"]} | {c["cls"] for c in fx["bayes_cases"]} == {
+        "NormalizingFlowNetwork", "MixtureDensityNetwork", "KernelMixtureNetwork", "BayesNormalizingFlowNetwork",
+        "BayesMixtureDensityNetwork", "BayesKernelMixtureNetwork"}
     for c in fx["bayes_cases"]:
         b = c["build"]
         x, y = t64(c["x"]), t64(c["y"])
@@ -221,7 +226,12 @@ def test_bayesian_fixture_matches_oracle_draw_loop():
                 h = h @ w[: fan_in * units].reshape(fan_in, units) + w[fan_in * units:]
                 if li < len(c["posterior_params"]) - 1:
                     h = torch.tanh(h)
-            lp = fo.chain_log_prob(h, y_circ, ["radial"] * b["n_flows"], b["n_dims"], True)
+            if c["cls"] == "BayesNormalizingFlowNetwork":
+                lp = fo.chain_log_prob(h, y_circ, ["radial"] * b["n_flows"], b["n_dims"], True)
+            elif c["cls"] == "BayesMixtureDensityNetwork":
+                lp = fo.mdn_log_prob(h, y_circ, b["n_centers"], b["n_dims"])
+            else:
+                lp = fo.kmn_log_prob(h, y_circ, t64(c["locs"]), t64(c["scales"]))
             scores.append(-fo.nll(lp, st["y_std"]))
         scores = torch.stack(scores)
         got = (torch.logsumexp(scores, 0) - np.log(S)).mean()
