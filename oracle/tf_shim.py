@@ -36,12 +36,16 @@ class _EagerTensor(torch.Tensor):
     """torch tensor that, like a TF EagerTensor, combines with NumPy arrays on either side
     (BaseEstimator.py:85 computes ``ndarray - tensor * ndarray``)."""
 
+    def numpy(self):
+        # an EagerTensor's .numpy() never fails because some earlier tape watched an ancestor
+        return torch.Tensor.numpy(self.detach().as_subclass(torch.Tensor))
+
 
 def _binary(name):
     base = getattr(torch.Tensor, name)
 
     def op(self, other):
-        if isinstance(other, (np.ndarray, np.generic, _Variable)):
+        if isinstance(other, (np.ndarray, np.generic, _Variable, list, tuple)):  # TF converts nested lists too
             other = _t(other)
         return base(self, other)
 
@@ -126,13 +130,16 @@ class _Variable:
     def shape(self):
         return self._v.shape
 
+    def numpy(self):
+        return _t(self._v).numpy()
+
     def __mul__(self, other):
         return self._v * _t(other)
 
     __rmul__ = __mul__
 
     def __getitem__(self, i):
-        return self._v[i]
+        return _t(self._v)[i]
 
 
 # ------------------------------------------------------------------ tfp.bijectors
@@ -269,7 +276,7 @@ class _MultivariateNormalDiag(_Distribution):
 
     @property
     def batch_shape(self):
-        return tuple(torch.broadcast_shapes(self.loc.shape, self.scale.shape)[:-1])
+        return _Shape(torch.broadcast_shapes(self.loc.shape, self.scale.shape)[:-1])
 
     def log_prob(self, x):
         e = (_t(x) - self.loc) / self.scale
@@ -289,7 +296,16 @@ class _Mixture(_Distribution):
 
     def __init__(self, cat=None, components=None, **kw):
         self.cat, self.components = cat, list(components)
-        assert self.cat.logits.shape[-1] == len(self.components)
+        # TFP validates the static shapes and raises ValueError (tests/test_distribution_layers.py:51,64)
+        if self.cat.logits.shape[-1] != len(self.components):
+            raise ValueError("cat.num_classes != len(components): %d vs %d"
+                             % (self.cat.logits.shape[-1], len(self.components)))
+        if len({tuple(c.event_shape) for c in self.components}) != 1:
+            raise ValueError("components must all have the same event shape")
+
+    @property
+    def batch_shape(self):
+        return _Shape(self.cat.logits.shape[:-1])
 
     @property
     def event_shape(self):
@@ -307,6 +323,20 @@ class _MixtureSameFamily(_Distribution):
     def __init__(self, mixture_distribution=None, components_distribution=None, **kw):
         self.mixture_distribution = mixture_distribution
         self.components_distribution = components_distribution
+
+    @property
+    def batch_shape(self):
+        return _Shape(self.mixture_distribution.logits.shape[:-1])
+
+    def _sample(self):
+        """One draw per batch member (torch RNG; only its shape is ever looked at,
+        tests/test_distribution_layers.py:118,123)."""
+        comp = self.components_distribution
+        idx = torch.distributions.Categorical(logits=self.mixture_distribution.logits.detach()).sample()
+        loc = (comp.loc + torch.zeros_like(comp.loc / comp.scale)).detach()
+        scale = (comp.scale + torch.zeros_like(loc)).detach().abs()
+        pick = idx[..., None, None].expand(*idx.shape, 1, loc.shape[-1])
+        return _t((loc + scale * torch.randn_like(loc)).gather(-2, pick).squeeze(-2))
 
     @property
     def event_shape(self):
@@ -328,6 +358,10 @@ class _TransformedDistribution(_Distribution):
     def event_shape(self):
         return self.distribution.event_shape
 
+    @property
+    def batch_shape(self):
+        return self.distribution.batch_shape
+
     def log_prob(self, y):
         y = _t(y)
         x = self.bijector.inverse(y)
@@ -338,6 +372,10 @@ class _TransformedDistribution(_Distribution):
 class _Normal(_Distribution):
     def __init__(self, loc=None, scale=None, **kw):
         self.loc, self.scale = _t(loc), _t(scale)
+
+    @property
+    def batch_shape(self):
+        return _Shape(torch.broadcast_shapes(self.loc.shape, self.scale.shape))
 
     def _mean(self):
         return self.loc + torch.zeros_like(self.scale)
@@ -360,6 +398,16 @@ class _Independent(_Distribution):
     def log_prob(self, x):
         lp = self.distribution.log_prob(x)
         return torch.sum(lp, dim=tuple(range(-self.n, 0)))
+
+    @property
+    def batch_shape(self):
+        b = self.distribution.batch_shape
+        return _Shape(b[: len(b) - self.n])
+
+    @property
+    def event_shape(self):
+        b = self.distribution.batch_shape
+        return _Shape(b[len(b) - self.n:])
 
     def _mean(self):
         return self.distribution._mean()
@@ -582,7 +630,8 @@ def install(dtype=torch.float64):
         expand_dims=lambda x, axis: torch.unsqueeze(_t(x), axis),
         zeros_like=lambda x: torch.zeros_like(_t(x)),
         ones_like=lambda x: torch.ones_like(_t(x)),
-        zeros=lambda shape, dtype=None: torch.zeros(shape, dtype=_DTYPE),
+        zeros=lambda shape, dtype=None: _t(torch.zeros(shape, dtype=_DTYPE)),
+        ones=lambda shape, dtype=None: _t(torch.ones(shape, dtype=_DTYPE)),
         constant=lambda v, dtype=None: _t(v),
         concat=lambda values, axis=0: torch.cat([_t(v) for v in values], dim=axis),
         convert_to_tensor=lambda v, dtype=None: _t(v),

@@ -259,3 +259,21 @@ def test_reference_code_in_float32_sits_within_the_parity_bars():
             else:
                 worst_dt = max(worst_dt, e)
     assert 1e-8 < worst_lp < 2e-6 and 1e-8 < worst_dt < 2e-5, (worst_lp, worst_dt)
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="/root/reference does not travel to the GPU box")
+def test_reference_own_unit_tests_pass_on_the_stand_ins():
+    """The reference's own unit tests for this path (tests/test_flows.py, tests/test_distribution_layers.py:
+    shapes, parameter counts, bijector order, exception types, row independence), unmodified, against its own
+    code on the TF / TFP stand-ins: evidence that the restated TFP glue behaves as the reference expects."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""), PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run(
+        [sys.executable, "-m", "pytest", "-p", "oracle.ref_pytest_plugin", "-p", "no:cacheprovider", "--rootdir", "/tmp",
+         "-c", os.devnull, "-q", "/root/reference/tests/test_flows.py", "/root/reference/tests/test_distribution_layers.py"],
+        cwd="/tmp", env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "11 passed" in r.stdout, r.stdout[-500:]
