@@ -89,6 +89,44 @@ def load_traffic(cfg):
     return None
 
 
+class _NearGpuCpus:
+    """Context: bind the calling thread to the CPUs NVML reports as local to GPU `gpu` (NUMA placement of
+    pinned host buffers), restore the previous affinity on exit.  Best effort: any failure leaves the
+    affinity untouched and says so in `note`."""
+
+    def __init__(self, gpu):
+        self.gpu, self.old, self.note = gpu, None, "unchanged"
+
+    def __enter__(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            old = os.sched_getaffinity(0)
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(idx))
+            new = os.sched_getaffinity(0)
+            self.old = old
+            self.note = "%d of %d cpus (NVML ideal affinity of the GPU)" % (len(new), len(old))
+        except Exception as e:  # no NVML, cpuset without the ideal CPUs, ...
+            self.note = "unchanged (%s)" % type(e).__name__
+        return self
+
+    def __exit__(self, *exc):
+        if self.old is not None:
+            try:
+                os.sched_setaffinity(0, self.old)
+            except Exception:
+                pass
+        return False
+
+
 class ClockSampler:
     """SM clock + throttle reasons polled through NVML in a background thread DURING the
     timed region (the region is a few milliseconds, too short for `nvidia-smi -lms`)."""
@@ -401,6 +439,12 @@ def run_ours(args):
     value = B * world * K / (total_ms * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call (pinned host buffers)
+    # the pinned buffers are allocated (first-touched) and the calls issued from the CPUs NVML reports as
+    # local to this GPU, so that on a multi-socket host the buffers do not sit behind the inter-socket link
+    # (the pool's VMs expose one NUMA node, where this is a no-op: "16 of 16 cpus").  The affinity is restored
+    # before the CPU-baseline leg.
+    near = _NearGpuCpus(local_rank)
+    near.__enter__()
     h_t = torch.empty((B, P), dtype=torch.float32).pin_memory()
     h_y = torch.empty((B, d), dtype=torch.float32).pin_memory()
     h_t.copy_(t)
@@ -436,6 +480,7 @@ def run_ours(args):
     e2e_s = parallel.max_over_ranks(time.perf_counter() - t0, device)
     parallel.barrier()
     e2e_value = B * world * e2e_steps / e2e_s
+    near.__exit__(None, None, None)
     h2d = 4 * B * (P + d)
     d2h = 4 * B * (1 + (P if bwd else 0)) + 8
     lib.nfn_host_release()
@@ -470,7 +515,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": ("nfn_mdn_forward_backward_host" if mdn else
                         "nfn_chain_forward_backward_host" if bwd else "nfn_chain_forward_host"),
-                "host_equals_device_bitwise": same},
+                "host_equals_device_bitwise": same, "host_cpus": near.note},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": load_traffic(cfg), "peak_source": peak_src,
