@@ -83,6 +83,39 @@ def reference_scorers():
     return quiet(mod.mle_log_likelihood_score), quiet(mod.bayesian_log_likelihood_score)
 
 
+def reference_plot_model(model, x, y_range, y_num):
+    """evaluation/visualization/flow_plotting.py:33-53 (plot_model), loaded by path with a recording
+    ``matplotlib.pyplot`` stand-in: returns the density heat-map the reference hands to ``imshow``
+    (one ``dist.prob(y_i)`` call per grid line, divided by ``sum(y_std)``)."""
+    import types
+
+    seen = {}
+    plt = types.ModuleType("matplotlib.pyplot")
+    plt.imshow = lambda img, **kw: seen.setdefault("heatmap", np.array(img, dtype=np.float64))
+    for name in ("xlabel", "ylabel", "xticks", "yticks", "colorbar", "plot"):
+        setattr(plt, name, lambda *a, **k: None)
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = plt
+    keep = {k: sys.modules.get(k) for k in ("matplotlib", "matplotlib.pyplot")}
+    sys.modules.update({"matplotlib": mpl, "matplotlib.pyplot": plt})
+    keep_bc, sys.dont_write_bytecode = sys.dont_write_bytecode, True
+    try:
+        spec = importlib.util.spec_from_file_location(
+            "_ref_flow_plotting", os.path.join(tf_shim.REFERENCE_ROOT, "evaluation", "visualization", "flow_plotting.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        with torch.no_grad():
+            mod.plot_model(x, model, y_range, y_num=y_num)
+    finally:
+        sys.dont_write_bytecode = keep_bc
+        for k, v in keep.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return seen["heatmap"]
+
+
 def make_data(kind, n, rng):
     if kind == "cosine":
         return reference_cosine(n)
@@ -168,6 +201,16 @@ def run_case(case, mods, DL, rng):
 
     scorer = reference_scorers()[0](model, x, y)  # evaluation/scorers.py:30-34
     assert abs(scorer - float(score)) <= 1e-12 * max(1.0, abs(scorer))
+    if case["data"] == "cosine" and case["cls"] == "NormalizingFlowNetwork":
+        # the density grid of plot_model (x must be increasing: the cosine x is a linspace)
+        rec["plot_y_range"], rec["plot_y_num"] = [-6.0, 6.0], 16
+        heat = reference_plot_model(model, x, rec["plot_y_range"], rec["plot_y_num"])
+        assert heat.shape == (16, len(x))
+        # row i is the density of y_i = linspace(hi, lo)[i] at every x: cross-check one line against pdf()
+        y_line = np.full_like(y, np.linspace(6.0, -6.0, 16)[5])
+        with torch.no_grad():
+            assert np.allclose(heat[5], model.pdf(x, y_line).numpy(), rtol=1e-12, atol=1e-300)
+        rec["plot_heatmap"] = heat.tolist()
     rec.update(log_pdf=lst(log_pdf), pdf=lst(pdf), score=float(score), loss=float(loss.detach()),
                grads=[lst(g) for g in grads], t=lst(h), scorer_mle=scorer)
     return rec

@@ -271,6 +271,14 @@ def test_estimators_match_reference_code_run(cuda_device, idx):
         assert scorers.mle_log_likelihood_score(scorers.DummySklearWrapper(model), x, y) == \
             pytest.approx(c["scorer_mle"], rel=2e-5)
 
+        if "plot_heatmap" in c:
+            # the density grid the reference's plot_model loop hands to imshow (flow_plotting.py:33-53), one launch here
+            lo, hi = c["plot_y_range"]
+            grid = model.pdf_grid(x, np.linspace(hi, lo, num=c["plot_y_num"]))
+            heat = np.asarray(c["plot_heatmap"])
+            assert tuple(grid.shape) == heat.shape
+            np.testing.assert_allclose(grid.cpu().numpy(), heat, rtol=1e-4, atol=1e-7)
+
         model._set_noise(0.0)  # training-time noise draws are RNG specific; the reference run had none either
         loss = model.train_step(model._to_dev(x), model._to_dev(y))
         assert float(loss) == pytest.approx(c["loss"], rel=2e-5)
