@@ -165,6 +165,11 @@ class BaseEstimator(torch.nn.Module):
             y = y + self.y_noise_std * torch.randn_like(y)
         return y
 
+    def _get_input_model(self):
+        """The reference's y input model as a callable ``(y, training=False)``: normalisation followed by
+        noise that is active in training only (BaseEstimator.py:61-69, tests/test_noise_reg.py:55-75)."""
+        return lambda y, training=False: self._y_input(y, training)
+
     def _log_ystd_sum(self):
         return torch.sum(torch.log(self.y_std))
 

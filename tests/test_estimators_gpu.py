@@ -362,3 +362,30 @@ def test_bayesian_estimator_matches_reference_code_run(cuda_device, idx, monkeyp
         assert score == pytest.approx(c["score"], rel=2e-5)
         for l, kl in zip(layers, c["kl"]):
             assert float(l.last_kl) == pytest.approx(kl, rel=1e-5)
+
+
+def test_y_noise_reg_like_the_reference(cuda_device):
+    """reference tests/test_noise_reg.py:55-75: the y input model is deterministic in evaluation and noisy in
+    training; pdf is deterministic after a fit with noise (tests/test_noise_reg.py:31-34)."""
+    from normalizingflownetwork_b200.estimators import NormalizingFlowNetwork
+
+    x_train = np.linspace([[-1]] * 3, [[1]] * 3, 10, dtype=np.float32).reshape((10, 3))
+    y_train = np.linspace([[-1]] * 3, [[1]] * 3, 10, dtype=np.float32).reshape((10, 3))
+    noise = NormalizingFlowNetwork(3, n_flows=3, hidden_sizes=(16, 16), trainable_base_dist=True,
+                                   noise_reg=("fixed_rate", 1.0))
+    try:
+        noise.fit(x_train, y_train, epochs=10, verbose=0)
+        assert float(noise.y_noise_std) == 1.0 and float(noise.x_noise_std) == 1.0
+        input_model = noise._get_input_model()
+        y1 = input_model(y_train, training=False).cpu().numpy()
+        y2 = input_model(y_train, training=False).cpu().numpy()
+        assert np.all(y1 == y2)
+        np.testing.assert_allclose(y1, (y_train - noise.y_mean.cpu().numpy()) / noise.y_std.cpu().numpy(), rtol=1e-6)
+        y1 = input_model(y_train, training=True).cpu().numpy()
+        y2 = input_model(y_train, training=True).cpu().numpy()
+        assert not np.all(y1 == y2)
+        out1 = noise.pdf(x_train, y_train).cpu().numpy()
+        out2 = noise.pdf(x_train, y_train).cpu().numpy()
+        assert np.all(out1 == out2) and np.all(np.isfinite(out1))
+    finally:
+        noise._set_noise(0.0)
