@@ -214,7 +214,6 @@ def test_bayesian_fixture_matches_oracle_draw_loop():
             h = h0
             for li, v in enumerate(c["posterior_params"]):
                 v = t64(v)
-                units = b["hidden_sizes"][li] if li < len(b["hidden_sizes"]) else None
                 size = v.shape[0] if b["map_mode"] else v.shape[0] // 2
                 fan_in = h.shape[1]
                 units = size // (fan_in + 1)
