@@ -21,6 +21,7 @@ onto ``torch.autograd.grad(create_graph=True)``).
 only run where ``/root/reference`` exists (this container), the fixture travels.
 """
 import importlib
+import importlib.machinery
 import math
 import sys
 import types
@@ -580,6 +581,8 @@ def _module(name, **attrs):
     m = types.ModuleType(name)
     m.__dict__.update(attrs)
     m.__shim__ = True
+    # a spec, so that ``importlib.util.find_spec("tensorflow")`` probes (torch._dynamo does one) do not trip
+    m.__spec__ = importlib.machinery.ModuleSpec(name, None)
     return m
 
 
@@ -695,6 +698,8 @@ def load_reference(root=REFERENCE_ROOT, dtype=torch.float64):
     pkg = types.ModuleType("estimators")
     pkg.__path__ = [os.path.join(root, "estimators")]
     pkg.__shim__ = True
+    pkg.__spec__ = importlib.machinery.ModuleSpec("estimators", None, is_package=True)
+    pkg.__spec__.submodule_search_locations = pkg.__path__
     for name in [n for n in sys.modules if n == "estimators" or n.startswith("estimators.")]:
         del sys.modules[name]
     sys.modules["estimators"] = pkg
