@@ -17,6 +17,12 @@ Because the tensors are torch tensors, gradients of the reference's log_prob wit
 its inputs come from torch autograd THROUGH the reference's code (``tf.GradientTape`` is mapped
 onto ``torch.autograd.grad(create_graph=True)``).
 
+Beyond the flow / layer surface the module also stands in for the Keras pieces the estimator classes use
+(``Sequential``, ``Dense``, ``Lambda``, ``GaussianNoise``, ``DenseVariational``, a minimal mini-batch Adam
+``fit`` / ``evaluate``), which is enough for all 23 tests of the reference's own suite that it does not mark
+slow to pass unmodified (``oracle/ref_pytest_plugin.py``).  The golden fixtures never use the training loop
+or the stand-in RNG: they set weights and draws explicitly.
+
 ``oracle/make_reference_run.py`` uses this to freeze ``tests/golden/reference_run.json``; it can
 only run where ``/root/reference`` exists (this container), the fixture travels.
 """
@@ -31,6 +37,11 @@ import torch
 
 REFERENCE_ROOT = "/root/reference"
 _DTYPE = torch.float64
+_GEN = torch.Generator().manual_seed(22)  # stands in for TF's global RNG (tf.random.set_seed reseeds it)
+
+
+def _randn(shape):
+    return torch.randn(tuple(shape), generator=_GEN, dtype=torch.float64).to(_DTYPE)
 
 
 class _EagerTensor(torch.Tensor):
@@ -40,6 +51,11 @@ class _EagerTensor(torch.Tensor):
     def numpy(self):
         # an EagerTensor's .numpy() never fails because some earlier tape watched an ancestor
         return torch.Tensor.numpy(self.detach().as_subclass(torch.Tensor))
+
+    @property
+    def shape(self):
+        # tf.TensorShape compares equal to a list (tests/test_ml_estimator.py:28: ``.shape == [10]``)
+        return _Shape(self.size())
 
 
 def _binary(name):
@@ -249,8 +265,11 @@ class _Distribution:
     def mean(self):
         return self._mean()
 
-    def sample(self):
-        return self._sample()
+    def sample(self, sample_shape=None):
+        if sample_shape is None:
+            return self._sample()
+        n = int(sample_shape)
+        return torch.stack([self._sample() for _ in range(n)], 0)
 
     def prob(self, x):
         return torch.exp(self.log_prob(x))
@@ -278,6 +297,10 @@ class _MultivariateNormalDiag(_Distribution):
     @property
     def batch_shape(self):
         return _Shape(torch.broadcast_shapes(self.loc.shape, self.scale.shape)[:-1])
+
+    def _sample(self):
+        shape = tuple(torch.broadcast_shapes(self.loc.shape, self.scale.shape))
+        return _t(self.loc + self.scale * _randn(shape))
 
     def log_prob(self, x):
         e = (_t(x) - self.loc) / self.scale
@@ -382,9 +405,12 @@ class _Normal(_Distribution):
         return self.loc + torch.zeros_like(self.scale)
 
     def _sample(self):
-        assert _EPS_QUEUE, "sample() without queued draws (oracle.tf_shim.push_draws)"
-        eps = _EPS_QUEUE.pop(0)
-        assert tuple(eps.shape) == tuple(torch.broadcast_shapes(self.loc.shape, self.scale.shape))
+        shape = tuple(torch.broadcast_shapes(self.loc.shape, self.scale.shape))
+        if _EPS_QUEUE:  # draws owned (and recorded) by a harness
+            eps = _EPS_QUEUE.pop(0)
+            assert tuple(eps.shape) == shape
+        else:
+            eps = _randn(shape)
         return self.loc + self.scale * eps
 
     def log_prob(self, x):
@@ -482,11 +508,11 @@ class _VariableLayer:
     """tfp.layers.VariableLayer (DistributionLayers.py:80-85): ignores its input."""
 
     def __init__(self, shape=None, dtype=None, initializer="zeros", trainable=True, **kw):
-        # "normal" (BayesianNNEstimator.py:102) is Keras RandomNormal(stddev=0.05); the harness overwrites
-        # ``variable`` with seeded values, so both initialisers start from zeros here
+        # "normal" (BayesianNNEstimator.py:102) is Keras RandomNormal(stddev=0.05); the fixture harness
+        # overwrites ``variable`` with its own seeded values
         assert initializer in ("zeros", "normal")
         n = shape if isinstance(shape, int) else int(np.prod(shape))
-        self.variable = torch.zeros(n, dtype=_DTYPE)
+        self.variable = torch.zeros(n, dtype=_DTYPE) if initializer == "zeros" else 0.05 * _randn((n,))
         self.trainable = trainable
 
     def __call__(self, _x):
@@ -503,21 +529,23 @@ class _Lambda:
 
 class _GaussianNoise:
     """tf.keras.layers.GaussianNoise (BaseEstimator.py:68, MaximumLikelihoodNNEstimator.py:41):
-    identity unless training.  Training-time noise would need TF's RNG stream: not emulated."""
+    identity unless training."""
 
     def __init__(self, stddev, **kw):
         self.stddev = stddev
 
     def __call__(self, x, training=False):
-        if training and float(_t(self.stddev)) != 0.0:
-            raise NotImplementedError("training-time GaussianNoise draws are TF-RNG specific")
+        std = float(_t(self.stddev))
+        if training and std != 0.0:  # from the stand-in RNG: only "is there noise" is ever asserted
+            x = _t(x)
+            return x + std * _randn(x.shape)
         return x
 
 
 class _Dense:
     """tf.keras.layers.Dense(units, activation) (MaximumLikelihoodNNEstimator.py:42-43):
-    ``activation(x @ kernel + bias)``, kernel [in, units].  Weights are set by the harness
-    (``set_weights``), never initialised here."""
+    ``activation(x @ kernel + bias)``, kernel [in, units].  The fixture harness sets the weights
+    (``set_weights``); otherwise they are built on first call like Keras does."""
 
     _ACT = {"linear": lambda v: v, None: lambda v: v, "tanh": torch.tanh, "relu": torch.relu,
             "sigmoid": torch.sigmoid}
@@ -535,8 +563,13 @@ class _Dense:
         return [self.kernel, self.bias]
 
     def __call__(self, x):
-        assert self.kernel is not None, "Dense weights not set"
-        return self._ACT[self.activation](_t(x) @ self.kernel + self.bias)
+        x = _t(x)
+        if self.kernel is None:  # Keras defaults: glorot-uniform kernel, zero bias
+            fan_in = x.shape[-1]
+            limit = math.sqrt(6.0 / (fan_in + self.units))
+            self.kernel = ((torch.rand(fan_in, self.units, generator=_GEN, dtype=torch.float64) * 2 - 1) * limit).to(_DTYPE)
+            self.bias = torch.zeros(self.units, dtype=_DTYPE)
+        return self._ACT[self.activation](x @ self.kernel + self.bias)
 
 
 class _Sequential:
@@ -551,8 +584,7 @@ class _Sequential:
         self.layers.append(layer)
 
     def call(self, x, training=False):
-        if isinstance(x, np.ndarray) or not isinstance(x, torch.Tensor):
-            x = _t(x)
+        x = _t(x)
         for layer in self.layers:
             x = layer(x, training=training) if isinstance(layer, _GaussianNoise) else layer(x)
         return x
@@ -568,13 +600,71 @@ class _Sequential:
     def compile(self, optimizer=None, loss=None, **kw):
         self.optimizer, self.loss = optimizer, loss
 
-    def fit(self, *a, **kw):
-        raise NotImplementedError("the Keras training loop is not emulated")
+    # -- a minimal Keras training loop, enough for the reference's own (non-slow) estimator tests:
+    #    mini-batches of 32, shuffled; loss = mean(loss_fn(y, model(x, training=True))) + sum(model.losses);
+    #    Adam with Keras' epsilon.  Not used for any fixture (those set weights explicitly).
+    def _total_loss(self, x, y, training):
+        per_sample = self.loss(_t(y), self.call(x, training=training))
+        return per_sample.mean() + sum(self.losses, torch.zeros((), dtype=_DTYPE))
+
+    def fit(self, x=None, y=None, batch_size=None, epochs=None, verbose=0, callbacks=None, shuffle=True, **kw):
+        x, y = _t(x).as_subclass(torch.Tensor), _t(y).as_subclass(torch.Tensor)
+        n, bs = x.shape[0], int(batch_size or 32)
+        with torch.no_grad():
+            self.call(x[:2], training=False)  # builds the lazily created weights
+        slots = _trainable_slots(self, set())
+        params = []
+        for holder, attr in slots:
+            v = getattr(holder, attr).detach().as_subclass(torch.Tensor).clone().requires_grad_(True)
+            setattr(holder, attr, v)
+            params.append(v)
+        opt = torch.optim.Adam(params, lr=float(getattr(self.optimizer, "learning_rate", 1e-3)), eps=1e-7)
+        self.history = []
+        for _ in range(int(epochs or 1)):
+            order = torch.randperm(n, generator=_GEN) if shuffle else torch.arange(n)
+            total = 0.0
+            for lo in range(0, n, bs):
+                idx = order[lo:lo + bs]
+                opt.zero_grad(set_to_none=True)
+                loss = self._total_loss(x[idx], y[idx], training=True)
+                loss.backward()
+                opt.step()
+                total += float(loss.detach()) * len(idx)
+            self.history.append(total / n)
+        for (holder, attr), v in zip(slots, params):
+            setattr(holder, attr, v.detach())
+        return self
+
+    def evaluate(self, x=None, y=None, **kw):
+        with torch.no_grad():
+            return float(self._total_loss(x, y, training=False))
 
 
 class _Adam:
     def __init__(self, learning_rate=0.001, **kw):
         self.learning_rate = learning_rate
+
+
+def _trainable_slots(obj, seen):
+    """(holder, attribute) pairs of the trainable tensors reachable from a layer / model: Dense kernels and
+    biases, trainable VariableLayers (DenseVariational posteriors / priors, the KMN scale model)."""
+    if id(obj) in seen:
+        return []
+    seen.add(id(obj))
+    out = []
+    if isinstance(obj, _Dense):
+        out += [(obj, "kernel"), (obj, "bias")]
+    elif isinstance(obj, _VariableLayer):
+        if obj.trainable:
+            out.append((obj, "variable"))
+    if isinstance(obj, (list, tuple)):
+        for o in obj:
+            out += _trainable_slots(o, seen)
+    elif isinstance(obj, (_Sequential, _DenseVariational, _DistributionLambda, _Dense, _Lambda)):
+        for v in vars(obj).values():
+            if isinstance(v, (list, tuple, _Sequential, _DenseVariational, _DistributionLambda, _Dense, _VariableLayer)):
+                out += _trainable_slots(v, seen)
+    return out
 
 
 def _module(name, **attrs):
@@ -600,6 +690,7 @@ def install(dtype=torch.float64):
         reduce_sum=_reduce_sum,
         softplus=_softplus,
         tanh=lambda x: torch.tanh(_t(x)),
+        sin=lambda x: torch.sin(_t(x)),
         log=lambda x: torch.log(_t(x)),
         abs=lambda x: torch.abs(_t(x)),
         expm1=lambda x: torch.expm1(_t(x)),
@@ -628,7 +719,7 @@ def install(dtype=torch.float64):
         abs=tf_math.abs,
         reduce_sum=_reduce_sum,
         reduce_prod=lambda x, axis=None: torch.prod(_t(x)) if axis is None else torch.prod(_t(x), dim=axis),
-        random=_module("tensorflow.random", set_seed=lambda seed: None),
+        random=_module("tensorflow.random", set_seed=lambda seed: _GEN.manual_seed(int(seed))),
         squeeze=lambda x, axis=None: torch.squeeze(_t(x)) if axis is None else torch.squeeze(_t(x), dim=axis),
         expand_dims=lambda x, axis: torch.unsqueeze(_t(x), axis),
         zeros_like=lambda x: torch.zeros_like(_t(x)),
@@ -673,11 +764,11 @@ def uninstall():
     """Drop the stand-in modules and the reference modules loaded through them."""
     for name in list(sys.modules):
         top = name.split(".")[0]
-        if top in ("tensorflow", "tensorflow_probability", "estimators") and \
+        if top in ("tensorflow", "tensorflow_probability", "estimators", "evaluation") and \
                 getattr(sys.modules.get(top), "__shim__", False):
             if name != top:
                 del sys.modules[name]
-    for top in ("tensorflow", "tensorflow_probability", "estimators"):
+    for top in ("tensorflow", "tensorflow_probability", "estimators", "evaluation"):
         if getattr(sys.modules.get(top), "__shim__", False):
             del sys.modules[top]
 
@@ -725,3 +816,28 @@ def load_reference_module(name, root=REFERENCE_ROOT):
         sys.dont_write_bytecode = keep
     assert mod.__file__.startswith(root), mod.__file__
     return mod
+
+
+def load_reference_package(root=REFERENCE_ROOT, dtype=torch.float64):
+    """``load_reference()`` plus the body of the reference's ``estimators/__init__.py`` executed in the package
+    object (so ``from estimators import NormalizingFlowNetwork, ...`` works as in the reference's tests) and an
+    ``evaluation`` package object for ``evaluation.scorers``."""
+    import os
+
+    flows, layers = load_reference(root, dtype)
+    pkg = sys.modules["estimators"]
+    init = os.path.join(root, "estimators", "__init__.py")
+    keep, sys.dont_write_bytecode = sys.dont_write_bytecode, True
+    try:
+        with open(init) as f:
+            exec(compile(f.read(), init, "exec"), pkg.__dict__)
+        ev = types.ModuleType("evaluation")
+        ev.__path__ = [os.path.join(root, "evaluation")]
+        ev.__shim__ = True
+        ev.__spec__ = importlib.machinery.ModuleSpec("evaluation", None, is_package=True)
+        ev.__spec__.submodule_search_locations = ev.__path__
+        sys.modules["evaluation"] = ev
+        importlib.import_module("evaluation.scorers")
+    finally:
+        sys.dont_write_bytecode = keep
+    return pkg
