@@ -407,6 +407,82 @@ def test_full_size_properties_cfg2(cuda_device, nfn_lib):
     assert_grad((dt[idx] * B).cpu().numpy(), ref_dt)
 
 
+def test_full_size_properties_cfg3_forward(cuda_device, nfn_lib):
+    """BASELINE config 3 at its per-GPU size (2^23 events x 128 parameters, 4.3 GB, forward only):
+    finite, a row shard scored alone equals its slice of the whole bit for bit (what lets ranks shard rows with
+    no exchange), one event broadcast against a shard, and a random sample of rows against the float64 oracle."""
+    from normalizingflownetwork_b200 import functional as F
+
+    ft, d, tb = CONFIG_CHAINS["cfg3"]
+    B, P = 1 << 23, 128
+    g = torch.Generator(device=cuda_device).manual_seed(22)
+    t = torch.randn((B, P), generator=g, device=cuda_device)
+    t.mul_(0.5)
+    y = torch.randn((B, d), generator=g, device=cuda_device)
+    lp = F.chain_forward(t, y, ft, d, tb)
+    assert lp.shape == (B,) and torch.isfinite(lp).all()
+    lo, hi = (1 << 22) + 4096, (1 << 22) + 4096 + 100_003  # ragged shard length
+    assert torch.equal(F.chain_forward(t[lo:hi], y[lo:hi], ft, d, tb), lp[lo:hi])
+    lb = F.chain_forward(t[lo:lo + 4096], y[lo + 7:lo + 8], ft, d, tb)
+    idx = torch.randint(0, B, (4096,), generator=g, device=cuda_device)
+    ref = an.chain_forward_backward(t[idx].cpu().numpy(), y[idx].cpu().numpy(), ft, d, tb, need_grad=False)
+    assert_logp(lp[idx].cpu().numpy(), ref)
+    ref_b = an.chain_forward_backward(t[lo:lo + 4096].cpu().numpy(), y[lo + 7:lo + 8].cpu().numpy(), ft, d, tb,
+                                      need_grad=False)
+    assert_logp(lb.cpu().numpy(), ref_b)
+
+
+def test_full_size_properties_cfg4(cuda_device, nfn_lib):
+    """BASELINE config 4 at its per-GPU size (2^20 rows = S * B folded draws, 5 radial flows, d = 1, fwd+bwd)."""
+    from normalizingflownetwork_b200 import functional as F
+
+    ft, d, tb = CONFIG_CHAINS["cfg4"]
+    B, P = 1 << 20, 17
+    g = torch.Generator(device=cuda_device).manual_seed(22)
+    t = torch.randn((B, P), generator=g, device=cuda_device) * 0.5
+    y = torch.randn((B, d), generator=g, device=cuda_device)
+    lsum = torch.zeros(1, dtype=torch.float64, device=cuda_device)
+    col = torch.zeros(P, dtype=torch.float64, device=cuda_device)
+    lp, dt, _ = F.chain_forward_backward(t, y, ft, d, tb, g_scale=-1.0 / B, logp_sum=lsum, dt_colsum=col)
+    assert torch.isfinite(lp).all() and torch.isfinite(dt).all()
+    assert abs(lsum.item() - lp.double().sum().item()) < 1e-7 * B
+    np.testing.assert_allclose(col.cpu().numpy(), dt.double().sum(0).cpu().numpy(), rtol=2e-3, atol=1e-6)
+    assert torch.allclose(F.chain_forward(t, y, ft, d, tb), lp, rtol=1e-6, atol=1e-6)
+    # the [S, B] -> [B] posterior-predictive epilogue over the folded draws (S = 32 draws of 2^15 rows)
+    S = 32
+    lme = F.logmeanexp_draws(lp.view(S, B // S))
+    want = torch.logsumexp(lp.view(S, B // S).double(), 0) - np.log(S)
+    assert torch.allclose(lme.double(), want, rtol=1e-5, atol=1e-5)
+    idx = torch.randint(0, B, (4096,), generator=g, device=cuda_device)
+    ref_lp, ref_dt, _ = an.chain_forward_backward(t[idx].cpu().numpy(), y[idx].cpu().numpy(), ft, d, tb,
+                                                  upstream=-1.0)
+    assert_logp(lp[idx].cpu().numpy(), ref_lp)
+    assert_grad((dt[idx] * B).cpu().numpy(), ref_dt)
+
+
+def test_full_size_properties_cfg5_mdn(cuda_device, nfn_lib):
+    """BASELINE config 5 at full size (MDN, 20 components, d = 2, P = 100, 2^22 rows, fwd+bwd)."""
+    from normalizingflownetwork_b200 import functional as F
+
+    K, d = 20, 2
+    B, P = 1 << 22, 100
+    g = torch.Generator(device=cuda_device).manual_seed(22)
+    t = torch.randn((B, P), generator=g, device=cuda_device) * 0.5
+    y = torch.randn((B, d), generator=g, device=cuda_device)
+    lsum = torch.zeros(1, dtype=torch.float64, device=cuda_device)
+    lp, dt, _ = F.mdn_forward_backward(t, y, K, d, g_scale=-1.0 / B, logp_sum=lsum)
+    assert torch.isfinite(lp).all() and torch.isfinite(dt).all()
+    assert abs(lsum.item() - lp.double().sum().item()) < 1e-7 * B
+    # the mixture-weight gradients of a row sum to zero (softmax): a checksum over the whole batch
+    assert float(dt[:, 2 * K * d:].double().sum(1).abs().max()) * B < 1e-4
+    lo, hi = (1 << 21) + 1024, (1 << 21) + 1024 + 50_001
+    assert torch.allclose(F.mdn_forward(t[lo:hi], y[lo:hi], K, d), lp[lo:hi], rtol=1e-6, atol=1e-6)
+    idx = torch.randint(0, B, (4096,), generator=g, device=cuda_device)
+    ref_lp, ref_dt, _ = an.mdn_forward_backward(t[idx].cpu().numpy(), y[idx].cpu().numpy(), K, d, upstream=-1.0)
+    assert_logp(lp[idx].cpu().numpy(), ref_lp)
+    assert_grad((dt[idx] * B).cpu().numpy(), ref_dt)
+
+
 # ----------------------------------------------------------------------------- mixture heads
 def test_golden_mixture_vectors(cuda_device, nfn_lib, math_mode):
     from normalizingflownetwork_b200 import functional as F
