@@ -278,3 +278,68 @@ def test_reference_own_unit_tests_pass_on_the_stand_ins():
         cwd="/tmp", env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "23 passed, 6 deselected" in r.stdout, r.stdout[-500:]
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="/root/reference does not travel to the GPU box")
+def test_oracles_equal_reference_code_on_random_chains_and_mixtures():
+    """Beyond the frozen cases: 60 seeded random chain configurations (0-12 flows of random type, d = 1..6, both
+    base-distribution modes, sigma 0.5 / 1 / 2, per-row and broadcast events) and 20 random MDN / KMN heads, the
+    reference's own layer code (stand-ins, float64) against both oracles, values and gradients."""
+    from oracle import tf_shim
+
+    rng = np.random.default_rng(2222)
+    FLOWS, DL = tf_shim.load_reference()
+    try:
+        names = sorted(FLOWS)
+        for case in range(60):
+            K, d, tb = int(rng.integers(0, 13)), int(rng.integers(1, 7)), bool(rng.integers(0, 2))
+            ft = [names[i] for i in rng.integers(0, 3, size=K)]
+            layer = DL.InverseNormalizingFlowLayer(ft, d, trainable_base_dist=tb)
+            P = layer.get_total_param_size()
+            assert P == fo.chain_param_size(ft, d, tb)
+            if P == 0:
+                continue
+            B, sigma = int(rng.integers(1, 9)), float(rng.choice([0.5, 1.0, 2.0]))
+            t = t64(rng.normal(0.0, sigma, size=(B, P))).requires_grad_(True)
+            y = t64(rng.normal(0.0, 1.0, size=(B if case % 3 else 1, d))).requires_grad_(True)
+            up = t64(rng.normal(size=(B,)))
+            lp = layer(t).log_prob(y)
+            dt, dy = torch.autograd.grad(lp, [t, y], grad_outputs=up)
+            olp, odt, ody = fo.with_grad(fo.chain_log_prob, t.detach(), y.detach(), ft, d, tb, upstream=up, want_dy=True)
+            tag = "case %d %s d=%d tb=%s" % (case, ft, d, tb)
+            np.testing.assert_allclose(olp.numpy(), lp.detach().numpy(), rtol=1e-11, atol=1e-11, err_msg=tag)
+            np.testing.assert_allclose(odt.numpy(), dt.numpy(), rtol=1e-8, atol=1e-10, err_msg=tag)
+            np.testing.assert_allclose(ody.numpy(), dy.numpy(), rtol=1e-8, atol=1e-10, err_msg=tag)
+            if y.shape[0] == B:
+                alp, adt, ady = an.chain_forward_backward(t.detach().numpy(), y.detach().numpy(), ft, d, tb,
+                                                          upstream=up.numpy())
+                np.testing.assert_allclose(alp, lp.detach().numpy(), rtol=1e-11, atol=1e-11, err_msg=tag)
+                np.testing.assert_allclose(adt, dt.numpy(), rtol=1e-8, atol=1e-10, err_msg=tag)
+                np.testing.assert_allclose(ady, dy.numpy(), rtol=1e-8, atol=1e-10, err_msg=tag)
+        for case in range(20):
+            K, d, B = int(rng.integers(1, 9)), int(rng.integers(1, 5)), int(rng.integers(1, 7))
+            y = t64(rng.normal(size=(B, d)))
+            up = t64(rng.normal(size=(B,)))
+            if case % 2:
+                layer = DL.GaussianMixtureLayer(K, d)
+                t = t64(rng.normal(0.0, 2.0, size=(B, layer.get_total_param_size()))).requires_grad_(True)
+                lp = layer(t).log_prob(y)
+                olp, odt = fo.with_grad(fo.mdn_log_prob, t.detach(), y, K, d, upstream=up)
+            else:
+                init = (0.3, 0.7, 1.5)[: int(rng.integers(1, 4))]
+                layer = DL.GaussianKernelsLayer(K, d, trainable_scale=True, init_scales=init)
+                sv = t64(rng.normal(0.0, 0.5, size=(len(init),)))
+                layer.scale_model.layers[0].variable = sv
+                locs = np.tile(rng.normal(size=(K, d)), (len(init), 1))
+                layer.locs.assign(locs)
+                layer.locs = layer.locs.value()[None]
+                t = t64(rng.normal(0.0, 2.0, size=(B, K * len(init)))).requires_grad_(True)
+                lp = layer(t).log_prob(y)
+                scales = fo.kmn_scales(sv, K, init)
+                olp, odt = fo.with_grad(lambda tt, yy: fo.kmn_log_prob(tt, yy, t64(locs), scales), t.detach(), y,
+                                        upstream=up)
+            (dt,) = torch.autograd.grad(lp, [t], grad_outputs=up)
+            np.testing.assert_allclose(olp.numpy(), lp.detach().numpy(), rtol=1e-11, atol=1e-11)
+            np.testing.assert_allclose(odt.numpy(), dt.numpy(), rtol=1e-8, atol=1e-11)
+    finally:
+        tf_shim.uninstall()
