@@ -8,7 +8,7 @@ TEST INFRASTRUCTURE ONLY.  Runs only where ``/root/reference`` exists (this cont
 
 ``estimators/{BaseEstimator,MaximumLikelihoodNNEstimator,NormalizingFlowNetwork,MixtureDensityNetwork,
 KernelMixtureNetwork}.py`` are imported unmodified through ``oracle/tf_shim.py`` (torch-CPU float64
-stand-ins for TF / Keras / TFP; the Keras training loop is not emulated).  Per case the script builds the
+stand-ins for TF / Keras / TFP; nothing is trained here: weights and draws are set explicitly).  Per case the script builds the
 reference estimator via its ``build_function``, calls the reference's ``_assign_data_normalization`` /
 ``_assign_noise_regularisation``, sets seeded Dense weights, and records
   log_pdf(x, y), pdf(x, y), score(x, y)                       (BaseEstimator.py:43-47, :71-86)
