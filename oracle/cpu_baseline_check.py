@@ -1,9 +1,9 @@
 """Is the timed CPU port (`oracle/flow_oracle.py`, bench.py's cpu_baseline / --impl reference) a fair stand-in
 for the reference's Python?  Where /root/reference exists, run the reference's OWN layer code on the float32
 torch-CPU stand-ins (oracle/tf_shim.py) and the port on the same config-2 inputs, forward + autograd backward,
-and print both timings and the number of aten ops each dispatches.  CPU only; not part of the product.
+and print both timings and the number of aten ops each dispatches.  TEST INFRASTRUCTURE ONLY (CPU).
 
-    python tools/cpu_baseline_check.py [rows]
+    python -m oracle.cpu_baseline_check [rows]
 """
 import os
 import sys
