@@ -761,7 +761,8 @@ def install(dtype=torch.float64):
 
 
 def uninstall():
-    """Drop the stand-in modules and the reference modules loaded through them."""
+    """Drop the stand-in modules, the reference modules loaded through them and any queued draws."""
+    del _EPS_QUEUE[:]
     for name in list(sys.modules):
         top = name.split(".")[0]
         if top in ("tensorflow", "tensorflow_probability", "estimators", "evaluation") and \
