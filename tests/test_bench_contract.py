@@ -62,3 +62,20 @@ def test_gpu_arm_fails_loudly_without_a_gpu():
                        capture_output=True, text=True, timeout=300)
     assert r.returncode != 0  # no CPU fallback behind the GPU arm
     assert not [l for l in r.stdout.splitlines() if l.startswith("{") and '"value"' in l]
+
+
+def test_near_gpu_cpus_is_best_effort_and_restores_affinity():
+    sys.path.insert(0, ROOT)
+    try:
+        import bench
+    finally:
+        sys.path.remove(ROOT)
+    before = os.sched_getaffinity(0)
+    with bench._NearGpuCpus(0) as near:
+        inside = os.sched_getaffinity(0)
+        assert inside <= before and near.note
+    assert os.sched_getaffinity(0) == before
+    import torch
+
+    if not torch.cuda.is_available():
+        assert near.note.startswith("unchanged")  # no NVML device here: nothing is touched
