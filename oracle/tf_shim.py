@@ -310,8 +310,8 @@ class _MultivariateNormalDiag(_Distribution):
 
 
 class _Categorical(_Distribution):
-    def __init__(self, logits=None, **kw):
-        self.logits = _t(logits)
+    def __init__(self, logits=None, probs=None, **kw):
+        self.logits = _t(logits) if logits is not None else torch.log(_t(probs))
 
 
 class _Mixture(_Distribution):
@@ -330,6 +330,15 @@ class _Mixture(_Distribution):
     @property
     def batch_shape(self):
         return _Shape(self.cat.logits.shape[:-1])
+
+    def _sample(self):
+        """One draw per batch member from the stand-in RNG (the reference's tests use it to make data)."""
+        logits = self.cat.logits.detach().as_subclass(torch.Tensor)
+        u = torch.rand(tuple(logits.shape[:-1]) + (1,), generator=_GEN, dtype=torch.float64).to(logits.dtype)
+        idx = (torch.cumsum(torch.softmax(logits, -1), -1) < u).sum(-1).clamp(max=logits.shape[-1] - 1)
+        draws = torch.stack([c._sample().detach().as_subclass(torch.Tensor) for c in self.components], -2)
+        idx = idx.reshape(idx.shape + (1, 1)).expand(idx.shape + (1, draws.shape[-1]))
+        return _t(torch.gather(draws, -2, idx).squeeze(-2))
 
     @property
     def event_shape(self):
