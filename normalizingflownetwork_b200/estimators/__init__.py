@@ -1,18 +1,17 @@
-from .models import (  # noqa: F401
-    BayesKernelMixtureNetwork,
-    BayesMixtureDensityNetwork,
-    BayesNormalizingFlowNetwork,
-    KernelMixtureNetwork,
-    MixtureDensityNetwork,
-    NormalizingFlowNetwork,
-)
+"""The estimator facade (reference API: ``fit / log_pdf / pdf / score``) on top of the fused CUDA heads.
 
-# same keys as the reference's estimators/__init__.py:8-15
-ESTIMATORS = {
-    "bayesian_NFN": BayesNormalizingFlowNetwork,
-    "bayesian_KMN": BayesKernelMixtureNetwork,
-    "bayesian_MDN": BayesMixtureDensityNetwork,
-    "NFN": NormalizingFlowNetwork,
-    "KMN": KernelMixtureNetwork,
-    "MDN": MixtureDensityNetwork,
-}
+The ``MaximumLikelihoodNNEstimator`` and ``BayesianNNEstimator`` submodules are the two training regimes (point weights with
+Adam on the mean NLL; mean-field weight posteriors with the KL term, S weight draws folded into the batch);
+``models`` holds the six concrete estimators, one per (regime, head) pair: flow chain, Gaussian mixture,
+kernel mixture.  ``ESTIMATORS`` uses the registry names of the reference's ``estimators/__init__.py:8-15``.
+"""
+from . import models as _models
+
+_HEADS = {"NFN": "NormalizingFlowNetwork", "MDN": "MixtureDensityNetwork", "KMN": "KernelMixtureNetwork"}
+ESTIMATORS = {}
+for _key, _cls in _HEADS.items():
+    ESTIMATORS[_key] = getattr(_models, _cls)
+    ESTIMATORS["bayesian_" + _key] = getattr(_models, "Bayes" + _cls)
+    globals()[_cls] = ESTIMATORS[_key]
+    globals()["Bayes" + _cls] = ESTIMATORS["bayesian_" + _key]
+del _key, _cls
