@@ -290,11 +290,205 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- our arm
+class HeadWorkload:
+    """One BASELINE config as device-resident synthetic tensors + the C-ABI launch of its head.
+
+    step() = one launch of the head kernel over this rank's rows (+ the one exchange a
+    data-parallel training step needs from the path when world > 1: the sum over ranks of
+    [dt column sums (P) | sum logp], fused into the kernel's last CTA over NVLink peer memory,
+    or one NCCL all-reduce with --exchange nccl).  `sets` > 1 rotates that many independent
+    tensor sets so that a per-step footprint near the 126 MB L2 cannot be served from it."""
+
+    def __init__(self, cfg, args, device, rank, world, lib, n_steps, rows=None, fwd_only=False, colsum=True,
+                 sets=1):
+        import torch
+
+        from normalizingflownetwork_b200 import _lib, parallel
+
+        self.torch, self._lib, self.lib, self.parallel = torch, _lib, lib, parallel
+        self.cfg, self.device, self.rank, self.world = cfg, device, rank, world
+        ft, d, tb, B, bwd = CONFIGS[cfg]
+        self.ft, self.d, self.tb = ft, d, tb
+        self.bwd = bool(bwd and not fwd_only)
+        self.B = int(rows or B)
+        self.P = param_size(ft, d, tb)
+        self.mdn = is_mdn(ft)
+        self.desc = None if self.mdn else _lib.make_desc(ft, d, tb)
+        self.specialized = True if self.mdn else bool(lib.nfn_chain_is_specialized(ctypes.byref(self.desc)))
+        B, P = self.B, self.P
+        gen = torch.Generator(device=device).manual_seed(22 + rank)
+        self.sets = []
+        for _ in range(max(1, sets)):
+            t = torch.randn((B, P), generator=gen, device=device) * 0.5
+            y = torch.randn((B, d), generator=gen, device=device)
+            logp = torch.empty(B, device=device)
+            dt = torch.empty((B, P), device=device) if self.bwd else None
+            self.sets.append((t, y, logp, dt))
+        # fp64 accumulators [dt column sums (P) | sum logp], one pre-zeroed row per step (keeps memsets off
+        # the critical path); a data-parallel step sums its row over ranks with ONE exchange
+        self.acc_ring = torch.zeros((n_steps + 8, P + 1), dtype=torch.float64, device=device)
+        # (the mixture kernels leave the column sums to a second pass over dt: not part of their step here)
+        self.want_col = bool(self.bwd and colsum and not self.mdn)
+        self.packed = bool(world > 1 and self.bwd)
+        self.use_peer = bool(self.packed and args.exchange == "peer" and not self.mdn)
+        self.comm = None
+        if self.use_peer:
+            # cudaIpc peer mapping can be unavailable (e.g. ranks in different containers): every rank must
+            # agree, so the outcome is all-reduced and the NCCL exchange is the fallback
+            try:
+                self.comm = parallel.PeerComm(P + 1, device)
+                ok = 1
+            except Exception as exc:  # noqa: BLE001
+                ok = 0
+                if rank == 0:
+                    print("peer exchange unavailable (%s): falling back to NCCL" % exc, file=sys.stderr)
+            flag = torch.tensor([ok], device=device)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                if self.comm is not None:
+                    self.comm.close()
+                self.comm, self.use_peer = None, False
+        self.step_no = 0
+        self.g_scale = -1.0 / (B * world)
+        self.stream = _lib.current_stream(device)
+        self.bytes_per_row = 4 * ((2 * P if self.bwd else P) + d + 1)
+
+    # ------------------------------------------------------------------ launches
+    def kernel(self):
+        _lib, lib, P, B, d = self._lib, self.lib, self.P, self.B, self.d
+        t, y, logp, dt = self.sets[self.step_no % len(self.sets)]
+        row = self.acc_ring.data_ptr() + self.step_no * (P + 1) * 8
+        lsum = ctypes.c_void_p(row + 8 * P)
+        col = ctypes.c_void_p(row) if self.want_col else None
+        if self.mdn and not self.bwd:
+            _lib.check(lib.nfn_mdn_forward(self.ft[1], d, _lib.ptr(t), _lib.ptr(y), B, _lib.ptr(logp), B, self.stream))
+        elif self.use_peer:  # ONE launch: fused fwd+bwd + all-reduce of [dt column sums | sum logp] over NVLink
+            _lib.check(lib.nfn_chain_forward_backward_peer(
+                ctypes.byref(self.desc), _lib.ptr(t), _lib.ptr(y), B, None, ctypes.c_float(self.g_scale),
+                _lib.ptr(logp), _lib.ptr(dt), None, 1 if self.want_col else 0, self.comm.comm, ctypes.c_void_p(row), B,
+                self.stream))
+        elif self.mdn:
+            _lib.check(lib.nfn_mdn_forward_backward(
+                self.ft[1], d, _lib.ptr(t), _lib.ptr(y), B, None, ctypes.c_float(self.g_scale), _lib.ptr(logp),
+                _lib.ptr(dt), None, lsum, col, B, self.stream))
+        elif self.bwd:
+            _lib.check(lib.nfn_chain_forward_backward(
+                ctypes.byref(self.desc), _lib.ptr(t), _lib.ptr(y), B, None, ctypes.c_float(self.g_scale),
+                _lib.ptr(logp), _lib.ptr(dt), None, lsum, col, B, self.stream))
+        else:
+            _lib.check(lib.nfn_chain_forward(ctypes.byref(self.desc), _lib.ptr(t), _lib.ptr(y), B, _lib.ptr(logp), B,
+                                             self.stream))
+
+    def exchange(self):
+        if self.packed and not self.use_peer:
+            self.torch.distributed.all_reduce(self.acc_ring[self.step_no])
+        self.step_no += 1
+
+    def step(self):
+        self.kernel()
+        self.exchange()
+
+    @property
+    def step_is_one_kernel(self):
+        return not (self.packed and not self.use_peer)
+
+    # ------------------------------------------------------------------ timing
+    def time_steps(self, K, with_exchange=True):
+        """K back-to-back steps under ONE CUDA-event pair on the launch stream (no per-launch probes: an event
+        pair around every launch opens gaps and defeats the programmatic-dependent-launch overlap), bracketed
+        by barrier + synchronize; returns the max over ranks in ms."""
+        torch, parallel = self.torch, self.parallel
+        torch.cuda.synchronize()
+        parallel.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if with_exchange:
+            for _ in range(K):
+                self.kernel()
+                self.exchange()
+        else:
+            for _ in range(K):
+                self.kernel()
+                self.step_no += 1
+        e1.record()
+        torch.cuda.synchronize()
+        parallel.barrier()
+        torch.cuda.synchronize()
+        return parallel.max_over_ranks(e0.elapsed_time(e1), self.device)
+
+    # ------------------------------------------------------------------ the result of the last step, checked
+    def exchange_check(self):
+        """Compares the accumulator row of the LAST executed step -- after the cross-rank exchange when
+        world > 1 -- with a float64 torch reduction of the same step's outputs summed over ranks by a plain
+        NCCL all-reduce.  This is what proves that the fused peer all-reduce delivered the cross-rank sum
+        (and that the in-kernel column sums are in the timed region)."""
+        torch = self.torch
+        if not self.bwd:
+            return None
+        last = self.step_no - 1
+        t, y, logp, dt = self.sets[last % len(self.sets)]
+        got = self.acc_ring[last].clone()
+        ref = torch.zeros(self.P + 1, dtype=torch.float64, device=self.device)
+        if self.want_col:
+            ref[: self.P] = dt.double().sum(0)
+        ref[self.P] = logp.double().sum()
+        if self.world > 1:
+            torch.distributed.all_reduce(ref)
+        if not self.want_col:
+            got[: self.P] = 0.0
+        col_scale = float(ref[: self.P].abs().max()) if self.want_col else 0.0
+        err_col = float((got[: self.P] - ref[: self.P]).abs().max()) / max(col_scale, 1e-30) if self.want_col else 0.0
+        err_lp = abs(float(got[self.P] - ref[self.P])) / max(abs(float(ref[self.P])), 1e-30)
+        nan = bool(torch.isnan(got).any().item())
+        out = {"max_rel_err": max(err_col, err_lp), "colsum_rel_err": err_col, "logp_sum_rel_err": err_lp, "nan": nan,
+               "payload_values": self.P + 1, "payload_nonzero": int((got != 0).sum().item()),
+               "payload_abs_max": float(got.abs().max()), "ranks_summed": self.world,
+               "how": ("fused peer all-reduce in the kernel's last CTA" if self.use_peer else
+                       "NCCL all-reduce of the accumulator row" if self.packed else "single rank: in-kernel fp64 accumulators")
+                      + " vs float64 torch sums of dt / logp" + (" + NCCL all-reduce" if self.world > 1 else "")}
+        # column sums: fp32 partial sums per CTA, then fp64 atomics -> 1e-4 of the largest column; sum logp: fp64
+        out["ok"] = bool((not nan) and err_col < 1e-4 and err_lp < 1e-6 and
+                         (out["payload_nonzero"] > (self.P // 2 if self.want_col else 0)))
+        return out
+
+    def close(self):
+        if self.comm is not None:
+            self.comm.close()
+            self.comm = None
+        self.sets = []
+
+
+def measure_other_config(cfg, args, device, rank, world, lib, steps=10, warmup=3):
+    """A few steps of another BASELINE config, same launch path and timing rules as the headline."""
+    import torch
+
+    peak, _ = load_peaks()
+    # cfg4's per-step footprint (151 MB) is only just above the 126 MB L2: rotate two tensor sets
+    sets = 2 if cfg == "cfg4" else 1
+    wl = HeadWorkload(cfg, args, device, rank, world, lib, steps + warmup + 32, sets=sets)
+    try:
+        for _ in range(warmup + (20 if world > 1 else 0)):
+            wl.step()
+        ms = wl.time_steps(steps) / steps
+        check = wl.exchange_check()
+        out = {"workload": WORKLOAD_NAMES[cfg], "rows_per_gpu": wl.B, "fwd_bwd": wl.bwd, "steps": steps,
+               "ms_per_step": ms, "samples_per_s": wl.B * world / (ms * 1e-3),
+               "roofline_frac": wl.bytes_per_row * wl.B / (ms * 1e-3) / 1e9 / peak,
+               "bytes_per_row": wl.bytes_per_row, "tensor_sets_rotated": sets}
+        if check is not None:
+            out["exchange_check"] = {k: check[k] for k in ("ok", "max_rel_err", "nan", "payload_nonzero")}
+        return out
+    finally:
+        wl.close()
+        del wl
+        torch.cuda.empty_cache()
+
+
 def run_ours(args):
     import torch
 
     from normalizingflownetwork_b200 import _lib, parallel
-    from normalizingflownetwork_b200 import functional as F
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: normalizingflownetwork_b200 has no CPU fallback")
@@ -303,121 +497,34 @@ def run_ours(args):
     device = torch.device("cuda", local_rank)
     lib = _lib.load()
     cfg = args.config
-    ft, d, tb, B, bwd = CONFIGS[cfg]
-    if args.fwd_only:
-        bwd = False
-    if args.rows:
-        B = args.rows
-    P = param_size(ft, d, tb)
-    mdn = is_mdn(ft)
-    desc = None if mdn else _lib.make_desc(ft, d, tb)
-    specialized = True if mdn else bool(lib.nfn_chain_is_specialized(ctypes.byref(desc)))
     K, W = args.steps, args.warmup
-
-    gen = torch.Generator(device=device).manual_seed(22 + rank)
-    t = torch.randn((B, P), generator=gen, device=device) * 0.5
-    y = torch.randn((B, d), generator=gen, device=device)
-    logp = torch.empty(B, device=device)
-    dt = torch.empty((B, P), device=device) if bwd else None
-    # fp64 accumulators [gradient payload / dt column sums (P) | sum logp], one row per step,
-    # zeroed once up front (a ring of pre-zeroed buffers keeps memsets off the critical path);
-    # a data-parallel step sums its row over ranks with ONE all-reduce.
-    acc_ring = torch.zeros((K + W + 32, P + 1), dtype=torch.float64, device=device)
-    want_col = bool(bwd and args.colsum and not mdn)
-    packed = (world > 1 and bwd)
-    use_peer = bool(packed and args.exchange == "peer" and not mdn)
-    comm = None
-    if use_peer:
-        # cudaIpc peer mapping can be unavailable (e.g. ranks in different containers): every rank must
-        # agree, so the outcome is all-reduced and the NCCL exchange is the fallback
-        try:
-            comm = parallel.PeerComm(P + 1, device)
-            ok = 1
-        except Exception as exc:  # noqa: BLE001
-            ok = 0
-            if rank == 0:
-                print("peer exchange unavailable (%s): falling back to NCCL" % exc, file=sys.stderr)
-        flag = torch.tensor([ok], device=device)
-        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            if comm is not None:
-                comm.close()
-            comm, use_peer = None, False
-    step_no = [0]
-    acc_base = acc_ring.data_ptr()
-    row_bytes = (P + 1) * 8
-    g_scale = -1.0 / (B * world)
-    stream = _lib.current_stream(device)
-
-    def kernel():
-        row = acc_base + step_no[0] * row_bytes
-        lsum = ctypes.c_void_p(row + 8 * P)
-        col = ctypes.c_void_p(row) if want_col else None
-        if mdn and not bwd:
-            _lib.check(lib.nfn_mdn_forward(ft[1], d, _lib.ptr(t), _lib.ptr(y), B, _lib.ptr(logp), B, stream))
-        elif use_peer:  # ONE launch: fused fwd+bwd + all-reduce of [payload | sum logp] in the last CTA
-            _lib.check(lib.nfn_chain_forward_backward_peer(
-                ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), B, None, ctypes.c_float(g_scale), _lib.ptr(logp),
-                _lib.ptr(dt), None, 1 if want_col else 0, comm.comm, ctypes.c_void_p(row), B, stream))
-        elif mdn:
-            _lib.check(lib.nfn_mdn_forward_backward(
-                ft[1], d, _lib.ptr(t), _lib.ptr(y), B, None, ctypes.c_float(g_scale), _lib.ptr(logp),
-                _lib.ptr(dt), None, lsum, None, B, stream))
-        elif bwd:
-            _lib.check(lib.nfn_chain_forward_backward(
-                ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), B, None, ctypes.c_float(g_scale), _lib.ptr(logp),
-                _lib.ptr(dt), None, lsum, col, B, stream))
-        else:
-            _lib.check(lib.nfn_chain_forward(ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), B, _lib.ptr(logp), B,
-                                             stream))
-
-    def exchange():
-        if packed and not use_peer:
-            torch.distributed.all_reduce(acc_ring[step_no[0]])
-        step_no[0] += 1
-
-    def step():
-        kernel()
-        exchange()
+    # N > 1: the per-step exchange couples the ranks, so cold NVLink links / peer mappings and start-up skew
+    # would be billed to the first timed steps; top the warm-up up to 30 untimed steps (reported in config)
+    extra_warmup = max(0, 30 - W) if world > 1 else 0
+    wl = HeadWorkload(cfg, args, device, rank, world, lib, 3 * K + W + extra_warmup + 64, rows=args.rows or None,
+                      fwd_only=args.fwd_only, colsum=not args.no_colsum)
+    B, P, d, bwd, mdn = wl.B, wl.P, wl.d, wl.bwd, wl.mdn
+    t, y, logp, dt = wl.sets[0]
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # N > 1: the per-step exchange couples the ranks, so cold NVLink links / peer mappings and start-up skew
-    # would be billed to the first timed steps; top the warm-up up to 30 untimed steps (reported in config)
-    extra_warmup = max(0, 30 - W) if world > 1 else 0
     for _ in range(W + extra_warmup):
-        step()
-    torch.cuda.synchronize()
-    parallel.barrier()
-    torch.cuda.synchronize()
-
+        wl.step()
     lib.nfn_launch_count_reset()
     wall0 = time.perf_counter()
-    # per-launch kernel time: events around every `stride`-th launch of the timed region (at
-    # most 16 probes, so the probes themselves do not open gaps between back-to-back launches)
-    stride = max(1, K // 16)
-    ev = {i: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for i in range(0, K, stride)}
-    t_start = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for i in range(K):
-        probe = ev.get(i)
-        if probe is not None:
-            probe[0].record()
-        kernel()
-        if probe is not None:
-            probe[1].record()
-        exchange()
-    t_end.record()
-    torch.cuda.synchronize()
-    parallel.barrier()
-    torch.cuda.synchronize()
+    total_ms = wl.time_steps(K)
     launches = int(lib.nfn_launch_count_reset())
-    total_ms = parallel.max_over_ranks(t_start.elapsed_time(t_end), device)
-    kern_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev.values())
-    kern_ms = parallel.max_over_ranks(kern_ms, device)
+    ms_per_step = total_ms / K
+    value = B * world * K / (total_ms * 1e-3)
+    check = wl.exchange_check()
+    # average launch duration of the dominant kernel: the timed region itself when a step is exactly one
+    # launch of it, otherwise a second pass of K back-to-back launches without the NCCL exchange
+    if wl.step_is_one_kernel:
+        kern_ms, kern_how = ms_per_step, "timed region / steps (a step is exactly one launch of this kernel)"
+    else:
+        kern_ms = wl.time_steps(K, with_exchange=False) / K
+        kern_how = "separate pass: %d back-to-back launches under one event pair (the step adds an NCCL all-reduce)" % K
     wall1 = time.perf_counter()
     replay_note = None
     if rank == 0 and sum(1 for smp in sampler.samples if wall0 <= smp[0] <= wall1) < 3 and world == 1:
@@ -426,15 +533,13 @@ def run_ours(args):
         t_rep = time.perf_counter()
         while time.perf_counter() - t_rep < 0.04:
             for _ in range(20):
-                kernel()
+                wl.kernel()
             torch.cuda.synchronize()
         wall1 = time.perf_counter()
         replay_note = "timed region + 40 ms untimed replay of the same launches (timed region shorter than 3 NVML polls)"
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     if clocks is not None and replay_note and clocks.get("window") == "timed region":
         clocks["window"] = replay_note
-    ms_per_step = total_ms / K
-    value = B * world * K / (total_ms * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call (pinned host buffers)
     # the pinned buffers are allocated (first-touched) and the calls issued from the CPUs NVML reports as
@@ -450,6 +555,7 @@ def run_ours(args):
     h_logp = torch.empty(B, dtype=torch.float32).pin_memory()
     h_dt = torch.empty((B, P), dtype=torch.float32).pin_memory() if bwd else None
     h_sum = ctypes.c_double(0.0)
+    ft, desc, g_scale = wl.ft, wl.desc, wl.g_scale
 
     def e2e_step():
         if mdn and not bwd:
@@ -482,14 +588,30 @@ def run_ours(args):
     h2d = 4 * B * (P + d)
     d2h = 4 * B * (1 + (P if bwd else 0)) + 8
     lib.nfn_host_release()
-    if comm is not None:
-        comm.close()
     # the host path must reproduce the device path bit for bit
     same = bool(torch.equal(h_logp, logp.cpu()))
+    specialized, use_peer, packed, want_col = wl.specialized, wl.use_peer, wl.packed, wl.want_col
+    bytes_per_row = wl.bytes_per_row
+    wl.close()
+    del wl, t, y, logp, dt, h_t, h_dt
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, a few steps each, on the same line (every rank takes part: weak scaling)
+    others = {}
+    if not args.rows and not args.fwd_only and not args.no_other_configs and cfg == "cfg2":
+        for oc in ("cfg3", "cfg4", "cfg5"):
+            try:
+                others[oc] = measure_other_config(oc, args, device, rank, world, lib)
+            except Exception as exc:  # noqa: BLE001 -- an extra must not take the headline down
+                others[oc] = {"error": str(exc)[:200]}
+        if world == 1:
+            try:
+                others["cfg1-pipeline"] = cfg1_pipeline(args.steps, 3, cpu=False)
+            except Exception as exc:  # noqa: BLE001
+                others["cfg1-pipeline"] = {"error": str(exc)[:200]}
 
     if rank != 0:
-        return 0
-    bytes_per_row = 4 * ((2 * P if bwd else P) + d + 1)
+        return 0 if (check is None or check["ok"]) else 3
     peak, peak_src = load_peaks()
     achieved = bytes_per_row * B / (kern_ms * 1e-3) / 1e9
     cpu = cpu_baseline(cfg) if (world == 1 and not args.no_cpu_baseline) else None
@@ -502,13 +624,15 @@ def run_ours(args):
             "workload": WORKLOAD_NAMES[cfg], "rows_per_gpu": B, "param_width": P, "n_dims": d,
             "fwd_bwd": bwd, "specialized_kernel": specialized, "math": "accurate" if os.environ.get(
                 "NFN_B200_MATH") == "accurate" else "fast",
+            "dt_column_sums_in_kernel": want_col,
             "l2": "inputs+outputs per step (%d MB) exceed the 126 MB L2; no flush needed" % (
                 bytes_per_row * B // (1 << 20)),
             "parallelism": "dp%d (rows sharded, no data-path collective%s)" % (
-                world, ("; [P-value gradient payload | sum logp] summed over ranks every step, " + (
+                world, ("; [dt column sums (P) | sum logp] summed over ranks every step, " + (
                     "fused into the kernel's last CTA over NVLink peer memory" if use_peer else
                     "one NCCL all-reduce")) if packed else ""),
             "t_sigma": 0.5, "seed": 22, "extra_untimed_warmup_steps": extra_warmup,
+            "timing": "one CUDA-event pair around the %d steps, no per-launch probes" % K,
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": ("nfn_mdn_forward_backward_host" if mdn else
@@ -517,14 +641,22 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": load_traffic(cfg), "peak_source": peak_src,
-                     "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": bytes_per_row * B},
+                     "kernel_ms": kern_ms, "kernel_ms_how": kern_how,
+                     "algorithmic_bytes_per_launch": bytes_per_row * B},
         "clocks": clocks,
     }
+    if check is not None:
+        line["exchange_check"] = check
+    if others:
+        line["other_configs"] = others
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if fused is not None:
         line["fused_dense_step"] = fused
     print(json.dumps(line), flush=True)
+    if check is not None and not check["ok"]:
+        print("exchange_check FAILED: %r" % (check,), file=sys.stderr)
+        return 3
     return 0
 
 
@@ -566,7 +698,7 @@ def fused_dense_step(cfg, device, steps=20):
             "bytes_per_row": 4 * (2 * H + d + 1), "hbm_frac": 4 * (2 * H + d + 1) * B / (us * 1e-6) / 1e9 / load_peaks()[0]}
 
 
-def run_cfg1_pipeline(args):
+def cfg1_pipeline(K, W, cpu=True):
     """BASELINE config 1 as the real pipeline: NormalizingFlowNetwork (3 radial flows, 1-D y,
     MLP (16,16) tanh) on gen_cosine_noise_data(2048): latency of log_pdf and of one Adam step
     (eager launches vs one CUDA-graph replay), next to the same pipeline on the host cores
@@ -575,14 +707,12 @@ def run_cfg1_pipeline(args):
 
     from normalizingflownetwork_b200.estimators import NormalizingFlowNetwork
     from normalizingflownetwork_b200.simulation import gen_cosine_noise_data
-    from oracle import flow_oracle as fo
 
     B = 2048
     x, y = gen_cosine_noise_data(B, noise_std=0.3, heterosced_noise=0.5)
     model = NormalizingFlowNetwork.build_function(n_dims=1, n_flows=3, hidden_sizes=(16, 16), activation="tanh")
     model.fit(x, y, batch_size=B, epochs=3, verbose=0)
     xd, yd = model._to_dev(x), model._to_dev(y)
-    K, W = args.steps, args.warmup
 
     def timed(fn, n):
         for _ in range(W):
@@ -612,7 +742,11 @@ def run_cfg1_pipeline(args):
         model.log_pdf_graphed(x, y).cpu()
     us_logpdf_e2e_graph = (time.perf_counter() - t0) * 1e6 / K
 
+    if not cpu:
+        return _cfg1_line(B, K, W, us_logpdf, us_logpdf_graph, us_logpdf_e2e, us_logpdf_e2e_graph, us_step, us_step_graph, None)
     # CPU port of the same pipeline
+    from oracle import flow_oracle as fo
+
     torch.set_num_threads(os.cpu_count() or 1)
     lin = [m.linear for m in model.net if hasattr(m, "linear")]
     Ws = [(l.weight.detach().cpu().clone().requires_grad_(True), l.bias.detach().cpu().clone().requires_grad_(True))
@@ -646,6 +780,13 @@ def run_cfg1_pipeline(args):
     with torch.no_grad():
         us_cpu_logpdf = cpu_timed(cpu_logp, 50)
     us_cpu_step = cpu_timed(cpu_step, 50)
+    return _cfg1_line(B, K, W, us_logpdf, us_logpdf_graph, us_logpdf_e2e, us_logpdf_e2e_graph, us_step, us_step_graph,
+                      {"kind": "port", "cores": os.cpu_count(), "log_pdf_us": us_cpu_logpdf,
+                       "fit_step_us": us_cpu_step, "unit": "us",
+                       "sample": "same 2048-row batch; torch-CPU MLP + fp32 restatement of the reference's TF graph"})
+
+
+def _cfg1_line(B, K, W, us_logpdf, us_logpdf_graph, us_logpdf_e2e, us_logpdf_e2e_graph, us_step, us_step_graph, cpu):
     line = {
         "metric": "NFN config-1 pipeline latency (log_pdf, Adam fit step), batch 2048", "unit": "us",
         "higher_is_better": False, "n_gpus": 1, "steps": K, "warmup": W, "dtype": "f32", "data": "synthetic",
@@ -656,12 +797,15 @@ def run_cfg1_pipeline(args):
         "log_pdf_host_in_host_out_cuda_graph_us": us_logpdf_e2e_graph,
         "fit_step_eager_us": us_step, "fit_step_cuda_graph_us": us_step_graph,
         "samples_per_s_fit_graph": B / (us_step_graph * 1e-6), "samples_per_s_log_pdf": B / (us_logpdf * 1e-6),
-        "cpu_baseline": {"kind": "port", "cores": os.cpu_count(), "log_pdf_us": us_cpu_logpdf,
-                         "fit_step_us": us_cpu_step, "unit": "us",
-                         "sample": "same 2048-row batch; torch-CPU MLP + fp32 restatement of the reference's TF graph"},
         "note": "launch-latency-bound (197 KB of head traffic): no roofline claim",
     }
-    print(json.dumps(line), flush=True)
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    return line
+
+
+def run_cfg1_pipeline(args):
+    print(json.dumps(cfg1_pipeline(args.steps, args.warmup)), flush=True)
     return 0
 
 
@@ -677,7 +821,10 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the step sums its fp64 accumulators over ranks -- 'peer' = fused into the "
                          "kernel's last CTA over NVLink peer memory (default), 'nccl' = a separate all-reduce")
-    ap.add_argument("--colsum", action="store_true", help="also accumulate dt column sums at N=1 (tuning)")
+    ap.add_argument("--no-colsum", action="store_true",
+                    help="leave the in-kernel dt column sums (bias gradient of the emitting layer) out (tuning)")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the other BASELINE configs that are reported next to the cfg2 headline")
     ap.add_argument("--fwd-only", action="store_true", help="time the forward-only kernel of the config (tuning)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -266,6 +266,20 @@ int64_t nfn_launch_count_reset(void);
  * environment variable NFN_B200_MATH=accurate selects 1 at first use. */
 int nfn_set_math_mode(int accurate);
 
+/* Process-wide run-time switches (tests, A/B tuning).  Each has an environment default that is read once,
+ * at first use; no launch path calls getenv.  Names and values:
+ *   "math"          0 fast | 1 accurate                                   (NFN_B200_MATH=accurate)
+ *   "force_generic" 1: every chain through the runtime-chain kernel       (NFN_B200_FORCE_GENERIC)
+ *   "force_jit"     1: skip the ahead-of-time kernel instances            (NFN_B200_FORCE_JIT)
+ *   "jit"           0: runtime specialiser off                            (NFN_B200_JIT=0)
+ *   "chain_io"      -1 measured default | 0 cp.async CTA-tile kernels | 1 bulk-copy / TMA warp-tile kernels
+ *                                                                         (NFN_B200_CHAIN_IO=cpasync|tma)
+ *   "dense_mma"     0 auto | 1 tcgen05 | 2 mma.sync                       (NFN_B200_DENSE_MMA=tc5|sync)
+ *   "pdl"           0: no programmatic dependent launch                   (NFN_B200_PDL=0)
+ * Unknown names return NFN_ERR_DESC. */
+int nfn_set_option(const char* name, int value);
+int nfn_get_option(const char* name);
+
 const char* nfn_last_error(void);
 int nfn_version(void);
 

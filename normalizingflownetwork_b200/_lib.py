@@ -42,6 +42,8 @@ SIGNATURES = {
     "nfn_version": (ctypes.c_int, []),
     "nfn_last_error": (ctypes.c_char_p, []),
     "nfn_set_math_mode": (ctypes.c_int, [ctypes.c_int]),
+    "nfn_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
+    "nfn_get_option": (ctypes.c_int, [ctypes.c_char_p]),
     "nfn_launch_count_reset": (_i64, []),
     "nfn_host_release": (ctypes.c_int, []),
     "nfn_chain_param_size": (ctypes.c_int, [ctypes.POINTER(ChainDesc)]),

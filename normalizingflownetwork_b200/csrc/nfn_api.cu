@@ -4,9 +4,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
+
+#include <cuda.h>
 
 #include "nfn_common.h"
 
@@ -52,21 +55,72 @@ const DeviceInfo& device_info() {
   return info;
 }
 
-static int g_math_mode = -1;
-int math_mode() {
-  if (g_math_mode < 0) {
-    const char* e = getenv("NFN_B200_MATH");
-    g_math_mode = (e && (!strcmp(e, "accurate") || !strcmp(e, "1"))) ? 1 : 0;
-  }
-  return g_math_mode;
+// ------------------------------------------------------------------ options
+// Every switch is read from the environment ONCE (first use) and can be changed afterwards with
+// nfn_set_option(); a launch never calls getenv.  `g_opt_gen` invalidates the per-thread descriptor cache.
+static int g_opt[kOptCount];
+static std::once_flag g_opt_once;
+static std::atomic<unsigned> g_opt_gen{1};
+
+static bool env_is(const char* name, const char* a, const char* b = nullptr) {
+  const char* e = getenv(name);
+  return e && (!strcmp(e, a) || (b && !strcmp(e, b)));
 }
 
-bool pdl_enabled() {
-  static const bool on = [] {
-    const char* ev = getenv("NFN_B200_PDL");
-    return !(ev && strcmp(ev, "0") == 0);
+static void init_options() {
+  g_opt[kOptMath] = env_is("NFN_B200_MATH", "accurate", "1") ? 1 : 0;
+  g_opt[kOptForceGeneric] = getenv("NFN_B200_FORCE_GENERIC") ? 1 : 0;
+  g_opt[kOptForceJit] = getenv("NFN_B200_FORCE_JIT") ? 1 : 0;
+  g_opt[kOptJit] = env_is("NFN_B200_JIT", "0") ? 0 : 1;
+  g_opt[kOptChainIo] = env_is("NFN_B200_CHAIN_IO", "tma", "bulk") ? 1 : (env_is("NFN_B200_CHAIN_IO", "cpasync", "ldgsts") ? 0 : -1);
+  g_opt[kOptDenseMma] = env_is("NFN_B200_DENSE_MMA", "tc5") ? 1 : (env_is("NFN_B200_DENSE_MMA", "sync") ? 2 : 0);
+  g_opt[kOptPdl] = env_is("NFN_B200_PDL", "0") ? 0 : 1;
+  g_opt[kOptDebug] = getenv("NFN_B200_DEBUG") ? 1 : 0;
+  long mb = 16;
+  if (const char* ev = getenv("NFN_B200_HOST_CHUNK_MB")) {
+    const long v = atol(ev);
+    if (v >= 1 && v <= 1024) mb = v;
+  }
+  g_opt[kOptHostChunkMb] = (int)mb;
+}
+
+int option(Opt o) {
+  std::call_once(g_opt_once, init_options);
+  return g_opt[o];
+}
+
+static const char* const kOptNames[kOptCount] = {"math", "force_generic", "force_jit", "jit", "chain_io",
+                                                 "dense_mma", "pdl", "debug", "host_chunk_mb"};
+
+int math_mode() { return option(kOptMath); }
+int chain_io_override() { return option(kOptChainIo); }
+bool pdl_enabled() { return option(kOptPdl) != 0; }
+
+int encode_row_tensor_map(TensorMap* out, const float* base, long long rows, int P, int W) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static const EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return (EncodeFn)fn;
   }();
-  return on;
+  if (!encode) return set_error(NFN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  if (rows < 1 || rows >= (1ll << 31)) return set_error(NFN_ERR_SHAPE, "B=%lld outside the tensor map's range", rows);
+  static_assert(sizeof(CUtensorMap) == sizeof(TensorMap), "CUtensorMap is 128 bytes");
+  const CUtensorMapSwizzle swz = W == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : (W == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const cuuint64_t dims[2] = {(cuuint64_t)P, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)P * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)W, 32u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2u, const_cast<float*>(base),
+                            dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(NFN_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d) for [%lld, %d], box [32, %d]", (int)r, rows, P, W);
+  return NFN_OK;
 }
 
 // ------------------------------------------------------------------ registry
@@ -89,7 +143,7 @@ long long jit_compile_check(const nfn_chain_desc* desc, int mode, std::string& l
 const ChainKernels* find_chain(const std::string& key) {
   // test / tuning switches: FORCE_GENERIC skips both specialised paths, FORCE_JIT skips the
   // ahead-of-time instances so that the runtime specialiser serves every chain
-  if (getenv("NFN_B200_FORCE_GENERIC") || getenv("NFN_B200_FORCE_JIT")) return nullptr;
+  if (option(kOptForceGeneric) || option(kOptForceJit)) return nullptr;
   auto it = registry().find(key);
   return it == registry().end() ? nullptr : &it->second;
 }
@@ -100,7 +154,7 @@ static std::unordered_map<std::string, DenseKernels>& dense_registry() {
 }
 void register_dense(const std::string& key, const DenseKernels& k) { dense_registry()[key] = k; }
 const DenseKernels* find_dense(const std::string& key) {
-  if (getenv("NFN_B200_FORCE_JIT")) return nullptr;
+  if (option(kOptForceJit)) return nullptr;
   auto it = dense_registry().find(key);
   return it == dense_registry().end() ? nullptr : &it->second;
 }
@@ -141,15 +195,42 @@ static int check_rows(int64_t B, int64_t y_rows) {
   return NFN_OK;
 }
 
+// Per-thread memo of the last descriptor's registry lookup: a launch of the same chain as the previous one
+// (the normal case) builds no key string and touches no map.
+struct DescMemo {
+  nfn_chain_desc desc;
+  unsigned gen = 0;
+  std::string key;
+  const ChainKernels* kernels = nullptr;
+};
+static thread_local DescMemo g_memo;
+
+static const DescMemo& lookup_chain(const nfn_chain_desc* desc) {
+  DescMemo& m = g_memo;
+  const unsigned gen = g_opt_gen.load(std::memory_order_relaxed);
+  const size_t used = offsetof(nfn_chain_desc, flow_type) + (size_t)desc->n_flows;
+  if (m.gen != gen || m.desc.n_flows != desc->n_flows || memcmp(&m.desc, desc, used) != 0) {
+    memset(&m.desc, 0, sizeof(m.desc));
+    memcpy(&m.desc, desc, used);
+    m.key = chain_key(desc->n_dims, desc->trainable_base != 0, desc->n_flows, desc->flow_type);
+    m.kernels = find_chain(m.key);
+    m.gen = gen;
+  }
+  return m;
+}
+
 static int chain_dispatch(const nfn_chain_desc* desc, const ChainArgs& a, bool bwd, cudaStream_t st) {
-  const std::string key = chain_key(desc->n_dims, desc->trainable_base != 0, desc->n_flows, desc->flow_type);
+  const DescMemo& memo = lookup_chain(desc);
+  const std::string& key = memo.key;
   const int mode = math_mode();
-  const ChainKernels* k = find_chain(key);
+  const ChainKernels* k = memo.kernels;
   cudaError_t e;
   if (k && k->fn[mode][bwd ? 1 : 0]) {
-    e = k->fn[mode][bwd ? 1 : 0](a, st);
+    const int io = chain_io_override();
+    const bool warp_tile = k->fnw[mode][bwd ? 1 : 0] && (io >= 0 ? io == 1 : chain_prefers_warp_tile(k->P, bwd));
+    e = (warp_tile ? k->fnw : k->fn)[mode][bwd ? 1 : 0](a, st);
   } else {
-    if (!getenv("NFN_B200_FORCE_GENERIC")) {
+    if (!option(kOptForceGeneric)) {
       bool served = false;
       e = launch_chain_jit(desc, key, a, bwd, mode, st, &served);
       if (e != cudaSuccess || served) return cuda_error(e, key.c_str());
@@ -186,9 +267,25 @@ int64_t nfn_launch_count_reset(void) {
   return n;
 }
 
-int nfn_set_math_mode(int accurate) {
-  g_math_mode = accurate ? 1 : 0;
-  return NFN_OK;
+int nfn_set_math_mode(int accurate) { return nfn_set_option("math", accurate ? 1 : 0); }
+
+int nfn_set_option(const char* name, int value) {
+  if (!name) return set_error(NFN_ERR_NULL, "option name is NULL");
+  option(kOptMath);  // environment defaults first
+  for (int i = 0; i < kOptCount; ++i)
+    if (!strcmp(name, kOptNames[i])) {
+      g_opt[i] = value;
+      g_opt_gen.fetch_add(1);
+      return NFN_OK;
+    }
+  return set_error(NFN_ERR_DESC, "unknown option '%s'", name);
+}
+
+int nfn_get_option(const char* name) {
+  if (!name) return set_error(NFN_ERR_NULL, "option name is NULL");
+  for (int i = 0; i < kOptCount; ++i)
+    if (!strcmp(name, kOptNames[i])) return option((Opt)i);
+  return set_error(NFN_ERR_DESC, "unknown option '%s'", name);
 }
 
 int nfn_chain_param_size(const nfn_chain_desc* desc) {
@@ -211,7 +308,7 @@ int64_t nfn_jit_compile_check(const nfn_chain_desc* desc, int accurate) {
 int nfn_chain_is_specialized(const nfn_chain_desc* desc) {
   int rc = check_desc(desc);
   if (rc != NFN_OK) return rc;
-  return find_chain(chain_key(desc->n_dims, desc->trainable_base != 0, desc->n_flows, desc->flow_type)) ? 1 : 0;
+  return lookup_chain(desc).kernels ? 1 : 0;
 }
 
 int nfn_chain_forward(const nfn_chain_desc* desc, const float* t, const float* y, int64_t y_rows,
@@ -313,8 +410,7 @@ static int dense_dispatch(const nfn_chain_desc* desc, int hidden, const DenseArg
   // weight tiles, a one-tile pipeline delay): B = 2048..16384 rows 8.4 vs 6.2 us (P = 11), 10.8 vs 10.3 us
   // (P = 48); the crossover tracks rows x parameters, so tcgen05 takes launches with B * P >= 4 M (fwd+bwd) /
   // 1 M (forward).  NFN_B200_DENSE_MMA=tc5|sync forces one of them (A/B comparisons, tests).
-  const char* ev = getenv("NFN_B200_DENSE_MMA");
-  const bool force5 = ev && strcmp(ev, "tc5") == 0, force_sync = ev && strcmp(ev, "sync") == 0;
+  const bool force5 = option(kOptDenseMma) == 1, force_sync = option(kOptDenseMma) == 2;
   const bool want5 = force5 || (!force_sync && a.B * (long long)param_size(desc) >= (bwd ? (4ll << 20) : (1ll << 20)));
   if (want5 && k && k->fn5[mode][bwd ? 1 : 0]) return cuda_error(k->fn5[mode][bwd ? 1 : 0](a, st), key.c_str());
   bool served = false;
@@ -607,11 +703,7 @@ static int host_pipeline(int P, int d, bool bwd, const float* t, const float* y,
   }
   // ~16 MiB of parameters per chunk (NFN_B200_HOST_CHUNK_MB overrides, tuning only), at least 3
   // chunks in flight when B allows it
-  size_t chunk_mb = 16;
-  if (const char* ev = getenv("NFN_B200_HOST_CHUNK_MB")) {
-    const long v = atol(ev);
-    if (v >= 1 && v <= 1024) chunk_mb = (size_t)v;
-  }
+  const size_t chunk_mb = (size_t)option(kOptHostChunkMb);
   int64_t rows = (int64_t)((chunk_mb << 20) / ((size_t)(P > 0 ? P : 1) * sizeof(float)));
   rows = rows / 1024 * 1024;
   if (rows < 1024) rows = 1024;

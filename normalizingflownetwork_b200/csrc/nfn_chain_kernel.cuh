@@ -118,35 +118,65 @@ struct ChainArgs {
 };
 
 // ---------------------------------------------------------------- smem span load/store
+// A parameter row is addressed either through a plain pointer (row-major tile with row stride S,
+// the cp.async kernels and the fused Dense kernels) or through an SRow (the warp-tile kernels
+// below, where the bulk-copy engine lays the tile down unpadded, 128-byte-swizzled when the row
+// width needs it).  Span<OFF, N, V> moves N consecutive floats starting at column OFF with the
+// widest accesses the alignment allows; all offsets are compile-time.
+NFN_DEVI char* dyn_smem() {
+  extern __shared__ __align__(16) char nfn_dyn_smem_[];
+  return nfn_dyn_smem_;
+}
+
+// CW 16-byte chunks per box row (1 = linear layout), BOXB bytes between consecutive boxes of a tile:
+// column col lives at x[(col/4) % CW] + ((col/4) / CW) * BOXB + (col % 4) * 4 bytes past the dynamic
+// shared-memory base; x[c] = (this thread's row base) + ((c ^ swizzle key of the row) << 4).
+template <int CW, int BOXB>
+struct SRow {
+  unsigned x[CW];
+  template <int COL>
+  NFN_DEVI char* at() const {
+    constexpr int k = COL / 4;
+    return dyn_smem() + (x[k % CW] + (unsigned)((k / CW) * BOXB + (COL % 4) * 4));
+  }
+};
+
+template <int OFF, class T> NFN_DEVI const T* row_ptr(const float* row) { return reinterpret_cast<const T*>(row + OFF); }
+template <int OFF, class T> NFN_DEVI T* row_ptr(float* row) { return reinterpret_cast<T*>(row + OFF); }
+template <int OFF, class T, int CW, int BOXB>
+NFN_DEVI T* row_ptr(SRow<CW, BOXB> row) { return reinterpret_cast<T*>(row.template at<OFF>()); }
+
 template <int OFF, int N, int V>
 struct Span {
-  NFN_DEVI static void load(const float* row, float* out) {
+  template <class R>
+  NFN_DEVI static void load(R row, float* out) {
     if constexpr (N <= 0) {
       return;
     } else if constexpr (V >= 4 && OFF % 4 == 0 && N >= 4) {
-      const float4 v = *reinterpret_cast<const float4*>(row + OFF);
+      const float4 v = *row_ptr<OFF, const float4>(row);
       out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
       Span<OFF + 4, N - 4, V>::load(row, out + 4);
     } else if constexpr (V >= 2 && OFF % 2 == 0 && N >= 2) {
-      const float2 v = *reinterpret_cast<const float2*>(row + OFF);
+      const float2 v = *row_ptr<OFF, const float2>(row);
       out[0] = v.x; out[1] = v.y;
       Span<OFF + 2, N - 2, V>::load(row, out + 2);
     } else {
-      out[0] = row[OFF];
+      out[0] = *row_ptr<OFF, const float>(row);
       Span<OFF + 1, N - 1, V>::load(row, out + 1);
     }
   }
-  NFN_DEVI static void store(float* row, const float* in) {
+  template <class R>
+  NFN_DEVI static void store(R row, const float* in) {
     if constexpr (N <= 0) {
       return;
     } else if constexpr (V >= 4 && OFF % 4 == 0 && N >= 4) {
-      *reinterpret_cast<float4*>(row + OFF) = make_float4(in[0], in[1], in[2], in[3]);
+      *row_ptr<OFF, float4>(row) = make_float4(in[0], in[1], in[2], in[3]);
       Span<OFF + 4, N - 4, V>::store(row, in + 4);
     } else if constexpr (V >= 2 && OFF % 2 == 0 && N >= 2) {
-      *reinterpret_cast<float2*>(row + OFF) = make_float2(in[0], in[1]);
+      *row_ptr<OFF, float2>(row) = make_float2(in[0], in[1]);
       Span<OFF + 2, N - 2, V>::store(row, in + 2);
     } else {
-      row[OFF] = in[0];
+      *row_ptr<OFF, float>(row) = in[0];
       Span<OFF + 1, N - 1, V>::store(row, in + 1);
     }
   }
@@ -282,7 +312,8 @@ struct TileIO {
 template <class Spec, class M, int V, bool SAVE, int K0>
 struct FwdSweep {
   // flows K0 .. K-1
-  NFN_DEVI static void run(float* row, float (&z)[Spec::D], float (&zs)[Spec::KA][Spec::D],
+  template <class R>
+  NFN_DEVI static void run(R row, float (&z)[Spec::D], float (&zs)[Spec::KA][Spec::D],
                            LogDetAcc<M>& ld) {
     if constexpr (K0 < Spec::K) {
       constexpr int D = Spec::D;
@@ -312,7 +343,8 @@ struct FwdSweep {
 template <class Spec, class M, int V, int K0>
 struct BwdSweep {
   // flows K0 .. 0 (descending)
-  NFN_DEVI static void run(float* row, const float (&zs)[Spec::KA][Spec::D], float (&G)[Spec::D],
+  template <class R>
+  NFN_DEVI static void run(R row, const float (&zs)[Spec::KA][Spec::D], float (&G)[Spec::D],
                            float cot) {
     if constexpr (K0 >= 0) {
       constexpr int D = Spec::D;
@@ -647,6 +679,436 @@ NFN_DEVI void chain_body(const ChainArgs& a) {
 template <class Spec, bool BWD, class M, int T, int NB, int MINB>
 __global__ void __launch_bounds__(T, MINB) chain_kernel(const ChainArgs a) {
   chain_body<Spec, BWD, M, T, NB>(a);
+}
+
+
+// ================================================================ warp-tile kernels (bulk-copy engine)
+// Second generation of the chain kernel: every WARP owns its own tile pipeline, there is no CTA
+// barrier in the tile loop, and the tile moves through the bulk-copy engine instead of through
+// per-thread cp.async / LDS / STG instructions:
+//
+//   global t  --one elected lane: cp.async.bulk (1-D) or cp.async.bulk.tensor.2d (TMA), mbarrier
+//               complete_tx-->  smem warp tile [32 rows x P], UNPADDED
+//   lane r reads row r at compile-time offsets, runs the chain, writes d logp / d theta in place
+//   smem warp tile  --fence.proxy.async + one elected lane: bulk store (bulk_group)-->  global dt
+//
+// A warp tile is 32 consecutive rows = one contiguous 128*P-byte span.  Unpadded rows are
+// bank-conflict free for the per-thread V-wide reads exactly when P/V is odd (see row_stride);
+// otherwise (P % 8 == 0) the tile is loaded as boxes of [32 rows x W columns], W*4 = 32/64/128
+// bytes, through a 2-D tensor map with the matching 32B/64B/128B swizzle: the hardware XORs
+// the 16-byte chunk index with the row's address bits, thread r undoes it with a per-thread XOR key
+// that is folded into CW = W/4 base registers (SRow), so every parameter access still is one
+// LDS/STS at [register + immediate] and 8 consecutive lanes hit 8 distinct bank groups.
+// Out-of-range rows of the last tile are zero-filled / clipped by the tensor unit itself.
+struct alignas(64) TensorMap {   // CUtensorMap (128 opaque bytes), declared here so that NVRTC needs no cuda.h
+  unsigned long long opaque[16];
+};
+
+// box width (floats) of the swizzled layout for row width P; 0: linear layout (1-D bulk copies)
+__host__ __device__ constexpr int warp_tile_box(int P) {
+  return (P % 8 != 0) ? 0 : (P % 32 == 0 ? 32 : (P % 16 == 0 ? 16 : 8));
+}
+
+template <int P>
+struct WarpTile {
+  static constexpr int V = row_vec(P);
+  static constexpr bool kSwz = warp_tile_box(P) > 0;
+  static constexpr int W = kSwz ? warp_tile_box(P) : 4;
+  static constexpr int CW = kSwz ? W / 4 : 1;
+  static constexpr int NBX = kSwz ? P / W : 1;                 // boxes per tile
+  static constexpr int kBoxBytes = kSwz ? 32 * W * 4 : 16;     // linear layout: "boxes" of one chunk
+  static constexpr int kRowBytes = kSwz ? W * 4 : P * 4;       // smem pitch of this thread's row
+  static constexpr unsigned kTileBytes = 128u * P;
+  using Row = SRow<CW, kBoxBytes>;
+
+  NFN_DEVI static int key(int r) {
+    if constexpr (!kSwz) return 0;
+    else if constexpr (W == 32) return r & 7;
+    else if constexpr (W == 16) return (r >> 1) & 3;
+    else return (r >> 2) & 1;
+  }
+  // accessor of row r (0..31) of the tile at byte offset `tile` of the dynamic shared memory
+  NFN_DEVI static Row row(unsigned tile, int r) {
+    Row x;
+    const unsigned base = tile + (unsigned)(r * kRowBytes);
+#pragma unroll
+    for (int c = 0; c < CW; ++c) x.x[c] = base + (unsigned)((c ^ key(r)) << 4);
+    return x;
+  }
+  // byte offset (inside the tile) of V-wide column group g of row r
+  NFN_DEVI static unsigned group_off(int r, int g) {
+    if constexpr (!kSwz) {
+      return (unsigned)((r * P + g * V) * 4);
+    } else {
+      const int j = g / CW, c = g % CW;
+      return (unsigned)(j * kBoxBytes + r * kRowBytes + ((c ^ key(r)) << 4));
+    }
+  }
+};
+
+// ---- mbarrier / bulk-copy PTX
+NFN_DEVI void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+NFN_DEVI void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+NFN_DEVI void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "NFN_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra NFN_MBAR_DONE;\n"
+      "bra NFN_MBAR_WAIT;\n"
+      "NFN_MBAR_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+NFN_DEVI void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+NFN_DEVI bool elect_one() {
+  unsigned pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+NFN_DEVI void bulk_load_1d(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+NFN_DEVI void bulk_store_1d(void* dst, unsigned src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+NFN_DEVI void tma_load_2d(unsigned dst, const TensorMap* tm, int c0, int c1, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(tm), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+NFN_DEVI void tma_store_2d(const TensorMap* tm, int c0, int c1, unsigned src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(c0),
+               "r"(c1), "r"(src)
+               : "memory");
+}
+NFN_DEVI void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+NFN_DEVI void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+// ---- column sums of dt, warp-private: lane -> (V-wide column group, slice of the 32 rows); the partial
+// sums stay in registers across all tiles of the warp and meet in shared memory once, at the very end.
+template <int P>
+struct WarpColSum {
+  using L = WarpTile<P>;
+  static constexpr int V = L::V;
+  static constexpr int NG = P / V;                       // column groups
+  static constexpr int NGL = (NG + 31) / 32;             // groups per lane when NG > 32
+  __host__ __device__ static constexpr int row_splits() {
+    int rs = 1;
+    while (NG * rs * 2 <= 32) rs *= 2;
+    return rs;
+  }
+  static constexpr int RS = NG > 32 ? 1 : row_splits();  // slices of the 32 rows
+  static constexpr int RPS = 32 / RS;                    // rows per slice
+  float acc[NGL][V];
+
+  NFN_DEVI void clear() {
+#pragma unroll
+    for (int m = 0; m < NGL; ++m)
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[m][v] = 0.0f;
+  }
+  // rows [0, nvalid) of the tile at byte offset `tile`
+  NFN_DEVI void add_tile(unsigned tile, int lane, int nvalid) {
+    const char* base = dyn_smem() + tile;
+#pragma unroll
+    for (int m = 0; m < NGL; ++m) {
+      const int u = lane + 32 * m;
+      if (u < NG * RS) {
+        const int g = u % NG, r0 = (u / NG) * RPS;
+#pragma unroll 8
+        for (int i = 0; i < RPS; ++i) {
+          const int r = r0 + i;
+          if (r < nvalid) {
+            const char* p = base + L::group_off(r, g);
+            if constexpr (V == 4) {
+              const float4 x = *reinterpret_cast<const float4*>(p);
+              acc[m][0] += x.x; acc[m][1] += x.y; acc[m][2] += x.z; acc[m][3] += x.w;
+            } else if constexpr (V == 2) {
+              const float2 x = *reinterpret_cast<const float2*>(p);
+              acc[m][0] += x.x; acc[m][1] += x.y;
+            } else {
+              acc[m][0] += *reinterpret_cast<const float*>(p);
+            }
+          }
+        }
+      }
+    }
+  }
+  // scratch[warp][RS][P] floats; every lane deposits its partial sums (caller syncs the CTA afterwards)
+  NFN_DEVI void deposit(float* scratch, int warp, int lane) const {
+#pragma unroll
+    for (int m = 0; m < NGL; ++m) {
+      const int u = lane + 32 * m;
+      if (u < NG * RS) {
+        const int g = u % NG, rs = u / NG;
+#pragma unroll
+        for (int v = 0; v < V; ++v) scratch[(warp * RS + rs) * P + g * V + v] = acc[m][v];
+      }
+    }
+  }
+};
+
+// Launch geometry of the warp-tile kernels: NW warps per CTA (T = 32 NW threads), NB tile buffers per
+// warp, MINB resident CTAs per SM.  Wanted: 8 warps per SM with 3 buffers each for the fused kernel (load of
+// tile i+1 in flight, tile i in the registers, store of tile i-1 draining), 12 warps with 2 buffers for the
+// forward kernel; wide rows get fewer buffers, then fewer warps, until the tiles fit the SM's 227 KB.
+__host__ __device__ constexpr ChainGeometry warp_tile_geometry(int P, bool bwd) {
+#ifdef NFN_TUNE_WNB
+  int nb = NFN_TUNE_WNB;
+#else
+  int nb = bwd ? 3 : 2;
+#endif
+#ifdef NFN_TUNE_WWARPS
+  const int want = NFN_TUNE_WWARPS;
+#else
+  const int want = bwd ? 8 : 12;
+#endif
+  const unsigned tile = 128u * (unsigned)(P > 0 ? P : 1);
+  const unsigned budget = 227u * 1024u - 4u * 2560u;   // per SM, minus per-CTA reservations / alignment slack
+  while (nb > 2 && (unsigned)(want * nb) * tile > budget) --nb;
+  int warps = (int)(budget / ((unsigned)nb * tile));
+  if (warps > want) warps = want;
+  if (warps < 1) warps = 1;
+  const int ctas = (warps + 3) / 4;
+  const int nw = warps / ctas;
+  return ChainGeometry{nw * 32, nb, ctas, (unsigned)(nw * nb) * tile + 1024u, 0, 0, 0};
+}
+
+template <class Spec, bool BWD, class M, int NW, int NB>
+NFN_DEVI void chain_body_w(const ChainArgs& a, const TensorMap* tm_t, const TensorMap* tm_dt) {
+  constexpr int D = Spec::D;
+  constexpr int P = Spec::P();
+  static_assert(P > 0, "the warp-tile kernel needs a parameter row");
+  using L = WarpTile<P>;
+  using CS = WarpColSum<P>;
+  constexpr int V = L::V;
+  constexpr int T = NW * 32;
+  static_assert(NB >= 2 && NB <= 4, "2..4 tile buffers per warp");
+
+  __shared__ __align__(8) unsigned long long full[NW * NB];
+  __shared__ double red[NW];
+
+  // warp-uniform by construction (the compiler keeps the tile bookkeeping in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = (int)(threadIdx.x & 31);
+  const unsigned dyn_u32 = smem_u32(dyn_smem());
+  const unsigned pad = (1024u - (dyn_u32 & 1023u)) & 1023u;   // swizzle patterns are functions of the address
+  const unsigned tile0 = pad + (unsigned)(warp * NB) * L::kTileBytes;  // byte offset of this warp's buffer 0
+  const unsigned bar0 = smem_u32(full) + (unsigned)(warp * NB) * 8u;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NW * NB; ++i) mbar_init(smem_u32(full) + 8u * i, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // programmatic dependent launch, see chain_body
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  const long long nwt = (a.B + 31) / 32;                        // warp tiles
+  const long long GW = (long long)gridDim.x * NW;               // warps in the grid
+  long long wt = (long long)blockIdx.x * NW + warp;
+  // the last tile of a linear-layout kernel may be ragged: its bytes are not a whole number of 16-byte
+  // chunks in general, so it is moved with plain loads / stores by the lanes (one warp, once per launch)
+  const long long ragged = (!L::kSwz && (a.B & 31)) ? nwt - 1 : -1;
+
+  auto issue_load = [&](int slot, long long tl) {
+    if (tl == ragged) return;
+    if (elect_one()) {
+      const unsigned bar = bar0 + 8u * slot, dst = dyn_u32 + tile0 + (unsigned)slot * L::kTileBytes;
+      mbar_expect_tx(bar, L::kTileBytes);
+      if constexpr (L::kSwz) {
+#pragma unroll
+        for (int j = 0; j < L::NBX; ++j) tma_load_2d(dst + (unsigned)(j * L::kBoxBytes), tm_t, j * L::W, (int)(tl * 32), bar);
+      } else {
+        bulk_load_1d(dst, a.t + tl * (32 * P), L::kTileBytes, bar);
+      }
+    }
+  };
+
+  // prologue: NB-1 tiles in flight (forward) / NB-2 + the refill at the end of the first iteration (fused)
+  constexpr int kAhead = BWD ? NB - 2 : NB - 1;   // loads issued ahead of the tile being consumed, at its start
+#pragma unroll
+  for (int s = 0; s < NB - 1; ++s) {
+    const long long tl = wt + (long long)s * GW;
+    if (s <= kAhead && tl < nwt) issue_load(s, tl);
+  }
+
+  float y_nxt[D];
+  float g_nxt = 1.0f;
+  {
+    const long long r0 = wt * 32 + lane;
+#pragma unroll
+    for (int i = 0; i < D; ++i) y_nxt[i] = 0.0f;
+    if (wt < nwt && r0 < a.B) {
+      load_event<D>(a.y, a.y_broadcast ? 0 : r0, y_nxt);
+      if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + r0); }
+    }
+  }
+
+  CS cs;
+  if constexpr (BWD) cs.clear();
+  double lsum = 0.0;
+  int slot = 0;
+  unsigned parity = 0;
+  for (; wt < nwt; wt += GW) {
+    const unsigned tile = tile0 + (unsigned)slot * L::kTileBytes;
+    float z[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) z[i] = y_nxt[i];
+    const float g_cur = g_nxt;
+    {
+      const long long rn = (wt + GW) * 32 + lane;
+      if (rn < a.B) {
+        load_event<D>(a.y, a.y_broadcast ? 0 : rn, y_nxt);
+        if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + rn); }
+      }
+    }
+    if constexpr (!BWD) {
+      // forward: nothing is written back, the buffer of the previous tile is free as soon as every lane
+      // has left it (the __syncwarp that ended the previous iteration): refill it right away
+      const long long nxt = wt + (long long)(NB - 1) * GW;
+      if (nxt < nwt) issue_load(slot == 0 ? NB - 1 : slot - 1, nxt);
+    }
+    const int nvalid = (a.B - wt * 32 >= 32) ? 32 : (int)(a.B - wt * 32);
+    if (wt == ragged) {
+      float* dstf = reinterpret_cast<float*>(dyn_smem() + tile);
+      const float* src = a.t + wt * (32 * P);
+      for (int e = lane; e < nvalid * P; e += 32) dstf[e] = __ldg(src + e);
+      __syncwarp();
+    } else {
+      mbar_wait(bar0 + 8u * slot, parity);
+    }
+
+    const long long r = wt * 32 + lane;
+    const typename L::Row row = L::row(tile, lane);
+    bool done = false;
+    if constexpr (!BWD) {
+      if (a.grid_ny > 0) {
+        if (r < a.B) {
+          using Base = BaseDist<D, Spec::BASE, M>;
+          float bth[Base::NA];
+          if constexpr (Spec::BASE) Span<0, 2 * D, V>::load(row, bth);
+          for (int j = 0; j < a.grid_ny; ++j) {
+            float zg[D];
+            load_event<D>(a.y, j, zg);  // same address for the whole warp: one broadcast load
+            float zs[Spec::KA][D];
+            LogDetAcc<M> ld;
+            FwdSweep<Spec, M, V, false, 0>::run(row, zg, zs, ld);
+            a.logp[(long long)j * a.B + r] = Base::log_prob(bth, zg) + ld.nat();
+          }
+        }
+        done = true;
+      }
+    }
+    if (!done && r < a.B) {
+      float zs[Spec::KA][D];
+      LogDetAcc<M> ld;
+      FwdSweep<Spec, M, V, BWD, 0>::run(row, z, zs, ld);
+      using Base = BaseDist<D, Spec::BASE, M>;
+      float bth[Base::NA];
+      if constexpr (Spec::BASE) Span<0, 2 * D, V>::load(row, bth);
+      const float lp = (BWD ? Base::log_prob_save(bth, z) : Base::log_prob(bth, z)) + ld.nat();
+      a.logp[r] = lp;
+      lsum += (double)lp;
+      if constexpr (BWD) {
+        const float cot = a.g_scale * g_cur;
+        float G[D];
+        float gb[Base::NA];
+        Base::bwd_saved(bth, z, cot, G, gb);
+        if constexpr (Spec::BASE) Span<0, 2 * D, V>::store(row, gb);
+        BwdSweep<Spec, M, V, Spec::K - 1>::run(row, zs, G, cot);
+        if (a.dy) store_event<D>(a.dy, r, G);
+      }
+    }
+
+    if constexpr (BWD) {
+      fence_async_smem();   // this lane's gradient writes -> visible to the bulk-copy engine
+      __syncwarp();
+      if (wt == ragged) {
+        const float* srcf = reinterpret_cast<const float*>(dyn_smem() + tile);
+        float* dst = a.dt + wt * (32 * P);
+        for (int e = lane; e < nvalid * P; e += 32) dst[e] = srcf[e];
+      } else if (elect_one()) {
+        const unsigned src = dyn_u32 + tile;
+        if constexpr (L::kSwz) {
+#pragma unroll
+          for (int j = 0; j < L::NBX; ++j) tma_store_2d(tm_dt, j * L::W, (int)(wt * 32), src + (unsigned)(j * L::kBoxBytes));
+        } else {
+          bulk_store_1d(a.dt + wt * (32 * P), src, L::kTileBytes);
+        }
+        bulk_commit();
+      }
+      if (a.dt_colsum) cs.add_tile(tile, lane, nvalid);
+      // refill the buffer of the PREVIOUS tile: its store was committed one whole iteration ago, so waiting
+      // for "all but the newest group have been read" costs nothing
+      const long long nxt = wt + (long long)(NB - 1) * GW;
+      if (nxt < nwt) {
+        if (elect_one()) bulk_wait_read<1>();
+        __syncwarp();
+        issue_load(slot == 0 ? NB - 1 : slot - 1, nxt);
+      }
+    } else {
+      __syncwarp();
+    }
+    if (++slot == NB) { slot = 0; parity ^= 1u; }
+  }
+
+  if constexpr (BWD) {
+    // the tile buffers must outlive the bulk stores that read them
+    bulk_wait_read<0>();
+  }
+  if (a.logp_sum) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    if (lane == 0) red[warp] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < NW; ++i) s += red[i];
+      atomicAdd(a.logp_sum, s);
+    }
+  }
+  if constexpr (BWD) {
+    if (a.dt_colsum) {
+      __syncthreads();      // every warp is done with its tile buffers: reuse them as scratch
+      float* scratch = reinterpret_cast<float*>(dyn_smem() + pad);
+      cs.deposit(scratch, warp, lane);
+      __syncthreads();
+      for (int j = threadIdx.x; j < P; j += T) {
+        float s = 0.0f;
+#pragma unroll
+        for (int q = 0; q < NW * CS::RS; ++q) s += scratch[q * P + j];
+        atomicAdd(a.dt_colsum + j, (double)s);
+      }
+    }
+  }
+  if (a.peer.world > 0) peer_allreduce<T>(a.peer);
+}
+
+template <class Spec, bool BWD, class M, int NW, int NB, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
+chain_kernel_w(const ChainArgs a, const __grid_constant__ TensorMap tm_t, const __grid_constant__ TensorMap tm_dt) {
+  chain_body_w<Spec, BWD, M, NW, NB>(a, &tm_t, &tm_dt);
 }
 
 }  // namespace nfn

@@ -29,7 +29,20 @@ struct DeviceInfo {
 };
 const DeviceInfo& device_info();
 
-// Math mode: 0 = fast (MUFU-based, default), 1 = accurate (CUDA libm + IEEE division).
+// Run-time switches: environment defaults read once, nfn_set_option() afterwards (no getenv on a launch path).
+enum Opt {
+  kOptMath,          // 0 fast (MUFU-based, default) / 1 accurate (CUDA libm + IEEE division)   NFN_B200_MATH
+  kOptForceGeneric,  // every chain through the runtime-chain kernel                          NFN_B200_FORCE_GENERIC
+  kOptForceJit,      // skip the ahead-of-time instances                                      NFN_B200_FORCE_JIT
+  kOptJit,           // runtime specialiser enabled (default 1)                               NFN_B200_JIT=0
+  kOptChainIo,       // -1 measured default / 0 cp.async CTA tiles / 1 bulk copy, TMA warp tiles  NFN_B200_CHAIN_IO
+  kOptDenseMma,      // 0 auto / 1 tcgen05 / 2 mma.sync                                       NFN_B200_DENSE_MMA
+  kOptPdl,           // programmatic dependent launch (default 1)                             NFN_B200_PDL=0
+  kOptDebug,         // NFN_B200_DEBUG
+  kOptHostChunkMb,   // NFN_B200_HOST_CHUNK_MB
+  kOptCount
+};
+int option(Opt o);
 int math_mode();
 // Programmatic dependent launch for the specialised chain kernels (NFN_B200_PDL=0 turns it off).
 bool pdl_enabled();
@@ -38,8 +51,27 @@ typedef cudaError_t (*ChainLaunchFn)(const ChainArgs&, cudaStream_t);
 
 struct ChainKernels {
   // [math mode][bwd]
-  ChainLaunchFn fn[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  ChainLaunchFn fn[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // cp.async CTA-tile kernels
+  ChainLaunchFn fnw[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // bulk-copy / TMA warp-tile kernels
+  int P = 0;
 };
+
+// Which of the two kernel generations serves a launch: NFN_B200_CHAIN_IO=tma|cpasync forces one (A/B runs,
+// tests); otherwise the measured default for the row width / direction (chain_prefers_warp_tile).
+int chain_io_override();   // -1: none, 0: cp.async, 1: bulk copy / TMA
+__host__ __device__ constexpr bool chain_prefers_warp_tile(int P, bool bwd) {
+#ifdef NFN_WARP_TILE_DEFAULT
+  return P > 0 && (NFN_WARP_TILE_DEFAULT != 0);
+#else
+  (void)bwd;
+  return false;
+#endif
+}
+
+// 2-D tensor map over a row-major fp32 matrix [rows, P] with boxes of [32 rows x W columns] and the
+// 32B/64B/128B swizzle that matches W (WarpTile<P>); cuTensorMapEncodeTiled through the runtime's
+// driver entry point (the library does not link libcuda).
+int encode_row_tensor_map(TensorMap* out, const float* base, long long rows, int P, int W);
 
 std::string chain_key(int d, bool base, int k, const uint8_t* types);
 void register_chain(const std::string& key, const ChainKernels& k);
@@ -119,6 +151,59 @@ cudaError_t launch_chain(const ChainArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+template <class Spec, bool BWD, class M>
+cudaError_t launch_chain_w(const ChainArgs& a, cudaStream_t st) {
+  constexpr int P = Spec::P();
+  if constexpr (P <= 0) {
+    return launch_chain<Spec, BWD, M>(a, st);
+  } else {
+    constexpr ChainGeometry kGeo = warp_tile_geometry(P, BWD);
+    constexpr int NW = kGeo.T / 32;
+    constexpr int NB = kGeo.NB;
+    constexpr int MINB = kGeo.MINB;
+    constexpr size_t kSmem = kGeo.smem_bytes;
+    using L = WarpTile<P>;
+    auto kern = chain_kernel_w<Spec, BWD, M, NW, NB, MINB>;
+    struct Cfg {
+      int device = -1;
+      int ctas_per_sm = 0;
+    };
+    static thread_local Cfg cfg;
+    const DeviceInfo& di = device_info();
+    if (cfg.device != di.device) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+      if (e != cudaSuccess) return e;
+      int occ = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, kSmem);
+      if (e != cudaSuccess) return e;
+      cfg.ctas_per_sm = occ > 0 ? occ : 1;
+      cfg.device = di.device;
+    }
+    TensorMap tm_t{}, tm_dt{};
+    if constexpr (L::kSwz) {
+      if (encode_row_tensor_map(&tm_t, a.t, a.B, P, L::W) != NFN_OK) return cudaErrorInvalidValue;
+      if (BWD && encode_row_tensor_map(&tm_dt, a.dt, a.B, P, L::W) != NFN_OK) return cudaErrorInvalidValue;
+    }
+    const long long ntiles = (a.B + NW * 32 - 1) / (NW * 32);
+    long long grid = (long long)di.sm_count * cfg.ctas_per_sm;
+    if (grid > ntiles) grid = ntiles;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)grid);
+    lc.blockDim = dim3((unsigned)(NW * 32));
+    lc.dynamicSmemBytes = kSmem;
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&lc, kern, a, tm_t, tm_dt);
+    if (e != cudaSuccess) return e;
+    count_launch();
+    return cudaGetLastError();
+  }
+}
+
 template <class Spec>
 struct ChainRegistrar {
   explicit ChainRegistrar() {
@@ -127,6 +212,13 @@ struct ChainRegistrar {
     k.fn[0][1] = &launch_chain<Spec, true, MathFast>;
     k.fn[1][0] = &launch_chain<Spec, false, MathAccurate>;
     k.fn[1][1] = &launch_chain<Spec, true, MathAccurate>;
+    k.P = Spec::P();
+    if constexpr (Spec::P() > 0) {
+      k.fnw[0][0] = &launch_chain_w<Spec, false, MathFast>;
+      k.fnw[0][1] = &launch_chain_w<Spec, true, MathFast>;
+      k.fnw[1][0] = &launch_chain_w<Spec, false, MathAccurate>;
+      k.fnw[1][1] = &launch_chain_w<Spec, true, MathAccurate>;
+    }
     uint8_t types[Spec::KA];
     for (int i = 0; i < Spec::K; ++i) types[i] = (uint8_t)Spec::type(i);
     register_chain(chain_key(Spec::D, Spec::BASE, Spec::K, types), k);
@@ -202,7 +294,7 @@ cudaError_t launch_dense_tc5(const DenseArgs& a, cudaStream_t st) {
 #else
     int occ = tc5::resident_ctas(Spec::P(), H, BWD);
 #endif
-    if (getenv("NFN_B200_DEBUG"))
+    if (option(kOptDebug))
       fprintf(stderr, "[nfn_b200] dense_tc5 P=%d H=%d bwd=%d: %d CTAs/SM, TMEM cap %d, smem %u B, %d SMs\n", Spec::P(), H,
               (int)BWD, occ, kByTmem, kSmem, di.sm_count);
     cfg.ctas_per_sm = occ > 0 ? occ : 1;

@@ -155,6 +155,25 @@ std::string program_source(const nfn_chain_desc* d, int mode, const ChainGeometr
   return s;
 }
 
+// the warp-tile (bulk copy / TMA) generation of the same kernels
+std::string program_source_w(const nfn_chain_desc* d, int mode, const ChainGeometry (&geo)[2]) {
+  std::string spec = "nfn::ChainSpec<" + std::to_string(d->n_dims) + ", " + (d->trainable_base ? "true" : "false");
+  for (int k = 0; k < d->n_flows; ++k) spec += ", " + std::to_string((int)d->flow_type[k]);
+  spec += ">";
+  const char* math = mode == 0 ? "nfn::MathFast" : "nfn::MathAccurate";
+  std::string s = "#include \"nfn_chain_kernel.cuh\"\n";
+  s += "using Spec = " + spec + ";\n";
+  const char* names[2] = {"nfn_jit_chain_w_fwd", "nfn_jit_chain_w_fwd_bwd"};
+  for (int b = 0; b < 2; ++b) {
+    s += "extern \"C\" __global__ void __launch_bounds__(" + std::to_string(geo[b].T) + ", " +
+         std::to_string(geo[b].MINB) + ") " + names[b] +
+         "(const nfn::ChainArgs a, const __grid_constant__ nfn::TensorMap tm_t, const __grid_constant__ nfn::TensorMap "
+         "tm_dt) {\n  nfn::chain_body_w<Spec, " + (b ? "true" : "false") + ", " + math + ", " +
+         std::to_string(geo[b].T / 32) + ", " + std::to_string(geo[b].NB) + ">(a, &tm_t, &tm_dt);\n}\n";
+  }
+  return s;
+}
+
 bool compile_cubin(const std::string& src, std::vector<char>& cubin, std::string& log) {
   Nvrtc& n = nvrtc();
   if (!n.ok) {
@@ -210,7 +229,7 @@ static JitEntry* get_or_build(const std::string& ckey, const std::string& src, c
     e.geo[0] = geo[0];
     e.geo[1] = geo[1];
     const std::string all = src + nfn_jit_src_math + nfn_jit_src_flows + nfn_jit_src_chain + nfn_jit_src_dense +
-                            nfn_jit_src_dense_tc5 + "|sm_100a|v3";
+                            nfn_jit_src_dense_tc5 + "|sm_100a|v4";
     char name[64];
     snprintf(name, sizeof(name), "/chain_%016llx.cubin", fnv1a(all));
     const std::string path = cache_dir() + name;
@@ -249,10 +268,7 @@ static JitEntry* get_or_build(const std::string& ckey, const std::string& src, c
   return it->second.failed ? nullptr : &it->second;
 }
 
-static bool jit_enabled() {
-  const char* env = getenv("NFN_B200_JIT");
-  return !(env && !strcmp(env, "0"));
-}
+static bool jit_enabled() { return option(kOptJit) != 0; }
 
 static int desc_param_size(const nfn_chain_desc* desc) {
   int P = desc->trainable_base ? 2 * desc->n_dims : 0;
@@ -289,6 +305,34 @@ cudaError_t launch_chain_jit(const nfn_chain_desc* desc, const std::string& key,
   if (!jit_enabled()) return cudaSuccess;
   const int P = desc_param_size(desc);
   if (!jit_eligible(desc, P)) return cudaSuccess;
+  const int io = chain_io_override();
+  if (P > 0 && (io >= 0 ? io == 1 : chain_prefers_warp_tile(P, bwd))) {
+    const ChainGeometry geo[2] = {warp_tile_geometry(P, false), warp_tile_geometry(P, true)};
+    const char* const names[2] = {"nfn_jit_chain_w_fwd", "nfn_jit_chain_w_fwd_bwd"};
+    const std::string ckey = key + "|w|m" + std::to_string(mode) + "|dev" + std::to_string(device_info().device);
+    JitEntry* ent = get_or_build(ckey, program_source_w(desc, mode, geo), names, geo);
+    if (ent) {
+      TensorMap tm_t{}, tm_dt{};
+      const int W = warp_tile_box(P);
+      if (W > 0) {
+        if (encode_row_tensor_map(&tm_t, a.t, a.B, P, W) != NFN_OK) return cudaErrorInvalidValue;
+        if (bwd && encode_row_tensor_map(&tm_dt, a.dt, a.B, P, W) != NFN_OK) return cudaErrorInvalidValue;
+      }
+      const int b = bwd ? 1 : 0, T = ent->geo[b].T;
+      const long long ntiles = (a.B + T - 1) / T;
+      long long grid = (long long)device_info().sm_count * ent->ctas_per_sm[b];
+      if (grid > ntiles) grid = ntiles;
+      ChainArgs args = a;
+      void* params[] = {&args, &tm_t, &tm_dt};
+      cudaError_t ce = cudaLaunchKernel((const void*)ent->kern[b], dim3((unsigned)grid), dim3((unsigned)T), params,
+                                        ent->geo[b].smem_bytes, st);
+      if (ce == cudaSuccess) {
+        count_launch();
+        *served = true;
+      }
+      return ce;
+    }
+  }
   const ChainGeometry geo[2] = {chain_geometry(P, false), chain_geometry(P, true)};
   const char* const names[2] = {"nfn_jit_chain_fwd", "nfn_jit_chain_fwd_bwd"};
   const std::string ckey = key + "|m" + std::to_string(mode) + "|dev" + std::to_string(device_info().device);
@@ -424,7 +468,14 @@ long long jit_compile_check(const nfn_chain_desc* desc, int mode, std::string& l
   ChainGeometry geo[2] = {chain_geometry(P, false), chain_geometry(P, true)};
   std::vector<char> cubin;
   if (!compile_cubin(program_source(desc, mode, geo), cubin, log)) return -1;
-  return (long long)cubin.size();
+  long long total = (long long)cubin.size();
+  if (P > 0) {  // the warp-tile generation must build from the same embedded headers
+    ChainGeometry geow[2] = {warp_tile_geometry(P, false), warp_tile_geometry(P, true)};
+    std::vector<char> cubin_w;
+    if (!compile_cubin(program_source_w(desc, mode, geow), cubin_w, log)) return -1;
+    total += (long long)cubin_w.size();
+  }
+  return total;
 }
 
 // number of chains compiled (or loaded from the disk cache) by this process

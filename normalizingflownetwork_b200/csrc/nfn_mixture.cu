@@ -13,6 +13,8 @@
 // width is a runtime value here (K is not a template parameter); D and the row vector
 // width V are.  Forward is an online logsumexp (one EX2 per component); the reverse sweep
 // reuses sigma (written over sigma_raw by the forward pass) so softplus is not recomputed.
+#include <unordered_map>
+
 #include "nfn_common.h"
 
 namespace nfn {
@@ -496,12 +498,30 @@ static int launch_tiled(Kern kern, const MixArgs& a, const RtTile& g, size_t sme
   if (smem > (size_t)di.smem_optin)
     return set_error(NFN_ERR_UNSUPPORTED, "%s: row of %d floats needs %zu bytes of shared memory (> %d)", name,
                      g.P, smem, di.smem_optin);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return cuda_error(e, name);
-  int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kMixT, smem);
-  if (e != cudaSuccess) return cuda_error(e, name);
-  if (occ < 1) occ = 1;
+  // once per (kernel, device): opt in to the device's full dynamic shared memory, so that no later launch with a
+  // different component count has to touch the attribute again (a per-launch cudaFuncSetAttribute races between
+  // host threads using different K); the occupancy answer is memoised per (kernel, device, bytes)
+  struct Memo {
+    int device = -1;
+    std::unordered_map<size_t, int> occ;
+  };
+  static thread_local std::unordered_map<const void*, Memo> memo;
+  Memo& m = memo[(const void*)kern];
+  cudaError_t e;
+  if (m.device != di.device) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin);
+    if (e != cudaSuccess) return cuda_error(e, name);
+    m.device = di.device;
+    m.occ.clear();
+  }
+  auto it = m.occ.find(smem);
+  if (it == m.occ.end()) {
+    int o = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kMixT, smem);
+    if (e != cudaSuccess) return cuda_error(e, name);
+    it = m.occ.emplace(smem, o < 1 ? 1 : o).first;
+  }
+  const int occ = it->second;
   const long long ntiles = (a.B + kMixT - 1) / kMixT;
   long long grid = (long long)di.sm_count * occ;
   if (grid > ntiles) grid = ntiles;

@@ -80,6 +80,19 @@ class BaseEstimator(torch.nn.Module):
         self.stop_training = False
         self.to(self.device)
 
+    # ------------------------------------------------------------------ checkpoints
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        # the normalisation statistics are registered as [1] placeholders and take the data's shape in fit():
+        # give them the checkpoint's shape before the stock (shape-checking) copy
+        for name in ("x_mean", "x_std", "y_mean", "y_std"):
+            src = state_dict.get(prefix + name)
+            cur = getattr(self, name)
+            if src is not None and tuple(src.shape) != tuple(cur.shape):
+                setattr(self, name, torch.zeros(tuple(src.shape), dtype=cur.dtype, device=cur.device))
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                                      error_msgs)
+
     # ------------------------------------------------------------------ forward
     def _to_dev(self, a):
         if torch.is_tensor(a):

@@ -22,8 +22,10 @@ class DenseVariational(torch.nn.Module):
     """y = act(x @ kernel + bias) with (kernel, bias) ~ q = mean-field normal; adds
     kl_weight * KL(q || prior) to the loss (exact, or one-sample estimate)."""
 
-    def __init__(self, units, kl_weight, kl_use_exact, activation, map_mode, trainable_prior, prior_scale):
+    def __init__(self, units, kl_weight, kl_use_exact, activation, map_mode, trainable_prior, prior_scale,
+                 device=None):
         super().__init__()
+        self._device = device
         self.units = units
         self.kl_weight = kl_weight
         self.kl_use_exact = kl_use_exact
@@ -45,6 +47,16 @@ class DenseVariational(torch.nn.Module):
         self.prior_loc = torch.nn.Parameter(torch.zeros(size, device=device), requires_grad=self.trainable_prior)
         self._post = MeanFieldLayer(size, scale=None, map_mode=self.map_mode)
         self._prior = MeanFieldLayer(size, scale=self.prior_scale)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        # a fresh layer has no parameters yet (its input width is unknown until the first call): take the
+        # width from the checkpoint so that its tensors are loaded instead of reported as unexpected
+        loc = state_dict.get(prefix + "prior_loc")
+        if self.in_features is None and loc is not None:
+            self._materialise((loc.numel() - self.units) // self.units, self._device or loc.device)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                                      error_msgs)
 
     def _dists(self):
         return self._post(self.posterior_params), self._prior(self.prior_loc)
@@ -87,7 +99,10 @@ class BayesianNNEstimator(BaseEstimator):
         torch.manual_seed(random_seed)
         torch.nn.Module.__init__(self)
         self.map_mode = map_mode
-        self._bayes_cfg = dict(trainable_prior=trainable_prior, prior_scale=prior_scale, map_mode=map_mode)
+        from .BaseEstimator import default_device
+
+        self._bayes_cfg = dict(trainable_prior=trainable_prior, prior_scale=prior_scale, map_mode=map_mode,
+                               device=torch.device(device) if device is not None else default_device())
         layers = self._get_dense_layers(hidden_sizes=hidden_sizes, output_size=dist_layer.get_total_param_size(),
                                         posterior=None, prior=None, kl_weight_scale=kl_weight_scale,
                                         kl_use_exact=kl_use_exact, activation=activation)
@@ -114,7 +129,7 @@ class BayesianNNEstimator(BaseEstimator):
         assert kl_weight_scale <= 1.0
         cfg = getattr(self, "_bayes_cfg", dict(trainable_prior=False, prior_scale=1.0, map_mode=False))
         mk = lambda units, act: DenseVariational(units, kl_weight_scale, kl_use_exact, act, cfg["map_mode"],
-                                                 cfg["trainable_prior"], cfg["prior_scale"])
+                                                 cfg["trainable_prior"], cfg["prior_scale"], cfg.get("device"))
         normalization = [_Normalise(self)]
         noise_reg = [_GaussianNoise(self, "x_noise_std")]
         hidden = [mk(size, activation) for size in hidden_sizes]

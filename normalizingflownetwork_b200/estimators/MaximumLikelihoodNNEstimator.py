@@ -17,12 +17,13 @@ class _Dense(torch.nn.Module):
         self.linear = torch.nn.LazyLinear(units)
         self.act = ACTIVATIONS[activation]()
         self._activation = activation
-        self._init = False
         self._seed = seed
         self.fused = True   # one kernel each way for the layer (csrc/nfn_mlp.cu) when its shape allows
 
     def forward(self, x):
-        if not self._init:
+        # Glorot-initialise only a weight that does not exist yet: after load_state_dict() the lazy layer has
+        # been materialised WITH the checkpoint's values, which must survive the first call
+        if isinstance(self.linear.weight, torch.nn.parameter.UninitializedParameter):
             self.linear(x)  # materialises the lazy weight
             with torch.no_grad():
                 # own generator: the initial weights depend on (random_seed, layer), not on
@@ -32,7 +33,6 @@ class _Dense(torch.nn.Module):
                 torch.nn.init.xavier_uniform_(w, generator=gen)
                 self.linear.weight.copy_(w)
                 self.linear.bias.zero_()
-            self._init = True
         lin = self.linear
         if (self.fused and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
                 and F.dense_act_supported(lin.in_features, lin.out_features, self._activation)):

@@ -5,13 +5,20 @@ Adam on the mean NLL; mean-field weight posteriors with the KL term, S weight dr
 ``models`` holds the six concrete estimators, one per (regime, head) pair: flow chain, Gaussian mixture,
 kernel mixture.  ``ESTIMATORS`` uses the registry names of the reference's ``estimators/__init__.py:8-15``.
 """
-from . import models as _models
+from .models import (
+    BayesKernelMixtureNetwork,
+    BayesMixtureDensityNetwork,
+    BayesNormalizingFlowNetwork,
+    KernelMixtureNetwork,
+    MixtureDensityNetwork,
+    NormalizingFlowNetwork,
+)
 
-_HEADS = {"NFN": "NormalizingFlowNetwork", "MDN": "MixtureDensityNetwork", "KMN": "KernelMixtureNetwork"}
-ESTIMATORS = {}
-for _key, _cls in _HEADS.items():
-    ESTIMATORS[_key] = getattr(_models, _cls)
-    ESTIMATORS["bayesian_" + _key] = getattr(_models, "Bayes" + _cls)
-    globals()[_cls] = ESTIMATORS[_key]
-    globals()["Bayes" + _cls] = ESTIMATORS["bayesian_" + _key]
-del _key, _cls
+ESTIMATORS = {
+    "NFN": NormalizingFlowNetwork,
+    "MDN": MixtureDensityNetwork,
+    "KMN": KernelMixtureNetwork,
+    "bayesian_NFN": BayesNormalizingFlowNetwork,
+    "bayesian_MDN": BayesMixtureDensityNetwork,
+    "bayesian_KMN": BayesKernelMixtureNetwork,
+}

@@ -52,6 +52,21 @@ def _prep_ty(t, y, n_dims, width, what):
     return _aligned(t), _aligned(y), B
 
 
+def _check_y(y, n_dims, B, what):
+    """The C ABI cannot see tensor extents: a wrong-shaped y would be an out-of-bounds device read."""
+    if y.dim() != 2 or y.shape[1] != n_dims or y.shape[0] not in (B, 1):
+        raise ValueError("%s: y must be [%d, %d] or [1, %d], got %s" % (what, B, n_dims, n_dims, tuple(y.shape)))
+
+
+def _prep_g(g_logp, B, dev, what):
+    if g_logp is None:
+        return None
+    g_logp = _as_f32_cuda(g_logp, "g_logp", device=dev).reshape(-1)
+    if g_logp.numel() != B:
+        raise ValueError("%s: g_logp must have B=%d elements, got %d" % (what, B, g_logp.numel()))
+    return g_logp
+
+
 # ----------------------------------------------------------------------------- flow chain
 def chain_param_size(flow_types, n_dims, trainable_base_dist):
     lib = _lib.load()
@@ -141,8 +156,7 @@ def chain_forward_backward_peer(t, y, flow_types, n_dims, trainable_base_dist, c
     dt = out_dt if out_dt is not None else torch.empty((B, P), dtype=torch.float32, device=dev)
     if reduced is None:
         reduced = torch.empty(P + 1, dtype=torch.float64, device=dev)
-    if g_logp is not None:
-        g_logp = _as_f32_cuda(g_logp, "g_logp", device=dev).reshape(-1)
+    g_logp = _prep_g(g_logp, B, dev, "chain_forward_backward_peer")
     with torch.cuda.device(dev):
         _lib.check(lib.nfn_chain_forward_backward_peer(
             ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), y.shape[0], _lib.ptr(g_logp), ctypes.c_float(g_scale),
@@ -239,6 +253,7 @@ def dense_chain_forward(h, W, bias, y, flow_types, n_dims, trainable_base_dist):
     y = _aligned(_as_f32_cuda(y, "y", device=dev))
     B, H = h.shape
     assert tuple(W.shape) == (H, P) and tuple(bias.shape) == (P,), "W must be [H, P] and bias [P]"
+    _check_y(y, n_dims, B, "dense_chain_forward")
     logp = torch.empty(B, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.nfn_dense_chain_forward(ctypes.byref(desc), H, _lib.ptr(h), _lib.ptr(W), _lib.ptr(bias),
@@ -260,14 +275,14 @@ def dense_chain_forward_backward(h, W, bias, y, flow_types, n_dims, trainable_ba
     y = _aligned(_as_f32_cuda(y, "y", device=dev))
     B, H = h.shape
     assert tuple(W.shape) == (H, P) and tuple(bias.shape) == (P,), "W must be [H, P] and bias [P]"
+    _check_y(y, n_dims, B, "dense_chain_forward_backward")
     logp = torch.empty(B, dtype=torch.float32, device=dev)
     dh = torch.empty((B, H), dtype=torch.float32, device=dev)
     if dW is None:
         dW = torch.zeros((H, P), dtype=torch.float32, device=dev)
     if dbias is None:
         dbias = torch.zeros(P, dtype=torch.float32, device=dev)
-    if g_logp is not None:
-        g_logp = _as_f32_cuda(g_logp, "g_logp", device=dev).reshape(-1)
+    g_logp = _prep_g(g_logp, B, dev, "dense_chain_forward_backward")
     with torch.cuda.device(dev):
         _lib.check(lib.nfn_dense_chain_forward_backward(
             ctypes.byref(desc), H, _lib.ptr(h), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(y), y.shape[0],
@@ -481,3 +496,21 @@ def launch_count_reset():
 
 def set_math_mode(accurate):
     _lib.check(_lib.load().nfn_set_math_mode(1 if accurate else 0))
+
+
+_OPTION_VALUES = {
+    "chain_io": {"auto": -1, "cpasync": 0, "tma": 1},
+    "dense_mma": {"auto": 0, "tc5": 1, "sync": 2},
+}
+
+
+def set_option(name, value):
+    """Process-wide run-time switch of libnfn_b200 (include/nfn_b200.h: nfn_set_option).  ``value`` is an int,
+    a bool, or for "chain_io" / "dense_mma" one of the symbolic names ("auto", "cpasync", "tma" / "tc5", "sync")."""
+    if isinstance(value, str):
+        value = _OPTION_VALUES[name][value]
+    _lib.check(_lib.load().nfn_set_option(name.encode(), int(value)))
+
+
+def get_option(name):
+    return int(_lib.check(_lib.load().nfn_get_option(name.encode())))

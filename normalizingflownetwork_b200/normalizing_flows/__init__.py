@@ -10,5 +10,4 @@ from .AffineFlow import AffineFlow
 from .PlanarFlow import PlanarFlow
 from .RadialFlow import RadialFlow
 
-FLOWS = {cls.flow_type: cls for cls in (PlanarFlow, RadialFlow, AffineFlow)}
-assert sorted(FLOWS) == ["affine", "planar", "radial"]
+FLOWS = {"planar": PlanarFlow, "radial": RadialFlow, "affine": AffineFlow}

@@ -37,10 +37,11 @@ def _oracle(h, W, b, y, ft, d, tb, up):
 def dense_impl(request):
     """auto: the library's own choice (tcgen05 / TMEM kernel for P >= 32, warp-level mma.sync below);
     sync / tc5: one implementation forced for every chain that has both (ahead-of-time instances)."""
-    if request.param != "auto":
-        os.environ["NFN_B200_DENSE_MMA"] = request.param
+    from normalizingflownetwork_b200 import functional as F
+
+    F.set_option("dense_mma", request.param)
     yield request.param
-    os.environ.pop("NFN_B200_DENSE_MMA", None)
+    F.set_option("dense_mma", "auto")
 
 
 def rel(got, ref):

@@ -389,3 +389,31 @@ def test_y_noise_reg_like_the_reference(cuda_device):
         assert np.all(out1 == out2) and np.all(np.isfinite(out1))
     finally:
         noise._set_noise(0.0)
+
+
+@pytest.mark.parametrize("name,kwargs", [("NFN", dict(n_flows=3)), ("MDN", dict(n_centers=4)), ("KMN", dict(n_centers=5)),
+                                         ("bayesian_NFN", dict(kl_weight_scale=1e-3, n_flows=2, map_mode=True)),
+                                         ("bayesian_MDN", dict(kl_weight_scale=1e-3, n_centers=3, map_mode=True))])
+def test_checkpoint_round_trip(cuda_device, name, kwargs):
+    """save -> fresh estimator -> strict load -> identical log_pdf (the first forward after the load must not
+    re-initialise the lazily created weights; the [dim]-shaped normalisation statistics and the variational
+    layers' parameters must be restored)."""
+    from normalizingflownetwork_b200.estimators import ESTIMATORS
+
+    d = 2
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(300, d)).astype(np.float32)
+    y = (np.sin(x) + 0.1 * rng.normal(size=(300, d))).astype(np.float32) * np.array([1.0, 3.0], np.float32)
+    model = ESTIMATORS[name](d, **kwargs)
+    model.fit(x, y, batch_size=100, epochs=2, verbose=0)
+    want = model.log_pdf(x, y).clone()
+    state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    fresh = ESTIMATORS[name](d, **kwargs)
+    if name == "KMN":  # the kernel centres are data, not state: chosen by fit / set_center_points
+        fresh.dist_layer.set_center_points(((y - y.mean(0)) / y.std(0)).astype(np.float32))
+    res = fresh.load_state_dict(state, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert tuple(fresh.y_std.shape) == (d,)
+    got = fresh.log_pdf(x, y)
+    assert torch.equal(got, want), float((got - want).abs().max())
+    assert torch.equal(fresh.log_pdf(x, y), want)   # and the second call too

@@ -54,17 +54,20 @@ def math_mode(request, nfn_lib):
     F.set_math_mode(False)
 
 
-@pytest.fixture(params=["specialized", "jit", "generic"])
-def kernel_path(request):
+@pytest.fixture(params=["specialized", "specialized-tma", "jit", "jit-tma", "generic"])
+def kernel_path(request, nfn_lib):
     """specialized: ahead-of-time instance where one exists (else runtime-specialised);
-    jit: every chain through the NVRTC runtime specialiser; generic: runtime-chain kernel."""
-    if request.param == "generic":
-        os.environ["NFN_B200_FORCE_GENERIC"] = "1"
-    elif request.param == "jit":
-        os.environ["NFN_B200_FORCE_JIT"] = "1"
+    jit: every chain through the NVRTC runtime specialiser; generic: runtime-chain kernel.
+    Both specialised paths exist in two generations: cp.async CTA tiles and bulk-copy / TMA warp tiles."""
+    from normalizingflownetwork_b200 import functional as F
+
+    F.set_option("force_generic", request.param == "generic")
+    F.set_option("force_jit", request.param.startswith("jit"))
+    F.set_option("chain_io", "tma" if request.param.endswith("-tma") else "cpasync")
     yield request.param
-    os.environ.pop("NFN_B200_FORCE_GENERIC", None)
-    os.environ.pop("NFN_B200_FORCE_JIT", None)
+    F.set_option("force_generic", 0)
+    F.set_option("force_jit", 0)
+    F.set_option("chain_io", "auto")
 
 
 def dev(x, device):
@@ -303,11 +306,11 @@ def test_runtime_specialiser_serves_unlisted_chains(cuda_device, nfn_lib):
     F.chain_forward(dev(t, cuda_device), dev(y, cuda_device), ft, d, tb)
     assert nfn_lib.nfn_jit_cache_size() == before + 1  # second call hits the cache
     # NFN_B200_JIT=0 sends the same chain to the generic kernel; results agree within tolerance
-    os.environ["NFN_B200_JIT"] = "0"
+    F.set_option("jit", 0)
     try:
         lp_g, dt_g, _ = F.chain_forward_backward(dev(t, cuda_device), dev(y, cuda_device), ft, d, tb, g_scale=-1.0)
     finally:
-        os.environ.pop("NFN_B200_JIT")
+        F.set_option("jit", 1)
     assert_logp(lp_g.cpu().numpy(), ref_lp)
     assert torch.allclose(lp, lp_g, rtol=1e-5, atol=1e-5)
     assert torch.allclose(dt, dt_g, rtol=1e-3, atol=1e-4)
@@ -578,6 +581,7 @@ def test_outputs_stay_inside_their_buffers(cuda_device, nfn_lib, kernel_path):
     import ctypes
 
     from normalizingflownetwork_b200 import _lib
+    from normalizingflownetwork_b200 import functional as F
 
     SENT = 12345.0
     PAD = 1024  # floats on each side
@@ -616,7 +620,7 @@ def test_outputs_stay_inside_their_buffers(cuda_device, nfn_lib, kernel_path):
         desc = _lib.make_desc(ft, d, tb)
         H, P = 16, 48
         for impl, B in [(i, b) for i in ("sync", "tc5") for b in (1, 33, 129, 1000, 128 * 300 + 5)]:
-            os.environ["NFN_B200_DENSE_MMA"] = impl   # both GEMM implementations (warp-level mma.sync; tcgen05 / TMEM)
+            F.set_option("dense_mma", impl)   # both GEMM implementations (warp-level mma.sync; tcgen05 / TMEM)
             h = torch.tanh(torch.randn((B, H), generator=g, device=cuda_device))
             W = torch.randn((H, P), generator=g, device=cuda_device) * 0.1
             bias = torch.zeros(P, device=cuda_device)
@@ -634,7 +638,7 @@ def test_outputs_stay_inside_their_buffers(cuda_device, nfn_lib, kernel_path):
             torch.cuda.synchronize()
             assert intact(b_lp, B) and intact(b_dh, B * H) and intact(b_dw, H * P) and intact(b_db, P), (impl, B)
             assert torch.isfinite(lp).all() and torch.isfinite(dh).all() and torch.isfinite(dW).all(), (impl, B)
-        os.environ.pop("NFN_B200_DENSE_MMA", None)
+        F.set_option("dense_mma", "auto")
         K, dm = 20, 2
         Pm = 2 * K * dm + K
         for B in (1, 129, 1000):

@@ -46,13 +46,13 @@ def _check_rank(rank, world, device, steps=6):
     expect = world * torch.arange(P + 1, dtype=torch.float64, device=device) + sum(range(world))
     assert torch.equal(out, expect)
     # a chain served by the generic kernel gets the same exchange from a second tiny launch
-    os.environ["NFN_B200_FORCE_GENERIC"] = "1"
+    F.set_option("force_generic", 1)
     try:
         t = torch.randn((3000, P), generator=g, device=device) * 0.5
         y = torch.randn((3000, d), generator=g, device=device)
         lp, dt, red = F.chain_forward_backward_peer(t, y, ft, d, tb, comm, want_colsum=True)
     finally:
-        os.environ.pop("NFN_B200_FORCE_GENERIC")
+        F.set_option("force_generic", 0)
     local = torch.cat([dt.double().sum(0), lp.double().sum().reshape(1)])
     if world > 1:
         torch.distributed.all_reduce(local)

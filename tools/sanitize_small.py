@@ -14,9 +14,14 @@ for ft, d, tb in [(["planar", "radial", "affine"] * 3 + ["planar"], 2, True), ([
         F.chain_forward(t, y, ft, d, tb)
         col = torch.zeros(P, dtype=torch.float64, device=dev); ls = torch.zeros(1, dtype=torch.float64, device=dev)
         F.chain_forward_backward(t, y, ft, d, tb, g_scale=-1.0 / B, want_dy=True, logp_sum=ls, dt_colsum=col)
-    os.environ["NFN_B200_FORCE_GENERIC"] = "1"
+    F.set_option("force_generic", 1)
     F.chain_forward_backward(rnd(300, P), rnd(300, d, sc=1.0), ft, d, tb)
-    os.environ.pop("NFN_B200_FORCE_GENERIC")
+    F.set_option("force_generic", 0)
+    for io in ("cpasync", "tma"):   # both kernel generations
+        F.set_option("chain_io", io)
+        F.chain_forward(rnd(700, P), rnd(700, d, sc=1.0), ft, d, tb)
+        F.chain_forward_backward(rnd(700, P), rnd(700, d, sc=1.0), ft, d, tb, want_dy=True)
+    F.set_option("chain_io", "auto")
 for K, d in [(20, 2), (3, 1), (5, 5)]:
     P = 2 * K * d + K
     F.mdn_forward_backward(rnd(333, P), rnd(333, d, sc=1.0), K, d, want_dy=True)
