@@ -45,7 +45,8 @@ typedef enum nfn_status {
   NFN_ERR_SHAPE = -3,       /* bad B / y_rows / width */
   NFN_ERR_ALIGN = -4,       /* t or dt not 16-byte aligned */
   NFN_ERR_CUDA = -5,        /* CUDA runtime error, see nfn_last_error() */
-  NFN_ERR_UNSUPPORTED = -6  /* valid request this build cannot serve */
+  NFN_ERR_UNSUPPORTED = -6, /* valid request this build cannot serve */
+  NFN_ERR_PEER_TIMEOUT = -7 /* a rank did not arrive at a peer exchange in time (nfn_peer_status) */
 } nfn_status;
 
 /* Flow type codes: the keys of FLOWS in estimators/normalizing_flows/__init__.py:5 */
@@ -133,9 +134,17 @@ int nfn_chain_forward_backward(const nfn_chain_desc* desc, const float* t, const
  * memory (push into each peer's IPC-mapped region, flag, wait, sum in rank order --
  * deterministic), so the step needs no separate collective launch.  `reduced` (device
  * double[P + 1]) holds the sums over all ranks when the kernel completes.  Every rank of the
- * communicator must make the same sequence of calls; a rank that never arrives is abandoned
- * after ~1 s (NaN in `reduced`) instead of hanging the GPU.  want_colsum = 0 skips the
- * in-kernel column sums (their slots stay 0 unless the caller accumulated into them).
+ * communicator must make the same sequence of calls.  A rank that does not arrive within the
+ * time-out (30 s; NFN_B200_PEER_TIMEOUT_S at communicator creation) is abandoned instead of hanging
+ * the GPU: `reduced` gets NaN AND a sticky device flag is raised that nfn_peer_status() reports as
+ * NFN_ERR_PEER_TIMEOUT -- never a silent NaN.  A call that fails does not advance the exchange
+ * sequence.  want_colsum = 0 skips the in-kernel column sums (their slots stay 0).
+ *
+ * Split-phase mode (nfn_peer_set_deferred(comm, 1)): a launch only PUSHES its totals; one CTA at the
+ * head of the NEXT launch on the communicator (or nfn_peer_flush) collects them into the `reduced`
+ * pointer the earlier call was given.  `reduced` of call k is therefore complete when call k+1 (or
+ * the flush) completes.  This takes rank skew and the NVLink round trip off every kernel's tail: a
+ * consumer that runs after the next launch's head (optimizer kernel, next step) sees no wait at all.
  *
  * Communicator set-up (see normalizingflownetwork_b200/parallel.py:PeerComm):
  *   nfn_peer_alloc        cudaMalloc + zero one region, export its 64-byte cudaIpc handle
@@ -153,6 +162,9 @@ int nfn_peer_free(void* region);
 int nfn_peer_comm_create(int world, int rank, int n_values, void* const* regions, nfn_peer_comm** comm);
 int nfn_peer_comm_destroy(nfn_peer_comm* comm);
 int nfn_peer_allreduce(nfn_peer_comm* comm, const double* values, double* reduced, void* stream);
+int nfn_peer_set_deferred(nfn_peer_comm* comm, int deferred);   /* 1: split-phase mode (no exchange may be pending) */
+int nfn_peer_flush(nfn_peer_comm* comm, void* stream);          /* split-phase: complete the pending exchange */
+int nfn_peer_status(nfn_peer_comm* comm);                       /* synchronises; NFN_OK or NFN_ERR_PEER_TIMEOUT */
 int nfn_chain_forward_backward_peer(const nfn_chain_desc* desc, const float* t, const float* y,
                                     int64_t y_rows, const float* g_logp, float g_scale, float* logp,
                                     float* dt, float* dy, int want_colsum, nfn_peer_comm* comm,

@@ -67,6 +67,9 @@ SIGNATURES = {
                                             ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]),
     "nfn_peer_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "nfn_peer_allreduce": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, _c_float_p, ctypes.c_void_p]),
+    "nfn_peer_set_deferred": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "nfn_peer_flush": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "nfn_peer_status": (ctypes.c_int, [ctypes.c_void_p]),
     "nfn_chain_forward_backward_peer": (ctypes.c_int, [ctypes.POINTER(ChainDesc), _c_float_p, _c_float_p, _i64,
                                                       _c_float_p, ctypes.c_float, _c_float_p, _c_float_p,
                                                       _c_float_p, ctypes.c_int, ctypes.c_void_p, _c_float_p,

@@ -82,6 +82,8 @@ static void init_options() {
     if (v >= 1 && v <= 1024) mb = v;
   }
   g_opt[kOptHostChunkMb] = (int)mb;
+  g_opt[kOptTuneWnb] = getenv("NFN_B200_TUNE_WNB") ? atoi(getenv("NFN_B200_TUNE_WNB")) : 0;
+  g_opt[kOptTuneWwarps] = getenv("NFN_B200_TUNE_WWARPS") ? atoi(getenv("NFN_B200_TUNE_WWARPS")) : 0;
 }
 
 int option(Opt o) {
@@ -90,7 +92,7 @@ int option(Opt o) {
 }
 
 static const char* const kOptNames[kOptCount] = {"math", "force_generic", "force_jit", "jit", "chain_io",
-                                                 "dense_mma", "pdl", "debug", "host_chunk_mb"};
+                                                 "dense_mma", "pdl", "debug", "host_chunk_mb", "tune_wnb", "tune_wwarps"};
 
 int math_mode() { return option(kOptMath); }
 int chain_io_override() { return option(kOptChainIo); }
@@ -387,13 +389,19 @@ int nfn_chain_forward_backward_peer(const nfn_chain_desc* desc, const float* t, 
   if (a.peer.n_values != P + 1)
     return set_error(NFN_ERR_SHAPE, "communicator carries %d values, the chain needs P + 1 = %d", a.peer.n_values,
                      P + 1);
-  if (B == 0)  // nothing local to add, but every rank must still take part in the exchange
-    return launch_peer_allreduce(a.peer, (cudaStream_t)stream);
-  a.t = t; a.y = y; a.g_logp = g_logp; a.logp = logp; a.dt = dt; a.dy = dy;
-  a.logp_sum = a.peer.acc + P;
-  a.dt_colsum = want_colsum ? a.peer.acc : nullptr;
-  a.B = B; a.g_scale = g_scale; a.y_broadcast = (y_rows == 1 && B != 1);
-  return chain_dispatch(desc, a, true, (cudaStream_t)stream);
+  if (B == 0) {  // nothing local to add, but every rank must still take part in the exchange
+    rc = launch_peer_allreduce(a.peer, (cudaStream_t)stream);
+  } else {
+    a.t = t; a.y = y; a.g_logp = g_logp; a.logp = logp; a.dt = dt; a.dy = dy;
+    a.logp_sum = a.peer.acc + P;
+    a.dt_colsum = want_colsum ? a.peer.acc : nullptr;
+    a.B = B; a.g_scale = g_scale; a.y_broadcast = (y_rows == 1 && B != 1);
+    rc = chain_dispatch(desc, a, true, (cudaStream_t)stream);
+  }
+  // the exchange's sequence number advances only once the launch is in the stream: an error return leaves this
+  // rank in step with its peers
+  if (rc == NFN_OK) peer_commit(comm, reduced);
+  return rc;
 }
 
 // ------------------------------------------------------------------ fused Dense(P) + chain

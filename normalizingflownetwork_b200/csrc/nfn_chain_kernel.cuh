@@ -90,11 +90,18 @@ constexpr int kMaxPeers = 8;
 struct PeerArgs {
   double* base[kMaxPeers];     // peer regions as mapped into this process (own region included)
   double* acc;                 // local accumulators [n_values], self-resetting
-  double* out;                 // reduced result [n_values], local
+  double* out;                 // reduced result [n_values] of THIS launch's exchange, local
   unsigned* ticket;            // CTA arrival counter, self-resetting
-  unsigned long long step;     // launch sequence number of this communicator
+  unsigned long long step;     // sequence number of this launch's exchange
   int world, rank, n_values;
-  int pad_;
+  // Split-phase mode (deferred != 0): this launch only PUSHES its totals; the sums of the previous exchange
+  // (`pending_step`, into `pending_out`) are collected by one CTA at the head of this launch, i.e. behind
+  // its own tile work, so rank skew and the NVLink round trip never sit on a kernel's tail.
+  int deferred;
+  double* pending_out;         // nullptr: nothing to collect
+  unsigned long long pending_step;
+  unsigned* status;            // sticky error word: != 0 once a peer failed to arrive within the time-out
+  long long timeout_cycles;
 };
 
 struct ChainArgs {
@@ -460,9 +467,66 @@ NFN_DEVI void st_volatile_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Called by every thread of every CTA after the CTA's accumulator atomics.  The last CTA to
-// arrive runs the exchange; a peer that never shows up is abandoned after ~1 s (NaN result)
-// so that a failed rank cannot hang this GPU.
+// Collect: sum, in rank order (deterministic), the words every peer pushed into THIS rank's region for exchange
+// `step` and write the totals to `out`.  Any number of threads (strided over the values), no barrier inside.
+// A peer that does not arrive within timeout_cycles is abandoned: NaN in `out` AND the sticky status word is
+// set, which the host reads back (nfn_peer_status) -- a time-out is an error, never a silent NaN.
+NFN_DEVI void peer_collect(const PeerArgs& p, unsigned long long step, double* out, int tid, int nthreads) {
+  const int W = p.world, NV = p.n_values, par = (int)(step & 1ull);
+  const unsigned long long tag = ((step + 1ull) & 0xffffffffull) << 32;  // never 0 in the first 2^32 steps
+  const long long t0 = clock64();
+  for (int j = tid; j < NV; j += nthreads) {
+    const unsigned long long* mine =
+        reinterpret_cast<const unsigned long long*>(p.base[p.rank]) + ((size_t)par * W * NV + j) * 2;
+    double sum = 0.0;
+    bool timeout = false;
+    for (int q = 0; q < W; ++q) {
+      const unsigned long long* src = mine + (size_t)q * NV * 2;
+      unsigned long long a0, a1;
+      while (true) {
+        a0 = ld_volatile_u64(src);
+        a1 = ld_volatile_u64(src + 1);
+        if ((a0 & 0xffffffff00000000ull) == tag && (a1 & 0xffffffff00000000ull) == tag) break;
+        if (clock64() - t0 > p.timeout_cycles) {
+          timeout = true;
+          break;
+        }
+      }
+      sum += __longlong_as_double((long long)((a0 & 0xffffffffull) | (a1 << 32)));
+    }
+    if (timeout) atomicOr(p.status, 1u);
+    out[j] = timeout ? __longlong_as_double(0x7ff8000000000000ll) : sum;
+  }
+}
+
+// Push: take (and reset) the local totals and write (value half | step tag) words into slot [parity][rank] of
+// EVERY peer's region (own region included).
+NFN_DEVI void peer_push(const PeerArgs& p, int tid, int nthreads) {
+  const int W = p.world, NV = p.n_values, par = (int)(p.step & 1ull);
+  const unsigned long long tag = ((p.step + 1ull) & 0xffffffffull) << 32;
+  for (int j = tid; j < NV; j += nthreads) {
+    const unsigned long long bits = atomicExch(reinterpret_cast<unsigned long long*>(p.acc + j), 0ull);
+    const unsigned long long w0 = (bits & 0xffffffffull) | tag, w1 = (bits >> 32) | tag;
+    const size_t off = ((size_t)(par * W + p.rank) * NV + j) * 2;
+    for (int q = 0; q < W; ++q) {
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.base[q]) + off;
+      st_volatile_u64(dst, w0);
+      st_volatile_u64(dst + 1, w1);
+    }
+  }
+}
+
+// Head of a launch in split-phase mode: the LAST CTA of the grid (it starts last and owns the fewest tiles)
+// collects the previous exchange.  Slot reuse stays safe: a rank pushes exchange s+2 into the slots of exchange s
+// only after its own collect of s+1 has seen every peer's s+1 words, and a peer pushes s+1 only after all its
+// CTAs -- its collector of s included -- have arrived at the ticket.
+NFN_DEVI void peer_head(const PeerArgs& p) {
+  if (p.world > 0 && p.deferred && p.pending_out && blockIdx.x == gridDim.x - 1)
+    peer_collect(p, p.pending_step, p.pending_out, (int)threadIdx.x, (int)blockDim.x);
+}
+
+// Tail of a launch: called by every thread of every CTA after the CTA's accumulator atomics.  The last CTA to
+// arrive pushes; unless the communicator is in split-phase mode it also collects this exchange right away.
 template <int T>
 NFN_DEVI void peer_allreduce(const PeerArgs& p) {
   __shared__ int s_last;
@@ -475,40 +539,8 @@ NFN_DEVI void peer_allreduce(const PeerArgs& p) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const int W = p.world, NV = p.n_values, par = (int)(p.step & 1ull);
-  const unsigned long long tag = ((p.step + 1ull) & 0xffffffffull) << 32;  // never 0 in the first 2^32 steps
-  for (int j = threadIdx.x; j < NV; j += T) {
-    // 1. take (and reset) the local total, push (value half | tag) words to every peer
-    const unsigned long long bits = atomicExch(reinterpret_cast<unsigned long long*>(p.acc + j), 0ull);
-    const unsigned long long w0 = (bits & 0xffffffffull) | tag, w1 = (bits >> 32) | tag;
-    const size_t off = ((size_t)(par * W + p.rank) * NV + j) * 2;
-    for (int q = 0; q < W; ++q) {
-      unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.base[q]) + off;
-      st_volatile_u64(dst, w0);
-      st_volatile_u64(dst + 1, w1);
-    }
-    // 2. poll this rank's region for every peer's words of this step; 3. sum in rank order
-    const unsigned long long* mine =
-        reinterpret_cast<const unsigned long long*>(p.base[p.rank]) + ((size_t)par * W * NV + j) * 2;
-    double sum = 0.0;
-    bool timeout = false;
-    const long long t0 = clock64();
-    for (int q = 0; q < W; ++q) {
-      const unsigned long long* src = mine + (size_t)q * NV * 2;
-      unsigned long long a0, a1;
-      while (true) {
-        a0 = ld_volatile_u64(src);
-        a1 = ld_volatile_u64(src + 1);
-        if ((a0 & 0xffffffff00000000ull) == tag && (a1 & 0xffffffff00000000ull) == tag) break;
-        if (clock64() - t0 > 2000000000ll) {  // ~1 s at 2 GHz
-          timeout = true;
-          break;
-        }
-      }
-      sum += __longlong_as_double((long long)((a0 & 0xffffffffull) | (a1 << 32)));
-    }
-    p.out[j] = timeout ? __longlong_as_double(0x7ff8000000000000ll) : sum;
-  }
+  peer_push(p, (int)threadIdx.x, T);
+  if (!p.deferred) peer_collect(p, p.step, p.out, (int)threadIdx.x, T);
   if (threadIdx.x == 0) *p.ticket = 0u;
 }
 
@@ -571,6 +603,8 @@ NFN_DEVI void chain_body(const ChainArgs& a) {
       if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + r0); }
     }
   }
+
+  peer_head(a.peer);  // split-phase exchange: collect the previous launch's sums behind the first loads
 
   int slot = 0;  // buffer holding the current tile
   for (; tile < ntiles; tile += gridDim.x) {
@@ -800,94 +834,120 @@ NFN_DEVI void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "me
 template <int N>
 NFN_DEVI void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
-// ---- column sums of dt, warp-private: lane -> (V-wide column group, slice of the 32 rows); the partial
-// sums stay in registers across all tiles of the warp and meet in shared memory once, at the very end.
+// ---- column sums of dt (bias gradient of the emitting layer), warp-private partial sums kept in REGISTERS
+// across all tiles of the warp and combined once, at the very end of the kernel.  Three strategies:
+//   kOwnRow  (linear layout, P <= 32): every lane adds its own gradient row (P accumulators per lane; the row
+//            was written a moment ago, so the values usually never leave the registers);
+//   kSwizzled (TMA layout): CW lanes share one box row (its CW 16-byte chunks), 32/CW rows per step -- a step
+//            reads whole 128-byte lines, conflict-free, at [lane register + immediate] addresses; a lane owns the
+//            same logical chunk of every box, i.e. 4 * NBX accumulators;
+//   kColumn  (linear layout, wide rows): lane l owns columns l, l + 32, ... and walks the 32 rows.
 template <int P>
 struct WarpColSum {
   using L = WarpTile<P>;
   static constexpr int V = L::V;
-  static constexpr int NG = P / V;                       // column groups
-  static constexpr int NGL = (NG + 31) / 32;             // groups per lane when NG > 32
-  __host__ __device__ static constexpr int row_splits() {
-    int rs = 1;
-    while (NG * rs * 2 <= 32) rs *= 2;
-    return rs;
-  }
-  static constexpr int RS = NG > 32 ? 1 : row_splits();  // slices of the 32 rows
-  static constexpr int RPS = 32 / RS;                    // rows per slice
-  float acc[NGL][V];
+  enum { kOwnRow = 0, kSwizzled = 1, kColumn = 2 };
+  static constexpr int kMode = L::kSwz ? kSwizzled : (P <= 32 ? kOwnRow : kColumn);
+  static constexpr int CW = L::CW;                       // lanes per box row (swizzled)
+  static constexpr int RPS = 32 / CW;                    // rows per step (swizzled)
+  static constexpr int NCOL = (P + 31) / 32;             // columns per lane (kColumn)
+  static constexpr int NACC = kMode == kOwnRow ? P : (kMode == kSwizzled ? 4 * L::NBX : NCOL);
+  float acc[NACC];
 
   NFN_DEVI void clear() {
 #pragma unroll
-    for (int m = 0; m < NGL; ++m)
-#pragma unroll
-      for (int v = 0; v < V; ++v) acc[m][v] = 0.0f;
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0f;
   }
-  // rows [0, nvalid) of the tile at byte offset `tile`
+
+  // kOwnRow: called by the lanes that own a valid row, right after their reverse sweep
+  NFN_DEVI void add_own_row(typename L::Row row) {
+    if constexpr (kMode == kOwnRow) {
+      float g[P];
+      Span<0, P, V>::load(row, g);
+#pragma unroll
+      for (int i = 0; i < P; ++i) acc[i] += g[i];
+    }
+  }
+
+  // kSwizzled / kColumn: called by the whole warp once the tile's gradients are in shared memory; rows >= nvalid
+  // of a swizzled tile hold the zero fill of the tensor unit (their lanes wrote nothing)
   NFN_DEVI void add_tile(unsigned tile, int lane, int nvalid) {
     const char* base = dyn_smem() + tile;
+    if constexpr (kMode == kSwizzled) {
+      const int c = lane % CW, q = lane / CW;
 #pragma unroll
-    for (int m = 0; m < NGL; ++m) {
-      const int u = lane + 32 * m;
-      if (u < NG * RS) {
-        const int g = u % NG, r0 = (u / NG) * RPS;
+      for (int j = 0; j < L::NBX; ++j) {
+#pragma unroll
+        for (int s = 0; s < CW; ++s) {                   // 32 rows = CW steps of RPS rows
+          const int r = s * RPS + q;
+          const float4 x = *reinterpret_cast<const float4*>(base + j * L::kBoxBytes + r * L::kRowBytes +
+                                                            ((c ^ L::key(r)) << 4));
+          acc[4 * j + 0] += x.x; acc[4 * j + 1] += x.y; acc[4 * j + 2] += x.z; acc[4 * j + 3] += x.w;
+        }
+      }
+    } else if constexpr (kMode == kColumn) {
+#pragma unroll
+      for (int m = 0; m < NCOL; ++m) {
+        const int col = lane + 32 * m;
+        if (col < P) {
 #pragma unroll 8
-        for (int i = 0; i < RPS; ++i) {
-          const int r = r0 + i;
-          if (r < nvalid) {
-            const char* p = base + L::group_off(r, g);
-            if constexpr (V == 4) {
-              const float4 x = *reinterpret_cast<const float4*>(p);
-              acc[m][0] += x.x; acc[m][1] += x.y; acc[m][2] += x.z; acc[m][3] += x.w;
-            } else if constexpr (V == 2) {
-              const float2 x = *reinterpret_cast<const float2*>(p);
-              acc[m][0] += x.x; acc[m][1] += x.y;
-            } else {
-              acc[m][0] += *reinterpret_cast<const float*>(p);
-            }
-          }
+          for (int r = 0; r < 32; ++r)
+            if (r < nvalid) acc[m] += *reinterpret_cast<const float*>(base + (r * P + col) * 4);
         }
       }
     }
   }
-  // scratch[warp][RS][P] floats; every lane deposits its partial sums (caller syncs the CTA afterwards)
-  NFN_DEVI void deposit(float* scratch, int warp, int lane) const {
+
+  // warp-level totals -> s_part[P] (one row per warp); every lane of the warp must call
+  NFN_DEVI void deposit(float* s_part, int lane) {
+    if constexpr (kMode == kOwnRow) {
 #pragma unroll
-    for (int m = 0; m < NGL; ++m) {
-      const int u = lane + 32 * m;
-      if (u < NG * RS) {
-        const int g = u % NG, rs = u / NG;
+      for (int i = 0; i < P; ++i) {
+        float v = acc[i];
 #pragma unroll
-        for (int v = 0; v < V; ++v) scratch[(warp * RS + rs) * P + g * V + v] = acc[m][v];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_part[i] = v;
+      }
+    } else if constexpr (kMode == kSwizzled) {
+      const int c = lane % CW;
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int o = 16; o >= CW; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);   // over the row groups q
+        if (lane < CW) s_part[(i / 4) * L::W + 4 * c + (i % 4)] = v;                  // box i/4, chunk c
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < NCOL; ++m) {
+        const int col = lane + 32 * m;
+        if (col < P) s_part[col] = acc[m];
       }
     }
   }
 };
 
 // Launch geometry of the warp-tile kernels: NW warps per CTA (T = 32 NW threads), NB tile buffers per
-// warp, MINB resident CTAs per SM.  Wanted: 8 warps per SM with 3 buffers each for the fused kernel (load of
-// tile i+1 in flight, tile i in the registers, store of tile i-1 draining), 12 warps with 2 buffers for the
-// forward kernel; wide rows get fewer buffers, then fewer warps, until the tiles fit the SM's 227 KB.
-__host__ __device__ constexpr ChainGeometry warp_tile_geometry(int P, bool bwd) {
-#ifdef NFN_TUNE_WNB
-  int nb = NFN_TUNE_WNB;
-#else
-  int nb = bwd ? 3 : 2;
-#endif
-#ifdef NFN_TUNE_WWARPS
-  const int want = NFN_TUNE_WWARPS;
-#else
-  const int want = bwd ? 8 : 12;
-#endif
+// warp, MINB resident CTAs per SM (the grid is SMs x MINB, never more).  `hist` = K * D, the floats of z history
+// a thread keeps for the reverse sweep (a proxy for its register footprint).  nb / warps > 0 override the
+// defaults (A/B sweeps through the runtime specialiser: options "tune_wnb", "tune_wwarps").
+//
+// Defaults from the sweeps on B200 (profiles/tuning_r02.md).  The fused kernel refills a buffer only after its
+// store has drained, i.e. at the END of an iteration: with 2 buffers the next tile's load latency is exposed
+// unless enough other warps cover it, with 3 it hides behind the current tile's arithmetic.
+__host__ __device__ constexpr ChainGeometry warp_tile_geometry(int P, bool bwd, int hist, int nb = 0, int warps = 0) {
   const unsigned tile = 128u * (unsigned)(P > 0 ? P : 1);
   const unsigned budget = 227u * 1024u - 4u * 2560u;   // per SM, minus per-CTA reservations / alignment slack
+  int want = warps;
+  if (nb <= 0) nb = bwd ? ((hist >= 12 && tile * 32u <= budget) ? 2 : 3) : 2;
+  if (want <= 0) want = bwd ? (hist > 40 ? 8 : 16) : 12;
   while (nb > 2 && (unsigned)(want * nb) * tile > budget) --nb;
-  int warps = (int)(budget / ((unsigned)nb * tile));
-  if (warps > want) warps = want;
-  if (warps < 1) warps = 1;
-  const int ctas = (warps + 3) / 4;
-  const int nw = warps / ctas;
-  return ChainGeometry{nw * 32, nb, ctas, (unsigned)(nw * nb) * tile + 1024u, 0, 0, 0};
+  int w = (int)(budget / ((unsigned)nb * tile));
+  if (w > want) w = want;
+  if (w < 1) w = 1;
+  const int ctas = (w + 3) / 4;
+  const int nw = w / ctas;
+  return ChainGeometry{nw * 32, nb, ctas, (unsigned)(nw * nb) * tile + 1024u, 0, ctas, 0};
 }
 
 template <class Spec, bool BWD, class M, int NW, int NB>
@@ -964,6 +1024,10 @@ NFN_DEVI void chain_body_w(const ChainArgs& a, const TensorMap* tm_t, const Tens
     }
   }
 
+  // split-phase exchange: one warp of the last CTA collects the previous launch's sums behind its first loads
+  if (a.peer.world > 0 && a.peer.deferred && a.peer.pending_out && blockIdx.x == gridDim.x - 1 && warp == NW - 1)
+    peer_collect(a.peer, a.peer.pending_step, a.peer.pending_out, lane, 32);
+
   CS cs;
   if constexpr (BWD) cs.clear();
   double lsum = 0.0;
@@ -1037,6 +1101,7 @@ NFN_DEVI void chain_body_w(const ChainArgs& a, const TensorMap* tm_t, const Tens
         if constexpr (Spec::BASE) Span<0, 2 * D, V>::store(row, gb);
         BwdSweep<Spec, M, V, Spec::K - 1>::run(row, zs, G, cot);
         if (a.dy) store_event<D>(a.dy, r, G);
+        if constexpr (CS::kMode == CS::kOwnRow) { if (a.dt_colsum) cs.add_own_row(row); }
       }
     }
 
@@ -1057,7 +1122,7 @@ NFN_DEVI void chain_body_w(const ChainArgs& a, const TensorMap* tm_t, const Tens
         }
         bulk_commit();
       }
-      if (a.dt_colsum) cs.add_tile(tile, lane, nvalid);
+      if constexpr (CS::kMode != CS::kOwnRow) { if (a.dt_colsum) cs.add_tile(tile, lane, nvalid); }
       // refill the buffer of the PREVIOUS tile: its store was committed one whole iteration ago, so waiting
       // for "all but the newest group have been read" costs nothing
       const long long nxt = wt + (long long)(NB - 1) * GW;
@@ -1090,14 +1155,14 @@ NFN_DEVI void chain_body_w(const ChainArgs& a, const TensorMap* tm_t, const Tens
   }
   if constexpr (BWD) {
     if (a.dt_colsum) {
-      __syncthreads();      // every warp is done with its tile buffers: reuse them as scratch
+      __syncthreads();      // every warp is done with its tile buffers: reuse them as scratch [NW][P]
       float* scratch = reinterpret_cast<float*>(dyn_smem() + pad);
-      cs.deposit(scratch, warp, lane);
+      cs.deposit(scratch + warp * P, lane);
       __syncthreads();
       for (int j = threadIdx.x; j < P; j += T) {
         float s = 0.0f;
 #pragma unroll
-        for (int q = 0; q < NW * CS::RS; ++q) s += scratch[q * P + j];
+        for (int q = 0; q < NW; ++q) s += scratch[q * P + j];
         atomicAdd(a.dt_colsum + j, (double)s);
       }
     }

@@ -40,6 +40,8 @@ enum Opt {
   kOptPdl,           // programmatic dependent launch (default 1)                             NFN_B200_PDL=0
   kOptDebug,         // NFN_B200_DEBUG
   kOptHostChunkMb,   // NFN_B200_HOST_CHUNK_MB
+  kOptTuneWnb,       // warp-tile kernels through the runtime specialiser: tile buffers per warp (0: default)
+  kOptTuneWwarps,    // ... and warps per SM (0: default)                                     A/B sweeps only
   kOptCount
 };
 int option(Opt o);
@@ -157,7 +159,7 @@ cudaError_t launch_chain_w(const ChainArgs& a, cudaStream_t st) {
   if constexpr (P <= 0) {
     return launch_chain<Spec, BWD, M>(a, st);
   } else {
-    constexpr ChainGeometry kGeo = warp_tile_geometry(P, BWD);
+    constexpr ChainGeometry kGeo = warp_tile_geometry(P, BWD, Spec::K * Spec::D);
     constexpr int NW = kGeo.T / 32;
     constexpr int NB = kGeo.NB;
     constexpr int MINB = kGeo.MINB;
@@ -176,7 +178,7 @@ cudaError_t launch_chain_w(const ChainArgs& a, cudaStream_t st) {
       int occ = 0;
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, kSmem);
       if (e != cudaSuccess) return e;
-      cfg.ctas_per_sm = occ > 0 ? occ : 1;
+      cfg.ctas_per_sm = occ > 0 ? (occ < MINB ? occ : MINB) : 1;   // the geometry's CTA count, never more
       cfg.device = di.device;
     }
     TensorMap tm_t{}, tm_dt{};
@@ -337,7 +339,8 @@ cudaError_t launch_chain_jit(const nfn_chain_desc* desc, const std::string& key,
                              int mode, cudaStream_t st, bool* served);
 
 // peer-memory communicator (nfn_peer.cu)
-PeerArgs make_peer_args(::nfn_peer_comm* c, double* out);
+PeerArgs make_peer_args(::nfn_peer_comm* c, double* out);   // reads the communicator, changes nothing
+void peer_commit(::nfn_peer_comm* c, double* out);          // after a successful launch: advance the sequence
 int launch_peer_allreduce(const PeerArgs& p, cudaStream_t st);
 
 // mixture heads (nfn_mixture.cu)

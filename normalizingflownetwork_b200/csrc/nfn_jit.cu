@@ -307,9 +307,11 @@ cudaError_t launch_chain_jit(const nfn_chain_desc* desc, const std::string& key,
   if (!jit_eligible(desc, P)) return cudaSuccess;
   const int io = chain_io_override();
   if (P > 0 && (io >= 0 ? io == 1 : chain_prefers_warp_tile(P, bwd))) {
-    const ChainGeometry geo[2] = {warp_tile_geometry(P, false), warp_tile_geometry(P, true)};
+    const int hist = desc->n_flows * desc->n_dims, tnb = option(kOptTuneWnb), tw = option(kOptTuneWwarps);
+    const ChainGeometry geo[2] = {warp_tile_geometry(P, false, hist, tnb, tw), warp_tile_geometry(P, true, hist, tnb, tw)};
     const char* const names[2] = {"nfn_jit_chain_w_fwd", "nfn_jit_chain_w_fwd_bwd"};
-    const std::string ckey = key + "|w|m" + std::to_string(mode) + "|dev" + std::to_string(device_info().device);
+    const std::string ckey = key + "|w" + std::to_string(tnb) + "." + std::to_string(tw) + "|m" + std::to_string(mode) +
+                             "|dev" + std::to_string(device_info().device);
     JitEntry* ent = get_or_build(ckey, program_source_w(desc, mode, geo), names, geo);
     if (ent) {
       TensorMap tm_t{}, tm_dt{};
@@ -324,8 +326,17 @@ cudaError_t launch_chain_jit(const nfn_chain_desc* desc, const std::string& key,
       if (grid > ntiles) grid = ntiles;
       ChainArgs args = a;
       void* params[] = {&args, &tm_t, &tm_dt};
-      cudaError_t ce = cudaLaunchKernel((const void*)ent->kern[b], dim3((unsigned)grid), dim3((unsigned)T), params,
-                                        ent->geo[b].smem_bytes, st);
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3((unsigned)grid);
+      lc.blockDim = dim3((unsigned)T);
+      lc.dynamicSmemBytes = ent->geo[b].smem_bytes;
+      lc.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = at;
+      lc.numAttrs = pdl_enabled() ? 1 : 0;
+      cudaError_t ce = cudaLaunchKernelExC(&lc, (const void*)ent->kern[b], params);
       if (ce == cudaSuccess) {
         count_launch();
         *served = true;
@@ -470,7 +481,8 @@ long long jit_compile_check(const nfn_chain_desc* desc, int mode, std::string& l
   if (!compile_cubin(program_source(desc, mode, geo), cubin, log)) return -1;
   long long total = (long long)cubin.size();
   if (P > 0) {  // the warp-tile generation must build from the same embedded headers
-    ChainGeometry geow[2] = {warp_tile_geometry(P, false), warp_tile_geometry(P, true)};
+    const int hist = desc->n_flows * desc->n_dims;
+    ChainGeometry geow[2] = {warp_tile_geometry(P, false, hist), warp_tile_geometry(P, true, hist)};
     std::vector<char> cubin_w;
     if (!compile_cubin(program_source_w(desc, mode, geow), cubin_w, log)) return -1;
     total += (long long)cubin_w.size();

@@ -495,9 +495,9 @@ template <class Kern>
 static int launch_tiled(Kern kern, const MixArgs& a, const RtTile& g, size_t smem, int nb, const char* name,
                         cudaStream_t st) {
   const DeviceInfo& di = device_info();
-  if (smem > (size_t)di.smem_optin)
+  if (smem + 2048 > (size_t)di.smem_optin)
     return set_error(NFN_ERR_UNSUPPORTED, "%s: row of %d floats needs %zu bytes of shared memory (> %d)", name,
-                     g.P, smem, di.smem_optin);
+                     g.P, smem, di.smem_optin - 2048);
   // once per (kernel, device): opt in to the device's full dynamic shared memory, so that no later launch with a
   // different component count has to touch the attribute again (a per-launch cudaFuncSetAttribute races between
   // host threads using different K); the occupancy answer is memoised per (kernel, device, bytes)
@@ -509,7 +509,10 @@ static int launch_tiled(Kern kern, const MixArgs& a, const RtTile& g, size_t sme
   Memo& m = memo[(const void*)kern];
   cudaError_t e;
   if (m.device != di.device) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin);
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return cuda_error(e, name);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin - (int)fa.sharedSizeBytes);
     if (e != cudaSuccess) return cuda_error(e, name);
     m.device = di.device;
     m.occ.clear();

@@ -6,6 +6,7 @@
 // torch.distributed and every rank maps its peers with cudaIpcOpenMemHandle (NVLink P2P).
 // The exchange itself runs inside the compute kernel's last CTA (peer_allreduce in
 // nfn_chain_kernel.cuh) or, for kernels without that epilogue, in a one-CTA kernel here.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -16,24 +17,45 @@ struct nfn_peer_comm {
   double* base[nfn::kMaxPeers] = {};
   double* acc = nullptr;       // [n_values] local accumulators (self-resetting)
   unsigned* ticket = nullptr;  // CTA arrival counter (self-resetting)
-  unsigned long long step = 0;
+  unsigned* status = nullptr;  // sticky device error word (time-outs)
+  unsigned long long step = 0; // exchanges issued so far
+  int deferred = 0;            // split-phase mode
+  double* pending_out = nullptr;        // split-phase: where the sums of exchange step-1 still have to go
+  long long timeout_cycles = 60000000000ll;  // ~30 s at 2 GHz
 };
 
 namespace nfn {
 
-__global__ void __launch_bounds__(128) peer_allreduce_kernel(const PeerArgs p) { peer_allreduce<128>(p); }
+__global__ void __launch_bounds__(128) peer_allreduce_kernel(const PeerArgs p) {
+  peer_head(p);
+  peer_allreduce<128>(p);
+}
+__global__ void __launch_bounds__(128) peer_flush_kernel(const PeerArgs p) { peer_head(p); }
 
+// Arguments of the NEXT exchange.  Nothing in the communicator changes here: the caller commits
+// (peer_commit) only after its launch succeeded, so a failed call leaves this rank's sequence number, parity
+// and pending result in step with its peers.
 PeerArgs make_peer_args(nfn_peer_comm* c, double* out) {
   PeerArgs p{};
   for (int i = 0; i < kMaxPeers; ++i) p.base[i] = c->base[i];
   p.acc = c->acc;
   p.out = out;
   p.ticket = c->ticket;
-  p.step = c->step++;
+  p.step = c->step;
   p.world = c->world;
   p.rank = c->rank;
   p.n_values = c->n_values;
+  p.deferred = c->deferred;
+  p.pending_out = c->deferred ? c->pending_out : nullptr;
+  p.pending_step = c->step - 1;
+  p.status = c->status;
+  p.timeout_cycles = c->timeout_cycles;
   return p;
+}
+
+void peer_commit(nfn_peer_comm* c, double* out) {
+  ++c->step;
+  c->pending_out = c->deferred ? out : nullptr;
 }
 
 int launch_peer_allreduce(const PeerArgs& p, cudaStream_t st) {
@@ -107,11 +129,16 @@ int nfn_peer_comm_create(int world, int rank, int n_values, void* const* regions
   }
   cudaError_t e = cudaMalloc((void**)&c->acc, (size_t)n_values * sizeof(double) + 16);
   if (e == cudaSuccess) e = cudaMemset(c->acc, 0, (size_t)n_values * sizeof(double) + 16);
+  if (const char* ev = getenv("NFN_B200_PEER_TIMEOUT_S")) {  // set-up time only, never on a launch path
+    const double sec = atof(ev);
+    if (sec > 0.0) c->timeout_cycles = (long long)(sec * 2.0e9);
+  }
   if (e != cudaSuccess) {
     delete c;
     return cuda_error(e, "cudaMalloc(peer accumulators)");
   }
   c->ticket = (unsigned*)(c->acc + n_values);
+  c->status = c->ticket + 1;
   *comm = c;
   return NFN_OK;
 }
@@ -130,7 +157,39 @@ int nfn_peer_allreduce(nfn_peer_comm* comm, const double* values, double* reduce
   cudaError_t e = cudaMemcpyAsync(comm->acc, values, (size_t)comm->n_values * sizeof(double),
                                   cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) return cuda_error(e, "cudaMemcpyAsync(values)");
-  return launch_peer_allreduce(make_peer_args(comm, reduced), st);
+  int rc = launch_peer_allreduce(make_peer_args(comm, reduced), st);
+  if (rc == NFN_OK) peer_commit(comm, reduced);
+  return rc;
+}
+
+int nfn_peer_set_deferred(nfn_peer_comm* comm, int deferred) {
+  if (!comm) return set_error(NFN_ERR_NULL, "comm is NULL");
+  if (comm->pending_out) return set_error(NFN_ERR_SHAPE, "an exchange is still pending: call nfn_peer_flush first");
+  comm->deferred = deferred ? 1 : 0;
+  return NFN_OK;
+}
+
+int nfn_peer_flush(nfn_peer_comm* comm, void* stream) {
+  if (!comm) return set_error(NFN_ERR_NULL, "comm is NULL");
+  if (!comm->deferred || !comm->pending_out) return NFN_OK;
+  PeerArgs p = make_peer_args(comm, nullptr);
+  peer_flush_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(p);
+  count_launch();
+  int rc = cuda_error(cudaGetLastError(), "peer_flush_kernel");
+  if (rc == NFN_OK) comm->pending_out = nullptr;
+  return rc;
+}
+
+int nfn_peer_status(nfn_peer_comm* comm) {
+  if (!comm) return set_error(NFN_ERR_NULL, "comm is NULL");
+  unsigned st = 0;
+  cudaError_t e = cudaMemcpy(&st, comm->status, sizeof(st), cudaMemcpyDeviceToHost);  // synchronises
+  if (e != cudaSuccess) return cuda_error(e, "cudaMemcpy(peer status)");
+  if (st != 0)
+    return set_error(NFN_ERR_PEER_TIMEOUT,
+                     "a peer did not arrive within the exchange time-out (%.1f s): the reduced sums of that step are NaN "
+                     "and the ranks may have diverged", (double)comm->timeout_cycles / 2.0e9);
+  return NFN_OK;
 }
 
 }  // extern "C"

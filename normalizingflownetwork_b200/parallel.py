@@ -147,6 +147,21 @@ class PeerComm:
                                                         self._lib.current_stream(self.device)))
         return out
 
+    def set_deferred(self, deferred=True):
+        """Split-phase mode: a launch pushes its totals, the NEXT launch on this communicator (or flush())
+        collects them into the earlier call's ``reduced`` tensor (include/nfn_b200.h)."""
+        self._lib.check(self.lib.nfn_peer_set_deferred(self.comm, 1 if deferred else 0))
+
+    def flush(self):
+        """Complete the pending exchange of split-phase mode (one tiny kernel on the current stream)."""
+        with torch.cuda.device(self.device):
+            self._lib.check(self.lib.nfn_peer_flush(self.comm, self._lib.current_stream(self.device)))
+
+    def status(self):
+        """Synchronises; raises NfnError(NFN_ERR_PEER_TIMEOUT) if any exchange timed out on a peer."""
+        with torch.cuda.device(self.device):
+            self._lib.check(self.lib.nfn_peer_status(self.comm))
+
     def _release(self):
         with torch.cuda.device(self.device):
             if self.comm is not None:
@@ -160,11 +175,19 @@ class PeerComm:
     def close(self):
         if getattr(self, "comm", None) is None:
             return
+        err = None
         with torch.cuda.device(self.device):
+            try:
+                self.flush()
+                self.status()
+            except Exception as exc:  # noqa: BLE001 -- still unmap; every rank must reach the barrier
+                err = exc
             torch.cuda.synchronize()
             if self.world > 1:
                 dist.barrier()  # nobody unmaps while a peer may still push
         self._release()
+        if err is not None:
+            raise err
 
 
 def barrier():

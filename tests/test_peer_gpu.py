@@ -57,6 +57,33 @@ def _check_rank(rank, world, device, steps=6):
     if world > 1:
         torch.distributed.all_reduce(local)
     assert torch.allclose(red, local, rtol=1e-4, atol=1e-5)
+    # split-phase mode: a launch only pushes; the next launch on the communicator (or flush) collects into the
+    # EARLIER call's `reduced` tensor -- both kernel generations
+    comm.set_deferred(True)
+    for io in ("cpasync", "tma"):
+        F.set_option("chain_io", io)
+        pend = []
+        for step in range(5):
+            B = 20_000 + 777 * rank + 31 * step
+            t = torch.randn((B, P), generator=g, device=device) * 0.5
+            y = torch.randn((B, d), generator=g, device=device)
+            red = torch.full((P + 1,), float("nan"), dtype=torch.float64, device=device)
+            lp, dt, red = F.chain_forward_backward_peer(t, y, ft, d, tb, comm, g_scale=-1.0 / B, want_colsum=True,
+                                                        reduced=red)
+            local = torch.cat([dt.double().sum(0), lp.double().sum().reshape(1)])
+            if world > 1:
+                torch.distributed.all_reduce(local)
+            pend.append((red, local))
+            if step >= 1:  # the previous call's sums are complete once THIS launch has run
+                torch.cuda.synchronize()
+                r0, l0 = pend[step - 1]
+                assert torch.allclose(r0, l0, rtol=1e-4, atol=1e-5), (io, step, (r0 - l0).abs().max())
+        comm.flush()
+        torch.cuda.synchronize()
+        assert torch.allclose(pend[-1][0], pend[-1][1], rtol=1e-4, atol=1e-5), io
+    F.set_option("chain_io", "auto")
+    comm.set_deferred(False)
+    comm.status()   # no exchange timed out
     comm.close()
 
 
