@@ -43,6 +43,9 @@ CONFIGS = {
     "cfg1": (["radial"] * 3, 1, True, 2048, True),
     # MDN head: flow_types slot holds ("mdn", n_centers)
     "cfg5": (("mdn", 20), 2, None, 1 << 22, True),
+    # not BASELINE configs: the chains NormalizingFlowNetwork builds by default (n_flows = 10, all radial), tuning only
+    "r10d1": (["radial"] * 10, 1, True, 1 << 20, True),
+    "r10d2": (["radial"] * 10, 2, True, 1 << 20, True),
 }
 WORKLOAD_NAMES = {
     "cfg5": "MDN 20-component Gaussian mixture head, 2-D y, P=100, batch 2^22 per GPU, logsumexp log-lik fwd+bwd",
@@ -50,6 +53,8 @@ WORKLOAD_NAMES = {
     "cfg3": "NFN 16 flows (radial,planar)x8, 4-D y, P=128, 2^23 (x,y) pairs per GPU, density-grid log-prob fwd",
     "cfg4": "Bayesian NFN 5 radial flows, 1-D y, P=17, S*B = 2^20 rows per GPU, log-prob fwd+bwd",
     "cfg1": "NFN 3 radial flows, 1-D y, P=11, batch 2048, log-prob fwd+bwd",
+    "r10d1": "NFN 10 radial flows, 1-D y, P=32, batch 2^20 per GPU, log-prob fwd+bwd (tuning)",
+    "r10d2": "NFN 10 radial flows, 2-D y, P=44, batch 2^20 per GPU, log-prob fwd+bwd (tuning)",
 }
 METRIC = "flow log-prob fwd+bwd samples/sec"
 UNIT = "samples/s"

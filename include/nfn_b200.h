@@ -208,6 +208,15 @@ int nfn_dense_act_forward(const float* x, const float* weight, const float* bias
 int nfn_dense_act_backward(const float* x, const float* out, const float* dout, const float* weight, int64_t B,
                            int in_features, int units, int act, float* dx, float* dweight, float* dbias,
                            void* stream);
+/* The same with the estimators' input normalisation fused into the layer (the FIRST layer of the network):
+ * x is the raw conditioning input and every read of it becomes (x - x_mean) / (x_std + 1e-8), the Lambda layer of
+ * reference estimators/MaximumLikelihoodNNEstimator.py:40.  x_mean / x_std are device float[K] (both or neither).
+ * The backward form serves the first layer only (dx == NULL, K <= 4, N <= 32), else NFN_ERR_UNSUPPORTED. */
+int nfn_dense_act_forward_x(const float* x, const float* x_mean, const float* x_std, const float* weight,
+                            const float* bias, int64_t B, int in_features, int units, int act, float* out, void* stream);
+int nfn_dense_act_backward_x(const float* x, const float* x_mean, const float* x_std, const float* out, const float* dout,
+                             const float* weight, int64_t B, int in_features, int units, int act, float* dx,
+                             float* dweight, float* dbias, void* stream);
 
 /*
  * One bijector on its own: Flow(t, n_dims).forward(z) and ._forward_log_det_jacobian(z)
@@ -244,6 +253,62 @@ int nfn_kmn_forward_backward(int n_components, int n_dims, const float* t, const
                              int64_t y_rows, const float* locs, const float* scales,
                              const float* g_logp, float g_scale, float* logp, float* dt, float* dy,
                              float* dscales, double* logp_sum, int64_t B, void* stream);
+
+/*
+ * Event transform: the estimators' y pipeline fused into the heads as a prologue / epilogue,
+ * so that normalisation, noise regularisation, the normalisation Jacobian and `pdf`'s exp cost no extra pass over
+ * y or logp.  Replaces, per call (reference estimators/BaseEstimator.py):
+ *   NFN_XF_NORMALISE  y' = (y - mean) / std                      :61-69 (`(x - y_mean) / y_std`; also :73, :82)
+ *   NFN_XF_NOISE      y' += noise_std * N(0, 1), training only   :66-68 (GaussianNoise) -- Philox4x32-10, key `seed`,
+ *                     counter (global row, offset + *offset_dev): the caller advances the offset once per call;
+ *                     `offset_dev` (device uint64, nullable) lets a captured CUDA graph draw fresh noise per replay
+ *   logp_shift        added to every log-prob: -sum(log y_std)    :57 (`+ tf.reduce_sum(tf.math.log(y_std))` of the
+ *                     NLL), :86 (`log_prob - sum log y_std`)
+ *   NFN_XF_EXP        logp[] receives exp(log-prob + logp_shift)  :75 (`prob / prod(y_std)`)
+ * The `_x` entry points are the plain ones with one more argument (NULL = identity).  logp_sum accumulates what
+ * is written to logp[]; dy (where requested) is the gradient with respect to the transformed event y'.
+ */
+enum { NFN_XF_NORMALISE = 1, NFN_XF_NOISE = 2, NFN_XF_EXP = 4 };
+typedef struct nfn_event_xform {
+  float mean[NFN_MAX_DIMS];
+  float std[NFN_MAX_DIMS];
+  float noise_std;
+  float logp_shift;
+  uint64_t seed;
+  uint64_t offset;
+  const uint64_t* offset_dev;
+  int32_t flags;
+  int32_t reserved;
+} nfn_event_xform;
+
+int nfn_chain_forward_x(const nfn_chain_desc* desc, const float* t, const float* y, int64_t y_rows,
+                        float* logp, int64_t B, const nfn_event_xform* xf, void* stream);
+int nfn_chain_forward_grid_x(const nfn_chain_desc* desc, const float* t, const float* y_grid, int64_t n_y,
+                             float* logp, int64_t B, const nfn_event_xform* xf, void* stream);
+int nfn_chain_forward_backward_x(const nfn_chain_desc* desc, const float* t, const float* y,
+                                 int64_t y_rows, const float* g_logp, float g_scale, float* logp,
+                                 float* dt, float* dy, double* logp_sum, double* dt_colsum, int64_t B,
+                                 const nfn_event_xform* xf, void* stream);
+int nfn_dense_chain_forward_x(const nfn_chain_desc* desc, int hidden, const float* h, const float* W,
+                              const float* bias, const float* y, int64_t y_rows, float* logp, int64_t B,
+                              const nfn_event_xform* xf, void* stream);
+int nfn_dense_chain_forward_backward_x(const nfn_chain_desc* desc, int hidden, const float* h, const float* W,
+                                       const float* bias, const float* y, int64_t y_rows, const float* g_logp,
+                                       float g_scale, float* logp, float* dh, float* dW, float* dbias,
+                                       double* logp_sum, int64_t B, const nfn_event_xform* xf, void* stream);
+int nfn_mdn_forward_x(int n_centers, int n_dims, const float* t, const float* y, int64_t y_rows,
+                      float* logp, int64_t B, const nfn_event_xform* xf, void* stream);
+int nfn_mdn_forward_backward_x(int n_centers, int n_dims, const float* t, const float* y,
+                               int64_t y_rows, const float* g_logp, float g_scale, float* logp,
+                               float* dt, float* dy, double* logp_sum, double* dt_colsum, int64_t B,
+                               const nfn_event_xform* xf, void* stream);
+int nfn_kmn_forward_x(int n_components, int n_dims, const float* t, const float* y, int64_t y_rows,
+                      const float* locs, const float* scales, float* logp, int64_t B, const nfn_event_xform* xf,
+                      void* stream);
+int nfn_kmn_forward_backward_x(int n_components, int n_dims, const float* t, const float* y,
+                               int64_t y_rows, const float* locs, const float* scales,
+                               const float* g_logp, float g_scale, float* logp, float* dt, float* dy,
+                               float* dscales, double* logp_sum, int64_t B, const nfn_event_xform* xf, void* stream);
 
 /*
  * Posterior-predictive epilogue of BayesianNNEstimator.score

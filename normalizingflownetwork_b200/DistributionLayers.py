@@ -96,11 +96,17 @@ class FlowChainDistribution:
     def prob(self, y):
         return torch.exp(self.log_prob(y))
 
-    def log_prob_grid(self, y_grid):
+    def log_prob_x(self, y, xform):
+        """Forward-only log_prob with the estimator's y pipeline (normalisation, Jacobian shift, optional exp)
+        fused into the kernel: ``y`` is the RAW event, ``xform`` a ``functional.make_xform`` result."""
+        return F.chain_forward(self.t.detach(), _to_tensor_like(y, self.t), self.flow_types, self.n_dims,
+                               self.trainable_base_dist, xform=xform)
+
+    def log_prob_grid(self, y_grid, xform=None):
         """[n_y, B]: every event of ``y_grid[n_y, d]`` against every batch row, parameters read once
         (what the reference's plot_model does with one ``dist.prob(y[i])`` call per grid line)."""
         return F.chain_forward_grid(self.t, _to_tensor_like(y_grid, self.t), self.flow_types, self.n_dims,
-                                    self.trainable_base_dist)
+                                    self.trainable_base_dist, xform=xform)
 
     def prob_grid(self, y_grid):
         return torch.exp(self.log_prob_grid(y_grid))
@@ -137,6 +143,13 @@ class FusedDenseFlowChainDistribution(FlowChainDistribution):
             return super().log_prob(y)
         return F.dense_chain_forward(self.h, self.W, self.bias, y, self.flow_types, self.n_dims,
                                      self.trainable_base_dist)
+
+    def log_prob_x(self, y, xform):
+        y = _to_tensor_like(y, self.h)
+        if y.shape[0] not in (self.h.shape[0], 1):
+            return super().log_prob_x(y, xform)
+        return F.dense_chain_forward(self.h.detach(), self.W.detach(), self.bias.detach(), y, self.flow_types,
+                                     self.n_dims, self.trainable_base_dist, xform=xform)
 
 
 class InverseNormalizingFlowLayer(torch.nn.Module):
@@ -219,6 +232,10 @@ class GaussianMixtureDistribution:
     def log_prob(self, y):
         return F.mdn_log_prob(self.t, _to_tensor_like(y, self.t), self.n_centers, self.n_dims)
 
+    def log_prob_x(self, y, xform):
+        """Forward-only, raw ``y``, the estimator's y pipeline fused into the kernel (see FlowChainDistribution)."""
+        return F.mdn_forward(self.t.detach(), _to_tensor_like(y, self.t), self.n_centers, self.n_dims, xform=xform)
+
     def prob(self, y):
         return torch.exp(self.log_prob(y))
 
@@ -269,6 +286,11 @@ class GaussianKernelsDistribution:
     def log_prob(self, y):
         return F.kmn_log_prob(self.t, _to_tensor_like(y, self.t), self.locs.to(self.t.device),
                               self.scales.to(self.t.device))
+
+    def log_prob_x(self, y, xform):
+        """Forward-only, raw ``y``, the estimator's y pipeline fused into the kernel (see FlowChainDistribution)."""
+        return F.kmn_forward(self.t.detach(), _to_tensor_like(y, self.t), self.locs.to(self.t.device),
+                             self.scales.detach().to(self.t.device), xform=xform)
 
     def prob(self, y):
         return torch.exp(self.log_prob(y))

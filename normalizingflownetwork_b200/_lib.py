@@ -31,6 +31,26 @@ class ChainDesc(ctypes.Structure):
     ]
 
 
+class EventXform(ctypes.Structure):
+    """struct nfn_event_xform (include/nfn_b200.h): y normalisation / noise / Jacobian shift / exp fused into a head."""
+
+    _fields_ = [
+        ("mean", ctypes.c_float * NFN_MAX_DIMS),
+        ("std", ctypes.c_float * NFN_MAX_DIMS),
+        ("noise_std", ctypes.c_float),
+        ("logp_shift", ctypes.c_float),
+        ("seed", ctypes.c_uint64),
+        ("offset", ctypes.c_uint64),
+        ("offset_dev", ctypes.c_void_p),
+        ("flags", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+XF_NORMALISE, XF_NOISE, XF_EXP = 1, 2, 4
+_xf_p = ctypes.POINTER(EventXform)
+
+
 class NfnError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("libnfn_b200 error %d: %s" % (code, msg))
@@ -102,6 +122,38 @@ SIGNATURES = {
                                                _c_float_p, _c_float_p, _c_float_p, ctypes.c_float,
                                                _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                                ctypes.c_void_p, _i64, ctypes.c_void_p]),
+    "nfn_chain_forward_x": (ctypes.c_int, [ctypes.POINTER(ChainDesc), _c_float_p, _c_float_p, _i64,
+                                          _c_float_p, _i64, _xf_p, ctypes.c_void_p]),
+    "nfn_chain_forward_grid_x": (ctypes.c_int, [ctypes.POINTER(ChainDesc), _c_float_p, _c_float_p, _i64,
+                                               _c_float_p, _i64, _xf_p, ctypes.c_void_p]),
+    "nfn_chain_forward_backward_x": (ctypes.c_int, [ctypes.POINTER(ChainDesc), _c_float_p, _c_float_p, _i64,
+                                                   _c_float_p, ctypes.c_float, _c_float_p, _c_float_p,
+                                                   _c_float_p, ctypes.c_void_p, _c_float_p, _i64, _xf_p,
+                                                   ctypes.c_void_p]),
+    "nfn_dense_chain_forward_x": (ctypes.c_int, [ctypes.POINTER(ChainDesc), ctypes.c_int, _c_float_p, _c_float_p,
+                                                _c_float_p, _c_float_p, _i64, _c_float_p, _i64, _xf_p,
+                                                ctypes.c_void_p]),
+    "nfn_dense_chain_forward_backward_x": (ctypes.c_int, [ctypes.POINTER(ChainDesc), ctypes.c_int, _c_float_p,
+                                                         _c_float_p, _c_float_p, _c_float_p, _i64, _c_float_p,
+                                                         ctypes.c_float, _c_float_p, _c_float_p, _c_float_p,
+                                                         _c_float_p, ctypes.c_void_p, _i64, _xf_p, ctypes.c_void_p]),
+    "nfn_dense_act_forward_x": (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _i64,
+                                              ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, ctypes.c_void_p]),
+    "nfn_dense_act_backward_x": (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                               _i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p,
+                                               _c_float_p, ctypes.c_void_p]),
+    "nfn_mdn_forward_x": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _i64,
+                                        _c_float_p, _i64, _xf_p, ctypes.c_void_p]),
+    "nfn_mdn_forward_backward_x": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _i64,
+                                                 _c_float_p, ctypes.c_float, _c_float_p, _c_float_p,
+                                                 _c_float_p, ctypes.c_void_p, _c_float_p, _i64, _xf_p,
+                                                 ctypes.c_void_p]),
+    "nfn_kmn_forward_x": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _i64,
+                                        _c_float_p, _c_float_p, _c_float_p, _i64, _xf_p, ctypes.c_void_p]),
+    "nfn_kmn_forward_backward_x": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _i64,
+                                                 _c_float_p, _c_float_p, _c_float_p, ctypes.c_float,
+                                                 _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                                 ctypes.c_void_p, _i64, _xf_p, ctypes.c_void_p]),
     "nfn_logmeanexp_draws": (ctypes.c_int, [_c_float_p, _i64, _i64, _c_float_p, ctypes.c_void_p]),
     "nfn_chain_forward_host": (ctypes.c_int, [ctypes.POINTER(ChainDesc), _c_float_p, _c_float_p, _i64,
                                              _c_float_p, _i64]),

@@ -221,6 +221,23 @@ static const DescMemo& lookup_chain(const nfn_chain_desc* desc) {
   return m;
 }
 
+static_assert(sizeof(nfn_event_xform) == sizeof(EventXform), "nfn_event_xform mirrors nfn::EventXform");
+
+// validates the caller's event transform for an n_dims-dimensional head and copies it into the kernel arguments
+static int set_xform(EventXform& dst, const nfn_event_xform* xf, int n_dims) {
+  memset(&dst, 0, sizeof(dst));
+  if (!xf) return NFN_OK;
+  if (xf->flags & ~(NFN_XF_NORMALISE | NFN_XF_NOISE | NFN_XF_EXP))
+    return set_error(NFN_ERR_DESC, "event transform: unknown flag bits 0x%x", xf->flags);
+  if (xf->flags & NFN_XF_NORMALISE)
+    for (int i = 0; i < n_dims; ++i)
+      if (!(xf->std[i] != 0.0f)) return set_error(NFN_ERR_DESC, "event transform: std[%d] is zero or NaN", i);
+  if ((xf->flags & NFN_XF_NOISE) && !(xf->noise_std >= 0.0f))
+    return set_error(NFN_ERR_DESC, "event transform: noise_std=%g", (double)xf->noise_std);
+  memcpy(&dst, xf, sizeof(dst));
+  return NFN_OK;
+}
+
 static int chain_dispatch(const nfn_chain_desc* desc, const ChainArgs& a, bool bwd, cudaStream_t st) {
   const DescMemo& memo = lookup_chain(desc);
   const std::string& key = memo.key;
@@ -315,6 +332,11 @@ int nfn_chain_is_specialized(const nfn_chain_desc* desc) {
 
 int nfn_chain_forward(const nfn_chain_desc* desc, const float* t, const float* y, int64_t y_rows,
                       float* logp, int64_t B, void* stream) {
+  return nfn_chain_forward_x(desc, t, y, y_rows, logp, B, nullptr, stream);
+}
+
+int nfn_chain_forward_x(const nfn_chain_desc* desc, const float* t, const float* y, int64_t y_rows,
+                        float* logp, int64_t B, const nfn_event_xform* xf, void* stream) {
   int rc = check_desc(desc);
   if (rc != NFN_OK) return rc;
   if ((rc = check_rows(B, y_rows)) != NFN_OK) return rc;
@@ -326,11 +348,17 @@ int nfn_chain_forward(const nfn_chain_desc* desc, const float* t, const float* y
     return set_error(NFN_ERR_ALIGN, "y must be %zu-byte aligned", event_align(desc->n_dims));
   ChainArgs a{};
   a.t = t; a.y = y; a.logp = logp; a.B = B; a.g_scale = 1.0f; a.y_broadcast = (y_rows == 1 && B != 1);
+  if ((rc = set_xform(a.xf, xf, desc->n_dims)) != NFN_OK) return rc;
   return chain_dispatch(desc, a, false, (cudaStream_t)stream);
 }
 
 int nfn_chain_forward_grid(const nfn_chain_desc* desc, const float* t, const float* y_grid, int64_t n_y,
                            float* logp, int64_t B, void* stream) {
+  return nfn_chain_forward_grid_x(desc, t, y_grid, n_y, logp, B, nullptr, stream);
+}
+
+int nfn_chain_forward_grid_x(const nfn_chain_desc* desc, const float* t, const float* y_grid, int64_t n_y,
+                             float* logp, int64_t B, const nfn_event_xform* xf, void* stream) {
   int rc = check_desc(desc);
   if (rc != NFN_OK) return rc;
   if (B < 0 || n_y < 0 || n_y > (1 << 30)) return set_error(NFN_ERR_SHAPE, "B=%lld, n_y=%lld", (long long)B, (long long)n_y);
@@ -342,6 +370,7 @@ int nfn_chain_forward_grid(const nfn_chain_desc* desc, const float* t, const flo
     return set_error(NFN_ERR_ALIGN, "y_grid must be %zu-byte aligned", event_align(desc->n_dims));
   ChainArgs a{};
   a.t = t; a.y = y_grid; a.logp = logp; a.B = B; a.g_scale = 1.0f; a.y_broadcast = 1; a.grid_ny = (int)n_y;
+  if ((rc = set_xform(a.xf, xf, desc->n_dims)) != NFN_OK) return rc;
   return chain_dispatch(desc, a, false, (cudaStream_t)stream);
 }
 
@@ -349,6 +378,14 @@ int nfn_chain_forward_backward(const nfn_chain_desc* desc, const float* t, const
                                int64_t y_rows, const float* g_logp, float g_scale, float* logp,
                                float* dt, float* dy, double* logp_sum, double* dt_colsum, int64_t B,
                                void* stream) {
+  return nfn_chain_forward_backward_x(desc, t, y, y_rows, g_logp, g_scale, logp, dt, dy, logp_sum, dt_colsum, B, nullptr,
+                                      stream);
+}
+
+int nfn_chain_forward_backward_x(const nfn_chain_desc* desc, const float* t, const float* y,
+                                 int64_t y_rows, const float* g_logp, float g_scale, float* logp,
+                                 float* dt, float* dy, double* logp_sum, double* dt_colsum, int64_t B,
+                                 const nfn_event_xform* xf, void* stream) {
   int rc = check_desc(desc);
   if (rc != NFN_OK) return rc;
   if ((rc = check_rows(B, y_rows)) != NFN_OK) return rc;
@@ -365,6 +402,7 @@ int nfn_chain_forward_backward(const nfn_chain_desc* desc, const float* t, const
   a.t = t; a.y = y; a.g_logp = g_logp; a.logp = logp; a.dt = dt; a.dy = dy;
   a.logp_sum = logp_sum; a.dt_colsum = dt_colsum; a.B = B; a.g_scale = g_scale;
   a.y_broadcast = (y_rows == 1 && B != 1);
+  if ((rc = set_xform(a.xf, xf, desc->n_dims)) != NFN_OK) return rc;
   return chain_dispatch(desc, a, true, (cudaStream_t)stream);
 }
 
@@ -457,11 +495,18 @@ static int dense_common(const nfn_chain_desc* desc, int hidden, const float* h, 
 int nfn_dense_chain_forward(const nfn_chain_desc* desc, int hidden, const float* h, const float* W,
                             const float* bias, const float* y, int64_t y_rows, float* logp, int64_t B,
                             void* stream) {
+  return nfn_dense_chain_forward_x(desc, hidden, h, W, bias, y, y_rows, logp, B, nullptr, stream);
+}
+
+int nfn_dense_chain_forward_x(const nfn_chain_desc* desc, int hidden, const float* h, const float* W,
+                              const float* bias, const float* y, int64_t y_rows, float* logp, int64_t B,
+                              const nfn_event_xform* xf, void* stream) {
   int rc = dense_common(desc, hidden, h, W, bias, y, y_rows, logp, B);
   if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
   DenseArgs a{};
   a.h = h; a.W = W; a.bias = bias; a.y = y; a.logp = logp; a.B = B; a.g_scale = 1.0f;
   a.y_broadcast = (y_rows == 1 && B != 1);
+  if ((rc = set_xform(a.xf, xf, desc->n_dims)) != NFN_OK) return rc;
   return dense_dispatch(desc, hidden, a, false, (cudaStream_t)stream);
 }
 
@@ -469,6 +514,14 @@ int nfn_dense_chain_forward_backward(const nfn_chain_desc* desc, int hidden, con
                                      const float* bias, const float* y, int64_t y_rows, const float* g_logp,
                                      float g_scale, float* logp, float* dh, float* dW, float* dbias,
                                      double* logp_sum, int64_t B, void* stream) {
+  return nfn_dense_chain_forward_backward_x(desc, hidden, h, W, bias, y, y_rows, g_logp, g_scale, logp, dh, dW, dbias,
+                                            logp_sum, B, nullptr, stream);
+}
+
+int nfn_dense_chain_forward_backward_x(const nfn_chain_desc* desc, int hidden, const float* h, const float* W,
+                                       const float* bias, const float* y, int64_t y_rows, const float* g_logp,
+                                       float g_scale, float* logp, float* dh, float* dW, float* dbias,
+                                       double* logp_sum, int64_t B, const nfn_event_xform* xf, void* stream) {
   int rc = dense_common(desc, hidden, h, W, bias, y, y_rows, logp, B);
   if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
   if (!dh || !dW || !dbias) return set_error(NFN_ERR_NULL, "dh, dW and dbias must be non-NULL");
@@ -477,6 +530,7 @@ int nfn_dense_chain_forward_backward(const nfn_chain_desc* desc, int hidden, con
   a.h = h; a.W = W; a.bias = bias; a.y = y; a.g_logp = g_logp; a.logp = logp; a.dh = dh; a.dW = dW;
   a.dbias = dbias; a.logp_sum = logp_sum; a.B = B; a.g_scale = g_scale;
   a.y_broadcast = (y_rows == 1 && B != 1);
+  if ((rc = set_xform(a.xf, xf, desc->n_dims)) != NFN_OK) return rc;
   return dense_dispatch(desc, hidden, a, true, (cudaStream_t)stream);
 }
 
@@ -504,6 +558,12 @@ int nfn_dense_act_supported(int in_features, int units, int act) {
 
 int nfn_dense_act_forward(const float* x, const float* weight, const float* bias, int64_t B, int in_features,
                           int units, int act, float* out, void* stream) {
+  return nfn_dense_act_forward_x(x, nullptr, nullptr, weight, bias, B, in_features, units, act, out, stream);
+}
+
+int nfn_dense_act_forward_x(const float* x, const float* x_mean, const float* x_std, const float* weight, const float* bias,
+                            int64_t B, int in_features, int units, int act, float* out, void* stream) {
+  if ((x_mean == nullptr) != (x_std == nullptr)) return set_error(NFN_ERR_NULL, "x_mean and x_std go together");
   if (!mlp_layer_supported(in_features, units, act))
     return set_error(NFN_ERR_UNSUPPORTED, "dense layer %d -> %d (act %d) is outside the fused kernels' range", in_features,
                      units, act);
@@ -512,12 +572,22 @@ int nfn_dense_act_forward(const float* x, const float* weight, const float* bias
   if (!x || !weight || !bias || !out) return set_error(NFN_ERR_NULL, "x, weight, bias and out must be non-NULL");
   if (!aligned(out, 16) || (in_features % 4 == 0 && !aligned(x, 16)))
     return set_error(NFN_ERR_ALIGN, "x and out must be 16-byte aligned");
-  return launch_dense_act_forward(x, weight, bias, out, B, in_features, units, act, (cudaStream_t)stream);
+  return launch_dense_act_forward(x, x_mean, x_std, weight, bias, out, B, in_features, units, act, (cudaStream_t)stream);
 }
 
 int nfn_dense_act_backward(const float* x, const float* out, const float* dout, const float* weight, int64_t B,
                            int in_features, int units, int act, float* dx, float* dweight, float* dbias,
                            void* stream) {
+  return nfn_dense_act_backward_x(x, nullptr, nullptr, out, dout, weight, B, in_features, units, act, dx, dweight, dbias,
+                                  stream);
+}
+
+int nfn_dense_act_backward_x(const float* x, const float* x_mean, const float* x_std, const float* out, const float* dout,
+                             const float* weight, int64_t B, int in_features, int units, int act, float* dx,
+                             float* dweight, float* dbias, void* stream) {
+  if ((x_mean == nullptr) != (x_std == nullptr)) return set_error(NFN_ERR_NULL, "x_mean and x_std go together");
+  if (x_mean && (dx != nullptr || in_features > 4 || units > 32))
+    return set_error(NFN_ERR_UNSUPPORTED, "the fused input normalisation serves the first layer only (no dx, <= 4 inputs, <= 32 units)");
   if (!mlp_layer_supported(in_features, units, act))
     return set_error(NFN_ERR_UNSUPPORTED, "dense layer %d -> %d (act %d) is outside the fused kernels' range", in_features,
                      units, act);
@@ -527,7 +597,7 @@ int nfn_dense_act_backward(const float* x, const float* out, const float* dout, 
     return set_error(NFN_ERR_NULL, "x, out, dout, weight, dweight and dbias must be non-NULL");
   if (!aligned(out, 16) || !aligned(dout, 16) || (in_features % 4 == 0 && !aligned(x, 16)))
     return set_error(NFN_ERR_ALIGN, "x, out and dout must be 16-byte aligned");
-  return launch_dense_act_backward(x, out, dout, weight, dx, dweight, dbias, B, in_features, units, act,
+  return launch_dense_act_backward(x, x_mean, x_std, out, dout, weight, dx, dweight, dbias, B, in_features, units, act,
                                    (cudaStream_t)stream);
 }
 
@@ -564,11 +634,17 @@ static int mix_common(int K, int d, const float* t, const float* y, int64_t y_ro
 
 int nfn_mdn_forward(int n_centers, int n_dims, const float* t, const float* y, int64_t y_rows,
                     float* logp, int64_t B, void* stream) {
+  return nfn_mdn_forward_x(n_centers, n_dims, t, y, y_rows, logp, B, nullptr, stream);
+}
+
+int nfn_mdn_forward_x(int n_centers, int n_dims, const float* t, const float* y, int64_t y_rows,
+                      float* logp, int64_t B, const nfn_event_xform* xf, void* stream) {
   int rc = mix_common(n_centers, n_dims, t, y, y_rows, logp, B);
   if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
   MixArgs a{};
   a.t = t; a.y = y; a.logp = logp; a.B = B; a.g_scale = 1.0f; a.K = n_centers;
   a.y_broadcast = (y_rows == 1 && B != 1);
+  if ((rc = set_xform(a.xf, xf, n_dims)) != NFN_OK) return rc;
   return launch_mdn(n_dims, false, a, (cudaStream_t)stream);
 }
 
@@ -576,6 +652,14 @@ int nfn_mdn_forward_backward(int n_centers, int n_dims, const float* t, const fl
                              int64_t y_rows, const float* g_logp, float g_scale, float* logp,
                              float* dt, float* dy, double* logp_sum, double* dt_colsum, int64_t B,
                              void* stream) {
+  return nfn_mdn_forward_backward_x(n_centers, n_dims, t, y, y_rows, g_logp, g_scale, logp, dt, dy, logp_sum, dt_colsum, B,
+                                    nullptr, stream);
+}
+
+int nfn_mdn_forward_backward_x(int n_centers, int n_dims, const float* t, const float* y,
+                               int64_t y_rows, const float* g_logp, float g_scale, float* logp,
+                               float* dt, float* dy, double* logp_sum, double* dt_colsum, int64_t B,
+                               const nfn_event_xform* xf, void* stream) {
   int rc = mix_common(n_centers, n_dims, t, y, y_rows, logp, B);
   if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
   if (!dt) return set_error(NFN_ERR_NULL, "dt must be non-NULL");
@@ -585,17 +669,25 @@ int nfn_mdn_forward_backward(int n_centers, int n_dims, const float* t, const fl
   a.t = t; a.y = y; a.g_logp = g_logp; a.logp = logp; a.dt = dt; a.dy = dy; a.logp_sum = logp_sum;
   a.dt_colsum = dt_colsum; a.B = B; a.g_scale = g_scale; a.K = n_centers;
   a.y_broadcast = (y_rows == 1 && B != 1);
+  if ((rc = set_xform(a.xf, xf, n_dims)) != NFN_OK) return rc;
   return launch_mdn(n_dims, true, a, (cudaStream_t)stream);
 }
 
 int nfn_kmn_forward(int n_components, int n_dims, const float* t, const float* y, int64_t y_rows,
                     const float* locs, const float* scales, float* logp, int64_t B, void* stream) {
+  return nfn_kmn_forward_x(n_components, n_dims, t, y, y_rows, locs, scales, logp, B, nullptr, stream);
+}
+
+int nfn_kmn_forward_x(int n_components, int n_dims, const float* t, const float* y, int64_t y_rows,
+                      const float* locs, const float* scales, float* logp, int64_t B, const nfn_event_xform* xf,
+                      void* stream) {
   int rc = mix_common(n_components, n_dims, t, y, y_rows, logp, B);
   if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
   if (!locs || !scales) return set_error(NFN_ERR_NULL, "locs and scales must be non-NULL");
   MixArgs a{};
   a.t = t; a.y = y; a.locs = locs; a.scales = scales; a.logp = logp; a.B = B; a.g_scale = 1.0f;
   a.K = n_components; a.y_broadcast = (y_rows == 1 && B != 1);
+  if ((rc = set_xform(a.xf, xf, n_dims)) != NFN_OK) return rc;
   return launch_kmn(n_dims, false, a, (cudaStream_t)stream);
 }
 
@@ -603,6 +695,14 @@ int nfn_kmn_forward_backward(int n_components, int n_dims, const float* t, const
                              int64_t y_rows, const float* locs, const float* scales,
                              const float* g_logp, float g_scale, float* logp, float* dt, float* dy,
                              float* dscales, double* logp_sum, int64_t B, void* stream) {
+  return nfn_kmn_forward_backward_x(n_components, n_dims, t, y, y_rows, locs, scales, g_logp, g_scale, logp, dt, dy, dscales,
+                                    logp_sum, B, nullptr, stream);
+}
+
+int nfn_kmn_forward_backward_x(int n_components, int n_dims, const float* t, const float* y,
+                               int64_t y_rows, const float* locs, const float* scales,
+                               const float* g_logp, float g_scale, float* logp, float* dt, float* dy,
+                               float* dscales, double* logp_sum, int64_t B, const nfn_event_xform* xf, void* stream) {
   int rc = mix_common(n_components, n_dims, t, y, y_rows, logp, B);
   if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
   if (!locs || !scales || !dt) return set_error(NFN_ERR_NULL, "locs, scales and dt must be non-NULL");
@@ -612,6 +712,7 @@ int nfn_kmn_forward_backward(int n_components, int n_dims, const float* t, const
   a.t = t; a.y = y; a.g_logp = g_logp; a.locs = locs; a.scales = scales; a.logp = logp; a.dt = dt;
   a.dy = dy; a.dscales = dscales; a.logp_sum = logp_sum; a.B = B; a.g_scale = g_scale;
   a.K = n_components; a.y_broadcast = (y_rows == 1 && B != 1);
+  if ((rc = set_xform(a.xf, xf, n_dims)) != NFN_OK) return rc;
   return launch_kmn(n_dims, true, a, (cudaStream_t)stream);
 }
 

@@ -78,6 +78,89 @@ __host__ __device__ constexpr ChainGeometry chain_geometry(int P, bool bwd) {
   return ChainGeometry{T, nb, minb, tile * (unsigned)nb, 0, 0, 0};
 }
 
+// ---------------------------------------------------------------- event transform
+// The estimators' y pipeline, folded into the heads as a prologue / epilogue so that it costs no extra pass over
+// y or logp (reference estimators/BaseEstimator.py):
+//   kXfNormalise  y' = (y - y_mean) / y_std            (:61-69; IEEE division, like the reference's op)
+//   kXfNoise      y' += noise_std * N(0, 1)             (:66-68, training only) -- Philox4x32-10 keyed by `seed`,
+//                 counter = (global row, `offset`): reproducible, independent of the launch geometry
+//   logp_shift    added to every log-prob: -sum log y_std, the normalisation Jacobian (:55-59, :85-86)
+//   kXfExp        the output is exp(logp + logp_shift) = prob / prod y_std  (pdf, :71-75)
+// flags == 0 and logp_shift == 0 is the identity (what the plain entry points pass).  dy, where requested, is the
+// gradient with respect to the TRANSFORMED event y'.
+enum : int { kXfNormalise = 1, kXfNoise = 2, kXfExp = 4 };
+struct EventXform {
+  float mean[8];
+  float std[8];
+  float noise_std;
+  float logp_shift;
+  unsigned long long seed;
+  unsigned long long offset;
+  const unsigned long long* offset_dev;   // nullable: added to `offset` (a device-side step counter)
+  int flags;
+  int pad_;
+};
+
+NFN_DEVI void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
+                            unsigned (&out)[4]) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// D standard normals for global row r (Box-Muller on Philox words; block b of 4 normals uses counter word 3 = b)
+template <int D>
+NFN_DEVI void row_normals(const EventXform& xf, long long r, float (&n)[D]) {
+  const unsigned long long off = xf.offset + (xf.offset_dev ? __ldg(xf.offset_dev) : 0ull);
+#pragma unroll
+  for (int b = 0; b < (D + 3) / 4; ++b) {
+    unsigned w[4];
+    philox4x32_10((unsigned)r, (unsigned)((unsigned long long)r >> 32), (unsigned)off,
+                  (unsigned)(off >> 32) ^ ((unsigned)b << 28), (unsigned)xf.seed, (unsigned)(xf.seed >> 32), w);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float u1 = fmaf((float)w[2 * h], 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0, 1]
+      const float u2 = (float)w[2 * h + 1] * 2.3283064365386963e-10f;                             // [0, 1]
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float sn, cs;
+      sincospif(2.0f * u2, &sn, &cs);
+      if (4 * b + 2 * h < D) n[4 * b + 2 * h] = rad * cs;
+      if (4 * b + 2 * h + 1 < D) n[4 * b + 2 * h + 1] = rad * sn;
+    }
+  }
+}
+
+// y -> y' in place; r is the GLOBAL row of the event (the noise counter), `noise` = false for grid events
+template <int D>
+NFN_DEVI void xform_event(const EventXform& xf, long long r, float (&z)[D], bool noise = true) {
+  if (xf.flags & kXfNormalise) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) z[i] = __fdiv_rn(z[i] - xf.mean[i], xf.std[i]);
+  }
+  if (noise && (xf.flags & kXfNoise)) {
+    float n[D];
+    row_normals<D>(xf, r, n);
+#pragma unroll
+    for (int i = 0; i < D; ++i) z[i] = fmaf(xf.noise_std, n[i], z[i]);
+  }
+}
+
+// the value written to logp[]: log-prob (+ shift), or the density itself
+template <class M>
+NFN_DEVI float xform_out(const EventXform& xf, float lp) {
+  const float v = lp + xf.logp_shift;
+  if (xf.flags & kXfExp) {
+    if constexpr (M::kFast) return M::exp(v); else return expf(v);
+  }
+  return v;
+}
+
 // In-kernel all-reduce of the fp64 accumulators over NVLink peer memory (nfn_peer.cu).
 // Every rank owns one IPC-shared region of 8-byte words laid out as
 //   words[2][world][n_values][2]        (2 = step parity; 2 words per fp64 value)
@@ -122,6 +205,7 @@ struct ChainArgs {
   int grid_ny;
   int pad_;
   PeerArgs peer;
+  EventXform xf;
 };
 
 // ---------------------------------------------------------------- smem span load/store
@@ -612,6 +696,7 @@ NFN_DEVI void chain_body(const ChainArgs& a) {
     float z[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) z[i] = y_nxt[i];
+    if (a.xf.flags) xform_event<D>(a.xf, tile * T + threadIdx.x, z);
     const float g_cur = g_nxt;
     {
       const long long rn = (tile + gridDim.x) * T + threadIdx.x;
@@ -648,10 +733,11 @@ NFN_DEVI void chain_body(const ChainArgs& a) {
           for (int j = 0; j < a.grid_ny; ++j) {
             float zg[D];
             load_event<D>(a.y, j, zg);  // same address for the whole warp: one broadcast load
+            if (a.xf.flags) xform_event<D>(a.xf, j, zg, false);
             float zs[Spec::KA][D];
             LogDetAcc<M> ld;
             FwdSweep<Spec, M, V, false, 0>::run(row, zg, zs, ld);
-            a.logp[(long long)j * a.B + r] = Base::log_prob(bth, zg) + ld.nat();
+            a.logp[(long long)j * a.B + r] = xform_out<M>(a.xf, Base::log_prob(bth, zg) + ld.nat());
           }
         }
         if constexpr (P > 0) __syncthreads();
@@ -669,8 +755,9 @@ NFN_DEVI void chain_body(const ChainArgs& a) {
       if constexpr (Spec::BASE) Span<0, 2 * D, V>::load(row, bth);
       // fused kernel: sigma stays in registers (bth) for the reverse sweep
       const float lp = (BWD ? Base::log_prob_save(bth, z) : Base::log_prob(bth, z)) + ld.nat();
-      a.logp[r] = lp;
-      lsum += (double)lp;
+      const float lpo = xform_out<M>(a.xf, lp);   // + the normalisation Jacobian (or the density itself)
+      a.logp[r] = lpo;
+      lsum += (double)lpo;
       if constexpr (BWD) {
         const float cot = a.g_scale * g_cur;
         float G[D];
@@ -932,18 +1019,34 @@ struct WarpColSum {
 // a thread keeps for the reverse sweep (a proxy for its register footprint).  nb / warps > 0 override the
 // defaults (A/B sweeps through the runtime specialiser: options "tune_wnb", "tune_wwarps").
 //
-// Defaults from the sweeps on B200 (profiles/tuning_r02.md).  The fused kernel refills a buffer only after its
-// store has drained, i.e. at the END of an iteration: with 2 buffers the next tile's load latency is exposed
-// unless enough other warps cover it, with 3 it hides behind the current tile's arithmetic.
+// Defaults from the sweeps on B200 (profiles/tuning_r02.md).  What the kernels need is BYTES IN FLIGHT: the
+// loaded DRAM latency is ~2 us, so ~90 KB of loads per SM must be outstanding to stream at the HBM rate.  The
+// fused kernel refills a buffer only after its store has drained (at the END of an iteration), so of NB buffers
+// one is in the registers' hands, one is draining and NB - 2 are loading: small tiles take 16 warps x 3 buffers;
+// when that does not fit the SM's 227 KB, depth beats warps (4 buffers, as many warps as fit, whole CTAs of 4).
+// The forward kernel (nothing to store) keeps NB - 1 loads in flight per warp: 2 buffers, ~64 KB per SM.
 __host__ __device__ constexpr ChainGeometry warp_tile_geometry(int P, bool bwd, int hist, int nb = 0, int warps = 0) {
   const unsigned tile = 128u * (unsigned)(P > 0 ? P : 1);
   const unsigned budget = 227u * 1024u - 4u * 2560u;   // per SM, minus per-CTA reservations / alignment slack
+  (void)hist;
   int want = warps;
-  if (nb <= 0) nb = bwd ? ((hist >= 12 && tile * 32u <= budget) ? 2 : 3) : 2;
-  if (want <= 0) want = bwd ? (hist > 40 ? 8 : 16) : 12;
-  while (nb > 2 && (unsigned)(want * nb) * tile > budget) --nb;
+  if (bwd) {
+    if (nb <= 0) nb = (16u * 3u * tile <= budget) ? 3 : 4;
+    if (want <= 0) want = 16;
+  } else {
+    if (nb <= 0) nb = 2;
+    if (want <= 0) {
+      want = (int)(65536u / tile);
+      want = want < 4 ? 4 : (want > 8 ? 8 : want);
+    }
+  }
   int w = (int)(budget / ((unsigned)nb * tile));
+  while (w < 4 && nb > 2) {   // very wide rows: give depth back until at least one CTA of 4 warps fits
+    --nb;
+    w = (int)(budget / ((unsigned)nb * tile));
+  }
   if (w > want) w = want;
+  if (warps <= 0 && w >= 8) w = w / 4 * 4;   // defaults use whole CTAs of 4 warps
   if (w < 1) w = 1;
   const int ctas = (w + 3) / 4;
   const int nw = w / ctas;
@@ -1038,6 +1141,7 @@ NFN_DEVI void chain_body_w(const ChainArgs& a, const TensorMap* tm_t, const Tens
     float z[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) z[i] = y_nxt[i];
+    if (a.xf.flags) xform_event<D>(a.xf, wt * 32 + lane, z);
     const float g_cur = g_nxt;
     {
       const long long rn = (wt + GW) * 32 + lane;
@@ -1074,10 +1178,11 @@ NFN_DEVI void chain_body_w(const ChainArgs& a, const TensorMap* tm_t, const Tens
           for (int j = 0; j < a.grid_ny; ++j) {
             float zg[D];
             load_event<D>(a.y, j, zg);  // same address for the whole warp: one broadcast load
+            if (a.xf.flags) xform_event<D>(a.xf, j, zg, false);
             float zs[Spec::KA][D];
             LogDetAcc<M> ld;
             FwdSweep<Spec, M, V, false, 0>::run(row, zg, zs, ld);
-            a.logp[(long long)j * a.B + r] = Base::log_prob(bth, zg) + ld.nat();
+            a.logp[(long long)j * a.B + r] = xform_out<M>(a.xf, Base::log_prob(bth, zg) + ld.nat());
           }
         }
         done = true;
@@ -1091,8 +1196,9 @@ NFN_DEVI void chain_body_w(const ChainArgs& a, const TensorMap* tm_t, const Tens
       float bth[Base::NA];
       if constexpr (Spec::BASE) Span<0, 2 * D, V>::load(row, bth);
       const float lp = (BWD ? Base::log_prob_save(bth, z) : Base::log_prob(bth, z)) + ld.nat();
-      a.logp[r] = lp;
-      lsum += (double)lp;
+      const float lpo = xform_out<M>(a.xf, lp);   // + the normalisation Jacobian (or the density itself)
+      a.logp[r] = lpo;
+      lsum += (double)lpo;
       if constexpr (BWD) {
         const float cot = a.g_scale * g_cur;
         float G[D];

@@ -61,13 +61,11 @@ struct ChainKernels {
 // Which of the two kernel generations serves a launch: NFN_B200_CHAIN_IO=tma|cpasync forces one (A/B runs,
 // tests); otherwise the measured default for the row width / direction (chain_prefers_warp_tile).
 int chain_io_override();   // -1: none, 0: cp.async, 1: bulk copy / TMA
+// Measured on B200 (profiles/tuning_r02.md): the warp-tile kernels win on every BASELINE chain, both directions
+// (cfg2 fwd+bwd with column sums 69 vs 83 us, cfg3 fwd 0.63 vs 0.72 ms, cfg4 27 vs 31 us).
 __host__ __device__ constexpr bool chain_prefers_warp_tile(int P, bool bwd) {
-#ifdef NFN_WARP_TILE_DEFAULT
-  return P > 0 && (NFN_WARP_TILE_DEFAULT != 0);
-#else
   (void)bwd;
-  return false;
-#endif
+  return P > 0;
 }
 
 // 2-D tensor map over a row-major fp32 matrix [rows, P] with boxes of [32 rows x W columns] and the
@@ -360,6 +358,7 @@ struct MixArgs {
   float g_scale;
   int y_broadcast;
   int K;                // components
+  EventXform xf;
 };
 int launch_mdn(int d, bool bwd, const MixArgs& a, cudaStream_t st);
 int launch_kmn(int d, bool bwd, const MixArgs& a, cudaStream_t st);
@@ -368,9 +367,11 @@ int launch_colsum(const float* dt, long long B, int P, double* out, cudaStream_t
 
 // hidden layers of the conditioning network (nfn_mlp.cu)
 int mlp_layer_supported(int K, int N, int act);
-int launch_dense_act_forward(const float* x, const float* w, const float* b, float* out, long long B, int K, int N,
-                             int act, cudaStream_t st);
-int launch_dense_act_backward(const float* x, const float* out, const float* dout, const float* w, float* dx,
-                              float* dW, float* db, long long B, int K, int N, int act, cudaStream_t st);
+// xmean / xstd (device, [K], nullable together): the estimators' input normalisation fused into the first layer
+int launch_dense_act_forward(const float* x, const float* xmean, const float* xstd, const float* w, const float* b,
+                             float* out, long long B, int K, int N, int act, cudaStream_t st);
+int launch_dense_act_backward(const float* x, const float* xmean, const float* xstd, const float* out, const float* dout,
+                              const float* w, float* dx, float* dW, float* db, long long B, int K, int N, int act,
+                              cudaStream_t st);
 
 }  // namespace nfn

@@ -35,6 +35,7 @@ struct DenseArgs {
   long long B;
   float g_scale;
   int y_broadcast;
+  EventXform xf;
 };
 
 // ---------------------------------------------------------------- tensor-core helpers
@@ -187,6 +188,7 @@ NFN_DEVI void dense_chain_body(const DenseArgs& a) {
     float z[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) z[i] = y_nxt[i];
+    if (a.xf.flags) xform_event<D>(a.xf, tile * T + tid, z);
     const float g_cur = g_nxt;
     {
       const long long nxt = tile + gridDim.x;
@@ -262,7 +264,7 @@ NFN_DEVI void dense_chain_body(const DenseArgs& a) {
       using Base = BaseDist<D, Spec::BASE, M>;
       float bth[Base::NA];
       if constexpr (Spec::BASE) Span<0, 2 * D, V>::load(row, bth);
-      const float lp = (BWD ? Base::log_prob_save(bth, z) : Base::log_prob(bth, z)) + ld.nat();
+      const float lp = xform_out<M>(a.xf, (BWD ? Base::log_prob_save(bth, z) : Base::log_prob(bth, z)) + ld.nat());
       a.logp[r] = lp;
       lsum += (double)lp;
       if constexpr (BWD) {

@@ -548,6 +548,7 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
       float z[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) z[i] = y_nxt[i];
+      if (a.xf.flags) xform_event<D>(a.xf, tile * T + tid, z);
       const float g_cur = g_nxt;
 
       // ---- t row out of TMEM (+ bias): thread r owns row r of the accumulator
@@ -575,7 +576,7 @@ NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
         using Base = BaseDist<D, Spec::BASE, M>;
         float bth[Base::NA];
         if constexpr (Spec::BASE) Span<0, 2 * D, V>::load(row, bth);
-        const float lp = (BWD ? Base::log_prob_save(bth, z) : Base::log_prob(bth, z)) + ld.nat();
+        const float lp = xform_out<M>(a.xf, (BWD ? Base::log_prob_save(bth, z) : Base::log_prob(bth, z)) + ld.nat());
         a.logp[r] = lp;
         {  // compensated fp32 sum (fp64 adds are 1/64 rate here): ls_hi - ls_lo carries ~48 bits
           const float yv = lp - ls_lo, tv = ls_hi + yv;

@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(128) chain_generic_kernel(const ChainArgs a, c
         for (int j = 0; j < a.grid_ny; ++j) {
           float zg[D];
           load_event<D>(a.y, j, zg);
+          if (a.xf.flags) xform_event<D>(a.xf, j, zg, false);
           LogDetAcc<M> ldg;
           for (int k = 0; k < c.K; ++k) {
             const float* p = row + c.off[k];
@@ -58,13 +59,14 @@ __global__ void __launch_bounds__(128) chain_generic_kernel(const ChainArgs a, c
             float dummy[1] = {0.0f};
             lpg = BaseDist<D, false, M>::log_prob(dummy, zg) + ldg.nat();
           }
-          a.logp[(long long)j * a.B + r] = lpg;
+          a.logp[(long long)j * a.B + r] = xform_out<M>(a.xf, lpg);
         }
         continue;
       }
     }
     float z[D];
     load_event<D>(a.y, a.y_broadcast ? 0 : r, z);
+    if (a.xf.flags) xform_event<D>(a.xf, r, z);
     float zs[BWD ? NFN_MAX_FLOWS * D : 1];
     LogDetAcc<M> ld;
     for (int k = 0; k < c.K; ++k) {
@@ -100,8 +102,9 @@ __global__ void __launch_bounds__(128) chain_generic_kernel(const ChainArgs a, c
       float dummy[1] = {0.0f};
       lp = BaseDist<D, false, M>::log_prob(dummy, z) + ld.nat();
     }
-    a.logp[r] = lp;
-    lsum += (double)lp;
+    const float lpo = xform_out<M>(a.xf, lp);
+    a.logp[r] = lpo;
+    lsum += (double)lpo;
     if constexpr (BWD) {
       float* drow = a.dt + r * c.P;
       const float cot = a.g_scale * (a.g_logp ? __ldg(a.g_logp + r) : 1.0f);

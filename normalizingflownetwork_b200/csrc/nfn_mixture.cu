@@ -186,6 +186,7 @@ struct EventPrefetch {
   NFN_DEVI void rotate(const MixArgs& a, long long tile, float (&y)[D], float& g) {
 #pragma unroll
     for (int i = 0; i < D; ++i) y[i] = y_nxt[i];
+    if (a.xf.flags) xform_event<D>(a.xf, tile * kMixT + threadIdx.x, y);
     g = g_nxt;
     fetch(a, (tile + gridDim.x) * kMixT + threadIdx.x);
   }
@@ -278,8 +279,9 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) mdn_kernel(const MixArgs a
       }
       const float top2 = m + M::lg2(s);  // log2 sum_k exp(logit_k + log N_k + d/2 log 2pi)
       const float logp = (top2 - lse2) * kLn2 - (float)D * kHalfLog2Pi;
-      a.logp[r] = logp;
-      lsum += (double)logp;
+      const float lpo = xform_out<M>(a.xf, logp);
+      a.logp[r] = lpo;
+      lsum += (double)lpo;
       if constexpr (BWD) {
         const float cot = a.g_scale * g_cur;
         float dy[D];
@@ -405,8 +407,9 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) kmn_kernel(const MixArgs a
       lse2 = lm + M::lg2(ls);
       top2 = m + M::lg2(s);
       const float logp = (top2 - lse2) * kLn2 - (float)D * kHalfLog2Pi;
-      a.logp[r] = logp;
-      lsum += (double)logp;
+      const float lpo = xform_out<M>(a.xf, logp);
+      a.logp[r] = lpo;
+      lsum += (double)lpo;
     }
     if constexpr (BWD) {
       if (valid) cot = a.g_scale * g_cur;

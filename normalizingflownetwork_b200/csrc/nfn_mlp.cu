@@ -86,7 +86,8 @@ __host__ __device__ constexpr int pad4(int n) { return (n + 3) / 4 * 4; }
 // KC > 0 fixes the input width at compile time (the common 16 -> 16 layer: a quarter of the instructions of the
 // runtime-K version were address arithmetic)
 template <int N, int ACT, int KC>
-__global__ void __launch_bounds__(kT) dense_act_fwd(const float* __restrict__ x, const float* __restrict__ weight,
+__global__ void __launch_bounds__(kT) dense_act_fwd(const float* __restrict__ x, const float* __restrict__ xmean,
+                                                   const float* __restrict__ xstd, const float* __restrict__ weight,
                                                    const float* __restrict__ bias, float* __restrict__ out,
                                                    long long B, int K_rt) {
   const int K = KC > 0 ? KC : K_rt;
@@ -114,7 +115,10 @@ __global__ void __launch_bounds__(kT) dense_act_fwd(const float* __restrict__ x,
     for (int n = 0; n < N; ++n) acc[n] = sb[n];
     const float* xr = sX + threadIdx.x * SX;
     for (int k = 0; k < K; ++k) {
-      const float a = xr[k];
+      float a = xr[k];
+      // input normalisation of the estimators' first layer, fused: (x - x_mean) / (x_std + 1e-8)
+      // (reference estimators/MaximumLikelihoodNNEstimator.py:40)
+      if (xmean) a = __fdiv_rn(a - __ldg(xmean + k), __ldg(xstd + k) + 1e-8f);
       const float4* w = reinterpret_cast<const float4*>(sW + k * N);
 #pragma unroll
       for (int c = 0; c < N / 4; ++c) {
@@ -298,7 +302,8 @@ __global__ void __launch_bounds__(kT, 4) dense_act_bwd(const float* __restrict__
 // sum_r dpre[r][n] -- which each thread accumulates in registers over its rows; warps meet with shuffles,
 // one atomic per entry per warp at the end.  No shared memory, no barriers.
 template <int N, int ACT, int KS>
-__global__ void __launch_bounds__(kT) dense_act_bwd_first(const float* __restrict__ x, const float* __restrict__ out,
+__global__ void __launch_bounds__(kT) dense_act_bwd_first(const float* __restrict__ x, const float* __restrict__ xmean,
+                                                         const float* __restrict__ xstd, const float* __restrict__ out,
                                                          const float* __restrict__ dout, float* __restrict__ dW,
                                                          float* __restrict__ db, long long B, int K) {
   float gw[KS][N], gb[N];
@@ -311,7 +316,10 @@ __global__ void __launch_bounds__(kT) dense_act_bwd_first(const float* __restric
   for (long long r = (long long)blockIdx.x * kT + threadIdx.x; r < B; r += (long long)gridDim.x * kT) {
     float xs[KS];
 #pragma unroll
-    for (int k = 0; k < KS; ++k) xs[k] = (k < K) ? __ldg(x + r * K + k) : 0.0f;
+    for (int k = 0; k < KS; ++k) {
+      xs[k] = (k < K) ? __ldg(x + r * K + k) : 0.0f;
+      if (xmean && k < K) xs[k] = __fdiv_rn(xs[k] - __ldg(xmean + k), __ldg(xstd + k) + 1e-8f);
+    }
     const float4* po = reinterpret_cast<const float4*>(out + r * N);
     const float4* pg = reinterpret_cast<const float4*>(dout + r * N);
 #pragma unroll
@@ -356,20 +364,21 @@ __global__ void __launch_bounds__(kT) dense_act_bwd_first(const float* __restric
 }
 
 template <int N, int ACT>
-cudaError_t launch_bwd_first(const float* x, const float* out, const float* dout, float* dW, float* db, long long B, int K,
-                             cudaStream_t st) {
+cudaError_t launch_bwd_first(const float* x, const float* xmean, const float* xstd, const float* out, const float* dout,
+                             float* dW, float* db, long long B, int K, cudaStream_t st) {
   const DeviceInfo& di = device_info();
   const long long ntiles = (B + kT - 1) / kT;
   long long grid = (long long)di.sm_count * 4;
   if (grid > ntiles) grid = ntiles;
-  if (K == 1) dense_act_bwd_first<N, ACT, 1><<<(unsigned)grid, kT, 0, st>>>(x, out, dout, dW, db, B, K);
-  else dense_act_bwd_first<N, ACT, 4><<<(unsigned)grid, kT, 0, st>>>(x, out, dout, dW, db, B, K);
+  if (K == 1) dense_act_bwd_first<N, ACT, 1><<<(unsigned)grid, kT, 0, st>>>(x, xmean, xstd, out, dout, dW, db, B, K);
+  else dense_act_bwd_first<N, ACT, 4><<<(unsigned)grid, kT, 0, st>>>(x, xmean, xstd, out, dout, dW, db, B, K);
   count_launch();
   return cudaGetLastError();
 }
 
 template <int N, int ACT>
-cudaError_t launch_fwd(const float* x, const float* w, const float* b, float* out, long long B, int K, cudaStream_t st) {
+cudaError_t launch_fwd(const float* x, const float* xmean, const float* xstd, const float* w, const float* b, float* out,
+                       long long B, int K, cudaStream_t st) {
   const DeviceInfo& di = device_info();
   const size_t smem = (size_t)(pad4(K * N) + N + kT * (pad4(K) + 4) + kT * (N + 4)) * sizeof(float);
   auto kern = (K == 16) ? dense_act_fwd<N, ACT, 16> : dense_act_fwd<N, ACT, 0>;
@@ -384,7 +393,7 @@ cudaError_t launch_fwd(const float* x, const float* w, const float* b, float* ou
   const long long ntiles = (B + kT - 1) / kT;
   long long grid = (long long)di.sm_count * 6;
   if (grid > ntiles) grid = ntiles;
-  kern<<<(unsigned)grid, kT, smem, st>>>(x, w, b, out, B, K);
+  kern<<<(unsigned)grid, kT, smem, st>>>(x, xmean, xstd, w, b, out, B, K);
   count_launch();
   return cudaGetLastError();
 }
@@ -414,28 +423,31 @@ cudaError_t launch_bwd(const float* x, const float* out, const float* dout, cons
 }
 
 template <int N>
-cudaError_t dispatch_fwd(int act, const float* x, const float* w, const float* b, float* out, long long B, int K,
-                         cudaStream_t st) {
+cudaError_t dispatch_fwd(int act, const float* x, const float* xmean, const float* xstd, const float* w, const float* b,
+                         float* out, long long B, int K, cudaStream_t st) {
   switch (act) {
-    case kLinear: return launch_fwd<N, kLinear>(x, w, b, out, B, K, st);
-    case kTanh: return launch_fwd<N, kTanh>(x, w, b, out, B, K, st);
-    case kRelu: return launch_fwd<N, kRelu>(x, w, b, out, B, K, st);
-    case kSigmoid: return launch_fwd<N, kSigmoid>(x, w, b, out, B, K, st);
-    default: return launch_fwd<N, kElu>(x, w, b, out, B, K, st);
+    case kLinear: return launch_fwd<N, kLinear>(x, xmean, xstd, w, b, out, B, K, st);
+    case kTanh: return launch_fwd<N, kTanh>(x, xmean, xstd, w, b, out, B, K, st);
+    case kRelu: return launch_fwd<N, kRelu>(x, xmean, xstd, w, b, out, B, K, st);
+    case kSigmoid: return launch_fwd<N, kSigmoid>(x, xmean, xstd, w, b, out, B, K, st);
+    default: return launch_fwd<N, kElu>(x, xmean, xstd, w, b, out, B, K, st);
   }
 }
 
 template <int N, int PER>
-cudaError_t dispatch_bwd(int act, const float* x, const float* out, const float* dout, const float* w, float* dx,
-                         float* dW, float* db, long long B, int K, cudaStream_t st) {
+cudaError_t dispatch_bwd(int act, const float* x, const float* xmean, const float* xstd, const float* out,
+                         const float* dout, const float* w, float* dx, float* dW, float* db, long long B, int K,
+                         cudaStream_t st) {
+  // the fused input normalisation exists where it is used: first layer of the network (few inputs, no input gradient)
+  if (xmean && !(N <= 32 && dx == nullptr && K <= 4)) return cudaErrorNotSupported;
   if constexpr (N <= 32) {
     if (dx == nullptr && K <= 4) {   // first layer of the network: streaming reduction, no staging
       switch (act) {
-        case kLinear: return launch_bwd_first<N, kLinear>(x, out, dout, dW, db, B, K, st);
-        case kTanh: return launch_bwd_first<N, kTanh>(x, out, dout, dW, db, B, K, st);
-        case kRelu: return launch_bwd_first<N, kRelu>(x, out, dout, dW, db, B, K, st);
-        case kSigmoid: return launch_bwd_first<N, kSigmoid>(x, out, dout, dW, db, B, K, st);
-        default: return launch_bwd_first<N, kElu>(x, out, dout, dW, db, B, K, st);
+        case kLinear: return launch_bwd_first<N, kLinear>(x, xmean, xstd, out, dout, dW, db, B, K, st);
+        case kTanh: return launch_bwd_first<N, kTanh>(x, xmean, xstd, out, dout, dW, db, B, K, st);
+        case kRelu: return launch_bwd_first<N, kRelu>(x, xmean, xstd, out, dout, dW, db, B, K, st);
+        case kSigmoid: return launch_bwd_first<N, kSigmoid>(x, xmean, xstd, out, dout, dW, db, B, K, st);
+        default: return launch_bwd_first<N, kElu>(x, xmean, xstd, out, dout, dW, db, B, K, st);
       }
     }
   }
@@ -454,36 +466,37 @@ int mlp_layer_supported(int K, int N, int act) {
   return K >= 1 && K <= 64 && (N == 8 || N == 16 || N == 32 || N == 64) && act >= 0 && act <= 4;
 }
 
-int launch_dense_act_forward(const float* x, const float* w, const float* b, float* out, long long B, int K, int N,
-                             int act, cudaStream_t st) {
+int launch_dense_act_forward(const float* x, const float* xmean, const float* xstd, const float* w, const float* b,
+                             float* out, long long B, int K, int N, int act, cudaStream_t st) {
   cudaError_t e;
   switch (N) {
-    case 8: e = dispatch_fwd<8>(act, x, w, b, out, B, K, st); break;
-    case 16: e = dispatch_fwd<16>(act, x, w, b, out, B, K, st); break;
-    case 32: e = dispatch_fwd<32>(act, x, w, b, out, B, K, st); break;
-    default: e = dispatch_fwd<64>(act, x, w, b, out, B, K, st); break;
+    case 8: e = dispatch_fwd<8>(act, x, xmean, xstd, w, b, out, B, K, st); break;
+    case 16: e = dispatch_fwd<16>(act, x, xmean, xstd, w, b, out, B, K, st); break;
+    case 32: e = dispatch_fwd<32>(act, x, xmean, xstd, w, b, out, B, K, st); break;
+    default: e = dispatch_fwd<64>(act, x, xmean, xstd, w, b, out, B, K, st); break;
   }
   return cuda_error(e, "dense_act_fwd");
 }
 
-int launch_dense_act_backward(const float* x, const float* out, const float* dout, const float* w, float* dx,
-                              float* dW, float* db, long long B, int K, int N, int act, cudaStream_t st) {
+int launch_dense_act_backward(const float* x, const float* xmean, const float* xstd, const float* out, const float* dout,
+                              const float* w, float* dx, float* dW, float* db, long long B, int K, int N, int act,
+                              cudaStream_t st) {
   cudaError_t e;
   // 4 x 4 blocks of the weight gradient per thread: one while ceil(K/4) * N/4 <= 128, else two (K * N <= 4096)
   const int G = ((K + 3) / 4) * (N / 4);
   if (G <= kT) {
     switch (N) {
-      case 8: e = dispatch_bwd<8, 1>(act, x, out, dout, w, dx, dW, db, B, K, st); break;
-      case 16: e = dispatch_bwd<16, 1>(act, x, out, dout, w, dx, dW, db, B, K, st); break;
-      case 32: e = dispatch_bwd<32, 1>(act, x, out, dout, w, dx, dW, db, B, K, st); break;
-      default: e = dispatch_bwd<64, 1>(act, x, out, dout, w, dx, dW, db, B, K, st); break;
+      case 8: e = dispatch_bwd<8, 1>(act, x, xmean, xstd, out, dout, w, dx, dW, db, B, K, st); break;
+      case 16: e = dispatch_bwd<16, 1>(act, x, xmean, xstd, out, dout, w, dx, dW, db, B, K, st); break;
+      case 32: e = dispatch_bwd<32, 1>(act, x, xmean, xstd, out, dout, w, dx, dW, db, B, K, st); break;
+      default: e = dispatch_bwd<64, 1>(act, x, xmean, xstd, out, dout, w, dx, dW, db, B, K, st); break;
     }
   } else {
     switch (N) {
-      case 8: e = dispatch_bwd<8, 2>(act, x, out, dout, w, dx, dW, db, B, K, st); break;
-      case 16: e = dispatch_bwd<16, 2>(act, x, out, dout, w, dx, dW, db, B, K, st); break;
-      case 32: e = dispatch_bwd<32, 2>(act, x, out, dout, w, dx, dW, db, B, K, st); break;
-      default: e = dispatch_bwd<64, 2>(act, x, out, dout, w, dx, dW, db, B, K, st); break;
+      case 8: e = dispatch_bwd<8, 2>(act, x, xmean, xstd, out, dout, w, dx, dW, db, B, K, st); break;
+      case 16: e = dispatch_bwd<16, 2>(act, x, xmean, xstd, out, dout, w, dx, dW, db, B, K, st); break;
+      case 32: e = dispatch_bwd<32, 2>(act, x, xmean, xstd, out, dout, w, dx, dW, db, B, K, st); break;
+      default: e = dispatch_bwd<64, 2>(act, x, xmean, xstd, out, dout, w, dx, dW, db, B, K, st); break;
     }
   }
   return cuda_error(e, "dense_act_bwd");

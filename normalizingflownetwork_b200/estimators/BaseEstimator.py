@@ -30,14 +30,28 @@ def default_device():
 
 
 class _Normalise(torch.nn.Module):
-    """Lambda x: (x - x_mean) / (x_std + 1e-8)  (MaximumLikelihoodNNEstimator.py:40)."""
+    """Lambda x: (x - x_mean) / (x_std + 1e-8)  (MaximumLikelihoodNNEstimator.py:40).
+
+    When the next Dense layer can take the normalisation as a fused prologue of its own kernel (nfn_mlp.cu:
+    first layer, <= 4 inputs, no x noise this call) this module passes x through untouched and the layer
+    reads the statistics itself (``fused_into`` is set by the estimator)."""
 
     def __init__(self, owner):
         super().__init__()
         self._owner = [owner]  # not a submodule
+        self.fused_into = None  # the _Dense layer that normalises on load, or None
+
+    def fused_now(self, x):
+        o = self._owner[0]
+        layer = self.fused_into
+        return (layer is not None and x.is_cuda and x.dim() == 2 and not (o.training and o.x_noise_std > 0.0)
+                and layer.can_fuse_xnorm(x))
 
     def forward(self, x):
         o = self._owner[0]
+        if self.fused_now(x):
+            self.fused_into.xnorm = (o.x_mean, o.x_std)   # consumed (and cleared) by the layer's next call
+            return x
         return (x - o.x_mean) / (o.x_std + 1e-8)
 
 
@@ -92,6 +106,7 @@ class BaseEstimator(torch.nn.Module):
                 setattr(self, name, torch.zeros(tuple(src.shape), dtype=cur.dtype, device=cur.device))
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                                       error_msgs)
+        self._invalidate_stats()
 
     # ------------------------------------------------------------------ forward
     def _to_dev(self, a):
@@ -158,6 +173,7 @@ class BaseEstimator(torch.nn.Module):
                 cur.copy_(new)
             else:
                 setattr(self, name, new)
+        self._invalidate_stats()
 
     def _assign_noise_regularisation(self, n_dims, n_datapoints):
         assert self.noise_fn_type in ["rule_of_thumb", "fixed_rate"]
@@ -178,6 +194,39 @@ class BaseEstimator(torch.nn.Module):
             y = y + self.y_noise_std * torch.randn_like(y)
         return y
 
+    # ------------------------------------------------------------------ fused y pipeline
+    def _invalidate_stats(self):
+        self._stats_host = None
+        self._stats_version = getattr(self, "_stats_version", 0) + 1
+
+    def _y_stats_host(self):
+        """Host copies of (y_mean, y_std, sum log y_std): kernel arguments by value, read back from the device once
+        per change of the statistics (fit / load_state_dict), never on a scoring or training call."""
+        st = getattr(self, "_stats_host", None)
+        if st is None:
+            mean = self.y_mean.detach().double().cpu().reshape(-1)
+            std = self.y_std.detach().double().cpu().reshape(-1)
+            # the Jacobian term in float32 like the reference's tf.reduce_sum(tf.math.log(y_std))
+            shift = float(torch.sum(torch.log(self.y_std.detach().float())).cpu())
+            st = (mean.tolist(), std.tolist(), shift)
+            self._stats_host = st
+        return st
+
+    def _xform(self, n_dims, training=False, exp_out=False):
+        """The event transform of one head launch: normalisation, training-only noise, -sum log y_std, exp."""
+        mean, std, shift = self._y_stats_host()
+        if len(mean) != n_dims:   # [1] placeholders before the first fit
+            mean, std = [mean[0]] * n_dims, [std[0]] * n_dims
+        noise = float(self.y_noise_std) if training else 0.0
+        ctr = None
+        if noise > 0.0:
+            if getattr(self, "_noise_ctr", None) is None:
+                self._noise_ctr = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self._noise_ctr += 1      # device-side step counter: a captured graph draws fresh noise per replay
+            ctr = self._noise_ctr
+        return F.make_xform(n_dims, mean, std, logp_shift=-shift, noise_std=noise, seed=self.random_seed,
+                            offset_dev=ctr, exp_out=exp_out)
+
     def _get_input_model(self):
         """The reference's y input model as a callable ``(y, training=False)``: normalisation followed by
         noise that is active in training only (BaseEstimator.py:61-69, tests/test_noise_reg.py:55-75)."""
@@ -187,21 +236,22 @@ class BaseEstimator(torch.nn.Module):
         return torch.sum(torch.log(self.y_std))
 
     # ------------------------------------------------------------------ head: fused fwd + reverse sweep
-    def _head_forward_backward(self, t, y, g_scale, logp_sum):
+    def _head_forward_backward(self, t, y, g_scale, logp_sum, xform=None):
         """Launches the fused kernel of the head; returns dt (and accumulates grads of the
-        head's own trainable parameters, i.e. the KMN bandwidths)."""
+        head's own trainable parameters, i.e. the KMN bandwidths).  With ``xform`` y is the RAW event and
+        ``logp_sum`` receives sum(logp - sum log y_std)."""
         layer = self.dist_layer
         td = t.detach()
         if isinstance(layer, InverseNormalizingFlowLayer):
             _, dt, _ = F.chain_forward_backward(td, y, layer._flow_types, layer._n_dims, layer._trainable_base_dist,
-                                                g_scale=g_scale, logp_sum=logp_sum)
+                                                g_scale=g_scale, logp_sum=logp_sum, xform=xform)
         elif isinstance(layer, GaussianMixtureLayer):
             _, dt, _ = F.mdn_forward_backward(td, y, layer._n_centers, layer._n_dims, g_scale=g_scale,
-                                              logp_sum=logp_sum)
+                                              logp_sum=logp_sum, xform=xform)
         elif isinstance(layer, GaussianKernelsLayer):
             scales = layer.scale_model()
             _, dt, _, dsc = F.kmn_forward_backward(td, y, layer.locs, scales.detach(), g_scale=g_scale,
-                                                   logp_sum=logp_sum)
+                                                   logp_sum=logp_sum, xform=xform)
             if scales.requires_grad:
                 scales.backward(dsc)
         else:
@@ -219,7 +269,10 @@ class BaseEstimator(torch.nn.Module):
         B = xb.shape[0]
         Bg = global_batch or B
         self.optimizer.zero_grad(set_to_none=True)
-        y = self._y_input(yb, training=True)
+        # y stays RAW: normalisation, the training-only noise and the -sum log y_std Jacobian run inside the head
+        # kernel (reference BaseEstimator.py:55-69), so logp_sum already is sum_b(log p_b - sum log y_std)
+        y = self._to_dev(yb)
+        xf = self._xform(y.shape[1], training=True)
         logp_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
         world = dist.get_world_size() if dist.is_initialized() else 1
         lin = self._fusable_last_layer()
@@ -230,14 +283,14 @@ class BaseEstimator(torch.nn.Module):
             h = self.hidden_from_x(xb)
             _, dh, dW, db = F.dense_chain_forward_backward(
                 h.detach(), lin.weight.detach().t().contiguous(), lin.bias.detach(), y, layer._flow_types,
-                layer._n_dims, layer._trainable_base_dist, g_scale=-1.0 / Bg, logp_sum=logp_sum)
+                layer._n_dims, layer._trainable_base_dist, g_scale=-1.0 / Bg, logp_sum=logp_sum, xform=xf)
             lin.weight.grad = dW.t().contiguous()
             lin.bias.grad = db
             if h.requires_grad:
                 h.backward(dh)
         else:
             t = self.params_from_x(xb)
-            dt = self._head_forward_backward(t, y, -1.0 / Bg, logp_sum)
+            dt = self._head_forward_backward(t, y, -1.0 / Bg, logp_sum, xform=xf)
             extra = self._extra_loss()
             if extra is not None:
                 # the regulariser is replicated on every rank: weight 1/world so that the summed
@@ -249,7 +302,7 @@ class BaseEstimator(torch.nn.Module):
         if world > 1:
             self._allreduce_grads(logp_sum)
         self.optimizer.step()
-        loss = -logp_sum.to(torch.float32) / Bg + self._log_ystd_sum()
+        loss = -logp_sum.to(torch.float32) / Bg
         if extra is not None:
             loss = loss + extra.detach()
         return loss.reshape(())
@@ -296,6 +349,8 @@ class BaseEstimator(torch.nn.Module):
                         else:
                             v.zero_()
         self._graph_batch = batch_size
+        # the head kernels take the normalisation statistics BY VALUE: a captured step is tied to them
+        self._graph_stats_version = getattr(self, "_stats_version", 0)
         return self
 
     def train_step_graphed(self, xb, yb):
@@ -321,12 +376,16 @@ class BaseEstimator(torch.nn.Module):
         self._score_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._score_graph):
             self._score_out = self.log_pdf(self._sx, self._sy)
+        self._score_stats_version = getattr(self, "_stats_version", 0)
         return self
 
     def log_pdf_graphed(self, x, y):
         """Replay the captured scoring graph on a new batch of the captured shape (device tensors, or host
         arrays which are copied in); the returned tensor is the graph's static output buffer (clone it to
         keep it across replays)."""
+        if getattr(self, "_score_stats_version", None) != getattr(self, "_stats_version", 0):
+            # new normalisation statistics since the capture (they are kernel arguments by value): capture again
+            self.capture_log_pdf(self._sx.shape[0], self._sx.shape[1], self._sy.shape[1])
         self._sx.copy_(x if torch.is_tensor(x) else torch.as_tensor(np.asarray(x, dtype=np.float32)))
         self._sy.copy_(y if torch.is_tensor(y) else torch.as_tensor(np.asarray(y, dtype=np.float32)))
         self._score_graph.replay()
@@ -359,7 +418,8 @@ class BaseEstimator(torch.nn.Module):
         gen = torch.Generator(device="cpu").manual_seed(self.random_seed)
         self.stop_training = False
         if cuda_graph and world == 1 and n >= batch_size:
-            if getattr(self, "_graph_batch", None) != batch_size:
+            if (getattr(self, "_graph_batch", None) != batch_size
+                    or getattr(self, "_graph_stats_version", None) != getattr(self, "_stats_version", 0)):
                 self.capture_train_step(batch_size, xd.shape[1], yd.shape[1])
         else:
             cuda_graph = False
@@ -392,6 +452,9 @@ class BaseEstimator(torch.nn.Module):
     def _neg_log_likelihood(self, x, y, training=False):
         """Per-sample NLL incl. the normalisation Jacobian (BaseEstimator.py:55-59)."""
         dist_ = self.forward(x, training=training)
+        if not training and hasattr(dist_, "log_prob_x"):   # one launch: y pipeline fused into the head
+            yd = self._to_dev(y)
+            return -dist_.log_prob_x(yd, self._xform(yd.shape[-1]))
         return -dist_.log_prob(self._y_input(y, training)) + self._log_ystd_sum()
 
     def _get_neg_log_likelihood(self):
@@ -411,7 +474,10 @@ class BaseEstimator(torch.nn.Module):
         assert tuple(np.shape(x)) == tuple(np.shape(y))
         with torch.no_grad():
             output = self.forward(x)
-            y_circ = (self._to_dev(y) - self.y_mean) / self.y_std
+            yd = self._to_dev(y)
+            if hasattr(output, "log_prob_x"):   # exp(log p - sum log y_std) written by the kernel itself
+                return output.log_prob_x(yd, self._xform(yd.shape[-1], exp_out=True))
+            y_circ = (yd - self.y_mean) / self.y_std
             return output.prob(y_circ) / torch.prod(self.y_std)
 
     def pdf_grid(self, x, y_values):
@@ -419,11 +485,11 @@ class BaseEstimator(torch.nn.Module):
         loop (evaluation/visualization/flow_plotting.py:33-53) as ONE kernel launch for NF heads."""
         with torch.no_grad():
             output = self.forward(x)
-            y_circ = (self._to_dev(np.asarray(y_values, np.float32).reshape(-1, self.y_mean.numel())) - self.y_mean) / self.y_std
+            y_raw = self._to_dev(np.asarray(y_values, np.float32).reshape(-1, self.y_mean.numel()))
             if hasattr(output, "log_prob_grid"):
-                lp = output.log_prob_grid(y_circ)
-            else:
-                lp = torch.stack([output.log_prob(y_circ[i:i + 1]) for i in range(y_circ.shape[0])])
+                return output.log_prob_grid(y_raw, xform=self._xform(y_raw.shape[-1], exp_out=True))
+            y_circ = (y_raw - self.y_mean) / self.y_std
+            lp = torch.stack([output.log_prob(y_circ[i:i + 1]) for i in range(y_circ.shape[0])])
             return torch.exp(lp - self._log_ystd_sum())
 
     def log_pdf(self, x, y):
@@ -433,5 +499,8 @@ class BaseEstimator(torch.nn.Module):
         with torch.no_grad():
             output = self.forward(x)
             assert output.event_shape == y.shape[-1]
-            y_circ = (self._to_dev(y) - self.y_mean) / self.y_std
+            yd = self._to_dev(y)
+            if hasattr(output, "log_prob_x"):   # normalisation and -sum log y_std inside the head kernel
+                return output.log_prob_x(yd, self._xform(yd.shape[-1]))
+            y_circ = (yd - self.y_mean) / self.y_std
             return output.log_prob(y_circ) - self._log_ystd_sum()

@@ -169,16 +169,17 @@ class BayesianNNEstimator(BaseEstimator):
         Bg = global_batch or B
         self.optimizer.zero_grad(set_to_none=True)
         t = self.params_from_x_draws(xb, S)
-        y = self._y_input(yb, training=True).repeat(S, 1)
+        # raw y: normalisation, training noise (independent per folded row) and the Jacobian run in the head kernel
+        y = self._to_dev(yb).repeat(S, 1)
         logp_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
-        dt = self._head_forward_backward(t, y, -1.0 / (S * Bg), logp_sum)
+        dt = self._head_forward_backward(t, y, -1.0 / (S * Bg), logp_sum, xform=self._xform(y.shape[1], training=True))
         extra = self._extra_loss()
         world = dist.get_world_size() if dist.is_initialized() else 1
         torch.autograd.backward([t, extra], [dt, torch.full_like(extra, 1.0 / world)])
         if world > 1:
             self._allreduce_grads(logp_sum)
         self.optimizer.step()
-        loss = -logp_sum.to(torch.float32) / (S * Bg) + self._log_ystd_sum() + extra.detach()
+        loss = -logp_sum.to(torch.float32) / (S * Bg) + extra.detach()
         return loss.reshape(())
 
     def _extra_loss(self):
@@ -197,7 +198,7 @@ class BayesianNNEstimator(BaseEstimator):
         """log (1/S) sum_s p(y | x, w_s) per sample, S draws folded into the batch."""
         S = posterior_draws or (1 if self.map_mode else 50)
         x = self._to_dev(np.asarray(x_data, np.float32) if not torch.is_tensor(x_data) else x_data)
-        y = self._y_input(y_data, training=False)
+        y = self._to_dev(np.asarray(y_data, np.float32) if not torch.is_tensor(y_data) else y_data)
         B = x.shape[0]
         chunk = max(1, max_rows // S)
         out = torch.empty(B, dtype=torch.float32, device=self.device)
@@ -207,7 +208,7 @@ class BayesianNNEstimator(BaseEstimator):
                 hi = min(B, lo + chunk)
                 t = self.params_from_x_draws(x[lo:hi], S)
                 yy = y[lo:hi].repeat(S, 1)
-                logp = self.dist_layer(t).log_prob(yy) - self._log_ystd_sum()
+                logp = self.dist_layer(t).log_prob_x(yy, self._xform(yy.shape[1]))
                 out[lo:hi] = F.logmeanexp_draws(logp.view(S, hi - lo))
         return out
 

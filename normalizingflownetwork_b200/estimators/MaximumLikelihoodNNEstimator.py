@@ -19,6 +19,7 @@ class _Dense(torch.nn.Module):
         self._activation = activation
         self._seed = seed
         self.fused = True   # one kernel each way for the layer (csrc/nfn_mlp.cu) when its shape allows
+        self.xnorm = None   # (x_mean, x_std) handed over by _Normalise for THIS call: normalise on load
 
     def forward(self, x):
         # Glorot-initialise only a weight that does not exist yet: after load_state_dict() the lazy layer has
@@ -34,10 +35,23 @@ class _Dense(torch.nn.Module):
                 self.linear.weight.copy_(w)
                 self.linear.bias.zero_()
         lin = self.linear
+        xnorm, self.xnorm = self.xnorm, None
         if (self.fused and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
                 and F.dense_act_supported(lin.in_features, lin.out_features, self._activation)):
+            if xnorm is not None:
+                return F.dense_act(x.contiguous(), lin.weight, lin.bias, self._activation, xnorm[0], xnorm[1])
             return F.dense_act(x.contiguous(), lin.weight, lin.bias, self._activation)
+        if xnorm is not None:   # (cannot happen: can_fuse_xnorm said yes) -- normalise here rather than skip it
+            x = (x - xnorm[0]) / (xnorm[1] + 1e-8)
         return self.act(lin(x))
+
+    def can_fuse_xnorm(self, x):
+        """True when this layer's kernels can read raw x and normalise it on load (first layer, both ways)."""
+        lin = self.linear
+        if isinstance(lin.weight, torch.nn.parameter.UninitializedParameter):
+            return False
+        return (self.fused and x.dtype == torch.float32
+                and F.dense_act_xnorm_supported(lin.in_features, lin.out_features, self._activation))
 
 
 class MaximumLikelihoodNNEstimator(BaseEstimator):
@@ -60,6 +74,8 @@ class MaximumLikelihoodNNEstimator(BaseEstimator):
         seed = 1000 * getattr(self, "random_seed", 22)
         hidden = [_Dense(size, activation, seed + i) for i, size in enumerate(hidden_sizes)]
         output = [_Dense(output_size, "linear", seed + len(hidden_sizes))]
+        if hidden:   # the first hidden layer can take the input normalisation as a prologue of its own kernel
+            normalization[0].fused_into = hidden[0]
         return normalization + noise_reg + hidden + output
 
     def _ensure_optimizer(self):

@@ -52,6 +52,39 @@ def _prep_ty(t, y, n_dims, width, what):
     return _aligned(t), _aligned(y), B
 
 
+def _xf(xform):
+    """NULL or a pointer to the caller's ``_lib.EventXform`` (the y pipeline fused into the head, see make_xform)."""
+    return None if xform is None else ctypes.byref(xform)
+
+
+def make_xform(n_dims, mean=None, std=None, logp_shift=0.0, noise_std=0.0, seed=0, offset=0, offset_dev=None,
+               exp_out=False):
+    """Build the event transform of a head launch (include/nfn_b200.h: nfn_event_xform).
+
+    mean / std: host sequences of length n_dims -> y' = (y - mean) / std;  noise_std > 0 adds N(0, noise_std^2)
+    noise drawn in the kernel (Philox keyed by ``seed``, counter (row, offset + *offset_dev));  logp_shift is
+    added to every log-prob;  exp_out writes exp(logp + shift), i.e. the density."""
+    xf = _lib.EventXform()
+    flags = 0
+    if mean is not None:
+        assert len(mean) == n_dims and len(std) == n_dims
+        for i in range(n_dims):
+            xf.mean[i] = float(mean[i])
+            xf.std[i] = float(std[i])
+        flags |= _lib.XF_NORMALISE
+    if noise_std and noise_std > 0.0:
+        xf.noise_std = float(noise_std)
+        xf.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        xf.offset = int(offset) & 0xFFFFFFFFFFFFFFFF
+        xf.offset_dev = None if offset_dev is None else offset_dev.data_ptr()
+        flags |= _lib.XF_NOISE
+    if exp_out:
+        flags |= _lib.XF_EXP
+    xf.logp_shift = float(logp_shift)
+    xf.flags = flags
+    return xf
+
+
 def _check_y(y, n_dims, B, what):
     """The C ABI cannot see tensor extents: a wrong-shaped y would be an out-of-bounds device read."""
     if y.dim() != 2 or y.shape[1] != n_dims or y.shape[0] not in (B, 1):
@@ -78,7 +111,7 @@ def chain_is_specialized(flow_types, n_dims, trainable_base_dist):
     return bool(_lib.check(lib.nfn_chain_is_specialized(ctypes.byref(_lib.make_desc(flow_types, n_dims, trainable_base_dist)))))
 
 
-def chain_forward(t, y, flow_types, n_dims, trainable_base_dist):
+def chain_forward(t, y, flow_types, n_dims, trainable_base_dist, xform=None):
     """log_prob[B] of the inverted flow chain (no autograd)."""
     lib = _lib.load()
     desc = _lib.make_desc(flow_types, n_dims, trainable_base_dist)
@@ -86,12 +119,12 @@ def chain_forward(t, y, flow_types, n_dims, trainable_base_dist):
     t, y, B = _prep_ty(t, y, n_dims, P, "chain_forward")
     logp = torch.empty(B, dtype=torch.float32, device=t.device)
     with torch.cuda.device(t.device):
-        _lib.check(lib.nfn_chain_forward(ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), y.shape[0],
-                                         _lib.ptr(logp), B, _lib.current_stream(t.device)))
+        _lib.check(lib.nfn_chain_forward_x(ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), y.shape[0],
+                                           _lib.ptr(logp), B, _xf(xform), _lib.current_stream(t.device)))
     return logp
 
 
-def chain_forward_grid(t, y_grid, flow_types, n_dims, trainable_base_dist):
+def chain_forward_grid(t, y_grid, flow_types, n_dims, trainable_base_dist, xform=None):
     """log_prob of every parameter row against every event: returns [n_y, B] (event-major).
     The parameter tensor is read once, not once per event."""
     lib = _lib.load()
@@ -106,13 +139,13 @@ def chain_forward_grid(t, y_grid, flow_types, n_dims, trainable_base_dist):
     B, ny = t.shape[0], y_grid.shape[0]
     logp = torch.empty((ny, B), dtype=torch.float32, device=t.device)
     with torch.cuda.device(t.device):
-        _lib.check(lib.nfn_chain_forward_grid(ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y_grid), ny, _lib.ptr(logp),
-                                              B, _lib.current_stream(t.device)))
+        _lib.check(lib.nfn_chain_forward_grid_x(ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y_grid), ny, _lib.ptr(logp),
+                                                B, _xf(xform), _lib.current_stream(t.device)))
     return logp
 
 
 def chain_forward_backward(t, y, flow_types, n_dims, trainable_base_dist, g_logp=None, g_scale=1.0,
-                           want_dy=False, logp_sum=None, dt_colsum=None, out_logp=None, out_dt=None):
+                           want_dy=False, logp_sum=None, dt_colsum=None, out_logp=None, out_dt=None, xform=None):
     """Fused forward + reverse sweep.  Returns (logp[B], dt[B,P], dy[B,d] or None).
 
     dt = cot[:, None] * dlogp/dt with cot = g_scale * (g_logp if given else 1).
@@ -133,10 +166,10 @@ def chain_forward_backward(t, y, flow_types, n_dims, trainable_base_dist, g_logp
         if g_logp.numel() != B:
             raise ValueError("g_logp must have B=%d elements" % B)
     with torch.cuda.device(dev):
-        _lib.check(lib.nfn_chain_forward_backward(
+        _lib.check(lib.nfn_chain_forward_backward_x(
             ctypes.byref(desc), _lib.ptr(t), _lib.ptr(y), y.shape[0], _lib.ptr(g_logp),
             ctypes.c_float(g_scale), _lib.ptr(logp), _lib.ptr(dt), _lib.ptr(dy), _lib.ptr(logp_sum),
-            _lib.ptr(dt_colsum), B, _lib.current_stream(dev)))
+            _lib.ptr(dt_colsum), B, _xf(xform), _lib.current_stream(dev)))
     return logp, dt, dy
 
 
@@ -176,8 +209,10 @@ def dense_act_supported(in_features, units, activation):
     return bool(_lib.load().nfn_dense_act_supported(int(in_features), int(units), ACT_CODES[activation]))
 
 
-def dense_act_forward(x, weight, bias, activation):
-    """act(x @ weight.T + bias) in one kernel; weight is torch's [units, in_features]."""
+def dense_act_forward(x, weight, bias, activation, x_mean=None, x_std=None):
+    """act(x' @ weight.T + bias) in one kernel; weight is torch's [units, in_features].  With x_mean / x_std
+    (device [in_features]) the layer reads x' = (x - x_mean) / (x_std + 1e-8): the estimators' input normalisation
+    fused into their first layer."""
     lib = _lib.load()
     x = _aligned(_as_f32_cuda(x, "x"))
     weight = _as_f32_cuda(weight, "weight", device=x.device)
@@ -185,14 +220,18 @@ def dense_act_forward(x, weight, bias, activation):
     B, K = x.shape
     N = weight.shape[0]
     assert tuple(weight.shape) == (N, K) and tuple(bias.shape) == (N,)
+    if x_mean is not None:
+        x_mean, x_std = _as_f32_cuda(x_mean, "x_mean", device=x.device), _as_f32_cuda(x_std, "x_std", device=x.device)
+        assert x_mean.numel() == K and x_std.numel() == K
     out = torch.empty((B, N), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(lib.nfn_dense_act_forward(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias), B, K, N,
-                                             ACT_CODES[activation], _lib.ptr(out), _lib.current_stream(x.device)))
+        _lib.check(lib.nfn_dense_act_forward_x(_lib.ptr(x), _lib.ptr(x_mean), _lib.ptr(x_std), _lib.ptr(weight),
+                                               _lib.ptr(bias), B, K, N, ACT_CODES[activation], _lib.ptr(out),
+                                               _lib.current_stream(x.device)))
     return out
 
 
-def dense_act_backward(x, out, dout, weight, activation, need_dx=True):
+def dense_act_backward(x, out, dout, weight, activation, need_dx=True, x_mean=None, x_std=None):
     """Gradients of dense_act_forward given the layer's OUTPUT: returns (dx or None, dweight, dbias)."""
     lib = _lib.load()
     x = _aligned(_as_f32_cuda(x, "x"))
@@ -206,33 +245,38 @@ def dense_act_backward(x, out, dout, weight, activation, need_dx=True):
     dW = torch.zeros((N, K), dtype=torch.float32, device=dev)
     db = torch.zeros(N, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.nfn_dense_act_backward(_lib.ptr(x), _lib.ptr(out), _lib.ptr(dout), _lib.ptr(weight), B, K, N,
-                                              ACT_CODES[activation], _lib.ptr(dx), _lib.ptr(dW), _lib.ptr(db),
-                                              _lib.current_stream(dev)))
+        _lib.check(lib.nfn_dense_act_backward_x(_lib.ptr(x), _lib.ptr(x_mean), _lib.ptr(x_std), _lib.ptr(out),
+                                                _lib.ptr(dout), _lib.ptr(weight), B, K, N, ACT_CODES[activation],
+                                                _lib.ptr(dx), _lib.ptr(dW), _lib.ptr(db), _lib.current_stream(dev)))
     return dx, dW, db
+
+
+def dense_act_xnorm_supported(in_features, units, activation):
+    """True when the FIRST layer of a network can take the input normalisation as a fused prologue (both ways)."""
+    return dense_act_supported(in_features, units, activation) and in_features <= 4 and units <= 32
 
 
 class _DenseAct(torch.autograd.Function):
     """Dense(units, activation) as one kernel each way (csrc/nfn_mlp.cu)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, activation):
-        out = dense_act_forward(x, weight, bias, activation)
-        ctx.save_for_backward(x, out, weight)
+    def forward(ctx, x, weight, bias, activation, x_mean, x_std):
+        out = dense_act_forward(x, weight, bias, activation, x_mean, x_std)
+        ctx.save_for_backward(x, out, weight, x_mean, x_std)
         ctx.activation = activation
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, out, weight = ctx.saved_tensors
+        x, out, weight, x_mean, x_std = ctx.saved_tensors
         dx, dW, db = dense_act_backward(x, out, dout.contiguous(), weight, ctx.activation,
-                                        need_dx=ctx.needs_input_grad[0])
-        return dx, dW, db, None
+                                        need_dx=ctx.needs_input_grad[0], x_mean=x_mean, x_std=x_std)
+        return dx, dW, db, None, None, None
 
 
-def dense_act(x, weight, bias, activation):
+def dense_act(x, weight, bias, activation, x_mean=None, x_std=None):
     """Differentiable fused hidden layer (forward kernel under no_grad, Function otherwise)."""
-    return _DenseAct.apply(x, weight, bias, activation)
+    return _DenseAct.apply(x, weight, bias, activation, x_mean, x_std)
 
 
 # ----------------------------------------------------------------------------- fused Dense(P) + chain
@@ -240,7 +284,7 @@ def dense_chain_supported(hidden):
     return hidden in (16, 32, 48, 64)
 
 
-def dense_chain_forward(h, W, bias, y, flow_types, n_dims, trainable_base_dist):
+def dense_chain_forward(h, W, bias, y, flow_types, n_dims, trainable_base_dist, xform=None):
     """log_prob[B] with the emitting layer fused: t = h @ W + bias never touches HBM.
     h [B, H], W [H, P] (Keras kernel layout = torch ``linear.weight.t()``), bias [P]."""
     lib = _lib.load()
@@ -256,13 +300,14 @@ def dense_chain_forward(h, W, bias, y, flow_types, n_dims, trainable_base_dist):
     _check_y(y, n_dims, B, "dense_chain_forward")
     logp = torch.empty(B, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.nfn_dense_chain_forward(ctypes.byref(desc), H, _lib.ptr(h), _lib.ptr(W), _lib.ptr(bias),
-                                               _lib.ptr(y), y.shape[0], _lib.ptr(logp), B, _lib.current_stream(dev)))
+        _lib.check(lib.nfn_dense_chain_forward_x(ctypes.byref(desc), H, _lib.ptr(h), _lib.ptr(W), _lib.ptr(bias),
+                                                 _lib.ptr(y), y.shape[0], _lib.ptr(logp), B, _xf(xform),
+                                                 _lib.current_stream(dev)))
     return logp
 
 
 def dense_chain_forward_backward(h, W, bias, y, flow_types, n_dims, trainable_base_dist, g_logp=None, g_scale=1.0,
-                                 logp_sum=None, dW=None, dbias=None):
+                                 logp_sum=None, dW=None, dbias=None, xform=None):
     """Fused layer + chain, forward and reverse sweep.  Returns (logp[B], dh[B,H], dW[H,P], dbias[P]);
     dW / dbias are accumulated into when given (else fresh zero tensors)."""
     lib = _lib.load()
@@ -284,10 +329,10 @@ def dense_chain_forward_backward(h, W, bias, y, flow_types, n_dims, trainable_ba
         dbias = torch.zeros(P, dtype=torch.float32, device=dev)
     g_logp = _prep_g(g_logp, B, dev, "dense_chain_forward_backward")
     with torch.cuda.device(dev):
-        _lib.check(lib.nfn_dense_chain_forward_backward(
+        _lib.check(lib.nfn_dense_chain_forward_backward_x(
             ctypes.byref(desc), H, _lib.ptr(h), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(y), y.shape[0],
             _lib.ptr(g_logp), ctypes.c_float(g_scale), _lib.ptr(logp), _lib.ptr(dh), _lib.ptr(dW), _lib.ptr(dbias),
-            _lib.ptr(logp_sum), B, _lib.current_stream(dev)))
+            _lib.ptr(logp_sum), B, _xf(xform), _lib.current_stream(dev)))
     return logp, dh, dW, dbias
 
 
@@ -353,18 +398,18 @@ def mdn_param_size(n_centers, n_dims):
     return 2 * n_centers * n_dims + n_centers
 
 
-def mdn_forward(t, y, n_centers, n_dims):
+def mdn_forward(t, y, n_centers, n_dims, xform=None):
     lib = _lib.load()
     t, y, B = _prep_ty(t, y, n_dims, mdn_param_size(n_centers, n_dims), "mdn_forward")
     logp = torch.empty(B, dtype=torch.float32, device=t.device)
     with torch.cuda.device(t.device):
-        _lib.check(lib.nfn_mdn_forward(n_centers, n_dims, _lib.ptr(t), _lib.ptr(y), y.shape[0],
-                                       _lib.ptr(logp), B, _lib.current_stream(t.device)))
+        _lib.check(lib.nfn_mdn_forward_x(n_centers, n_dims, _lib.ptr(t), _lib.ptr(y), y.shape[0],
+                                         _lib.ptr(logp), B, _xf(xform), _lib.current_stream(t.device)))
     return logp
 
 
 def mdn_forward_backward(t, y, n_centers, n_dims, g_logp=None, g_scale=1.0, want_dy=False,
-                         logp_sum=None, dt_colsum=None):
+                         logp_sum=None, dt_colsum=None, xform=None):
     lib = _lib.load()
     P = mdn_param_size(n_centers, n_dims)
     t, y, B = _prep_ty(t, y, n_dims, P, "mdn_forward_backward")
@@ -375,10 +420,10 @@ def mdn_forward_backward(t, y, n_centers, n_dims, g_logp=None, g_scale=1.0, want
     if g_logp is not None:
         g_logp = _as_f32_cuda(g_logp, "g_logp", device=dev).reshape(-1)
     with torch.cuda.device(dev):
-        _lib.check(lib.nfn_mdn_forward_backward(
+        _lib.check(lib.nfn_mdn_forward_backward_x(
             n_centers, n_dims, _lib.ptr(t), _lib.ptr(y), y.shape[0], _lib.ptr(g_logp),
             ctypes.c_float(g_scale), _lib.ptr(logp), _lib.ptr(dt), _lib.ptr(dy), _lib.ptr(logp_sum),
-            _lib.ptr(dt_colsum), B, _lib.current_stream(dev)))
+            _lib.ptr(dt_colsum), B, _xf(xform), _lib.current_stream(dev)))
     return logp, dt, dy
 
 
@@ -412,7 +457,7 @@ def mdn_log_prob(t, y, n_centers, n_dims):
 
 
 # ----------------------------------------------------------------------------- KMN head
-def kmn_forward(t, y, locs, scales):
+def kmn_forward(t, y, locs, scales, xform=None):
     lib = _lib.load()
     locs = _as_f32_cuda(locs, "locs")
     M, d = locs.shape
@@ -420,13 +465,14 @@ def kmn_forward(t, y, locs, scales):
     t, y, B = _prep_ty(t, y, d, M, "kmn_forward")
     logp = torch.empty(B, dtype=torch.float32, device=t.device)
     with torch.cuda.device(t.device):
-        _lib.check(lib.nfn_kmn_forward(M, d, _lib.ptr(t), _lib.ptr(y), y.shape[0], _lib.ptr(locs),
-                                       _lib.ptr(scales), _lib.ptr(logp), B, _lib.current_stream(t.device)))
+        _lib.check(lib.nfn_kmn_forward_x(M, d, _lib.ptr(t), _lib.ptr(y), y.shape[0], _lib.ptr(locs),
+                                         _lib.ptr(scales), _lib.ptr(logp), B, _xf(xform),
+                                         _lib.current_stream(t.device)))
     return logp
 
 
 def kmn_forward_backward(t, y, locs, scales, g_logp=None, g_scale=1.0, want_dy=False, want_dscales=True,
-                         logp_sum=None):
+                         logp_sum=None, xform=None):
     lib = _lib.load()
     locs = _as_f32_cuda(locs, "locs")
     M, d = locs.shape
@@ -440,10 +486,10 @@ def kmn_forward_backward(t, y, locs, scales, g_logp=None, g_scale=1.0, want_dy=F
     if g_logp is not None:
         g_logp = _as_f32_cuda(g_logp, "g_logp", device=dev).reshape(-1)
     with torch.cuda.device(dev):
-        _lib.check(lib.nfn_kmn_forward_backward(
+        _lib.check(lib.nfn_kmn_forward_backward_x(
             M, d, _lib.ptr(t), _lib.ptr(y), y.shape[0], _lib.ptr(locs), _lib.ptr(scales), _lib.ptr(g_logp),
             ctypes.c_float(g_scale), _lib.ptr(logp), _lib.ptr(dt), _lib.ptr(dy), _lib.ptr(dscales),
-            _lib.ptr(logp_sum), B, _lib.current_stream(dev)))
+            _lib.ptr(logp_sum), B, _xf(xform), _lib.current_stream(dev)))
     return logp, dt, dy, dscales
 
 
