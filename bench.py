@@ -32,6 +32,8 @@ import statistics
 import sys
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -490,6 +492,77 @@ class HeadWorkload:
         self.sets = []
 
 
+def cfg4_bayes_train_step(device, rank, world, steps=10, warmup=4):
+    """BASELINE config 4 as the estimator-level training step it names: Bayesian NFN (5 radial flows, 1-D y, one
+    hidden layer of 10 tanh units, the reference's defaults), S = 32 Monte-Carlo weight draws folded into the batch,
+    2^15 samples per GPU -> S * B = 2^20 folded rows per GPU (2^18 samples on 8 GPUs), data-parallel: every rank
+    runs the variational MLP (batched GEMMs), ONE fused head launch over its 2^20 folded rows, the MLP backward,
+    then ONE float32 all-reduce of the flat gradient buffer and Adam.  Reports the step time (max over ranks) and
+    where it goes: the head kernel alone and the all-reduce alone, each timed separately with CUDA events."""
+    import torch
+
+    from normalizingflownetwork_b200 import parallel
+    from normalizingflownetwork_b200 import functional as F
+    from normalizingflownetwork_b200.estimators import BayesNormalizingFlowNetwork
+
+    S, Bl = 32, 1 << 15
+    g = torch.Generator(device="cpu").manual_seed(22 + rank)
+    x = torch.rand((Bl, 1), generator=g) * 6.0 - 3.0
+    y = torch.cos(x) + 0.3 * torch.randn((Bl, 1), generator=g)
+    model = BayesNormalizingFlowNetwork(1, kl_weight_scale=1.0 / (Bl * world), n_flows=5, hidden_sizes=(10,),
+                                        activation="tanh", n_train_draws=S, learning_rate=2e-2)
+    model._assign_data_normalization(x.numpy(), y.numpy())
+    with torch.no_grad():
+        model.params_from_x(x[:2].numpy())
+    model.optimizer = torch.optim.Adam(model.parameters(), lr=model.learning_rate, eps=1e-7)
+    xd, yd = model._to_dev(x), model._to_dev(y)
+    Bg = Bl * world
+
+    def timed(fn, n):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        parallel.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        parallel.barrier()
+        return parallel.max_over_ranks(e0.elapsed_time(e1), device) / n   # ms
+
+    losses = []
+    step_ms = timed(lambda: losses.append(model.train_step(xd, yd, global_batch=Bg)), steps)
+    loss = float(losses[-1])
+    # breakdown: the head kernel on t[S * Bl, 17] alone, and the all-reduce of the flat gradient buffer alone
+    layer = model.dist_layer
+    with torch.no_grad():
+        t = model.params_from_x_draws(xd, S)
+    yy = yd.repeat(S, 1)
+    ls = torch.zeros(1, dtype=torch.float64, device=device)
+    xf = model._xform(1, training=True)
+    head_ms = timed(lambda: F.chain_forward_backward(t, yy, layer._flow_types, 1, True, g_scale=-1.0 / (S * Bg),
+                                                     logp_sum=ls, xform=xf), steps)
+    red_ms = None
+    n_grad = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    if world > 1:
+        red = model._grad_reducer()
+        red_ms = timed(red.reduce, steps)
+    peak, _ = load_peaks()
+    return {"workload": "Bayesian NFN 5 radial flows, 1-D y, hidden (10,) tanh, S=32 draws folded, %d samples per GPU "
+                        "(S*B = 2^20 folded rows per GPU), Adam training step, data-parallel" % Bl,
+            "global_samples_per_step": Bg, "folded_rows_per_gpu": S * Bl, "ms_per_step": step_ms,
+            "samples_per_s": Bg / (step_ms * 1e-3), "folded_rows_per_s": S * Bg / (step_ms * 1e-3),
+            "loss": loss, "loss_finite": bool(np.isfinite(loss)),
+            "breakdown_ms": {"head_kernel_fwd_bwd": head_ms, "flat_grad_allreduce": red_ms,
+                             "mlp_fwd_bwd_kl_adam_and_launch_gaps": step_ms - head_ms - (red_ms or 0.0)},
+            "head_roofline_frac": 4 * (2 * 17 + 1 + 1) * S * Bl / (head_ms * 1e-3) / 1e9 / peak,
+            "allreduce": ("one float32 NCCL all-reduce of %d values (flat gradient buffer + sum logp)" % (n_grad + 2))
+                         if world > 1 else None, "eager": True}
+
+
 def measure_other_config(cfg, args, device, rank, world, lib, steps=10, warmup=3):
     """A few steps of another BASELINE config, same launch path and timing rules as the headline."""
     import torch
@@ -646,6 +719,10 @@ def run_ours(args):
                 others[oc] = measure_other_config(oc, args, device, rank, world, lib)
             except Exception as exc:  # noqa: BLE001 -- an extra must not take the headline down
                 others[oc] = {"error": str(exc)[:200]}
+        try:
+            others["cfg4-train"] = cfg4_bayes_train_step(device, rank, world)
+        except Exception as exc:  # noqa: BLE001
+            others["cfg4-train"] = {"error": str(exc)[:300]}
         if world == 1:
             try:
                 others["cfg1-pipeline"] = cfg1_pipeline(args.steps, 3, cpu=False)

@@ -133,9 +133,16 @@ class BaseEstimator(torch.nn.Module):
             return None
         if not F.dense_chain_supported(lin.in_features) or self.dist_layer.get_total_param_size() < 1:
             return None
-        if dist.is_initialized() and dist.get_world_size() > 1:
-            return None  # the data-parallel step all-reduces autograd's .grad tensors; keep it simple
         return lin
+
+    def _emitting_kernel(self, lin):
+        """The emitting layer's weight in the Keras kernel layout [H, P] the fused head reads (= weight.t()),
+        transposed once per weight VERSION, not once per call (a scoring call would otherwise spend a launch on it)."""
+        key = (lin.weight.data_ptr(), lin.weight._version)
+        if getattr(self, "_wt_key", None) != key:
+            self._wt = lin.weight.detach().t().contiguous()
+            self._wt_key = key
+        return self._wt
 
     def hidden_from_x(self, x):
         h = self._to_dev(x)
@@ -151,7 +158,7 @@ class BaseEstimator(torch.nn.Module):
                 lin = self._fusable_last_layer()
                 if lin is not None and not training:
                     layer = self.dist_layer
-                    return FusedDenseFlowChainDistribution(self.hidden_from_x(x), lin.weight.t().contiguous(),
+                    return FusedDenseFlowChainDistribution(self.hidden_from_x(x), self._emitting_kernel(lin),
                                                            lin.bias, layer._flow_types, layer._n_dims,
                                                            layer._trainable_base_dist)
                 return self.dist_layer(self.params_from_x(x))
@@ -268,13 +275,19 @@ class BaseEstimator(torch.nn.Module):
         self.train(True)
         B = xb.shape[0]
         Bg = global_batch or B
-        self.optimizer.zero_grad(set_to_none=True)
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        reducer = self._grad_reducer() if world > 1 else None
+        if reducer is not None:
+            reducer.zero()     # gradients live in ONE flat buffer: every rank all-reduces it once per step
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
+        if B == 0:
+            return self._empty_shard_step(reducer, Bg, world)
         # y stays RAW: normalisation, the training-only noise and the -sum log y_std Jacobian run inside the head
         # kernel (reference BaseEstimator.py:55-69), so logp_sum already is sum_b(log p_b - sum log y_std)
         y = self._to_dev(yb)
         xf = self._xform(y.shape[1], training=True)
         logp_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
-        world = dist.get_world_size() if dist.is_initialized() else 1
         lin = self._fusable_last_layer()
         if lin is not None and self._extra_loss() is None:
             # ONE kernel for [Dense(P) forward, flow chain forward + reverse sweep, Dense(P) backward]:
@@ -282,10 +295,14 @@ class BaseEstimator(torch.nn.Module):
             layer = self.dist_layer
             h = self.hidden_from_x(xb)
             _, dh, dW, db = F.dense_chain_forward_backward(
-                h.detach(), lin.weight.detach().t().contiguous(), lin.bias.detach(), y, layer._flow_types,
+                h.detach(), self._emitting_kernel(lin), lin.bias.detach(), y, layer._flow_types,
                 layer._n_dims, layer._trainable_base_dist, g_scale=-1.0 / Bg, logp_sum=logp_sum, xform=xf)
-            lin.weight.grad = dW.t().contiguous()
-            lin.bias.grad = db
+            if reducer is not None:     # accumulate into the flat buffer's views
+                lin.weight.grad.copy_(dW.t())
+                lin.bias.grad.copy_(db)
+            else:
+                lin.weight.grad = dW.t().contiguous()
+                lin.bias.grad = db
             if h.requires_grad:
                 h.backward(dh)
         else:
@@ -299,8 +316,8 @@ class BaseEstimator(torch.nn.Module):
             else:
                 t.backward(dt)
         extra = self._extra_loss()
-        if world > 1:
-            self._allreduce_grads(logp_sum)
+        if reducer is not None:
+            logp_sum = self._reduce_step(reducer, logp_sum)
         self.optimizer.step()
         loss = -logp_sum.to(torch.float32) / Bg
         if extra is not None:
@@ -391,17 +408,44 @@ class BaseEstimator(torch.nn.Module):
         self._score_graph.replay()
         return self._score_out
 
-    def _allreduce_grads(self, logp_sum):
-        """One flat all-reduce(sum) of [all parameter grads | sum logp]."""
-        params = [p for p in self.parameters() if p.grad is not None]
-        flat = torch.cat([p.grad.reshape(-1).to(torch.float64) for p in params] + [logp_sum.reshape(-1)])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        off = 0
-        for p in params:
-            n = p.numel()
-            p.grad.copy_(flat[off: off + n].view_as(p.grad))
-            off += n
-        logp_sum.copy_(flat[off:])
+    # ------------------------------------------------------------------ data-parallel step
+    def _grad_reducer(self):
+        """The flat gradient buffer of this model (parallel.FlatGradReducer), built at the first data-parallel step
+        (all lazy layers exist by then) and rebuilt if the set of trainable parameters changes."""
+        from ..parallel import FlatGradReducer
+
+        params = [p for p in self.parameters() if p.requires_grad]
+        red = getattr(self, "_reducer", None)
+        if red is None or len(red.params) != len(params) or any(a is not b for a, b in zip(red.params, params)):
+            red = FlatGradReducer(params, n_scalars=1)
+            self._reducer = red
+        return red
+
+    def _reduce_step(self, reducer, logp_sum):
+        """ONE float32 all-reduce of [all parameter gradients | sum logp (hi, lo)]; returns the global sum logp."""
+        reducer.put_scalars(logp_sum.reshape(-1))
+        reducer.reduce()
+        return reducer.get_scalars().reshape(1)
+
+    def _empty_shard_step(self, reducer, Bg, world, denom=None):
+        """This rank's shard of the mini-batch is empty (tail batch with fewer rows than ranks).  It still takes
+        part in the step: zero data gradients, its share of the replicated regulariser, the same all-reduce and
+        optimiser step as every other rank -- skipping would pair its NEXT collective with the peers' current one."""
+        logp_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
+        extra = self._refresh_extra_loss()
+        if extra is not None:
+            extra.backward(torch.full_like(extra, 1.0 / world))
+        if reducer is not None:
+            logp_sum = self._reduce_step(reducer, logp_sum)
+        self.optimizer.step()
+        loss = -logp_sum.to(torch.float32) / (denom or Bg)
+        if extra is not None:
+            loss = loss + extra.detach()
+        return loss.reshape(())
+
+    def _refresh_extra_loss(self):
+        """The regulariser without a forward pass over data (subclasses with one override this)."""
+        return None
 
     # ------------------------------------------------------------------ Keras-like API
     def fit(self, x, y, batch_size=None, epochs=None, verbose=1, shuffle=True, cuda_graph=False, **kwargs):
@@ -433,7 +477,7 @@ class BaseEstimator(torch.nn.Module):
                     from ..parallel import shard_rows
                     a, b = shard_rows(gb, rank, world)
                     idx = idx[a:b]
-                if idx.numel() == 0:
+                if idx.numel() == 0 and world == 1:
                     continue
                 if cuda_graph and idx.numel() == batch_size:
                     losses.append(self.train_step_graphed(xd[idx], yd[idx]).clone())

@@ -91,6 +91,26 @@ class DenseVariational(torch.nn.Module):
             out = torch.baddbmm(w[:, nk:].unsqueeze(1), x, w[:, :nk].view(n_draws, self.in_features, self.units))
         return self.act(out)
 
+    def refresh_kl(self, n_draws=None, generator=None):
+        """The layer's KL term without data (a data-parallel rank whose shard of the mini-batch is empty): draws
+        the weights exactly as ``forward`` would, so that the replicated weight-noise generators of all ranks stay
+        in step, and leaves ``last_kl`` behind."""
+        if self.in_features is None:
+            return None
+        q, r = self._dists()
+        loc, scale = q.base_dist.loc, q.base_dist.scale
+        if self.map_mode:
+            w = loc if n_draws is None else loc.expand(n_draws, -1)
+        else:
+            shape = tuple(loc.shape) if n_draws is None else (n_draws,) + tuple(loc.shape)
+            w = loc + scale * torch.randn(shape, device=loc.device, generator=generator)
+        if n_draws is None:
+            self.last_kl = self.kl_weight * self._kl(q, r, w)
+        else:
+            self.last_kl = self.kl_weight * (self._kl(q, r, None) if self.kl_use_exact
+                                             else (q.log_prob(w) - r.log_prob(w)).mean())
+        return self.last_kl
+
 
 class BayesianNNEstimator(BaseEstimator):
     def __init__(self, dist_layer, kl_weight_scale, kl_use_exact=True, hidden_sizes=(10,), activation="tanh",
@@ -167,20 +187,33 @@ class BayesianNNEstimator(BaseEstimator):
         S = self.n_train_draws
         B = xb.shape[0]
         Bg = global_batch or B
-        self.optimizer.zero_grad(set_to_none=True)
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        reducer = self._grad_reducer() if world > 1 else None
+        if reducer is not None:
+            reducer.zero()
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
+        if B == 0:
+            return self._empty_shard_step(reducer, Bg, world, denom=S * Bg)
         t = self.params_from_x_draws(xb, S)
         # raw y: normalisation, training noise (independent per folded row) and the Jacobian run in the head kernel
         y = self._to_dev(yb).repeat(S, 1)
         logp_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
         dt = self._head_forward_backward(t, y, -1.0 / (S * Bg), logp_sum, xform=self._xform(y.shape[1], training=True))
         extra = self._extra_loss()
-        world = dist.get_world_size() if dist.is_initialized() else 1
         torch.autograd.backward([t, extra], [dt, torch.full_like(extra, 1.0 / world)])
-        if world > 1:
-            self._allreduce_grads(logp_sum)
+        if reducer is not None:
+            logp_sum = self._reduce_step(reducer, logp_sum)
         self.optimizer.step()
         loss = -logp_sum.to(torch.float32) / (S * Bg) + extra.detach()
         return loss.reshape(())
+
+    def _refresh_extra_loss(self):
+        S = self.n_train_draws if (self.n_train_draws > 1 and not self.map_mode) else None
+        for layer in self.net:
+            if isinstance(layer, DenseVariational):
+                layer.refresh_kl(n_draws=S, generator=self._weight_generator())
+        return self._extra_loss()
 
     def _extra_loss(self):
         kls = [l.last_kl for l in self.net if isinstance(l, DenseVariational) and l.last_kl is not None]

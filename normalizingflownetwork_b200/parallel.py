@@ -74,6 +74,57 @@ class PackedAllReduce:
         return out
 
 
+class FlatGradReducer:
+    """All parameter gradients of a model as views of ONE preallocated float32 buffer, plus a few float64 scalars
+    (the step's sum of log-probs) carried as float32 (hi, lo) pairs: a data-parallel step is ``zero()``, the
+    usual backward (autograd accumulates into the views in place), ``reduce()`` = one all-reduce(sum) of the flat
+    buffer -- no concatenation, no dtype round trip, no per-parameter collectives.
+
+    Every rank must call ``reduce()`` once per step, including a rank whose shard of the mini-batch is empty
+    (it contributes zeros): the collective sequence is identical on all ranks by construction.
+    Works on CUDA tensors over NCCL and on CPU tensors over gloo (tests/test_dist_gloo.py)."""
+
+    def __init__(self, params, n_scalars=1):
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params, "no trainable parameters"
+        dev = self.params[0].device
+        self.sizes = [p.numel() for p in self.params]
+        self.n_scalars = int(n_scalars)
+        self.flat = torch.zeros(sum(self.sizes) + 2 * self.n_scalars, dtype=torch.float32, device=dev)
+        off = 0
+        self.views = []
+        for p, n in zip(self.params, self.sizes):
+            assert p.dtype == torch.float32 and p.device == dev
+            self.views.append(self.flat[off: off + n].view(p.shape))
+            off += n
+        self._tail = self.flat[off:]
+        self.attach()
+
+    def attach(self):
+        """(Re)install the views as the parameters' .grad (optimizers' zero_grad(set_to_none=True) drops them)."""
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def zero(self):
+        self.flat.zero_()
+        self.attach()
+
+    def put_scalars(self, values64):
+        """values64: float64 tensor [n_scalars]; stored as float32 (hi, lo) so that the sum keeps ~48 bits."""
+        hi = values64.to(torch.float32)
+        lo = (values64 - hi.to(torch.float64)).to(torch.float32)
+        self._tail[0::2].copy_(hi)
+        self._tail[1::2].copy_(lo)
+
+    def get_scalars(self):
+        return self._tail[0::2].to(torch.float64) + self._tail[1::2].to(torch.float64)
+
+    def reduce(self):
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        return self.flat
+
+
 class PeerComm:
     """Peer-memory communicator for the fused in-kernel all-reduce (include/nfn_b200.h,
     csrc/nfn_peer.cu).  One per process / GPU.  Each rank allocates one IPC-exportable region,
