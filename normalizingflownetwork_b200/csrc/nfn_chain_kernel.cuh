@@ -1024,7 +1024,7 @@ struct WarpColSum {
 // fused kernel refills a buffer only after its store has drained (at the END of an iteration), so of NB buffers
 // one is in the registers' hands, one is draining and NB - 2 are loading: small tiles take 16 warps x 3 buffers;
 // when that does not fit the SM's 227 KB, depth beats warps (4 buffers, as many warps as fit, whole CTAs of 4).
-// The forward kernel (nothing to store) keeps NB - 1 loads in flight per warp: 2 buffers, ~64 KB per SM.
+// The forward kernel (nothing to store) keeps NB - 1 loads in flight per warp.
 __host__ __device__ constexpr ChainGeometry warp_tile_geometry(int P, bool bwd, int hist, int nb = 0, int warps = 0) {
   const unsigned tile = 128u * (unsigned)(P > 0 ? P : 1);
   const unsigned budget = 227u * 1024u - 4u * 2560u;   // per SM, minus per-CTA reservations / alignment slack
@@ -1034,10 +1034,12 @@ __host__ __device__ constexpr ChainGeometry warp_tile_geometry(int P, bool bwd, 
     if (nb <= 0) nb = (16u * 3u * tile <= budget) ? 3 : 4;
     if (want <= 0) want = 16;
   } else {
-    if (nb <= 0) nb = 2;
+    // ~64 KB of loads in flight per SM: 4 warps x 16 KB tiles (cfg3), 8 x 6 KB (cfg2), 16 x 4 KB; tiles under 3 KB
+    // (1-D chains, a handful of flows) need every warp slot and a third buffer: 32 warps x 3
+    if (nb <= 0) nb = tile < 3072u ? 3 : 2;
     if (want <= 0) {
-      want = (int)(65536u / tile);
-      want = want < 4 ? 4 : (want > 8 ? 8 : want);
+      want = (int)(65536u / tile) / 4 * 4;
+      want = want < 4 ? 4 : (want > 32 ? 32 : want);
     }
   }
   int w = (int)(budget / ((unsigned)nb * tile));
