@@ -344,8 +344,8 @@ class HeadWorkload:
             # agree, so the outcome is all-reduced and the NCCL exchange is the fallback
             try:
                 self.comm = parallel.PeerComm(P + 1, device)
-                # split-phase: a launch pushes its totals at its tail, the sums are collected at the head of the
-                # next launch (the last step's by an explicit flush) -- no rank waits for another at a kernel's end
+                # split-phase: the last CTA of a launch collects the PREVIOUS step's sums (delivered a kernel ago) and
+                # pushes its own without waiting; the last step's sums by an explicit flush
                 self.comm.set_deferred(not args.peer_blocking)
                 ok = 1
             except Exception as exc:  # noqa: BLE001
@@ -748,8 +748,9 @@ def run_ours(args):
                 bytes_per_row * B // (1 << 20)),
             "parallelism": "dp%d (rows sharded, no data-path collective%s)" % (
                 world, ("; [dt column sums (P) | sum logp] summed over ranks every step, " + (
-                    ("fused into the kernel over NVLink peer memory (push at the tail of step i, collected at the head "
-                     "of step i+1; the last step's by a flush inside the timed region)" if not args.peer_blocking else
+                    ("fused into the kernel over NVLink peer memory, split-phase (the last CTA of step i+1 collects step "
+                     "i's sums, then pushes its own; the last step's by a flush inside the timed region)"
+                     if not args.peer_blocking else
                      "fused into the kernel's last CTA over NVLink peer memory (push + wait)") if use_peer else
                     "one NCCL all-reduce")) if packed else ""),
             "t_sigma": 0.5, "seed": 22, "extra_untimed_warmup_steps": extra_warmup,

@@ -177,9 +177,10 @@ struct PeerArgs {
   unsigned* ticket;            // CTA arrival counter, self-resetting
   unsigned long long step;     // sequence number of this launch's exchange
   int world, rank, n_values;
-  // Split-phase mode (deferred != 0): this launch only PUSHES its totals; the sums of the previous exchange
-  // (`pending_step`, into `pending_out`) are collected by one CTA at the head of this launch, i.e. behind
-  // its own tile work, so rank skew and the NVLink round trip never sit on a kernel's tail.
+  // Split-phase mode (deferred != 0): the last CTA of this launch first COLLECTS the sums of the PREVIOUS exchange
+  // (`pending_step`, into `pending_out`) -- pushed by the peers a whole kernel ago, so they are simply there -- and
+  // then pushes this launch's totals without waiting for anybody: rank skew up to one kernel duration and the
+  // NVLink latency never sit on a kernel's tail.
   int deferred;
   double* pending_out;         // nullptr: nothing to collect
   unsigned long long pending_step;
@@ -600,17 +601,18 @@ NFN_DEVI void peer_push(const PeerArgs& p, int tid, int nthreads) {
   }
 }
 
-// Head of a launch in split-phase mode: the LAST CTA of the grid (it starts last and owns the fewest tiles)
-// collects the previous exchange.  Slot reuse stays safe: a rank pushes exchange s+2 into the slots of exchange s
-// only after its own collect of s+1 has seen every peer's s+1 words, and a peer pushes s+1 only after all its
-// CTAs -- its collector of s included -- have arrived at the ticket.
+// Completes a pending split-phase exchange on its own (nfn_peer_flush: after the last step of a loop).
 NFN_DEVI void peer_head(const PeerArgs& p) {
-  if (p.world > 0 && p.deferred && p.pending_out && blockIdx.x == gridDim.x - 1)
+  if (p.world > 0 && p.deferred && p.pending_out)
     peer_collect(p, p.pending_step, p.pending_out, (int)threadIdx.x, (int)blockDim.x);
 }
 
 // Tail of a launch: called by every thread of every CTA after the CTA's accumulator atomics.  The last CTA to
-// arrive pushes; unless the communicator is in split-phase mode it also collects this exchange right away.
+// arrive runs the exchange:
+//   blocking   : push this step's totals, wait for every peer's, sum            (one NVLink round trip + skew)
+//   split-phase: collect the PREVIOUS step's sums (already delivered), then push this step's totals.
+// Collect-before-push keeps slot reuse safe: a rank overwrites the slots of exchange s (with s+2) only after its
+// own collect of s+1 has seen every peer's s+1 words, and a peer pushes s+1 only after it has collected s.
 template <int T>
 NFN_DEVI void peer_allreduce(const PeerArgs& p) {
   __shared__ int s_last;
@@ -623,8 +625,13 @@ NFN_DEVI void peer_allreduce(const PeerArgs& p) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  peer_push(p, (int)threadIdx.x, T);
-  if (!p.deferred) peer_collect(p, p.step, p.out, (int)threadIdx.x, T);
+  if (p.deferred) {
+    if (p.pending_out) peer_collect(p, p.pending_step, p.pending_out, (int)threadIdx.x, T);
+    peer_push(p, (int)threadIdx.x, T);
+  } else {
+    peer_push(p, (int)threadIdx.x, T);
+    peer_collect(p, p.step, p.out, (int)threadIdx.x, T);
+  }
   if (threadIdx.x == 0) *p.ticket = 0u;
 }
 
@@ -687,8 +694,6 @@ NFN_DEVI void chain_body(const ChainArgs& a) {
       if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + r0); }
     }
   }
-
-  peer_head(a.peer);  // split-phase exchange: collect the previous launch's sums behind the first loads
 
   int slot = 0;  // buffer holding the current tile
   for (; tile < ntiles; tile += gridDim.x) {
@@ -1128,10 +1133,6 @@ NFN_DEVI void chain_body_w(const ChainArgs& a, const TensorMap* tm_t, const Tens
       if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + r0); }
     }
   }
-
-  // split-phase exchange: one warp of the last CTA collects the previous launch's sums behind its first loads
-  if (a.peer.world > 0 && a.peer.deferred && a.peer.pending_out && blockIdx.x == gridDim.x - 1 && warp == NW - 1)
-    peer_collect(a.peer, a.peer.pending_step, a.peer.pending_out, lane, 32);
 
   CS cs;
   if constexpr (BWD) cs.clear();

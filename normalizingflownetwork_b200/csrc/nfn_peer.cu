@@ -26,10 +26,7 @@ struct nfn_peer_comm {
 
 namespace nfn {
 
-__global__ void __launch_bounds__(128) peer_allreduce_kernel(const PeerArgs p) {
-  peer_head(p);
-  peer_allreduce<128>(p);
-}
+__global__ void __launch_bounds__(128) peer_allreduce_kernel(const PeerArgs p) { peer_allreduce<128>(p); }
 __global__ void __launch_bounds__(128) peer_flush_kernel(const PeerArgs p) { peer_head(p); }
 
 // Arguments of the NEXT exchange.  Nothing in the communicator changes here: the caller commits
