@@ -359,6 +359,7 @@ class HeadWorkload:
                     self.comm.close()
                 self.comm, self.use_peer = None, False
         self.step_no = 0
+        self._align = torch.zeros(1, device=device)
         self.g_scale = -1.0 / (B * world)
         self.stream = _lib.current_stream(device)
         self.bytes_per_row = 4 * ((2 * P if self.bwd else P) + d + 1)
@@ -417,6 +418,12 @@ class HeadWorkload:
         parallel.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if self.world > 1:
+            # the host threads of the ranks leave the barrier tens of microseconds apart, which a 20-step region
+            # (1.4 ms) would bill to the ranks that wait for the late one's first exchange: line the GPUs up in
+            # STREAM order -- a tiny all-reduce ends at (nearly) the same instant on every GPU, the start event
+            # and the K steps are queued right behind it without another host synchronisation
+            torch.distributed.all_reduce(self._align)
         e0.record()
         if with_exchange:
             for _ in range(K):
@@ -563,7 +570,7 @@ def cfg4_bayes_train_step(device, rank, world, steps=10, warmup=4):
                          if world > 1 else None, "eager": True}
 
 
-def measure_other_config(cfg, args, device, rank, world, lib, steps=10, warmup=3):
+def measure_other_config(cfg, args, device, rank, world, lib, steps=20, warmup=3):
     """A few steps of another BASELINE config, same launch path and timing rules as the headline."""
     import torch
 
@@ -754,7 +761,9 @@ def run_ours(args):
                      "fused into the kernel's last CTA over NVLink peer memory (push + wait)") if use_peer else
                     "one NCCL all-reduce")) if packed else ""),
             "t_sigma": 0.5, "seed": 22, "extra_untimed_warmup_steps": extra_warmup,
-            "timing": "one CUDA-event pair around the %d steps, no per-launch probes" % K,
+            "timing": "one CUDA-event pair around the %d steps, no per-launch probes" % K + (
+                "; after barrier + synchronize the ranks' streams are lined up by one tiny all-reduce queued directly "
+                "before the start event" if world > 1 else ""),
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": ("nfn_mdn_forward_backward_host" if mdn else
