@@ -344,8 +344,8 @@ class HeadWorkload:
             # agree, so the outcome is all-reduced and the NCCL exchange is the fallback
             try:
                 self.comm = parallel.PeerComm(P + 1, device)
-                # split-phase: the last CTA of a launch collects the PREVIOUS step's sums (delivered a kernel ago) and
-                # pushes its own without waiting; the last step's sums by an explicit flush
+                # split-phase: a launch sends the PREVIOUS step's totals from its head and collects their sums at its
+                # tail (NVLink latency and rank skew hide behind a kernel of tile work); the last step's by a flush
                 self.comm.set_deferred(not args.peer_blocking)
                 ok = 1
             except Exception as exc:  # noqa: BLE001
@@ -611,8 +611,10 @@ def run_ours(args):
     K, W = args.steps, args.warmup
     # N > 1: the per-step exchange couples the ranks, so cold NVLink links / peer mappings and start-up skew
     # would be billed to the first timed steps; top the warm-up up to 30 untimed steps (reported in config)
+    # (NVLink links idle into a low-power state: the untimed warm-up runs for ~50 ms of steps, not for a count)
     extra_warmup = max(0, 30 - W) if world > 1 else 0
-    wl = HeadWorkload(cfg, args, device, rank, world, lib, 3 * K + W + extra_warmup + 64, rows=args.rows or None,
+    wl = HeadWorkload(cfg, args, device, rank, world, lib, 3 * K + W + extra_warmup + 64 + (700 if world > 1 else 0),
+                      rows=args.rows or None,
                       fwd_only=args.fwd_only, colsum=not args.no_colsum)
     B, P, d, bwd, mdn = wl.B, wl.P, wl.d, wl.bwd, wl.mdn
     t, y, logp, dt = wl.sets[0]
@@ -622,6 +624,14 @@ def run_ours(args):
         sampler.start()
     for _ in range(W + extra_warmup):
         wl.step()
+    if world > 1:
+        torch.cuda.synchronize()
+        t_w = time.perf_counter()
+        while time.perf_counter() - t_w < 0.05 and wl.step_no < extra_warmup + W + 600:
+            for _ in range(50):
+                wl.step()
+            torch.cuda.synchronize()
+        extra_warmup = wl.step_no - W
     lib.nfn_launch_count_reset()
     wall0 = time.perf_counter()
     total_ms = wl.time_steps(K)
@@ -755,8 +765,8 @@ def run_ours(args):
                 bytes_per_row * B // (1 << 20)),
             "parallelism": "dp%d (rows sharded, no data-path collective%s)" % (
                 world, ("; [dt column sums (P) | sum logp] summed over ranks every step, " + (
-                    ("fused into the kernel over NVLink peer memory, split-phase (the last CTA of step i+1 collects step "
-                     "i's sums, then pushes its own; the last step's by a flush inside the timed region)"
+                    ("fused into the kernel over NVLink peer memory, split-phase (step i+1 sends step i's totals from its "
+                     "head and collects the sums at its tail; the last step's by a flush inside the timed region)"
                      if not args.peer_blocking else
                      "fused into the kernel's last CTA over NVLink peer memory (push + wait)") if use_peer else
                     "one NCCL all-reduce")) if packed else ""),

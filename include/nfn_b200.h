@@ -140,11 +140,12 @@ int nfn_chain_forward_backward(const nfn_chain_desc* desc, const float* t, const
  * NFN_ERR_PEER_TIMEOUT -- never a silent NaN.  A call that fails does not advance the exchange
  * sequence.  want_colsum = 0 skips the in-kernel column sums (their slots stay 0).
  *
- * Split-phase mode (nfn_peer_set_deferred(comm, 1)): the last CTA of a launch first collects the sums
- * of the PREVIOUS exchange on the communicator (into the `reduced` pointer that earlier call was
- * given) and then pushes its own totals without waiting.  `reduced` of call k is therefore complete
- * when call k+1 (or nfn_peer_flush) completes.  The peers' words of the previous exchange were pushed
- * a whole kernel ago, so rank skew up to one kernel duration and the NVLink latency are off the tail.
+ * Split-phase mode (nfn_peer_set_deferred(comm, 1)): a launch leaves its totals in local accumulators;
+ * the NEXT launch on the communicator sends them to the peers from its head (one warp, behind its first
+ * loads) and collects the cross-rank sums at its tail, into the `reduced` pointer the earlier call was
+ * given.  `reduced` of call k is therefore complete when call k+1 (or nfn_peer_flush) completes.  The
+ * NVLink round trip and up to one kernel duration of rank skew overlap with a whole kernel of tile work,
+ * and no kernel's completion waits for remote stores of its own.
  *
  * Communicator set-up (see normalizingflownetwork_b200/parallel.py:PeerComm):
  *   nfn_peer_alloc        cudaMalloc + zero one region, export its 64-byte cudaIpc handle

@@ -177,12 +177,14 @@ struct PeerArgs {
   unsigned* ticket;            // CTA arrival counter, self-resetting
   unsigned long long step;     // sequence number of this launch's exchange
   int world, rank, n_values;
-  // Split-phase mode (deferred != 0): the last CTA of this launch first COLLECTS the sums of the PREVIOUS exchange
-  // (`pending_step`, into `pending_out`) -- pushed by the peers a whole kernel ago, so they are simply there -- and
-  // then pushes this launch's totals without waiting for anybody: rank skew up to one kernel duration and the
-  // NVLink latency never sit on a kernel's tail.
+  // Split-phase mode (deferred != 0): a launch leaves its totals in the local accumulators `acc` (two sets,
+  // alternating by step parity).  The NEXT launch on the communicator pushes them to the peers from its HEAD (one
+  // warp of CTA 0, behind that CTA's first loads) and collects the cross-rank sums at its TAIL (`pending_step`,
+  // into `pending_out`): the NVLink round trip and up to a kernel duration of rank skew overlap with a whole
+  // kernel of tile work, and a kernel's completion never waits for remote stores of its own.
   int deferred;
-  double* pending_out;         // nullptr: nothing to collect
+  double* pending_out;         // nullptr: nothing pending
+  double* acc_prev;            // the accumulators the previous launch filled
   unsigned long long pending_step;
   unsigned* status;            // sticky error word: != 0 once a peer failed to arrive within the time-out
   long long timeout_cycles;
@@ -584,13 +586,13 @@ NFN_DEVI void peer_collect(const PeerArgs& p, unsigned long long step, double* o
   }
 }
 
-// Push: take (and reset) the local totals and write (value half | step tag) words into slot [parity][rank] of
-// EVERY peer's region (own region included).
-NFN_DEVI void peer_push(const PeerArgs& p, int tid, int nthreads) {
-  const int W = p.world, NV = p.n_values, par = (int)(p.step & 1ull);
-  const unsigned long long tag = ((p.step + 1ull) & 0xffffffffull) << 32;
+// Push: take (and reset) the local totals `acc` of exchange `step` and write (value half | step tag) words into
+// slot [parity][rank] of EVERY peer's region (own region included).
+NFN_DEVI void peer_push(const PeerArgs& p, double* acc, unsigned long long step, int tid, int nthreads) {
+  const int W = p.world, NV = p.n_values, par = (int)(step & 1ull);
+  const unsigned long long tag = ((step + 1ull) & 0xffffffffull) << 32;
   for (int j = tid; j < NV; j += nthreads) {
-    const unsigned long long bits = atomicExch(reinterpret_cast<unsigned long long*>(p.acc + j), 0ull);
+    const unsigned long long bits = atomicExch(reinterpret_cast<unsigned long long*>(acc + j), 0ull);
     const unsigned long long w0 = (bits & 0xffffffffull) | tag, w1 = (bits >> 32) | tag;
     const size_t off = ((size_t)(par * W + p.rank) * NV + j) * 2;
     for (int q = 0; q < W; ++q) {
@@ -601,18 +603,20 @@ NFN_DEVI void peer_push(const PeerArgs& p, int tid, int nthreads) {
   }
 }
 
-// Completes a pending split-phase exchange on its own (nfn_peer_flush: after the last step of a loop).
-NFN_DEVI void peer_head(const PeerArgs& p) {
-  if (p.world > 0 && p.deferred && p.pending_out)
-    peer_collect(p, p.pending_step, p.pending_out, (int)threadIdx.x, (int)blockDim.x);
+// Head of a launch in split-phase mode: the previous launch's totals go out to the peers.  Called by a few
+// threads of ONE CTA after griddepcontrol.wait (the previous launch has completed, its accumulators are final).
+NFN_DEVI void peer_head(const PeerArgs& p, int tid, int nthreads) {
+  if (p.world > 0 && p.deferred && p.pending_out) peer_push(p, p.acc_prev, p.pending_step, tid, nthreads);
 }
 
 // Tail of a launch: called by every thread of every CTA after the CTA's accumulator atomics.  The last CTA to
 // arrive runs the exchange:
 //   blocking   : push this step's totals, wait for every peer's, sum            (one NVLink round trip + skew)
-//   split-phase: collect the PREVIOUS step's sums (already delivered), then push this step's totals.
-// Collect-before-push keeps slot reuse safe: a rank overwrites the slots of exchange s (with s+2) only after its
-// own collect of s+1 has seen every peer's s+1 words, and a peer pushes s+1 only after it has collected s.
+//   split-phase: collect the PREVIOUS step's sums (pushed from the heads a kernel ago: no wait unless a peer is
+//                more than a kernel behind); this step's totals stay in `acc` for the next launch / the flush.
+// Slot reuse is safe: exchange s+2 is pushed (head of launch s+3) only after the same rank's launch s+2 has
+// collected s+1 from every peer, and a peer pushes s+1 (head of its launch s+2) only after its launch s+1 --
+// collect of s included -- has completed.
 template <int T>
 NFN_DEVI void peer_allreduce(const PeerArgs& p) {
   __shared__ int s_last;
@@ -627,9 +631,8 @@ NFN_DEVI void peer_allreduce(const PeerArgs& p) {
   __threadfence();
   if (p.deferred) {
     if (p.pending_out) peer_collect(p, p.pending_step, p.pending_out, (int)threadIdx.x, T);
-    peer_push(p, (int)threadIdx.x, T);
   } else {
-    peer_push(p, (int)threadIdx.x, T);
+    peer_push(p, p.acc, p.step, (int)threadIdx.x, T);
     peer_collect(p, p.step, p.out, (int)threadIdx.x, T);
   }
   if (threadIdx.x == 0) *p.ticket = 0u;
@@ -694,6 +697,8 @@ NFN_DEVI void chain_body(const ChainArgs& a) {
       if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + r0); }
     }
   }
+
+  if (blockIdx.x == 0) peer_head(a.peer, (int)threadIdx.x, T);   // split-phase: the previous step's totals go out
 
   int slot = 0;  // buffer holding the current tile
   for (; tile < ntiles; tile += gridDim.x) {
@@ -1133,6 +1138,9 @@ NFN_DEVI void chain_body_w(const ChainArgs& a, const TensorMap* tm_t, const Tens
       if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + r0); }
     }
   }
+
+  // split-phase exchange: one warp of CTA 0 sends the previous step's totals to the peers, behind its first loads
+  if (blockIdx.x == 0 && warp == 0) peer_head(a.peer, lane, 32);
 
   CS cs;
   if constexpr (BWD) cs.clear();

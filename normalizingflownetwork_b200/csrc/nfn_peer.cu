@@ -15,7 +15,7 @@
 struct nfn_peer_comm {
   int world = 0, rank = 0, n_values = 0;
   double* base[nfn::kMaxPeers] = {};
-  double* acc = nullptr;       // [n_values] local accumulators (self-resetting)
+  double* acc = nullptr;       // [2][n_values] local accumulators (self-resetting), one set per step parity
   unsigned* ticket = nullptr;  // CTA arrival counter (self-resetting)
   unsigned* status = nullptr;  // sticky device error word (time-outs)
   unsigned long long step = 0; // exchanges issued so far
@@ -26,8 +26,16 @@ struct nfn_peer_comm {
 
 namespace nfn {
 
-__global__ void __launch_bounds__(128) peer_allreduce_kernel(const PeerArgs p) { peer_allreduce<128>(p); }
-__global__ void __launch_bounds__(128) peer_flush_kernel(const PeerArgs p) { peer_head(p); }
+__global__ void __launch_bounds__(128) peer_allreduce_kernel(const PeerArgs p) {
+  peer_head(p, (int)threadIdx.x, 128);
+  peer_allreduce<128>(p);
+}
+// split-phase: send the last launch's totals and collect their sums (one CTA)
+__global__ void __launch_bounds__(128) peer_flush_kernel(const PeerArgs p) {
+  peer_head(p, (int)threadIdx.x, 128);
+  if (p.world > 0 && p.deferred && p.pending_out)
+    peer_collect(p, p.pending_step, p.pending_out, (int)threadIdx.x, 128);
+}
 
 // Arguments of the NEXT exchange.  Nothing in the communicator changes here: the caller commits
 // (peer_commit) only after its launch succeeded, so a failed call leaves this rank's sequence number, parity
@@ -35,7 +43,8 @@ __global__ void __launch_bounds__(128) peer_flush_kernel(const PeerArgs p) { pee
 PeerArgs make_peer_args(nfn_peer_comm* c, double* out) {
   PeerArgs p{};
   for (int i = 0; i < kMaxPeers; ++i) p.base[i] = c->base[i];
-  p.acc = c->acc;
+  p.acc = c->acc + (size_t)(c->step & 1ull) * c->n_values;          // this exchange's accumulators
+  p.acc_prev = c->acc + (size_t)((c->step + 1ull) & 1ull) * c->n_values;  // the previous exchange's
   p.out = out;
   p.ticket = c->ticket;
   p.step = c->step;
@@ -124,8 +133,8 @@ int nfn_peer_comm_create(int world, int rank, int n_values, void* const* regions
     }
     c->base[i] = (double*)regions[i];
   }
-  cudaError_t e = cudaMalloc((void**)&c->acc, (size_t)n_values * sizeof(double) + 16);
-  if (e == cudaSuccess) e = cudaMemset(c->acc, 0, (size_t)n_values * sizeof(double) + 16);
+  cudaError_t e = cudaMalloc((void**)&c->acc, (size_t)2 * n_values * sizeof(double) + 16);
+  if (e == cudaSuccess) e = cudaMemset(c->acc, 0, (size_t)2 * n_values * sizeof(double) + 16);
   if (const char* ev = getenv("NFN_B200_PEER_TIMEOUT_S")) {  // set-up time only, never on a launch path
     const double sec = atof(ev);
     if (sec > 0.0) c->timeout_cycles = (long long)(sec * 2.0e9);
@@ -134,7 +143,7 @@ int nfn_peer_comm_create(int world, int rank, int n_values, void* const* regions
     delete c;
     return cuda_error(e, "cudaMalloc(peer accumulators)");
   }
-  c->ticket = (unsigned*)(c->acc + n_values);
+  c->ticket = (unsigned*)(c->acc + 2 * n_values);
   c->status = c->ticket + 1;
   *comm = c;
   return NFN_OK;
@@ -151,10 +160,10 @@ int nfn_peer_allreduce(nfn_peer_comm* comm, const double* values, double* reduce
   if (!comm || !values || !reduced) return set_error(NFN_ERR_NULL, "comm, values and reduced must be non-NULL");
   cudaStream_t st = (cudaStream_t)stream;
   // accumulate the caller's values into the (zero) local accumulators, then exchange
-  cudaError_t e = cudaMemcpyAsync(comm->acc, values, (size_t)comm->n_values * sizeof(double),
-                                  cudaMemcpyDeviceToDevice, st);
+  const PeerArgs pa = make_peer_args(comm, reduced);
+  cudaError_t e = cudaMemcpyAsync(pa.acc, values, (size_t)comm->n_values * sizeof(double), cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) return cuda_error(e, "cudaMemcpyAsync(values)");
-  int rc = launch_peer_allreduce(make_peer_args(comm, reduced), st);
+  int rc = launch_peer_allreduce(pa, st);
   if (rc == NFN_OK) peer_commit(comm, reduced);
   return rc;
 }
