@@ -555,34 +555,45 @@ NFN_DEVI void st_volatile_u64(unsigned long long* p, unsigned long long v) {
 }
 
 // Collect: sum, in rank order (deterministic), the words every peer pushed into THIS rank's region for exchange
-// `step` and write the totals to `out`.  Any number of threads (strided over the values), no barrier inside.
+// `step` and write the totals to `out`.  Must be called by ALL threads of one CTA (barriers inside).  Work item
+// (value j, peer q) -> one thread: every word pair is requested at once (one L2 latency in the steady state, where
+// everything has long arrived) instead of peer after peer; the per-value sums then run over shared memory.
 // A peer that does not arrive within timeout_cycles is abandoned: NaN in `out` AND the sticky status word is
 // set, which the host reads back (nfn_peer_status) -- a time-out is an error, never a silent NaN.
+constexpr int kPeerChunk = 64;   // values per pass (shared scratch: kPeerChunk x kMaxPeers doubles)
 NFN_DEVI void peer_collect(const PeerArgs& p, unsigned long long step, double* out, int tid, int nthreads) {
+  __shared__ double s_val[kPeerChunk * kMaxPeers];
+  __shared__ int s_timeout;
   const int W = p.world, NV = p.n_values, par = (int)(step & 1ull);
   const unsigned long long tag = ((step + 1ull) & 0xffffffffull) << 32;  // never 0 in the first 2^32 steps
+  const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(p.base[p.rank]) + (size_t)par * W * NV * 2;
   const long long t0 = clock64();
-  for (int j = tid; j < NV; j += nthreads) {
-    const unsigned long long* mine =
-        reinterpret_cast<const unsigned long long*>(p.base[p.rank]) + ((size_t)par * W * NV + j) * 2;
-    double sum = 0.0;
-    bool timeout = false;
-    for (int q = 0; q < W; ++q) {
-      const unsigned long long* src = mine + (size_t)q * NV * 2;
-      unsigned long long a0, a1;
-      while (true) {
-        a0 = ld_volatile_u64(src);
-        a1 = ld_volatile_u64(src + 1);
-        if ((a0 & 0xffffffff00000000ull) == tag && (a1 & 0xffffffff00000000ull) == tag) break;
+  if (tid == 0) s_timeout = 0;
+  for (int j0 = 0; j0 < NV; j0 += kPeerChunk) {
+    const int nj = NV - j0 < kPeerChunk ? NV - j0 : kPeerChunk;
+    __syncthreads();
+    for (int i = tid; i < nj * W; i += nthreads) {
+      const int j = j0 + i / W, q = i % W;
+      const unsigned long long* src = mine + ((size_t)q * NV + j) * 2;
+      unsigned long long a0 = ld_volatile_u64(src), a1 = ld_volatile_u64(src + 1);
+      while ((a0 & 0xffffffff00000000ull) != tag || (a1 & 0xffffffff00000000ull) != tag) {
         if (clock64() - t0 > p.timeout_cycles) {
-          timeout = true;
+          s_timeout = 1;
           break;
         }
+        a0 = ld_volatile_u64(src);
+        a1 = ld_volatile_u64(src + 1);
       }
-      sum += __longlong_as_double((long long)((a0 & 0xffffffffull) | (a1 << 32)));
+      s_val[i] = __longlong_as_double((long long)((a0 & 0xffffffffull) | (a1 << 32)));
     }
-    if (timeout) atomicOr(p.status, 1u);
-    out[j] = timeout ? __longlong_as_double(0x7ff8000000000000ll) : sum;
+    __syncthreads();
+    const bool timeout = s_timeout != 0;
+    for (int jj = tid; jj < nj; jj += nthreads) {
+      double sum = 0.0;
+      for (int q = 0; q < W; ++q) sum += s_val[jj * W + q];
+      out[j0 + jj] = timeout ? __longlong_as_double(0x7ff8000000000000ll) : sum;
+    }
+    if (timeout && tid == 0) atomicOr(p.status, 1u);
   }
 }
 
