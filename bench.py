@@ -336,7 +336,7 @@ class HeadWorkload:
         self.acc_ring = torch.zeros((n_steps + 8, P + 1), dtype=torch.float64, device=device)
         # (the mixture kernels leave the column sums to a second pass over dt: not part of their step here)
         self.want_col = bool(self.bwd and colsum and not self.mdn)
-        self.packed = bool(world > 1 and self.bwd)
+        self.packed = bool((world > 1 or args.force_peer) and self.bwd)
         self.use_peer = bool(self.packed and args.exchange == "peer" and not self.mdn)
         self.comm = None
         if self.use_peer:
@@ -353,7 +353,8 @@ class HeadWorkload:
                 if rank == 0:
                     print("peer exchange unavailable (%s): falling back to NCCL" % exc, file=sys.stderr)
             flag = torch.tensor([ok], device=device)
-            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+            if world > 1:
+                torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
             if int(flag.item()) == 0:
                 if self.comm is not None:
                     self.comm.close()
@@ -611,8 +612,9 @@ def run_ours(args):
     K, W = args.steps, args.warmup
     # N > 1: the per-step exchange couples the ranks, so cold NVLink links / peer mappings and start-up skew
     # would be billed to the first timed steps; top the warm-up up to 30 untimed steps (reported in config)
-    # (NVLink links idle into a low-power state: the untimed warm-up runs for ~50 ms of steps, not for a count)
-    extra_warmup = max(0, 30 - W) if world > 1 else 0
+    # (NVLink links idle into a low-power state and a fresh process group is cold: ~45 ms of untimed steps.  The
+    # count is FIXED: every rank must issue the same number of exchanges, a time-based loop would not)
+    extra_warmup = max(0, 600 - W) if world > 1 else 0
     wl = HeadWorkload(cfg, args, device, rank, world, lib, 3 * K + W + extra_warmup + 64 + (700 if world > 1 else 0),
                       rows=args.rows or None,
                       fwd_only=args.fwd_only, colsum=not args.no_colsum)
@@ -624,14 +626,6 @@ def run_ours(args):
         sampler.start()
     for _ in range(W + extra_warmup):
         wl.step()
-    if world > 1:
-        torch.cuda.synchronize()
-        t_w = time.perf_counter()
-        while time.perf_counter() - t_w < 0.05 and wl.step_no < extra_warmup + W + 600:
-            for _ in range(50):
-                wl.step()
-            torch.cuda.synchronize()
-        extra_warmup = wl.step_no - W
     lib.nfn_launch_count_reset()
     wall0 = time.perf_counter()
     total_ms = wl.time_steps(K)
@@ -966,6 +960,9 @@ def main():
     ap.add_argument("--peer-blocking", action="store_true",
                     help="N > 1, peer exchange: wait for the peers in the last CTA of every launch (round-1 behaviour) "
                          "instead of the split-phase exchange")
+    ap.add_argument("--force-peer", action="store_true",
+                    help="N = 1: run the step through the peer-exchange entry point (a world of one) to measure the "
+                         "protocol's local cost")
     ap.add_argument("--no-colsum", action="store_true",
                     help="leave the in-kernel dt column sums (bias gradient of the emitting layer) out (tuning)")
     ap.add_argument("--no-other-configs", action="store_true",

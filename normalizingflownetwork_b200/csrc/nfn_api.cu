@@ -244,14 +244,35 @@ static int chain_dispatch(const nfn_chain_desc* desc, const ChainArgs& a, bool b
   const int mode = math_mode();
   const ChainKernels* k = memo.kernels;
   cudaError_t e;
+  // Split-phase peer exchange: the warp-tile kernels carry it in one CTA of their own grid; every other kernel
+  // runs without a peer epilogue and is followed by the one-CTA exchange launch.
+  const bool split = a.peer.world > 0 && a.peer.deferred;
+  const int io = chain_io_override();
+  const int P = param_size(desc);
+  const bool want_w = P > 0 && (io >= 0 ? io == 1 : chain_prefers_warp_tile(P, bwd));
   if (k && k->fn[mode][bwd ? 1 : 0]) {
-    const int io = chain_io_override();
-    const bool warp_tile = k->fnw[mode][bwd ? 1 : 0] && (io >= 0 ? io == 1 : chain_prefers_warp_tile(k->P, bwd));
-    e = (warp_tile ? k->fnw : k->fn)[mode][bwd ? 1 : 0](a, st);
+    const bool warp_tile = k->fnw[mode][bwd ? 1 : 0] && want_w;
+    if (split && !warp_tile) {
+      ChainArgs c = a;
+      c.peer.world = 0;
+      e = k->fn[mode][bwd ? 1 : 0](c, st);
+      if (e == cudaSuccess) {
+        int rc = launch_peer_allreduce(a.peer, st);
+        if (rc != NFN_OK) return rc;
+      }
+    } else {
+      e = (warp_tile ? k->fnw : k->fn)[mode][bwd ? 1 : 0](a, st);
+    }
   } else {
     if (!option(kOptForceGeneric)) {
       bool served = false;
-      e = launch_chain_jit(desc, key, a, bwd, mode, st, &served);
+      ChainArgs c = a;
+      if (split && !want_w) c.peer.world = 0;
+      e = launch_chain_jit(desc, key, c, bwd, mode, st, &served);
+      if (e == cudaSuccess && served && split && !want_w) {
+        int rc = launch_peer_allreduce(a.peer, st);
+        if (rc != NFN_OK) return rc;
+      }
       if (e != cudaSuccess || served) return cuda_error(e, key.c_str());
     }
     ChainArgs g = a;

@@ -178,10 +178,10 @@ struct PeerArgs {
   unsigned long long step;     // sequence number of this launch's exchange
   int world, rank, n_values;
   // Split-phase mode (deferred != 0): a launch leaves its totals in the local accumulators `acc` (two sets,
-  // alternating by step parity).  The NEXT launch on the communicator pushes them to the peers from its HEAD (one
-  // warp of CTA 0, behind that CTA's first loads) and collects the cross-rank sums at its TAIL (`pending_step`,
-  // into `pending_out`): the NVLink round trip and up to a kernel duration of rank skew overlap with a whole
-  // kernel of tile work, and a kernel's completion never waits for remote stores of its own.
+  // alternating by step parity) and does NOTHING else at its tail.  The NEXT launch on the communicator gives up
+  // one CTA of its persistent grid to the exchange: that CTA pushes the previous totals to the peers, collects the
+  // cross-rank sums (`pending_step`, into `pending_out`) and exits, all while the other CTAs stream tiles.  No
+  // ticket, no fence, no round trip on any kernel's critical path; the price is 1 / grid of the tile throughput.
   int deferred;
   double* pending_out;         // nullptr: nothing pending
   double* acc_prev;            // the accumulators the previous launch filled
@@ -614,20 +614,21 @@ NFN_DEVI void peer_push(const PeerArgs& p, double* acc, unsigned long long step,
   }
 }
 
-// Head of a launch in split-phase mode: the previous launch's totals go out to the peers.  Called by a few
-// threads of ONE CTA after griddepcontrol.wait (the previous launch has completed, its accumulators are final).
-NFN_DEVI void peer_head(const PeerArgs& p, int tid, int nthreads) {
-  if (p.world > 0 && p.deferred && p.pending_out) peer_push(p, p.acc_prev, p.pending_step, tid, nthreads);
+// Split-phase exchange of the PREVIOUS launch's totals: push them to every peer, collect every peer's, write the
+// sums.  Whole CTA (barriers inside); runs after griddepcontrol.wait, i.e. the previous launch has completed and
+// its accumulators are final.  Slot reuse is safe: exchange s+2 is pushed (by launch s+3) only after the same
+// rank's launch s+2 has collected s+1 from every peer, and a peer pushes s+1 only after its launch s+1 -- its
+// collect of s included -- has completed.
+NFN_DEVI void peer_exchange_prev(const PeerArgs& p, int tid, int nthreads) {
+  if (p.pending_out) {
+    peer_push(p, p.acc_prev, p.pending_step, tid, nthreads);
+    peer_collect(p, p.pending_step, p.pending_out, tid, nthreads);
+  }
 }
 
-// Tail of a launch: called by every thread of every CTA after the CTA's accumulator atomics.  The last CTA to
-// arrive runs the exchange:
-//   blocking   : push this step's totals, wait for every peer's, sum            (one NVLink round trip + skew)
-//   split-phase: collect the PREVIOUS step's sums (pushed from the heads a kernel ago: no wait unless a peer is
-//                more than a kernel behind); this step's totals stay in `acc` for the next launch / the flush.
-// Slot reuse is safe: exchange s+2 is pushed (head of launch s+3) only after the same rank's launch s+2 has
-// collected s+1 from every peer, and a peer pushes s+1 (head of its launch s+2) only after its launch s+1 --
-// collect of s included -- has completed.
+// Blocking exchange at the tail of a launch: called by every thread of every CTA after the CTA's accumulator
+// atomics.  The last CTA to arrive pushes this step's totals, waits for every peer's and sums them: one NVLink
+// round trip plus the rank skew on the kernel's tail, `out` complete when the kernel completes.
 template <int T>
 NFN_DEVI void peer_allreduce(const PeerArgs& p) {
   __shared__ int s_last;
@@ -640,12 +641,8 @@ NFN_DEVI void peer_allreduce(const PeerArgs& p) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (p.deferred) {
-    if (p.pending_out) peer_collect(p, p.pending_step, p.pending_out, (int)threadIdx.x, T);
-  } else {
-    peer_push(p, p.acc, p.step, (int)threadIdx.x, T);
-    peer_collect(p, p.step, p.out, (int)threadIdx.x, T);
-  }
+  peer_push(p, p.acc, p.step, (int)threadIdx.x, T);
+  peer_collect(p, p.step, p.out, (int)threadIdx.x, T);
   if (threadIdx.x == 0) *p.ticket = 0u;
 }
 
@@ -708,8 +705,6 @@ NFN_DEVI void chain_body(const ChainArgs& a) {
       if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + r0); }
     }
   }
-
-  if (blockIdx.x == 0) peer_head(a.peer, (int)threadIdx.x, T);   // split-phase: the previous step's totals go out
 
   int slot = 0;  // buffer holding the current tile
   for (; tile < ntiles; tile += gridDim.x) {
@@ -815,7 +810,8 @@ NFN_DEVI void chain_body(const ChainArgs& a) {
       for (int j = threadIdx.x; j < P; j += T) atomicAdd(a.dt_colsum + j, (double)s_col[j]);
     }
   }
-  if (a.peer.world > 0) peer_allreduce<T>(a.peer);
+  // (split-phase mode is served by a separate one-CTA exchange launch for this kernel generation, see chain_dispatch)
+  if (a.peer.world > 0 && !a.peer.deferred) peer_allreduce<T>(a.peer);
 }
 
 template <class Spec, bool BWD, class M, int T, int NB, int MINB>
@@ -1109,8 +1105,17 @@ NFN_DEVI void chain_body_w(const ChainArgs& a, const TensorMap* tm_t, const Tens
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
+  // split-phase exchange: the LAST CTA of the grid carries no tiles; it exchanges the previous launch's totals with
+  // the peers while the other CTAs stream, and exits.  (A grid of one CTA does both, one after the other.)
+  const bool xch = a.peer.world > 0 && a.peer.deferred != 0;
+  const int tile_ctas = (xch && gridDim.x > 1) ? (int)gridDim.x - 1 : (int)gridDim.x;
+  if (xch) {
+    if ((int)blockIdx.x == tile_ctas || gridDim.x == 1) peer_exchange_prev(a.peer, (int)threadIdx.x, T);
+    if ((int)blockIdx.x == tile_ctas) return;
+  }
+
   const long long nwt = (a.B + 31) / 32;                        // warp tiles
-  const long long GW = (long long)gridDim.x * NW;               // warps in the grid
+  const long long GW = (long long)tile_ctas * NW;               // tile-carrying warps in the grid
   long long wt = (long long)blockIdx.x * NW + warp;
   // the last tile of a linear-layout kernel may be ragged: its bytes are not a whole number of 16-byte
   // chunks in general, so it is moved with plain loads / stores by the lanes (one warp, once per launch)
@@ -1149,9 +1154,6 @@ NFN_DEVI void chain_body_w(const ChainArgs& a, const TensorMap* tm_t, const Tens
       if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + r0); }
     }
   }
-
-  // split-phase exchange: one warp of CTA 0 sends the previous step's totals to the peers, behind its first loads
-  if (blockIdx.x == 0 && warp == 0) peer_head(a.peer, lane, 32);
 
   CS cs;
   if constexpr (BWD) cs.clear();
@@ -1295,7 +1297,7 @@ NFN_DEVI void chain_body_w(const ChainArgs& a, const TensorMap* tm_t, const Tens
       }
     }
   }
-  if (a.peer.world > 0) peer_allreduce<T>(a.peer);
+  if (a.peer.world > 0 && !a.peer.deferred) peer_allreduce<T>(a.peer);   // blocking exchange at the tail
 }
 
 template <class Spec, bool BWD, class M, int NW, int NB, int MINB>

@@ -184,7 +184,8 @@ cudaError_t launch_chain_w(const ChainArgs& a, cudaStream_t st) {
       if (encode_row_tensor_map(&tm_t, a.t, a.B, P, L::W) != NFN_OK) return cudaErrorInvalidValue;
       if (BWD && encode_row_tensor_map(&tm_dt, a.dt, a.B, P, L::W) != NFN_OK) return cudaErrorInvalidValue;
     }
-    const long long ntiles = (a.B + NW * 32 - 1) / (NW * 32);
+    // split-phase peer exchange: the last CTA of the grid carries the exchange instead of tiles
+    const long long ntiles = (a.B + NW * 32 - 1) / (NW * 32) + ((a.peer.world > 0 && a.peer.deferred) ? 1 : 0);
     long long grid = (long long)di.sm_count * cfg.ctas_per_sm;
     if (grid > ntiles) grid = ntiles;
     cudaLaunchConfig_t lc = {};

@@ -321,7 +321,7 @@ cudaError_t launch_chain_jit(const nfn_chain_desc* desc, const std::string& key,
         if (bwd && encode_row_tensor_map(&tm_dt, a.dt, a.B, P, W) != NFN_OK) return cudaErrorInvalidValue;
       }
       const int b = bwd ? 1 : 0, T = ent->geo[b].T;
-      const long long ntiles = (a.B + T - 1) / T;
+      const long long ntiles = (a.B + T - 1) / T + ((a.peer.world > 0 && a.peer.deferred) ? 1 : 0);  // + the exchange CTA
       long long grid = (long long)device_info().sm_count * ent->ctas_per_sm[b];
       if (grid > ntiles) grid = ntiles;
       ChainArgs args = a;
@@ -343,6 +343,8 @@ cudaError_t launch_chain_jit(const nfn_chain_desc* desc, const std::string& key,
       }
       return ce;
     }
+    // (the warp-tile build failed) a split-phase exchange needs its CTA: leave the launch to the generic path
+    if (a.peer.world > 0 && a.peer.deferred) return cudaSuccess;
   }
   const ChainGeometry geo[2] = {chain_geometry(P, false), chain_geometry(P, true)};
   const char* const names[2] = {"nfn_jit_chain_fwd", "nfn_jit_chain_fwd_bwd"};

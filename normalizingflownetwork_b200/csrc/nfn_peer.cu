@@ -26,15 +26,14 @@ struct nfn_peer_comm {
 
 namespace nfn {
 
+// one CTA: blocking mode exchanges THIS step's totals, split-phase mode the previous step's
 __global__ void __launch_bounds__(128) peer_allreduce_kernel(const PeerArgs p) {
-  peer_head(p, (int)threadIdx.x, 128);
-  peer_allreduce<128>(p);
+  if (p.deferred) peer_exchange_prev(p, (int)threadIdx.x, 128);
+  else peer_allreduce<128>(p);
 }
 // split-phase: send the last launch's totals and collect their sums (one CTA)
 __global__ void __launch_bounds__(128) peer_flush_kernel(const PeerArgs p) {
-  peer_head(p, (int)threadIdx.x, 128);
-  if (p.world > 0 && p.deferred && p.pending_out)
-    peer_collect(p, p.pending_step, p.pending_out, (int)threadIdx.x, 128);
+  if (p.world > 0 && p.deferred) peer_exchange_prev(p, (int)threadIdx.x, 128);
 }
 
 // Arguments of the NEXT exchange.  Nothing in the communicator changes here: the caller commits
