@@ -2,8 +2,7 @@
 cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out; O=gpurun_out
 N=${1:-2}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-timeout 300 python -m pytest tests/test_peer_gpu.py -m gpu -x -q > $O/pytest_peer_n$N.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_peer_n$N.log
-timeout 600 $TR bench.py --gpus $N --steps 20 --warmup 5 --peer-blocking --no-other-configs > /dev/null 2>&1
+timeout 600 python -m pytest tests/test_peer_gpu.py tests/test_dp_fit_gpu.py -m gpu -x -q > $O/pytest_peer_n$N.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_peer_n$N.log
 timeout 600 $TR bench.py --gpus $N --steps 20 --warmup 5 > $O/bench_n$N.json 2> $O/bench_n$N.err; echo "bench n$N rc=$?"
 timeout 600 $TR bench.py --gpus $N --steps 20 --warmup 5 --peer-blocking --no-other-configs > $O/bench_n${N}_blocking.json 2> $O/bench_n${N}_blocking.err; echo "rc=$?"
 timeout 600 $TR bench.py --gpus $N --steps 20 --warmup 5 --exchange nccl --no-other-configs > $O/bench_n${N}_nccl.json 2> $O/bench_n${N}_nccl.err; echo "rc=$?"
