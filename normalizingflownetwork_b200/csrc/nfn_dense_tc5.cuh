@@ -20,13 +20,12 @@
 //                              that only holds level-2 chunks of dt stops after [h0 | 1]: N = H + 16)
 //   D2 row r -> dh[r, :] ; the D3 lanes (level, p) leave as atomics into dW[:, p], db[p].
 //
-// Two pipelines share these pieces:
-//   * pipe 1 (forward-only kernels, and backward shapes whose accumulators do not fit twice): the 128 compute
-//     threads do everything but the issuing; a second warpgroup's first lane issues the MMAs.
-//   * pipe 2 (backward, the default): the second warpgroup also WORKS.  Its thread r loads and splits the h row,
-//     splits the dt row, drains dh and dW; the compute threads only run the flows and hand their dt row over
-//     through TENSOR MEMORY (tcgen05.st into the D1 buffer their t row came from, double-buffered).  The compute
-//     warps lose a third of their instructions and the SM gains eight more warps to issue from.
+// Roles: the 128 threads of warpgroup 0 own one row each (t row out of TMEM, flows, dt split, dh drain); in
+// warpgroup 1 the first warp's elected lane issues every MMA, and the other three warps stage the h tiles
+// (global -> three bf16 levels -> smem ring, one tile ahead), so that no compute thread touches h at all.
+// (A second pipeline, in which warpgroup 1 also split the dt rows handed over through tensor memory, was built
+// and measured slower -- the hand-over chain dt -> split -> GEMM 2/3 -> drain serialises behind the issuing
+// warp; profiles/tuning_r02.md section 6, commit "experimental warp-specialised backward pipeline".)
 //
 // Why bf16 levels and not TF32: the backward GEMMs contract over the ROWS of the tile, i.e. they need the
 // dt and h tiles transposed.  With the no-swizzle canonical layout (8 x 16-byte core matrices) an
@@ -46,20 +45,14 @@ typedef unsigned int uint32_t;
 
 #include "nfn_dense_chain.cuh"
 
-#ifndef NFN_TC5_PIPE2
-#define NFN_TC5_PIPE2 1   // 0: every backward kernel on pipe 1 (A/B builds)
-#endif
-#ifndef NFN_TC5_HREGS
-#define NFN_TC5_HREGS 80  // registers per thread of the staging warpgroup on pipe 2 (the compute warpgroup gets 256 - this)
-#endif
-
 namespace nfn {
 namespace tc5 {
 
 constexpr int kRows = 128;     // rows per tile == compute threads per CTA == TMEM lanes
-// + a second warpgroup: its first lane issues every tcgen05.mma, and on pipe 2 its threads do the operand
-// staging.  A whole warpgroup because registers are handed out per warpgroup (setmaxnreg).
+// + a second warpgroup: its first warp issues every tcgen05.mma, its other three warps stage the h tiles.
+// A whole warpgroup because registers are handed out per warpgroup (setmaxnreg).
 constexpr int kThreads = 256;
+constexpr int kStagers = 96;    // threads of warps 5..7, which stage the h tiles
 __host__ __device__ constexpr int round16(int x) { return (x + 15) / 16 * 16; }
 __host__ __device__ constexpr unsigned pow2_cols(int c) { return c <= 32 ? 32u : c <= 64 ? 64u : c <= 128 ? 128u : c <= 256 ? 256u : 512u; }
 
@@ -98,12 +91,7 @@ __host__ __device__ constexpr int g_cols3(int P, int H, int npass) {   // TMEM c
   for (int j = 0; j < npass; ++j) c += g_N3(P, H, j);
   return c;
 }
-// pipe 2 needs two D1 buffers next to D2 and D3
-__host__ __device__ constexpr bool g_pipe2(int P, int H, bool bwd) {
-  return bwd && NFN_TC5_PIPE2 != 0 && 2 * round16(P) + 3 * H + g_cols3(P, H, g_NP3(P)) <= 256;
-}
-__host__ __device__ constexpr int g_nD1(int P, int H, bool bwd) { return g_pipe2(P, H, bwd) ? 2 : 1; }
-__host__ __device__ constexpr int g_cD2(int P, int H, bool bwd) { return g_nD1(P, H, bwd) * round16(P); }
+__host__ __device__ constexpr int g_cD2(int P, int H, bool bwd) { return round16(P); }
 __host__ __device__ constexpr int g_cD3(int P, int H, bool bwd) { return g_cD2(P, H, bwd) + 3 * H; }
 __host__ __device__ constexpr unsigned tmem_cols(int P, int H, bool bwd) {
   return pow2_cols(bwd ? g_cD3(P, H, bwd) + g_cols3(P, H, g_NP3(P)) : round16(P));
@@ -112,13 +100,13 @@ __host__ __device__ constexpr unsigned tmem_cols(int P, int H, bool bwd) {
 // (rounded down to 8); the second warpgroup keeps regs_issuer of it and the compute warpgroup gets the rest.
 // The sum must never exceed the CTA's pool, or setmaxnreg.inc would wait forever.
 __host__ __device__ constexpr int regs_launch(int minb) { return 65536 / (minb * kThreads) / 8 * 8; }
-__host__ __device__ constexpr int regs_issuer(int minb, bool pipe2) { return pipe2 ? NFN_TC5_HREGS : (minb <= 2 ? 56 : 32); }
-__host__ __device__ constexpr int regs_compute(int minb, bool pipe2) { return 2 * regs_launch(minb) - regs_issuer(minb, pipe2); }
+__host__ __device__ constexpr int regs_issuer(int minb) { return 56; }   // issuing warp + the three h-staging warps (rows prefetched in registers)
+__host__ __device__ constexpr int regs_compute(int minb) { return 2 * regs_launch(minb) - regs_issuer(minb); }
 // resident CTAs per SM the kernel's register plan is built for (shared memory and TMEM columns permitting)
 __host__ __device__ constexpr int min_blocks(int P, int H, bool bwd) {
   const int by_smem = (int)((227u * 1024u) / (smem_bytes(P, H, bwd) + 1024u));
   const int by_tmem = (int)(512u / tmem_cols(P, H, bwd));
-  const int want = bwd ? 2 : 3;   // compute warpgroup registers: 184-200 (fwd+bwd), 128 (forward)
+  const int want = bwd ? 2 : 3;   // compute warpgroup registers: 200 (fwd+bwd), 104 (forward)
   const int cap = by_smem < by_tmem ? by_smem : by_tmem;
   // never below 2: this value fixes the register plan (256 threads x 128 registers at launch, re-split by
   // setmaxnreg); when shared memory allows a single CTA the plan is simply the 2-CTA one
@@ -172,8 +160,7 @@ struct Geo {
   static constexpr unsigned kBytes = smem_bytes(P, H, BWD);
   // MN-major reads of the dt tiles with M = 128 run (16 - PN/8) chunks past the tile: what follows must be ours
   static_assert(!BWD || 6 * kW >= (unsigned)(16 * NP3 - 3 * CL) * 128, "operand over-read must stay in the CTA's smem");
-  // TMEM columns: D1 [PN] (x 2 on pipe 2) | D2 [3H: dt W0^T | dt W1^T | dt W2^T] | D3 [passes: dt^T h0 | db .. | dt^T h1 | dt^T h2]
-  static constexpr bool kPipe2 = g_pipe2(P, H, BWD);
+  // TMEM columns: D1 [PN] | D2 [3H: dt W0^T | dt W1^T | dt W2^T] | D3 [passes: dt^T h0 | db .. | dt^T h1 | dt^T h2]
   static constexpr int cD1 = 0, cD2 = g_cD2(P, H, BWD), cD3 = g_cD3(P, H, BWD);
   __host__ __device__ static constexpr int cD3p(int j) { return cD3 + g_cols3(P, H, j); }
   static constexpr unsigned kCols = tmem_cols(P, H, BWD);
@@ -216,8 +203,6 @@ NFN_DEVI void mbar_wait(unsigned bar, unsigned parity) {
 NFN_DEVI void mbar_arrive(unsigned bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// the 128 threads of the second warpgroup (named barrier 1; barrier 0 is __syncthreads)
-NFN_DEVI void helper_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 NFN_DEVI void tmem_alloc(unsigned smem_dst, unsigned cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -255,7 +240,7 @@ NFN_DEVI bool elect_one() {
 NFN_DEVI void mma_commit(unsigned bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// 16 / 8 consecutive columns of this thread's TMEM lane
+// 16 consecutive columns of this thread's TMEM lane
 NFN_DEVI void tmem_ld16(unsigned taddr, unsigned (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -264,21 +249,7 @@ NFN_DEVI void tmem_ld16(unsigned taddr, unsigned (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
-NFN_DEVI void tmem_ld8(unsigned taddr, unsigned (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
-NFN_DEVI void tmem_st16(unsigned taddr, const unsigned (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
 NFN_DEVI void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-NFN_DEVI void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // N columns (multiple of 16) of this thread's lane -> floats; the values are pinned behind the wait
 template <int N>
 NFN_DEVI void tmem_load_row(unsigned taddr, float (&out)[N]) {
@@ -294,44 +265,6 @@ NFN_DEVI void tmem_load_row(unsigned taddr, float (&out)[N]) {
       asm volatile("" : "+r"(r[i][j]));  // a use the compiler cannot hoist above the wait
       out[16 * i + j] = __uint_as_float(r[i][j]);
     }
-}
-// 8 columns -> floats (one wait per call)
-NFN_DEVI void tmem_load8(unsigned taddr, float (&out)[8]) {
-  unsigned r[8];
-  tmem_ld8(taddr, r);
-  tmem_ld_wait();
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    asm volatile("" : "+r"(r[j]));
-    out[j] = __uint_as_float(r[j]);
-  }
-}
-// three 8-column blocks with one wait
-NFN_DEVI void tmem_load8x3(unsigned t0, unsigned t1, unsigned t2, float (&o0)[8], float (&o1)[8], float (&o2)[8]) {
-  unsigned r0[8], r1[8], r2[8];
-  tmem_ld8(t0, r0);
-  tmem_ld8(t1, r1);
-  tmem_ld8(t2, r2);
-  tmem_ld_wait();
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    asm volatile("" : "+r"(r0[j]), "+r"(r1[j]), "+r"(r2[j]));
-    o0[j] = __uint_as_float(r0[j]);
-    o1[j] = __uint_as_float(r1[j]);
-    o2[j] = __uint_as_float(r2[j]);
-  }
-}
-// floats -> N columns of this thread's lane (the caller waits: tmem_st_wait)
-template <int N>
-NFN_DEVI void tmem_store_row(unsigned taddr, const float (&in)[N]) {
-  static_assert(N % 16 == 0, "16-column granules");
-#pragma unroll
-  for (int i = 0; i < N / 16; ++i) {
-    unsigned r[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(in[16 * i + j]);
-    tmem_st16(taddr + 16u * i, r);
-  }
 }
 NFN_DEVI void sts_u4(unsigned saddr, unsigned a, unsigned b, unsigned c, unsigned d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -531,14 +464,16 @@ NFN_DEVI void issue_gemm23(unsigned tmem_base, unsigned sbase, unsigned a_off, b
   __syncwarp();
 }
 
-// ------------------------------------------------------------------ pipe 1: compute threads do the staging
+// ------------------------------------------------------------------ the fused body
 template <class Spec, int H, bool BWD, class M, int MINB>
-NFN_DEVI void dense_tc5_body1(const DenseArgs& a) {
-  constexpr int kRegsIssuer = regs_issuer(MINB, false), kRegsCompute = regs_compute(MINB, false);
+NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
+  constexpr int kRegsIssuer = regs_issuer(MINB), kRegsCompute = regs_compute(MINB);
   static_assert(kRows * (kRegsIssuer + kRegsCompute) <= kThreads * regs_launch(MINB), "register pool");
   static_assert(kRegsCompute <= 232 && kRegsCompute % 8 == 0 && kRegsIssuer % 8 == 0, "setmaxnreg range");
   constexpr int D = Spec::D;
   constexpr int P = Spec::P();
+  static_assert(P > 0 && P <= 128, "1..128 parameter columns");
+  static_assert(H % 16 == 0 && H >= 16 && H <= 64, "hidden width must be 16, 32, 48 or 64");
   using G = Geo<P, H, BWD>;
   constexpr int PN = G::PN, T = kRows, NT = kThreads;
   // the parameter row lives in REGISTERS (straight out of TMEM): every access of the flow code is a
@@ -550,9 +485,11 @@ NFN_DEVI void dense_tc5_body1(const DenseArgs& a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double red[NT / 32];
   const unsigned sbase = smem_u32(smem_raw);
-  // bar1 / bar2: tensor pipe -> compute threads (GEMM 1 done / GEMM 2+3 done);
-  // bar_h / bar_d: compute threads -> issuing thread (h tile written and D1 consumed / dt tiles written and D2, D3 drained)
-  const unsigned bar1 = sbase + G::oBar, bar2 = bar1 + 8, bar_h = bar1 + 16, bar_d = bar1 + 24, tmem_slot = bar1 + 64;
+  // bar1 / bar2: tensor pipe -> compute threads and stagers (GEMM 1 done / GEMM 2+3 done);
+  // bar_h / bar_d: compute threads -> issuing thread (D1 consumed / dt tiles written and D2, D3 drained);
+  // bar_hw: stagers -> issuing thread (h tile written)
+  const unsigned bar1 = sbase + G::oBar, bar2 = bar1 + 8, bar_h = bar1 + 16, bar_d = bar1 + 24, bar_hw = bar1 + 32,
+                 tmem_slot = bar1 + 64;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const long long ntiles = (a.B + T - 1) / T;
@@ -563,6 +500,7 @@ NFN_DEVI void dense_tc5_body1(const DenseArgs& a) {
     mbar_init(bar2, 1);
     mbar_init(bar_h, T);
     mbar_init(bar_d, T);
+    mbar_init(bar_hw, kStagers);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, G::kCols);
@@ -576,23 +514,9 @@ NFN_DEVI void dense_tc5_body1(const DenseArgs& a) {
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);   // the same value in every lane: say so
   const unsigned lane_base = tmem_base + ((unsigned)(warp * 32) << 16);
 
-  // this thread's row of the next tile: h (registers), y, upstream cotangent
-  float h_nxt[H];
+  // this thread's row of the next tile: y, upstream cotangent
   float y_nxt[D];
   float g_nxt = 1.0f;
-  auto fetch_h = [&](long long tile) {
-    const long long r = tile * T + tid;
-#pragma unroll
-    for (int i = 0; i < H; ++i) h_nxt[i] = 0.0f;
-    if (tile < ntiles && r < a.B) {
-      const float4* src = reinterpret_cast<const float4*>(a.h + r * H);
-#pragma unroll
-      for (int c = 0; c < H / 4; ++c) {
-        const float4 v = __ldg(src + c);
-        h_nxt[4 * c] = v.x; h_nxt[4 * c + 1] = v.y; h_nxt[4 * c + 2] = v.z; h_nxt[4 * c + 3] = v.w;
-      }
-    }
-  };
   auto fetch_y = [&](long long tile) {
     const long long r = tile * T + tid;
     if (tile < ntiles && r < a.B) {
@@ -604,7 +528,6 @@ NFN_DEVI void dense_tc5_body1(const DenseArgs& a) {
   for (int i = 0; i < D; ++i) y_nxt[i] = 0.0f;
   long long tile = blockIdx.x;
 
-  const unsigned a_row = sbase + G::oA + (tid >> 3) * kGrpA + (tid & 7) * 16;  // this thread's row in the h tile
   const unsigned d_row = sbase + G::oD + (tid >> 3) * kGrpD + (tid & 7) * 16;   // ... in the dt tile
   float ls_hi = 0.0f, ls_lo = 0.0f;   // this thread's sum of logp (compensated)
   // GEMM 3, pass j: TMEM lane m holds chunk 16 j + m / 8 of the [level 0 | level 1 | level 2] row groups, i.e.
@@ -619,10 +542,6 @@ NFN_DEVI void dense_tc5_body1(const DenseArgs& a) {
   float dw_acc[kRegAcc ? H : 1], db_acc = 0.0f;
 #pragma unroll
   for (int k = 0; k < (kRegAcc ? H : 1); ++k) dw_acc[k] = 0.0f;
-  auto split_h = [&](int buf) {
-#pragma unroll
-    for (int c = 0; c < H / 8; ++c) store_levels8(a_row + buf * G::kA + c * 128, G::lvlA(1), G::lvlA(2), h_nxt + 8 * c);
-  };
   // dh row of a finished tile out of TMEM (sum of the three W-level blocks, smallest first) -> global
   auto drain_backward = [&](long long r_done) {
     // 16 hidden columns at a time: three level blocks in, one sum out (bounded register footprint for wide H)
@@ -685,36 +604,86 @@ NFN_DEVI void dense_tc5_body1(const DenseArgs& a) {
   // (b) GEMM 1 of the NEXT tile is issued as soon as this tile's t row has left TMEM, a whole flow sweep
   //     before its result is needed, and GEMM 2 / 3 of this tile complete behind the next tile's flows:
   //     dh / dW are collected one tile late.
-  //   compute, tile i: wait GEMM 1(i) -> t row -> split h(i+1) -> arrive bar_h -> flows -> [wait GEMM 2/3(i-1),
-  //                    drain] -> split dt(i) -> arrive bar_d
-  //   issuer,  tile i: wait bar_h -> GEMM 1(i+1) -> wait bar_d -> GEMM 2/3(i)
+  //   compute, tile i: wait GEMM 1(i) -> t row -> arrive bar_h -> flows -> [wait GEMM 2/3(i-1), drain] ->
+  //                    split dt(i) -> arrive bar_d
+  //   stagers, tile i: (loads of h(i) in flight) wait GEMM 1(i-1) -> split h(i) -> ring slot i % NA -> arrive bar_hw
+  //   issuer,  tile i: wait bar_h, bar_hw -> GEMM 1(i+1) -> wait bar_d -> GEMM 2/3(i)
   if (tid >= T) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssuer));
     if (warp == T / 32) {
       unsigned k = 0;
       mbar_wait(bar_h, 0);
+      mbar_wait(bar_hw, 0);
       issue_gemm1<P, H, BWD>(tmem_base + G::cD1, sbase, 0u, bar1);
       for (long long tl = blockIdx.x; tl < ntiles; tl += gridDim.x, ++k) {
         const int buf = (int)(k % G::NA);
         mbar_wait(bar_h, (k + 1) & 1);
-        if (tl + gridDim.x < ntiles)
+        if (tl + gridDim.x < ntiles) {
+          mbar_wait(bar_hw, (k + 1) & 1);
           issue_gemm1<P, H, BWD>(tmem_base + G::cD1, sbase, (unsigned)((k + 1) % G::NA) * G::kA, bar1);
+        }
         if constexpr (BWD) {
           mbar_wait(bar_d, k & 1);
           issue_gemm23<P, H>(tmem_base, sbase, (unsigned)buf * G::kA, (k % kFlush) == 0, bar2);
         }
       }
+    } else {
+      // ---- stagers (warps 5..7): the h tile of every tile of this CTA, global -> three bf16 levels -> ring slot.
+      // Work item = (8-column chunk c, row r), chunk-major, so that 8 consecutive threads write 8 consecutive
+      // rows of one chunk: 128 contiguous bytes per level, conflict-free; each reads 32 bytes of its row.
+      // Ring slot p % NA was last read by GEMM 1 / GEMM 3 of tile p - NA, all issued before GEMM 1(p-1): the
+      // commit behind GEMM 1(p-1) (bar1) covers every earlier MMA of the issuing thread, so one wait frees the slot
+      // -- and keeps this loop exactly one tile ahead of the flows, which is also what orders the phases of bar_hw.
+      constexpr int kItems = kRows * (H / 8);
+      constexpr int kPer = (kItems + kStagers - 1) / kStagers;   // items per thread: 3 (H = 16) .. 11 (H = 64)
+      constexpr bool kPrefetch = kPer <= 3;                       // rows held in registers across the wait
+      const int ht = tid - (kThreads - kStagers);
+      unsigned p = 0;
+      for (long long tl = blockIdx.x; tl < ntiles; tl += gridDim.x, ++p) {
+        const unsigned slot = sbase + G::oA + (p % G::NA) * G::kA;
+        float v[kPrefetch ? kPer : 1][8];
+        auto load_item = [&](int item, float (&o)[8]) {
+          const long long r = tl * T + (item & (kRows - 1));
+          if (item < kItems && r < a.B) {
+            const float4* src = reinterpret_cast<const float4*>(a.h + r * H + 8 * (item >> 7));
+            const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+            o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v0.w; o[4] = v1.x; o[5] = v1.y; o[6] = v1.z; o[7] = v1.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = 0.0f;   // rows past B stage zeros: they add nothing to dW / db
+          }
+        };
+        auto store_item = [&](int item, const float (&o)[8]) {
+          if (item < kItems) {
+            const int r = item & (kRows - 1), c = item >> 7;
+            store_levels8(slot + (r >> 3) * kGrpA + c * 128 + (r & 7) * 16, G::lvlA(1), G::lvlA(2), o);
+          }
+        };
+        if constexpr (kPrefetch) {
+#pragma unroll
+          for (int i = 0; i < kPer; ++i) load_item(ht + i * kStagers, v[i]);
+        }
+        if (p > 0) mbar_wait(bar1, (p - 1) & 1);
+        if constexpr (kPrefetch) {
+#pragma unroll
+          for (int i = 0; i < kPer; ++i) store_item(ht + i * kStagers, v[i]);
+        } else {
+#pragma unroll 1
+          for (int i = 0; i < kPer; ++i) {
+            load_item(ht + i * kStagers, v[0]);
+            store_item(ht + i * kStagers, v[0]);
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_hw);
+      }
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute));
-    fetch_h(tile);
-    split_h(0);
-    fence_proxy_async();
-    mbar_arrive(bar_h);
-    fetch_h(tile + gridDim.x);
+    mbar_arrive(bar_h);   // phase 0: D1 is free
     fetch_y(tile);
 
-    unsigned it = 0;          // tiles done by this CTA: mbarrier phase parity, h tile in use
+    unsigned it = 0;          // tiles done by this CTA: mbarrier phase parity
     long long r_prev = a.B;   // this thread's row of the previous tile (B: none)
     for (; tile < ntiles; tile += gridDim.x, ++it) {
       float z[D];
@@ -729,12 +698,9 @@ NFN_DEVI void dense_tc5_body1(const DenseArgs& a) {
       float row[PN];
       tmem_load_row<PN>(lane_base + G::cD1, row);
 
-      // ---- next tile's h row (fetched one tile ago) -> its h tile; D1 has been read: GEMM 1(i+1) may go
-      split_h((int)((it + 1) % G::NA));
-      fence_proxy_async();
+      // ---- D1 has been read: GEMM 1(i+1) may go
       tc_fence_before();
       mbar_arrive(bar_h);
-      fetch_h(tile + 2 * (long long)gridDim.x);   // consumed at the top of the next iteration
       fetch_y(tile + gridDim.x);
 
       // ---- per-row flow chain (registers), dt written in place over t
@@ -813,327 +779,6 @@ NFN_DEVI void dense_tc5_body1(const DenseArgs& a) {
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, G::kCols);
-}
-
-// ------------------------------------------------------------------ pipe 2: warp-specialised backward
-// Per CTA tile k (this CTA's k-th tile), three actors:
-//   compute thread r (warpgroup 0, most of the registers):
-//       wait GEMM 1(k) -> t row out of D1[k & 1] -> flows forward + reverse -> dt row back INTO D1[k & 1]
-//       (tcgen05.st) -> arrive bar_t[k & 1].  Nothing else: no splitting, no shared-memory tile traffic.
-//   helper thread r (warpgroup 1), in this order:
-//       wait GEMM 2/3(k-1) -> dh row of tile k-1 out of D2 -> global (dW / db every 16 tiles)
-//       split the h row of tile k+2 (prefetched one tile earlier still) -> h ring -> arrive bar_hw
-//       wait bar_t[k & 1] -> dt row out of D1[k & 1] -> three bf16 levels -> dt tile -> arrive bar_d
-//   issuing lane (first warp of warpgroup 1, after its helper duties):
-//       wait bar_d -> GEMM 1(k+2) into D1[k & 1], then GEMM 2/3(k)
-// Barrier phases cannot alias: bar1 and bar_t alternate between two barriers (a producer would have to be two
-// tiles ahead of a consumer, which the chain GEMM 1(k+2) <- bar_d(k) <- bar_t(k) forbids), and the helper
-// warpgroup meets at a named barrier once per tile, so no helper warp arrives twice in one phase of bar_hw / bar_d.
-template <class Spec, int H, class M, int MINB>
-NFN_DEVI void dense_tc5_body2(const DenseArgs& a) {
-  constexpr int kRegsHelper = regs_issuer(MINB, true), kRegsCompute = regs_compute(MINB, true);
-  static_assert(kRows * (kRegsHelper + kRegsCompute) <= kThreads * regs_launch(MINB), "register pool");
-  static_assert(kRegsCompute <= 232 && kRegsCompute % 8 == 0 && kRegsHelper % 8 == 0, "setmaxnreg range");
-  constexpr int D = Spec::D;
-  constexpr int P = Spec::P();
-  using G = Geo<P, H, true>;
-  static_assert(G::kPipe2, "two D1 buffers must fit");
-  constexpr int PN = G::PN, T = kRows, NT = kThreads;
-  constexpr int V = 1;
-  constexpr unsigned kGrpA = G::kGrpA, kGrpD = G::kGrpD;
-  constexpr unsigned kFlush = 16u;   // tiles per accumulation window of dW / db in tensor memory
-
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ double red[NT / 32];
-  const unsigned sbase = smem_u32(smem_raw);
-  // bar1[2]: tensor pipe -> compute (GEMM 1 done);  bar2: tensor pipe -> helpers (GEMM 2 + 3 done);
-  // bar_hw: helpers -> issuer (h tile written);  bar_t[2]: compute -> helpers (dt row in D1);
-  // bar_d: helpers -> issuer (dt tile written, D1 and D2 free)
-  const unsigned bar1 = sbase + G::oBar, bar2 = bar1 + 16, bar_hw = bar1 + 24, bar_t = bar1 + 32, bar_d = bar1 + 48,
-                 tmem_slot = bar1 + 64;
-
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const long long ntiles = (a.B + T - 1) / T;
-
-  if (tid == 0) {
-    mbar_init(bar1, 1);
-    mbar_init(bar1 + 8, 1);
-    mbar_init(bar2, 1);
-    mbar_init(bar_hw, T);
-    mbar_init(bar_t, T);
-    mbar_init(bar_t + 8, T);
-    mbar_init(bar_d, T);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, G::kCols);
-  stage_constants<P, H, true>(a, sbase, tid);
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  unsigned tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
-  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
-  // a warp reaches the TMEM lanes 32 (warp % 4) .. + 31: helper warp 4 + q shares them with compute warp q
-  const unsigned lane_base = tmem_base + ((unsigned)((warp & 3) * 32) << 16);
-  float ls_hi = 0.0f, ls_lo = 0.0f;
-
-  if (tid >= T) {
-    // ================================================================ helpers + issuer
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsHelper));
-    const int hr = tid - T;                      // this thread's row of every tile
-    const bool issuer = (warp == T / 32);
-    const unsigned a_row = sbase + G::oA + (hr >> 3) * kGrpA + (hr & 7) * 16;
-    const unsigned d_row = sbase + G::oD + (hr >> 3) * kGrpD + (hr & 7) * 16;
-
-    // h row of a tile: prefetched into registers one tile ahead when it is narrow, else loaded chunk by chunk
-    constexpr bool kPrefetchH = (H <= 32);
-    float h_nxt[kPrefetchH ? H : 1];
-    auto fetch_h = [&](long long tile) {
-      if constexpr (kPrefetchH) {
-        const long long r = tile * T + hr;
-#pragma unroll
-        for (int i = 0; i < H; ++i) h_nxt[i] = 0.0f;
-        if (tile < ntiles && r < a.B) {
-          const float4* src = reinterpret_cast<const float4*>(a.h + r * H);
-#pragma unroll
-          for (int c = 0; c < H / 4; ++c) {
-            const float4 v = __ldg(src + c);
-            h_nxt[4 * c] = v.x; h_nxt[4 * c + 1] = v.y; h_nxt[4 * c + 2] = v.z; h_nxt[4 * c + 3] = v.w;
-          }
-        }
-      }
-    };
-    auto split_h = [&](int buf, long long tile) {
-      if constexpr (kPrefetchH) {
-#pragma unroll
-        for (int c = 0; c < H / 8; ++c) store_levels8(a_row + buf * G::kA + c * 128, G::lvlA(1), G::lvlA(2), h_nxt + 8 * c);
-      } else {
-        const long long r = tile * T + hr;
-        const bool live = r < a.B;
-        const float4* src = reinterpret_cast<const float4*>(a.h + (live ? r : 0) * H);
-#pragma unroll 2
-        for (int c = 0; c < H / 8; ++c) {
-          float v[8];
-          const float4 v0 = live ? __ldg(src + 2 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 v1 = live ? __ldg(src + 2 * c + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-          v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
-          store_levels8(a_row + buf * G::kA + c * 128, G::lvlA(1), G::lvlA(2), v);
-        }
-      }
-    };
-    // dh row of a finished tile: the three W-level blocks of D2, smallest first -> global
-    auto drain_dh = [&](long long r_done) {
-#pragma unroll
-      for (int c = 0; c < H / 8; ++c) {
-        float b0[8], b1[8], b2[8];
-        tmem_load8x3(lane_base + G::cD2 + 8 * c, lane_base + G::cD2 + H + 8 * c, lane_base + G::cD2 + 2 * H + 8 * c, b0, b1, b2);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          add2(b2[2 * q], b2[2 * q + 1], b1[2 * q], b1[2 * q + 1], b1[2 * q], b1[2 * q + 1]);
-          add2(b1[2 * q], b1[2 * q + 1], b0[2 * q], b0[2 * q + 1], b0[2 * q], b0[2 * q + 1]);
-        }
-        if (r_done < a.B) {
-          st_stream_f4(a.dh + r_done * H + 8 * c, make_float4(b0[0], b0[1], b0[2], b0[3]));
-          st_stream_f4(a.dh + r_done * H + 8 * c + 4, make_float4(b0[4], b0[5], b0[6], b0[7]));
-        }
-      }
-    };
-    // dW / db lanes of D3 (TMEM lane = (level, p) of pass j) -> atomics, which also sum the levels and the CTAs
-    auto flush_dw = [&]() {
-#pragma unroll
-      for (int j = 0; j < G::NP3; ++j) {
-        if (16 * j + 4 * (warp & 3) < 3 * G::CL) {   // this warp's 4 chunks of pass j exist (warp-uniform)
-          const int q = 16 * j + (hr >> 3), p = (q % G::CL) * 8 + (hr & 7);
-          const bool live = q < 3 * G::CL && p < P;
-          const unsigned c0 = lane_base + G::cD3p(j);
-#pragma unroll
-          for (int c = 0; c < H / 8; ++c) {
-            float b0[8];
-            if (G::short3(j)) {   // compile-time after unrolling
-              tmem_load8(c0 + 8 * c, b0);
-            } else {
-              float b1[8], b2[8];
-              tmem_load8x3(c0 + 8 * c, c0 + H + 16 + 8 * c, c0 + 2 * H + 16 + 8 * c, b0, b1, b2);
-#pragma unroll
-              for (int k = 0; k < 8; ++k) b0[k] = (b2[k] + b1[k]) + b0[k];
-            }
-            if (live) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) atomicAdd(a.dW + (8 * c + k) * P + p, b0[k]);
-            }
-          }
-          float bv[8];
-          tmem_load8(c0 + H, bv);
-          if (live) atomicAdd(a.dbias + p, bv[0]);
-        }
-      }
-    };
-    // dt row of tile k out of D1[k & 1] -> three level tiles; the load of the next 16 columns is in flight while
-    // the current ones are split (this is the one stretch between the end of a tile's flows and its GEMMs)
-    auto split_dt = [&](unsigned d1) {
-      unsigned r[2][16];
-      tmem_ld16(d1, r[0]);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < PN / 16; ++c) {
-        if (c + 1 < PN / 16) tmem_ld16(d1 + 16 * (c + 1), r[(c + 1) & 1]);
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          asm volatile("" : "+r"(r[c & 1][j]));
-          v[j] = __uint_as_float(r[c & 1][j]);
-        }
-        store_levels8(d_row + (2 * c) * 128, G::kLvlD, 2 * G::kLvlD, v);
-        store_levels8(d_row + (2 * c + 1) * 128, G::kLvlD, 2 * G::kLvlD, v + 8);
-        if (c + 1 < PN / 16) tmem_ld_wait();
-      }
-    };
-
-    // The h rows run TWO tiles ahead of the flows (ring of three tiles) and everything that does not depend on
-    // the compute threads -- the previous tile's dh / dW drain, the next-but-one tile's h split -- happens BEFORE
-    // the wait for their dt rows, i.e. in the helpers' idle time: after bar_t only the dt split stands between
-    // the end of tile k's flows and GEMM 1(k+2).
-    long long tl = blockIdx.x;
-    const long long step = gridDim.x;
-    fetch_h(tl);
-    split_h(0, tl);
-    fence_proxy_async();
-    mbar_arrive(bar_hw);                       // phase 0: h(0)
-    fetch_h(tl + step);
-    if (issuer) {
-      mbar_wait(bar_hw, 0);
-      issue_gemm1<P, H, true>(tmem_base + G::cD1, sbase, 0u, bar1);
-    }
-    helper_sync();                             // phase 0 has been seen complete before anyone arrives for phase 1
-    split_h(1, tl + step);
-    fence_proxy_async();
-    mbar_arrive(bar_hw);                       // phase 1: h(1) (zeros when this CTA has a single tile)
-    fetch_h(tl + 2 * step);
-    if (issuer) {
-      mbar_wait(bar_hw, 1);
-      if (tl + step < ntiles) issue_gemm1<P, H, true>(tmem_base + G::cD1 + PN, sbase, G::kA, bar1 + 8);
-    }
-    unsigned k = 0;
-    long long r_prev = a.B;
-    for (; tl < ntiles; tl += step, ++k) {
-      helper_sync();   // every helper warp has finished tile k-1 (see the phase argument above)
-      if (k > 0) {     // GEMM 2 / 3 of tile k-1 were issued a whole flow sweep ago: dh out; h(k-1), the dt tile and D2 free
-        mbar_wait(bar2, (k - 1) & 1);
-        tc_fence_after();
-        drain_dh(r_prev);
-        if (k % kFlush == 0) flush_dw();   // tile k starts a new accumulation window in D3
-      }
-      r_prev = tl * T + hr;
-      split_h((int)((k + 2) % G::NA), tl + 2 * step);   // into the tile h(k-1) just left
-      fence_proxy_async();
-      mbar_arrive(bar_hw);                               // phase k + 2
-      fetch_h(tl + 3 * step);
-      // ---- the compute threads' dt rows of tile k are in D1[k & 1]
-      mbar_wait(bar_t + 8 * (k & 1), (k >> 1) & 1);
-      tc_fence_after();
-      split_dt(lane_base + G::cD1 + (k & 1) * PN);
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(bar_d);
-      if (issuer) {
-        mbar_wait(bar_d, k & 1);      // dt tile written; D1[k & 1] and D2 are free
-        mbar_wait(bar_hw, k & 1);     // phase k + 2 (complete long ago; waited so that the phases are consumed in order)
-        if (tl + 2 * step < ntiles)
-          issue_gemm1<P, H, true>(tmem_base + G::cD1 + (k & 1) * PN, sbase, (unsigned)((k + 2) % G::NA) * G::kA,
-                                  bar1 + 8 * (k & 1));
-        issue_gemm23<P, H>(tmem_base, sbase, (unsigned)(k % G::NA) * G::kA, (k % kFlush) == 0, bar2);
-      }
-    }
-    if (k > 0) {
-      mbar_wait(bar2, (k - 1) & 1);
-      tc_fence_after();
-      drain_dh(r_prev);
-      flush_dw();
-    }
-  } else {
-    // ================================================================ compute: the flows, nothing else
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute));
-    float y_nxt[D];
-    float g_nxt = 1.0f;
-    auto fetch_y = [&](long long tile) {
-      const long long r = tile * T + tid;
-      if (tile < ntiles && r < a.B) {
-        load_event<D>(a.y, a.y_broadcast ? 0 : r, y_nxt);
-        if (a.g_logp) g_nxt = __ldg(a.g_logp + r);
-      }
-    };
-#pragma unroll
-    for (int i = 0; i < D; ++i) y_nxt[i] = 0.0f;
-    long long tile = blockIdx.x;
-    fetch_y(tile);
-    unsigned it = 0;
-    for (; tile < ntiles; tile += gridDim.x, ++it) {
-      float z[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) z[i] = y_nxt[i];
-      if (a.xf.flags) xform_event<D>(a.xf, tile * T + tid, z);
-      const float g_cur = g_nxt;
-      fetch_y(tile + gridDim.x);
-
-      const unsigned d1 = lane_base + G::cD1 + (it & 1) * PN;
-      mbar_wait(bar1 + 8 * (it & 1), (it >> 1) & 1);
-      tc_fence_after();
-      float row[PN];
-      tmem_load_row<PN>(d1, row);
-
-      const long long r = tile * T + tid;
-      if (r < a.B) {
-        float zs[Spec::KA][D];
-        LogDetAcc<M> ld;
-        FwdSweep<Spec, M, V, true, 0>::run(row, z, zs, ld);
-        using Base = BaseDist<D, Spec::BASE, M>;
-        float bth[Base::NA];
-        if constexpr (Spec::BASE) Span<0, 2 * D, V>::load(row, bth);
-        const float lp = xform_out<M>(a.xf, Base::log_prob_save(bth, z) + ld.nat());
-        a.logp[r] = lp;
-        {
-          const float yv = lp - ls_lo, tv = ls_hi + yv;
-          ls_lo = (tv - ls_hi) - yv;
-          ls_hi = tv;
-        }
-        const float cot = a.g_scale * g_cur;
-        float Gz[D];
-        float gb[Base::NA];
-        Base::bwd_saved(bth, z, cot, Gz, gb);
-        if constexpr (Spec::BASE) Span<0, 2 * D, V>::store(row, gb);
-        BwdSweep<Spec, M, V, Spec::K - 1>::run(row, zs, Gz, cot);
-      } else {
-        // rows past B: h was zero, t = bias; their dt must not reach dW / db
-#pragma unroll
-        for (int j = 0; j < PN; ++j) row[j] = 0.0f;
-      }
-      // (the pad columns P .. PN of a live row are exact zeros out of GEMM 1 and no flow touches them)
-      tmem_store_row<PN>(d1, row);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(bar_t + 8 * (it & 1));
-    }
-  }
-  __syncwarp();
-  const double lsum = (double)ls_hi - (double)ls_lo;
-
-  if (a.logp_sum) {
-    const double sblk = block_sum<NT>(lsum, red);
-    if (tid == 0) atomicAdd(a.logp_sum, sblk);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, G::kCols);
-}
-
-// ------------------------------------------------------------------ entry: the pipeline the shape gets
-template <class Spec, int H, bool BWD, class M, int MINB>
-NFN_DEVI void dense_tc5_body(const DenseArgs& a) {
-  static_assert(Spec::P() > 0 && Spec::P() <= 128, "1..128 parameter columns");
-  static_assert(H % 16 == 0 && H >= 16 && H <= 64, "hidden width must be 16, 32, 48 or 64");
-  if constexpr (g_pipe2(Spec::P(), H, BWD)) dense_tc5_body2<Spec, H, M, MINB>(a);
-  else dense_tc5_body1<Spec, H, BWD, M, MINB>(a);
 }
 
 template <class Spec, int H, bool BWD, class M, int MINB>
