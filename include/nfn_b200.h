@@ -303,6 +303,24 @@ int nfn_mdn_forward_backward_x(int n_centers, int n_dims, const float* t, const 
                                int64_t y_rows, const float* g_logp, float g_scale, float* logp,
                                float* dt, float* dy, double* logp_sum, double* dt_colsum, int64_t B,
                                const nfn_event_xform* xf, void* stream);
+/*
+ * The emitting Dense(P) layer fused into the MDN head: replaces `Dense(output_size, "linear")`
+ * (MaximumLikelihoodNNEstimator.py:43) + GaussianMixtureLayer's log_prob (DistributionLayers.py:196-212) + their
+ * tape gradients, P = n_centers * (2 n_dims + 1).  Same contract as nfn_dense_chain_*_x: t = h W + bias is formed
+ * tile by tile in shared memory (3xTF32 mma.sync, fp32-level accuracy), the mixture's per-row arithmetic is the
+ * one of nfn_mdn_forward_backward, and per row the kernel moves 4 (2 hidden + n_dims + 1) bytes instead of
+ * 4 (2 P + n_dims + 1).  hidden must be 16, 32, 48 or 64; NFN_ERR_UNSUPPORTED when no kernel can serve the request
+ * (no ahead-of-time instance and NVRTC unavailable, or the tile does not fit shared memory): compose then.
+ */
+int nfn_dense_mdn_forward_x(int n_centers, int n_dims, int hidden, const float* h, const float* W, const float* bias,
+                            const float* y, int64_t y_rows, float* logp, int64_t B, const nfn_event_xform* xf,
+                            void* stream);
+int nfn_dense_mdn_forward_backward_x(int n_centers, int n_dims, int hidden, const float* h, const float* W,
+                                     const float* bias, const float* y, int64_t y_rows, const float* g_logp,
+                                     float g_scale, float* logp, float* dh, float* dW, float* dbias, double* logp_sum,
+                                     int64_t B, const nfn_event_xform* xf, void* stream);
+/* bytes of the NVRTC-built cubin for this mixture / hidden width (>= 0), or a negative nfn_status */
+int64_t nfn_jit_dense_mdn_compile_check(int n_centers, int n_dims, int hidden, int accurate);
 int nfn_kmn_forward_x(int n_components, int n_dims, const float* t, const float* y, int64_t y_rows,
                       const float* locs, const float* scales, float* logp, int64_t B, const nfn_event_xform* xf,
                       void* stream);

@@ -240,6 +240,43 @@ class GaussianMixtureDistribution:
         return torch.exp(self.log_prob(y))
 
 
+class FusedDenseGaussianMixtureDistribution(GaussianMixtureDistribution):
+    """The same mixture with the emitting Dense(P) layer folded into the kernel (see
+    FusedDenseFlowChainDistribution): holds h[B, H] and the layer's (W[H, P], bias[P]) instead of t[B, P];
+    ``.t`` materialises the parameter rows on demand."""
+
+    def __init__(self, h, W, bias, n_centers, n_dims):
+        self.h, self.W, self.bias = h, W, bias
+        self.n_centers = n_centers
+        self.n_dims = n_dims
+        self._t = None
+
+    @property
+    def t(self):
+        if self._t is None:
+            self._t = torch.addmm(self.bias, self.h, self.W)
+        return self._t
+
+    @property
+    def batch_shape(self):
+        return _Shape(self.h.shape[:-1])
+
+    def log_prob(self, y):
+        y = _to_tensor_like(y, self.h)
+        if torch.is_grad_enabled() and (self.h.requires_grad or self.W.requires_grad):
+            return super().log_prob(y)  # autograd path goes through t
+        if y.shape[0] not in (self.h.shape[0], 1):
+            return super().log_prob(y)
+        return F.dense_mdn_forward(self.h, self.W, self.bias, y, self.n_centers, self.n_dims)
+
+    def log_prob_x(self, y, xform):
+        y = _to_tensor_like(y, self.h)
+        if y.shape[0] not in (self.h.shape[0], 1):
+            return super().log_prob_x(y, xform)
+        return F.dense_mdn_forward(self.h.detach(), self.W.detach(), self.bias.detach(), y, self.n_centers,
+                                   self.n_dims, xform=xform)
+
+
 class GaussianMixtureLayer(torch.nn.Module):
     """Mixture of ``n_centers`` diagonal Gaussians with per-sample locs, softplus scales and
     mixture logits (reference :174-212)."""

@@ -694,6 +694,72 @@ int nfn_mdn_forward_backward_x(int n_centers, int n_dims, const float* t, const 
   return launch_mdn(n_dims, true, a, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------ fused Dense(P) + MDN head
+static int dense_mdn_common(int K, int d, int hidden, const float* h, const float* W, const float* bias, const float* y,
+                            int64_t y_rows, float* logp, int64_t B) {
+  if (K < 1 || K > 4096) return set_error(NFN_ERR_DESC, "n_centers=%d outside 1..4096", K);
+  if (d < 1 || d > NFN_MAX_DIMS) return set_error(NFN_ERR_DESC, "n_dims=%d outside 1..%d", d, NFN_MAX_DIMS);
+  if (hidden < 1) return set_error(NFN_ERR_SHAPE, "hidden=%d", hidden);
+  int rc = check_rows(B, y_rows);
+  if (rc != NFN_OK) return rc;
+  if (B == 0) return 1;
+  if (!h || !W || !bias || !y || !logp) return set_error(NFN_ERR_NULL, "h, W, bias, y and logp must be non-NULL");
+  if (!aligned(h, 16)) return set_error(NFN_ERR_ALIGN, "h must be 16-byte aligned");
+  if (!aligned(y, event_align(d))) return set_error(NFN_ERR_ALIGN, "y must be %zu-byte aligned", event_align(d));
+  return NFN_OK;
+}
+
+static int dense_mdn_dispatch(int K, int d, int hidden, const DenseArgs& a, bool bwd, cudaStream_t st) {
+  const int mode = math_mode();
+  const std::string key = dense_mdn_key(K, d, hidden);
+  const DenseKernels* k = find_dense(key);
+  if (k && k->fn[mode][bwd ? 1 : 0]) return cuda_error(k->fn[mode][bwd ? 1 : 0](a, st), key.c_str());
+  bool served = false;
+  cudaError_t e = launch_dense_mdn_jit(K, d, hidden, a, bwd, mode, st, &served);
+  if (e != cudaSuccess) return cuda_error(e, key.c_str());
+  if (!served)
+    return set_error(NFN_ERR_UNSUPPORTED,
+                     "no fused dense kernel for a %d-component %d-D mixture with hidden width %d (needs a multiple of "
+                     "16 <= 64 and an ahead-of-time instance or NVRTC): compose the layer and nfn_mdn_forward_backward instead",
+                     K, d, hidden);
+  return NFN_OK;
+}
+
+int nfn_dense_mdn_forward_x(int n_centers, int n_dims, int hidden, const float* h, const float* W, const float* bias,
+                            const float* y, int64_t y_rows, float* logp, int64_t B, const nfn_event_xform* xf,
+                            void* stream) {
+  int rc = dense_mdn_common(n_centers, n_dims, hidden, h, W, bias, y, y_rows, logp, B);
+  if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
+  DenseArgs a{};
+  a.h = h; a.W = W; a.bias = bias; a.y = y; a.logp = logp; a.B = B; a.g_scale = 1.0f;
+  a.y_broadcast = (y_rows == 1 && B != 1);
+  if ((rc = set_xform(a.xf, xf, n_dims)) != NFN_OK) return rc;
+  return dense_mdn_dispatch(n_centers, n_dims, hidden, a, false, (cudaStream_t)stream);
+}
+
+int nfn_dense_mdn_forward_backward_x(int n_centers, int n_dims, int hidden, const float* h, const float* W,
+                                     const float* bias, const float* y, int64_t y_rows, const float* g_logp,
+                                     float g_scale, float* logp, float* dh, float* dW, float* dbias, double* logp_sum,
+                                     int64_t B, const nfn_event_xform* xf, void* stream) {
+  int rc = dense_mdn_common(n_centers, n_dims, hidden, h, W, bias, y, y_rows, logp, B);
+  if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
+  if (!dh || !dW || !dbias) return set_error(NFN_ERR_NULL, "dh, dW and dbias must be non-NULL");
+  if (!aligned(dh, 16)) return set_error(NFN_ERR_ALIGN, "dh must be 16-byte aligned");
+  DenseArgs a{};
+  a.h = h; a.W = W; a.bias = bias; a.y = y; a.g_logp = g_logp; a.logp = logp; a.dh = dh; a.dW = dW;
+  a.dbias = dbias; a.logp_sum = logp_sum; a.B = B; a.g_scale = g_scale;
+  a.y_broadcast = (y_rows == 1 && B != 1);
+  if ((rc = set_xform(a.xf, xf, n_dims)) != NFN_OK) return rc;
+  return dense_mdn_dispatch(n_centers, n_dims, hidden, a, true, (cudaStream_t)stream);
+}
+
+int64_t nfn_jit_dense_mdn_compile_check(int n_centers, int n_dims, int hidden, int accurate) {
+  std::string log;
+  const long long n = jit_dense_mdn_compile_check(n_centers, n_dims, hidden, accurate ? 1 : 0, log);
+  if (n < 0) return set_error(NFN_ERR_UNSUPPORTED, "dense+mdn runtime specialisation failed: %s", log.c_str());
+  return n;
+}
+
 int nfn_kmn_forward(int n_components, int n_dims, const float* t, const float* y, int64_t y_rows,
                     const float* locs, const float* scales, float* logp, int64_t B, void* stream) {
   return nfn_kmn_forward_x(n_components, n_dims, t, y, y_rows, locs, scales, logp, B, nullptr, stream);

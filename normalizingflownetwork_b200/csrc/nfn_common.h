@@ -327,8 +327,60 @@ struct DenseRegistrar {
   }
 };
 
+// ------------------------------------------------------------------ fused Dense(P) + MDN head (mma.sync body)
+template <int K, int D, int H, bool BWD, class M>
+cudaError_t launch_dense_mdn(const DenseArgs& a, cudaStream_t st) {
+  constexpr int T = 128;
+  constexpr int P = MdnHead<K, D>::P;
+  constexpr unsigned kSmem = dense_smem_bytes(P, H, T, BWD);
+  constexpr int kBySmem = (int)((227u * 1024u) / (kSmem + 1024u));
+  constexpr int kWant = BWD ? 2 : 3;
+  constexpr int MINB = kBySmem < 1 ? 1 : (kBySmem < kWant ? kBySmem : kWant);
+  auto kern = dense_mdn_kernel<K, D, H, BWD, M, T, MINB>;
+  struct Cfg {
+    int device = -1;
+    int ctas_per_sm = 0;
+  };
+  static thread_local Cfg cfg;
+  const DeviceInfo& di = device_info();
+  if (cfg.device != di.device) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, kSmem);
+    if (e != cudaSuccess) return e;
+    cfg.ctas_per_sm = occ > 0 ? occ : 1;
+    cfg.device = di.device;
+  }
+  const long long ntiles = (a.B + T - 1) / T;
+  long long grid = (long long)di.sm_count * cfg.ctas_per_sm;
+  if (grid > ntiles) grid = ntiles;
+  kern<<<(unsigned)grid, T, kSmem, st>>>(a);
+  count_launch();
+  return cudaGetLastError();
+}
+
+inline std::string dense_mdn_key(int K, int D, int H) {
+  return "mdn|k" + std::to_string(K) + "d" + std::to_string(D) + "|h" + std::to_string(H);
+}
+
+template <int K, int D, int H>
+struct DenseMdnRegistrar {
+  explicit DenseMdnRegistrar() {
+    DenseKernels k;
+    k.fn[0][0] = &launch_dense_mdn<K, D, H, false, MathFast>;
+    k.fn[0][1] = &launch_dense_mdn<K, D, H, true, MathFast>;
+    k.fn[1][0] = &launch_dense_mdn<K, D, H, false, MathAccurate>;
+    k.fn[1][1] = &launch_dense_mdn<K, D, H, true, MathAccurate>;
+    register_dense(dense_mdn_key(K, D, H), k);
+  }
+};
+
 cudaError_t launch_dense_jit(const nfn_chain_desc* desc, int H, const std::string& key, const DenseArgs& a,
                              bool bwd, int mode, cudaStream_t st, bool* served);
+cudaError_t launch_dense_mdn_jit(int K, int D, int H, const DenseArgs& a, bool bwd, int mode, cudaStream_t st,
+                                 bool* served);
+long long jit_dense_mdn_compile_check(int K, int D, int H, int mode, std::string& log);
 cudaError_t launch_dense_tc5_jit(const nfn_chain_desc* desc, int H, const std::string& key, const DenseArgs& a,
                                  bool bwd, int mode, cudaStream_t st, bool* served);
 

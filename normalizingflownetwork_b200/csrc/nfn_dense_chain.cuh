@@ -18,6 +18,7 @@
 // 1e-5 log-prob parity bar needs; plain TF32 (10-bit mantissa) would not pass it.
 #pragma once
 #include "nfn_chain_kernel.cuh"
+#include "nfn_mixture_row.cuh"
 
 namespace nfn {
 
@@ -113,16 +114,61 @@ struct DenseGeometry {
   }
 };
 
+// ---------------------------------------------------------------- what runs on a parameter row
+// A head turns row r of t (in shared memory, stride S) and the event y_r into log p(y_r | t_r) and, in place,
+// cot * d log p / d t_r.  Two of them share the GEMM scaffolding below.
+//   ChainHead<Spec>: the inverted flow chain (reference estimators/DistributionLayers.py:215-294)
+template <class Spec>
+struct ChainHead {
+  static constexpr int D = Spec::D;
+  static constexpr int P = Spec::P();
+  template <bool BWD, class M>
+  NFN_DEVI static float run(float* row, float (&z)[D], float cot) {
+    constexpr int V = row_vec(P);
+    float zs[Spec::KA][D];
+    LogDetAcc<M> ld;
+    FwdSweep<Spec, M, V, BWD, 0>::run(row, z, zs, ld);
+    using Base = BaseDist<D, Spec::BASE, M>;
+    float bth[Base::NA];
+    if constexpr (Spec::BASE) Span<0, 2 * D, V>::load(row, bth);
+    const float lp = (BWD ? Base::log_prob_save(bth, z) : Base::log_prob(bth, z)) + ld.nat();
+    if constexpr (BWD) {
+      float Gz[D];
+      float gb[Base::NA];
+      Base::bwd_saved(bth, z, cot, Gz, gb);
+      if constexpr (Spec::BASE) Span<0, 2 * D, V>::store(row, gb);
+      BwdSweep<Spec, M, V, Spec::K - 1>::run(row, zs, Gz, cot);
+    }
+    return lp;
+  }
+};
+//   MdnHead<K, D>: the K-component Gaussian mixture (reference estimators/DistributionLayers.py:196-212, fed by
+//   the Dense(P) layer of MaximumLikelihoodNNEstimator.py:43); row arithmetic shared with nfn_mixture.cu
+template <int K_, int D_>
+struct MdnHead {
+  static constexpr int D = D_;
+  static constexpr int K = K_;
+  static constexpr int P = K_ * (2 * D_ + 1);
+  template <bool BWD, class M>
+  NFN_DEVI static float run(float* row, float (&z)[D], float cot) {
+    constexpr bool V4 = (P % 4 == 0);           // row_stride keeps 16-byte row alignment then
+    constexpr int LG = (V4 && K % 4 == 0) ? 4 : 1;
+    float dy[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) dy[i] = 0.0f;
+    return mdn_row<D, V4, LG, BWD, M>(row, K, z, cot, dy);
+  }
+};
+
 // ---------------------------------------------------------------- the fused body
-template <class Spec, int H, bool BWD, class M, int T>
-NFN_DEVI void dense_chain_body(const DenseArgs& a) {
-  constexpr int D = Spec::D;
-  constexpr int P = Spec::P();
+template <class Head, int H, bool BWD, class M, int T>
+NFN_DEVI void dense_head_body(const DenseArgs& a) {
+  constexpr int D = Head::D;
+  constexpr int P = Head::P;
   static_assert(P > 0, "the fused dense kernel needs at least one parameter column");
   static_assert(H % 16 == 0 && H >= 16 && H <= 64, "hidden width must be 16, 32, 48 or 64");
   using G = DenseGeometry<P, H, T>;
   constexpr int S = G::S, HS = G::HS, P8 = G::P8, PW = G::PW, NW = G::NW;
-  constexpr int V = row_vec(P);
   constexpr int NT = P8 / 8;   // n-tiles over the parameter columns
   constexpr int KH = H / 8;    // k-steps over the hidden units
 
@@ -254,27 +300,13 @@ NFN_DEVI void dense_chain_body(const DenseArgs& a) {
     }
     __syncwarp();
 
-    // ---- per-row flow chain (registers), dt written in place over t
+    // ---- per-row head (flow chain or mixture), dt written in place over t
     const long long r = tile * T + tid;
     float* row = tT + tid * S;
     if (r < a.B) {
-      float zs[Spec::KA][D];
-      LogDetAcc<M> ld;
-      FwdSweep<Spec, M, V, BWD, 0>::run(row, z, zs, ld);
-      using Base = BaseDist<D, Spec::BASE, M>;
-      float bth[Base::NA];
-      if constexpr (Spec::BASE) Span<0, 2 * D, V>::load(row, bth);
-      const float lp = xform_out<M>(a.xf, (BWD ? Base::log_prob_save(bth, z) : Base::log_prob(bth, z)) + ld.nat());
+      const float lp = xform_out<M>(a.xf, Head::template run<BWD, M>(row, z, BWD ? a.g_scale * g_cur : 0.0f));
       a.logp[r] = lp;
       lsum += (double)lp;
-      if constexpr (BWD) {
-        const float cot = a.g_scale * g_cur;
-        float Gz[D];
-        float gb[Base::NA];
-        Base::bwd_saved(bth, z, cot, Gz, gb);
-        if constexpr (Spec::BASE) Span<0, 2 * D, V>::store(row, gb);
-        BwdSweep<Spec, M, V, Spec::K - 1>::run(row, zs, Gz, cot);
-      }
     } else if constexpr (BWD) {
 #pragma unroll
       for (int j = 0; j < P; ++j) row[j] = 0.0f;   // rows past B contribute nothing to dW / db
@@ -300,44 +332,54 @@ NFN_DEVI void dense_chain_body(const DenseArgs& a) {
             split_tf32(hp[4 * HS], ah[ks][2], al[ks][2]);
             split_tf32(hp[4 * HS + 8], ah[ks][3], al[ks][3]);
           }
-          float c[NT][4], cb[NT][4];
+          // n-tiles in groups of at most NG, so that the accumulators of a wide head (MDN: 13 n-tiles) stay in
+          // registers; the A fragments above are reused by every group
+          constexpr int NG = NT <= 7 ? NT : (NT + 1) / 2 <= 7 ? (NT + 1) / 2 : 7;
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt) {
-            c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.0f;
-            cb[nt][0] = cb[nt][1] = cb[nt][2] = cb[nt][3] = 0.0f;
-          }
+          for (int n0 = 0; n0 < NT; n0 += NG) {
+            float c[NG][4], cb[NG][4];
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            unsigned bh[NT][2], bl[NT][2];
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-              const int col = 8 * nt + g;
-              split_tf32((col < P) ? tT[(R0 + 8 * ks + tig) * S + col] : 0.0f, bh[nt][0], bl[nt][0]);
-              split_tf32((col < P) ? tT[(R0 + 8 * ks + tig + 4) * S + col] : 0.0f, bh[nt][1], bl[nt][1]);
+            for (int nt = 0; nt < NG; ++nt) {
+              c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.0f;
+              cb[nt][0] = cb[nt][1] = cb[nt][2] = cb[nt][3] = 0.0f;
             }
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) mma_tf32(c[nt], al[ks], bh[nt]);
+            for (int ks = 0; ks < 4; ++ks) {
+              unsigned bh[NG][2], bl[NG][2];
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) mma_tf32(c[nt], ah[ks], bl[nt]);
+              for (int nt = 0; nt < NG; ++nt) {
+                if (n0 + nt < NT) {
+                  const int col = 8 * (n0 + nt) + g;
+                  split_tf32((col < P) ? tT[(R0 + 8 * ks + tig) * S + col] : 0.0f, bh[nt][0], bl[nt][0]);
+                  split_tf32((col < P) ? tT[(R0 + 8 * ks + tig + 4) * S + col] : 0.0f, bh[nt][1], bl[nt][1]);
+                }
+              }
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) mma_tf32(c[nt], ah[ks], bh[nt]);
-            if (mt == 0) {  // bias gradient: ones^T dt
+              for (int nt = 0; nt < NG; ++nt) if (n0 + nt < NT) mma_tf32(c[nt], al[ks], bh[nt]);
 #pragma unroll
-              for (int nt = 0; nt < NT; ++nt) mma_tf32(cb[nt], one, bl[nt]);
+              for (int nt = 0; nt < NG; ++nt) if (n0 + nt < NT) mma_tf32(c[nt], ah[ks], bl[nt]);
 #pragma unroll
-              for (int nt = 0; nt < NT; ++nt) mma_tf32(cb[nt], one, bh[nt]);
+              for (int nt = 0; nt < NG; ++nt) if (n0 + nt < NT) mma_tf32(c[nt], ah[ks], bh[nt]);
+              if (mt == 0) {  // bias gradient: ones^T dt
+#pragma unroll
+                for (int nt = 0; nt < NG; ++nt) if (n0 + nt < NT) mma_tf32(cb[nt], one, bl[nt]);
+#pragma unroll
+                for (int nt = 0; nt < NG; ++nt) if (n0 + nt < NT) mma_tf32(cb[nt], one, bh[nt]);
+              }
             }
-          }
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt) {
-            if (mt == 0 && g == 0) {
-              accb[8 * nt + 2 * tig] += cb[nt][0];
-              accb[8 * nt + 2 * tig + 1] += cb[nt][1];
+            for (int nt = 0; nt < NG; ++nt) {
+              if (n0 + nt < NT) {
+                if (mt == 0 && g == 0) {
+                  accb[8 * (n0 + nt) + 2 * tig] += cb[nt][0];
+                  accb[8 * (n0 + nt) + 2 * tig + 1] += cb[nt][1];
+                }
+                float* p0 = acc + (16 * mt + g) * P8 + 8 * (n0 + nt) + 2 * tig;
+                float* p1 = p0 + 8 * P8;
+                p0[0] += c[nt][0]; p0[1] += c[nt][1];
+                p1[0] += c[nt][2]; p1[1] += c[nt][3];
+              }
             }
-            float* p0 = acc + (16 * mt + g) * P8 + 8 * nt + 2 * tig;
-            float* p1 = p0 + 8 * P8;
-            p0[0] += c[nt][0]; p0[1] += c[nt][1];
-            p1[0] += c[nt][2]; p1[1] += c[nt][3];
           }
         }
       }
@@ -435,9 +477,20 @@ NFN_DEVI void dense_chain_body(const DenseArgs& a) {
   }
 }
 
+// the flow-chain instance under its historical name (ahead-of-time instances and the runtime specialiser use it)
+template <class Spec, int H, bool BWD, class M, int T>
+NFN_DEVI void dense_chain_body(const DenseArgs& a) {
+  dense_head_body<ChainHead<Spec>, H, BWD, M, T>(a);
+}
+
 template <class Spec, int H, bool BWD, class M, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) dense_chain_kernel(const DenseArgs a) {
   dense_chain_body<Spec, H, BWD, M, T>(a);
+}
+
+template <int K, int D, int H, bool BWD, class M, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) dense_mdn_kernel(const DenseArgs a) {
+  dense_head_body<MdnHead<K, D>, H, BWD, M, T>(a);
 }
 
 }  // namespace nfn

@@ -30,6 +30,7 @@ extern const char* const nfn_jit_src_flows;
 extern const char* const nfn_jit_src_chain;
 extern const char* const nfn_jit_src_dense;
 extern const char* const nfn_jit_src_dense_tc5;
+extern const char* const nfn_jit_src_mixture_row;
 
 namespace nfn {
 
@@ -180,12 +181,12 @@ bool compile_cubin(const std::string& src, std::vector<char>& cubin, std::string
     log = "libnvrtc.so.12 not found";
     return false;
   }
-  const char* headers[5] = {nfn_jit_src_math, nfn_jit_src_flows, nfn_jit_src_chain, nfn_jit_src_dense,
-                            nfn_jit_src_dense_tc5};
-  const char* hnames[5] = {"nfn_math.cuh", "nfn_flows.cuh", "nfn_chain_kernel.cuh", "nfn_dense_chain.cuh",
-                           "nfn_dense_tc5.cuh"};
+  const char* headers[6] = {nfn_jit_src_math, nfn_jit_src_flows, nfn_jit_src_chain, nfn_jit_src_dense,
+                            nfn_jit_src_dense_tc5, nfn_jit_src_mixture_row};
+  const char* hnames[6] = {"nfn_math.cuh", "nfn_flows.cuh", "nfn_chain_kernel.cuh", "nfn_dense_chain.cuh",
+                           "nfn_dense_tc5.cuh", "nfn_mixture_row.cuh"};
   nvrtcProgram prog = nullptr;
-  int rc = n.CreateProgram(&prog, src.c_str(), "nfn_jit_chain.cu", 5, headers, hnames);
+  int rc = n.CreateProgram(&prog, src.c_str(), "nfn_jit_chain.cu", 6, headers, hnames);
   if (rc != 0) {
     log = "nvrtcCreateProgram failed";
     return false;
@@ -229,7 +230,7 @@ static JitEntry* get_or_build(const std::string& ckey, const std::string& src, c
     e.geo[0] = geo[0];
     e.geo[1] = geo[1];
     const std::string all = src + nfn_jit_src_math + nfn_jit_src_flows + nfn_jit_src_chain + nfn_jit_src_dense +
-                            nfn_jit_src_dense_tc5 + "|sm_100a|v4";
+                            nfn_jit_src_dense_tc5 + nfn_jit_src_mixture_row + "|sm_100a|v5";
     char name[64];
     snprintf(name, sizeof(name), "/chain_%016llx.cubin", fnv1a(all));
     const std::string path = cache_dir() + name;
@@ -498,6 +499,54 @@ int jit_cache_size() {
   int n = 0;
   for (auto& kv : g_cache) n += kv.second.failed ? 0 : 1;
   return n;
+}
+
+// ------------------------------------------------------------------ fused Dense(P) + MDN head
+static std::string dense_mdn_program_source(int K, int D, int H, int mode, const ChainGeometry (&geo)[2]) {
+  const char* math = mode == 0 ? "nfn::MathFast" : "nfn::MathAccurate";
+  std::string s = "#include \"nfn_dense_chain.cuh\"\nusing Head = nfn::MdnHead<" + std::to_string(K) + ", " +
+                  std::to_string(D) + ">;\n";
+  const char* names[2] = {"nfn_jit_dense_mdn_fwd", "nfn_jit_dense_mdn_fwd_bwd"};
+  for (int b = 0; b < 2; ++b) {
+    s += "extern \"C\" __global__ void __launch_bounds__(" + std::to_string(geo[b].T) + ", " +
+         std::to_string(geo[b].MINB) + ") " + names[b] + "(const nfn::DenseArgs a) {\n  nfn::dense_head_body<Head, " +
+         std::to_string(H) + ", " + (b ? "true" : "false") + ", " + math + ", " + std::to_string(geo[b].T) +
+         ">(a);\n}\n";
+  }
+  return s;
+}
+
+static bool dense_mdn_eligible(int K, int D, int H, const ChainGeometry (&geo)[2]) {
+  return K >= 1 && D >= 1 && D <= 8 && H % 16 == 0 && H >= 16 && H <= 64 && geo[1].smem_bytes <= 220u * 1024u;
+}
+
+// served == false (with cudaSuccess): the caller must use the unfused path
+cudaError_t launch_dense_mdn_jit(int K, int D, int H, const DenseArgs& a, bool bwd, int mode, cudaStream_t st,
+                                 bool* served) {
+  *served = false;
+  if (!jit_enabled()) return cudaSuccess;
+  ChainGeometry geo[2];
+  dense_geometry(K * (2 * D + 1), H, geo);
+  if (!dense_mdn_eligible(K, D, H, geo)) return cudaSuccess;
+  const char* const names[2] = {"nfn_jit_dense_mdn_fwd", "nfn_jit_dense_mdn_fwd_bwd"};
+  const std::string ckey = dense_mdn_key(K, D, H) + "|m" + std::to_string(mode) + "|dev" + std::to_string(device_info().device);
+  JitEntry* ent = get_or_build(ckey, dense_mdn_program_source(K, D, H, mode, geo), names, geo);
+  if (!ent) return cudaSuccess;
+  cudaError_t ce = launch_entry(ent, bwd ? 1 : 0, a, a.B, st);
+  if (ce == cudaSuccess) *served = true;
+  return ce;
+}
+
+long long jit_dense_mdn_compile_check(int K, int D, int H, int mode, std::string& log) {
+  ChainGeometry geo[2];
+  dense_geometry(K * (2 * D + 1), H, geo);
+  if (!dense_mdn_eligible(K, D, H, geo)) {
+    log = "mixture / hidden width not eligible for the fused kernel";
+    return -1;
+  }
+  std::vector<char> cubin;
+  if (!compile_cubin(dense_mdn_program_source(K, D, H, mode, geo), cubin, log)) return -1;
+  return (long long)cubin.size();
 }
 
 }  // namespace nfn

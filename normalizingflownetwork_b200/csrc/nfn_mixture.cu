@@ -16,6 +16,7 @@
 #include <unordered_map>
 
 #include "nfn_common.h"
+#include "nfn_mixture_row.cuh"
 
 namespace nfn {
 
@@ -131,41 +132,6 @@ struct RtPipe {
   }
 };
 
-// per-thread load/store of N consecutive floats at a runtime offset whose alignment
-// (in floats) is at least A (compile time)
-template <int N, int A>
-NFN_DEVI void ld_vec(const float* p, float (&v)[N]) {
-  if constexpr (A >= 4 && N % 4 == 0) {
-#pragma unroll
-    for (int i = 0; i < N; i += 4) {
-      const float4 x = *reinterpret_cast<const float4*>(p + i);
-      v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
-    }
-  } else if constexpr (A >= 2 && N % 2 == 0) {
-#pragma unroll
-    for (int i = 0; i < N; i += 2) {
-      const float2 x = *reinterpret_cast<const float2*>(p + i);
-      v[i] = x.x; v[i + 1] = x.y;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = p[i];
-  }
-}
-template <int N, int A>
-NFN_DEVI void st_vec(float* p, const float (&v)[N]) {
-  if constexpr (A >= 4 && N % 4 == 0) {
-#pragma unroll
-    for (int i = 0; i < N; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-  } else if constexpr (A >= 2 && N % 2 == 0) {
-#pragma unroll
-    for (int i = 0; i < N; i += 2) *reinterpret_cast<float2*>(p + i) = make_float2(v[i], v[i + 1]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < N; ++i) p[i] = v[i];
-  }
-}
-
 // y (and the upstream cotangent) of the next tile are fetched one iteration ahead so their
 // DRAM latency hides behind the current tile's arithmetic
 template <int D, bool BWD>
@@ -192,21 +158,6 @@ struct EventPrefetch {
   }
 };
 
-// online logsumexp update with one exponential
-template <class M>
-NFN_DEVI void lse_push(float x, float& m, float& s) {
-  const float e = M::exp(-fabsf(x - m));
-  s = (x > m) ? fmaf(s, e, 1.0f) : s + e;
-  m = fmaxf(m, x);
-}
-// the same in base 2 (x, m in log2 units): no multiply in front of the EX2
-template <class M>
-NFN_DEVI void lse2_push(float x, float& m, float& s) {
-  const float e = M::ex2(-fabsf(x - m));
-  s = (x > m) ? fmaf(s, e, 1.0f) : s + e;
-  m = fmaxf(m, x);
-}
-
 // ------------------------------------------------------------------ MDN
 // V4: rows are 16-byte aligned in smem (P % 4 == 0) so the (mu, sigma_raw) block of a
 // component, 2*D floats at offset k*2*D, can be read with the widest aligned vectors.
@@ -217,10 +168,7 @@ template <int D, bool V4, int LG, bool BWD, class M>
 __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) mdn_kernel(const MixArgs a, const RtTile g, const int nb) {
   extern __shared__ __align__(16) float smem[];
   __shared__ double red[kMixT / 32];
-  constexpr int A = V4 ? ((2 * D) % 4 == 0 ? 4 : ((2 * D) % 2 == 0 ? 2 : 1)) : 1;
-  constexpr float kHalfLog2e = 0.5f * kLog2e;
   const int K = a.K;
-  const int LO = 2 * K * D;  // logits offset
   const long long ntiles = (a.B + kMixT - 1) / kMixT;
   double lsum = 0.0;
   const int tile_floats = kMixT * g.S;
@@ -244,83 +192,14 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) mdn_kernel(const MixArgs a
     const long long r = tile * kMixT + threadIdx.x;
     if (r < a.B) {
       float* row = buf + threadIdx.x * g.S;
-      // log-softmax normaliser of the logits (log2 units)
-      float lm = -INFINITY, ls = 0.0f;
-      for (int k0 = 0; k0 < K; k0 += LG) {
-        float lg[LG];
-        ld_vec<LG, LG>(row + LO + k0, lg);
+      float dy[D];
 #pragma unroll
-        for (int j = 0; j < LG; ++j) lse2_push<M>(lg[j] * kLog2e, lm, ls);
-      }
-      const float lse2 = lm + M::lg2(ls);
-      // components, online logsumexp
-      float m = -INFINITY, s = 0.0f;
-      for (int k0 = 0; k0 < K; k0 += LG) {
-        float lg[LG];
-        ld_vec<LG, LG>(row + LO + k0, lg);
-#pragma unroll
-        for (int j = 0; j < LG; ++j) {
-          float* blk = row + (k0 + j) * 2 * D;
-          float th[2 * D];
-          ld_vec<2 * D, A>(blk, th);
-          float quad = 0.0f, prod = 1.0f;
-#pragma unroll
-          for (int i = 0; i < D; ++i) {
-            const float sig = M::softplus(fmaf(0.05f, th[D + i], kC0));
-            const float e = M::div(y[i] - th[i], sig);
-            quad = fmaf(e, e, quad);
-            prod *= sig;
-            if constexpr (BWD) th[D + i] = sig;
-          }
-          if constexpr (BWD) st_vec<2 * D, A>(blk, th);  // keep sigma for the reverse sweep
-          const float lp2 = fmaf(lg[j], kLog2e, -kHalfLog2e * quad) - M::lg2(prod);
-          lse2_push<M>(lp2, m, s);
-        }
-      }
-      const float top2 = m + M::lg2(s);  // log2 sum_k exp(logit_k + log N_k + d/2 log 2pi)
-      const float logp = (top2 - lse2) * kLn2 - (float)D * kHalfLog2Pi;
+      for (int i = 0; i < D; ++i) dy[i] = 0.0f;
+      const float logp = mdn_row<D, V4, LG, BWD, M>(row, K, y, BWD ? a.g_scale * g_cur : 0.0f, dy);
       const float lpo = xform_out<M>(a.xf, logp);
       a.logp[r] = lpo;
       lsum += (double)lpo;
       if constexpr (BWD) {
-        const float cot = a.g_scale * g_cur;
-        float dy[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) dy[i] = 0.0f;
-        for (int k0 = 0; k0 < K; k0 += LG) {
-          float lg[LG];
-          ld_vec<LG, LG>(row + LO + k0, lg);
-#pragma unroll
-          for (int j = 0; j < LG; ++j) {
-            float* blk = row + (k0 + j) * 2 * D;
-            float th[2 * D];
-            ld_vec<2 * D, A>(blk, th);                       // (mu, sigma)
-            float e[D], rs[D];
-            float quad = 0.0f, prod = 1.0f;
-#pragma unroll
-            for (int i = 0; i < D; ++i) {
-              rs[i] = M::rcp(th[D + i]);
-              e[i] = (y[i] - th[i]) * rs[i];
-              quad = fmaf(e[i], e[i], quad);
-              prod *= th[D + i];
-            }
-            const float l2 = lg[j] * kLog2e;
-            const float lp2 = fmaf(-kHalfLog2e, quad, l2) - M::lg2(prod);
-            const float crho = cot * M::ex2(lp2 - top2);     // cot * responsibility
-            lg[j] = fmaf(-cot, M::ex2(l2 - lse2), crho);     // cot * (rho_k - softmax_k)
-#pragma unroll
-            for (int i = 0; i < D; ++i) {
-              const float gm = crho * e[i] * rs[i];
-              // d sigma / d raw = 0.05 * sigmoid(x), and sigmoid(x) = 1 - exp(-softplus(x))
-              const float dsig = 0.05f * M::one_minus_exp_neg(th[D + i]);
-              th[D + i] = crho * fmaf(e[i], e[i], -1.0f) * rs[i] * dsig;
-              th[i] = gm;
-              dy[i] -= gm;
-            }
-            st_vec<2 * D, A>(blk, th);
-          }
-          st_vec<LG, LG>(row + LO + k0, lg);
-        }
         if (a.dy) store_event<D>(a.dy, r, dy);
       }
     }
@@ -386,7 +265,7 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) kmn_kernel(const MixArgs a
     float* row = buf + threadIdx.x * g.S;
     float lse2 = 0.0f, top2 = 0.0f, cot = 0.0f;
     if (valid) {
-      float lm = -INFINITY, ls = 0.0f, m = -INFINITY, s = 0.0f;
+      float lm = NFN_NEG_INF, ls = 0.0f, m = NFN_NEG_INF, s = 0.0f;
       for (int k0 = 0; k0 < K; k0 += LG) {
         float lg[LG];
         ld_vec<LG, LG>(row + k0, lg);
@@ -615,7 +494,7 @@ __global__ void __launch_bounds__(256) logmeanexp_kernel(const float* __restrict
                                                          float* __restrict__ out) {
   for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B;
        b += (long long)gridDim.x * blockDim.x) {
-    float m = -INFINITY, s = 0.0f;
+    float m = NFN_NEG_INF, s = 0.0f;
     for (long long k = 0; k < S; ++k) lse_push<MathAccurate>(__ldg(in + k * B + b), m, s);
     out[b] = m + logf(s) - logf((float)S);
   }

@@ -17,6 +17,7 @@ import torch.distributed as dist
 from .. import functional as F
 from ..DistributionLayers import (
     FusedDenseFlowChainDistribution,
+    FusedDenseGaussianMixtureDistribution,
     GaussianKernelsLayer,
     GaussianMixtureLayer,
     InverseNormalizingFlowLayer,
@@ -122,16 +123,20 @@ class BaseEstimator(torch.nn.Module):
     fuse_last_layer = True
 
     def _fusable_last_layer(self):
-        """The emitting Dense(P) layer if it can be folded into the flow kernel:
-        NF head with at least one parameter, plain (non-variational) linear output layer whose
+        """The emitting Dense(P) layer if it can be folded into the head kernel:
+        NF head with at least one parameter or MDN head, plain (non-variational) linear output layer whose
         input width is 16, 32, 48 or 64."""
-        if not self.fuse_last_layer or not isinstance(self.dist_layer, InverseNormalizingFlowLayer):
+        layer = self.dist_layer
+        if not self.fuse_last_layer or not isinstance(layer, (InverseNormalizingFlowLayer, GaussianMixtureLayer)):
             return None
         last = self.net[-1]
         lin = getattr(last, "linear", None)
         if lin is None or not isinstance(lin, torch.nn.Linear) or isinstance(lin, torch.nn.LazyLinear):
             return None
-        if not F.dense_chain_supported(lin.in_features) or self.dist_layer.get_total_param_size() < 1:
+        if not F.dense_chain_supported(lin.in_features) or layer.get_total_param_size() < 1:
+            return None
+        if isinstance(layer, GaussianMixtureLayer) and not F.dense_mdn_supported(lin.in_features, layer._n_centers,
+                                                                                  layer._n_dims):
             return None
         return lin
 
@@ -158,6 +163,9 @@ class BaseEstimator(torch.nn.Module):
                 lin = self._fusable_last_layer()
                 if lin is not None and not training:
                     layer = self.dist_layer
+                    if isinstance(layer, GaussianMixtureLayer):
+                        return FusedDenseGaussianMixtureDistribution(self.hidden_from_x(x), self._emitting_kernel(lin),
+                                                                     lin.bias, layer._n_centers, layer._n_dims)
                     return FusedDenseFlowChainDistribution(self.hidden_from_x(x), self._emitting_kernel(lin),
                                                            lin.bias, layer._flow_types, layer._n_dims,
                                                            layer._trainable_base_dist)
@@ -294,9 +302,14 @@ class BaseEstimator(torch.nn.Module):
             # t / dt never touch HBM; the kernel returns dh, dW, dbias
             layer = self.dist_layer
             h = self.hidden_from_x(xb)
-            _, dh, dW, db = F.dense_chain_forward_backward(
-                h.detach(), self._emitting_kernel(lin), lin.bias.detach(), y, layer._flow_types,
-                layer._n_dims, layer._trainable_base_dist, g_scale=-1.0 / Bg, logp_sum=logp_sum, xform=xf)
+            if isinstance(layer, GaussianMixtureLayer):
+                _, dh, dW, db = F.dense_mdn_forward_backward(
+                    h.detach(), self._emitting_kernel(lin), lin.bias.detach(), y, layer._n_centers, layer._n_dims,
+                    g_scale=-1.0 / Bg, logp_sum=logp_sum, xform=xf)
+            else:
+                _, dh, dW, db = F.dense_chain_forward_backward(
+                    h.detach(), self._emitting_kernel(lin), lin.bias.detach(), y, layer._flow_types,
+                    layer._n_dims, layer._trainable_base_dist, g_scale=-1.0 / Bg, logp_sum=logp_sum, xform=xf)
             if reducer is not None:     # accumulate into the flat buffer's views
                 lin.weight.grad.copy_(dW.t())
                 lin.bias.grad.copy_(db)

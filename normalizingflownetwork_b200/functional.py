@@ -427,6 +427,73 @@ def mdn_forward_backward(t, y, n_centers, n_dims, g_logp=None, g_scale=1.0, want
     return logp, dt, dy
 
 
+def dense_mdn_supported(hidden, n_centers, n_dims):
+    """Whether the fused Dense(P)+MDN kernel can serve this shape: hidden width 16/32/48/64 and a 128-row tile of
+    P = K (2 d + 1) columns (+ the layer's operands and accumulators) inside 220 KB of shared memory
+    (``dense_smem_bytes`` in csrc/nfn_dense_chain.cuh)."""
+    if hidden not in (16, 32, 48, 64) or n_centers < 1 or not 1 <= n_dims <= 8:
+        return False
+    P = mdn_param_size(n_centers, n_dims)
+    S = P + 4 if (P % 4 == 0 and (P // 4) % 2 == 0) else P
+    P8 = (P + 7) // 8 * 8
+    PW = P8
+    while PW % 32 not in (8, 24):
+        PW += 1
+    floats = 128 * S + 2 * 128 * (hidden + 4) + hidden * PW + P8 + 4 * hidden * P8 + 4 * P8
+    return 4 * floats <= 220 * 1024
+
+
+def dense_mdn_forward(h, W, bias, y, n_centers, n_dims, xform=None):
+    """log_prob[B] of the K-component mixture with the emitting layer fused: t = h @ W + bias never touches HBM.
+    h [B, H], W [H, P] (Keras kernel layout = torch ``linear.weight.t()``), bias [P], P = K (2 d + 1).
+    Reference: Dense(output_size) of MaximumLikelihoodNNEstimator.py:43 + DistributionLayers.py:196-212."""
+    lib = _lib.load()
+    P = mdn_param_size(n_centers, n_dims)
+    h = _aligned(_as_f32_cuda(h, "h"))
+    dev = h.device
+    W = _as_f32_cuda(W, "W", device=dev)
+    bias = _as_f32_cuda(bias, "bias", device=dev)
+    y = _aligned(_as_f32_cuda(y, "y", device=dev))
+    B, H = h.shape
+    assert tuple(W.shape) == (H, P) and tuple(bias.shape) == (P,), "W must be [H, P] and bias [P]"
+    _check_y(y, n_dims, B, "dense_mdn_forward")
+    logp = torch.empty(B, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_dense_mdn_forward_x(n_centers, n_dims, H, _lib.ptr(h), _lib.ptr(W), _lib.ptr(bias),
+                                               _lib.ptr(y), y.shape[0], _lib.ptr(logp), B, _xf(xform),
+                                               _lib.current_stream(dev)))
+    return logp
+
+
+def dense_mdn_forward_backward(h, W, bias, y, n_centers, n_dims, g_logp=None, g_scale=1.0, logp_sum=None, dW=None,
+                               dbias=None, xform=None):
+    """Fused layer + mixture head, forward and reverse sweep.  Returns (logp[B], dh[B,H], dW[H,P], dbias[P]);
+    dW / dbias are accumulated into when given (else fresh zero tensors)."""
+    lib = _lib.load()
+    P = mdn_param_size(n_centers, n_dims)
+    h = _aligned(_as_f32_cuda(h, "h"))
+    dev = h.device
+    W = _as_f32_cuda(W, "W", device=dev)
+    bias = _as_f32_cuda(bias, "bias", device=dev)
+    y = _aligned(_as_f32_cuda(y, "y", device=dev))
+    B, H = h.shape
+    assert tuple(W.shape) == (H, P) and tuple(bias.shape) == (P,), "W must be [H, P] and bias [P]"
+    _check_y(y, n_dims, B, "dense_mdn_forward_backward")
+    logp = torch.empty(B, dtype=torch.float32, device=dev)
+    dh = torch.empty((B, H), dtype=torch.float32, device=dev)
+    if dW is None:
+        dW = torch.zeros((H, P), dtype=torch.float32, device=dev)
+    if dbias is None:
+        dbias = torch.zeros(P, dtype=torch.float32, device=dev)
+    g_logp = _prep_g(g_logp, B, dev, "dense_mdn_forward_backward")
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_dense_mdn_forward_backward_x(
+            n_centers, n_dims, H, _lib.ptr(h), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(y), y.shape[0],
+            _lib.ptr(g_logp), ctypes.c_float(g_scale), _lib.ptr(logp), _lib.ptr(dh), _lib.ptr(dW), _lib.ptr(dbias),
+            _lib.ptr(logp_sum), B, _xf(xform), _lib.current_stream(dev)))
+    return logp, dh, dW, dbias
+
+
 class _MdnLogProb(torch.autograd.Function):
     @staticmethod
     def forward(ctx, t, y, n_centers, n_dims):

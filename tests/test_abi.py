@@ -110,6 +110,10 @@ def test_runtime_specialiser_compiles_without_gpu(nfn_lib):
     assert nfn_lib.nfn_jit_dense_tc5_compile_check(ctypes.byref(desc), 16, 1) > 10_000, nfn_lib.nfn_last_error()
     # not eligible: hidden width the tensor-core tiles cannot take
     assert nfn_lib.nfn_jit_dense_tc5_compile_check(ctypes.byref(desc), 10, 0) < 0
+    # the fused Dense(P)+MDN kernel (same GEMM scaffolding, mixture head), a shape without an ahead-of-time instance
+    assert nfn_lib.nfn_jit_dense_mdn_compile_check(7, 3, 32, 0) > 10_000, nfn_lib.nfn_last_error()
+    assert nfn_lib.nfn_jit_dense_mdn_compile_check(20, 2, 16, 1) > 10_000, nfn_lib.nfn_last_error()
+    assert nfn_lib.nfn_jit_dense_mdn_compile_check(200, 2, 16, 0) < 0   # a 1000-column tile does not fit shared memory
 
 
 def test_missing_library_is_loud(monkeypatch, tmp_path):

@@ -148,3 +148,117 @@ def test_dense_chain_unsupported_width_is_reported(cuda_device, nfn_lib):
                               torch.zeros(11, device=cuda_device), torch.zeros((4, 1), device=cuda_device),
                               ["radial"] * 3, 1, True)
     assert ei.value.code == -6
+
+
+# ----------------------------------------------------------------------------- fused Dense(P) + MDN head
+MDN_CASES = [
+    # (n_centers, d, H) -- the first two have ahead-of-time instances, the rest are runtime-specialised
+    (20, 2, 16),   # BASELINE config 5: P = 100
+    (5, 1, 16),    # the reference's default MixtureDensityNetwork: P = 15 (odd row stride)
+    (7, 3, 32),    # P = 49
+    (4, 4, 64),    # P = 36 (padded row stride)
+    (3, 2, 48),    # P = 15
+]
+
+
+def _mdn_oracle(h, W, b, y, K, d, up):
+    t = h.astype(np.float64) @ W.astype(np.float64) + b.astype(np.float64)
+    lp, dt, _ = an.mdn_forward_backward(t, y, K, d, upstream=up)
+    return lp, dt @ W.astype(np.float64).T, h.astype(np.float64).T @ dt, dt.sum(0)
+
+
+@pytest.mark.parametrize("case", range(len(MDN_CASES)))
+@pytest.mark.parametrize("B", [1, 100, 128 * 5 + 77, 20_000])
+def test_dense_mdn_vs_oracle(cuda_device, nfn_lib, case, B):
+    """Dense(P) + Gaussian mixture head in one kernel against the float64 oracle composed with float64 matmuls
+    (reference MaximumLikelihoodNNEstimator.py:43 + DistributionLayers.py:196-212)."""
+    from normalizingflownetwork_b200 import functional as F
+
+    K, d, H = MDN_CASES[case]
+    P = K * (2 * d + 1)
+    assert F.dense_mdn_supported(H, K, d)
+    rng = np.random.default_rng(5000 * case + B)
+    h = np.tanh(rng.normal(0, 1.0, (B, H))).astype(np.float32)
+    W = (rng.normal(0, 1.0, (H, P)) / np.sqrt(H)).astype(np.float32)
+    b = rng.normal(0, 0.5, (P,)).astype(np.float32)
+    y = rng.normal(0, 1.0, (B, d)).astype(np.float32)
+    up = rng.normal(0, 1.0, (B,)).astype(np.float32)
+    ref_lp, ref_dh, ref_dW, ref_db = _mdn_oracle(h, W, b, y, K, d, up * 0.5)
+    dev = lambda x: torch.tensor(x, device=cuda_device)
+    lsum = torch.zeros(1, dtype=torch.float64, device=cuda_device)
+    lp, dh, dW, db = F.dense_mdn_forward_backward(dev(h), dev(W), dev(b), dev(y), K, d, g_logp=dev(up), g_scale=0.5,
+                                                  logp_sum=lsum)
+    assert rel(lp.cpu().numpy(), ref_lp) <= 1e-5
+    assert rel(dh.cpu().numpy(), ref_dh) <= 1e-4
+    assert np.abs(dW.cpu().numpy() - ref_dW).max() <= 1e-4 * max(1.0, np.abs(ref_dW).max())
+    assert np.abs(db.cpu().numpy() - ref_db).max() <= 1e-4 * max(1.0, np.abs(ref_db).max())
+    assert abs(lsum.item() - lp.double().sum().item()) <= 1e-9 * np.abs(ref_lp).sum() + 1e-6
+    lp_f = F.dense_mdn_forward(dev(h), dev(W), dev(b), dev(y), K, d)
+    assert rel(lp_f.cpu().numpy(), ref_lp) <= 1e-5
+    # y broadcast
+    t64 = h.astype(np.float64) @ W.astype(np.float64) + b
+    ref_b = an.mdn_forward_backward(t64, y[:1], K, d, need_grad=False)
+    got_b = F.dense_mdn_forward(dev(h), dev(W), dev(b), dev(y[:1]), K, d).cpu().numpy()
+    assert rel(got_b, ref_b) <= 1e-5
+
+
+def test_dense_mdn_equals_unfused_composition(cuda_device, nfn_lib):
+    """Same answer as float64 matmul + the streaming MDN kernel (identical row arithmetic: nfn_mixture_row.cuh),
+    gradients accumulate (+=), the y pipeline of the estimators rides along, ragged multi-tile batch."""
+    from normalizingflownetwork_b200 import functional as F
+
+    K, d, H = 20, 2, 16
+    P, B = K * (2 * d + 1), 150_001
+    g = torch.Generator(device=cuda_device).manual_seed(9)
+    h = torch.tanh(torch.randn((B, H), generator=g, device=cuda_device))
+    W = torch.randn((H, P), generator=g, device=cuda_device) * 0.25
+    b = torch.randn(P, generator=g, device=cuda_device) * 0.3
+    y = torch.randn((B, d), generator=g, device=cuda_device) * 2.0 + 1.0
+    xf = F.make_xform(d, mean=[1.0, 0.8], std=[2.0, 1.7], logp_shift=-float(np.log(2.0) + np.log(1.7)))
+    t = (h.double() @ W.double() + b.double()).float()
+    lp_u, dt_u, _ = F.mdn_forward_backward(t, y, K, d, g_scale=-1.0 / B, xform=xf)
+    lp, dh, dW, db = F.dense_mdn_forward_backward(h, W, b, y, K, d, g_scale=-1.0 / B, xform=xf)
+    assert torch.allclose(lp, lp_u, rtol=1e-5, atol=1e-5)
+    dh_ref = (dt_u.double() @ W.double().T).float()
+    assert torch.allclose(dh * B, dh_ref * B, rtol=1e-4, atol=1e-4)
+    dW_ref, db_ref = (h.double().T @ dt_u.double()).float(), dt_u.double().sum(0).float()
+    assert (dW - dW_ref).abs().max() <= 1e-4 * dW_ref.abs().max()
+    assert (db - db_ref).abs().max() <= 1e-4 * db_ref.abs().max()
+    dW2, db2 = dW.clone(), db.clone()
+    F.dense_mdn_forward_backward(h, W, b, y, K, d, g_scale=-1.0 / B, dW=dW2, dbias=db2, xform=xf)
+    assert torch.allclose(dW2, 2 * dW, rtol=1e-4, atol=1e-7) and torch.allclose(db2, 2 * db, rtol=1e-4, atol=1e-7)
+    assert torch.allclose(F.dense_mdn_forward(h, W, b, y, K, d, xform=xf), lp, rtol=1e-6, atol=1e-6)
+
+
+def test_dense_mdn_unsupported_shapes_are_reported(cuda_device, nfn_lib):
+    from normalizingflownetwork_b200 import _lib
+    from normalizingflownetwork_b200 import functional as F
+
+    assert not F.dense_mdn_supported(16, 200, 2) and not F.dense_mdn_supported(10, 5, 1)
+    with pytest.raises(_lib.NfnError) as ei:   # hidden width 10
+        F.dense_mdn_forward(torch.zeros((4, 10), device=cuda_device), torch.zeros((10, 15), device=cuda_device),
+                            torch.zeros(15, device=cuda_device), torch.zeros((4, 1), device=cuda_device), 5, 1)
+    assert ei.value.code == -6
+
+
+def test_mdn_estimator_uses_the_fused_layer(cuda_device, nfn_lib):
+    """MixtureDensityNetwork: train_step and log_pdf through the fused Dense(P)+MDN kernel equal the unfused path."""
+    from normalizingflownetwork_b200 import functional as F
+    from normalizingflownetwork_b200.estimators import MixtureDensityNetwork
+
+    rng = np.random.default_rng(3)
+    x = rng.normal(0, 1, (4096, 1)).astype(np.float32)
+    y = (np.sin(x) + 0.3 * rng.normal(0, 1, (4096, 1))).astype(np.float32)
+    models = []
+    for fuse in (True, False):
+        torch.manual_seed(11)
+        m = MixtureDensityNetwork.build_function(n_dims=1, n_centers=5, hidden_sizes=(16, 16), activation="tanh")
+        m.fuse_last_layer = fuse
+        m.fit(x, y, batch_size=1024, epochs=1, verbose=0)
+        models.append(m)
+    assert models[0]._fusable_last_layer() is not None and models[1]._fusable_last_layer() is None
+    F.launch_count_reset()
+    lp_f, lp_u = models[0].log_pdf(x, y), models[1].log_pdf(x, y)
+    assert torch.allclose(torch.as_tensor(lp_f).cpu(), torch.as_tensor(lp_u).cpu(), rtol=2e-4, atol=2e-4)
+    for (n0, p0), (n1, p1) in zip(models[0].named_parameters(), models[1].named_parameters()):
+        assert n0 == n1 and torch.allclose(p0, p1, rtol=2e-3, atol=2e-4), n0
