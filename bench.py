@@ -561,17 +561,36 @@ def cfg4_bayes_train_step(device, rank, world, steps=10, warmup=4):
     if world > 1:
         red = model._grad_reducer()
         red_ms = timed(red.reduce, steps)
+    # one GPU: the same step captured once into a CUDA graph and replayed (the eager step is ~120 small launches)
+    graph_ms = graph_err = None
+    if world == 1:
+        try:
+            model.capture_train_step(Bl, 1, 1)
+            graph_ms = timed(lambda: model.train_step_graphed(xd, yd), steps)
+            loss_g = float(model._graph_loss)
+            if not np.isfinite(loss_g):
+                graph_err = "non-finite loss from the captured step"
+        except Exception as exc:  # noqa: BLE001 -- an optional extra must not take the headline down
+            graph_err = str(exc)[:200]
     peak, _ = load_peaks()
+    fused = model._fused_draws_plan() is not None
     return {"workload": "Bayesian NFN 5 radial flows, 1-D y, hidden (10,) tanh, S=32 draws folded, %d samples per GPU "
                         "(S*B = 2^20 folded rows per GPU), Adam training step, data-parallel" % Bl,
             "global_samples_per_step": Bg, "folded_rows_per_gpu": S * Bl, "ms_per_step": step_ms,
             "samples_per_s": Bg / (step_ms * 1e-3), "folded_rows_per_s": S * Bg / (step_ms * 1e-3),
             "loss": loss, "loss_finite": bool(np.isfinite(loss)),
             "breakdown_ms": {"head_kernel_fwd_bwd": head_ms, "flat_grad_allreduce": red_ms,
-                             "mlp_fwd_bwd_kl_adam_and_launch_gaps": step_ms - head_ms - (red_ms or 0.0)},
+                             "everything_else_and_launch_gaps": step_ms - head_ms - (red_ms or 0.0)},
             "head_roofline_frac": 4 * (2 * 17 + 1 + 1) * S * Bl / (head_ms * 1e-3) / 1e9 / peak,
             "allreduce": ("one float32 NCCL all-reduce of %d values (flat gradient buffer + sum logp)" % (n_grad + 2))
-                         if world > 1 else None, "eager": True}
+                         if world > 1 else None, "eager": True,
+            "folded_draw_kernels": fused, "how": (
+                "3 kernels for the network: first variational layer over S*B folded rows, emitting layer + flow chain + "
+                "both backward GEMMs with per-draw weights (t / dt / repeated y never in HBM), first layer's per-draw "
+                "weight gradient; weight draws, exact KL and Adam in torch" if fused else
+                "batched GEMMs + streaming head + autograd"),
+            "cuda_graph_ms_per_step": graph_ms, "cuda_graph_error": graph_err,
+            "samples_per_s_cuda_graph": (Bg / (graph_ms * 1e-3)) if graph_ms else None}
 
 
 def measure_other_config(cfg, args, device, rank, world, lib, steps=20, warmup=3):

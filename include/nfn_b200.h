@@ -304,6 +304,37 @@ int nfn_mdn_forward_backward_x(int n_centers, int n_dims, const float* t, const 
                                float* dt, float* dy, double* logp_sum, double* dt_colsum, int64_t B,
                                const nfn_event_xform* xf, void* stream);
 /*
+ * S posterior weight draws folded into the batch: what the Bayesian estimators' Monte-Carlo loop
+ * (BayesianNNEstimator.py:65-76: `for _ in range(posterior_draws): self(x).log_prob(y)`, and the S-draw training
+ * step of BASELINE config 4) becomes when every draw is a slab of ONE launch.  Rows are draw-major: row
+ * s * rows_per_draw + b is sample b under weight draw s.
+ *   nfn_dense_act_*_draws         the first tfp.layers.DenseVariational layer (BayesianNNEstimator.py:103-118):
+ *                                 x [rows_per_draw, in] is read per SAMPLE, w [draws, in*units + units] is the
+ *                                 layer's flat per-draw sample [kernel (in x units) | bias]; out / dout
+ *                                 [draws * rows_per_draw, out_width] with columns units .. out_width zero (the row
+ *                                 width the fused head wants); dw [draws, in*units + units] += per-draw gradient.
+ *                                 x_mean / x_std (nullable together) fuse the input normalisation
+ *                                 (MaximumLikelihoodNNEstimator.py:40).  in <= 8, units <= 64, out_width % 8 == 0.
+ *   nfn_dense_chain_*_draws_x     the emitting DenseVariational layer + the flow chain, per-draw weights
+ *                                 W [draws, hidden, P], bias [draws, P], dW / dbias likewise (+=); y [rows_per_draw, d]
+ *                                 per SAMPLE (not repeated); h, logp, dh, g_logp are folded.  Served by the
+ *                                 mma.sync kernel (weights re-staged per draw); B = draws * rows_per_draw.
+ */
+int nfn_dense_act_forward_draws(const float* x, const float* x_mean, const float* x_std, const float* w, int draws,
+                                int64_t rows_per_draw, int in_features, int units, int out_width, int act, float* out,
+                                void* stream);
+int nfn_dense_act_backward_draws(const float* x, const float* x_mean, const float* x_std, const float* out,
+                                 const float* dout, int draws, int64_t rows_per_draw, int in_features, int units,
+                                 int out_width, int act, float* dw, void* stream);
+int nfn_dense_chain_forward_draws_x(const nfn_chain_desc* desc, int hidden, int draws, int64_t rows_per_draw,
+                                    const float* h, const float* W, const float* bias, const float* y, int64_t y_rows,
+                                    float* logp, const nfn_event_xform* xf, void* stream);
+int nfn_dense_chain_forward_backward_draws_x(const nfn_chain_desc* desc, int hidden, int draws, int64_t rows_per_draw,
+                                             const float* h, const float* W, const float* bias, const float* y,
+                                             int64_t y_rows, const float* g_logp, float g_scale, float* logp, float* dh,
+                                             float* dW, float* dbias, double* logp_sum, const nfn_event_xform* xf,
+                                             void* stream);
+/*
  * The emitting Dense(P) layer fused into the MDN head: replaces `Dense(output_size, "linear")`
  * (MaximumLikelihoodNNEstimator.py:43) + GaussianMixtureLayer's log_prob (DistributionLayers.py:196-212) + their
  * tape gradients, P = n_centers * (2 n_dims + 1).  Same contract as nfn_dense_chain_*_x: t = h W + bias is formed

@@ -440,7 +440,10 @@ class MeanFieldLayer(torch.nn.Module):
 
 class _IndependentNormal(torch.distributions.Independent):
     def __init__(self, loc, scale):
-        super().__init__(torch.distributions.Normal(loc, scale), 1)
+        # no argument validation: it reduces every parameter tensor to a bool and reads it back on the host -- eight
+        # device-to-host synchronisations per Bayesian training step (measured), and it cannot be graph-captured;
+        # the scale is 1e-3 + softplus(.) or a positive constant by construction
+        super().__init__(torch.distributions.Normal(loc, scale, validate_args=False), 1, validate_args=False)
 
     @property
     def event_shape(self):

@@ -555,6 +555,103 @@ int nfn_dense_chain_forward_backward_x(const nfn_chain_desc* desc, int hidden, c
   return dense_dispatch(desc, hidden, a, true, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------ folded posterior draws (Bayesian estimators)
+// mma.sync body only (its weights are re-staged per draw from a few hundred bytes; the tcgen05 kernel pre-splits
+// its weight tiles once per CTA)
+static int dense_draws_dispatch(const nfn_chain_desc* desc, int hidden, const DenseArgs& a, bool bwd, cudaStream_t st) {
+  const std::string key = chain_key(desc->n_dims, desc->trainable_base != 0, desc->n_flows, desc->flow_type);
+  const int mode = math_mode();
+  const DenseKernels* k = find_dense(key + "|h" + std::to_string(hidden));
+  if (k && k->fn[mode][bwd ? 1 : 0]) return cuda_error(k->fn[mode][bwd ? 1 : 0](a, st), key.c_str());
+  bool served = false;
+  cudaError_t e = launch_dense_jit(desc, hidden, key, a, bwd, mode, st, &served);
+  if (e != cudaSuccess) return cuda_error(e, key.c_str());
+  if (!served)
+    return set_error(NFN_ERR_UNSUPPORTED, "no fused dense kernel for chain %s with hidden width %d", key.c_str(), hidden);
+  return NFN_OK;
+}
+
+static int draws_common(int draws, int64_t rows_per_draw, int64_t y_rows) {
+  if (draws < 1 || draws > 65535) return set_error(NFN_ERR_SHAPE, "draws=%d outside 1..65535", draws);
+  if (rows_per_draw < 0) return set_error(NFN_ERR_SHAPE, "rows_per_draw=%lld", (long long)rows_per_draw);
+  if (y_rows != rows_per_draw && y_rows != 1)
+    return set_error(NFN_ERR_SHAPE, "y must have rows_per_draw=%lld rows (one per sample, not per folded row) or 1",
+                     (long long)rows_per_draw);
+  return NFN_OK;
+}
+
+int nfn_dense_chain_forward_draws_x(const nfn_chain_desc* desc, int hidden, int draws, int64_t rows_per_draw,
+                                    const float* h, const float* W, const float* bias, const float* y, int64_t y_rows,
+                                    float* logp, const nfn_event_xform* xf, void* stream) {
+  int rc = draws_common(draws, rows_per_draw, y_rows);
+  if (rc != NFN_OK) return rc;
+  const int64_t B = (int64_t)draws * rows_per_draw;
+  rc = dense_common(desc, hidden, h, W, bias, y, 1, logp, B);   // (y rows were checked against rows_per_draw above)
+  if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
+  DenseArgs a{};
+  a.h = h; a.W = W; a.bias = bias; a.y = y; a.logp = logp; a.B = B; a.g_scale = 1.0f;
+  a.y_broadcast = (y_rows == 1 && rows_per_draw != 1);
+  a.draws = draws; a.rows_per_draw = rows_per_draw;
+  if ((rc = set_xform(a.xf, xf, desc->n_dims)) != NFN_OK) return rc;
+  return dense_draws_dispatch(desc, hidden, a, false, (cudaStream_t)stream);
+}
+
+int nfn_dense_chain_forward_backward_draws_x(const nfn_chain_desc* desc, int hidden, int draws, int64_t rows_per_draw,
+                                             const float* h, const float* W, const float* bias, const float* y,
+                                             int64_t y_rows, const float* g_logp, float g_scale, float* logp, float* dh,
+                                             float* dW, float* dbias, double* logp_sum, const nfn_event_xform* xf,
+                                             void* stream) {
+  int rc = draws_common(draws, rows_per_draw, y_rows);
+  if (rc != NFN_OK) return rc;
+  const int64_t B = (int64_t)draws * rows_per_draw;
+  rc = dense_common(desc, hidden, h, W, bias, y, 1, logp, B);   // (y rows were checked against rows_per_draw above)
+  if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
+  if (!dh || !dW || !dbias) return set_error(NFN_ERR_NULL, "dh, dW and dbias must be non-NULL");
+  if (!aligned(dh, 16)) return set_error(NFN_ERR_ALIGN, "dh must be 16-byte aligned");
+  DenseArgs a{};
+  a.h = h; a.W = W; a.bias = bias; a.y = y; a.g_logp = g_logp; a.logp = logp; a.dh = dh; a.dW = dW;
+  a.dbias = dbias; a.logp_sum = logp_sum; a.B = B; a.g_scale = g_scale;
+  a.y_broadcast = (y_rows == 1 && rows_per_draw != 1);
+  a.draws = draws; a.rows_per_draw = rows_per_draw;
+  if ((rc = set_xform(a.xf, xf, desc->n_dims)) != NFN_OK) return rc;
+  return dense_draws_dispatch(desc, hidden, a, true, (cudaStream_t)stream);
+}
+
+static int act_draws_common(const float* x, const float* x_mean, const float* x_std, int draws, int64_t rows_per_draw,
+                            int in_features, int units, int out_width, int act) {
+  if (draws < 1 || draws > 65535) return set_error(NFN_ERR_SHAPE, "draws=%d outside 1..65535", draws);
+  if (rows_per_draw < 0) return set_error(NFN_ERR_SHAPE, "rows_per_draw=%lld", (long long)rows_per_draw);
+  if (!mlp_draws_supported(in_features, units, out_width, act))
+    return set_error(NFN_ERR_UNSUPPORTED, "folded first layer %d -> %d (row width %d, act %d) is outside the kernel's range "
+                     "(<= 8 inputs, <= 64 units, row width a multiple of 8 <= 64)", in_features, units, out_width, act);
+  if (rows_per_draw == 0) return 1;
+  if (!x) return set_error(NFN_ERR_NULL, "x must be non-NULL");
+  if ((x_mean == nullptr) != (x_std == nullptr)) return set_error(NFN_ERR_NULL, "x_mean and x_std go together");
+  return NFN_OK;
+}
+
+int nfn_dense_act_forward_draws(const float* x, const float* x_mean, const float* x_std, const float* w, int draws,
+                                int64_t rows_per_draw, int in_features, int units, int out_width, int act, float* out,
+                                void* stream) {
+  int rc = act_draws_common(x, x_mean, x_std, draws, rows_per_draw, in_features, units, out_width, act);
+  if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
+  if (!w || !out) return set_error(NFN_ERR_NULL, "w and out must be non-NULL");
+  if (!aligned(out, 16)) return set_error(NFN_ERR_ALIGN, "out must be 16-byte aligned");
+  return launch_dense_act_draws(false, x, x_mean, x_std, w, nullptr, nullptr, out, nullptr, draws, rows_per_draw, in_features,
+                                units, out_width, act, (cudaStream_t)stream);
+}
+
+int nfn_dense_act_backward_draws(const float* x, const float* x_mean, const float* x_std, const float* out,
+                                 const float* dout, int draws, int64_t rows_per_draw, int in_features, int units,
+                                 int out_width, int act, float* dw, void* stream) {
+  int rc = act_draws_common(x, x_mean, x_std, draws, rows_per_draw, in_features, units, out_width, act);
+  if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
+  if (!out || !dout || !dw) return set_error(NFN_ERR_NULL, "out, dout and dw must be non-NULL");
+  if (!aligned(out, 16) || !aligned(dout, 16)) return set_error(NFN_ERR_ALIGN, "out and dout must be 16-byte aligned");
+  return launch_dense_act_draws(true, x, x_mean, x_std, nullptr, out, dout, nullptr, dw, draws, rows_per_draw, in_features,
+                                units, out_width, act, (cudaStream_t)stream);
+}
+
 int64_t nfn_jit_dense_tc5_compile_check(const nfn_chain_desc* desc, int hidden, int accurate) {
   int rc = check_desc(desc);
   if (rc != NFN_OK) return rc;

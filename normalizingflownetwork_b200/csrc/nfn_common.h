@@ -427,4 +427,10 @@ int launch_dense_act_backward(const float* x, const float* xmean, const float* x
                               const float* w, float* dx, float* dW, float* db, long long B, int K, int N, int act,
                               cudaStream_t st);
 
+// first variational layer with S folded weight draws (nfn_mlp.cu)
+int mlp_draws_supported(int K, int N, int NP, int act);
+int launch_dense_act_draws(bool bwd, const float* x, const float* xmean, const float* xstd, const float* w,
+                           const float* out_in, const float* dout, float* out, float* dw, int S, long long Bd, int K, int N,
+                           int NP, int act, cudaStream_t st);
+
 }  // namespace nfn

@@ -37,6 +37,12 @@ struct DenseArgs {
   float g_scale;
   int y_broadcast;
   EventXform xf;
+  // S posterior weight draws folded into the batch (reference BayesianNNEstimator.py:65-76; mma.sync body only):
+  // rows are draw-major, row s * rows_per_draw + b is sample b under draw s; W [S][H][P], bias [S][P], dW [S][H][P],
+  // dbias [S][P] are per draw, y [rows_per_draw][d] is per SAMPLE (not repeated); h, logp, dh, g_logp are folded.
+  // draws <= 1: one weight set for all B rows.
+  int draws;
+  long long rows_per_draw;
 };
 
 // ---------------------------------------------------------------- tensor-core helpers
@@ -183,68 +189,113 @@ NFN_DEVI void dense_head_body(const DenseArgs& a) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tig = lane & 3;
-  const long long ntiles = (a.B + T - 1) / T;
+  // Tiles never straddle two draws: a draw is cut into its own tiles, and with folded draws every CTA takes a
+  // CONTIGUOUS range of tiles, so that it changes weights at most a few times (one weight set: round-robin tiles)
+  const bool batched = a.draws > 1;
+  const long long Bd = batched ? a.rows_per_draw : a.B;       // rows that share one weight set
+  const long long tpd = (Bd + T - 1) / T;                     // tiles per draw
+  const long long ntiles = (batched ? (long long)a.draws : 1ll) * tpd;
+  long long tile = batched ? ntiles * blockIdx.x / gridDim.x : blockIdx.x;
+  const long long tile_end = batched ? ntiles * (blockIdx.x + 1) / gridDim.x : ntiles;
+  const long long tstep = batched ? 1 : gridDim.x;
+  // tile -> (draw, first row inside the draw, first folded row)
+  auto draw_of = [&](long long t) -> long long { return batched ? t / tpd : 0; };
+  auto rd0_of = [&](long long t) -> long long { return (t - draw_of(t) * tpd) * T; };
+  auto fold0_of = [&](long long t) -> long long { return draw_of(t) * Bd + rd0_of(t); };
 
-  // weights, bias (zero-padded to P8 columns), accumulators
-  for (int i = tid; i < H * PW; i += T) {
-    const int k = i / PW, n = i % PW;
-    sW[i] = (n < P) ? __ldg(a.W + k * P + n) : 0.0f;
-  }
-  for (int i = tid; i < P8; i += T) sB[i] = (i < P) ? __ldg(a.bias + i) : 0.0f;
+  // weights, bias (zero-padded to P8 columns) of one draw
+  auto stage_weights = [&](long long s) {
+    const float* Ws = a.W + s * (long long)(H * P);
+    const float* bs = a.bias + s * (long long)P;
+    for (int i = tid; i < H * PW; i += T) {
+      const int k = i / PW, n = i % PW;
+      sW[i] = (n < P) ? __ldg(Ws + k * P + n) : 0.0f;
+    }
+    for (int i = tid; i < P8; i += T) sB[i] = (i < P) ? __ldg(bs + i) : 0.0f;
+  };
+  // per-warp partial sums of dW / db -> global (one atomic per entry per CTA and draw), then cleared
+  auto flush_grads = [&](long long s) {
+    float* dWs = a.dW + s * (long long)(H * P);
+    float* dbs = a.dbias + s * (long long)P;
+    for (int i = tid; i < H * P8; i += T) {
+      const int k = i / P8, n = i % P8;
+      float v = 0.0f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        v += sAcc[w * (H * P8) + i];
+        sAcc[w * (H * P8) + i] = 0.0f;
+      }
+      if (n < P) atomicAdd(dWs + k * P + n, v);
+    }
+    for (int n = tid; n < P8; n += T) {
+      float v = 0.0f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        v += sAccB[w * P8 + n];
+        sAccB[w * P8 + n] = 0.0f;
+      }
+      if (n < P) atomicAdd(dbs + n, v);
+    }
+  };
   if constexpr (BWD) {
     for (int i = tid; i < G::kAcc + G::kAccB; i += T) sAcc[i] = 0.0f;
   }
-
-  __syncthreads();
+  long long s_cur = -1;   // draw whose weights are staged
 
   // Every warp owns rows [32 warp, 32 warp + 32) of each tile end to end (h load, the three GEMMs,
   // the per-row flow chain, the dh store), so the tile loop needs only warp-level barriers.
-  // async h rows of this warp: 16-byte chunks into rows of stride HS; rows past B are zeroed
-  auto load_h = [&](int buf, long long tile) {
+  // async h rows of this warp: 16-byte chunks into rows of stride HS; rows past the draw's end are zeroed
+  auto load_h = [&](int buf, long long t) {
     constexpr int CPR = H / 4;  // chunks per row
     float* dst = hT + buf * G::kH + (warp * 32) * HS;
-    const long long row0 = tile * T + warp * 32;
+    const long long rd = rd0_of(t) + warp * 32, row0 = fold0_of(t) + warp * 32;
     for (int q = lane; q < 32 * CPR; q += 32) {
       const int r = q / CPR, c = q % CPR;
       float* d = dst + r * HS + 4 * c;
-      if (row0 + r < a.B) cp_async16(smem_u32(d), a.h + (row0 + r) * H + 4 * c);
+      if (rd + r < Bd) cp_async16(smem_u32(d), a.h + (row0 + r) * H + 4 * c);
       else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
 
-  long long tile = blockIdx.x;
-  if (tile < ntiles) load_h(0, tile);
+  if (tile < tile_end) load_h(0, tile);
   cp_async_commit();
 
   float y_nxt[D];
   float g_nxt = 1.0f;
-  {
-    const long long r0 = tile * T + tid;
-#pragma unroll
-    for (int i = 0; i < D; ++i) y_nxt[i] = 0.0f;
-    if (tile < ntiles && r0 < a.B) {
-      load_event<D>(a.y, a.y_broadcast ? 0 : r0, y_nxt);
-      if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + r0); }
+  // y is indexed by the SAMPLE (row inside the draw), the cotangent by the folded row
+  auto fetch_event = [&](long long t) {
+    const long long rd = rd0_of(t) + tid;
+    if (t < tile_end && rd < Bd) {
+      load_event<D>(a.y, a.y_broadcast ? 0 : rd, y_nxt);
+      if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + fold0_of(t) + tid); }
     }
-  }
+  };
+#pragma unroll
+  for (int i = 0; i < D; ++i) y_nxt[i] = 0.0f;
+  fetch_event(tile);
   double lsum = 0.0;
   int buf = 0;
 
-  for (; tile < ntiles; tile += gridDim.x) {
+  for (; tile < tile_end; tile += tstep) {
+    if (draw_of(tile) != s_cur) {   // (CTA-uniform) first tile, or the next draw's weights
+      __syncthreads();              // every warp is done with the old weights and has added its last partial sums
+      if constexpr (BWD) { if (s_cur >= 0) flush_grads(s_cur); }
+      s_cur = draw_of(tile);
+      stage_weights(s_cur);
+      __syncthreads();
+    }
+    const long long rd = rd0_of(tile) + tid;      // this thread's row inside the draw
+    const long long r = fold0_of(tile) + tid;     // ... and in the folded batch
     float z[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) z[i] = y_nxt[i];
-    if (a.xf.flags) xform_event<D>(a.xf, tile * T + tid, z);
+    if (a.xf.flags) xform_event<D>(a.xf, r, z);
     const float g_cur = g_nxt;
     {
-      const long long nxt = tile + gridDim.x;
-      if (nxt < ntiles) load_h(buf ^ 1, nxt);   // the other buffer was drained at the end of the last iteration
+      const long long nxt = tile + tstep;
+      if (nxt < tile_end) load_h(buf ^ 1, nxt);   // the other buffer was drained at the end of the last iteration
       cp_async_commit();
-      const long long rn = nxt * T + tid;
-      if (rn < a.B) {
-        load_event<D>(a.y, a.y_broadcast ? 0 : rn, y_nxt);
-        if constexpr (BWD) { if (a.g_logp) g_nxt = __ldg(a.g_logp + rn); }
-      }
+      fetch_event(nxt);
       cp_async_wait<1>();
       __syncwarp();
     }
@@ -301,15 +352,14 @@ NFN_DEVI void dense_head_body(const DenseArgs& a) {
     __syncwarp();
 
     // ---- per-row head (flow chain or mixture), dt written in place over t
-    const long long r = tile * T + tid;
     float* row = tT + tid * S;
-    if (r < a.B) {
+    if (rd < Bd) {
       const float lp = xform_out<M>(a.xf, Head::template run<BWD, M>(row, z, BWD ? a.g_scale * g_cur : 0.0f));
       a.logp[r] = lp;
       lsum += (double)lp;
     } else if constexpr (BWD) {
 #pragma unroll
-      for (int j = 0; j < P; ++j) row[j] = 0.0f;   // rows past B contribute nothing to dW / db
+      for (int j = 0; j < P; ++j) row[j] = 0.0f;   // rows past the end contribute nothing to dW / db
     }
 
     if constexpr (BWD) {
@@ -439,11 +489,11 @@ NFN_DEVI void dense_head_body(const DenseArgs& a) {
       // ---- dh rows of this warp -> global, coalesced 16-byte streaming stores
       {
         constexpr int CPR = H / 4;
-        const long long row0 = tile * T + warp * 32;
+        const long long row0 = fold0_of(tile) + warp * 32, rdw = rd0_of(tile) + warp * 32;
         const float* src = hcur + (warp * 32) * HS;
         for (int q = lane; q < 32 * CPR; q += 32) {
           const int rr = q / CPR, cc = q % CPR;
-          if (row0 + rr < a.B)
+          if (rdw + rr < Bd)
             st_stream_f4(a.dh + (row0 + rr) * H + 4 * cc, *reinterpret_cast<const float4*>(src + rr * HS + 4 * cc));
         }
       }
@@ -459,21 +509,7 @@ NFN_DEVI void dense_head_body(const DenseArgs& a) {
   }
   if constexpr (BWD) {
     __syncthreads();
-    for (int i = tid; i < H * P8; i += T) {
-      const int k = i / P8, n = i % P8;
-      if (n < P) {
-        float v = 0.0f;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) v += sAcc[w * (H * P8) + i];
-        atomicAdd(a.dW + k * P + n, v);
-      }
-    }
-    for (int n = tid; n < P; n += T) {
-      float v = 0.0f;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) v += sAccB[w * P8 + n];
-      atomicAdd(a.dbias + n, v);
-    }
+    if (s_cur >= 0) flush_grads(s_cur);
   }
 }
 

@@ -460,6 +460,134 @@ cudaError_t dispatch_bwd(int act, const float* x, const float* xmean, const floa
   }
 }
 
+// ---------------------------------------------------------------- first layer with folded weight draws
+// The Bayesian estimators fold S posterior weight draws into the batch (reference BayesianNNEstimator.py:65-76;
+// BASELINE config 4): row s * Bd + b is sample b under draw s.  The first variational layer has few inputs
+// (K <= 8) and per-draw weights w[s] = [kernel (K x N) | bias (N)] (tfp DenseVariational's flat layout), so one
+// draw's weights are a few hundred bytes of shared memory and x is read once per draw from L2:
+//   forward   out[s Bd + b][n] = act(xn_b . kernel_s[:, n] + bias_s[n])  for n < N, zero for N <= n < NP
+//             (NP = the row width the fused Dense(P)+head kernel wants: a multiple of 16)
+//   backward  dw[s] += [ xn^T dpre_s | 1^T dpre_s ],  dpre = dout * act'(out)      (no input gradient)
+// blockIdx.y = draw; blockIdx.z (backward) = an 8-column slice of the units, whose (K + 1) x 8 sums stay in
+// registers over the thread's rows and meet through warp shuffles and shared memory once, at the end.
+constexpr int kDrawT = 256;
+constexpr int kDrawMaxK = 8;
+
+__device__ __forceinline__ void load_xn(const float* __restrict__ x, const float* __restrict__ xmean,
+                                        const float* __restrict__ xstd, long long b, int K, float (&xn)[kDrawMaxK]) {
+#pragma unroll
+  for (int k = 0; k < kDrawMaxK; ++k) {
+    float v = 0.0f;
+    if (k < K) {
+      v = __ldg(x + b * K + k);
+      if (xmean) v = __fdiv_rn(v - __ldg(xmean + k), __ldg(xstd + k) + 1e-8f);
+    }
+    xn[k] = v;
+  }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kDrawT) dense_act_draws_fwd(const float* __restrict__ x, const float* __restrict__ xmean,
+                                                            const float* __restrict__ xstd, const float* __restrict__ w,
+                                                            float* __restrict__ out, long long Bd, int K, int N, int NP) {
+  extern __shared__ __align__(16) float smem[];   // [K * N + N]
+  const int s = blockIdx.y;
+  const float* ws = w + (long long)s * (K * N + N);
+  for (int i = threadIdx.x; i < K * N + N; i += kDrawT) smem[i] = __ldg(ws + i);
+  __syncthreads();
+  const float* sb = smem + K * N;
+  for (long long b = (long long)blockIdx.x * kDrawT + threadIdx.x; b < Bd; b += (long long)gridDim.x * kDrawT) {
+    float xn[kDrawMaxK];
+    load_xn(x, xmean, xstd, b, K, xn);
+    float* o = out + ((long long)s * Bd + b) * NP;
+    for (int n0 = 0; n0 < NP; n0 += 4) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + j;
+        float acc = 0.0f;
+        if (n < N) {
+          acc = sb[n];
+#pragma unroll
+          for (int k = 0; k < kDrawMaxK; ++k)
+            if (k < K) acc = fmaf(xn[k], smem[k * N + n], acc);
+          acc = act_fwd<ACT>(acc);
+        }
+        v[j] = acc;
+      }
+      *reinterpret_cast<float4*>(o + n0) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kDrawT) dense_act_draws_bwd(const float* __restrict__ x, const float* __restrict__ xmean,
+                                                            const float* __restrict__ xstd, const float* __restrict__ out,
+                                                            const float* __restrict__ dout, float* __restrict__ dw,
+                                                            long long Bd, int K, int N, int NP) {
+  __shared__ float part[kDrawT / 32][(kDrawMaxK + 1) * 8];
+  const int s = blockIdx.y, n0 = 8 * blockIdx.z;
+  float acc[kDrawMaxK + 1][8];
+#pragma unroll
+  for (int k = 0; k <= kDrawMaxK; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.0f;
+  for (long long b = (long long)blockIdx.x * kDrawT + threadIdx.x; b < Bd; b += (long long)gridDim.x * kDrawT) {
+    float xn[kDrawMaxK];
+    load_xn(x, xmean, xstd, b, K, xn);
+    const long long row = ((long long)s * Bd + b) * NP + n0;
+    const float4 o0 = __ldg(reinterpret_cast<const float4*>(out + row)), o1 = __ldg(reinterpret_cast<const float4*>(out + row + 4));
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(dout + row)), d1 = __ldg(reinterpret_cast<const float4*>(dout + row + 4));
+    const float o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+    const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dpre = d[j] * act_bwd<ACT>(o[j]);
+      acc[kDrawMaxK][j] += dpre;
+#pragma unroll
+      for (int k = 0; k < kDrawMaxK; ++k) acc[k][j] = fmaf(xn[k], dpre, acc[k][j]);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k <= kDrawMaxK; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[k][j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) part[warp][k * 8 + j] = v;
+    }
+  __syncthreads();
+  float* dws = dw + (long long)s * (K * N + N);
+  for (int e = threadIdx.x; e < (kDrawMaxK + 1) * 8; e += kDrawT) {
+    const int k = e / 8, n = n0 + e % 8;
+    if (n < N && (k < K || k == kDrawMaxK)) {
+      float v = 0.0f;
+#pragma unroll
+      for (int wq = 0; wq < kDrawT / 32; ++wq) v += part[wq][e];
+      atomicAdd(dws + (k == kDrawMaxK ? K * N + n : k * N + n), v);
+    }
+  }
+}
+
+template <int ACT>
+cudaError_t launch_draws(bool bwd, const float* x, const float* xmean, const float* xstd, const float* w, const float* out_in,
+                         const float* dout, float* out, float* dw, int S, long long Bd, int K, int N, int NP,
+                         cudaStream_t st) {
+  const DeviceInfo& di = device_info();
+  const long long tiles = (Bd + kDrawT - 1) / kDrawT;
+  const int slices = bwd ? (N + 7) / 8 : 1;
+  long long gx = ((long long)di.sm_count * 8 + (long long)S * slices - 1) / ((long long)S * slices);   // ~8 CTAs per SM overall
+  if (gx < 1) gx = 1;
+  if (gx > tiles) gx = tiles;
+  const dim3 grid((unsigned)gx, (unsigned)S, (unsigned)slices);
+  if (bwd) dense_act_draws_bwd<ACT><<<grid, kDrawT, 0, st>>>(x, xmean, xstd, out_in, dout, dw, Bd, K, N, NP);
+  else dense_act_draws_fwd<ACT><<<grid, kDrawT, (size_t)(K * N + N) * sizeof(float), st>>>(x, xmean, xstd, w, out, Bd, K, N, NP);
+  count_launch();
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 int mlp_layer_supported(int K, int N, int act) {
@@ -500,6 +628,24 @@ int launch_dense_act_backward(const float* x, const float* xmean, const float* x
     }
   }
   return cuda_error(e, "dense_act_bwd");
+}
+
+int mlp_draws_supported(int K, int N, int NP, int act) {
+  return K >= 1 && K <= kDrawMaxK && N >= 1 && N <= 64 && NP >= N && NP % 8 == 0 && NP <= 64 && act >= 0 && act <= 4;
+}
+
+int launch_dense_act_draws(bool bwd, const float* x, const float* xmean, const float* xstd, const float* w,
+                           const float* out_in, const float* dout, float* out, float* dw, int S, long long Bd, int K, int N,
+                           int NP, int act, cudaStream_t st) {
+  cudaError_t e;
+  switch (act) {
+    case kLinear: e = launch_draws<kLinear>(bwd, x, xmean, xstd, w, out_in, dout, out, dw, S, Bd, K, N, NP, st); break;
+    case kTanh: e = launch_draws<kTanh>(bwd, x, xmean, xstd, w, out_in, dout, out, dw, S, Bd, K, N, NP, st); break;
+    case kRelu: e = launch_draws<kRelu>(bwd, x, xmean, xstd, w, out_in, dout, out, dw, S, Bd, K, N, NP, st); break;
+    case kSigmoid: e = launch_draws<kSigmoid>(bwd, x, xmean, xstd, w, out_in, dout, out, dw, S, Bd, K, N, NP, st); break;
+    default: e = launch_draws<kElu>(bwd, x, xmean, xstd, w, out_in, dout, out, dw, S, Bd, K, N, NP, st); break;
+  }
+  return cuda_error(e, bwd ? "dense_act_draws_bwd" : "dense_act_draws_fwd");
 }
 
 }  // namespace nfn

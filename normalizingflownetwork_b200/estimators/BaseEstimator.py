@@ -365,6 +365,8 @@ class BaseEstimator(torch.nn.Module):
                 self.train_step(self._gx, self._gy)
         torch.cuda.current_stream(self.device).wait_stream(side)
         self._graph = torch.cuda.CUDAGraph()
+        for gen in self._graph_generators():   # private torch generators drawn from inside the step
+            self._graph.register_generator_state(gen)
         with torch.cuda.graph(self._graph):
             self._graph_loss = self.train_step(self._gx, self._gy)
         # the warm-up and capture steps ran on zeros: restore the real state
@@ -382,6 +384,10 @@ class BaseEstimator(torch.nn.Module):
         # the head kernels take the normalisation statistics BY VALUE: a captured step is tied to them
         self._graph_stats_version = getattr(self, "_stats_version", 0)
         return self
+
+    def _graph_generators(self):
+        """torch.Generator objects the training step draws from (they must be registered with a capturing graph)."""
+        return []
 
     def train_step_graphed(self, xb, yb):
         """Replay the captured step on a new mini-batch (device tensors of the captured shape)."""

@@ -162,6 +162,9 @@ class BayesianNNEstimator(BaseEstimator):
             self._wgen = torch.Generator(device=self.device).manual_seed(self.random_seed + 1)
         return self._wgen
 
+    def _graph_generators(self):
+        return [self._weight_generator()]
+
     def params_from_x(self, x):
         h = self._to_dev(x)
         for layer in self.net:
@@ -176,6 +179,62 @@ class BayesianNNEstimator(BaseEstimator):
         for layer in self.net[2:]:
             h = layer(h, n_draws=n_draws, generator=self._weight_generator())
         return h.reshape(n_draws * h.shape[1], h.shape[2])
+
+    # ------------------------------------------------------------------ folded draws, fused kernels
+    fuse_draws = True
+
+    def _fused_draws_plan(self):
+        """(first layer, emitting layer, padded hidden width) when the S-draw step can run on the folded-draw kernels:
+        one hidden DenseVariational layer of <= 64 units fed by <= 8 inputs, a flow-chain head, no x noise."""
+        from ..DistributionLayers import InverseNormalizingFlowLayer
+
+        if not self.fuse_draws or self.map_mode or not isinstance(self.dist_layer, InverseNormalizingFlowLayer):
+            return None
+        dense = [l for l in self.net if isinstance(l, DenseVariational)]
+        if len(dense) != 2 or dense[0].in_features is None or dense[1].in_features is None:
+            return None
+        if self.training and self.x_noise_std > 0.0:
+            return None
+        l1, l2 = dense
+        hp = (l1.units + 15) // 16 * 16
+        name = {v: k for k, v in ACTIVATIONS.items()}.get(type(l1.act))
+        if name is None or not F.dense_act_draws_supported(l1.in_features, l1.units, hp, name):
+            return None
+        if not F.dense_chain_supported(hp) or self.dist_layer.get_total_param_size() < 1:
+            return None
+        return l1, l2, hp, name
+
+    def _draw_weights(self, layer, S):
+        """w [S, size] = loc + scale * eps (the same draws, in the same order, as DenseVariational.forward), and the
+        layer's KL term left in ``last_kl``."""
+        q, r = layer._dists()
+        loc, scale = q.base_dist.loc, q.base_dist.scale
+        w = loc + scale * torch.randn((S,) + tuple(loc.shape), device=loc.device, generator=self._weight_generator())
+        layer.last_kl = layer.kl_weight * (layer._kl(q, r, None) if layer.kl_use_exact
+                                           else (q.log_prob(w) - r.log_prob(w)).mean())
+        return w
+
+    def _fused_draws_forward_backward(self, plan, xb, y, S, g_scale, logp_sum, xform):
+        """x [B, in], raw y [B, d] -> per-draw weight samples (autograd leaves' children) and their gradients.
+        Three kernels: first layer over S*B folded rows, emitting layer + flow chain + both backward GEMMs, first
+        layer's per-draw weight gradient.  Neither t nor dt nor a repeated y ever exists in HBM."""
+        l1, l2, hp, act = plan
+        layer = self.dist_layer
+        P = layer.get_total_param_size()
+        w1, w2 = self._draw_weights(l1, S), self._draw_weights(l2, S)
+        x = self._to_dev(xb)
+        with torch.no_grad():
+            h = F.dense_act_forward_draws(x, w1, l1.units, act, hp, x_mean=self.x_mean, x_std=self.x_std)
+            nk = l2.in_features * P
+            W2 = torch.zeros((S, hp, P), dtype=torch.float32, device=self.device)
+            W2[:, :l2.in_features, :] = w2[:, :nk].view(S, l2.in_features, P)
+            b2 = w2[:, nk:].contiguous()
+            _, dh, dW2, db2 = F.dense_chain_forward_backward_draws(
+                h, W2, b2, y, layer._flow_types, layer._n_dims, layer._trainable_base_dist, g_scale=g_scale,
+                logp_sum=logp_sum, xform=xform)
+            dw1 = F.dense_act_backward_draws(x, h, dh, S, l1.units, act, x_mean=self.x_mean, x_std=self.x_std)
+            dw2 = torch.cat([dW2[:, :l2.in_features, :].reshape(S, nk), db2], dim=1)
+        return (w1, w2), (dw1, dw2)
 
     def train_step(self, xb, yb, global_batch=None):
         if self.n_train_draws <= 1 or self.map_mode:
@@ -195,13 +254,22 @@ class BayesianNNEstimator(BaseEstimator):
             self.optimizer.zero_grad(set_to_none=True)
         if B == 0:
             return self._empty_shard_step(reducer, Bg, world, denom=S * Bg)
-        t = self.params_from_x_draws(xb, S)
-        # raw y: normalisation, training noise (independent per folded row) and the Jacobian run in the head kernel
-        y = self._to_dev(yb).repeat(S, 1)
         logp_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
-        dt = self._head_forward_backward(t, y, -1.0 / (S * Bg), logp_sum, xform=self._xform(y.shape[1], training=True))
-        extra = self._extra_loss()
-        torch.autograd.backward([t, extra], [dt, torch.full_like(extra, 1.0 / world)])
+        plan = self._fused_draws_plan()
+        if plan is not None:
+            y = self._to_dev(yb)
+            ws, dws = self._fused_draws_forward_backward(plan, xb, y, S, -1.0 / (S * Bg), logp_sum,
+                                                         self._xform(y.shape[1], training=True))
+            extra = self._extra_loss()
+            torch.autograd.backward(list(ws) + [extra], list(dws) + [torch.full_like(extra, 1.0 / world)])
+        else:
+            t = self.params_from_x_draws(xb, S)
+            # raw y: normalisation, training noise (independent per folded row) and the Jacobian run in the head kernel
+            y = self._to_dev(yb).repeat(S, 1)
+            dt = self._head_forward_backward(t, y, -1.0 / (S * Bg), logp_sum,
+                                             xform=self._xform(y.shape[1], training=True))
+            extra = self._extra_loss()
+            torch.autograd.backward([t, extra], [dt, torch.full_like(extra, 1.0 / world)])
         if reducer is not None:
             logp_sum = self._reduce_step(reducer, logp_sum)
         self.optimizer.step()

@@ -336,6 +336,105 @@ def dense_chain_forward_backward(h, W, bias, y, flow_types, n_dims, trainable_ba
     return logp, dh, dW, dbias
 
 
+# ----------------------------------------------------------------------------- folded posterior draws
+def dense_act_draws_supported(in_features, units, out_width, activation):
+    return (1 <= in_features <= 8 and 1 <= units <= 64 and out_width >= units and out_width % 8 == 0 and out_width <= 64
+            and activation in ACT_CODES)
+
+
+def dense_act_forward_draws(x, w, units, activation, out_width, x_mean=None, x_std=None):
+    """First variational layer with S weight draws folded into the batch: x [B, in] (per sample), w [S, in*units + units]
+    (tfp DenseVariational's flat [kernel | bias] sample per draw) -> out [S*B, out_width], draw-major, columns
+    units .. out_width zero.  Reference: BayesianNNEstimator.py:65-76, :103-118."""
+    lib = _lib.load()
+    x = _as_f32_cuda(x, "x")
+    dev = x.device
+    w = _as_f32_cuda(w, "w", device=dev)
+    B, K = x.shape
+    S = w.shape[0]
+    assert w.shape[1] == K * units + units, "w must be [S, in*units + units]"
+    out = torch.empty((S * B, out_width), dtype=torch.float32, device=dev)
+    xm = _as_f32_cuda(x_mean, "x_mean", device=dev) if x_mean is not None else None
+    xs = _as_f32_cuda(x_std, "x_std", device=dev) if x_std is not None else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_dense_act_forward_draws(_lib.ptr(x), _lib.ptr(xm), _lib.ptr(xs), _lib.ptr(w), S, B, K, units,
+                                                   out_width, ACT_CODES[activation], _lib.ptr(out),
+                                                   _lib.current_stream(dev)))
+    return out
+
+
+def dense_act_backward_draws(x, out, dout, n_draws, units, activation, x_mean=None, x_std=None):
+    """Per-draw gradient of the folded first layer: dw [S, in*units + units] = [xn^T dpre_s | 1^T dpre_s]."""
+    lib = _lib.load()
+    x = _as_f32_cuda(x, "x")
+    dev = x.device
+    out = _aligned(_as_f32_cuda(out, "out", device=dev))
+    dout = _aligned(_as_f32_cuda(dout, "dout", device=dev))
+    B, K = x.shape
+    assert out.shape == dout.shape and out.shape[0] == n_draws * B
+    dw = torch.zeros((n_draws, K * units + units), dtype=torch.float32, device=dev)
+    xm = _as_f32_cuda(x_mean, "x_mean", device=dev) if x_mean is not None else None
+    xs = _as_f32_cuda(x_std, "x_std", device=dev) if x_std is not None else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_dense_act_backward_draws(_lib.ptr(x), _lib.ptr(xm), _lib.ptr(xs), _lib.ptr(out), _lib.ptr(dout),
+                                                    n_draws, B, K, units, out.shape[1], ACT_CODES[activation],
+                                                    _lib.ptr(dw), _lib.current_stream(dev)))
+    return dw
+
+
+def dense_chain_forward_draws(h, W, bias, y, flow_types, n_dims, trainable_base_dist, xform=None):
+    """Fused emitting layer + flow chain with per-draw weights: h [S*B, H] (draw-major), W [S, H, P], bias [S, P],
+    y [B, d] per sample (or one row).  Returns logp [S*B]."""
+    lib = _lib.load()
+    desc = _lib.make_desc(flow_types, n_dims, trainable_base_dist)
+    P = _lib.check(lib.nfn_chain_param_size(ctypes.byref(desc)))
+    h = _aligned(_as_f32_cuda(h, "h"))
+    dev = h.device
+    W = _as_f32_cuda(W, "W", device=dev)
+    bias = _as_f32_cuda(bias, "bias", device=dev)
+    y = _aligned(_as_f32_cuda(y, "y", device=dev))
+    S, H = W.shape[0], W.shape[1]
+    assert tuple(W.shape) == (S, H, P) and tuple(bias.shape) == (S, P) and h.shape[1] == H and h.shape[0] % S == 0
+    Bd = h.shape[0] // S
+    if y.dim() != 2 or y.shape[1] != n_dims or y.shape[0] not in (Bd, 1):
+        raise ValueError("y must be [rows_per_draw, n_dims] or one row")
+    logp = torch.empty(S * Bd, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_dense_chain_forward_draws_x(ctypes.byref(desc), H, S, Bd, _lib.ptr(h), _lib.ptr(W), _lib.ptr(bias),
+                                                       _lib.ptr(y), y.shape[0], _lib.ptr(logp), _xf(xform),
+                                                       _lib.current_stream(dev)))
+    return logp
+
+
+def dense_chain_forward_backward_draws(h, W, bias, y, flow_types, n_dims, trainable_base_dist, g_logp=None, g_scale=1.0,
+                                       logp_sum=None, xform=None):
+    """Forward + reverse sweep of the above.  Returns (logp [S*B], dh [S*B, H], dW [S, H, P], dbias [S, P])."""
+    lib = _lib.load()
+    desc = _lib.make_desc(flow_types, n_dims, trainable_base_dist)
+    P = _lib.check(lib.nfn_chain_param_size(ctypes.byref(desc)))
+    h = _aligned(_as_f32_cuda(h, "h"))
+    dev = h.device
+    W = _as_f32_cuda(W, "W", device=dev)
+    bias = _as_f32_cuda(bias, "bias", device=dev)
+    y = _aligned(_as_f32_cuda(y, "y", device=dev))
+    S, H = W.shape[0], W.shape[1]
+    assert tuple(W.shape) == (S, H, P) and tuple(bias.shape) == (S, P) and h.shape[1] == H and h.shape[0] % S == 0
+    Bd = h.shape[0] // S
+    if y.dim() != 2 or y.shape[1] != n_dims or y.shape[0] not in (Bd, 1):
+        raise ValueError("y must be [rows_per_draw, n_dims] or one row")
+    logp = torch.empty(S * Bd, dtype=torch.float32, device=dev)
+    dh = torch.empty((S * Bd, H), dtype=torch.float32, device=dev)
+    dW = torch.zeros((S, H, P), dtype=torch.float32, device=dev)
+    dbias = torch.zeros((S, P), dtype=torch.float32, device=dev)
+    g_logp = _prep_g(g_logp, S * Bd, dev, "dense_chain_forward_backward_draws")
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_dense_chain_forward_backward_draws_x(
+            ctypes.byref(desc), H, S, Bd, _lib.ptr(h), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(y), y.shape[0],
+            _lib.ptr(g_logp), ctypes.c_float(g_scale), _lib.ptr(logp), _lib.ptr(dh), _lib.ptr(dW), _lib.ptr(dbias),
+            _lib.ptr(logp_sum), _xf(xform), _lib.current_stream(dev)))
+    return logp, dh, dW, dbias
+
+
 class _ChainLogProb(torch.autograd.Function):
     @staticmethod
     def forward(ctx, t, y, flow_types, n_dims, trainable_base_dist):
