@@ -525,7 +525,7 @@ def cfg4_bayes_train_step(device, rank, world, steps=10, warmup=4):
     model._assign_data_normalization(x.numpy(), y.numpy())
     with torch.no_grad():
         model.params_from_x(x[:2].numpy())
-    model.optimizer = torch.optim.Adam(model.parameters(), lr=model.learning_rate, eps=1e-7)
+    model.optimizer = model._make_adam()
     xd, yd = model._to_dev(x), model._to_dev(y)
     Bg = Bl * world
 
@@ -561,17 +561,17 @@ def cfg4_bayes_train_step(device, rank, world, steps=10, warmup=4):
     if world > 1:
         red = model._grad_reducer()
         red_ms = timed(red.reduce, steps)
-    # one GPU: the same step captured once into a CUDA graph and replayed (the eager step is ~120 small launches)
+    # one GPU: the same step captured once into a CUDA graph and replayed (the eager step is ~120 small launches).
+    # Not at N > 1: a captured step containing the NCCL all-reduce never completed its replay on 2 GPUs (measured).
     graph_ms = graph_err = None
     if world == 1:
         try:
             model.capture_train_step(Bl, 1, 1)
             graph_ms = timed(lambda: model.train_step_graphed(xd, yd), steps)
-            loss_g = float(model._graph_loss)
-            if not np.isfinite(loss_g):
+            if not np.isfinite(float(model._graph_loss)):
                 graph_err = "non-finite loss from the captured step"
         except Exception as exc:  # noqa: BLE001 -- an optional extra must not take the headline down
-            graph_err = str(exc)[:200]
+            graph_ms, graph_err = None, str(exc)[:200]
     peak, _ = load_peaks()
     fused = model._fused_draws_plan() is not None
     return {"workload": "Bayesian NFN 5 radial flows, 1-D y, hidden (10,) tanh, S=32 draws folded, %d samples per GPU "

@@ -335,6 +335,20 @@ int nfn_dense_chain_forward_backward_draws_x(const nfn_chain_desc* desc, int hid
                                              float* dW, float* dbias, double* logp_sum, const nfn_event_xform* xf,
                                              void* stream);
 /*
+ * Weight-space arithmetic of one tfp.layers.DenseVariational layer with the reference's mean-field posterior and
+ * normal prior (estimators/DistributionLayers.py:17-71, BayesianNNEstimator.py:78-118), one launch each way instead
+ * of ~40 elementwise launches: params [2 n] = (loc | raw scale), sigma = 1e-3 + softplus(log(e - 1) + 0.05 raw).
+ *   nfn_variational_sample           w [draws, n] = loc + sigma * eps[draws, n];  *kl += KL(q || N(prior_loc, prior_scale))
+ *                                    (kl device double, nullable)
+ *   nfn_variational_sample_backward  dparams [2 n] += d/dparams of (sum dw . w + g_kl * KL), dprior_loc [n] += likewise
+ *                                    (nullable: fixed prior); dw nullable (KL only), g_kl device float (nullable = 0)
+ */
+int nfn_variational_sample(const float* params, const float* prior_loc, float prior_scale, const float* eps, int n,
+                           int draws, float* w, double* kl, void* stream);
+int nfn_variational_sample_backward(const float* params, const float* prior_loc, float prior_scale, const float* eps,
+                                    const float* dw, const float* g_kl, int n, int draws, float* dparams,
+                                    float* dprior_loc, void* stream);
+/*
  * The emitting Dense(P) layer fused into the MDN head: replaces `Dense(output_size, "linear")`
  * (MaximumLikelihoodNNEstimator.py:43) + GaussianMixtureLayer's log_prob (DistributionLayers.py:196-212) + their
  * tape gradients, P = n_centers * (2 n_dims + 1).  Same contract as nfn_dense_chain_*_x: t = h W + bias is formed

@@ -148,6 +148,11 @@ SIGNATURES = {
                                                  _c_float_p, ctypes.c_float, _c_float_p, _c_float_p,
                                                  _c_float_p, ctypes.c_void_p, _c_float_p, _i64, _xf_p,
                                                  ctypes.c_void_p]),
+    "nfn_variational_sample": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_float, _c_float_p, ctypes.c_int,
+                                             ctypes.c_int, _c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "nfn_variational_sample_backward": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_float, _c_float_p, _c_float_p,
+                                                      _c_float_p, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p,
+                                                      ctypes.c_void_p]),
     "nfn_dense_act_forward_draws": (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, _i64,
                                                   ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p,
                                                   ctypes.c_void_p]),

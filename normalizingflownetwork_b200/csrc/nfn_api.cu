@@ -652,6 +652,27 @@ int nfn_dense_act_backward_draws(const float* x, const float* x_mean, const floa
                                 units, out_width, act, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------ mean-field weight posterior (Bayesian estimators)
+int nfn_variational_sample(const float* params, const float* prior_loc, float prior_scale, const float* eps, int n,
+                           int draws, float* w, double* kl, void* stream) {
+  if (n < 1 || draws < 1) return set_error(NFN_ERR_SHAPE, "n=%d draws=%d", n, draws);
+  if (!(prior_scale > 0.0f)) return set_error(NFN_ERR_DESC, "prior_scale must be positive");
+  if (!params || !prior_loc || !eps || !w) return set_error(NFN_ERR_NULL, "params, prior_loc, eps and w must be non-NULL");
+  return launch_variational(false, params, prior_loc, prior_scale, eps, nullptr, nullptr, n, draws, w, kl, nullptr, nullptr,
+                            (cudaStream_t)stream);
+}
+
+int nfn_variational_sample_backward(const float* params, const float* prior_loc, float prior_scale, const float* eps,
+                                    const float* dw, const float* g_kl, int n, int draws, float* dparams,
+                                    float* dprior_loc, void* stream) {
+  if (n < 1 || draws < 1) return set_error(NFN_ERR_SHAPE, "n=%d draws=%d", n, draws);
+  if (!(prior_scale > 0.0f)) return set_error(NFN_ERR_DESC, "prior_scale must be positive");
+  if (!params || !prior_loc || !dparams) return set_error(NFN_ERR_NULL, "params, prior_loc and dparams must be non-NULL");
+  if (dw && !eps) return set_error(NFN_ERR_NULL, "eps must accompany dw");
+  return launch_variational(true, params, prior_loc, prior_scale, eps, dw, g_kl, n, draws, nullptr, nullptr, dparams,
+                            dprior_loc, (cudaStream_t)stream);
+}
+
 int64_t nfn_jit_dense_tc5_compile_check(const nfn_chain_desc* desc, int hidden, int accurate) {
   int rc = check_desc(desc);
   if (rc != NFN_OK) return rc;

@@ -433,4 +433,9 @@ int launch_dense_act_draws(bool bwd, const float* x, const float* xmean, const f
                            const float* out_in, const float* dout, float* out, float* dw, int S, long long Bd, int K, int N,
                            int NP, int act, cudaStream_t st);
 
+// mean-field weight posterior: S samples + exact KL, and their gradient (nfn_variational.cu)
+int launch_variational(bool bwd, const float* params, const float* prior_loc, float prior_scale, const float* eps,
+                       const float* dw, const float* gkl, int n, int S, float* w, double* kl, float* dparams,
+                       float* dprior_loc, cudaStream_t st);
+
 }  // namespace nfn

@@ -338,11 +338,13 @@ class BaseEstimator(torch.nn.Module):
         return loss.reshape(())
 
     # ------------------------------------------------------------------ CUDA-graph train step
-    def capture_train_step(self, batch_size, x_dim, y_dim):
+    def capture_train_step(self, batch_size, x_dim, y_dim, global_batch=None):
         """Capture one whole optimiser step (MLP forward, fused head kernel, MLP backward, Adam)
         into a CUDA graph for mini-batches of exactly ``batch_size`` rows.  Small batches are
         launch-latency-bound (config 1: 2048 rows = 197 KB of head traffic); replaying one graph
-        removes ~30 separate launches per step.  Single-process only."""
+        removes ~30 separate launches per step.  Single-process only: a captured step that contains the
+        data-parallel all-reduce of the flat gradient buffer did not complete on 2 GPUs (measured: the replay
+        never returned), so data-parallel training stays eager."""
         assert self.optimizer is not None, "call fit() once (or _ensure_optimizer) before capturing"
         assert not (dist.is_initialized() and dist.get_world_size() > 1), "graph capture is single-GPU"
         for g in self.optimizer.param_groups:
@@ -362,13 +364,13 @@ class BaseEstimator(torch.nn.Module):
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(3):  # warm-up outside capture: kernel attributes, JIT, allocator pools
-                self.train_step(self._gx, self._gy)
+                self.train_step(self._gx, self._gy, global_batch=global_batch)
         torch.cuda.current_stream(self.device).wait_stream(side)
         self._graph = torch.cuda.CUDAGraph()
         for gen in self._graph_generators():   # private torch generators drawn from inside the step
             self._graph.register_generator_state(gen)
         with torch.cuda.graph(self._graph):
-            self._graph_loss = self.train_step(self._gx, self._gy)
+            self._graph_loss = self.train_step(self._gx, self._gy, global_batch=global_batch)
         # the warm-up and capture steps ran on zeros: restore the real state
         self.load_state_dict(saved_model)
         with torch.no_grad():
@@ -384,6 +386,13 @@ class BaseEstimator(torch.nn.Module):
         # the head kernels take the normalisation statistics BY VALUE: a captured step is tied to them
         self._graph_stats_version = getattr(self, "_stats_version", 0)
         return self
+
+    def _make_adam(self):
+        """Adam as the reference configures it (tf.compat.v2.optimizers.Adam, epsilon 1e-7); on the GPU the fused
+        multi-tensor implementation: the whole update is one launch instead of ~10."""
+        params = [p for p in self.parameters()]
+        fused = bool(params) and all(p.is_cuda for p in params)
+        return torch.optim.Adam(params, lr=self.learning_rate, eps=1e-7, fused=fused)
 
     def _graph_generators(self):
         """torch.Generator objects the training step draws from (they must be registered with a capturing graph)."""

@@ -204,15 +204,46 @@ class BayesianNNEstimator(BaseEstimator):
             return None
         return l1, l2, hp, name
 
-    def _draw_weights(self, layer, S):
+    def _draw_weights(self, layer, S, with_kl=True):
         """w [S, size] = loc + scale * eps (the same draws, in the same order, as DenseVariational.forward), and the
         layer's KL term left in ``last_kl``."""
+        if layer.kl_use_exact and layer.posterior_params.is_cuda and with_kl:
+            # one kernel each way for the sample and the exact KL (csrc/nfn_variational.cu)
+            n = layer.prior_loc.numel()
+            eps = torch.randn((S, n), device=layer.posterior_params.device, generator=self._weight_generator())
+            w, kl = F.variational_sample(layer.posterior_params, layer.prior_loc, eps, layer.prior_scale)
+            layer.last_kl = layer.kl_weight * kl
+            return w
         q, r = layer._dists()
         loc, scale = q.base_dist.loc, q.base_dist.scale
         w = loc + scale * torch.randn((S,) + tuple(loc.shape), device=loc.device, generator=self._weight_generator())
-        layer.last_kl = layer.kl_weight * (layer._kl(q, r, None) if layer.kl_use_exact
-                                           else (q.log_prob(w) - r.log_prob(w)).mean())
+        if with_kl:
+            layer.last_kl = layer.kl_weight * (layer._kl(q, r, None) if layer.kl_use_exact
+                                               else (q.log_prob(w) - r.log_prob(w)).mean())
         return w
+
+    def _emitting_operands(self, l2, w2, hp):
+        """The emitting layer's per-draw sample as the fused head's operands: W [S, hp, P] (rows past the layer's
+        inputs zero, matching the zero columns of the padded hidden rows) and bias [S, P]."""
+        S = w2.shape[0]
+        P = self.dist_layer.get_total_param_size()
+        nk = l2.in_features * P
+        W2 = torch.zeros((S, hp, P), dtype=torch.float32, device=self.device)
+        W2[:, :l2.in_features, :] = w2[:, :nk].view(S, l2.in_features, P)
+        return W2, w2[:, nk:].contiguous()
+
+    def _fused_draws_log_prob(self, plan, x, y, S, xform):
+        """log p(y_b | x_b, w_s) for S fresh weight draws, [S, B]: two kernels (first layer over the folded rows,
+        emitting layer + flow chain), no parameter tensor in HBM."""
+        l1, l2, hp, act = plan
+        layer = self.dist_layer
+        with torch.no_grad():
+            w1, w2 = self._draw_weights(l1, S), self._draw_weights(l2, S)   # (also leaves the layers' KL terms behind, like a forward pass)
+            h = F.dense_act_forward_draws(x, w1, l1.units, act, hp, x_mean=self.x_mean, x_std=self.x_std)
+            W2, b2 = self._emitting_operands(l2, w2, hp)
+            logp = F.dense_chain_forward_draws(h, W2, b2, y, layer._flow_types, layer._n_dims,
+                                               layer._trainable_base_dist, xform=xform)
+        return logp.view(S, x.shape[0])
 
     def _fused_draws_forward_backward(self, plan, xb, y, S, g_scale, logp_sum, xform):
         """x [B, in], raw y [B, d] -> per-draw weight samples (autograd leaves' children) and their gradients.
@@ -226,9 +257,7 @@ class BayesianNNEstimator(BaseEstimator):
         with torch.no_grad():
             h = F.dense_act_forward_draws(x, w1, l1.units, act, hp, x_mean=self.x_mean, x_std=self.x_std)
             nk = l2.in_features * P
-            W2 = torch.zeros((S, hp, P), dtype=torch.float32, device=self.device)
-            W2[:, :l2.in_features, :] = w2[:, :nk].view(S, l2.in_features, P)
-            b2 = w2[:, nk:].contiguous()
+            W2, b2 = self._emitting_operands(l2, w2, hp)
             _, dh, dW2, db2 = F.dense_chain_forward_backward_draws(
                 h, W2, b2, y, layer._flow_types, layer._n_dims, layer._trainable_base_dist, g_scale=g_scale,
                 logp_sum=logp_sum, xform=xform)
@@ -292,7 +321,7 @@ class BayesianNNEstimator(BaseEstimator):
         with torch.no_grad():
             self.params_from_x(np.asarray(x)[:2])
         if self.optimizer is None:
-            self.optimizer = torch.optim.Adam(self.parameters(), lr=self.learning_rate, eps=1e-7)
+            self.optimizer = self._make_adam()
         return super().fit(x, y, batch_size=batch_size, epochs=epochs, verbose=verbose, **kwargs)
 
     def log_posterior_predictive(self, x_data, y_data, posterior_draws=None, max_rows=1 << 22):
@@ -304,9 +333,15 @@ class BayesianNNEstimator(BaseEstimator):
         chunk = max(1, max_rows // S)
         out = torch.empty(B, dtype=torch.float32, device=self.device)
         self.train(False)
+        plan = self._fused_draws_plan() if S > 1 else None
         with torch.no_grad():
             for lo in range(0, B, chunk):
                 hi = min(B, lo + chunk)
+                if plan is not None:
+                    logp = self._fused_draws_log_prob(plan, x[lo:hi].contiguous(), y[lo:hi].contiguous(), S,
+                                                      self._xform(y.shape[1]))
+                    out[lo:hi] = F.logmeanexp_draws(logp)
+                    continue
                 t = self.params_from_x_draws(x[lo:hi], S)
                 yy = y[lo:hi].repeat(S, 1)
                 logp = self.dist_layer(t).log_prob_x(yy, self._xform(yy.shape[1]))

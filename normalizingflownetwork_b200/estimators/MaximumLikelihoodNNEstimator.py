@@ -81,7 +81,7 @@ class MaximumLikelihoodNNEstimator(BaseEstimator):
     def _ensure_optimizer(self):
         if self.optimizer is None:
             # Keras Adam defaults (epsilon 1e-7)
-            self.optimizer = torch.optim.Adam(self.parameters(), lr=self.learning_rate, eps=1e-7)
+            self.optimizer = self._make_adam()
 
     def fit(self, x, y, batch_size=None, epochs=None, verbose=1, **kwargs):
         import numpy as np

@@ -336,6 +336,50 @@ def dense_chain_forward_backward(h, W, bias, y, flow_types, n_dims, trainable_ba
     return logp, dh, dW, dbias
 
 
+# ----------------------------------------------------------------------------- mean-field weight posterior
+class _VariationalSample(torch.autograd.Function):
+    """(w [S, n], KL) of one DenseVariational layer from its flat posterior parameters: one kernel each way
+    (csrc/nfn_variational.cu) instead of ~40 torch launches; reference DistributionLayers.py:17-71."""
+
+    @staticmethod
+    def forward(ctx, params, prior_loc, eps, prior_scale):
+        lib = _lib.load()
+        S, n = eps.shape
+        dev = params.device
+        p, pl, e = params.detach().contiguous(), prior_loc.detach().contiguous(), eps.contiguous()
+        w = torch.empty((S, n), dtype=torch.float32, device=dev)
+        kl = torch.zeros(1, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.nfn_variational_sample(_lib.ptr(p), _lib.ptr(pl), ctypes.c_float(prior_scale), _lib.ptr(e), n, S,
+                                                  _lib.ptr(w), _lib.ptr(kl), _lib.current_stream(dev)))
+        ctx.save_for_backward(p, pl, e)
+        ctx.prior_scale = prior_scale
+        ctx.need_prior = prior_loc.requires_grad
+        return w, kl.to(torch.float32).reshape(())
+
+    @staticmethod
+    def backward(ctx, dw, dkl):
+        lib = _lib.load()
+        p, pl, e = ctx.saved_tensors
+        S, n = e.shape
+        dev = p.device
+        dparams = torch.zeros_like(p)
+        dprior = torch.zeros_like(pl) if ctx.need_prior else None
+        dwc = dw.contiguous() if dw is not None else None
+        g = dkl.to(torch.float32).reshape(1).contiguous() if dkl is not None else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.nfn_variational_sample_backward(
+                _lib.ptr(p), _lib.ptr(pl), ctypes.c_float(ctx.prior_scale), _lib.ptr(e), _lib.ptr(dwc), _lib.ptr(g), n, S,
+                _lib.ptr(dparams), _lib.ptr(dprior), _lib.current_stream(dev)))
+        return dparams, dprior, None, None
+
+
+def variational_sample(posterior_params, prior_loc, eps, prior_scale):
+    """w [S, n] = loc + (1e-3 + softplus(c0 + 0.05 raw)) * eps and the exact KL(q || N(prior_loc, prior_scale)) as a
+    float32 scalar, differentiable with respect to ``posterior_params`` [2 n] (and ``prior_loc`` [n] if it is trained)."""
+    return _VariationalSample.apply(posterior_params, prior_loc, eps, float(prior_scale))
+
+
 # ----------------------------------------------------------------------------- folded posterior draws
 def dense_act_draws_supported(in_features, units, out_width, activation):
     return (1 <= in_features <= 8 and 1 <= units <= 64 and out_width >= units and out_width % 8 == 0 and out_width <= 64

@@ -125,3 +125,32 @@ def test_bayesian_train_step_replays_as_a_cuda_graph(cuda_device, nfn_lib):
     assert len(set(round(v, 6) for v in losses[:5])) > 1          # the replays are not one frozen draw
     assert np.mean(losses[-10:]) < np.mean(losses[:10])
     assert any(float((p - q).abs().max()) > 0 for p, q in zip(m.parameters(), before))
+
+
+@pytest.mark.parametrize("trainable_prior", [False, True])
+def test_variational_sample_matches_torch_distributions(cuda_device, nfn_lib, trainable_prior):
+    """w = loc + sigma * eps and the exact Normal-Normal KL in one kernel each way against the composed torch version
+    (MeanFieldLayer + torch.distributions.kl_divergence), values and gradients."""
+    from normalizingflownetwork_b200 import functional as F
+    from normalizingflownetwork_b200.DistributionLayers import MeanFieldLayer
+
+    n, S, ps = 187, 32, 0.7
+    g = torch.Generator(device=cuda_device).manual_seed(4)
+    params = (torch.randn(2 * n, generator=g, device=cuda_device) * 2.0).requires_grad_(True)
+    prior = (torch.randn(n, generator=g, device=cuda_device) * 0.3).requires_grad_(trainable_prior)
+    eps = torch.randn((S, n), generator=g, device=cuda_device)
+    up = torch.randn((S, n), generator=g, device=cuda_device)
+    w, kl = F.variational_sample(params, prior, eps, ps)
+    (w * up).sum().add(0.37 * kl).backward()
+    got = (w.detach().clone(), float(kl), params.grad.clone(), prior.grad.clone() if trainable_prior else None)
+    p2 = params.detach().double().requires_grad_(True)
+    pr2 = prior.detach().double().requires_grad_(trainable_prior)
+    q, r = MeanFieldLayer(n, scale=None)(p2), MeanFieldLayer(n, scale=ps)(pr2)
+    w_ref = q.base_dist.loc + q.base_dist.scale * eps.double()
+    kl_ref = torch.distributions.kl_divergence(q, r)
+    (w_ref * up.double()).sum().add(0.37 * kl_ref).backward()
+    assert torch.allclose(got[0].double(), w_ref, rtol=1e-5, atol=1e-6)
+    assert got[1] == pytest.approx(float(kl_ref), rel=1e-5)
+    assert float((got[2].double() - p2.grad).abs().max()) <= 1e-4 * float(p2.grad.abs().max())
+    if trainable_prior:
+        assert float((got[3].double() - pr2.grad).abs().max()) <= 1e-4 * max(1e-6, float(pr2.grad.abs().max()))

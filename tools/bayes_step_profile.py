@@ -17,7 +17,7 @@ model = BayesNormalizingFlowNetwork(1, kl_weight_scale=1.0 / Bl, n_flows=5, hidd
 model._assign_data_normalization(x.numpy(), y.numpy())
 with torch.no_grad():
     model.params_from_x(x[:2].numpy())
-model.optimizer = torch.optim.Adam(model.parameters(), lr=model.learning_rate, eps=1e-7)
+model.optimizer = model._make_adam()
 xd, yd = model._to_dev(x), model._to_dev(y)
 for _ in range(5):
     model.train_step(xd, yd)
