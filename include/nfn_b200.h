@@ -364,6 +364,16 @@ int nfn_dense_mdn_forward_backward_x(int n_centers, int n_dims, int hidden, cons
                                      const float* bias, const float* y, int64_t y_rows, const float* g_logp,
                                      float g_scale, float* logp, float* dh, float* dW, float* dbias, double* logp_sum,
                                      int64_t B, const nfn_event_xform* xf, void* stream);
+/* ... with S folded weight draws (per-draw W [draws, hidden, P], bias [draws, P]; see nfn_dense_chain_*_draws_x):
+ * the Bayesian mixture density network's Monte-Carlo loop (BayesMixtureDensityNetwork, BayesianNNEstimator.py:65-76) */
+int nfn_dense_mdn_forward_draws_x(int n_centers, int n_dims, int hidden, int draws, int64_t rows_per_draw, const float* h,
+                                  const float* W, const float* bias, const float* y, int64_t y_rows, float* logp,
+                                  const nfn_event_xform* xf, void* stream);
+int nfn_dense_mdn_forward_backward_draws_x(int n_centers, int n_dims, int hidden, int draws, int64_t rows_per_draw,
+                                           const float* h, const float* W, const float* bias, const float* y,
+                                           int64_t y_rows, const float* g_logp, float g_scale, float* logp, float* dh,
+                                           float* dW, float* dbias, double* logp_sum, const nfn_event_xform* xf,
+                                           void* stream);
 /* bytes of the NVRTC-built cubin for this mixture / hidden width (>= 0), or a negative nfn_status */
 int64_t nfn_jit_dense_mdn_compile_check(int n_centers, int n_dims, int hidden, int accurate);
 int nfn_kmn_forward_x(int n_components, int n_dims, const float* t, const float* y, int64_t y_rows,

@@ -84,6 +84,7 @@ static void init_options() {
   g_opt[kOptHostChunkMb] = (int)mb;
   g_opt[kOptTuneWnb] = getenv("NFN_B200_TUNE_WNB") ? atoi(getenv("NFN_B200_TUNE_WNB")) : 0;
   g_opt[kOptTuneWwarps] = getenv("NFN_B200_TUNE_WWARPS") ? atoi(getenv("NFN_B200_TUNE_WWARPS")) : 0;
+  g_opt[kOptMlpMma] = env_is("NFN_B200_MLP_MMA", "0") ? 0 : 1;
 }
 
 int option(Opt o) {
@@ -92,7 +93,8 @@ int option(Opt o) {
 }
 
 static const char* const kOptNames[kOptCount] = {"math", "force_generic", "force_jit", "jit", "chain_io",
-                                                 "dense_mma", "pdl", "debug", "host_chunk_mb", "tune_wnb", "tune_wwarps"};
+                                                 "dense_mma", "pdl", "debug", "host_chunk_mb", "tune_wnb", "tune_wwarps",
+                                                 "mlp_mma"};
 
 int math_mode() { return option(kOptMath); }
 int chain_io_override() { return option(kOptChainIo); }
@@ -867,6 +869,43 @@ int nfn_dense_mdn_forward_backward_x(int n_centers, int n_dims, int hidden, cons
   a.h = h; a.W = W; a.bias = bias; a.y = y; a.g_logp = g_logp; a.logp = logp; a.dh = dh; a.dW = dW;
   a.dbias = dbias; a.logp_sum = logp_sum; a.B = B; a.g_scale = g_scale;
   a.y_broadcast = (y_rows == 1 && B != 1);
+  if ((rc = set_xform(a.xf, xf, n_dims)) != NFN_OK) return rc;
+  return dense_mdn_dispatch(n_centers, n_dims, hidden, a, true, (cudaStream_t)stream);
+}
+
+int nfn_dense_mdn_forward_draws_x(int n_centers, int n_dims, int hidden, int draws, int64_t rows_per_draw, const float* h,
+                                  const float* W, const float* bias, const float* y, int64_t y_rows, float* logp,
+                                  const nfn_event_xform* xf, void* stream) {
+  int rc = draws_common(draws, rows_per_draw, y_rows);
+  if (rc != NFN_OK) return rc;
+  const int64_t B = (int64_t)draws * rows_per_draw;
+  rc = dense_mdn_common(n_centers, n_dims, hidden, h, W, bias, y, 1, logp, B);
+  if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
+  DenseArgs a{};
+  a.h = h; a.W = W; a.bias = bias; a.y = y; a.logp = logp; a.B = B; a.g_scale = 1.0f;
+  a.y_broadcast = (y_rows == 1 && rows_per_draw != 1);
+  a.draws = draws; a.rows_per_draw = rows_per_draw;
+  if ((rc = set_xform(a.xf, xf, n_dims)) != NFN_OK) return rc;
+  return dense_mdn_dispatch(n_centers, n_dims, hidden, a, false, (cudaStream_t)stream);
+}
+
+int nfn_dense_mdn_forward_backward_draws_x(int n_centers, int n_dims, int hidden, int draws, int64_t rows_per_draw,
+                                           const float* h, const float* W, const float* bias, const float* y,
+                                           int64_t y_rows, const float* g_logp, float g_scale, float* logp, float* dh,
+                                           float* dW, float* dbias, double* logp_sum, const nfn_event_xform* xf,
+                                           void* stream) {
+  int rc = draws_common(draws, rows_per_draw, y_rows);
+  if (rc != NFN_OK) return rc;
+  const int64_t B = (int64_t)draws * rows_per_draw;
+  rc = dense_mdn_common(n_centers, n_dims, hidden, h, W, bias, y, 1, logp, B);
+  if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
+  if (!dh || !dW || !dbias) return set_error(NFN_ERR_NULL, "dh, dW and dbias must be non-NULL");
+  if (!aligned(dh, 16)) return set_error(NFN_ERR_ALIGN, "dh must be 16-byte aligned");
+  DenseArgs a{};
+  a.h = h; a.W = W; a.bias = bias; a.y = y; a.g_logp = g_logp; a.logp = logp; a.dh = dh; a.dW = dW;
+  a.dbias = dbias; a.logp_sum = logp_sum; a.B = B; a.g_scale = g_scale;
+  a.y_broadcast = (y_rows == 1 && rows_per_draw != 1);
+  a.draws = draws; a.rows_per_draw = rows_per_draw;
   if ((rc = set_xform(a.xf, xf, n_dims)) != NFN_OK) return rc;
   return dense_mdn_dispatch(n_centers, n_dims, hidden, a, true, (cudaStream_t)stream);
 }

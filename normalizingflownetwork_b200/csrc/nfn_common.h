@@ -42,6 +42,7 @@ enum Opt {
   kOptHostChunkMb,   // NFN_B200_HOST_CHUNK_MB
   kOptTuneWnb,       // warp-tile kernels through the runtime specialiser: tile buffers per warp (0: default)
   kOptTuneWwarps,    // ... and warps per SM (0: default)                                     A/B sweeps only
+  kOptMlpMma,        // hidden layers' backward on the tensor cores (default 1)               NFN_B200_MLP_MMA=0
   kOptCount
 };
 int option(Opt o);

@@ -296,6 +296,162 @@ __global__ void __launch_bounds__(kT, 4) dense_act_bwd(const float* __restrict__
   }
 }
 
+// ---------------------------------------------------------------- backward on the tensor cores (hidden layers)
+// The 16/32-wide hidden layers' backward is two small GEMMs per row tile -- dx = dpre W (contraction over the
+// units) and dW += dpre^T x (contraction over the tile's ROWS) -- which the kernel above does with 2 x K x N scalar
+// FMAs per row (46 M warp instructions at B = 2^20, 16 -> 16: 3x off its memory floor, issue-bound).  Here both run
+// as warp-level mma.sync.m16n8k8 TF32 with the error-compensated split of nfn_dense_chain.cuh (3 products, fp32-grade):
+// every warp owns 32 rows of the tile, the W fragments of dx are split once per kernel and live in registers, the
+// dW accumulators stay in registers over ALL tiles of the CTA (N K / 32 per thread) and meet in shared memory once.
+template <int N, int K, int ACT>
+__global__ void __launch_bounds__(kT, 4) dense_act_bwd_mma(const float* __restrict__ x, const float* __restrict__ out,
+                                                          const float* __restrict__ dout, const float* __restrict__ weight,
+                                                          float* __restrict__ dx, float* __restrict__ dW,
+                                                          float* __restrict__ db, long long B) {
+  static_assert(N % 16 == 0 && K % 8 == 0 && N * K <= 512, "tile shape");
+  constexpr int SX = K + 4, SD = N + 4, SO = (N > K ? N : K) + 4, KS = w_stride(K);
+  constexpr int N4 = N / 4;
+  constexpr int MT = N / 16;       // dW: m-tiles over the units
+  constexpr int NK = K / 8;        // dW / dx: n-tiles over the inputs
+  constexpr int KN = N / 8;        // dx: k-steps over the units
+  extern __shared__ __align__(16) float smem[];
+  float* sW = smem;                // [N][KS]
+  float* sX = sW + N * KS;         // [kT][SX]
+  float* sD = sX + kT * SX;        // [kT][SD]   dout, then dpre
+  float* sO = sD + kT * SD;        // [kT][SO]   out, then dx
+  for (int i = threadIdx.x; i < N * K; i += kT) sW[(i / K) * KS + i % K] = __ldg(weight + i);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+  const int R0 = warp * 32;
+  __syncthreads();
+  // B fragments of dx = dpre W: (k = unit 8 ks + tig [+4], n = input 8 nt + g), split once
+  unsigned wh[KN][NK][2], wl[KN][NK][2];
+#pragma unroll
+  for (int ks = 0; ks < KN; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < NK; ++nt) {
+      split_tf32(sW[(8 * ks + tig) * KS + 8 * nt + g], wh[ks][nt][0], wl[ks][nt][0]);
+      split_tf32(sW[(8 * ks + tig + 4) * KS + 8 * nt + g], wh[ks][nt][1], wl[ks][nt][1]);
+    }
+  float cw[MT][NK][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NK; ++nt) cw[mt][nt][0] = cw[mt][nt][1] = cw[mt][nt][2] = cw[mt][nt][3] = 0.0f;
+  float gb[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) gb[n] = 0.0f;
+
+  const long long ntiles = (B + kT - 1) / kT;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * kT;
+    tile_copy<true>(sX, SX, const_cast<float*>(x), row0, B, K);
+    tile_copy<true>(sD, SD, const_cast<float*>(dout), row0, B, N);
+    tile_copy<true>(sO, SO, const_cast<float*>(out), row0, B, N);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    {  // dpre for this thread's row, in place over dout (rows past B are zero: dpre = 0)
+      float4* myd = reinterpret_cast<float4*>(sD + threadIdx.x * SD);
+      const float4* myo = reinterpret_cast<const float4*>(sO + threadIdx.x * SO);
+#pragma unroll
+      for (int c = 0; c < N4; ++c) {
+        const float4 d = myd[c], o = myo[c];
+        const float4 p = make_float4(d.x * act_bwd<ACT>(o.x), d.y * act_bwd<ACT>(o.y), d.z * act_bwd<ACT>(o.z),
+                                     d.w * act_bwd<ACT>(o.w));
+        myd[c] = p;
+        gb[4 * c] += p.x; gb[4 * c + 1] += p.y; gb[4 * c + 2] += p.z; gb[4 * c + 3] += p.w;
+      }
+    }
+    __syncwarp();
+    // ---- dx[32 rows of this warp][K] = dpre W, written over the (consumed) out rows
+#pragma unroll
+    for (int m2 = 0; m2 < 2; ++m2) {
+      const int r0 = R0 + 16 * m2;
+      unsigned ah[KN][4], al[KN][4];
+#pragma unroll
+      for (int ks = 0; ks < KN; ++ks) {
+        split_tf32(sD[(r0 + g) * SD + 8 * ks + tig], ah[ks][0], al[ks][0]);
+        split_tf32(sD[(r0 + g + 8) * SD + 8 * ks + tig], ah[ks][1], al[ks][1]);
+        split_tf32(sD[(r0 + g) * SD + 8 * ks + tig + 4], ah[ks][2], al[ks][2]);
+        split_tf32(sD[(r0 + g + 8) * SD + 8 * ks + tig + 4], ah[ks][3], al[ks][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NK; ++nt) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < KN; ++ks) mma_tf32(c, al[ks], wh[ks][nt]);
+#pragma unroll
+        for (int ks = 0; ks < KN; ++ks) mma_tf32(c, ah[ks], wl[ks][nt]);
+#pragma unroll
+        for (int ks = 0; ks < KN; ++ks) mma_tf32(c, ah[ks], wh[ks][nt]);
+        *reinterpret_cast<float2*>(sO + (r0 + g) * SO + 8 * nt + 2 * tig) = make_float2(c[0], c[1]);
+        *reinterpret_cast<float2*>(sO + (r0 + g + 8) * SO + 8 * nt + 2 * tig) = make_float2(c[2], c[3]);
+      }
+    }
+    // ---- dW[N][K] += dpre^T x over this warp's 32 rows (4 k-steps of 8 rows)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      unsigned ah[MT][4], al[MT][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const float* dp = sD + (R0 + 8 * ks + tig) * SD + 16 * mt + g;
+        split_tf32(dp[0], ah[mt][0], al[mt][0]);
+        split_tf32(dp[8], ah[mt][1], al[mt][1]);
+        split_tf32(dp[4 * SD], ah[mt][2], al[mt][2]);
+        split_tf32(dp[4 * SD + 8], ah[mt][3], al[mt][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NK; ++nt) {
+        unsigned bh[2], bl[2];
+        split_tf32(sX[(R0 + 8 * ks + tig) * SX + 8 * nt + g], bh[0], bl[0]);
+        split_tf32(sX[(R0 + 8 * ks + tig + 4) * SX + 8 * nt + g], bh[1], bl[1]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_tf32(cw[mt][nt], al[mt], bh);
+          mma_tf32(cw[mt][nt], ah[mt], bl);
+          mma_tf32(cw[mt][nt], ah[mt], bh);
+        }
+      }
+    }
+    __syncthreads();   // every warp's dx rows are in sO
+    tile_copy<false>(sO, SO, dx, row0, B, K);
+    __syncthreads();   // ... and stored before the next tile's copies land
+  }
+  // ---- the warps' dW fragments and bias sums meet in shared memory: one atomic per entry per CTA
+  float* sAcc = sX;    // [kT / 32][N * K] <= 4 * 1024 floats, inside sX | sD | sO (kT * (SX + SD + SO) >= 128 * 60)
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NK; ++nt) {
+      float* p0 = sAcc + warp * (N * K) + (16 * mt + g) * K + 8 * nt + 2 * tig;
+      p0[0] = cw[mt][nt][0]; p0[1] = cw[mt][nt][1];
+      p0[8 * K] = cw[mt][nt][2]; p0[8 * K + 1] = cw[mt][nt][3];
+    }
+  __syncthreads();
+  for (int o = threadIdx.x; o < N * K; o += kT) {
+    float v = 0.0f;
+#pragma unroll
+    for (int wi = 0; wi < kT / 32; ++wi) v += sAcc[wi * (N * K) + o];
+    atomicAdd(dW + o, v);
+  }
+  __syncthreads();
+  float* sRed = sX;    // [kT / 32][N]
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    float v = gb[n];
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+    if (lane == 0) sRed[warp * N + n] = v;
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += kT) {
+    float v = 0.0f;
+#pragma unroll
+    for (int wi = 0; wi < kT / 32; ++wi) v += sRed[wi * N + n];
+    atomicAdd(db + n, v);
+  }
+}
+
 // ---------------------------------------------------------------- backward, first layer
 // The first layer of the network has few inputs (the conditioning variable: K = 1 .. 4) and nobody wants its
 // input gradient: what is left is a streaming reduction -- dW[n][k] = sum_r dpre[r][n] x[r][k], db[n] =
@@ -420,6 +576,39 @@ cudaError_t launch_bwd(const float* x, const float* out, const float* dout, cons
   kern<<<(unsigned)grid, kT, smem, st>>>(x, out, dout, w, dx, dW, db, B, K);
   count_launch();
   return cudaGetLastError();
+}
+
+template <int N, int K, int ACT>
+cudaError_t launch_bwd_mma(const float* x, const float* out, const float* dout, const float* w, float* dx, float* dW, float* db,
+                           long long B, cudaStream_t st) {
+  const DeviceInfo& di = device_info();
+  constexpr int so = (N > K ? N : K) + 4;
+  constexpr size_t smem = (size_t)(N * w_stride(K) + kT * (K + 4) + kT * (N + 4) + kT * so) * sizeof(float);
+  auto kern = dense_act_bwd_mma<N, K, ACT>;
+  static thread_local int configured_for = -1;
+  if (configured_for != di.device) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured_for = di.device;
+  }
+  const long long ntiles = (B + kT - 1) / kT;
+  long long grid = (long long)di.sm_count * 4;
+  if (grid > ntiles) grid = ntiles;
+  kern<<<(unsigned)grid, kT, smem, st>>>(x, out, dout, w, dx, dW, db, B);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <int N, int K>
+cudaError_t dispatch_bwd_mma(int act, const float* x, const float* out, const float* dout, const float* w, float* dx,
+                             float* dW, float* db, long long B, cudaStream_t st) {
+  switch (act) {
+    case kLinear: return launch_bwd_mma<N, K, kLinear>(x, out, dout, w, dx, dW, db, B, st);
+    case kTanh: return launch_bwd_mma<N, K, kTanh>(x, out, dout, w, dx, dW, db, B, st);
+    case kRelu: return launch_bwd_mma<N, K, kRelu>(x, out, dout, w, dx, dW, db, B, st);
+    case kSigmoid: return launch_bwd_mma<N, K, kSigmoid>(x, out, dout, w, dx, dW, db, B, st);
+    default: return launch_bwd_mma<N, K, kElu>(x, out, dout, w, dx, dW, db, B, st);
+  }
 }
 
 template <int N>
@@ -610,6 +799,15 @@ int launch_dense_act_backward(const float* x, const float* xmean, const float* x
                               const float* w, float* dx, float* dW, float* db, long long B, int K, int N, int act,
                               cudaStream_t st) {
   cudaError_t e;
+  // hidden layers of the usual widths (input gradient wanted): both GEMMs on the tensor cores (NFN_B200_MLP_MMA=0: off)
+  // (32 x 32 keeps the scalar kernel: its 64 registers of split W fragments next to 32 accumulators spill)
+  if (option(kOptMlpMma) && dx != nullptr && xmean == nullptr && (K == 16 || K == 32) && (N == 16 || N == 32) &&
+      N * K <= 512) {
+    if (N == 16) e = K == 16 ? dispatch_bwd_mma<16, 16>(act, x, out, dout, w, dx, dW, db, B, st)
+                             : dispatch_bwd_mma<16, 32>(act, x, out, dout, w, dx, dW, db, B, st);
+    else e = dispatch_bwd_mma<32, 16>(act, x, out, dout, w, dx, dW, db, B, st);
+    return cuda_error(e, "dense_act_bwd_mma");
+  }
   // 4 x 4 blocks of the weight gradient per thread: one while ceil(K/4) * N/4 <= 128, else two (K * N <= 4096)
   const int G = ((K + 3) / 4) * (N / 4);
   if (G <= kT) {

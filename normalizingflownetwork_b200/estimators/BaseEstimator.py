@@ -143,7 +143,9 @@ class BaseEstimator(torch.nn.Module):
     def _emitting_kernel(self, lin):
         """The emitting layer's weight in the Keras kernel layout [H, P] the fused head reads (= weight.t()),
         transposed once per weight VERSION, not once per call (a scoring call would otherwise spend a launch on it)."""
-        key = (lin.weight.data_ptr(), lin.weight._version)
+        # (the optimiser epoch is part of the key: the fused multi-tensor Adam and a replayed CUDA graph both update
+        # the weights without touching torch's per-tensor version counter)
+        key = (lin.weight.data_ptr(), lin.weight._version, getattr(self, "_weights_epoch", 0))
         if getattr(self, "_wt_key", None) != key:
             self._wt = lin.weight.detach().t().contiguous()
             self._wt_key = key
@@ -332,6 +334,7 @@ class BaseEstimator(torch.nn.Module):
         if reducer is not None:
             logp_sum = self._reduce_step(reducer, logp_sum)
         self.optimizer.step()
+        self._weights_epoch = getattr(self, "_weights_epoch", 0) + 1
         loss = -logp_sum.to(torch.float32) / Bg
         if extra is not None:
             loss = loss + extra.detach()
@@ -403,6 +406,7 @@ class BaseEstimator(torch.nn.Module):
         self._gx.copy_(xb)
         self._gy.copy_(yb)
         self._graph.replay()
+        self._weights_epoch = getattr(self, "_weights_epoch", 0) + 1
         return self._graph_loss
 
     def capture_log_pdf(self, batch_size, x_dim, y_dim):
@@ -419,6 +423,7 @@ class BaseEstimator(torch.nn.Module):
                 self.log_pdf(self._sx, self._sy)
         torch.cuda.current_stream(self.device).wait_stream(side)
         self._score_graph = torch.cuda.CUDAGraph()
+        self._wt_key = None   # the emitting layer's transposed kernel is re-formed INSIDE the graph: replays see new weights
         with torch.cuda.graph(self._score_graph):
             self._score_out = self.log_pdf(self._sx, self._sy)
         self._score_stats_version = getattr(self, "_stats_version", 0)
@@ -466,6 +471,7 @@ class BaseEstimator(torch.nn.Module):
         if reducer is not None:
             logp_sum = self._reduce_step(reducer, logp_sum)
         self.optimizer.step()
+        self._weights_epoch = getattr(self, "_weights_epoch", 0) + 1
         loss = -logp_sum.to(torch.float32) / (denom or Bg)
         if extra is not None:
             loss = loss + extra.detach()

@@ -185,10 +185,12 @@ class BayesianNNEstimator(BaseEstimator):
 
     def _fused_draws_plan(self):
         """(first layer, emitting layer, padded hidden width) when the S-draw step can run on the folded-draw kernels:
-        one hidden DenseVariational layer of <= 64 units fed by <= 8 inputs, a flow-chain head, no x noise."""
-        from ..DistributionLayers import InverseNormalizingFlowLayer
+        one hidden DenseVariational layer of <= 64 units fed by <= 8 inputs, a flow-chain or MDN head, no x noise."""
+        from ..DistributionLayers import GaussianMixtureLayer, InverseNormalizingFlowLayer
 
-        if not self.fuse_draws or self.map_mode or not isinstance(self.dist_layer, InverseNormalizingFlowLayer):
+        if not self.fuse_draws or self.map_mode:
+            return None
+        if not isinstance(self.dist_layer, (InverseNormalizingFlowLayer, GaussianMixtureLayer)):
             return None
         dense = [l for l in self.net if isinstance(l, DenseVariational)]
         if len(dense) != 2 or dense[0].in_features is None or dense[1].in_features is None:
@@ -202,7 +204,21 @@ class BayesianNNEstimator(BaseEstimator):
             return None
         if not F.dense_chain_supported(hp) or self.dist_layer.get_total_param_size() < 1:
             return None
+        if isinstance(self.dist_layer, GaussianMixtureLayer) and not F.dense_mdn_supported(
+                hp, self.dist_layer._n_centers, self.dist_layer._n_dims):
+            return None
         return l1, l2, hp, name
+
+    def _head_draws(self, h, W2, b2, y, backward, **kw):
+        """The emitting layer + density head over the folded rows with per-draw weights, whichever head this is."""
+        from ..DistributionLayers import GaussianMixtureLayer
+
+        layer = self.dist_layer
+        if isinstance(layer, GaussianMixtureLayer):
+            fn = F.dense_mdn_forward_backward_draws if backward else F.dense_mdn_forward_draws
+            return fn(h, W2, b2, y, layer._n_centers, layer._n_dims, **kw)
+        fn = F.dense_chain_forward_backward_draws if backward else F.dense_chain_forward_draws
+        return fn(h, W2, b2, y, layer._flow_types, layer._n_dims, layer._trainable_base_dist, **kw)
 
     def _draw_weights(self, layer, S, with_kl=True):
         """w [S, size] = loc + scale * eps (the same draws, in the same order, as DenseVariational.forward), and the
@@ -241,8 +257,7 @@ class BayesianNNEstimator(BaseEstimator):
             w1, w2 = self._draw_weights(l1, S), self._draw_weights(l2, S)   # (also leaves the layers' KL terms behind, like a forward pass)
             h = F.dense_act_forward_draws(x, w1, l1.units, act, hp, x_mean=self.x_mean, x_std=self.x_std)
             W2, b2 = self._emitting_operands(l2, w2, hp)
-            logp = F.dense_chain_forward_draws(h, W2, b2, y, layer._flow_types, layer._n_dims,
-                                               layer._trainable_base_dist, xform=xform)
+            logp = self._head_draws(h, W2, b2, y, False, xform=xform)
         return logp.view(S, x.shape[0])
 
     def _fused_draws_forward_backward(self, plan, xb, y, S, g_scale, logp_sum, xform):
@@ -258,9 +273,7 @@ class BayesianNNEstimator(BaseEstimator):
             h = F.dense_act_forward_draws(x, w1, l1.units, act, hp, x_mean=self.x_mean, x_std=self.x_std)
             nk = l2.in_features * P
             W2, b2 = self._emitting_operands(l2, w2, hp)
-            _, dh, dW2, db2 = F.dense_chain_forward_backward_draws(
-                h, W2, b2, y, layer._flow_types, layer._n_dims, layer._trainable_base_dist, g_scale=g_scale,
-                logp_sum=logp_sum, xform=xform)
+            _, dh, dW2, db2 = self._head_draws(h, W2, b2, y, True, g_scale=g_scale, logp_sum=logp_sum, xform=xform)
             dw1 = F.dense_act_backward_draws(x, h, dh, S, l1.units, act, x_mean=self.x_mean, x_std=self.x_std)
             dw2 = torch.cat([dW2[:, :l2.in_features, :].reshape(S, nk), db2], dim=1)
         return (w1, w2), (dw1, dw2)
@@ -302,6 +315,7 @@ class BayesianNNEstimator(BaseEstimator):
         if reducer is not None:
             logp_sum = self._reduce_step(reducer, logp_sum)
         self.optimizer.step()
+        self._weights_epoch = getattr(self, "_weights_epoch", 0) + 1
         loss = -logp_sum.to(torch.float32) / (S * Bg) + extra.detach()
         return loss.reshape(())
 

@@ -479,6 +479,52 @@ def dense_chain_forward_backward_draws(h, W, bias, y, flow_types, n_dims, traina
     return logp, dh, dW, dbias
 
 
+def _draws_operands(h, W, bias, y, P, n_dims, what):
+    h = _aligned(_as_f32_cuda(h, "h"))
+    dev = h.device
+    W = _as_f32_cuda(W, "W", device=dev)
+    bias = _as_f32_cuda(bias, "bias", device=dev)
+    y = _aligned(_as_f32_cuda(y, "y", device=dev))
+    S, H = W.shape[0], W.shape[1]
+    assert tuple(W.shape) == (S, H, P) and tuple(bias.shape) == (S, P) and h.shape[1] == H and h.shape[0] % S == 0, what
+    Bd = h.shape[0] // S
+    if y.dim() != 2 or y.shape[1] != n_dims or y.shape[0] not in (Bd, 1):
+        raise ValueError("%s: y must be [rows_per_draw, n_dims] or one row" % what)
+    return h, W, bias, y, S, H, Bd, dev
+
+
+def dense_mdn_forward_draws(h, W, bias, y, n_centers, n_dims, xform=None):
+    """Fused emitting layer + MDN head with per-draw weights (see dense_chain_forward_draws).  Returns logp [S*B]."""
+    lib = _lib.load()
+    P = mdn_param_size(n_centers, n_dims)
+    h, W, bias, y, S, H, Bd, dev = _draws_operands(h, W, bias, y, P, n_dims, "dense_mdn_forward_draws")
+    logp = torch.empty(S * Bd, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_dense_mdn_forward_draws_x(n_centers, n_dims, H, S, Bd, _lib.ptr(h), _lib.ptr(W), _lib.ptr(bias),
+                                                     _lib.ptr(y), y.shape[0], _lib.ptr(logp), _xf(xform),
+                                                     _lib.current_stream(dev)))
+    return logp
+
+
+def dense_mdn_forward_backward_draws(h, W, bias, y, n_centers, n_dims, g_logp=None, g_scale=1.0, logp_sum=None,
+                                     xform=None):
+    """Forward + reverse sweep of the above.  Returns (logp [S*B], dh [S*B, H], dW [S, H, P], dbias [S, P])."""
+    lib = _lib.load()
+    P = mdn_param_size(n_centers, n_dims)
+    h, W, bias, y, S, H, Bd, dev = _draws_operands(h, W, bias, y, P, n_dims, "dense_mdn_forward_backward_draws")
+    logp = torch.empty(S * Bd, dtype=torch.float32, device=dev)
+    dh = torch.empty((S * Bd, H), dtype=torch.float32, device=dev)
+    dW = torch.zeros((S, H, P), dtype=torch.float32, device=dev)
+    dbias = torch.zeros((S, P), dtype=torch.float32, device=dev)
+    g_logp = _prep_g(g_logp, S * Bd, dev, "dense_mdn_forward_backward_draws")
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_dense_mdn_forward_backward_draws_x(
+            n_centers, n_dims, H, S, Bd, _lib.ptr(h), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(y), y.shape[0],
+            _lib.ptr(g_logp), ctypes.c_float(g_scale), _lib.ptr(logp), _lib.ptr(dh), _lib.ptr(dW), _lib.ptr(dbias),
+            _lib.ptr(logp_sum), _xf(xform), _lib.current_stream(dev)))
+    return logp, dh, dW, dbias
+
+
 class _ChainLogProb(torch.autograd.Function):
     @staticmethod
     def forward(ctx, t, y, flow_types, n_dims, trainable_base_dist):

@@ -74,18 +74,25 @@ def test_dense_chain_with_folded_draws_equals_one_launch_per_draw(cuda_device, n
 
 
 @pytest.mark.parametrize("noise", [0.0, 0.2])
-def test_bayesian_train_step_on_the_folded_draw_kernels(cuda_device, nfn_lib, noise):
-    """BayesNormalizingFlowNetwork with S = 8 folded draws: the fused step (3 kernels, no t / dt / repeated y) leaves the
+@pytest.mark.parametrize("head", ["nfn", "mdn"])
+def test_bayesian_train_step_on_the_folded_draw_kernels(cuda_device, nfn_lib, noise, head):
+    """Bayesian NFN / MDN with S = 8 folded draws: the fused step (3 kernels, no t / dt / repeated y) leaves the
     same loss and the same gradients as the composed one (batched GEMMs + the streaming head + autograd)."""
-    from normalizingflownetwork_b200.estimators import BayesNormalizingFlowNetwork
+    from normalizingflownetwork_b200.estimators import BayesMixtureDensityNetwork, BayesNormalizingFlowNetwork
 
     rng = np.random.default_rng(5)
     x = rng.uniform(-3, 3, (2000, 1)).astype(np.float32)
     y = (np.cos(x) + 0.3 * rng.normal(0, 1, (2000, 1))).astype(np.float32)
     out = []
     for fuse in (True, False):
-        m = BayesNormalizingFlowNetwork(1, kl_weight_scale=1.0 / 2000, n_flows=5, hidden_sizes=(10,), activation="tanh",
-                                        n_train_draws=8, learning_rate=1e-2, noise_reg=("fixed_rate", noise))
+        if head == "mdn":
+            m = BayesMixtureDensityNetwork(1, kl_weight_scale=1.0 / 2000, n_centers=5, hidden_sizes=(10,),
+                                           activation="tanh", n_train_draws=8, learning_rate=1e-2,
+                                           noise_reg=("fixed_rate", noise))
+        else:
+            m = BayesNormalizingFlowNetwork(1, kl_weight_scale=1.0 / 2000, n_flows=5, hidden_sizes=(10,),
+                                            activation="tanh", n_train_draws=8, learning_rate=1e-2,
+                                            noise_reg=("fixed_rate", noise))
         m.fuse_draws = fuse
         m._assign_data_normalization(x, y)
         with torch.no_grad():
