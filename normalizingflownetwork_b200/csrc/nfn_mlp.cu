@@ -710,7 +710,7 @@ __global__ void __launch_bounds__(kDrawT) dense_act_draws_fwd(const float* __res
 }
 
 template <int ACT>
-__global__ void __launch_bounds__(kDrawT) dense_act_draws_bwd(const float* __restrict__ x, const float* __restrict__ xmean,
+__global__ void __launch_bounds__(kDrawT, 2) dense_act_draws_bwd(const float* __restrict__ x, const float* __restrict__ xmean,
                                                             const float* __restrict__ xstd, const float* __restrict__ out,
                                                             const float* __restrict__ dout, float* __restrict__ dw,
                                                             long long Bd, int K, int N, int NP) {
@@ -721,20 +721,39 @@ __global__ void __launch_bounds__(kDrawT) dense_act_draws_bwd(const float* __res
   for (int k = 0; k <= kDrawMaxK; ++k)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[k][j] = 0.0f;
-  for (long long b = (long long)blockIdx.x * kDrawT + threadIdx.x; b < Bd; b += (long long)gridDim.x * kDrawT) {
-    float xn[kDrawMaxK];
-    load_xn(x, xmean, xstd, b, K, xn);
-    const long long row = ((long long)s * Bd + b) * NP + n0;
-    const float4 o0 = __ldg(reinterpret_cast<const float4*>(out + row)), o1 = __ldg(reinterpret_cast<const float4*>(out + row + 4));
-    const float4 d0 = __ldg(reinterpret_cast<const float4*>(dout + row)), d1 = __ldg(reinterpret_cast<const float4*>(dout + row + 4));
-    const float o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-    const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+  // two rows per iteration: eight independent 16-byte loads in flight per thread (the pass is latency-, not
+  // bandwidth-bound with one CTA wave of ~14 rows per thread)
+  const long long stride = (long long)gridDim.x * kDrawT;
+  for (long long b0 = (long long)blockIdx.x * kDrawT + threadIdx.x; b0 < Bd; b0 += 2 * stride) {
+    float4 o[2][2], d[2][2];
+    float xn[2][kDrawMaxK];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float dpre = d[j] * act_bwd<ACT>(o[j]);
-      acc[kDrawMaxK][j] += dpre;
+    for (int u = 0; u < 2; ++u) {
+      const long long b = b0 + u * stride;
+      if (b < Bd) {
+        const long long row = ((long long)s * Bd + b) * NP + n0;
+        o[u][0] = __ldg(reinterpret_cast<const float4*>(out + row));
+        o[u][1] = __ldg(reinterpret_cast<const float4*>(out + row + 4));
+        d[u][0] = __ldg(reinterpret_cast<const float4*>(dout + row));
+        d[u][1] = __ldg(reinterpret_cast<const float4*>(dout + row + 4));
+        load_xn(x, xmean, xstd, b, K, xn[u]);
+      } else {
+        o[u][0] = o[u][1] = d[u][0] = d[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);   // dpre = 0: contributes nothing
 #pragma unroll
-      for (int k = 0; k < kDrawMaxK; ++k) acc[k][j] = fmaf(xn[k], dpre, acc[k][j]);
+        for (int k = 0; k < kDrawMaxK; ++k) xn[u][k] = 0.0f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float ov[8] = {o[u][0].x, o[u][0].y, o[u][0].z, o[u][0].w, o[u][1].x, o[u][1].y, o[u][1].z, o[u][1].w};
+      const float dv[8] = {d[u][0].x, d[u][0].y, d[u][0].z, d[u][0].w, d[u][1].x, d[u][1].y, d[u][1].z, d[u][1].w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dpre = dv[j] * act_bwd<ACT>(ov[j]);
+        acc[kDrawMaxK][j] += dpre;
+#pragma unroll
+        for (int k = 0; k < kDrawMaxK; ++k) acc[k][j] = fmaf(xn[u][k], dpre, acc[k][j]);
+      }
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -767,7 +786,10 @@ cudaError_t launch_draws(bool bwd, const float* x, const float* xmean, const flo
   const DeviceInfo& di = device_info();
   const long long tiles = (Bd + kDrawT - 1) / kDrawT;
   const int slices = bwd ? (N + 7) / 8 : 1;
-  long long gx = ((long long)di.sm_count * 8 + (long long)S * slices - 1) / ((long long)S * slices);   // ~8 CTAs per SM overall
+  // forward: ~8 CTAs per SM overall; backward: ONE resident wave (2 CTAs per SM at its register count), so that the
+  // shuffle / shared-memory / atomic epilogue is paid once per ~14 rows of a thread instead of once per ~3
+  const long long per_sm = bwd ? 2 : 8;
+  long long gx = ((long long)di.sm_count * per_sm + (long long)S * slices - 1) / ((long long)S * slices);
   if (gx < 1) gx = 1;
   if (gx > tiles) gx = tiles;
   const dim3 grid((unsigned)gx, (unsigned)S, (unsigned)slices);
