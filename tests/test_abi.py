@@ -132,3 +132,41 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, fn)).read()
                 assert "import oracle" not in text and "from oracle" not in text, fn
+
+
+def test_round2_entry_points_validate_before_touching_the_gpu(nfn_lib):
+    """The fused mixture / folded-draw / weight-posterior entry points reject bad requests with the documented status
+    codes before any CUDA call (so this runs without a GPU); NULL and shape checks of include/nfn_b200.h."""
+    from normalizingflownetwork_b200 import _lib
+    from normalizingflownetwork_b200 import functional as F
+
+    null = None
+    one = (ctypes.c_float * 16)()
+    ptr = ctypes.cast(one, ctypes.POINTER(ctypes.c_float))
+    # fused Dense(P)+MDN: descriptor-like arguments, then pointers
+    assert nfn_lib.nfn_dense_mdn_forward_x(0, 2, 16, ptr, ptr, ptr, ptr, 4, ptr, 4, null, null) == -2   # n_centers
+    assert nfn_lib.nfn_dense_mdn_forward_x(5, 9, 16, ptr, ptr, ptr, ptr, 4, ptr, 4, null, null) == -2   # n_dims
+    assert nfn_lib.nfn_dense_mdn_forward_x(5, 1, 0, ptr, ptr, ptr, ptr, 4, ptr, 4, null, null) == -3    # hidden
+    assert nfn_lib.nfn_dense_mdn_forward_x(5, 1, 16, ptr, ptr, ptr, ptr, 3, ptr, 4, null, null) == -3   # y_rows vs B
+    assert nfn_lib.nfn_dense_mdn_forward_x(5, 1, 16, null, ptr, ptr, ptr, 4, ptr, 4, null, null) == -1  # h is NULL
+    assert nfn_lib.nfn_dense_mdn_forward_x(5, 1, 16, ptr, ptr, ptr, ptr, 0, ptr, 0, null, null) in (0, -3)  # empty batch
+    # folded draws: y is per SAMPLE
+    d = _lib.make_desc(["radial"] * 5, 1, True)
+    assert nfn_lib.nfn_dense_chain_forward_draws_x(ctypes.byref(d), 16, 0, 8, ptr, ptr, ptr, ptr, 8, ptr, null, null) == -3
+    assert nfn_lib.nfn_dense_chain_forward_draws_x(ctypes.byref(d), 16, 4, 8, ptr, ptr, ptr, ptr, 32, ptr, null, null) == -3
+    assert b"per sample" in nfn_lib.nfn_last_error()
+    assert nfn_lib.nfn_dense_chain_forward_draws_x(ctypes.byref(d), 16, 4, 8, null, ptr, ptr, ptr, 8, ptr, null, null) == -1
+    assert nfn_lib.nfn_dense_act_forward_draws(ptr, null, null, ptr, 4, 8, 9, 10, 16, 1, ptr, null) == -6     # 9 inputs
+    assert nfn_lib.nfn_dense_act_forward_draws(ptr, null, null, ptr, 4, 8, 1, 10, 12, 1, ptr, null) == -6     # row width % 8
+    assert nfn_lib.nfn_dense_act_forward_draws(ptr, ptr, null, ptr, 4, 8, 1, 10, 16, 1, ptr, null) == -1      # mean without std
+    assert nfn_lib.nfn_dense_act_backward_draws(ptr, null, null, ptr, null, 4, 8, 1, 10, 16, 1, ptr, null) == -1
+    # mean-field weight posterior
+    assert nfn_lib.nfn_variational_sample(ptr, ptr, ctypes.c_float(1.0), ptr, 0, 4, ptr, null, null) == -3
+    assert nfn_lib.nfn_variational_sample(ptr, ptr, ctypes.c_float(0.0), ptr, 8, 4, ptr, null, null) == -2    # prior scale
+    assert nfn_lib.nfn_variational_sample(null, ptr, ctypes.c_float(1.0), ptr, 8, 4, ptr, null, null) == -1
+    assert nfn_lib.nfn_variational_sample_backward(ptr, ptr, ctypes.c_float(1.0), null, ptr, null, 8, 4, ptr, null, null) == -1
+    # the shape helpers the estimators consult mirror the kernels' limits
+    assert F.dense_mdn_supported(16, 20, 2) and F.dense_mdn_supported(64, 5, 1)
+    assert not F.dense_mdn_supported(16, 200, 2) and not F.dense_mdn_supported(24, 5, 1)
+    assert F.dense_act_draws_supported(1, 10, 16, "tanh") and not F.dense_act_draws_supported(9, 10, 16, "tanh")
+    assert not F.dense_act_draws_supported(1, 10, 12, "tanh") and not F.dense_act_draws_supported(1, 10, 16, "gelu")
