@@ -374,6 +374,21 @@ int nfn_dense_mdn_forward_backward_draws_x(int n_centers, int n_dims, int hidden
                                            int64_t y_rows, const float* g_logp, float g_scale, float* logp, float* dh,
                                            float* dW, float* dbias, double* logp_sum, const nfn_event_xform* xf,
                                            void* stream);
+/*
+ * ... and into the KMN head: `Dense(output_size)` (MaximumLikelihoodNNEstimator.py:43) + GaussianKernelsLayer's
+ * log_prob (DistributionLayers.py:118-133) + their tape gradients.  The layer emits the logits of n_components fixed
+ * kernels; locs [n_components, n_dims] and scales [n_components] (negative bandwidths are legal, DistributionLayers.py
+ * :98-116) are read once per CTA; dscales [n_components] += d sum(cot * logp) / d scales (nullable: fixed bandwidths).
+ */
+int nfn_dense_kmn_forward_x(int n_components, int n_dims, int hidden, const float* h, const float* W, const float* bias,
+                            const float* y, int64_t y_rows, const float* locs, const float* scales, float* logp, int64_t B,
+                            const nfn_event_xform* xf, void* stream);
+int nfn_dense_kmn_forward_backward_x(int n_components, int n_dims, int hidden, const float* h, const float* W,
+                                     const float* bias, const float* y, int64_t y_rows, const float* locs,
+                                     const float* scales, const float* g_logp, float g_scale, float* logp, float* dh,
+                                     float* dW, float* dbias, float* dscales, double* logp_sum, int64_t B,
+                                     const nfn_event_xform* xf, void* stream);
+int64_t nfn_jit_dense_kmn_compile_check(int n_components, int n_dims, int hidden, int accurate);
 /* bytes of the NVRTC-built cubin for this mixture / hidden width (>= 0), or a negative nfn_status */
 int64_t nfn_jit_dense_mdn_compile_check(int n_centers, int n_dims, int hidden, int accurate);
 int nfn_kmn_forward_x(int n_components, int n_dims, const float* t, const float* y, int64_t y_rows,

@@ -340,6 +340,44 @@ class GaussianKernelsDistribution:
         return locs + scales.unsqueeze(-1) * torch.randn_like(locs)
 
 
+class FusedDenseGaussianKernelsDistribution(GaussianKernelsDistribution):
+    """The kernel mixture with the emitting Dense(P) layer folded into the kernel (see
+    FusedDenseFlowChainDistribution): holds h[B, H] and the layer's (W[H, M], bias[M]); ``.t`` (the logits)
+    materialises on demand."""
+
+    def __init__(self, h, W, bias, locs, scales):
+        self.h, self.W, self.bias = h, W, bias
+        self.locs = locs
+        self.scales = scales
+        self._t = None
+
+    @property
+    def t(self):
+        if self._t is None:
+            self._t = torch.addmm(self.bias, self.h, self.W)
+        return self._t
+
+    @property
+    def batch_shape(self):
+        return _Shape(self.h.shape[:-1])
+
+    def log_prob(self, y):
+        y = _to_tensor_like(y, self.h)
+        if torch.is_grad_enabled() and (self.h.requires_grad or self.W.requires_grad or self.scales.requires_grad):
+            return super().log_prob(y)  # autograd path goes through t
+        if y.shape[0] not in (self.h.shape[0], 1):
+            return super().log_prob(y)
+        return F.dense_kmn_forward(self.h, self.W, self.bias, y, self.locs.to(self.h.device),
+                                   self.scales.detach().to(self.h.device))
+
+    def log_prob_x(self, y, xform):
+        y = _to_tensor_like(y, self.h)
+        if y.shape[0] not in (self.h.shape[0], 1):
+            return super().log_prob_x(y, xform)
+        return F.dense_kmn_forward(self.h.detach(), self.W.detach(), self.bias.detach(), y, self.locs.to(self.h.device),
+                                   self.scales.detach().to(self.h.device), xform=xform)
+
+
 class GaussianKernelsLayer(torch.nn.Module):
     """Kernel mixture: logits over fixed centres x trainable per-scale bandwidths
     (reference :74-171).  Bandwidth of scale group i is

@@ -181,6 +181,15 @@ SIGNATURES = {
                                                              _c_float_p, ctypes.c_float, _c_float_p, _c_float_p,
                                                              _c_float_p, _c_float_p, ctypes.c_void_p, _xf_p,
                                                              ctypes.c_void_p]),
+    "nfn_dense_kmn_forward_x": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p,
+                                              _c_float_p, _c_float_p, _i64, _c_float_p, _c_float_p, _c_float_p, _i64,
+                                              _xf_p, ctypes.c_void_p]),
+    "nfn_dense_kmn_forward_backward_x": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p,
+                                                       _c_float_p, _c_float_p, _c_float_p, _i64, _c_float_p,
+                                                       _c_float_p, _c_float_p, ctypes.c_float, _c_float_p,
+                                                       _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                                       ctypes.c_void_p, _i64, _xf_p, ctypes.c_void_p]),
+    "nfn_jit_dense_kmn_compile_check": (_i64, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "nfn_jit_dense_mdn_compile_check": (_i64, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "nfn_kmn_forward_x": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _i64,
                                         _c_float_p, _c_float_p, _c_float_p, _i64, _xf_p, ctypes.c_void_p]),

@@ -910,6 +910,63 @@ int nfn_dense_mdn_forward_backward_draws_x(int n_centers, int n_dims, int hidden
   return dense_mdn_dispatch(n_centers, n_dims, hidden, a, true, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------ fused Dense(P) + KMN head
+static int dense_kmn_dispatch(int MC, int d, int hidden, const DenseArgs& a, bool bwd, cudaStream_t st) {
+  const int mode = math_mode();
+  const std::string key = dense_kmn_key(MC, d, hidden);
+  const DenseKernels* k = find_dense(key);
+  if (k && k->fn[mode][bwd ? 1 : 0]) return cuda_error(k->fn[mode][bwd ? 1 : 0](a, st), key.c_str());
+  bool served = false;
+  cudaError_t e = launch_dense_kmn_jit(MC, d, hidden, a, bwd, mode, st, &served);
+  if (e != cudaSuccess) return cuda_error(e, key.c_str());
+  if (!served)
+    return set_error(NFN_ERR_UNSUPPORTED,
+                     "no fused dense kernel for %d %d-D Gaussian kernels with hidden width %d (needs a multiple of 16 <= 64 "
+                     "and an ahead-of-time instance or NVRTC): compose the layer and nfn_kmn_forward_backward instead",
+                     MC, d, hidden);
+  return NFN_OK;
+}
+
+int nfn_dense_kmn_forward_x(int n_components, int n_dims, int hidden, const float* h, const float* W, const float* bias,
+                            const float* y, int64_t y_rows, const float* locs, const float* scales, float* logp, int64_t B,
+                            const nfn_event_xform* xf, void* stream) {
+  int rc = dense_mdn_common(n_components, n_dims, hidden, h, W, bias, y, y_rows, logp, B);
+  if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
+  if (!locs || !scales) return set_error(NFN_ERR_NULL, "locs and scales must be non-NULL");
+  DenseArgs a{};
+  a.h = h; a.W = W; a.bias = bias; a.y = y; a.logp = logp; a.B = B; a.g_scale = 1.0f;
+  a.y_broadcast = (y_rows == 1 && B != 1);
+  a.locs = locs; a.scales = scales;
+  if ((rc = set_xform(a.xf, xf, n_dims)) != NFN_OK) return rc;
+  return dense_kmn_dispatch(n_components, n_dims, hidden, a, false, (cudaStream_t)stream);
+}
+
+int nfn_dense_kmn_forward_backward_x(int n_components, int n_dims, int hidden, const float* h, const float* W,
+                                     const float* bias, const float* y, int64_t y_rows, const float* locs,
+                                     const float* scales, const float* g_logp, float g_scale, float* logp, float* dh,
+                                     float* dW, float* dbias, float* dscales, double* logp_sum, int64_t B,
+                                     const nfn_event_xform* xf, void* stream) {
+  int rc = dense_mdn_common(n_components, n_dims, hidden, h, W, bias, y, y_rows, logp, B);
+  if (rc != NFN_OK) return rc > 0 ? NFN_OK : rc;
+  if (!locs || !scales) return set_error(NFN_ERR_NULL, "locs and scales must be non-NULL");
+  if (!dh || !dW || !dbias) return set_error(NFN_ERR_NULL, "dh, dW and dbias must be non-NULL");
+  if (!aligned(dh, 16)) return set_error(NFN_ERR_ALIGN, "dh must be 16-byte aligned");
+  DenseArgs a{};
+  a.h = h; a.W = W; a.bias = bias; a.y = y; a.g_logp = g_logp; a.logp = logp; a.dh = dh; a.dW = dW;
+  a.dbias = dbias; a.logp_sum = logp_sum; a.B = B; a.g_scale = g_scale;
+  a.y_broadcast = (y_rows == 1 && B != 1);
+  a.locs = locs; a.scales = scales; a.dscales = dscales;
+  if ((rc = set_xform(a.xf, xf, n_dims)) != NFN_OK) return rc;
+  return dense_kmn_dispatch(n_components, n_dims, hidden, a, true, (cudaStream_t)stream);
+}
+
+int64_t nfn_jit_dense_kmn_compile_check(int n_components, int n_dims, int hidden, int accurate) {
+  std::string log;
+  const long long n = jit_dense_kmn_compile_check(n_components, n_dims, hidden, accurate ? 1 : 0, log);
+  if (n < 0) return set_error(NFN_ERR_UNSUPPORTED, "dense+kmn runtime specialisation failed: %s", log.c_str());
+  return n;
+}
+
 int64_t nfn_jit_dense_mdn_compile_check(int n_centers, int n_dims, int hidden, int accurate) {
   std::string log;
   const long long n = jit_dense_mdn_compile_check(n_centers, n_dims, hidden, accurate ? 1 : 0, log);

@@ -377,8 +377,59 @@ struct DenseMdnRegistrar {
   }
 };
 
+// ------------------------------------------------------------------ fused Dense(P) + KMN head (mma.sync body)
+template <int MC, int D, int H, bool BWD, class M>
+cudaError_t launch_dense_kmn(const DenseArgs& a, cudaStream_t st) {
+  constexpr int T = 128;
+  constexpr unsigned kSmem = dense_smem_bytes(MC, H, T, BWD, kmn_extra_floats(MC, D, T, BWD));
+  constexpr int kBySmem = (int)((227u * 1024u) / (kSmem + 1024u));
+  constexpr int kWant = BWD ? 2 : 3;
+  constexpr int MINB = kBySmem < 1 ? 1 : (kBySmem < kWant ? kBySmem : kWant);
+  auto kern = dense_kmn_kernel<MC, D, H, BWD, M, T, MINB>;
+  struct Cfg {
+    int device = -1;
+    int ctas_per_sm = 0;
+  };
+  static thread_local Cfg cfg;
+  const DeviceInfo& di = device_info();
+  if (cfg.device != di.device) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, kSmem);
+    if (e != cudaSuccess) return e;
+    cfg.ctas_per_sm = occ > 0 ? occ : 1;
+    cfg.device = di.device;
+  }
+  const long long ntiles = (a.B + T - 1) / T;
+  long long grid = (long long)di.sm_count * cfg.ctas_per_sm;
+  if (grid > ntiles) grid = ntiles;
+  kern<<<(unsigned)grid, T, kSmem, st>>>(a);
+  count_launch();
+  return cudaGetLastError();
+}
+
+inline std::string dense_kmn_key(int MC, int D, int H) {
+  return "kmn|m" + std::to_string(MC) + "d" + std::to_string(D) + "|h" + std::to_string(H);
+}
+
+template <int MC, int D, int H>
+struct DenseKmnRegistrar {
+  explicit DenseKmnRegistrar() {
+    DenseKernels k;
+    k.fn[0][0] = &launch_dense_kmn<MC, D, H, false, MathFast>;
+    k.fn[0][1] = &launch_dense_kmn<MC, D, H, true, MathFast>;
+    k.fn[1][0] = &launch_dense_kmn<MC, D, H, false, MathAccurate>;
+    k.fn[1][1] = &launch_dense_kmn<MC, D, H, true, MathAccurate>;
+    register_dense(dense_kmn_key(MC, D, H), k);
+  }
+};
+
 cudaError_t launch_dense_jit(const nfn_chain_desc* desc, int H, const std::string& key, const DenseArgs& a,
                              bool bwd, int mode, cudaStream_t st, bool* served);
+cudaError_t launch_dense_kmn_jit(int MC, int D, int H, const DenseArgs& a, bool bwd, int mode, cudaStream_t st,
+                                 bool* served);
+long long jit_dense_kmn_compile_check(int MC, int D, int H, int mode, std::string& log);
 cudaError_t launch_dense_mdn_jit(int K, int D, int H, const DenseArgs& a, bool bwd, int mode, cudaStream_t st,
                                  bool* served);
 long long jit_dense_mdn_compile_check(int K, int D, int H, int mode, std::string& log);

@@ -43,6 +43,10 @@ struct DenseArgs {
   // draws <= 1: one weight set for all B rows.
   int draws;
   long long rows_per_draw;
+  // KMN head only: fixed centres [M][d], shared bandwidths [M] (may be negative), their gradient [M] += (nullable)
+  const float* locs;
+  const float* scales;
+  float* dscales;
 };
 
 // ---------------------------------------------------------------- tensor-core helpers
@@ -98,9 +102,14 @@ __host__ __device__ constexpr int w_stride(int n) {
 }
 
 // dynamic shared memory of the fused dense kernel (same arithmetic as DenseGeometry below)
-__host__ __device__ constexpr unsigned dense_smem_bytes(int P, int H, int T, bool bwd) {
+__host__ __device__ constexpr unsigned dense_smem_bytes(int P, int H, int T, bool bwd, int head_extra_floats = 0) {
   const int S = row_stride(P), HS = H + 4, P8 = (P + 7) / 8 * 8, PW = w_stride(P8), NW = T / 32;
-  return (unsigned)(4 * (T * S + 2 * T * HS + H * PW + P8 + (bwd ? NW * H * P8 + NW * P8 : 0)));
+  return (unsigned)(4 * (T * S + 2 * T * HS + H * PW + P8 + (bwd ? NW * H * P8 + NW * P8 : 0) + head_extra_floats));
+}
+// shared-memory floats the KMN head keeps next to the tiles: centres, two per-kernel coefficients, per-warp
+// bandwidth-gradient sums
+__host__ __device__ constexpr int kmn_extra_floats(int M, int D, int T, bool bwd) {
+  return M * (D + 2) + (bwd ? (T / 32) * M : 0);
 }
 
 template <int P, int H, int T>
@@ -124,12 +133,21 @@ struct DenseGeometry {
 // A head turns row r of t (in shared memory, stride S) and the event y_r into log p(y_r | t_r) and, in place,
 // cot * d log p / d t_r.  Two of them share the GEMM scaffolding below.
 //   ChainHead<Spec>: the inverted flow chain (reference estimators/DistributionLayers.py:215-294)
+// A head may keep per-kernel constants in shared memory behind the tiles (`extra_floats`, `stage`, `finish`) and may
+// ask to be called by ALL lanes of a warp, rows past the end included (`kAllLanes`: warp-level reductions inside).
+struct HeadNoState {
+  static constexpr bool kAllLanes = false;
+  __host__ __device__ static constexpr int extra_floats(int, bool) { return 0; }
+  template <bool BWD> NFN_DEVI static void stage(const DenseArgs&, float*, int, int) {}
+  template <bool BWD> NFN_DEVI static void finish(const DenseArgs&, float*, int, int) {}
+};
+
 template <class Spec>
-struct ChainHead {
+struct ChainHead : HeadNoState {
   static constexpr int D = Spec::D;
   static constexpr int P = Spec::P();
   template <bool BWD, class M>
-  NFN_DEVI static float run(float* row, float (&z)[D], float cot) {
+  NFN_DEVI static float run(float* row, float (&z)[D], float cot, bool, float*) {
     constexpr int V = row_vec(P);
     float zs[Spec::KA][D];
     LogDetAcc<M> ld;
@@ -151,18 +169,71 @@ struct ChainHead {
 //   MdnHead<K, D>: the K-component Gaussian mixture (reference estimators/DistributionLayers.py:196-212, fed by
 //   the Dense(P) layer of MaximumLikelihoodNNEstimator.py:43); row arithmetic shared with nfn_mixture.cu
 template <int K_, int D_>
-struct MdnHead {
+struct MdnHead : HeadNoState {
   static constexpr int D = D_;
   static constexpr int K = K_;
   static constexpr int P = K_ * (2 * D_ + 1);
   template <bool BWD, class M>
-  NFN_DEVI static float run(float* row, float (&z)[D], float cot) {
+  NFN_DEVI static float run(float* row, float (&z)[D], float cot, bool, float*) {
     constexpr bool V4 = (P % 4 == 0);           // row_stride keeps 16-byte row alignment then
     constexpr int LG = (V4 && K % 4 == 0) ? 4 : 1;
     float dy[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) dy[i] = 0.0f;
     return mdn_row<D, V4, LG, BWD, M>(row, K, z, cot, dy);
+  }
+};
+
+//   KmnHead<M, D>: M fixed Gaussian kernels with shared bandwidths, the row is their logits (reference
+//   estimators/DistributionLayers.py:74-133, fed by the Dense(P) layer of MaximumLikelihoodNNEstimator.py:43); row
+//   arithmetic shared with nfn_mixture.cu.  Shared-memory state: centres, -0.5 log2e / s^2, -d log2|s|, and (BWD) one
+//   row of bandwidth-gradient sums per warp.
+template <int M_, int D_>
+struct KmnHead {
+  static constexpr int D = D_;
+  static constexpr int P = M_;
+  static constexpr bool kAllLanes = true;
+  __host__ __device__ static constexpr int extra_floats(int T, bool bwd) { return kmn_extra_floats(M_, D_, T, bwd); }
+  template <bool BWD>
+  NFN_DEVI static void stage(const DenseArgs& a, float* ex, int tid, int T) {
+    float* s_loc = ex;
+    float* s_coef = s_loc + M_ * D_;
+    float* s_lnorm = s_coef + M_;
+    for (int i = tid; i < M_ * D_; i += T) s_loc[i] = __ldg(a.locs + i);
+    for (int i = tid; i < M_; i += T) {
+      const float sc = __ldg(a.scales + i);
+      s_coef[i] = -0.5f * kLog2e / (sc * sc);
+      s_lnorm[i] = -(float)D_ * log2f(fabsf(sc));
+    }
+    if constexpr (BWD) {
+      float* s_dsc = s_lnorm + M_;
+      for (int i = tid; i < (T / 32) * M_; i += T) s_dsc[i] = 0.0f;
+    }
+  }
+  template <bool BWD, class Mth>
+  NFN_DEVI static float run(float* row, float (&z)[D], float cot, bool valid, float* ex) {
+    constexpr int LG = (M_ % 4 == 0) ? 4 : 1;   // row_stride keeps 16-byte row alignment then
+    float* s_loc = ex;
+    float* s_coef = s_loc + M_ * D_;
+    float* s_lnorm = s_coef + M_;
+    float* my_dsc = BWD ? s_lnorm + M_ + (threadIdx.x >> 5) * M_ : nullptr;
+    float dy[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) dy[i] = 0.0f;
+    return kmn_row<D, LG, BWD, Mth>(row, M_, z, cot, valid, s_loc, s_coef, s_lnorm, my_dsc, dy);
+  }
+  template <bool BWD>
+  NFN_DEVI static void finish(const DenseArgs& a, float* ex, int tid, int T) {
+    if constexpr (BWD) {
+      if (a.dscales) {
+        const float* s_dsc = ex + M_ * (D_ + 2);
+        for (int i = tid; i < M_; i += T) {
+          float v = 0.0f;
+          for (int w = 0; w < T / 32; ++w) v += s_dsc[w * M_ + i];
+          atomicAdd(a.dscales + i, v / __ldg(a.scales + i));
+        }
+      }
+    }
   }
 };
 
@@ -186,6 +257,7 @@ NFN_DEVI void dense_head_body(const DenseArgs& a) {
   float* sB = sW + G::kW;              // [P8]
   float* sAcc = sB + P8;               // [NW][H][P8]   (BWD)
   float* sAccB = sAcc + G::kAcc;       // [NW][P8]      (BWD)
+  float* sHead = sB + P8 + (BWD ? G::kAcc + G::kAccB : 0);   // the head's own constants / accumulators
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tig = lane & 3;
@@ -240,6 +312,7 @@ NFN_DEVI void dense_head_body(const DenseArgs& a) {
   if constexpr (BWD) {
     for (int i = tid; i < G::kAcc + G::kAccB; i += T) sAcc[i] = 0.0f;
   }
+  Head::template stage<BWD>(a, sHead, tid, T);   // (made visible by the barrier in front of the first tile)
   long long s_cur = -1;   // draw whose weights are staged
 
   // Every warp owns rows [32 warp, 32 warp + 32) of each tile end to end (h load, the three GEMMs,
@@ -353,13 +426,20 @@ NFN_DEVI void dense_head_body(const DenseArgs& a) {
 
     // ---- per-row head (flow chain or mixture), dt written in place over t
     float* row = tT + tid * S;
-    if (rd < Bd) {
-      const float lp = xform_out<M>(a.xf, Head::template run<BWD, M>(row, z, BWD ? a.g_scale * g_cur : 0.0f));
-      a.logp[r] = lp;
-      lsum += (double)lp;
-    } else if constexpr (BWD) {
+    const bool valid = rd < Bd;
+    if (valid || Head::kAllLanes) {
+      const float lpn = Head::template run<BWD, M>(row, z, (BWD && valid) ? a.g_scale * g_cur : 0.0f, valid, sHead);
+      if (valid) {
+        const float lp = xform_out<M>(a.xf, lpn);
+        a.logp[r] = lp;
+        lsum += (double)lp;
+      }
+    }
+    if constexpr (BWD) {
+      if (!valid) {
 #pragma unroll
-      for (int j = 0; j < P; ++j) row[j] = 0.0f;   // rows past the end contribute nothing to dW / db
+        for (int j = 0; j < P; ++j) row[j] = 0.0f;   // rows past the end contribute nothing to dW / db
+      }
     }
 
     if constexpr (BWD) {
@@ -511,6 +591,7 @@ NFN_DEVI void dense_head_body(const DenseArgs& a) {
     __syncthreads();
     if (s_cur >= 0) flush_grads(s_cur);
   }
+  Head::template finish<BWD>(a, sHead, tid, T);   // (after the barrier above; forward-only heads have nothing to flush)
 }
 
 // the flow-chain instance under its historical name (ahead-of-time instances and the runtime specialiser use it)
@@ -527,6 +608,11 @@ __global__ void __launch_bounds__(T, MINB) dense_chain_kernel(const DenseArgs a)
 template <int K, int D, int H, bool BWD, class M, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) dense_mdn_kernel(const DenseArgs a) {
   dense_head_body<MdnHead<K, D>, H, BWD, M, T>(a);
+}
+
+template <int MC, int D, int H, bool BWD, class M, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) dense_kmn_kernel(const DenseArgs a) {
+  dense_head_body<KmnHead<MC, D>, H, BWD, M, T>(a);
 }
 
 }  // namespace nfn

@@ -549,4 +549,63 @@ long long jit_dense_mdn_compile_check(int K, int D, int H, int mode, std::string
   return (long long)cubin.size();
 }
 
+// ------------------------------------------------------------------ fused Dense(P) + KMN head
+static std::string dense_kmn_program_source(int MC, int D, int H, int mode, const ChainGeometry (&geo)[2]) {
+  const char* math = mode == 0 ? "nfn::MathFast" : "nfn::MathAccurate";
+  std::string s = "#include \"nfn_dense_chain.cuh\"\nusing Head = nfn::KmnHead<" + std::to_string(MC) + ", " +
+                  std::to_string(D) + ">;\n";
+  const char* names[2] = {"nfn_jit_dense_kmn_fwd", "nfn_jit_dense_kmn_fwd_bwd"};
+  for (int b = 0; b < 2; ++b) {
+    s += "extern \"C\" __global__ void __launch_bounds__(" + std::to_string(geo[b].T) + ", " +
+         std::to_string(geo[b].MINB) + ") " + names[b] + "(const nfn::DenseArgs a) {\n  nfn::dense_head_body<Head, " +
+         std::to_string(H) + ", " + (b ? "true" : "false") + ", " + math + ", " + std::to_string(geo[b].T) +
+         ">(a);\n}\n";
+  }
+  return s;
+}
+
+static void dense_kmn_geometry(int MC, int D, int H, ChainGeometry (&geo)[2]) {
+  for (int b = 0; b < 2; ++b) {
+    geo[b].T = 128;
+    geo[b].NB = 2;
+    geo[b].smem_bytes = dense_smem_bytes(MC, H, 128, b == 1, kmn_extra_floats(MC, D, 128, b == 1));
+    const int by_smem = (int)((227u * 1024u) / (geo[b].smem_bytes + 1024u));
+    const int want = b ? 2 : 3;
+    geo[b].MINB = by_smem < 1 ? 1 : (by_smem < want ? by_smem : want);
+  }
+}
+
+static bool dense_kmn_eligible(int MC, int D, int H, const ChainGeometry (&geo)[2]) {
+  return MC >= 1 && D >= 1 && D <= 8 && H % 16 == 0 && H >= 16 && H <= 64 && geo[1].smem_bytes <= 220u * 1024u;
+}
+
+// served == false (with cudaSuccess): the caller must use the unfused path
+cudaError_t launch_dense_kmn_jit(int MC, int D, int H, const DenseArgs& a, bool bwd, int mode, cudaStream_t st,
+                                 bool* served) {
+  *served = false;
+  if (!jit_enabled()) return cudaSuccess;
+  ChainGeometry geo[2];
+  dense_kmn_geometry(MC, D, H, geo);
+  if (!dense_kmn_eligible(MC, D, H, geo)) return cudaSuccess;
+  const char* const names[2] = {"nfn_jit_dense_kmn_fwd", "nfn_jit_dense_kmn_fwd_bwd"};
+  const std::string ckey = dense_kmn_key(MC, D, H) + "|m" + std::to_string(mode) + "|dev" + std::to_string(device_info().device);
+  JitEntry* ent = get_or_build(ckey, dense_kmn_program_source(MC, D, H, mode, geo), names, geo);
+  if (!ent) return cudaSuccess;
+  cudaError_t ce = launch_entry(ent, bwd ? 1 : 0, a, a.B, st);
+  if (ce == cudaSuccess) *served = true;
+  return ce;
+}
+
+long long jit_dense_kmn_compile_check(int MC, int D, int H, int mode, std::string& log) {
+  ChainGeometry geo[2];
+  dense_kmn_geometry(MC, D, H, geo);
+  if (!dense_kmn_eligible(MC, D, H, geo)) {
+    log = "kernel mixture / hidden width not eligible for the fused kernel";
+    return -1;
+  }
+  std::vector<char> cubin;
+  if (!compile_cubin(dense_kmn_program_source(MC, D, H, mode, geo), cubin, log)) return -1;
+  return (long long)cubin.size();
+}
+
 }  // namespace nfn

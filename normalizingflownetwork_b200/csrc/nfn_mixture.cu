@@ -263,74 +263,18 @@ __global__ void __launch_bounds__(kMixT, BWD ? 4 : 5) kmn_kernel(const MixArgs a
     const long long r = tile * kMixT + threadIdx.x;
     const bool valid = r < a.B;
     float* row = buf + threadIdx.x * g.S;
-    float lse2 = 0.0f, top2 = 0.0f, cot = 0.0f;
+    float dy[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) dy[i] = 0.0f;
+    const float logp = kmn_row<D, LG, BWD, M>(row, K, y, (BWD && valid) ? a.g_scale * g_cur : 0.0f, valid, s_loc, s_coef,
+                                              s_lnorm, (BWD && a.dscales) ? my_dsc : nullptr, dy);
     if (valid) {
-      float lm = NFN_NEG_INF, ls = 0.0f, m = NFN_NEG_INF, s = 0.0f;
-      for (int k0 = 0; k0 < K; k0 += LG) {
-        float lg[LG];
-        ld_vec<LG, LG>(row + k0, lg);
-#pragma unroll
-        for (int j = 0; j < LG; ++j) {
-          const int k = k0 + j;
-          const float l2 = lg[j] * kLog2e;
-          lse2_push<M>(l2, lm, ls);
-          float q = 0.0f;
-#pragma unroll
-          for (int i = 0; i < D; ++i) {
-            const float dlt = y[i] - s_loc[k * D + i];
-            q = fmaf(dlt, dlt, q);
-          }
-          lse2_push<M>(l2 + fmaf(s_coef[k], q, s_lnorm[k]), m, s);
-        }
-      }
-      lse2 = lm + M::lg2(ls);
-      top2 = m + M::lg2(s);
-      const float logp = (top2 - lse2) * kLn2 - (float)D * kHalfLog2Pi;
       const float lpo = xform_out<M>(a.xf, logp);
       a.logp[r] = lpo;
       lsum += (double)lpo;
-    }
-    if constexpr (BWD) {
-      if (valid) cot = a.g_scale * g_cur;
-      float dy[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) dy[i] = 0.0f;
-      for (int k0 = 0; k0 < K; k0 += LG) {  // all lanes stay in the loop: warp reduction of d/dscale
-        float lg[LG];
-        if (valid) {
-          ld_vec<LG, LG>(row + k0, lg);
-        } else {
-#pragma unroll
-          for (int j = 0; j < LG; ++j) lg[j] = 0.0f;
-        }
-#pragma unroll
-        for (int j = 0; j < LG; ++j) {
-          const int k = k0 + j;
-          float wsc = 0.0f;
-          if (valid) {
-            float q = 0.0f, dl[D];
-#pragma unroll
-            for (int i = 0; i < D; ++i) {
-              dl[i] = y[i] - s_loc[k * D + i];
-              q = fmaf(dl[i], dl[i], q);
-            }
-            const float l2 = lg[j] * kLog2e;
-            const float crho = cot * M::ex2(l2 + fmaf(s_coef[k], q, s_lnorm[k]) - top2);
-            lg[j] = fmaf(-cot, M::ex2(l2 - lse2), crho);
-            const float c2 = -2.0f * kLn2 * s_coef[k];        // 1 / s^2
-#pragma unroll
-            for (int i = 0; i < D; ++i) dy[i] -= crho * dl[i] * c2;
-            wsc = crho * fmaf(q, c2, -(float)D);               // * 1/s applied when the sums are flushed
-          }
-          if (a.dscales) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) wsc += __shfl_xor_sync(0xffffffffu, wsc, o);
-            if ((threadIdx.x & 31) == 0) my_dsc[k] += wsc;
-          }
-        }
-        if (valid) st_vec<LG, LG>(row + k0, lg);
+      if constexpr (BWD) {
+        if (a.dy) store_event<D>(a.dy, r, dy);
       }
-      if (valid && a.dy) store_event<D>(a.dy, r, dy);
     }
     __syncthreads();
     if constexpr (BWD) {

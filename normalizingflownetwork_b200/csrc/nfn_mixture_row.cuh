@@ -153,4 +153,77 @@ NFN_DEVI float mdn_row(float* row, const int K, const float (&y)[D], const float
   return logp;
 }
 
+// One KMN row (tfd.MixtureSameFamily over K fixed centres with shared isotropic bandwidths, reference
+// estimators/DistributionLayers.py:118-133): row = logits(K).  s_loc [K][D], s_coef [K] = -0.5 log2e / s^2,
+// s_lnorm [K] = -D log2|s| are per-kernel constants in shared memory.  Called by ALL lanes of a warp (`valid` masks
+// rows past the end): the bandwidth gradient is reduced over the warp's rows with shuffles and added to my_dsc [K]
+// (this warp's partial sums, * 1/s applied when they are flushed; nullptr: not wanted).  Returns log p (natural log);
+// with BWD overwrites the row with cot * d log p / d logits and accumulates the event gradient into dy.
+template <int D, int LG, bool BWD, class M>
+NFN_DEVI float kmn_row(float* row, const int K, const float (&y)[D], const float cot, const bool valid,
+                       const float* s_loc, const float* s_coef, const float* s_lnorm, float* my_dsc, float (&dy)[D]) {
+  float lse2 = 0.0f, top2 = 0.0f, logp = 0.0f;
+  if (valid) {
+    float lm = NFN_NEG_INF, ls = 0.0f, m = NFN_NEG_INF, s = 0.0f;
+    for (int k0 = 0; k0 < K; k0 += LG) {
+      float lg[LG];
+      ld_vec<LG, LG>(row + k0, lg);
+#pragma unroll
+      for (int j = 0; j < LG; ++j) {
+        const int k = k0 + j;
+        const float l2 = lg[j] * kLog2e;
+        lse2_push<M>(l2, lm, ls);
+        float q = 0.0f;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          const float dlt = y[i] - s_loc[k * D + i];
+          q = fmaf(dlt, dlt, q);
+        }
+        lse2_push<M>(l2 + fmaf(s_coef[k], q, s_lnorm[k]), m, s);
+      }
+    }
+    lse2 = lm + M::lg2(ls);
+    top2 = m + M::lg2(s);
+    logp = (top2 - lse2) * kLn2 - (float)D * kHalfLog2Pi;
+  }
+  if constexpr (BWD) {
+    for (int k0 = 0; k0 < K; k0 += LG) {  // all lanes stay in the loop: warp reduction of d/dscale
+      float lg[LG];
+      if (valid) {
+        ld_vec<LG, LG>(row + k0, lg);
+      } else {
+#pragma unroll
+        for (int j = 0; j < LG; ++j) lg[j] = 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < LG; ++j) {
+        const int k = k0 + j;
+        float wsc = 0.0f;
+        if (valid) {
+          float q = 0.0f, dl[D];
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            dl[i] = y[i] - s_loc[k * D + i];
+            q = fmaf(dl[i], dl[i], q);
+          }
+          const float l2 = lg[j] * kLog2e;
+          const float crho = cot * M::ex2(l2 + fmaf(s_coef[k], q, s_lnorm[k]) - top2);
+          lg[j] = fmaf(-cot, M::ex2(l2 - lse2), crho);
+          const float c2 = -2.0f * kLn2 * s_coef[k];        // 1 / s^2
+#pragma unroll
+          for (int i = 0; i < D; ++i) dy[i] -= crho * dl[i] * c2;
+          wsc = crho * fmaf(q, c2, -(float)D);               // * 1/s applied when the sums are flushed
+        }
+        if (my_dsc) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) wsc += __shfl_xor_sync(0xffffffffu, wsc, o);
+          if ((threadIdx.x & 31) == 0) my_dsc[k] += wsc;
+        }
+      }
+      if (valid) st_vec<LG, LG>(row + k0, lg);
+    }
+  }
+  return logp;
+}
+
 }  // namespace nfn

@@ -17,6 +17,7 @@ import torch.distributed as dist
 from .. import functional as F
 from ..DistributionLayers import (
     FusedDenseFlowChainDistribution,
+    FusedDenseGaussianKernelsDistribution,
     FusedDenseGaussianMixtureDistribution,
     GaussianKernelsLayer,
     GaussianMixtureLayer,
@@ -127,7 +128,8 @@ class BaseEstimator(torch.nn.Module):
         NF head with at least one parameter or MDN head, plain (non-variational) linear output layer whose
         input width is 16, 32, 48 or 64."""
         layer = self.dist_layer
-        if not self.fuse_last_layer or not isinstance(layer, (InverseNormalizingFlowLayer, GaussianMixtureLayer)):
+        if not self.fuse_last_layer or not isinstance(layer, (InverseNormalizingFlowLayer, GaussianMixtureLayer,
+                                                                  GaussianKernelsLayer)):
             return None
         last = self.net[-1]
         lin = getattr(last, "linear", None)
@@ -137,6 +139,10 @@ class BaseEstimator(torch.nn.Module):
             return None
         if isinstance(layer, GaussianMixtureLayer) and not F.dense_mdn_supported(lin.in_features, layer._n_centers,
                                                                                   layer._n_dims):
+            return None
+        if isinstance(layer, GaussianKernelsLayer) and not F.dense_kmn_supported(lin.in_features,
+                                                                                  layer.get_total_param_size(),
+                                                                                  layer.locs.shape[1]):
             return None
         return lin
 
@@ -168,6 +174,9 @@ class BaseEstimator(torch.nn.Module):
                     if isinstance(layer, GaussianMixtureLayer):
                         return FusedDenseGaussianMixtureDistribution(self.hidden_from_x(x), self._emitting_kernel(lin),
                                                                      lin.bias, layer._n_centers, layer._n_dims)
+                    if isinstance(layer, GaussianKernelsLayer):
+                        return FusedDenseGaussianKernelsDistribution(self.hidden_from_x(x), self._emitting_kernel(lin),
+                                                                     lin.bias, layer.locs, layer.scale_model())
                     return FusedDenseFlowChainDistribution(self.hidden_from_x(x), self._emitting_kernel(lin),
                                                            lin.bias, layer._flow_types, layer._n_dims,
                                                            layer._trainable_base_dist)
@@ -308,6 +317,13 @@ class BaseEstimator(torch.nn.Module):
                 _, dh, dW, db = F.dense_mdn_forward_backward(
                     h.detach(), self._emitting_kernel(lin), lin.bias.detach(), y, layer._n_centers, layer._n_dims,
                     g_scale=-1.0 / Bg, logp_sum=logp_sum, xform=xf)
+            elif isinstance(layer, GaussianKernelsLayer):
+                scales = layer.scale_model()
+                _, dh, dW, db, dsc = F.dense_kmn_forward_backward(
+                    h.detach(), self._emitting_kernel(lin), lin.bias.detach(), y, layer.locs, scales.detach(),
+                    g_scale=-1.0 / Bg, want_dscales=scales.requires_grad, logp_sum=logp_sum, xform=xf)
+                if scales.requires_grad:
+                    scales.backward(dsc)
             else:
                 _, dh, dW, db = F.dense_chain_forward_backward(
                     h.detach(), self._emitting_kernel(lin), lin.bias.detach(), y, layer._flow_types,

@@ -479,6 +479,77 @@ def dense_chain_forward_backward_draws(h, W, bias, y, flow_types, n_dims, traina
     return logp, dh, dW, dbias
 
 
+def dense_kmn_supported(hidden, n_components, n_dims):
+    """Whether the fused Dense(P)+KMN kernel can serve this shape (see dense_mdn_supported; P = n_components plus the
+    head's own shared-memory state: centres, two coefficients and four rows of bandwidth-gradient sums per kernel)."""
+    if hidden not in (16, 32, 48, 64) or n_components < 1 or not 1 <= n_dims <= 8:
+        return False
+    P = n_components
+    S = P + 4 if (P % 4 == 0 and (P // 4) % 2 == 0) else P
+    P8 = (P + 7) // 8 * 8
+    PW = P8
+    while PW % 32 not in (8, 24):
+        PW += 1
+    floats = 128 * S + 2 * 128 * (hidden + 4) + hidden * PW + P8 + 4 * hidden * P8 + 4 * P8 + P * (n_dims + 2) + 4 * P
+    return 4 * floats <= 220 * 1024
+
+
+def dense_kmn_forward(h, W, bias, y, locs, scales, xform=None):
+    """log_prob[B] of the kernel mixture with the emitting layer fused: the logits t = h @ W + bias never touch HBM.
+    h [B, H], W [H, M], bias [M], locs [M, d], scales [M].  Reference: Dense(output_size) of
+    MaximumLikelihoodNNEstimator.py:43 + DistributionLayers.py:118-133."""
+    lib = _lib.load()
+    locs = _as_f32_cuda(locs, "locs")
+    M, d = locs.shape
+    h = _aligned(_as_f32_cuda(h, "h", device=locs.device))
+    dev = h.device
+    scales = _as_f32_cuda(scales, "scales", device=dev).reshape(-1)
+    W = _as_f32_cuda(W, "W", device=dev)
+    bias = _as_f32_cuda(bias, "bias", device=dev)
+    y = _aligned(_as_f32_cuda(y, "y", device=dev))
+    B, H = h.shape
+    assert tuple(W.shape) == (H, M) and tuple(bias.shape) == (M,) and scales.numel() == M, "W [H, M], bias [M], scales [M]"
+    _check_y(y, d, B, "dense_kmn_forward")
+    logp = torch.empty(B, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_dense_kmn_forward_x(M, d, H, _lib.ptr(h), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(y), y.shape[0],
+                                               _lib.ptr(locs), _lib.ptr(scales), _lib.ptr(logp), B, _xf(xform),
+                                               _lib.current_stream(dev)))
+    return logp
+
+
+def dense_kmn_forward_backward(h, W, bias, y, locs, scales, g_logp=None, g_scale=1.0, want_dscales=True, logp_sum=None,
+                               dW=None, dbias=None, xform=None):
+    """Fused layer + kernel-mixture head, forward and reverse sweep.  Returns (logp[B], dh[B,H], dW[H,M], dbias[M],
+    dscales[M] or None); dW / dbias are accumulated into when given."""
+    lib = _lib.load()
+    locs = _as_f32_cuda(locs, "locs")
+    M, d = locs.shape
+    h = _aligned(_as_f32_cuda(h, "h", device=locs.device))
+    dev = h.device
+    scales = _as_f32_cuda(scales, "scales", device=dev).reshape(-1)
+    W = _as_f32_cuda(W, "W", device=dev)
+    bias = _as_f32_cuda(bias, "bias", device=dev)
+    y = _aligned(_as_f32_cuda(y, "y", device=dev))
+    B, H = h.shape
+    assert tuple(W.shape) == (H, M) and tuple(bias.shape) == (M,) and scales.numel() == M, "W [H, M], bias [M], scales [M]"
+    _check_y(y, d, B, "dense_kmn_forward_backward")
+    logp = torch.empty(B, dtype=torch.float32, device=dev)
+    dh = torch.empty((B, H), dtype=torch.float32, device=dev)
+    if dW is None:
+        dW = torch.zeros((H, M), dtype=torch.float32, device=dev)
+    if dbias is None:
+        dbias = torch.zeros(M, dtype=torch.float32, device=dev)
+    dscales = torch.zeros(M, dtype=torch.float32, device=dev) if want_dscales else None
+    g_logp = _prep_g(g_logp, B, dev, "dense_kmn_forward_backward")
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_dense_kmn_forward_backward_x(
+            M, d, H, _lib.ptr(h), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(y), y.shape[0], _lib.ptr(locs), _lib.ptr(scales),
+            _lib.ptr(g_logp), ctypes.c_float(g_scale), _lib.ptr(logp), _lib.ptr(dh), _lib.ptr(dW), _lib.ptr(dbias),
+            _lib.ptr(dscales), _lib.ptr(logp_sum), B, _xf(xform), _lib.current_stream(dev)))
+    return logp, dh, dW, dbias, dscales
+
+
 def _draws_operands(h, W, bias, y, P, n_dims, what):
     h = _aligned(_as_f32_cuda(h, "h"))
     dev = h.device

@@ -114,6 +114,10 @@ def test_runtime_specialiser_compiles_without_gpu(nfn_lib):
     assert nfn_lib.nfn_jit_dense_mdn_compile_check(7, 3, 32, 0) > 10_000, nfn_lib.nfn_last_error()
     assert nfn_lib.nfn_jit_dense_mdn_compile_check(20, 2, 16, 1) > 10_000, nfn_lib.nfn_last_error()
     assert nfn_lib.nfn_jit_dense_mdn_compile_check(200, 2, 16, 0) < 0   # a 1000-column tile does not fit shared memory
+    # ... and the fused Dense(P)+KMN kernel (head with its own shared-memory state)
+    assert nfn_lib.nfn_jit_dense_kmn_compile_check(60, 1, 16, 0) > 10_000, nfn_lib.nfn_last_error()
+    assert nfn_lib.nfn_jit_dense_kmn_compile_check(24, 3, 32, 1) > 10_000, nfn_lib.nfn_last_error()
+    assert nfn_lib.nfn_jit_dense_kmn_compile_check(2000, 1, 16, 0) < 0
 
 
 def test_missing_library_is_loud(monkeypatch, tmp_path):

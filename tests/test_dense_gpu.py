@@ -271,3 +271,108 @@ def test_mdn_estimator_uses_the_fused_layer(cuda_device, nfn_lib):
     assert len(g0) == len(g1) and len(g0) >= 6
     for a_, b_ in zip(g0, g1):
         assert float((a_ - b_).abs().max()) <= 2e-4 * max(1e-3, float(b_.abs().max()))
+
+
+# ----------------------------------------------------------------------------- fused Dense(P) + KMN head
+KMN_CASES = [
+    # (kernels M, d, H) -- the first has an ahead-of-time instance, the rest are runtime-specialised
+    (100, 1, 16),   # the reference's default KernelMixtureNetwork: 50 centres x 2 bandwidths
+    (60, 1, 16),    # its build_function default: 30 x 2
+    (24, 3, 32),
+    (7, 2, 48),     # odd width: scalar logit access
+]
+
+
+@pytest.mark.parametrize("case", range(len(KMN_CASES)))
+@pytest.mark.parametrize("B", [1, 100, 128 * 5 + 77, 20_000])
+def test_dense_kmn_vs_oracle(cuda_device, nfn_lib, case, B):
+    """Dense(P) + kernel-mixture head in one kernel against the float64 oracle composed with float64 matmuls
+    (reference MaximumLikelihoodNNEstimator.py:43 + DistributionLayers.py:118-133), negative bandwidths included."""
+    from normalizingflownetwork_b200 import functional as F
+
+    M, d, H = KMN_CASES[case]
+    assert F.dense_kmn_supported(H, M, d)
+    rng = np.random.default_rng(7000 * case + B)
+    h = np.tanh(rng.normal(0, 1.0, (B, H))).astype(np.float32)
+    W = (rng.normal(0, 1.0, (H, M)) / np.sqrt(H)).astype(np.float32)
+    b = rng.normal(0, 0.5, (M,)).astype(np.float32)
+    y = rng.normal(0, 1.0, (B, d)).astype(np.float32)
+    locs = rng.normal(0, 1.0, (M, d)).astype(np.float32)
+    scales = (rng.uniform(0.3, 0.9, (M,)) * rng.choice([-1.0, 1.0], (M,))).astype(np.float32)
+    up = rng.normal(0, 1.0, (B,)).astype(np.float32)
+    t = h.astype(np.float64) @ W.astype(np.float64) + b.astype(np.float64)
+    ref_lp, dt, ref_dsc, _ = an.kmn_forward_backward(t, y, locs, scales, upstream=up * 0.5)
+    ref_dh, ref_dW, ref_db = dt @ W.astype(np.float64).T, h.astype(np.float64).T @ dt, dt.sum(0)
+    dev = lambda x: torch.tensor(x, device=cuda_device)
+    lsum = torch.zeros(1, dtype=torch.float64, device=cuda_device)
+    lp, dh, dW, db, dsc = F.dense_kmn_forward_backward(dev(h), dev(W), dev(b), dev(y), dev(locs), dev(scales),
+                                                      g_logp=dev(up), g_scale=0.5, logp_sum=lsum)
+    assert rel(lp.cpu().numpy(), ref_lp) <= 1e-5
+    assert rel(dh.cpu().numpy(), ref_dh) <= 1e-4
+    assert np.abs(dW.cpu().numpy() - ref_dW).max() <= 1e-4 * max(1.0, np.abs(ref_dW).max())
+    assert np.abs(db.cpu().numpy() - ref_db).max() <= 1e-4 * max(1.0, np.abs(ref_db).max())
+    assert np.abs(dsc.cpu().numpy() - ref_dsc).max() <= 1e-4 * max(1.0, np.abs(ref_dsc).max()) * max(1.0, B ** 0.5 / 8)
+    assert abs(lsum.item() - lp.double().sum().item()) <= 1e-9 * np.abs(ref_lp).sum() + 1e-6
+    lp_f = F.dense_kmn_forward(dev(h), dev(W), dev(b), dev(y), dev(locs), dev(scales))
+    assert rel(lp_f.cpu().numpy(), ref_lp) <= 1e-5
+    got_b = F.dense_kmn_forward(dev(h), dev(W), dev(b), dev(y[:1]), dev(locs), dev(scales)).cpu().numpy()
+    assert rel(got_b, an.kmn_forward_backward(t, y[:1], locs, scales, need_grad=False)) <= 1e-5
+    # fixed bandwidths: no gradient buffer
+    out = F.dense_kmn_forward_backward(dev(h), dev(W), dev(b), dev(y), dev(locs), dev(scales), g_logp=dev(up), g_scale=0.5,
+                                       want_dscales=False)
+    assert out[4] is None and torch.allclose(out[0], lp)
+
+
+def test_dense_kmn_equals_unfused_composition(cuda_device, nfn_lib):
+    """Same answer as float64 matmul + the streaming KMN kernel (identical row arithmetic: nfn_mixture_row.cuh) on a
+    ragged multi-tile batch, with the estimators' y pipeline."""
+    from normalizingflownetwork_b200 import functional as F
+
+    M, d, H, B = 100, 1, 16, 150_001
+    g = torch.Generator(device=cuda_device).manual_seed(19)
+    h = torch.tanh(torch.randn((B, H), generator=g, device=cuda_device))
+    W = torch.randn((H, M), generator=g, device=cuda_device) * 0.25
+    b = torch.randn(M, generator=g, device=cuda_device) * 0.3
+    y = torch.randn((B, d), generator=g, device=cuda_device) * 2.0 + 1.0
+    locs = torch.randn((M, d), generator=g, device=cuda_device)
+    scales = torch.rand(M, generator=g, device=cuda_device) * 0.5 + 0.3
+    xf = F.make_xform(d, mean=[1.0], std=[2.0], logp_shift=-float(np.log(2.0)))
+    t = (h.double() @ W.double() + b.double()).float()
+    lp_u, dt_u, _, dsc_u = F.kmn_forward_backward(t, y, locs, scales, g_scale=-1.0 / B, xform=xf)
+    lp, dh, dW, db, dsc = F.dense_kmn_forward_backward(h, W, b, y, locs, scales, g_scale=-1.0 / B, xform=xf)
+    assert torch.allclose(lp, lp_u, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(dh * B, (dt_u.double() @ W.double().T).float() * B, rtol=1e-4, atol=1e-4)
+    dW_ref, db_ref = (h.double().T @ dt_u.double()).float(), dt_u.double().sum(0).float()
+    assert (dW - dW_ref).abs().max() <= 1e-4 * dW_ref.abs().max()
+    assert (db - db_ref).abs().max() <= 1e-4 * db_ref.abs().max()
+    assert (dsc - dsc_u).abs().max() <= 1e-4 * max(1e-6, float(dsc_u.abs().max()))
+
+
+def test_kmn_estimator_uses_the_fused_layer(cuda_device, nfn_lib):
+    """KernelMixtureNetwork: log_pdf and the training step's gradients (bandwidths included) through the fused
+    Dense(P)+KMN kernel equal the unfused path on the same weights."""
+    from normalizingflownetwork_b200.estimators import KernelMixtureNetwork
+
+    rng = np.random.default_rng(13)
+    x = rng.normal(0, 1, (4096, 1)).astype(np.float32)
+    y = (np.sin(x) + 0.3 * rng.normal(0, 1, (4096, 1))).astype(np.float32)
+    torch.manual_seed(5)
+    m = KernelMixtureNetwork.build_function(n_dims=1, n_centers=30, hidden_sizes=(16, 16), activation="tanh")
+    m.fit(x, y, batch_size=1024, epochs=2, verbose=0)
+    assert m._fusable_last_layer() is not None
+    lp_f = torch.as_tensor(m.log_pdf(x, y)).cpu()
+    m.fuse_last_layer = False
+    lp_u = torch.as_tensor(m.log_pdf(x, y)).cpu()
+    assert torch.allclose(lp_f, lp_u, rtol=1e-5, atol=1e-5)
+    m.optimizer = torch.optim.SGD(m.parameters(), lr=0.0)
+    xd, yd = m._to_dev(x), m._to_dev(y)
+    grads = []
+    for fuse in (True, False):
+        m.fuse_last_layer = fuse
+        loss = float(m.train_step(xd, yd))
+        grads.append((loss, {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}))
+    (l0, g0), (l1, g1) = grads
+    assert abs(l0 - l1) <= 1e-5 * max(1.0, abs(l1))
+    assert set(g0) == set(g1) and len(g0) >= 7        # three layers' weights and biases + the bandwidths
+    for n in g0:
+        assert float((g0[n] - g1[n]).abs().max()) <= 2e-4 * max(1e-3, float(g1[n].abs().max())), n
