@@ -349,6 +349,39 @@ int nfn_variational_sample_backward(const float* params, const float* prior_loc,
                                     const float* dw, const float* g_kl, int n, int draws, float* dparams,
                                     float* dprior_loc, void* stream);
 /*
+ * One S-draw training step of a Bayesian estimator with ONE hidden variational layer, network part, in a single call
+ * (BayesianNNEstimator.py:103-146 with the Monte-Carlo draws of :65-76 folded into the batch; BASELINE config 4):
+ *   weight samples + exact KL of both tfp.layers.DenseVariational layers   (nfn_variational_sample)
+ *   first layer over the draws * rows_per_draw folded rows                  (nfn_dense_act_forward_draws)
+ *   emitting layer + density head + both backward GEMMs, per-draw weights   (nfn_dense_chain / _mdn _draws_x)
+ *   first layer's per-draw weight gradient                                  (nfn_dense_act_backward_draws)
+ *   gradients of the posterior parameters through the samples and the KL    (nfn_variational_sample_backward)
+ * Seven launches, no host work between them -- what an eager framework spends ~0.7 ms of dispatch on.  The caller
+ * supplies the standard-normal draws eps (so that its own generator stays the source of randomness), the workspaces
+ * and the gradient buffers (+=).  head: mdn_centers == 0 -> the flow chain `desc`, else an MDN with that many centres
+ * of desc->n_dims dimensions.  hidden_width: row width of h / dh (units rounded up to 16).
+ */
+typedef struct nfn_variational_layer {
+  const float* posterior;   /* [2 n]: loc | raw scale */
+  const float* prior_loc;   /* [n] */
+  const float* eps;         /* [draws, n] */
+  float* w;                 /* [draws, n]  workspace: the samples, flat [kernel | bias] per draw */
+  float* dw;                /* [draws, n]  workspace: their gradient (zeroed by the call) */
+  float* dposterior;        /* [2 n] += */
+  float* dprior_loc;        /* [n] += , or NULL (fixed prior) */
+  double* kl;               /* device scalar += KL(q || prior), or NULL */
+  float prior_scale;
+  float kl_grad;            /* d loss / d KL of this layer (kl_weight / world size) */
+  int32_t n;                /* inputs * units + units */
+  int32_t reserved;
+} nfn_variational_layer;
+
+int nfn_bayes_train_step(const nfn_chain_desc* desc, int mdn_centers, int draws, int64_t rows_per_draw, int in_features,
+                         int units, int hidden_width, int act, const float* x, const float* x_mean, const float* x_std,
+                         const float* y, int64_t y_rows, const nfn_variational_layer* first,
+                         const nfn_variational_layer* emitting, float g_scale, float* h, float* dh, float* logp,
+                         double* logp_sum, const nfn_event_xform* xf, void* stream);
+/*
  * The emitting Dense(P) layer fused into the MDN head: replaces `Dense(output_size, "linear")`
  * (MaximumLikelihoodNNEstimator.py:43) + GaussianMixtureLayer's log_prob (DistributionLayers.py:196-212) + their
  * tape gradients, P = n_centers * (2 n_dims + 1).  Same contract as nfn_dense_chain_*_x: t = h W + bias is formed

@@ -31,6 +31,14 @@ class ChainDesc(ctypes.Structure):
     ]
 
 
+class VariationalLayer(ctypes.Structure):
+    """nfn_variational_layer (include/nfn_b200.h): one DenseVariational layer's operands for nfn_bayes_train_step."""
+    _fields_ = [("posterior", ctypes.c_void_p), ("prior_loc", ctypes.c_void_p), ("eps", ctypes.c_void_p),
+                ("w", ctypes.c_void_p), ("dw", ctypes.c_void_p), ("dposterior", ctypes.c_void_p),
+                ("dprior_loc", ctypes.c_void_p), ("kl", ctypes.c_void_p), ("prior_scale", ctypes.c_float),
+                ("kl_grad", ctypes.c_float), ("n", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
 class EventXform(ctypes.Structure):
     """struct nfn_event_xform (include/nfn_b200.h): y normalisation / noise / Jacobian shift / exp fused into a head."""
 
@@ -148,6 +156,11 @@ SIGNATURES = {
                                                  _c_float_p, ctypes.c_float, _c_float_p, _c_float_p,
                                                  _c_float_p, ctypes.c_void_p, _c_float_p, _i64, _xf_p,
                                                  ctypes.c_void_p]),
+    "nfn_bayes_train_step": (ctypes.c_int, [ctypes.POINTER(ChainDesc), ctypes.c_int, ctypes.c_int, _i64, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p,
+                                           _c_float_p, _i64, ctypes.POINTER(VariationalLayer),
+                                           ctypes.POINTER(VariationalLayer), ctypes.c_float, _c_float_p, _c_float_p,
+                                           _c_float_p, ctypes.c_void_p, _xf_p, ctypes.c_void_p]),
     "nfn_variational_sample": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_float, _c_float_p, ctypes.c_int,
                                              ctypes.c_int, _c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
     "nfn_variational_sample_backward": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_float, _c_float_p, _c_float_p,

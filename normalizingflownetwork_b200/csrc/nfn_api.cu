@@ -660,8 +660,8 @@ int nfn_variational_sample(const float* params, const float* prior_loc, float pr
   if (n < 1 || draws < 1) return set_error(NFN_ERR_SHAPE, "n=%d draws=%d", n, draws);
   if (!(prior_scale > 0.0f)) return set_error(NFN_ERR_DESC, "prior_scale must be positive");
   if (!params || !prior_loc || !eps || !w) return set_error(NFN_ERR_NULL, "params, prior_loc, eps and w must be non-NULL");
-  return launch_variational(false, params, prior_loc, prior_scale, eps, nullptr, nullptr, n, draws, w, kl, nullptr, nullptr,
-                            (cudaStream_t)stream);
+  return launch_variational(false, params, prior_loc, prior_scale, eps, nullptr, nullptr, 0.0f, n, draws, w, kl, nullptr,
+                            nullptr, (cudaStream_t)stream);
 }
 
 int nfn_variational_sample_backward(const float* params, const float* prior_loc, float prior_scale, const float* eps,
@@ -671,8 +671,75 @@ int nfn_variational_sample_backward(const float* params, const float* prior_loc,
   if (!(prior_scale > 0.0f)) return set_error(NFN_ERR_DESC, "prior_scale must be positive");
   if (!params || !prior_loc || !dparams) return set_error(NFN_ERR_NULL, "params, prior_loc and dparams must be non-NULL");
   if (dw && !eps) return set_error(NFN_ERR_NULL, "eps must accompany dw");
-  return launch_variational(true, params, prior_loc, prior_scale, eps, dw, g_kl, n, draws, nullptr, nullptr, dparams,
+  return launch_variational(true, params, prior_loc, prior_scale, eps, dw, g_kl, 0.0f, n, draws, nullptr, nullptr, dparams,
                             dprior_loc, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ one S-draw Bayesian training step, network part
+static int dense_mdn_dispatch(int K, int d, int hidden, const DenseArgs& a, bool bwd, cudaStream_t st);
+
+int nfn_bayes_train_step(const nfn_chain_desc* desc, int mdn_centers, int draws, int64_t rows_per_draw, int in_features,
+                         int units, int hidden_width, int act, const float* x, const float* x_mean, const float* x_std,
+                         const float* y, int64_t y_rows, const nfn_variational_layer* first,
+                         const nfn_variational_layer* emitting, float g_scale, float* h, float* dh, float* logp,
+                         double* logp_sum, const nfn_event_xform* xf, void* stream) {
+  int rc = check_desc(desc);
+  if (rc != NFN_OK) return rc;
+  if ((rc = draws_common(draws, rows_per_draw, y_rows)) != NFN_OK) return rc;
+  if ((rc = act_draws_common(x, x_mean, x_std, draws, rows_per_draw, in_features, units, hidden_width, act)) < 0) return rc;
+  if (hidden_width % 16 != 0 || hidden_width < 16 || hidden_width > 64)
+    return set_error(NFN_ERR_UNSUPPORTED, "hidden_width=%d must be 16, 32, 48 or 64", hidden_width);
+  if (mdn_centers < 0 || mdn_centers > 4096) return set_error(NFN_ERR_DESC, "mdn_centers=%d", mdn_centers);
+  const int P = mdn_centers > 0 ? mdn_centers * (2 * desc->n_dims + 1) : param_size(desc);
+  if (P < 1) return set_error(NFN_ERR_UNSUPPORTED, "the head has no parameters to emit");
+  if (!first || !emitting) return set_error(NFN_ERR_NULL, "both layers must be given");
+  if (first->n != in_features * units + units || emitting->n != units * P + P)
+    return set_error(NFN_ERR_SHAPE, "layer sizes %d / %d do not match %d -> %d -> %d", first->n, emitting->n, in_features, units, P);
+  const nfn_variational_layer* ls[2] = {first, emitting};
+  for (const nfn_variational_layer* l : ls) {
+    if (!l->posterior || !l->prior_loc || !l->eps || !l->w || !l->dw || !l->dposterior)
+      return set_error(NFN_ERR_NULL, "posterior, prior_loc, eps, w, dw and dposterior must be non-NULL");
+    if (!(l->prior_scale > 0.0f)) return set_error(NFN_ERR_DESC, "prior_scale must be positive");
+  }
+  if (rows_per_draw == 0) return NFN_OK;
+  if (!y || !h || !dh || !logp) return set_error(NFN_ERR_NULL, "y, h, dh and logp must be non-NULL");
+  if (!aligned(h, 16) || !aligned(dh, 16)) return set_error(NFN_ERR_ALIGN, "h and dh must be 16-byte aligned");
+  if (!aligned(y, event_align(desc->n_dims)))
+    return set_error(NFN_ERR_ALIGN, "y must be %zu-byte aligned", event_align(desc->n_dims));
+  cudaStream_t st = (cudaStream_t)stream;
+  // 1. the samples and the KL terms
+  for (const nfn_variational_layer* l : ls)
+    if ((rc = launch_variational(false, l->posterior, l->prior_loc, l->prior_scale, l->eps, nullptr, nullptr, 0.0f, l->n, draws,
+                                 l->w, l->kl, nullptr, nullptr, st)) != NFN_OK)
+      return rc;
+  // 2. first layer over the folded rows
+  if ((rc = launch_dense_act_draws(false, x, x_mean, x_std, first->w, nullptr, nullptr, h, nullptr, draws, rows_per_draw,
+                                   in_features, units, hidden_width, act, st)) != NFN_OK)
+    return rc;
+  // 3. emitting layer + head, weights and their gradient in the layer's own flat layout
+  cudaError_t ce = cudaMemsetAsync(emitting->dw, 0, sizeof(float) * (size_t)draws * emitting->n, st);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(first->dw, 0, sizeof(float) * (size_t)draws * first->n, st);
+  if (ce != cudaSuccess) return cuda_error(ce, "bayes_train_step memset");
+  DenseArgs a{};
+  a.h = h; a.W = emitting->w; a.bias = emitting->w; a.y = y; a.logp = logp; a.dh = dh; a.dW = emitting->dw;
+  a.dbias = emitting->dw; a.logp_sum = logp_sum; a.B = (int64_t)draws * rows_per_draw; a.g_scale = g_scale;
+  a.y_broadcast = (y_rows == 1 && rows_per_draw != 1);
+  a.draws = draws; a.rows_per_draw = rows_per_draw;
+  a.flat_rows = units; a.flat_stride = emitting->n;
+  if ((rc = set_xform(a.xf, xf, desc->n_dims)) != NFN_OK) return rc;
+  rc = mdn_centers > 0 ? dense_mdn_dispatch(mdn_centers, desc->n_dims, hidden_width, a, true, st)
+                       : dense_draws_dispatch(desc, hidden_width, a, true, st);
+  if (rc != NFN_OK) return rc;
+  // 4. first layer's per-draw weight gradient
+  if ((rc = launch_dense_act_draws(true, x, x_mean, x_std, nullptr, h, dh, nullptr, first->dw, draws, rows_per_draw,
+                                   in_features, units, hidden_width, act, st)) != NFN_OK)
+    return rc;
+  // 5. through the samples (and the KL) to the posterior parameters
+  for (const nfn_variational_layer* l : ls)
+    if ((rc = launch_variational(true, l->posterior, l->prior_loc, l->prior_scale, l->eps, l->dw, nullptr, l->kl_grad, l->n,
+                                 draws, nullptr, nullptr, l->dposterior, l->dprior_loc, st)) != NFN_OK)
+      return rc;
+  return NFN_OK;
 }
 
 int64_t nfn_jit_dense_tc5_compile_check(const nfn_chain_desc* desc, int hidden, int accurate) {

@@ -487,7 +487,7 @@ int launch_dense_act_draws(bool bwd, const float* x, const float* xmean, const f
 
 // mean-field weight posterior: S samples + exact KL, and their gradient (nfn_variational.cu)
 int launch_variational(bool bwd, const float* params, const float* prior_loc, float prior_scale, const float* eps,
-                       const float* dw, const float* gkl, int n, int S, float* w, double* kl, float* dparams,
+                       const float* dw, const float* gkl, float gkl_value, int n, int S, float* w, double* kl, float* dparams,
                        float* dprior_loc, cudaStream_t st);
 
 }  // namespace nfn

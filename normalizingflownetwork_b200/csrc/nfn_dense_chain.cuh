@@ -43,6 +43,12 @@ struct DenseArgs {
   // draws <= 1: one weight set for all B rows.
   int draws;
   long long rows_per_draw;
+  // Per-draw weights in tfp DenseVariational's FLAT sample layout (flat_rows > 0): draw s owns flat_stride floats at
+  // W + s * flat_stride = [kernel (flat_rows x P) | bias (P)], flat_rows <= H (rows flat_rows .. H of the operand are
+  // zero, matching the zero columns of a padded hidden row); dW has the same layout and receives the bias gradient
+  // behind the kernel's.  `bias` / `dbias` are ignored then.
+  int flat_rows;
+  long long flat_stride;
   // KMN head only: fixed centres [M][d], shared bandwidths [M] (may be negative), their gradient [M] += (nullable)
   const float* locs;
   const float* scales;
@@ -276,19 +282,20 @@ NFN_DEVI void dense_head_body(const DenseArgs& a) {
   auto fold0_of = [&](long long t) -> long long { return draw_of(t) * Bd + rd0_of(t); };
 
   // weights, bias (zero-padded to P8 columns) of one draw
+  const int w_rows = a.flat_rows > 0 ? a.flat_rows : H;
   auto stage_weights = [&](long long s) {
-    const float* Ws = a.W + s * (long long)(H * P);
-    const float* bs = a.bias + s * (long long)P;
+    const float* Ws = a.flat_rows > 0 ? a.W + s * a.flat_stride : a.W + s * (long long)(H * P);
+    const float* bs = a.flat_rows > 0 ? Ws + a.flat_rows * P : a.bias + s * (long long)P;
     for (int i = tid; i < H * PW; i += T) {
       const int k = i / PW, n = i % PW;
-      sW[i] = (n < P) ? __ldg(Ws + k * P + n) : 0.0f;
+      sW[i] = (n < P && k < w_rows) ? __ldg(Ws + k * P + n) : 0.0f;
     }
     for (int i = tid; i < P8; i += T) sB[i] = (i < P) ? __ldg(bs + i) : 0.0f;
   };
   // per-warp partial sums of dW / db -> global (one atomic per entry per CTA and draw), then cleared
   auto flush_grads = [&](long long s) {
-    float* dWs = a.dW + s * (long long)(H * P);
-    float* dbs = a.dbias + s * (long long)P;
+    float* dWs = a.flat_rows > 0 ? a.dW + s * a.flat_stride : a.dW + s * (long long)(H * P);
+    float* dbs = a.flat_rows > 0 ? dWs + a.flat_rows * P : a.dbias + s * (long long)P;
     for (int i = tid; i < H * P8; i += T) {
       const int k = i / P8, n = i % P8;
       float v = 0.0f;
@@ -297,7 +304,7 @@ NFN_DEVI void dense_head_body(const DenseArgs& a) {
         v += sAcc[w * (H * P8) + i];
         sAcc[w * (H * P8) + i] = 0.0f;
       }
-      if (n < P) atomicAdd(dWs + k * P + n, v);
+      if (n < P && k < w_rows) atomicAdd(dWs + k * P + n, v);
     }
     for (int n = tid; n < P8; n += T) {
       float v = 0.0f;

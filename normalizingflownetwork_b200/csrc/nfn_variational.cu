@@ -53,9 +53,10 @@ __global__ void __launch_bounds__(kVT) variational_fwd(const float* __restrict__
 
 __global__ void __launch_bounds__(kVT) variational_bwd(const float* __restrict__ params, const float* __restrict__ prior_loc,
                                                      float prior_scale, const float* __restrict__ eps,
-                                                     const float* __restrict__ dw, const float* __restrict__ gkl, int n, int S,
-                                                     float* __restrict__ dparams, float* __restrict__ dprior_loc) {
-  const float g = gkl ? __ldg(gkl) : 0.0f;
+                                                     const float* __restrict__ dw, const float* __restrict__ gkl, float gkl_value,
+                                                     int n, int S, float* __restrict__ dparams,
+                                                     float* __restrict__ dprior_loc) {
+  const float g = gkl ? __ldg(gkl) : gkl_value;
   const float inv_sr2 = 1.0f / (prior_scale * prior_scale);
   for (int i = blockIdx.x * kVT + threadIdx.x; i < n; i += gridDim.x * kVT) {
     const float loc = __ldg(params + i);
@@ -79,12 +80,12 @@ __global__ void __launch_bounds__(kVT) variational_bwd(const float* __restrict__
 }  // namespace
 
 int launch_variational(bool bwd, const float* params, const float* prior_loc, float prior_scale, const float* eps,
-                       const float* dw, const float* gkl, int n, int S, float* w, double* kl, float* dparams,
+                       const float* dw, const float* gkl, float gkl_value, int n, int S, float* w, double* kl, float* dparams,
                        float* dprior_loc, cudaStream_t st) {
   int blocks = (n + kVT - 1) / kVT;
   if (blocks > 64) blocks = 64;
   if (blocks < 1) blocks = 1;
-  if (bwd) variational_bwd<<<blocks, kVT, 0, st>>>(params, prior_loc, prior_scale, eps, dw, gkl, n, S, dparams, dprior_loc);
+  if (bwd) variational_bwd<<<blocks, kVT, 0, st>>>(params, prior_loc, prior_scale, eps, dw, gkl, gkl_value, n, S, dparams, dprior_loc);
   else variational_fwd<<<blocks, kVT, 0, st>>>(params, prior_loc, prior_scale, eps, n, S, w, kl);
   count_launch();
   return cuda_error(cudaGetLastError(), bwd ? "variational_bwd" : "variational_fwd");

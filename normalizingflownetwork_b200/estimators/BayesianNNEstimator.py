@@ -278,6 +278,53 @@ class BayesianNNEstimator(BaseEstimator):
             dw2 = torch.cat([dW2[:, :l2.in_features, :].reshape(S, nk), db2], dim=1)
         return (w1, w2), (dw1, dw2)
 
+    def _one_call_step(self, plan, xb, y, S, g_scale, logp_sum, xform, world):
+        """The network part of the step as ONE library call (nfn_bayes_train_step): no autograd graph, no per-kernel
+        dispatch; gradients are accumulated straight into the posterior parameters' .grad (which must exist)."""
+        from ..DistributionLayers import GaussianMixtureLayer
+
+        l1, l2, hp, act = plan
+        x = self._to_dev(xb)
+        B = x.shape[0]
+        n1, n2 = l1.prior_loc.numel(), l2.prior_loc.numel()
+        ws = getattr(self, "_bayes_ws", None)
+        if ws is None or ws["key"] != (S, B, hp, n1, n2):
+            f32 = dict(dtype=torch.float32, device=self.device)
+            ws = dict(key=(S, B, hp, n1, n2), w1=torch.empty((S, n1), **f32), w2=torch.empty((S, n2), **f32),
+                      dw1=torch.empty((S, n1), **f32), dw2=torch.empty((S, n2), **f32), h=torch.empty((S * B, hp), **f32),
+                      dh=torch.empty((S * B, hp), **f32), logp=torch.empty(S * B, **f32),
+                      kl=torch.zeros(2, dtype=torch.float64, device=self.device))
+            self._bayes_ws = ws
+        ws["kl"].zero_()
+        gen = self._weight_generator()
+        ops = []
+        for l, n in ((l1, n1), (l2, n2)):
+            if l.posterior_params.grad is None:
+                l.posterior_params.grad = torch.zeros_like(l.posterior_params)
+            if l.prior_loc.requires_grad and l.prior_loc.grad is None:
+                l.prior_loc.grad = torch.zeros_like(l.prior_loc)
+            ops.append(dict(posterior=l.posterior_params.detach(), prior_loc=l.prior_loc.detach(),
+                            eps=torch.randn((S, n), device=self.device, generator=gen),
+                            dposterior=l.posterior_params.grad,
+                            dprior_loc=l.prior_loc.grad if l.prior_loc.requires_grad else None,
+                            prior_scale=l.prior_scale, kl_grad=l.kl_weight / world))
+        layer = self.dist_layer
+        mdn = isinstance(layer, GaussianMixtureLayer)
+        f32c = lambda t: t.to(device=self.device, dtype=torch.float32).contiguous()
+        x, y = f32c(x), f32c(y)
+        F.bayes_train_step(x, y, ops[0], ops[1], l1.units, act, hp, S, g_scale, ws, logp_sum,
+                           flow_types=None if mdn else layer._flow_types, n_dims=layer._n_dims,
+                           trainable_base_dist=True if mdn else layer._trainable_base_dist,
+                           mdn_centers=layer._n_centers if mdn else 0, x_mean=f32c(self.x_mean), x_std=f32c(self.x_std), xform=xform)
+        kl = ws["kl"].to(torch.float32)
+        l1.last_kl, l2.last_kl = l1.kl_weight * kl[0], l2.kl_weight * kl[1]
+
+    def _one_call_ok(self, plan):
+        l1, l2 = plan[0], plan[1]
+        return (l1.kl_use_exact and l2.kl_use_exact and l1.posterior_params.is_cuda
+                and all(p is l1.posterior_params or p is l2.posterior_params or p is l1.prior_loc or p is l2.prior_loc
+                        for p in self.parameters() if p.requires_grad))
+
     def train_step(self, xb, yb, global_batch=None):
         if self.n_train_draws <= 1 or self.map_mode:
             return super().train_step(xb, yb, global_batch=global_batch)
@@ -290,15 +337,22 @@ class BayesianNNEstimator(BaseEstimator):
         Bg = global_batch or B
         world = dist.get_world_size() if dist.is_initialized() else 1
         reducer = self._grad_reducer() if world > 1 else None
+        plan = self._fused_draws_plan() if B > 0 else None
+        one_call = plan is not None and self._one_call_ok(plan)
         if reducer is not None:
             reducer.zero()
+        elif one_call:
+            self.optimizer.zero_grad(set_to_none=False)   # the library accumulates into the existing buffers
         else:
             self.optimizer.zero_grad(set_to_none=True)
         if B == 0:
             return self._empty_shard_step(reducer, Bg, world, denom=S * Bg)
         logp_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
-        plan = self._fused_draws_plan()
-        if plan is not None:
+        if one_call:
+            y = self._to_dev(yb)
+            self._one_call_step(plan, xb, y, S, -1.0 / (S * Bg), logp_sum, self._xform(y.shape[1], training=True), world)
+            extra = self._extra_loss()
+        elif plan is not None:
             y = self._to_dev(yb)
             ws, dws = self._fused_draws_forward_backward(plan, xb, y, S, -1.0 / (S * Bg), logp_sum,
                                                          self._xform(y.shape[1], training=True))

@@ -380,6 +380,35 @@ def variational_sample(posterior_params, prior_loc, eps, prior_scale):
     return _VariationalSample.apply(posterior_params, prior_loc, eps, float(prior_scale))
 
 
+def bayes_train_step(x, y, first, emitting, units, activation, hidden_width, n_draws, g_scale, ws, logp_sum,
+                     flow_types=None, n_dims=1, trainable_base_dist=True, mdn_centers=0, x_mean=None, x_std=None,
+                     xform=None):
+    """Network part of one S-draw Bayesian training step in ONE library call (nfn_bayes_train_step): samples + KL of
+    both variational layers, first layer over the folded rows, emitting layer + head + backward GEMMs with per-draw
+    weights, first layer's weight gradient, gradients of the posterior parameters.  ``first`` / ``emitting``: dicts
+    with posterior [2n], prior_loc [n], eps [S, n], dposterior [2n] (+=), dprior_loc [n] or None, prior_scale,
+    kl_grad; ``ws``: workspace dict (w1, w2, dw1, dw2, h, dh, logp, kl [2] float64) reused across steps."""
+    lib = _lib.load()
+    dev = x.device
+    desc = _lib.make_desc(flow_types if flow_types is not None else [], n_dims, trainable_base_dist)
+    B, K = x.shape
+    layers = []
+    for i, (l, w, dw) in enumerate(((first, ws["w1"], ws["dw1"]), (emitting, ws["w2"], ws["dw2"]))):
+        v = _lib.VariationalLayer()
+        v.posterior, v.prior_loc, v.eps = l["posterior"].data_ptr(), l["prior_loc"].data_ptr(), l["eps"].data_ptr()
+        v.w, v.dw, v.dposterior = w.data_ptr(), dw.data_ptr(), l["dposterior"].data_ptr()
+        v.dprior_loc = l["dprior_loc"].data_ptr() if l.get("dprior_loc") is not None else None
+        v.kl = ws["kl"].data_ptr() + 8 * i
+        v.prior_scale, v.kl_grad, v.n = float(l["prior_scale"]), float(l["kl_grad"]), int(l["prior_loc"].numel())
+        layers.append(v)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfn_bayes_train_step(
+            ctypes.byref(desc), int(mdn_centers), int(n_draws), B, K, int(units), int(hidden_width), ACT_CODES[activation],
+            _lib.ptr(x), _lib.ptr(x_mean), _lib.ptr(x_std), _lib.ptr(y), y.shape[0], ctypes.byref(layers[0]),
+            ctypes.byref(layers[1]), ctypes.c_float(g_scale), _lib.ptr(ws["h"]), _lib.ptr(ws["dh"]), _lib.ptr(ws["logp"]),
+            _lib.ptr(logp_sum), _xf(xform), _lib.current_stream(dev)))
+
+
 # ----------------------------------------------------------------------------- folded posterior draws
 def dense_act_draws_supported(in_features, units, out_width, activation):
     return (1 <= in_features <= 8 and 1 <= units <= 64 and out_width >= units and out_width % 8 == 0 and out_width <= 64

@@ -84,7 +84,7 @@ def test_bayesian_train_step_on_the_folded_draw_kernels(cuda_device, nfn_lib, no
     x = rng.uniform(-3, 3, (2000, 1)).astype(np.float32)
     y = (np.cos(x) + 0.3 * rng.normal(0, 1, (2000, 1))).astype(np.float32)
     out = []
-    for fuse in (True, False):
+    for fuse in (True, "autograd", False):   # one library call / per-kernel calls under autograd / composed torch path
         if head == "mdn":
             m = BayesMixtureDensityNetwork(1, kl_weight_scale=1.0 / 2000, n_centers=5, hidden_sizes=(10,),
                                            activation="tanh", n_train_draws=8, learning_rate=1e-2,
@@ -93,20 +93,23 @@ def test_bayesian_train_step_on_the_folded_draw_kernels(cuda_device, nfn_lib, no
             m = BayesNormalizingFlowNetwork(1, kl_weight_scale=1.0 / 2000, n_flows=5, hidden_sizes=(10,),
                                             activation="tanh", n_train_draws=8, learning_rate=1e-2,
                                             noise_reg=("fixed_rate", noise))
-        m.fuse_draws = fuse
+        m.fuse_draws = bool(fuse)
+        if fuse == "autograd":
+            m._one_call_ok = lambda plan: False
         m._assign_data_normalization(x, y)
         with torch.no_grad():
             m.params_from_x(x[:2])
         m.optimizer = torch.optim.Adam(m.parameters(), lr=m.learning_rate, eps=1e-7)
         m._wgen = None
-        assert (m._fused_draws_plan() is not None) == fuse or noise > 0.0
+        assert (m._fused_draws_plan() is not None) == bool(fuse) or noise > 0.0
         loss = m.train_step(m._to_dev(x), m._to_dev(y))
         out.append((float(loss), [p.grad.detach().clone() for p in m.parameters() if p.grad is not None]))
-    (l0, g0), (l1, g1) = out
-    assert np.isfinite(l0) and abs(l0 - l1) <= 2e-5 * max(1.0, abs(l1))
-    assert len(g0) == len(g1) and len(g0) >= 2
-    for a, b in zip(g0, g1):
-        assert float((a - b).abs().max()) <= 2e-4 * max(1e-3, float(b.abs().max()))
+    l1, g1 = out[-1]
+    for l0, g0 in out[:-1]:
+        assert np.isfinite(l0) and abs(l0 - l1) <= 2e-5 * max(1.0, abs(l1))
+        assert len(g0) == len(g1) and len(g0) >= 2
+        for a, b in zip(g0, g1):
+            assert float((a - b).abs().max()) <= 2e-4 * max(1e-3, float(b.abs().max()))
 
 
 def test_bayesian_train_step_replays_as_a_cuda_graph(cuda_device, nfn_lib):
