@@ -187,40 +187,59 @@ NFN_DEVI float kmn_row(float* row, const int K, const float (&y)[D], const float
     logp = (top2 - lse2) * kLn2 - (float)D * kHalfLog2Pi;
   }
   if constexpr (BWD) {
-    for (int k0 = 0; k0 < K; k0 += LG) {  // all lanes stay in the loop: warp reduction of d/dscale
-      float lg[LG];
-      if (valid) {
-        ld_vec<LG, LG>(row + k0, lg);
-      } else {
+    // Kernels in blocks of 32: every lane first forms its row's 32 bandwidth-gradient terms, then ONE butterfly
+    // reduce-scatter (16 + 8 + 4 + 2 + 1 = 31 shuffles) leaves lane L with the warp's sum for kernel kb + L -- instead
+    // of a 5-shuffle all-reduce per kernel (160 per block), which was most of this pass.  All lanes stay in the loops.
+    const unsigned lane = threadIdx.x & 31u;
+    for (int kb = 0; kb < K; kb += 32) {
+      float wv[32];
 #pragma unroll
-        for (int j = 0; j < LG; ++j) lg[j] = 0.0f;
-      }
+      for (int gq = 0; gq < 32 / LG; ++gq) {
+        const int k0 = kb + gq * LG;
+        float lg[LG];
+        const bool live = valid && k0 < K;     // (K % LG == 0: a group is inside or outside as a whole)
+        if (live) {
+          ld_vec<LG, LG>(row + k0, lg);
+        } else {
 #pragma unroll
-      for (int j = 0; j < LG; ++j) {
-        const int k = k0 + j;
-        float wsc = 0.0f;
-        if (valid) {
-          float q = 0.0f, dl[D];
+          for (int j = 0; j < LG; ++j) lg[j] = 0.0f;
+        }
 #pragma unroll
-          for (int i = 0; i < D; ++i) {
-            dl[i] = y[i] - s_loc[k * D + i];
-            q = fmaf(dl[i], dl[i], q);
+        for (int j = 0; j < LG; ++j) {
+          const int k = k0 + j;
+          float wsc = 0.0f;
+          if (live) {
+            float q = 0.0f, dl[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+              dl[i] = y[i] - s_loc[k * D + i];
+              q = fmaf(dl[i], dl[i], q);
+            }
+            const float l2 = lg[j] * kLog2e;
+            const float crho = cot * M::ex2(l2 + fmaf(s_coef[k], q, s_lnorm[k]) - top2);
+            lg[j] = fmaf(-cot, M::ex2(l2 - lse2), crho);
+            const float c2 = -2.0f * kLn2 * s_coef[k];        // 1 / s^2
+#pragma unroll
+            for (int i = 0; i < D; ++i) dy[i] -= crho * dl[i] * c2;
+            wsc = crho * fmaf(q, c2, -(float)D);               // * 1/s applied when the sums are flushed
           }
-          const float l2 = lg[j] * kLog2e;
-          const float crho = cot * M::ex2(l2 + fmaf(s_coef[k], q, s_lnorm[k]) - top2);
-          lg[j] = fmaf(-cot, M::ex2(l2 - lse2), crho);
-          const float c2 = -2.0f * kLn2 * s_coef[k];        // 1 / s^2
-#pragma unroll
-          for (int i = 0; i < D; ++i) dy[i] -= crho * dl[i] * c2;
-          wsc = crho * fmaf(q, c2, -(float)D);               // * 1/s applied when the sums are flushed
+          wv[gq * LG + j] = wsc;
         }
-        if (my_dsc) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) wsc += __shfl_xor_sync(0xffffffffu, wsc, o);
-          if ((threadIdx.x & 31) == 0) my_dsc[k] += wsc;
-        }
+        if (live) st_vec<LG, LG>(row + k0, lg);
       }
-      if (valid) st_vec<LG, LG>(row + k0, lg);
+      if (my_dsc) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool up = (lane & off) != 0;    // this lane keeps the upper half of what it still holds
+#pragma unroll
+          for (int i = 0; i < off; ++i) {
+            const float send = up ? wv[i] : wv[i + off];
+            const float keep = up ? wv[i + off] : wv[i];
+            wv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        if (kb + (int)lane < K) my_dsc[kb + lane] += wv[0];
+      }
     }
   }
   return logp;
