@@ -141,11 +141,11 @@ int nfn_chain_forward_backward(const nfn_chain_desc* desc, const float* t, const
  * sequence.  want_colsum = 0 skips the in-kernel column sums (their slots stay 0).
  *
  * Split-phase mode (nfn_peer_set_deferred(comm, 1)): a launch leaves its totals in local accumulators;
- * the NEXT launch on the communicator sends them to the peers from its head (one warp, behind its first
- * loads) and collects the cross-rank sums at its tail, into the `reduced` pointer the earlier call was
- * given.  `reduced` of call k is therefore complete when call k+1 (or nfn_peer_flush) completes.  The
- * NVLink round trip and up to one kernel duration of rank skew overlap with a whole kernel of tile work,
- * and no kernel's completion waits for remote stores of its own.
+ * ONE CTA of the NEXT launch's grid on the communicator (it carries no tiles) pushes them to the peers, collects
+ * the peers' totals, writes the cross-rank sums into the `reduced` pointer the earlier call was given, and exits.
+ * `reduced` of call k is therefore complete when call k+1 (or nfn_peer_flush) completes.  The NVLink round trip
+ * and up to one kernel duration of rank skew overlap with a whole kernel of tile work on the other CTAs, and
+ * nothing sits at any kernel's tail: no kernel's completion waits for remote stores of its own.
  *
  * Communicator set-up (see normalizingflownetwork_b200/parallel.py:PeerComm):
  *   nfn_peer_alloc        cudaMalloc + zero one region, export its 64-byte cudaIpc handle
@@ -475,6 +475,10 @@ int nfn_set_math_mode(int accurate);
  *                                                                         (NFN_B200_CHAIN_IO=cpasync|tma)
  *   "dense_mma"     0 auto | 1 tcgen05 | 2 mma.sync                       (NFN_B200_DENSE_MMA=tc5|sync)
  *   "pdl"           0: no programmatic dependent launch                   (NFN_B200_PDL=0)
+ *   "mlp_mma"       0: hidden layers' backward on the scalar kernels only  (NFN_B200_MLP_MMA=0)
+ *   "host_chunk_mb" chunk size of the *_host pipelines, 1..1024 (default 16) (NFN_B200_HOST_CHUNK_MB)
+ *   "debug"         1: launch geometry of the fused kernels on stderr       (NFN_B200_DEBUG)
+ *   "tune_wnb", "tune_wwarps"  geometry overrides of the runtime-specialised warp-tile kernels (tools only)
  * Unknown names return NFN_ERR_DESC. */
 int nfn_set_option(const char* name, int value);
 int nfn_get_option(const char* name);
