@@ -35,6 +35,18 @@ def test_library_exports_every_declared_symbol(nfn_lib):
     assert nfn_lib.nfn_version() == 100
 
 
+def test_integration_doc_indexes_every_declared_symbol():
+    """INTEGRATION.md names every entry point of the header (and nothing the header does not declare)."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    names = declared_functions()
+    missing = [n for n in names if "`%s`" % n not in text]
+    assert not missing, missing
+    index = text[text.index("## Every exported symbol"):text.index("## Error and threading contract")]
+    listed = set(re.findall(r"`(nfn_[a-z0-9_]+)`", index))
+    assert listed == set(names), (sorted(listed - set(names)), sorted(set(names) - listed))
+    assert "(%d;" % len(names) in index
+
+
 def test_struct_layout_matches_header():
     from normalizingflownetwork_b200 import _lib
 
