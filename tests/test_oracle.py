@@ -215,3 +215,67 @@ def test_estimator_level_terms():
     np.testing.assert_allclose(yn.numpy(), [[0.25, 1.0]])
     lp = torch.tensor([-1.5], dtype=torch.float64)
     assert float(fo.nll(lp, y_std)[0]) == pytest.approx(1.5 + np.log(6.0))
+
+
+# ----------------------------------------------------------------------------- first-principles pin
+def _np_logp(t_row, y, ft, d, tb):
+    out = an.chain_forward_backward(np.repeat(t_row, y.shape[0], 0), y, ft, d, tb, need_grad=False)
+    return out[0] if isinstance(out, tuple) else out
+
+
+@pytest.mark.parametrize("ft", [["radial"] * 3, ["radial"] * 5, ["planar"] * 4, ["planar", "radial", "affine"],
+                                ["affine", "radial", "planar", "radial"]], ids=lambda f: "".join(x[0] for x in f))
+@pytest.mark.parametrize("tb", [True, False])
+def test_oracle_density_is_normalised_1d(ft, tb):
+    """Independent of TFP, the shim and torch.distributions: whatever `TransformedDistribution(base,
+    Invert(Chain(flows)))` means, it is a probability density in y, so exp(log_prob) must integrate to 1 for ANY
+    parameter row.  A misread direction of the chain or sign of a log-det-Jacobian fails this at once (the reading
+    restated in SURVEY.md App. A.1 and in both oracles is: log p(y) = base.log_prob(f(y)) + sum fldj_k, y passing
+    through flow_types[0] first).  1-D events, trapezoid rule on a grid that covers the mass."""
+    y = np.linspace(-60.0, 60.0, 240001)[:, None]
+    for seed in range(3):
+        P = an_param_size(ft, 1, tb)
+        t = np.random.default_rng(seed).normal(0.0, 0.5, (1, P))
+        lp = _np_logp(t, y, ft, 1, tb)
+        assert abs(np.trapezoid(np.exp(lp), y[:, 0]) - 1.0) <= 1e-6, (ft, tb, seed)
+        # the literal (torch float64) restatement gives the same density on a coarser slice
+        ys = y[::400]
+        lp_t = fo.chain_log_prob(torch.tensor(np.repeat(t, ys.shape[0], 0)), torch.tensor(ys), ft, 1, tb).numpy()
+        assert np.max(np.abs(lp_t - lp[::400])) <= 1e-10
+
+
+def an_param_size(ft, d, tb):
+    return (2 * d if tb else 0) + sum(an.SIZES[f](d) for f in ft)
+
+
+@pytest.mark.parametrize("ft,seeds", [(["planar", "radial", "affine"] * 3 + ["planar"], (0, 2)),   # BASELINE config 2
+                                      (["radial", "planar"] * 2, (0, 1)), (["radial"] * 3, (0,))],
+                         ids=["cfg2", "rprp", "rrr"])
+def test_oracle_density_is_normalised_2d(ft, seeds):
+    """The same in two dimensions, where the reference's radial flow uses an L1 radius and a tape-derived
+    log-det (RadialFlow.py:51-70): the restated closed form still is the log-det of the map it applies."""
+    g = np.linspace(-30.0, 30.0, 1201)
+    Y = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)
+    for seed in seeds:
+        t = np.random.default_rng(seed).normal(0.0, 0.3, (1, an_param_size(ft, 2, True)))
+        p = np.exp(_np_logp(t, Y, ft, 2, True)).reshape(g.size, g.size)
+        total = np.trapezoid(np.trapezoid(p, g, axis=1), g)
+        assert abs(total - 1.0) <= 1e-4, (ft, seed, total)
+
+
+def test_mixture_heads_are_normalised_1d():
+    """MDN (Mixture of MVNDiag, DistributionLayers.py:196-212) and KMN (MixtureSameFamily over fixed centres,
+    :118-133; negative bandwidths are legal) as restated: densities in y."""
+    y = np.linspace(-60.0, 60.0, 120001)[:, None]
+    rng = np.random.default_rng(4)
+    K = 5
+    t = rng.normal(0.0, 0.7, (1, 3 * K))
+    lp = an.mdn_forward_backward(np.repeat(t, y.shape[0], 0), y, K, 1, need_grad=False)
+    lp = lp[0] if isinstance(lp, tuple) else lp
+    assert abs(np.trapezoid(np.exp(lp), y[:, 0]) - 1.0) <= 1e-6
+    M = 12
+    locs, scales = rng.normal(0.0, 2.0, (M, 1)), rng.normal(0.0, 0.6, M)   # some bandwidths negative
+    assert (scales < 0).any()
+    lp = an.kmn_forward_backward(np.repeat(rng.normal(0.0, 1.0, (1, M)), y.shape[0], 0), y, locs, scales, need_grad=False)
+    lp = lp[0] if isinstance(lp, tuple) else lp
+    assert abs(np.trapezoid(np.exp(lp), y[:, 0]) - 1.0) <= 1e-6
