@@ -64,3 +64,21 @@ def test_mixture_heads_integrate_to_one(cuda_device, nfn_lib):
     logits = torch.tensor(rng.normal(0.0, 1.0, (1, M)).astype(np.float32), device=cuda_device)
     lp = F.kmn_forward(logits.expand(n, M).contiguous(), yg, locs, scales)
     assert abs(float(_integral(torch.exp(lp.double()).unsqueeze(1), yg[:, 0])) - 1.0) <= 1e-4
+
+
+def test_config2_chain_density_integrates_to_one_2d(cuda_device, nfn_lib):
+    """BASELINE config 2's chain (10 flows, 2-D events): the headline kernel's density over a 1201 x 1201 grid,
+    one launch of the density-grid entry point per parameter row pair (same rows as the CPU twin in test_oracle.py)."""
+    from normalizingflownetwork_b200 import functional as F
+
+    ft, d, tb = ["planar", "radial", "affine"] * 3 + ["planar"], 2, True
+    P = F.chain_param_size(ft, d, tb)
+    t = np.concatenate([np.random.default_rng(seed).normal(0.0, 0.3, (1, P)) for seed in (0, 2)]).astype(np.float32)
+    g = torch.linspace(-30.0, 30.0, 1201, device=cuda_device, dtype=torch.float64).float()
+    Y = torch.stack(torch.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2).contiguous()
+    lp = F.chain_forward_grid(torch.tensor(t, device=cuda_device), Y, ft, d, tb)      # [1201 * 1201, 2]
+    p = torch.exp(lp.double()).reshape(g.numel(), g.numel(), 2)
+    h = (g[1:] - g[:-1]).double()
+    inner = (0.5 * (p[:, 1:] + p[:, :-1]) * h[None, :, None]).sum(1)                   # over the second coordinate
+    total = (0.5 * (inner[1:] + inner[:-1]) * h[:, None]).sum(0)
+    assert float((total - 1.0).abs().max()) <= 1e-3, total.tolist()
