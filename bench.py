@@ -73,6 +73,52 @@ def param_size(flow_types, d, tb):
     return sum(sz[f] for f in flow_types) + (2 * d if tb else 0)
 
 
+def arm_config(cfg, world, K, B, P, d, bwd, specialized, want_col, packed, use_peer, peer_blocking, extra_warmup):
+    """`config` of the JSON line: the workload and how the GPU arm runs it.  Both arms print THIS dict for the same
+    command line (the reference arm times a bounded sample of the same workload on the host cores and says which in
+    `cpu_baseline.sample`), so that the two lines of a round compare like with like."""
+    bytes_per_row = 4 * ((2 * P if bwd else P) + d + 1)
+    exchange = ""
+    if packed:
+        exchange = "; [dt column sums (P) | sum logp] summed over ranks every step, " + (
+            ("fused into the kernel over NVLink peer memory, split-phase (one CTA of step i+1's grid pushes step i's "
+             "totals, collects the peers' and writes the sums; the last step's by a flush inside the timed region)"
+             if not peer_blocking else
+             "fused into the kernel's last CTA over NVLink peer memory (push + wait)") if use_peer else
+            "one NCCL all-reduce")
+    return {
+        "workload": WORKLOAD_NAMES[cfg], "rows_per_gpu": B, "param_width": P, "n_dims": d,
+        "fwd_bwd": bwd, "specialized_kernel": specialized,
+        "math": "accurate" if os.environ.get("NFN_B200_MATH") == "accurate" else "fast",
+        "dt_column_sums_in_kernel": want_col,
+        "l2": "inputs+outputs per step (%d MB) exceed the 126 MB L2; no flush needed" % (bytes_per_row * B // (1 << 20)),
+        "parallelism": "dp%d (rows sharded, no data-path collective%s)" % (world, exchange),
+        "t_sigma": 0.5, "seed": 22, "extra_untimed_warmup_steps": extra_warmup,
+        "timing": "one CUDA-event pair around the %d steps, no per-launch probes" % K + (
+            "; after barrier + synchronize the ranks' streams are lined up by one tiny all-reduce queued directly "
+            "before the start event" if world > 1 else ""),
+    }
+
+
+def static_arm_config(args):
+    """The same dict without a GPU or the library (the reference arm): every entry follows from the command line and
+    the build's list of ahead-of-time chains; the exchange is the default the GPU arm selects for this world size."""
+    from normalizingflownetwork_b200 import build as nfn_build   # pure Python: the list of specialised chains
+
+    cfg = args.config
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ft, d, tb, rows, bwd = CONFIGS[cfg]
+    mdn = is_mdn(ft)
+    bwd = bool(bwd and not args.fwd_only)
+    specialized = True if mdn else any(
+        (d, bool(tb), list(ft)) == (sd, bool(sb), list(sf)) for sd, sb, sf in nfn_build.SPECIALIZED_CHAINS)
+    packed = bool((world > 1 or args.force_peer) and bwd)
+    use_peer = bool(packed and args.exchange == "peer" and not mdn)
+    return arm_config(cfg, world, args.steps, int(args.rows or rows), param_size(ft, d, tb), d, bwd, specialized,
+                      bool(bwd and not args.no_colsum and not mdn), packed, use_peer, args.peer_blocking,
+                      max(0, 600 - args.warmup) if world > 1 else 0)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -284,10 +330,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAMES[cfg], "rows_per_step": rows,
-                   "note": "bounded sample of the workload per step; host cores only"},
+        # the GPU arm's `config` for the same command line (what this run samples); the sample itself is below
+        "config": static_arm_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d rows per step; fp32 torch-CPU op-for-op restatement of the reference's TF "
+                         "sample": "%d rows per step (a bounded sample of the workload in `config`, host cores only); "
+                                   "fp32 torch-CPU op-for-op restatement of the reference's TF "
                                    "graph + autograd (TensorFlow/TFP not installable in this image)" % rows},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -784,25 +831,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {
-            "workload": WORKLOAD_NAMES[cfg], "rows_per_gpu": B, "param_width": P, "n_dims": d,
-            "fwd_bwd": bwd, "specialized_kernel": specialized, "math": "accurate" if os.environ.get(
-                "NFN_B200_MATH") == "accurate" else "fast",
-            "dt_column_sums_in_kernel": want_col,
-            "l2": "inputs+outputs per step (%d MB) exceed the 126 MB L2; no flush needed" % (
-                bytes_per_row * B // (1 << 20)),
-            "parallelism": "dp%d (rows sharded, no data-path collective%s)" % (
-                world, ("; [dt column sums (P) | sum logp] summed over ranks every step, " + (
-                    ("fused into the kernel over NVLink peer memory, split-phase (step i+1 sends step i's totals from its "
-                     "head and collects the sums at its tail; the last step's by a flush inside the timed region)"
-                     if not args.peer_blocking else
-                     "fused into the kernel's last CTA over NVLink peer memory (push + wait)") if use_peer else
-                    "one NCCL all-reduce")) if packed else ""),
-            "t_sigma": 0.5, "seed": 22, "extra_untimed_warmup_steps": extra_warmup,
-            "timing": "one CUDA-event pair around the %d steps, no per-launch probes" % K + (
-                "; after barrier + synchronize the ranks' streams are lined up by one tiny all-reduce queued directly "
-                "before the start event" if world > 1 else ""),
-        },
+        "config": arm_config(cfg, world, K, B, P, d, bwd, specialized, want_col, packed, use_peer, args.peer_blocking,
+                             extra_warmup),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": ("nfn_mdn_forward_backward_host" if mdn else
                         "nfn_chain_forward_backward_host" if bwd else "nfn_chain_forward_host"),

@@ -79,3 +79,20 @@ def test_near_gpu_cpus_is_best_effort_and_restores_affinity():
 
     if not torch.cuda.is_available():
         assert near.note.startswith("unchanged")  # no NVML device here: nothing is touched
+
+
+def test_both_arms_print_the_same_config():
+    """The reference arm times a bounded sample of the GPU arm's workload and must say so on the SAME `config`
+    (the driver compares the two lines): its config equals the one a B200 run of the GPU arm recorded for the same
+    command line (profiles/r02_bench_n1_builder.json, `--gpus 1 --steps 20 --warmup 5`)."""
+    with open(os.path.join(ROOT, "profiles", "r02_bench_n1_builder.json")) as f:
+        gpu = json.load(f)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps",
+                        str(gpu["steps"]), "--warmup", str(gpu["warmup"])], cwd=ROOT, capture_output=True, text=True,
+                       timeout=600, env=dict(os.environ, RANK="0", WORLD_SIZE="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert ref["config"] == gpu["config"]
+    assert ref["metric"] == gpu["metric"] and ref["unit"] == gpu["unit"]
+    assert ref["higher_is_better"] == gpu["higher_is_better"] and ref["dtype"] == gpu["dtype"]
+    assert "bounded sample" in ref["cpu_baseline"]["sample"]
