@@ -101,17 +101,16 @@ def arm_config(cfg, world, K, B, P, d, bwd, specialized, want_col, packed, use_p
 
 
 def static_arm_config(args):
-    """The same dict without a GPU or the library (the reference arm): every entry follows from the command line and
-    the build's list of ahead-of-time chains; the exchange is the default the GPU arm selects for this world size."""
-    from normalizingflownetwork_b200 import build as nfn_build   # pure Python: the list of specialised chains
-
+    """The same dict without a GPU, the library or the package (the reference arm): every entry follows from the
+    command line; the exchange is the default the GPU arm selects for this world size."""
     cfg = args.config
     world = int(os.environ.get("WORLD_SIZE", "1"))
     ft, d, tb, rows, bwd = CONFIGS[cfg]
     mdn = is_mdn(ft)
     bwd = bool(bwd and not args.fwd_only)
-    specialized = True if mdn else any(
-        (d, bool(tb), list(ft)) == (sd, bool(sb), list(sf)) for sd, sb, sf in nfn_build.SPECIALIZED_CHAINS)
+    # every chain in CONFIGS has an ahead-of-time kernel instance (build.py:SPECIALIZED_CHAINS; pinned by
+    # tests/test_bench_contract.py) -- stated here so that this arm imports nothing of the product
+    specialized = True
     packed = bool((world > 1 or args.force_peer) and bwd)
     use_peer = bool(packed and args.exchange == "peer" and not mdn)
     return arm_config(cfg, world, args.steps, int(args.rows or rows), param_size(ft, d, tb), d, bwd, specialized,

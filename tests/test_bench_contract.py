@@ -96,3 +96,17 @@ def test_both_arms_print_the_same_config():
     assert ref["metric"] == gpu["metric"] and ref["unit"] == gpu["unit"]
     assert ref["higher_is_better"] == gpu["higher_is_better"] and ref["dtype"] == gpu["dtype"]
     assert "bounded sample" in ref["cpu_baseline"]["sample"]
+
+
+def test_every_bench_chain_has_an_ahead_of_time_kernel():
+    """bench.static_arm_config states `specialized_kernel: true` without loading the library: keep that true."""
+    sys.path.insert(0, ROOT)
+    try:
+        import bench
+        from normalizingflownetwork_b200 import build as nfn_build
+    finally:
+        sys.path.remove(ROOT)
+    built = {(d, bool(b), tuple(f)) for d, b, f in nfn_build.SPECIALIZED_CHAINS}
+    for name, (ft, d, tb, _, _) in bench.CONFIGS.items():
+        if not bench.is_mdn(ft):
+            assert (d, bool(tb), tuple(ft)) in built, name
