@@ -91,7 +91,9 @@ def arm_config(cfg, world, K, B, P, d, bwd, specialized, want_col, packed, use_p
         "fwd_bwd": bwd, "specialized_kernel": specialized,
         "math": "accurate" if os.environ.get("NFN_B200_MATH") == "accurate" else "fast",
         "dt_column_sums_in_kernel": want_col,
-        "l2": "inputs+outputs per step (%d MB) exceed the 126 MB L2; no flush needed" % (bytes_per_row * B // (1 << 20)),
+        "l2": ("inputs+outputs per step (%d MB) exceed the 126 MB L2; no flush needed" if bytes_per_row * B > (126 << 20) else
+               "inputs+outputs per step (%d MB) FIT the 126 MB L2 and are not flushed: a debug / latency-bound row count, "
+               "not a roofline claim") % (bytes_per_row * B // (1 << 20)),
         "parallelism": "dp%d (rows sharded, no data-path collective%s)" % (world, exchange),
         "t_sigma": 0.5, "seed": 22, "extra_untimed_warmup_steps": extra_warmup,
         "timing": "one CUDA-event pair around the %d steps, no per-launch probes" % K + (
